@@ -1,0 +1,164 @@
+"""ctypes binding of ``libbliss_b200.so`` (the C ABI in ``include/bliss_b200.h``).
+
+Only raw device pointers (``tensor.data_ptr()``), sizes, scalars and the current CUDA stream
+cross this boundary — no torch types.  The library is built in-tree by :func:`build`
+(``nvcc -gencode arch=compute_100a,code=sm_100a``); there is NO fallback: if it is missing or a
+call fails, the op raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libbliss_b200.so")
+SOURCES = ["sampler.cu", "aggregate.cu", "bandit.cu", "gat.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+MODE_BANDIT, MODE_LADIES, MODE_UNIFORM = 0, 1, 2
+AGG_SUM, AGG_MEAN = 0, 1
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [os.path.join(_ROOT, "include", "bliss_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into ``libbliss_b200.so`` (in-tree)."""
+    if not force and not _stale():
+        return LIB_PATH
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(_CSRC, src.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(_CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out.decode(), file=sys.stderr)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out.decode()}")
+    cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if out.returncode != 0:
+        raise RuntimeError(f"link failed:\n{out.stdout.decode()}")
+    return LIB_PATH
+
+
+# ---- C structs (mirror include/bliss_b200.h) ---------------------------------------------
+class Graph(C.Structure):
+    _fields_ = [("num_nodes", C.c_int64), ("num_edges", C.c_int64), ("indptr", C.c_void_p),
+                ("indices", C.c_void_p), ("eid", C.c_void_p)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("n_seeds", C.c_int32), ("n_cand", C.c_int32), ("n_sel", C.c_int32), ("n_src", C.c_int32),
+                ("n_heavy", C.c_int32), ("n_light", C.c_int32), ("take_all", C.c_int32), ("iters", C.c_int32),
+                ("e_in", C.c_int64), ("n_edges", C.c_int64), ("c", C.c_double), ("s_last", C.c_double),
+                ("queue", C.c_int32 * 4), ("error", C.c_int32), ("pad", C.c_int32)]
+
+
+class Workspace(C.Structure):
+    _fields_ = [("acc", C.c_void_p), ("first_pos", C.c_void_p), ("node_info", C.c_void_p),
+                ("sel_bits", C.c_void_p), ("cand", C.c_void_p), ("p_cand", C.c_void_p), ("sel", C.c_void_p),
+                ("row_list", C.c_void_p), ("row_w", C.c_void_p), ("row_q", C.c_void_p),
+                ("row_cnt", C.c_void_p), ("row_t", C.c_void_p), ("cap_seeds", C.c_int64),
+                ("cap_sel", C.c_int64), ("ctr", C.c_void_p)]
+
+
+class BlockOut(C.Structure):
+    _fields_ = [("indptr", C.c_void_p), ("edge_src", C.c_void_p), ("edge_dst", C.c_void_p),
+                ("csc_pos", C.c_void_p), ("eid", C.c_void_p), ("q_ij", C.c_void_p), ("edge_w", C.c_void_p),
+                ("src_nid", C.c_void_p), ("node_prob", C.c_void_p), ("out_deg", C.c_void_p),
+                ("cap_edges", C.c_int64), ("cap_src", C.c_int64)]
+
+
+_P, _I32, _I64, _U32, _U64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_double
+_GP, _WP, _BP = C.POINTER(Graph), C.POINTER(Workspace), C.POINTER(BlockOut)
+
+#: every symbol ``include/bliss_b200.h`` declares, with its argument types
+PROTOTYPES = {
+    "bliss_version": [],
+    "bliss_workspace_init": [_WP, _I64, _P],
+    "bliss_frontier_plan": [_GP, _P, _I32, _WP, _P],
+    "bliss_frontier_prob": [_GP, _P, _I32, _P, _F, _I32, _WP, _P],
+    "bliss_poisson_scale": [_I32, _I32, _D, _I32, _WP, _P],
+    "bliss_select_poisson": [_I32, _U64, _U64, _U32, _P, _WP, _P],
+    "bliss_select_topk": [_I32, _I32, _U64, _U64, _U32, _P, _P, _WP, _P],
+    "bliss_philox_fill": [_U64, _U64, _U32, _P, _I64, _P, _P],
+    "bliss_block_count": [_GP, _P, _I32, _WP, _P],
+    "bliss_block_index": [_P, _I32, _WP, _BP, _P],
+    "bliss_block_fill": [_GP, _P, _I32, _P, _F, _I32, _WP, _BP, _P],
+    "bliss_block_finish": [_I32, _I32, _WP, _BP, _P],
+    "bliss_block_transpose": [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P],
+    "bliss_gather_rows": [_P, _P, _I64, _I32, _P, _P, _P],
+    "bliss_row_norm": [_P, _I64, _I32, _P, _P],
+    "bliss_spmm": [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P],
+    "bliss_gatv2_fwd": [_P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "bliss_gatv2_bwd_dst": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P],
+    "bliss_gatv2_bwd_src": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _P],
+    "bliss_gat_alpha_sums": [_P, _P, _P, _I32, _P, _P, _P],
+    "bliss_reward_update": [_GP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _I32, _I64,
+                            _P, _P, _P, _P, _P],
+    "bliss_apply_updates": [_P, _P, _I64, _P, _P, _P],
+    "bliss_l1_norm": [_P, _I64, _P, _P, _P],
+    "bliss_scale_by_inv": [_P, _I64, _P, _D, _P],
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / PyTorch fallback for the BLISS hot path)")
+        _lib = C.CDLL(LIB_PATH)
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+    return _lib
+
+
+class BlissNativeError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        kind = "bad argument" if rc < 0 else "cudaError"
+        raise BlissNativeError(f"{what} failed: {kind} {rc}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

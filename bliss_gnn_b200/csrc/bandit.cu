@@ -1,0 +1,263 @@
+// bandit.cu — EXP3 reward / weight update of the BLISS hot path on sm_100a.
+// Replaces calculate_alpha / calculate_rewards / update_exp3_weights (bandit_sampler.py:140-249):
+// five g-SDDMM launches, two scalar g-SpMMs, an index_put and a dense F.normalize over |E| per
+// layer per step in the reference become one pass over the block's edges that reads every
+// operand once and read-modify-writes the CSC-ordered weight in place.
+#include <float.h>
+#include "common.cuh"
+
+namespace bliss {
+
+__device__ __forceinline__ float nan_to_num_default(float x) {  // torch.nan_to_num(x)
+  if (isnan(x)) return 0.0f;
+  if (isinf(x)) return x > 0 ? FLT_MAX : -FLT_MAX;
+  return x;
+}
+__device__ __forceinline__ float nan_to_num_posinf0(float x) {  // torch.nan_to_num(x, posinf=0)
+  if (isnan(x)) return 0.0f;
+  if (isinf(x)) return x > 0 ? 0.0f : -FLT_MAX;
+  return x;
+}
+
+// GAT alpha (bandit_sampler.py:148-154) needs Σ a_ij and Σ q_ij per destination: warp per row,
+// fp64 accumulation rounded once (numeric contract).
+__global__ void __launch_bounds__(256) k_row_sums2(const int32_t* __restrict__ indptr, const float* __restrict__ a,
+                                                  const float* __restrict__ q, int n_rows,
+                                                  float* __restrict__ asum, float* __restrict__ qsum) {
+  const int lane = lane_id();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < n_rows; r += nwarps) {
+    double sa = 0.0, sq = 0.0;
+    for (int e = indptr[r] + lane; e < indptr[r + 1]; e += 32) {
+      sa += (double)a[e];
+      sq += (double)q[e];
+    }
+    sa = warp_sum(sa);
+    sq = warp_sum(sq);
+    if (lane == 0) {
+      asum[r] = __double2float_rn(sa);
+      qsum[r] = __double2float_rn(sq);
+    }
+  }
+}
+
+struct RewardArgs {
+  const int64_t* __restrict__ g_indptr;
+  const int32_t* __restrict__ blk_indptr;
+  const int32_t* __restrict__ edge_src;
+  const int32_t* __restrict__ edge_dst;
+  const int64_t* __restrict__ csc_pos;
+  const int32_t* __restrict__ dst_nid;
+  const float* __restrict__ q_ij;
+  const float* __restrict__ node_prob;
+  const float* __restrict__ embed_norm;
+  const float* __restrict__ w_static;
+  const float* __restrict__ a_ij;
+  const float* __restrict__ asum;
+  const float* __restrict__ qsum;
+  int alpha_mode;
+  float delta;
+  int64_t n_edges;
+  float* exp3_w;
+  float* rewards;
+  float* x_out;
+  double* l1_delta;
+};
+
+__global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
+  __shared__ double s_red[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double dsum = 0.0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < p.n_edges; e += stride) {
+    const int i = p.edge_dst[e];
+    const int u = p.edge_src[e];
+    const int64_t pos = p.csc_pos[e];
+    const float q = p.q_ij[e];
+    float alpha;
+    if (p.alpha_mode == 0) {
+      alpha = __ldg(p.w_static + pos);                                           // :157
+    } else {
+      float ad = nan_to_num_default(__fdiv_rn(p.a_ij[e], p.asum[i]));            // :152-153
+      alpha = __fmul_rn(ad, p.qsum[i]);                                          // :154
+    }
+    const float k_i = (float)(p.blk_indptr[i + 1] - p.blk_indptr[i]);            // :180
+    const float a_k = nan_to_num_posinf0(__fdiv_rn(__fmul_rn(alpha, alpha), k_i));   // :186-187
+    const float h = p.embed_norm[u];
+    const float hq = __fdiv_rn(__fmul_rn(h, h), __fmul_rn(q, q));                // :189
+    const float r = __fmul_rn(a_k, hq);                                          // :191
+    if (p.rewards) p.rewards[e] = r;
+    const int dn = p.dst_nid[i];
+    const float n_i = (float)(p.g_indptr[dn + 1] - p.g_indptr[dn]);              // :223
+    const float r_hat = __fdiv_rn(r, p.node_prob[u]);                            // :240
+    float x = __fmul_rn(r_hat, __fdiv_rn(p.delta, n_i));                         // :242
+    if (x > 1.0f) x = 1.0f;                                                      // :244
+    if (p.x_out) p.x_out[e] = x;
+    if (p.exp3_w) {
+      const float w_old = p.exp3_w[pos];
+      const float w_new = __fmul_rn(w_old, expf(x));                             // :246-248
+      p.exp3_w[pos] = w_new;
+      dsum += (double)w_new - (double)w_old;
+    }
+  }
+  if (p.l1_delta) {
+    dsum = block_sum(dsum, s_red);
+    if (threadIdx.x == 0 && dsum != 0.0) atomicAdd(p.l1_delta, dsum);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_apply_updates(const int64_t* __restrict__ pos, const float* __restrict__ x,
+                                                      int64_t n, float* exp3_w, double* l1_delta) {
+  __shared__ double s_red[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double dsum = 0.0;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += stride) {
+    // the same CSC position may be updated by several ranks: multiplicative -> atomic CAS loop
+    float* addr = exp3_w + pos[k];
+    const float f = expf(x[k]);
+    unsigned old = __float_as_uint(*addr), assumed;
+    do {
+      assumed = old;
+      old = atomicCAS(reinterpret_cast<unsigned*>(addr), assumed,
+                      __float_as_uint(__fmul_rn(__uint_as_float(assumed), f)));
+    } while (old != assumed);
+    const float w_old = __uint_as_float(old);
+    dsum += (double)__fmul_rn(w_old, f) - (double)w_old;
+  }
+  if (l1_delta) {
+    dsum = block_sum(dsum, s_red);
+    if (threadIdx.x == 0 && dsum != 0.0) atomicAdd(l1_delta, dsum);
+  }
+}
+
+// literal F.normalize(w, p=1): fixed two-level tree -> deterministic
+#define BLISS_NORM_BLOCKS 1024
+__global__ void __launch_bounds__(256) k_l1_partial(const float* __restrict__ w, int64_t n, double* __restrict__ partial) {
+  __shared__ double s_red[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  double acc = 0.0;
+  const int64_t n4 = n >> 2;
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(w);
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n4; v += stride / 4) {
+    float4 t = __ldg(w4 + v);
+    acc += ((double)fabsf(t.x) + (double)fabsf(t.y)) + ((double)fabsf(t.z) + (double)fabsf(t.w));
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t k = (n4 << 2) + threadIdx.x; k < n; k += blockDim.x) acc += (double)fabsf(w[k]);
+  }
+  acc = block_sum(acc, s_red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(1024) k_l1_final(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  __shared__ double s_red[32];
+  double acc = (threadIdx.x < n) ? partial[threadIdx.x] : 0.0;
+  acc = block_sum(acc, s_red);
+  if (threadIdx.x == 0) out[0] = acc;
+}
+__global__ void __launch_bounds__(256) k_scale_by_inv(float* __restrict__ w, int64_t n, const double* __restrict__ norm,
+                                                     double eps) {
+  // F.normalize: w / max(||w||_1, eps) with the denominator in the weights' dtype
+  const float den = (float)fmax(norm[0], eps);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  float4* __restrict__ w4 = reinterpret_cast<float4*>(w);
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n4; v += stride) {
+    float4 t = w4[v];
+    t.x = __fdiv_rn(t.x, den); t.y = __fdiv_rn(t.y, den); t.z = __fdiv_rn(t.z, den); t.w = __fdiv_rn(t.w, den);
+    w4[v] = t;
+  }
+  if (blockIdx.x == 0)
+    for (int64_t k = (n4 << 2) + threadIdx.x; k < n; k += blockDim.x) w[k] = __fdiv_rn(w[k], den);
+}
+
+}  // namespace bliss
+
+using namespace bliss;
+
+static inline int grid_for(int64_t n, int threads, int max_blocks) {
+  int64_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+extern "C" {
+
+int bliss_gat_alpha_sums(const int32_t* blk_indptr, const float* a_ij, const float* q_ij, int32_t n_dst,
+                         float* asum, float* qsum, void* stream) {
+  if (!blk_indptr || !a_ij || !q_ij || !asum || !qsum || n_dst < 0) return -1;
+  if (n_dst == 0) return 0;
+  k_row_sums2<<<grid_for((int64_t)n_dst * 32, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(
+      blk_indptr, a_ij, q_ij, n_dst, asum, qsum);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const int32_t* edge_src,
+                        const int32_t* edge_dst, const int64_t* csc_pos, const int32_t* dst_nid,
+                        const float* q_ij, const float* node_prob, const float* embed_norm,
+                        const float* w_static_csc, const float* a_ij, const float* asum, const float* qsum,
+                        int32_t alpha_mode, float delta, int32_t n_dst, int64_t n_edges, float* exp3_w_csc,
+                        float* rewards, float* x_out, double* l1_delta, void* stream) {
+  if (!g || n_edges < 0 || n_dst < 0) return -1;
+  if (n_edges == 0) return 0;
+  if (!blk_indptr || !edge_src || !edge_dst || !csc_pos || !dst_nid || !q_ij || !node_prob || !embed_norm) return -1;
+  if (alpha_mode == 0 && !w_static_csc) return -1;
+  if (alpha_mode == 1 && (!a_ij || !asum || !qsum)) return -1;
+  RewardArgs p;
+  p.g_indptr = g->indptr;
+  p.blk_indptr = blk_indptr;
+  p.edge_src = edge_src;
+  p.edge_dst = edge_dst;
+  p.csc_pos = csc_pos;
+  p.dst_nid = dst_nid;
+  p.q_ij = q_ij;
+  p.node_prob = node_prob;
+  p.embed_norm = embed_norm;
+  p.w_static = w_static_csc;
+  p.a_ij = a_ij;
+  p.asum = asum;
+  p.qsum = qsum;
+  p.alpha_mode = alpha_mode;
+  p.delta = delta;
+  p.n_edges = n_edges;
+  p.exp3_w = exp3_w_csc;
+  p.rewards = rewards;
+  p.x_out = x_out;
+  p.l1_delta = l1_delta;
+  k_reward_update<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(p);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_apply_updates(const int64_t* pos, const float* x, int64_t n, float* exp3_w_csc, double* l1_delta,
+                        void* stream) {
+  if (n < 0 || !exp3_w_csc) return -1;
+  if (n == 0) return 0;
+  if (!pos || !x) return -1;
+  k_apply_updates<<<grid_for(n, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(pos, x, n, exp3_w_csc, l1_delta);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_l1_norm(const float* w, int64_t n, double* partial, double* out, void* stream) {
+  if (!w || n < 0 || !partial || !out) return -1;
+  if ((uintptr_t)w % 16 != 0) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_l1_partial<<<BLISS_NORM_BLOCKS, 256, 0, st>>>(w, n, partial);
+  BLISS_CHECK_LAUNCH();
+  k_l1_final<<<1, 1024, 0, st>>>(partial, BLISS_NORM_BLOCKS, out);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_scale_by_inv(float* w, int64_t n, const double* norm, double eps, void* stream) {
+  if (!w || n < 0 || !norm) return -1;
+  if ((uintptr_t)w % 16 != 0) return -1;
+  if (n == 0) return 0;
+  k_scale_by_inv<<<grid_for(n / 4 + 1, 256, BLISS_SM_COUNT * 16), 256, 0, (cudaStream_t)stream>>>(w, n, norm, eps);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,996 @@
+// sampler.cu — per-layer sampling of the BLISS hot path on sm_100a:
+//   (1) layer-importance probabilities over the frontier's CSC neighbourhood,
+//   (2) Poisson scale search + Philox inclusion sampling (or top-k for the multinomial samplers),
+//   (3) block construction: filter, ordered compaction, relabelling, importance-weight
+//       normalisation.
+// Replaces bandit_sampler.py:47-138,269-425 and ladies_sampler.py:34-183 of the reference
+// (which reach DGL in_subgraph/compact_graphs/g-SpMM/g-SDDMM/to_block and torch sort/unique/
+// bernoulli).  Work distribution: the frontier's rows (in-edge lists of the seeds) are split
+// into heavy rows (one 256-thread CTA each, weights staged once in shared memory for the three
+// passes) and light rows (one warp each, values kept in registers); CTAs pull items from a
+// device-side queue, so no size ever travels to the host inside a layer.
+#include "common.cuh"
+
+namespace bliss {
+
+struct GraphView {
+  const int64_t* __restrict__ indptr;
+  const int32_t* __restrict__ indices;
+  const int32_t* __restrict__ eid;
+  int64_t num_nodes;
+};
+
+__device__ __forceinline__ int next_item(int* cursor, int n_items, int* s_item) {
+  __syncthreads();
+  if (threadIdx.x == 0) *s_item = atomicAdd(cursor, 1);
+  __syncthreads();
+  int it = *s_item;
+  return it < n_items ? it : -1;
+}
+
+// Every lane of the warp must call this (uniform control flow).
+__device__ __forceinline__ void append_candidate(bool first, int src, const bliss_workspace& ws) {
+  unsigned m = __ballot_sync(0xffffffffu, first);
+  if (m) {
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane_id() == leader) base = atomicAdd(&ws.ctr->n_cand, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (first) ws.cand[base + __popc(m & ((1u << lane_id()) - 1u))] = src;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// plan: register the seeds, split rows into heavy / light, reset the counters.  One CTA.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32_t* __restrict__ seeds,
+                                                       int n_seeds, bliss_workspace ws) {
+  __shared__ int s_scan[40];
+  __shared__ unsigned long long s_e[32];
+  bliss_counters* ctr = ws.ctr;
+  int heavy_base = 0, light_base = 0;
+  unsigned long long e_in = 0;
+  for (int base = 0; base < n_seeds; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    bool valid = i < n_seeds;
+    int s = 0;
+    long long d = 0;
+    if (valid) {
+      s = seeds[i];
+      d = g.indptr[s + 1] - g.indptr[s];
+      e_in += (unsigned long long)d;
+      ws.acc[s] = BLISS_REG_BIT;
+      ws.cand[i] = s;
+      ws.node_info[2 * s] = i;
+      ws.node_info[2 * s + 1] = __float_as_int(1.0f);
+      atomicOr(&ws.sel_bits[s >> 5], 1u << (s & 31));
+    }
+    int is_heavy = valid && d > BLISS_LIGHT_MAX;
+    int is_light = valid && !is_heavy;
+    int th, tl;
+    int ph = block_excl_scan(is_heavy, s_scan, &th);
+    int pl = block_excl_scan(is_light, s_scan, &tl);
+    if (is_heavy) ws.row_list[heavy_base + ph] = i;
+    if (is_light) ws.row_list[n_seeds - 1 - (light_base + pl)] = i;
+    heavy_base += th;
+    light_base += tl;
+  }
+  e_in = block_sum(e_in, s_e);
+  if (threadIdx.x == 0) {
+    ctr->n_seeds = n_seeds;
+    ctr->n_cand = n_seeds;
+    ctr->n_sel = 0;
+    ctr->n_src = n_seeds;
+    ctr->n_heavy = heavy_base;
+    ctr->n_light = light_base;
+    ctr->take_all = 0;
+    ctr->iters = 0;
+    ctr->e_in = (int64_t)e_in;
+    ctr->n_edges = 0;
+    ctr->c = 1.0;
+    ctr->s_last = 0.0;
+    ctr->queue[0] = ctr->queue[1] = ctr->queue[2] = ctr->queue[3] = 0;
+    ctr->error = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// (1) frontier probabilities.
+//   BANDIT: W_i = Σ_j w_ij ; q_ij = η/n_i + (1-η) w_ij/W_i ; Q_i = Σ_j q_ij ;
+//           acc[src] += fx((q_ij/Q_i)^2)                          bandit_sampler.py:129-137,67-73
+//   LADIES: acc[src] += fx(w_ij^2)                                ladies_sampler.py:46-47
+//   UNIFORM: acc[src] |= fx(1)                                    bandit_sampler.py:79-81
+// The first thread to touch acc[src] (old == 0) appends src to the candidate list.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scatter_term(bool uniform, float t, int src, double fx_scale,
+                                             const bliss_workspace& ws, bool valid) {
+  bool first = false;
+  if (valid) {
+    unsigned long long old;
+    if (uniform)
+      old = atomicOr((unsigned long long*)&ws.acc[src], (unsigned long long)fx_scale);
+    else
+      old = atomicAdd((unsigned long long*)&ws.acc[src], fx_term(t, fx_scale));
+    first = (old == 0ull);
+  }
+  append_candidate(first, src, ws);
+}
+
+__global__ void __launch_bounds__(BLISS_CTA) k_frontier_prob(GraphView g, const int32_t* __restrict__ seeds,
+                                                            const float* __restrict__ W, float eta,
+                                                            float one_minus_eta, int mode_flags,
+                                                            bliss_workspace ws, double fx_scale) {
+  const int mode = mode_flags & 1;                         // BANDIT / LADIES arithmetic
+  const bool uniform = (mode_flags & BLISS_MODE_UNIFORM);  // importance_sampling = 0
+  extern __shared__ float s_row[];  // BLISS_STAGE_CAP floats
+  __shared__ double s_red[32];
+  __shared__ int s_item;
+  bliss_counters* ctr = ws.ctr;
+  const int n_seeds = ctr->n_seeds, n_heavy = ctr->n_heavy, n_light = ctr->n_light;
+  const int n_items = n_heavy + (n_light + BLISS_WARPS - 1) / BLISS_WARPS;
+  const int tid = threadIdx.x;
+
+  for (;;) {
+    int item = next_item(&ctr->queue[0], n_items, &s_item);
+    if (item < 0) break;
+    if (item < n_heavy) {
+      // ---------------- heavy row: whole CTA ----------------
+      const int row = ws.row_list[item];
+      const int s = seeds[row];
+      const int64_t a = g.indptr[s];
+      const int d = (int)(g.indptr[s + 1] - a);
+      const int32_t* __restrict__ idx = g.indices + a;
+      const float* __restrict__ wr = W + a;
+      const int d_pad = (d + BLISS_CTA - 1) / BLISS_CTA * BLISS_CTA;
+      float row_q = 1.0f, row_w = 1.0f, eta_n = 0.0f;
+      if (mode == BLISS_MODE_BANDIT) {
+        // pass A: stream the weights once from HBM (128-bit loads), stage them, row sum in fp64
+        double acc = 0.0;
+        const int head = min(d, (int)(((16 - ((uintptr_t)wr & 15)) & 15) >> 2));
+        if (tid < head) {
+          float w = __ldg(wr + tid);
+          s_row[tid] = w;  // head < 4 <= STAGE_CAP
+          acc += (double)w;
+        }
+        const int nvec = (d - head) >> 2;
+        const float4* __restrict__ wv = reinterpret_cast<const float4*>(wr + head);
+#pragma unroll 4
+        for (int v = tid; v < nvec; v += BLISS_CTA) {
+          float4 w4 = __ldg(wv + v);
+          int k = head + 4 * v;
+          if (k + 3 < BLISS_STAGE_CAP) {
+            s_row[k] = w4.x; s_row[k + 1] = w4.y; s_row[k + 2] = w4.z; s_row[k + 3] = w4.w;
+          } else {
+            if (k < BLISS_STAGE_CAP) s_row[k] = w4.x;
+            if (k + 1 < BLISS_STAGE_CAP) s_row[k + 1] = w4.y;
+            if (k + 2 < BLISS_STAGE_CAP) s_row[k + 2] = w4.z;
+          }
+          acc += ((double)w4.x + (double)w4.y) + ((double)w4.z + (double)w4.w);
+        }
+        const int tail0 = head + 4 * nvec;
+        if (tail0 + tid < d) {
+          float w = __ldg(wr + tail0 + tid);
+          if (tail0 + tid < BLISS_STAGE_CAP) s_row[tail0 + tid] = w;
+          acc += (double)w;
+        }
+        // warm L2 with this row's source ids for pass C
+        for (int l = tid; l * 32 < d; l += BLISS_CTA)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(idx + l * 32));
+        row_w = __double2float_rn(block_sum(acc, s_red));
+        eta_n = __fdiv_rn(eta, (float)d);
+        // pass B: q_ij, row sum of q
+        double accq = 0.0;
+        for (int k = tid; k < d; k += BLISS_CTA) {
+          float w = (k < BLISS_STAGE_CAP) ? s_row[k] : __ldg(wr + k);
+          float q = edge_q(w, row_w, eta_n, one_minus_eta);
+          if (k < BLISS_STAGE_CAP) s_row[k] = q;
+          accq += (double)q;
+        }
+        row_q = __double2float_rn(block_sum(accq, s_red));
+        if (tid == 0) {
+          ws.row_w[row] = row_w;
+          ws.row_q[row] = row_q;
+        }
+      }
+      // pass C: scatter the squared normalised edge probabilities to the column accumulator
+      for (int k = tid; k < d_pad; k += BLISS_CTA) {
+        bool valid = k < d;
+        int src = 0;
+        float t = 0.0f;
+        if (valid) {
+          src = __ldg(idx + k);
+          if (uniform) {
+          } else if (mode == BLISS_MODE_BANDIT) {
+            float q = (k < BLISS_STAGE_CAP) ? s_row[k] : edge_q(__ldg(wr + k), row_w, eta_n, one_minus_eta);
+            float r = __fdiv_rn(q, row_q);
+            t = __fmul_rn(r, r);
+          } else {
+            float w = __ldg(wr + k);
+            t = __fmul_rn(w, w);
+          }
+        }
+        scatter_term(uniform, t, src, fx_scale, ws, valid);
+      }
+    } else {
+      // ---------------- light rows: one warp per row, values in registers ----------------
+      const int li = (item - n_heavy) * BLISS_WARPS + warp_id();
+      if (li < n_light) {
+        const int lane = lane_id();
+        const int row = ws.row_list[n_seeds - 1 - li];
+        const int s = seeds[row];
+        const int64_t a = g.indptr[s];
+        const int d = (int)(g.indptr[s + 1] - a);
+        const int32_t* __restrict__ idx = g.indices + a;
+        constexpr int R = BLISS_LIGHT_MAX / 32;
+        float v[R];
+        int src[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          int k = lane + 32 * r;
+          src[r] = (k < d) ? __ldg(idx + k) : 0;
+          v[r] = (k < d) ? __ldg(W + a + k) : 0.0f;
+        }
+        float row_q = 1.0f;
+        if (mode == BLISS_MODE_BANDIT) {
+          double acc = 0.0;
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc += (double)v[r];
+          float row_w = __double2float_rn(warp_sum(acc));
+          float eta_n = __fdiv_rn(eta, (float)d);
+          double accq = 0.0;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            int k = lane + 32 * r;
+            v[r] = (k < d) ? edge_q(v[r], row_w, eta_n, one_minus_eta) : 0.0f;
+            accq += (double)v[r];
+          }
+          row_q = __double2float_rn(warp_sum(accq));
+          if (lane == 0) {
+            ws.row_w[row] = row_w;
+            ws.row_q[row] = row_q;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (32 * r < d) {  // warp-uniform
+            int k = lane + 32 * r;
+            float t = 0.0f;
+            if (uniform) {
+            } else if (mode == BLISS_MODE_BANDIT) {
+              float q = __fdiv_rn(v[r], row_q);
+              t = __fmul_rn(q, q);
+            } else {
+              t = __fmul_rn(v[r], v[r]);
+            }
+            scatter_term(uniform, t, src[r], fx_scale, ws, k < d);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// (2a) candidate probabilities + Poisson scale search, on the device, no host round trips.
+//      One CTA; the candidate array is L2 resident.   bandit_sampler.py:391-401
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_poisson_scale(int n_seeds, int fanout, double eps, int poisson,
+                                                       bliss_workspace ws, double fx_inv_scale) {
+  __shared__ unsigned long long s_red[32];
+  bliss_counters* ctr = ws.ctr;
+  const int n_cand = ctr->n_cand;
+  for (int j = threadIdx.x; j < n_cand; j += blockDim.x) {
+    int nid = ws.cand[j];
+    ws.p_cand[j] = fx_to_prob(ws.acc[nid], fx_inv_scale);
+  }
+  if (!poisson) return;
+  if (n_cand <= fanout) {  // "prob.shape[0] <= num: return one"
+    if (threadIdx.x == 0) {
+      ctr->take_all = 1;
+      ctr->c = 1.0;
+    }
+    return;
+  }
+  __syncthreads();
+  double c = 1.0, S = 0.0;
+  int it = 0;
+  const double s_scale = (double)(1ull << BLISS_S_FIX_BITS);
+  const double s_inv = 1.0 / s_scale;
+  const double num = (double)fanout;
+  for (int i = 0; i < 50; ++i) {
+    it = i + 1;
+    const float cf = (float)c;
+    unsigned long long part = 0;
+    for (int j = threadIdx.x; j < n_cand; j += blockDim.x) {
+      float v = fminf(__fmul_rn(ws.p_cand[j], cf), 1.0f);
+      part += __double2ull_rn((double)v * s_scale);
+    }
+    unsigned long long tot = block_sum(part, s_red);
+    S = __ull2double_rn(tot) * s_inv;
+    if (fmin(S, num) / fmax(S, num) >= eps) break;
+    c *= num / S;
+  }
+  if (threadIdx.x == 0) {
+    ctr->c = c;
+    ctr->iters = it;
+    ctr->s_last = S;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// (2b) Poisson selection: u < P.   bandit_sampler.py:403-406,422-424
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void push_selected(bool sel, int nid, const bliss_workspace& ws) {
+  unsigned m = __ballot_sync(0xffffffffu, sel);
+  if (m) {
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane_id() == leader) base = atomicAdd(&ws.ctr->n_sel, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (sel) {
+      int slot = base + __popc(m & ((1u << lane_id()) - 1u));
+      if (slot < ws.cap_sel) {
+        ws.sel[slot] = nid;
+        atomicOr(&ws.sel_bits[nid >> 5], 1u << (nid & 31));
+      } else {
+        ws.ctr->error = BLISS_ERR_SEL_CAPACITY;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_select_poisson(int n_seeds, unsigned long long seed,
+                                                       unsigned long long step, unsigned layer,
+                                                       const float* __restrict__ u_inject,
+                                                       bliss_workspace ws) {
+  bliss_counters* ctr = ws.ctr;
+  const int n_cand = ctr->n_cand;
+  const float cf = (float)ctr->c;
+  const int take_all = ctr->take_all;
+  const int n_pad = (n_cand + 31) & ~31;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pad; j += gridDim.x * blockDim.x) {
+    bool sel = false;
+    int nid = 0;
+    if (j >= n_seeds && j < n_cand) {
+      nid = ws.cand[j];
+      float P = take_all ? 1.0f : fminf(__fmul_rn(ws.p_cand[j], cf), 1.0f);
+      float u = u_inject ? u_inject[nid] : philox_uniform(seed, step, layer, (unsigned)nid);
+      sel = u < P;
+      ws.node_info[2 * nid] = sel ? -2 : -1;
+      ws.node_info[2 * nid + 1] = __float_as_int(P);
+    }
+    push_selected(sel, nid, ws);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// (2c) multinomial-without-replacement selection = the k largest p / Exp(1).
+//      bandit_sampler.py:84-99, ladies_sampler.py:54-69.  Radix select over the key bits.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_topk_keys(int n_seeds, unsigned long long seed, unsigned long long step,
+                                                  unsigned layer, const float* __restrict__ u_inject,
+                                                  float* __restrict__ keys, bliss_workspace ws) {
+  const int n_cand = ws.ctr->n_cand;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_cand; j += gridDim.x * blockDim.x) {
+    int nid = ws.cand[j];
+    float u = u_inject ? u_inject[nid] : philox_uniform(seed, step, layer, (unsigned)nid);
+    float e = -log1pf(-u);
+    keys[j] = __fdiv_rn(ws.p_cand[j], e);
+    // every candidate starts unselected; seeds keep their local id (they stay block nodes)
+    ws.node_info[2 * nid + 1] = __float_as_int(ws.p_cand[j]);
+    if (j >= n_seeds) ws.node_info[2 * nid] = -1;
+  }
+}
+
+// One CTA: find the bit pattern T of the k-th largest key (keys are >= 0, so their float bits
+// order like unsigned ints) and how many keys equal to T are still needed.
+__global__ void __launch_bounds__(1024) k_topk_threshold(int fanout, const float* __restrict__ keys,
+                                                        unsigned* __restrict__ thr_out, bliss_workspace ws) {
+  __shared__ int hist[256];
+  __shared__ unsigned s_prefix;
+  __shared__ int s_need;
+  const int n_cand = ws.ctr->n_cand;
+  int k = min(fanout, n_cand);
+  if (threadIdx.x == 0) {
+    s_prefix = 0;
+    s_need = k;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    const unsigned mask_hi = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    for (int j = threadIdx.x; j < n_cand; j += blockDim.x) {
+      unsigned bits = __float_as_uint(keys[j]);
+      if ((bits & mask_hi) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int need = s_need, b = 255;
+      for (; b > 0; --b) {
+        if (hist[b] >= need) break;
+        need -= hist[b];
+      }
+      s_prefix = prefix | ((unsigned)b << shift);
+      s_need = need;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    thr_out[0] = s_prefix;        // threshold bits
+    thr_out[1] = (unsigned)s_need;  // how many keys == threshold to take (lowest slots first)
+    thr_out[2] = 0;               // tie cursor
+  }
+}
+
+// keys > T are selected; among keys == T the `need` lowest candidate slots (deterministic).
+__global__ void __launch_bounds__(1024) k_topk_mark(int n_seeds, const float* __restrict__ keys,
+                                                   unsigned* __restrict__ thr, bliss_workspace ws) {
+  // single CTA so ties are taken in slot order
+  __shared__ int s_scan[40];
+  const int n_cand = ws.ctr->n_cand;
+  const unsigned T = thr[0];
+  const int need = (int)thr[1];
+  int tie_base = 0;
+  const int n_pad = (n_cand + blockDim.x - 1) / blockDim.x * blockDim.x;
+  for (int j = threadIdx.x; j < n_pad; j += blockDim.x) {
+    bool valid = j < n_cand;
+    unsigned bits = valid ? __float_as_uint(keys[j]) : 0u;
+    int is_tie = valid && bits == T;
+    int tot;
+    int rank = block_excl_scan(is_tie, s_scan, &tot);
+    bool sel = valid && (bits > T || (is_tie && tie_base + rank < need));
+    tie_base += tot;
+    int nid = valid ? ws.cand[j] : 0;
+    if (valid && j < n_seeds) {
+      // seeds stay block nodes; an unselected seed loses its out-edges (bandit_sampler.py:295-298)
+      if (!sel) atomicAnd(&ws.sel_bits[nid >> 5], ~(1u << (nid & 31)));
+      sel = false;
+    } else if (sel) {
+      ws.node_info[2 * nid] = -2;
+    }
+    push_selected(sel, nid, ws);
+  }
+}
+
+__global__ void k_philox_fill(unsigned long long seed, unsigned long long step, unsigned layer,
+                              const int32_t* __restrict__ nids, int64_t n, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = philox_uniform(seed, step, layer, (unsigned)nids[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// (3a) count kept in-edges per seed (source selected) and record the first occurrence of every
+//      selected non-seed source: key = (row+1, position in row).   bandit_sampler.py:289-298
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void note_first(int src, unsigned long long key, const bliss_workspace& ws) {
+  if (ws.node_info[2 * src] < 0) {  // selected non-seed (-2); seeds hold their rank >= 0
+    unsigned long long cur = __ldcg((const unsigned long long*)&ws.first_pos[src]);
+    if (key < cur) atomicMin((unsigned long long*)&ws.first_pos[src], key);
+  }
+}
+
+__global__ void __launch_bounds__(BLISS_CTA) k_block_count(GraphView g, const int32_t* __restrict__ seeds,
+                                                          bliss_workspace ws) {
+  __shared__ int s_red[32];
+  __shared__ int s_item;
+  bliss_counters* ctr = ws.ctr;
+  const int n_seeds = ctr->n_seeds, n_heavy = ctr->n_heavy, n_light = ctr->n_light;
+  const int n_items = n_heavy + (n_light + BLISS_WARPS - 1) / BLISS_WARPS;
+  const int tid = threadIdx.x;
+  for (;;) {
+    int item = next_item(&ctr->queue[1], n_items, &s_item);
+    if (item < 0) break;
+    if (item < n_heavy) {
+      const int row = ws.row_list[item];
+      const int s = seeds[row];
+      const int64_t a = g.indptr[s];
+      const int d = (int)(g.indptr[s + 1] - a);
+      const int32_t* __restrict__ idx = g.indices + a;
+      const unsigned long long key_hi = (unsigned long long)(row + 1) << 32;
+      int cnt = 0;
+#pragma unroll 4
+      for (int k = tid; k < d; k += BLISS_CTA) {
+        int src = __ldg(idx + k);
+        if (test_bit(ws.sel_bits, src)) {
+          ++cnt;
+          note_first(src, key_hi | (unsigned)k, ws);
+        }
+      }
+      cnt = block_sum(cnt, s_red);
+      if (tid == 0) ws.row_cnt[row] = cnt;
+    } else {
+      const int li = (item - n_heavy) * BLISS_WARPS + warp_id();
+      if (li < n_light) {
+        const int row = ws.row_list[n_seeds - 1 - li];
+        const int s = seeds[row];
+        const int64_t a = g.indptr[s];
+        const int d = (int)(g.indptr[s + 1] - a);
+        const int32_t* __restrict__ idx = g.indices + a;
+        const unsigned long long key_hi = (unsigned long long)(row + 1) << 32;
+        int cnt = 0;
+        for (int k = lane_id(); k < d; k += 32) {
+          int src = __ldg(idx + k);
+          if (test_bit(ws.sel_bits, src)) {
+            ++cnt;
+            note_first(src, key_hi | (unsigned)k, ws);
+          }
+        }
+        cnt = warp_sum(cnt);
+        if (lane_id() == 0) ws.row_cnt[row] = cnt;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// (3b) block indptr (CTA 0) + local ids of the selected sources by first occurrence (all CTAs):
+//      src order = [seeds in seed order] ++ [selected non-seeds by first occurrence]
+//      (compact_graphs / to_block ordering).  Rank by counting over smem tiles.
+// ------------------------------------------------------------------------------------------
+#define BLISS_RANK_TILE 2048
+__global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__ seeds, int n_seeds,
+                                                    bliss_workspace ws, bliss_block_out out) {
+  __shared__ unsigned long long s_keys[BLISS_RANK_TILE];
+  __shared__ int s_scan[40];
+  bliss_counters* ctr = ws.ctr;
+  const int n_sel = min(ctr->n_sel, (int)ws.cap_sel);
+  if (blockIdx.x == 0) {
+    int base = 0;
+    for (int b = 0; b < n_seeds; b += blockDim.x) {
+      int i = b + threadIdx.x;
+      int v = (i < n_seeds) ? ws.row_cnt[i] : 0;
+      int tot;
+      int p = block_excl_scan(v, s_scan, &tot);
+      if (i < n_seeds) out.indptr[i] = base + p;
+      base += tot;
+    }
+    if (threadIdx.x == 0) {
+      out.indptr[n_seeds] = base;
+      ctr->n_edges = base;
+      ctr->n_src = n_seeds + n_sel;
+      if (base > out.cap_edges && out.cap_edges > 0) ctr->error |= BLISS_ERR_EDGE_CAPACITY;
+    }
+    for (int i = threadIdx.x; i < n_seeds; i += blockDim.x) {
+      int s = seeds[i];
+      out.src_nid[i] = s;
+      out.node_prob[i] = __int_as_float(ws.node_info[2 * s + 1]);
+      if (out.out_deg) out.out_deg[i] = 0;
+    }
+    __syncthreads();
+  }
+  const int n_chunks = (n_sel + blockDim.x - 1) / blockDim.x;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int j = chunk * blockDim.x + threadIdx.x;
+    const bool valid = j < n_sel;
+    const int nid = valid ? ws.sel[j] : 0;
+    const unsigned long long key = valid ? ws.first_pos[nid] : 0ull;
+    int rank = 0;
+    for (int t0 = 0; t0 < n_sel; t0 += BLISS_RANK_TILE) {
+      const int tn = min(BLISS_RANK_TILE, n_sel - t0);
+      __syncthreads();
+      for (int t = threadIdx.x; t < tn; t += blockDim.x) s_keys[t] = ws.first_pos[ws.sel[t0 + t]];
+      __syncthreads();
+      if (valid) {
+#pragma unroll 8
+        for (int t = 0; t < tn; ++t) rank += (s_keys[t] < key);
+      }
+    }
+    if (valid) {
+      const int local = n_seeds + rank;
+      ws.node_info[2 * nid] = local;
+      if (local < out.cap_src) {
+        out.src_nid[local] = nid;
+        out.node_prob[local] = __int_as_float(ws.node_info[2 * nid + 1]);
+        if (out.out_deg) out.out_deg[local] = 0;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// (3c) fill: ordered compaction of the kept in-edges of every seed into the block CSR with
+//      relabelled sources, q_ij, W~ = q_ij / P_src and Σ W~ per row.   bandit_sampler.py:306-316
+// ------------------------------------------------------------------------------------------
+struct FillCtx {
+  GraphView g;
+  const float* __restrict__ W;
+  float eta, one_minus_eta;
+  int mode;
+};
+
+__device__ __forceinline__ double fill_edge(const FillCtx& c, const bliss_workspace& ws,
+                                            const bliss_block_out& out, int64_t pos, int src, int row,
+                                            int slot, float row_w, float eta_n) {
+  const int2 info = *reinterpret_cast<const int2*>(&ws.node_info[2 * src]);
+  const float P = __int_as_float(info.y);
+  float base;
+  if (c.mode == BLISS_MODE_BANDIT)  // also with importance_sampling=0: q_ij is still W (:354-358)
+    base = edge_q(__ldg(c.W + pos), row_w, eta_n, c.one_minus_eta);
+  else
+    base = __ldg(c.W + pos);
+  const float wt = __fdiv_rn(base, P);
+  out.edge_src[slot] = info.x;
+  out.edge_dst[slot] = row;
+  out.csc_pos[slot] = pos;
+  if (out.eid) out.eid[slot] = c.g.eid ? c.g.eid[pos] : (int32_t)pos;
+  if (out.q_ij) out.q_ij[slot] = base;
+  out.edge_w[slot] = wt;
+  if (out.out_deg) atomicAdd(&out.out_deg[info.x], 1);
+  return (double)wt;
+}
+
+__global__ void __launch_bounds__(BLISS_CTA) k_block_fill(FillCtx c, const int32_t* __restrict__ seeds,
+                                                         bliss_workspace ws, bliss_block_out out) {
+  __shared__ double s_red[32];
+  __shared__ int s_scan[40];
+  __shared__ int s_item;
+  bliss_counters* ctr = ws.ctr;
+  const int n_seeds = ctr->n_seeds, n_heavy = ctr->n_heavy, n_light = ctr->n_light;
+  const int n_items = n_heavy + (n_light + BLISS_WARPS - 1) / BLISS_WARPS;
+  const int tid = threadIdx.x;
+  const bool needs_row_w = (c.mode != BLISS_MODE_LADIES);
+  if (ctr->n_edges > out.cap_edges) return;  // capacity error already flagged
+  for (;;) {
+    int item = next_item(&ctr->queue[2], n_items, &s_item);
+    if (item < 0) break;
+    if (item < n_heavy) {
+      const int row = ws.row_list[item];
+      const int s = seeds[row];
+      const int64_t a = c.g.indptr[s];
+      const int d = (int)(c.g.indptr[s + 1] - a);
+      const int32_t* __restrict__ idx = c.g.indices + a;
+      const float row_w = needs_row_w ? ws.row_w[row] : 1.0f;
+      const float eta_n = __fdiv_rn(c.eta, (float)d);
+      int base = out.indptr[row];
+      double acc = 0.0;
+      const int d_pad = (d + BLISS_CTA - 1) / BLISS_CTA * BLISS_CTA;
+      for (int k = tid; k < d_pad; k += BLISS_CTA) {
+        int src = (k < d) ? __ldg(idx + k) : 0;
+        int keep = (k < d) && test_bit(ws.sel_bits, src);
+        int tot;
+        int p = block_excl_scan(keep, s_scan, &tot);
+        if (keep) acc += fill_edge(c, ws, out, a + k, src, row, base + p, row_w, eta_n);
+        base += tot;
+      }
+      acc = block_sum(acc, s_red);
+      if (tid == 0) ws.row_t[row] = acc;
+    } else {
+      const int li = (item - n_heavy) * BLISS_WARPS + warp_id();
+      if (li < n_light) {
+        const int lane = lane_id();
+        const int row = ws.row_list[n_seeds - 1 - li];
+        const int s = seeds[row];
+        const int64_t a = c.g.indptr[s];
+        const int d = (int)(c.g.indptr[s + 1] - a);
+        const int32_t* __restrict__ idx = c.g.indices + a;
+        const float row_w = (needs_row_w && d > 0) ? ws.row_w[row] : 1.0f;
+        const float eta_n = __fdiv_rn(c.eta, (float)d);
+        int base = out.indptr[row];
+        double acc = 0.0;
+        for (int k0 = 0; k0 < d; k0 += 32) {
+          int k = k0 + lane;
+          int src = (k < d) ? __ldg(idx + k) : 0;
+          bool keep = (k < d) && test_bit(ws.sel_bits, src);
+          unsigned m = __ballot_sync(0xffffffffu, keep);
+          if (keep)
+            acc += fill_edge(c, ws, out, a + k, src, row, base + __popc(m & ((1u << lane) - 1u)), row_w, eta_n);
+          base += __popc(m);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) ws.row_t[row] = acc;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// (3d) finish: W~_e *= d_i / ΣW~ (bandit :316-320) or *= d_i (ladies :97); restore the
+//      workspace invariant for every node this layer touched.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_block_finish(int mode, bliss_workspace ws, bliss_block_out out) {
+  bliss_counters* ctr = ws.ctr;
+  const int64_t n_edges = (ctr->n_edges <= out.cap_edges) ? ctr->n_edges : 0;
+  const int n_cand = ctr->n_cand;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t e = t0; e < n_edges; e += stride) {
+    int i = out.edge_dst[e];
+    float d = (float)(out.indptr[i + 1] - out.indptr[i]);
+    float f = (mode == BLISS_MODE_LADIES) ? d : __fdiv_rn(d, __double2float_rn(ws.row_t[i]));
+    out.edge_w[e] = __fmul_rn(out.edge_w[e], f);
+  }
+  for (int64_t j = t0; j < n_cand; j += stride) {
+    int nid = ws.cand[j];
+    ws.acc[nid] = 0ull;
+    ws.first_pos[nid] = ~0ull;
+    ws.node_info[2 * nid] = -1;
+    ws.node_info[2 * nid + 1] = 0;
+    ws.sel_bits[nid >> 5] = 0u;
+  }
+}
+
+__global__ void k_ws_init(bliss_workspace ws, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += stride) {
+    ws.acc[v] = 0ull;
+    ws.first_pos[v] = ~0ull;
+    ws.node_info[2 * v] = -1;
+    ws.node_info[2 * v + 1] = 0;
+    if ((v & 31) == 0) ws.sel_bits[v >> 5] = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// source-major transpose of a block for the backward aggregation
+// ------------------------------------------------------------------------------------------
+__global__ void k_t_count(const int32_t* __restrict__ edge_src, int64_t n_edges, int32_t* __restrict__ cnt) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += stride)
+    atomicAdd(&cnt[edge_src[e]], 1);
+}
+// cnt_cursor holds the per-source counts on entry and the fill cursors (= row starts) on exit.
+__global__ void __launch_bounds__(1024) k_t_scan(int32_t* cnt_cursor, int n, int32_t* __restrict__ indptr) {
+  const int32_t* cnt = cnt_cursor;
+  int32_t* cursor = cnt_cursor;
+  __shared__ int s_scan[40];
+  int base = 0;
+  for (int b = 0; b < n; b += blockDim.x) {
+    int i = b + threadIdx.x;
+    int v = (i < n) ? cnt[i] : 0;
+    int tot;
+    int p = block_excl_scan(v, s_scan, &tot);
+    if (i < n) indptr[i] = base + p;
+    base += tot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) indptr[n] = base;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) cursor[i] = indptr[i];
+}
+// Edges of a source land in arbitrary order inside its segment; k_t_sort restores ascending edge
+// id so the backward sums are run-to-run deterministic.
+__global__ void k_t_fill(const int32_t* __restrict__ edge_src, int64_t n_edges, int32_t* __restrict__ cursor,
+                         int32_t* __restrict__ t_perm) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += stride) {
+    int slot = atomicAdd(&cursor[edge_src[e]], 1);
+    t_perm[slot] = (int32_t)e;
+  }
+}
+// Warp per source row: the edges of one source go to distinct destinations and edge ids grow
+// with the destination (block edges are destination-major), so ascending edge id == ascending
+// destination.  Each warp builds a bitmap of the row's destinations in shared memory; the rank
+// of an edge is the number of set bits below its destination.  O(len + n_dst/32) per row.
+__global__ void __launch_bounds__(256) k_t_sort(const int32_t* __restrict__ t_indptr, int n_src, int n_words,
+                                               const int32_t* __restrict__ edge_dst,
+                                               const int32_t* __restrict__ perm_in,
+                                               int32_t* __restrict__ t_perm, int32_t* __restrict__ t_dst) {
+  extern __shared__ unsigned s_bits[];  // per warp: n_words bitmap + n_words prefix
+  unsigned* bits = s_bits + (size_t)warp_id() * 2 * n_words;
+  unsigned* pre = bits + n_words;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = lane_id();
+  for (int r = warp; r < n_src; r += nwarps) {
+    const int a = t_indptr[r], b = t_indptr[r + 1];
+    if (b - a == 1) {
+      if (lane == 0) {
+        int e = perm_in[a];
+        t_perm[a] = e;
+        t_dst[a] = edge_dst[e];
+      }
+      continue;
+    }
+    if (b == a) continue;
+    for (int w = lane; w < n_words; w += 32) bits[w] = 0u;
+    __syncwarp();
+    for (int k = a + lane; k < b; k += 32) {
+      int dst = edge_dst[perm_in[k]];
+      atomicOr(&bits[dst >> 5], 1u << (dst & 31));
+    }
+    __syncwarp();
+    int base = 0;
+    for (int w0 = 0; w0 < n_words; w0 += 32) {
+      int w = w0 + lane;
+      int c = (w < n_words) ? __popc(bits[w]) : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (w < n_words) pre[w] = base + incl - c;
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    for (int k = a + lane; k < b; k += 32) {
+      int e = perm_in[k];
+      int dst = edge_dst[e];
+      int rank = pre[dst >> 5] + __popc(bits[dst >> 5] & ((1u << (dst & 31)) - 1u));
+      t_perm[a + rank] = e;
+      t_dst[a + rank] = dst;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace bliss
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace bliss;
+
+static inline GraphView view_of(const bliss_graph* g) {
+  GraphView v;
+  v.indptr = g->indptr;
+  v.indices = g->indices;
+  v.eid = g->eid;
+  v.num_nodes = g->num_nodes;
+  return v;
+}
+static inline int grid_for(int64_t n, int threads, int max_blocks) {
+  int64_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+static int g_prob_smem_set = 0;
+
+extern "C" {
+
+int bliss_version(void) { return BLISS_B200_VERSION; }
+
+int bliss_workspace_init(const bliss_workspace* ws, int64_t num_nodes, void* stream) {
+  if (!ws || num_nodes <= 0) return -1;
+  k_ws_init<<<grid_for(num_nodes, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(*ws, num_nodes);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_frontier_plan(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                        const bliss_workspace* ws, void* stream) {
+  if (!g || !seeds || !ws || n_seeds < 0 || n_seeds > ws->cap_seeds) return -1;
+  k_frontier_plan<<<1, 1024, 0, (cudaStream_t)stream>>>(view_of(g), seeds, n_seeds, *ws);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_frontier_prob(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                        const float* edge_weight_csc, float eta, int32_t mode,
+                        const bliss_workspace* ws, void* stream) {
+  if (!g || !seeds || !ws || n_seeds < 0) return -1;
+  if (!edge_weight_csc) return -1;
+  const size_t smem = BLISS_STAGE_CAP * sizeof(float);
+  if (!g_prob_smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_frontier_prob, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    g_prob_smem_set = 1;
+  }
+  const double fx_scale = (double)(1ull << fx_bits_for(n_seeds));
+  const float one_minus_eta = (float)(1.0 - (double)eta);
+  int blocks = grid_for((int64_t)n_seeds * 32, BLISS_CTA, BLISS_SM_COUNT * 6);
+  k_frontier_prob<<<blocks, BLISS_CTA, smem, (cudaStream_t)stream>>>(view_of(g), seeds, edge_weight_csc, eta,
+                                                                    one_minus_eta, mode, *ws, fx_scale);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_poisson_scale(int32_t n_seeds, int32_t fanout, double eps, int32_t poisson,
+                        const bliss_workspace* ws, void* stream) {
+  if (!ws || fanout < 0) return -1;
+  const double fx_inv = 1.0 / (double)(1ull << fx_bits_for(n_seeds));
+  k_poisson_scale<<<1, 1024, 0, (cudaStream_t)stream>>>(n_seeds, fanout, eps, poisson, *ws, fx_inv);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_select_poisson(int32_t n_seeds, uint64_t seed, uint64_t step, uint32_t layer,
+                         const float* u_inject, const bliss_workspace* ws, void* stream) {
+  if (!ws) return -1;
+  k_select_poisson<<<BLISS_SM_COUNT * 4, 256, 0, (cudaStream_t)stream>>>(n_seeds, seed, step, layer, u_inject, *ws);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_select_topk(int32_t n_seeds, int32_t fanout, uint64_t seed, uint64_t step, uint32_t layer,
+                      const float* u_inject, float* key_scratch, const bliss_workspace* ws, void* stream) {
+  if (!ws || !key_scratch) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  // the threshold triple lives in the tail of the caller's key scratch ([V + 4] floats)
+  unsigned* thr = reinterpret_cast<unsigned*>(key_scratch);
+  float* keys = key_scratch + 4;
+  k_topk_keys<<<BLISS_SM_COUNT * 4, 256, 0, st>>>(n_seeds, seed, step, layer, u_inject, keys, *ws);
+  BLISS_CHECK_LAUNCH();
+  k_topk_threshold<<<1, 1024, 0, st>>>(fanout, keys, thr, *ws);
+  BLISS_CHECK_LAUNCH();
+  k_topk_mark<<<1, 1024, 0, st>>>(n_seeds, keys, thr, *ws);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_philox_fill(uint64_t seed, uint64_t step, uint32_t layer, const int32_t* nids, int64_t n,
+                      float* out, void* stream) {
+  if (n < 0 || (n > 0 && (!nids || !out))) return -1;
+  if (n == 0) return 0;
+  k_philox_fill<<<grid_for(n, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(seed, step, layer, nids, n, out);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_block_count(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                      const bliss_workspace* ws, void* stream) {
+  if (!g || !seeds || !ws) return -1;
+  int blocks = grid_for((int64_t)n_seeds * 32, BLISS_CTA, BLISS_SM_COUNT * 8);
+  k_block_count<<<blocks, BLISS_CTA, 0, (cudaStream_t)stream>>>(view_of(g), seeds, *ws);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_block_index(const int32_t* seeds, int32_t n_seeds, const bliss_workspace* ws,
+                      const bliss_block_out* out, void* stream) {
+  if (!seeds || !ws || !out || !out->indptr || !out->src_nid || !out->node_prob) return -1;
+  k_block_index<<<BLISS_SM_COUNT, 256, 0, (cudaStream_t)stream>>>(seeds, n_seeds, *ws, *out);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_block_fill(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                     const float* edge_weight_csc, float eta, int32_t mode,
+                     const bliss_workspace* ws, const bliss_block_out* out, void* stream) {
+  if (!g || !seeds || !ws || !out || !edge_weight_csc) return -1;
+  if (!out->edge_src || !out->edge_dst || !out->csc_pos || !out->edge_w) return -1;
+  FillCtx c;
+  c.g = view_of(g);
+  c.W = edge_weight_csc;
+  c.eta = eta;
+  c.one_minus_eta = (float)(1.0 - (double)eta);
+  c.mode = mode & 1;
+  int blocks = grid_for((int64_t)n_seeds * 32, BLISS_CTA, BLISS_SM_COUNT * 8);
+  k_block_fill<<<blocks, BLISS_CTA, 0, (cudaStream_t)stream>>>(c, seeds, *ws, *out);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_block_finish(int32_t n_seeds, int32_t mode, const bliss_workspace* ws,
+                       const bliss_block_out* out, void* stream) {
+  if (!ws || !out) return -1;
+  (void)n_seeds;
+  k_block_finish<<<BLISS_SM_COUNT * 4, 256, 0, (cudaStream_t)stream>>>(mode & 1, *ws, *out);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
+                          int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor,
+                          int32_t* t_scratch, int32_t* t_dst, int32_t* t_perm, void* stream) {
+  if (n_edges < 0 || n_src < 0 || !t_indptr || !t_cursor) return -1;
+  if (n_edges > 0 && (!edge_src || !edge_dst || !t_scratch || !t_dst || !t_perm)) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(t_cursor, 0, sizeof(int32_t) * (size_t)(n_src > 0 ? n_src : 1), st);
+  if (e != cudaSuccess) return (int)e;
+  if (n_edges > 0) {
+    k_t_count<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, t_cursor);
+    BLISS_CHECK_LAUNCH();
+  }
+  k_t_scan<<<1, 1024, 0, st>>>(t_cursor, n_src, t_indptr);
+  BLISS_CHECK_LAUNCH();
+  if (n_edges == 0) return 0;
+  k_t_fill<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, t_cursor, t_scratch);
+  BLISS_CHECK_LAUNCH();
+  const int n_words = (n_dst + 31) / 32;
+  const size_t smem = (size_t)BLISS_WARPS * 2 * n_words * sizeof(unsigned);
+  if (smem > 200 * 1024) return -2;  // n_dst > ~100K destinations per block: not supported
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(k_t_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k_t_sort<<<grid_for((int64_t)n_src * 32, 256, BLISS_SM_COUNT * 4), 256, smem, st>>>(t_indptr, n_src, n_words, edge_dst,
+                                                                                  t_scratch, t_perm, t_dst);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,311 @@
+"""Drop-in models: ``SAGE`` / ``GCN`` / ``GATv2`` with the reference constructor signatures
+(``model.py:292-310,386-419,115-205``) over the sm_100a aggregation kernels.
+
+The DGL layers the reference instantiates — ``dglnn.SAGEConv(in, out, 'mean')``,
+``dglnn.GraphConv(norm='both', allow_zero_in_degree=True)`` and ``dglnn.GATv2Conv`` subclassed as
+``custom_GATv2Conv`` (``model.py:13-112``) — are re-implemented here with DGL-compatible
+parameter names (``fc_neigh`` / ``fc_self`` / ``weight`` / ``bias`` / ``fc_src`` / ``attn`` /
+``res_fc``) so reference checkpoints' state dicts line up.  The dense projections stay torch
+GEMMs; message passing, edge softmax and ``embed_norm`` are the custom kernels (``ops.py``).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .graph import Graph
+
+
+class SAGEConv(nn.Module):
+    """``dglnn.SAGEConv(in_feats, out_feats, 'mean')`` with ``edge_weight``."""
+
+    def __init__(self, in_feats, out_feats, aggregator_type="mean", feat_drop=0.0, bias=True):
+        super().__init__()
+        if aggregator_type != "mean":
+            raise NotImplementedError("the reference only builds SAGEConv(..., 'mean') (model.py:303-308)")
+        self._in_src_feats = self._in_dst_feats = in_feats
+        self._out_feats = out_feats
+        self.feat_drop = nn.Dropout(feat_drop)
+        self.fc_neigh = nn.Linear(in_feats, out_feats, bias=False)
+        self.fc_self = nn.Linear(in_feats, out_feats, bias=bias)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain("relu")
+        nn.init.xavier_uniform_(self.fc_self.weight, gain=gain)
+        nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
+
+    def forward(self, graph, feat, edge_weight=None):
+        feat_src = self.feat_drop(feat)
+        feat_dst = feat_src[: graph.number_of_dst_nodes()]
+        lin_before_mp = self._in_src_feats > self._out_feats
+        h = self.fc_neigh(feat_src) if lin_before_mp else feat_src
+        h_neigh = ops.spmm(graph, h, edge_weight, dst_scale=ops.mean_scale(graph))   # u_mul_e + fn.mean
+        if not lin_before_mp:
+            h_neigh = self.fc_neigh(h_neigh)
+        return self.fc_self(feat_dst) + h_neigh
+
+
+class GraphConv(nn.Module):
+    """``dglnn.GraphConv(in, out, norm='both', activation=..., allow_zero_in_degree=True)`` (a13)."""
+
+    def __init__(self, in_feats, out_feats, norm="both", weight=True, bias=True, activation=None,
+                 allow_zero_in_degree=False):
+        super().__init__()
+        if norm != "both" or not weight:
+            raise NotImplementedError("the reference only builds GraphConv(norm='both') with a weight")
+        self._in_feats, self._out_feats = in_feats, out_feats
+        self.weight = nn.Parameter(torch.empty(in_feats, out_feats))
+        self.bias = nn.Parameter(torch.empty(out_feats)) if bias else None
+        self._activation = activation
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.xavier_uniform_(self.weight)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, graph, feat, weight=None, edge_weight=None):
+        src_norm = getattr(graph, "_gcn_src_norm", None)
+        if src_norm is None:
+            src_norm = graph.out_degrees().to(torch.float32).clamp(min=1).pow(-0.5)
+            dst_norm = graph.in_degrees().to(torch.float32).clamp(min=1).pow(-0.5)
+            graph._gcn_src_norm, graph._gcn_dst_norm = src_norm, dst_norm
+        dst_norm = graph._gcn_dst_norm
+        w = self.weight
+        if self._in_feats > self._out_feats:
+            rst = ops.spmm(graph, torch.matmul(feat, w), edge_weight, src_scale=src_norm, dst_scale=dst_norm)
+        else:
+            rst = torch.matmul(ops.spmm(graph, feat, edge_weight, src_scale=src_norm, dst_scale=dst_norm), w)
+        if self.bias is not None:
+            rst = rst + self.bias
+        if self._activation is not None:
+            rst = self._activation(rst)
+        return rst
+
+
+class custom_GATv2Conv(nn.Module):
+    """``custom_GATv2Conv`` (``model.py:13-112``) — GATv2 layer with shared projection, no bias,
+    returning the **pre-softmax logits** as attention (``:108-110``); ``edge_weight`` accepted and
+    ignored like the reference (``:91-96`` commented out)."""
+
+    def __init__(self, in_feats, out_feats, num_heads, feat_drop=0.0, attn_drop=0.0, negative_slope=0.2,
+                 residual=False, activation=None, allow_zero_in_degree=False, bias=True, share_weights=False):
+        super().__init__()
+        if not share_weights or bias:
+            raise NotImplementedError("the reference only builds GATv2Conv(bias=False, share_weights=True)")
+        self._num_heads, self._in_src_feats, self._out_feats = num_heads, in_feats, out_feats
+        self._allow_zero_in_degree = allow_zero_in_degree
+        self.fc_src = nn.Linear(in_feats, out_feats * num_heads, bias=False)
+        self.fc_dst = self.fc_src
+        self.attn = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.feat_drop = nn.Dropout(feat_drop)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.negative_slope = negative_slope
+        if residual:
+            self.res_fc = (nn.Linear(in_feats, num_heads * out_feats, bias=False)
+                           if in_feats != out_feats * num_heads else nn.Identity())
+        else:
+            self.res_fc = None
+        self.activation = activation
+        self.share_weights = share_weights
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain("relu")
+        nn.init.xavier_normal_(self.fc_src.weight, gain=gain)
+        nn.init.xavier_normal_(self.attn, gain=gain)
+        if isinstance(self.res_fc, nn.Linear):
+            nn.init.xavier_normal_(self.res_fc.weight, gain=gain)
+
+    def forward(self, graph, feat, edge_weight=None, get_attention=False):
+        if not self._allow_zero_in_degree and bool((graph.in_degrees() == 0).any()):
+            raise RuntimeError("There are 0-in-degree nodes in the graph (model.py:49-61)")
+        h_src = h_dst = self.feat_drop(feat)                                              # :69
+        feat_src = self.fc_src(h_src).view(-1, self._num_heads, self._out_feats)          # :70
+        h_dst = h_dst[: graph.number_of_dst_nodes()]                                      # :79
+        mask = None
+        if self.training and self.attn_drop.p > 0:                                        # :88 attn_drop
+            keep = 1.0 - self.attn_drop.p
+            mask = (torch.rand(graph.num_edges(), self._num_heads, device=feat.device) < keep).float() / keep
+        rst, e = ops.gatv2_attention(graph, feat_src, self.attn, self.negative_slope, mask)   # :80-98
+        if self.res_fc is not None:
+            rst = rst + self.res_fc(h_dst).view(h_dst.shape[0], -1, self._out_feats)      # :101-103
+        if self.activation:
+            rst = self.activation(rst)                                                    # :105-106
+        return (rst, e.unsqueeze(-1)) if get_attention else rst                           # :108-112
+
+
+def _edge_weights(block):
+    return block.edata["edge_weights"] if "edge_weights" in block.edata else None
+
+
+class SAGE(nn.Module):
+    """``model.py:292-333``."""
+
+    def __init__(self, in_feats, n_hidden, n_classes, n_layers, activation, dropout):
+        super().__init__()
+        self.init(in_feats, n_hidden, n_classes, n_layers, activation, dropout)
+
+    def init(self, in_feats, n_hidden, n_classes, n_layers, activation, dropout):
+        self.n_layers, self.n_hidden, self.n_classes = n_layers, n_hidden, n_classes
+        self.layers = nn.ModuleList()
+        if n_layers > 1:
+            self.layers.append(SAGEConv(in_feats, n_hidden, "mean"))
+            for _ in range(1, n_layers - 1):
+                self.layers.append(SAGEConv(n_hidden, n_hidden, "mean"))
+            self.layers.append(SAGEConv(n_hidden, n_classes, "mean"))
+        else:
+            self.layers.append(SAGEConv(in_feats, n_classes, "mean"))
+        self.dropout = nn.Dropout(dropout)
+        self.activation = activation
+
+    def forward(self, blocks, x):
+        h = x
+        for l, (layer, block) in enumerate(zip(self.layers, blocks)):
+            block.srcdata["embed_norm"] = ops.row_norm(h)                             # :318
+            h = layer(block, h, edge_weight=_edge_weights(block))                         # :321-329
+            if l < len(self.layers) - 1:
+                h = self.dropout(self.activation(h))                                      # :330-332
+        return h
+
+    def inference(self, g, device, batch_size, use_uva=False, num_workers=0):
+        """``model.py:335-383``: layer-wise full-neighbour inference (no sampling, no edge weights).
+        The whole graph's CSC is one destination-major CSR, so each layer is a single SpMM."""
+        return _full_inference(self, g, lambda l, h: self.dropout(self.activation(h)))
+
+
+class GCN(nn.Module):
+    """``model.py:386-439``."""
+
+    def __init__(self, in_feats, n_hidden, n_classes, n_layers, activation, dropout):
+        super().__init__()
+        self.init(in_feats, n_hidden, n_classes, n_layers, activation, dropout)
+
+    def init(self, in_feats, n_hidden, n_classes, n_layers, activation, dropout):
+        self.n_layers, self.n_hidden, self.n_classes = n_layers, n_hidden, n_classes
+        self.layers = nn.ModuleList()
+        if n_layers > 1:
+            self.layers.append(GraphConv(in_feats, n_hidden, activation=activation, allow_zero_in_degree=True))
+            for _ in range(1, n_layers - 1):
+                self.layers.append(GraphConv(n_hidden, n_hidden, activation=activation, allow_zero_in_degree=True))
+            self.layers.append(GraphConv(n_hidden, n_classes, allow_zero_in_degree=True))
+        else:
+            self.layers.append(GraphConv(in_feats, n_classes, allow_zero_in_degree=True))
+        self.dropout = nn.Dropout(dropout)
+        self.activation = activation
+
+    def forward(self, blocks, x):
+        h = x
+        for l, (layer, block) in enumerate(zip(self.layers, blocks)):
+            block.srcdata["embed_norm"] = ops.row_norm(h)                             # :425
+            h = layer(block, h, edge_weight=_edge_weights(block))                         # :428-436
+            if l < len(self.layers) - 1:
+                h = self.dropout(h)                                                       # :437-438
+        return h
+
+    def inference(self, g, device, batch_size, use_uva=False, num_workers=0):
+        """``model.py:441-488``."""
+        return _full_inference(self, g, lambda l, h: self.dropout(h))
+
+
+class GATv2(nn.Module):
+    """``model.py:115-234``."""
+
+    def __init__(self, num_layers, in_dim, num_hidden, num_classes, heads, activation, feat_drop, attn_drop,
+                 negative_slope, residual):
+        super().__init__()
+        self.num_layers, self.num_hidden, self.num_classes, self.heads = num_layers, num_hidden, num_classes, heads
+        self.activation = activation
+        self.gatv2_layers = nn.ModuleList()
+        mk = lambda i, o, h, res, act: custom_GATv2Conv(                                  # noqa: E731
+            i, o, h, feat_drop, attn_drop, negative_slope, res, act, bias=False, share_weights=True,
+            allow_zero_in_degree=True)
+        if num_layers > 1:
+            self.gatv2_layers.append(mk(in_dim, num_hidden, heads[0], False, self.activation))
+            for l in range(1, num_layers - 1):
+                self.gatv2_layers.append(mk(num_hidden * heads[l - 1], num_hidden, heads[l], residual, self.activation))
+            self.gatv2_layers.append(mk(num_hidden * heads[-2], num_classes, heads[-1], residual, None))
+        else:
+            self.gatv2_layers.append(mk(in_dim, num_classes, heads[-1], residual, None))
+
+    def forward(self, blocks, inputs):
+        h = inputs
+        for l, block in enumerate(blocks):
+            block.srcdata["embed_norm"] = ops.row_norm(h)                             # :211
+            h, a = self.gatv2_layers[l](block, h, edge_weight=_edge_weights(block), get_attention=True)
+            block.edata["a_ij"] = torch.mean(a.squeeze(dim=-1), dim=1)                    # :224-227
+            h = h.flatten(1) if l < len(blocks) - 1 else h.mean(1)                        # :228-232
+        return h
+
+    def inference(self, g, device, batch_size, use_uva=False, num_workers=0):
+        """``model.py:236-289``."""
+        blk = _whole_graph_block(g)
+        was_training = self.training
+        self.eval()
+        h = g.ndata["features"].float()
+        with torch.no_grad():
+            for l, layer in enumerate(self.gatv2_layers):
+                h = layer(blk, h)
+                h = h.flatten(1) if l < len(self.gatv2_layers) - 1 else h.mean(1)
+        self.train(was_training)
+        return h
+
+
+class _WholeGraphBlock:
+    """The full graph seen as one block (every node is source and destination) — what
+    ``MultiLayerFullNeighborSampler(1)`` yields batch by batch in the reference's ``inference``."""
+
+    is_block = True
+
+    def __init__(self, g: Graph):
+        if g.num_edges() >= 2 ** 31:
+            raise NotImplementedError("whole-graph inference needs |E| < 2^31")
+        self.indptr = g.indptr.to(torch.int32)
+        self.edge_src = g.indices
+        n = g.num_nodes()
+        self.edge_dst = torch.repeat_interleave(torch.arange(n, dtype=torch.int32, device=g.device), g.in_degrees())
+        self._n = n
+        self.srcdata, self.dstdata, self.edata = {}, {}, {}
+        self._transpose = None
+
+    def num_src_nodes(self):
+        return self._n
+
+    num_dst_nodes = number_of_dst_nodes = number_of_src_nodes = num_src_nodes
+
+    def num_edges(self):
+        return int(self.edge_src.numel())
+
+    @property
+    def device(self):
+        return self.indptr.device
+
+    def in_degrees(self):
+        return self.indptr[1:] - self.indptr[:-1]
+
+    def out_degrees(self):
+        return torch.bincount(self.edge_src.long(), minlength=self._n)
+
+
+def _whole_graph_block(g: Graph):
+    blk = getattr(g, "_whole_block", None)
+    if blk is None:
+        blk = _WholeGraphBlock(g)
+        g._whole_block = blk
+    return blk
+
+
+def _full_inference(model, g: Graph, post):
+    blk = _whole_graph_block(g)
+    was_training = model.training
+    model.eval()
+    h = g.ndata["features"].float()
+    with torch.no_grad():
+        for l, layer in enumerate(model.layers):
+            h = layer(blk, h)
+            if l < len(model.layers) - 1:
+                h = post(l, h)
+    model.train(was_training)
+    return h

@@ -1,0 +1,167 @@
+"""Autograd-aware wrappers over the C ABI (``include/bliss_b200.h``): feature gather, row norms,
+SpMM (SAGE / GCN aggregation) and the fused GATv2 attention.  Every function launches the
+hand-written sm_100a kernels on torch's current stream; there is no PyTorch fallback — a tensor
+that is not a contiguous fp32 CUDA tensor raises.
+
+Reference call sites replaced: ``train_lightning.py:138`` (feature fetch), ``model.py:318,425,211``
+(``th.norm``), ``dglnn.SAGEConv`` / ``GraphConv`` message passing (``model.py:321-329,428-436``) and
+``custom_GATv2Conv.forward`` (``model.py:80-99``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as N
+
+
+def _req(t: torch.Tensor, dtype=torch.float32, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (the BLISS hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def gather_rows(table: torch.Tensor, nid: torch.Tensor, with_norm: bool = False):
+    """``table[nid]`` (lazy DGL frame gather, ``train_lightning.py:138-139``); optionally also the
+    row L2 norms of the gathered rows (``embed_norm`` of layer 0, ``model.py:318``)."""
+    if table.dtype != torch.float32 or table.dim() != 2:
+        # labels / masks / non-fp32 frames: not the hot path, plain indexing
+        out = table[nid.long()]
+        return (out, None) if with_norm else out
+    table = _req(table, name="table")
+    nid = _req(nid, torch.int32, "nid")
+    n, d = nid.numel(), table.shape[1]
+    out = torch.empty((n, d), dtype=torch.float32, device=table.device)
+    norm = torch.empty(n, dtype=torch.float32, device=table.device) if with_norm else None
+    N.check(N.lib().bliss_gather_rows(N.ptr(table), N.ptr(nid), n, d, N.ptr(out), N.ptr(norm), N.stream()),
+            "bliss_gather_rows")
+    return (out, norm) if with_norm else out
+
+
+def row_norm(x: torch.Tensor) -> torch.Tensor:
+    """``th.norm(h, dim=1)`` (``model.py:318``); detached — the bandit only reads it."""
+    x = _req(x.detach(), name="x")
+    x2 = x.reshape(x.shape[0], -1)
+    out = torch.empty(x2.shape[0], dtype=torch.float32, device=x.device)
+    N.check(N.lib().bliss_row_norm(N.ptr(x2), x2.shape[0], x2.shape[1], N.ptr(out), N.stream()), "bliss_row_norm")
+    return out
+
+
+def block_transpose(block):
+    """Source-major CSR of a block (cached on the block) for the backward aggregation."""
+    if block._transpose is None:
+        E, n_src, n_dst = block.num_edges(), block.num_src_nodes(), block.num_dst_nodes()
+        dev = block.device
+        t_indptr = torch.empty(n_src + 1, dtype=torch.int32, device=dev)
+        t_cursor = torch.empty(max(n_src, 1), dtype=torch.int32, device=dev)
+        t_scratch = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        t_dst = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        t_perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        N.check(N.lib().bliss_block_transpose(N.ptr(block.edge_src), N.ptr(block.edge_dst), E, n_src, n_dst,
+                                              N.ptr(t_indptr), N.ptr(t_cursor), N.ptr(t_scratch), N.ptr(t_dst),
+                                              N.ptr(t_perm), N.stream()), "bliss_block_transpose")
+        block._transpose = (t_indptr, t_dst[:E], t_perm[:E])
+    return block._transpose
+
+
+def _spmm_raw(indptr, col, perm, w, sscale, dscale, agg, x, n_rows):
+    d = x.shape[1]
+    y = torch.empty((n_rows, d), dtype=torch.float32, device=x.device)
+    N.check(N.lib().bliss_spmm(N.ptr(indptr), N.ptr(col), N.ptr(perm), N.ptr(w), N.ptr(sscale), N.ptr(dscale),
+                               agg, N.ptr(x), n_rows, d, N.ptr(y), N.stream()), "bliss_spmm")
+    return y
+
+
+class _SpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, block, w, sscale, dscale):
+        x = _req(x, name="x")
+        ctx.block, ctx.w, ctx.sscale, ctx.dscale = block, w, sscale, dscale
+        return _spmm_raw(block.indptr, block.edge_src, None, w, sscale, dscale, N.AGG_SUM, x,
+                         block.num_dst_nodes())
+
+    @staticmethod
+    def backward(ctx, gy):
+        block = ctx.block
+        t_indptr, t_dst, t_perm = block_transpose(block)
+        gy = _req(gy, name="grad")
+        # dx_c = sscale_c * Σ_{e: src_e = c} w_e * dscale_{dst_e} * dy_{dst_e}
+        gx = _spmm_raw(t_indptr, t_dst, t_perm, ctx.w, ctx.dscale, ctx.sscale, N.AGG_SUM, gy,
+                       block.num_src_nodes())
+        return gx, None, None, None, None
+
+
+def spmm(block, x, edge_weight=None, src_scale=None, dst_scale=None):
+    """``y_i = dst_scale_i · Σ_{e→i} w_e · src_scale_{src(e)} · x_{src(e)}`` (g-SpMM ``u_mul_e``/sum).
+    ``x`` is [n_src, D] fp32; differentiable w.r.t. ``x``."""
+    if x.dim() != 2:
+        raise ValueError("spmm expects [n_src, D]")
+    if edge_weight is not None:
+        edge_weight = _req(edge_weight.detach(), name="edge_weight")
+    return _SpMM.apply(x, block, edge_weight, src_scale, dst_scale)
+
+
+def mean_scale(block) -> torch.Tensor:
+    """1 / max(in_degree, 1) per destination (``fn.mean``), cached on the block."""
+    s = getattr(block, "_mean_scale", None)
+    if s is None:
+        s = 1.0 / block.in_degrees().clamp(min=1).to(torch.float32)
+        block._mean_scale = s
+    return s
+
+
+class _GATv2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, attn, block, drop_mask, slope):
+        feat = _req(feat, name="feat")          # [n_src, H, D]
+        attn_c = _req(attn, name="attn").reshape(attn.shape[-2], attn.shape[-1])
+        n_src, H, D = feat.shape
+        n_dst, E = block.num_dst_nodes(), block.num_edges()
+        dev = feat.device
+        out = torch.empty((n_dst, H, D), dtype=torch.float32, device=dev)
+        logits = torch.empty((E, H), dtype=torch.float32, device=dev)
+        rmax = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
+        rsum = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
+        N.check(N.lib().bliss_gatv2_fwd(N.ptr(block.indptr), N.ptr(block.edge_src), N.ptr(feat), N.ptr(attn_c),
+                                        N.ptr(drop_mask), slope, n_dst, H, D, N.ptr(out), N.ptr(logits),
+                                        N.ptr(rmax), N.ptr(rsum), N.stream()), "bliss_gatv2_fwd")
+        ctx.save_for_backward(feat, attn_c, logits, rmax, rsum, out)
+        ctx.block, ctx.drop_mask, ctx.slope, ctx.attn_shape = block, drop_mask, slope, attn.shape
+        ctx.mark_non_differentiable(logits)
+        return out, logits
+
+    @staticmethod
+    def backward(ctx, gout, _glogits):
+        feat, attn_c, logits, rmax, rsum, out = ctx.saved_tensors
+        block, mask, slope = ctx.block, ctx.drop_mask, ctx.slope
+        n_src, H, D = feat.shape
+        n_dst, E = block.num_dst_nodes(), block.num_edges()
+        gout = _req(gout, name="grad")
+        dev = feat.device
+        gfeat = torch.empty_like(feat)
+        gattn = torch.zeros_like(attn_c)
+        glogit = torch.empty((max(E, 1), H), dtype=torch.float32, device=dev)
+        L = N.lib()
+        N.check(L.bliss_gatv2_bwd_dst(N.ptr(block.indptr), N.ptr(block.edge_src), N.ptr(feat), N.ptr(attn_c),
+                                      N.ptr(mask), N.ptr(logits), N.ptr(rmax), N.ptr(rsum), N.ptr(out),
+                                      N.ptr(gout), slope, n_dst, H, D, N.ptr(glogit), N.ptr(gfeat),
+                                      N.ptr(gattn), N.stream()), "bliss_gatv2_bwd_dst")
+        t_indptr, t_dst, t_perm = block_transpose(block)
+        N.check(L.bliss_gatv2_bwd_src(N.ptr(t_indptr), N.ptr(t_dst), N.ptr(t_perm), N.ptr(feat), N.ptr(attn_c),
+                                      N.ptr(mask), N.ptr(logits), N.ptr(rmax), N.ptr(rsum), N.ptr(gout),
+                                      N.ptr(glogit), slope, n_src, n_dst, H, D, N.ptr(gfeat), N.stream()),
+                "bliss_gatv2_bwd_src")
+        return gfeat, gattn.reshape(ctx.attn_shape), None, None, None
+
+
+def gatv2_attention(block, feat, attn, negative_slope, drop_mask=None):
+    """Fused SDDMM(u_add_v) + leaky-relu + ·attn + edge-softmax + SpMM(u_mul_e) of
+    ``custom_GATv2Conv.forward`` (``model.py:80-99``) with shared source/destination projection.
+
+    feat [n_src, H, D], attn [1, H, D] → (ft [n_dst, H, D], logits [E, H]) where ``logits`` are the
+    pre-softmax scores the reference returns as attention (``model.py:108-110``).  ``drop_mask``
+    [E, H] (already scaled by 1/(1-p)) multiplies the softmax output (``attn_drop``, :88-90)."""
+    if drop_mask is not None:
+        drop_mask = _req(drop_mask, name="drop_mask")
+    return _GATv2.apply(feat, attn, block, drop_mask, float(negative_slope))

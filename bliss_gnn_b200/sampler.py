@@ -1,0 +1,473 @@
+"""Drop-in samplers: ``BanditLadiesSampler`` / ``PoissonBanditLadiesSampler``
+(reference ``bandit_sampler.py:29-424``) and ``LadiesSampler`` / ``PoissonLadiesSampler``
+(``ladies_sampler.py:24-183``) over the sm_100a kernels of ``csrc/sampler.cu`` and
+``csrc/bandit.cu``.
+
+Same class names, constructor signatures, public attributes and method names as the reference;
+``sample_blocks(g, seed_nodes, exclude_eids=None) -> (input_nodes, output_nodes, blocks)`` is the
+``dgl.dataloading.BlockSampler`` protocol and ``exp3(mfgs, g)`` the post-step bandit update
+(``train_lightning.py:463-471``).  What differs underneath:
+
+* the stage methods (``exp3_probabilities`` → ``compute_prob`` → ``select_neighbors`` →
+  ``generate_block``) pass a :class:`Frontier` handle (device workspace) instead of DGL sub-graphs;
+* EXP3 weights live CSC-ordered and un-normalised with a running L1 norm (``normalize='lazy'``);
+  ``exp3_weights`` exposes the reference's ``[L, |E|]`` edge-id-ordered normalised view.
+  ``normalize='literal'`` re-normalises densely after every update like ``bandit_sampler.py:249``;
+* randomness is one Philox4x32-10 draw per (seed, step, layer, node id) — ``rng_seed`` — or an
+  injected dense ``[|V|]`` array of uniforms (``inject_uniforms``), never a torch generator.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from . import _native as N
+from .graph import EID, NID, Block, Graph
+
+
+class _Workspace:
+    """Device buffers of one (sampler, graph) pair; every array is |V|-sized so no capacity can be
+    exceeded, and nothing |V|-sized is cleared per step (the finish kernel restores the
+    invariant for the touched nodes)."""
+
+    def __init__(self, g: Graph):
+        dev = g.device
+        if dev.type != "cuda":
+            raise RuntimeError("the BLISS samplers run on a CUDA graph only (no CPU fallback): use g.to('cuda')")
+        V = g.num_nodes()
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.acc = torch.empty(V, dtype=torch.int64, device=dev)
+        self.first_pos = torch.empty(V, dtype=torch.int64, device=dev)
+        self.node_info = torch.empty(2 * V, **i32)
+        self.sel_bits = torch.empty((V + 31) // 32, **i32)
+        self.cand = torch.empty(V, **i32)
+        self.p_cand = torch.empty(V, dtype=torch.float32, device=dev)
+        self.sel = torch.empty(V, **i32)
+        self.row_list = torch.empty(V, **i32)
+        self.row_w = torch.empty(V, dtype=torch.float32, device=dev)
+        self.row_q = torch.empty(V, dtype=torch.float32, device=dev)
+        self.row_cnt = torch.empty(V, **i32)
+        self.row_t = torch.empty(V, dtype=torch.float64, device=dev)
+        self.src_nid = torch.empty(V, **i32)
+        self.node_prob = torch.empty(V, dtype=torch.float32, device=dev)
+        self.key_scratch = None
+        self.ctr = torch.zeros(C.sizeof(N.Counters), dtype=torch.uint8, device=dev)
+        self.ctr_host = torch.zeros(C.sizeof(N.Counters), dtype=torch.uint8).pin_memory()
+        self.ws = N.Workspace(
+            acc=N.ptr(self.acc), first_pos=N.ptr(self.first_pos), node_info=N.ptr(self.node_info),
+            sel_bits=N.ptr(self.sel_bits), cand=N.ptr(self.cand), p_cand=N.ptr(self.p_cand), sel=N.ptr(self.sel),
+            row_list=N.ptr(self.row_list), row_w=N.ptr(self.row_w), row_q=N.ptr(self.row_q),
+            row_cnt=N.ptr(self.row_cnt), row_t=N.ptr(self.row_t), cap_seeds=V, cap_sel=V, ctr=N.ptr(self.ctr))
+        self.gview = N.Graph(num_nodes=V, num_edges=g.num_edges(), indptr=N.ptr(g.indptr),
+                             indices=N.ptr(g.indices), eid=N.ptr(g.eid))
+        self._keep = (g.indptr, g.indices, g.eid)
+        N.check(N.lib().bliss_workspace_init(C.byref(self.ws), V, N.stream()), "bliss_workspace_init")
+
+    def read_counters(self) -> N.Counters:
+        self.ctr_host.copy_(self.ctr, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return N.Counters.from_buffer_copy(self.ctr_host.numpy().tobytes())
+
+
+class Frontier:
+    """What ``exp3_probabilities`` / ``compute_prob`` hand on (the reference's ``insg`` + ``edge_prob``)."""
+
+    def __init__(self, g, wsp, seeds, n_seeds, layer, mode, weights):
+        self.g, self.wsp, self.seeds, self.n_seeds = g, wsp, seeds, n_seeds
+        self.layer, self.mode, self.weights = layer, mode, weights
+        self.counters: Optional[N.Counters] = None
+
+
+class BanditLadiesSampler:
+    """``bandit_sampler.py:29-367``: EXP3-bandit layer-importance sampler, multinomial selection."""
+
+    _poisson = False
+    _mode = N.MODE_BANDIT
+
+    def __init__(self, nodes_per_layer, importance_sampling=True, weight="w", out_weight="edge_weights",
+                 node_embedding="nfeat", node_prob="node_prob", replace=False, eta=0.4, num_steps=5000,
+                 model="sage", rng_seed: int = 0, normalize: str = "lazy", renorm_every: int = 64):
+        self.nodes_per_layer = nodes_per_layer
+        self.importance_sampling = importance_sampling
+        self.edge_weight = weight
+        self.output_weight = out_weight
+        self.node_prob = node_prob
+        self.node_embedding = node_embedding
+        self.replace = replace
+        self.eta = eta
+        self.T = num_steps
+        self.model = model
+        self.eps = 0.9999
+        if replace:
+            raise NotImplementedError("replace=True (multinomial with replacement) is not used by the reference CLI")
+        if normalize not in ("lazy", "literal"):
+            raise ValueError("normalize must be 'lazy' or 'literal'")
+        self.rng_seed = int(rng_seed)
+        self.step = 0
+        self.normalize = normalize
+        self.renorm_every = int(renorm_every)
+        self.inject_uniforms = None   # dense [|V|] float32 (or {layer: tensor}), test hook
+        self.process_group = None                              # set for data-parallel bandit exchange
+        self._w_csc: Optional[torch.Tensor] = None             # [L, |E|] un-normalised, CSC order
+        self._l1: Optional[torch.Tensor] = None                # [L] float64 running L1 norms
+        self._updated = None                                   # [L] bool: weights ever updated
+        self._updates_since_renorm = 0
+        self._wsp: Optional[_Workspace] = None
+        self._g: Optional[Graph] = None
+        self.last_counters: List[Optional[N.Counters]] = [None] * len(nodes_per_layer)
+
+    # ---- state --------------------------------------------------------------------------
+    def _bind(self, g: Graph):
+        if self._g is not g:
+            self._wsp = _Workspace(g)
+            self._g = g
+            self._w_csc = None
+        if self._w_csc is None and self._mode == N.MODE_BANDIT:
+            L, E = len(self.nodes_per_layer), g.num_edges()
+            e_pad = (E + 63) // 64 * 64      # every layer's row starts 256-byte aligned
+            self._w_buf = torch.ones(L, e_pad, dtype=torch.float32, device=g.device)  # bandit_sampler.py:343
+            self._w_csc = [self._w_buf[l, :E] for l in range(L)]
+            self._l1 = torch.full((L,), float(E), dtype=torch.float64, device=g.device)
+            self._updated = [False] * L
+            self._norm_partial = torch.empty(1024, dtype=torch.float64, device=g.device)
+        return self._wsp
+
+    @property
+    def exp3_weights(self):
+        """The reference's ``[L, |E|]`` edge-id-ordered weights (``bandit_sampler.py:43,343,249``):
+        all ones before the first update, L1-normalised afterwards."""
+        if self._w_csc is None:
+            return None
+        g = self._g
+        out = torch.empty(len(self._w_csc), g.num_edges(), dtype=torch.float32, device=g.device)
+        for l in range(len(self._w_csc)):
+            w = self._w_csc[l]
+            if self._updated[l]:
+                w = (w.double() / self._l1[l].clamp_min(1e-12)).float()
+            out[l, g.eid.long()] = w
+        return out
+
+    @exp3_weights.setter
+    def exp3_weights(self, value):
+        if value is None:
+            self._w_csc = None
+            return
+        g = self._g
+        if g is None:
+            raise RuntimeError("bind a graph first: call sample_blocks once or use set_exp3_weights(g, w)")
+        self.set_exp3_weights(g, value)
+
+    def set_exp3_weights(self, g: Graph, value: torch.Tensor):
+        """Load ``[L, |E|]`` weights given in edge-id order (checkpoint restore / tests)."""
+        self._bind(g)
+        v = value.to(device=g.device, dtype=torch.float32)
+        for l in range(v.shape[0]):
+            self._w_csc[l].copy_(v[l, g.eid.long()])
+        self._l1 = torch.stack([w.double().abs().sum() for w in self._w_csc])
+        self._updated = [True] * v.shape[0]
+
+    def state_dict(self):
+        return {"exp3_w_csc": torch.stack(list(self._w_csc)), "l1": self._l1, "updated": self._updated, "step": self.step,
+                "rng_seed": self.rng_seed}
+
+    def load_state_dict(self, sd, g: Graph):
+        self._bind(g)
+        for l, w in enumerate(sd["exp3_w_csc"]):
+            self._w_csc[l].copy_(w)
+        self._l1 = sd["l1"].to(g.device).clone()
+        self._updated = list(sd["updated"])
+        self.step = int(sd["step"])
+        self.rng_seed = int(sd["rng_seed"])
+
+    # ---- stage 1: edge probabilities ------------------------------------------------------
+    def exp3_probabilities(self, idx, g, seed_nodes):
+        """``bandit_sampler.py:101-138``: registers the frontier (replaces in_subgraph +
+        compact_graphs); q_ij itself is produced on the fly by the later passes.  Returns
+        ``(edge_prob, insg)`` as one :class:`Frontier` handle twice, to keep the call shape."""
+        wsp = self._bind(g)
+        n = int(seed_nodes.numel())
+        fr = Frontier(g, wsp, seed_nodes, n, idx, self._mode, self._w_csc[idx])
+        N.check(N.lib().bliss_frontier_plan(C.byref(wsp.gview), N.ptr(seed_nodes), n, C.byref(wsp.ws), N.stream()),
+                "bliss_frontier_plan")
+        return fr, fr
+
+    # ---- stage 2: node probabilities ---------------------------------------------------------
+    def _frontier_prob(self, fr: Frontier):
+        mode = fr.mode | (0 if self.importance_sampling else N.MODE_UNIFORM)
+        N.check(N.lib().bliss_frontier_prob(C.byref(fr.wsp.gview), N.ptr(fr.seeds), fr.n_seeds, N.ptr(fr.weights),
+                                            float(self.eta), mode, C.byref(fr.wsp.ws), N.stream()),
+                "bliss_frontier_prob")
+
+    def compute_prob(self, insg: Frontier, seed_nodes, edge_prob, num):
+        """``bandit_sampler.py:47-82`` (+ the Poisson scale search ``:381-406`` in the subclass)."""
+        self._frontier_prob(insg)
+        N.check(N.lib().bliss_poisson_scale(insg.n_seeds, int(num), float(self.eps), int(self._poisson),
+                                            C.byref(insg.wsp.ws), N.stream()), "bliss_poisson_scale")
+        return insg
+
+    # ---- stage 3: selection -------------------------------------------------------------------
+    def _u_ptr(self, g, layer=None):
+        u = self.inject_uniforms
+        if isinstance(u, dict):
+            u = u.get(layer)
+        if u is None:
+            return None
+        if u.dtype != torch.float32 or u.numel() != g.num_nodes() or u.device != g.device:
+            raise ValueError("inject_uniforms must be a float32 [num_nodes] tensor on the graph's device")
+        return N.ptr(u)
+
+    def select_neighbors(self, prob: Frontier, num):
+        """``bandit_sampler.py:84-99``: multinomial without replacement = top-k of p / Exp(1)."""
+        wsp = prob.wsp
+        if wsp.key_scratch is None:
+            wsp.key_scratch = torch.empty(prob.g.num_nodes() + 4, dtype=torch.float32, device=prob.g.device)
+        N.check(N.lib().bliss_select_topk(prob.n_seeds, int(num), self.rng_seed, self.step, prob.layer,
+                                          self._u_ptr(prob.g, prob.layer), N.ptr(wsp.key_scratch), C.byref(wsp.ws),
+                                          N.stream()), "bliss_select_topk")
+        return prob
+
+    # ---- stage 4: block construction ------------------------------------------------------------
+    def generate_block(self, insg: Frontier, neighbor_nodes_idx, seed_nodes, P_sg=None, W_sg=None):
+        """``bandit_sampler.py:269-339`` (``ladies_sampler.py:71-107``)."""
+        fr, wsp, g = insg, insg.wsp, insg.g
+        L, st = N.lib(), N.stream()
+        n_s = fr.n_seeds
+        dev = g.device
+        indptr = torch.empty(n_s + 1, dtype=torch.int32, device=dev)
+        out = N.BlockOut(indptr=N.ptr(indptr), src_nid=N.ptr(wsp.src_nid), node_prob=N.ptr(wsp.node_prob),
+                         cap_edges=0, cap_src=g.num_nodes())
+        N.check(L.bliss_block_count(C.byref(wsp.gview), N.ptr(fr.seeds), n_s, C.byref(wsp.ws), st), "bliss_block_count")
+        N.check(L.bliss_block_index(N.ptr(fr.seeds), n_s, C.byref(wsp.ws), C.byref(out), st), "bliss_block_index")
+        ctr = wsp.read_counters()            # the one host read of this layer: n_src, E_b
+        if ctr.error:
+            raise RuntimeError(f"BLISS sampler capacity error {ctr.error} in layer {fr.layer}")
+        fr.counters = ctr
+        self.last_counters[fr.layer] = ctr
+        n_src, E = int(ctr.n_src), int(ctr.n_edges)
+        edge_src = torch.empty(E, dtype=torch.int32, device=dev)
+        edge_dst = torch.empty(E, dtype=torch.int32, device=dev)
+        csc_pos = torch.empty(E, dtype=torch.int64, device=dev)
+        eid = torch.empty(E, dtype=torch.int32, device=dev)
+        edge_w = torch.empty(E, dtype=torch.float32, device=dev)
+        q_ij = torch.empty(E, dtype=torch.float32, device=dev) if fr.mode == N.MODE_BANDIT else None
+        out.edge_src, out.edge_dst, out.csc_pos = N.ptr(edge_src), N.ptr(edge_dst), N.ptr(csc_pos)
+        out.eid, out.edge_w, out.q_ij = N.ptr(eid), N.ptr(edge_w), N.ptr(q_ij)
+        out.cap_edges = E
+        if E > 0:
+            N.check(L.bliss_block_fill(C.byref(wsp.gview), N.ptr(fr.seeds), n_s, N.ptr(fr.weights), float(self.eta),
+                                       fr.mode, C.byref(wsp.ws), C.byref(out), st), "bliss_block_fill")
+        N.check(L.bliss_block_finish(n_s, fr.mode, C.byref(wsp.ws), C.byref(out), st), "bliss_block_finish")
+        src_nid = wsp.src_nid[:n_src].clone()
+        block = Block(indptr, edge_src, edge_dst, src_nid, fr.seeds, graph=g, csc_pos=csc_pos)
+        block.edata[EID] = eid                                                   # :337
+        block.edata[self.output_weight] = edge_w                                 # :324
+        self._attach(block, q_ij, wsp.node_prob[:n_src].clone())
+        return block
+
+    def _attach(self, block, q_ij, node_prob):
+        block.edata["q_ij"] = q_ij                                               # :326
+        block.srcdata[self.node_prob] = node_prob                                # :328
+
+    # ---- driver ---------------------------------------------------------------------------------
+    def _prep_seeds(self, g, seed_nodes):
+        s = torch.as_tensor(seed_nodes)
+        if s.device != g.device:
+            s = (s.pin_memory() if s.device.type == "cpu" and not s.is_pinned() else s).to(g.device, non_blocking=True)
+        return s.to(torch.int32).contiguous()
+
+    def sample_blocks(self, g, seed_nodes, exclude_eids=None):
+        """``bandit_sampler.py:341-367``."""
+        self._bind(g)
+        seed_nodes = self._prep_seeds(g, seed_nodes)
+        output_nodes = seed_nodes
+        blocks = []
+        for block_id in reversed(range(len(self.nodes_per_layer))):              # :350
+            num = self.nodes_per_layer[block_id]
+            edge_prob, insg = self.exp3_probabilities(block_id, g, seed_nodes)   # :354
+            node_prob = self.compute_prob(insg, seed_nodes, edge_prob, num)      # :356
+            chosen = self.select_neighbors(node_prob, num)                       # :360
+            block = self.generate_block(insg, chosen, seed_nodes, node_prob, edge_prob)   # :362
+            seed_nodes = block.srcdata[NID]                                      # :364
+            blocks.insert(0, block)                                              # :366
+        self.step += 1
+        return seed_nodes, output_nodes, blocks
+
+    # ---- bandit update ------------------------------------------------------------------------
+    def calculate_alpha(self, mfg):
+        """``bandit_sampler.py:140-158``.  SAGE/GCN: the static edge weight; GAT: from a_ij, q_ij."""
+        if self.model == "gat":
+            n_dst = mfg.num_dst_nodes()
+            asum = torch.empty(n_dst, dtype=torch.float32, device=mfg.device)
+            qsum = torch.empty(n_dst, dtype=torch.float32, device=mfg.device)
+            a = mfg.edata["a_ij"].detach().contiguous()
+            N.check(N.lib().bliss_gat_alpha_sums(N.ptr(mfg.indptr), N.ptr(a), N.ptr(mfg.edata["q_ij"]), n_dst,
+                                                 N.ptr(asum), N.ptr(qsum), N.stream()), "bliss_gat_alpha_sums")
+            return ("gat", a, asum, qsum)
+        return ("static", None, None, None)
+
+    def _reward_call(self, idx, mfg, g, alpha, weights, rewards=None, x_out=None, l1=None):
+        kind, a, asum, qsum = alpha
+        wsp = self._bind(g)
+        w_static = g.csc_edata(self.edge_weight) if kind == "static" else None
+        emb = mfg.srcdata["embed_norm"]
+        emb = emb.detach()
+        if emb.dtype != torch.float32:
+            emb = emb.float()
+        N.check(N.lib().bliss_reward_update(
+            C.byref(wsp.gview), N.ptr(mfg.indptr), N.ptr(mfg.edge_src), N.ptr(mfg.edge_dst), N.ptr(mfg.csc_pos),
+            N.ptr(mfg.dstdata[NID]), N.ptr(mfg.edata["q_ij"]), N.ptr(mfg.srcdata[self.node_prob]),
+            N.ptr(emb.contiguous()), N.ptr(w_static), N.ptr(a), N.ptr(asum), N.ptr(qsum),
+            1 if kind == "gat" else 0, 0.01, mfg.num_dst_nodes(), mfg.num_edges(), N.ptr(weights),
+            N.ptr(rewards), N.ptr(x_out), N.ptr(l1), N.stream()), "bliss_reward_update")
+
+    def calculate_rewards(self, idx, mfg, g, alpha):
+        """``bandit_sampler.py:160-193``: stores ``mfg.edata['rewards']`` (emit-only kernel call)."""
+        r = torch.empty(mfg.num_edges(), dtype=torch.float32, device=mfg.device)
+        self._reward_call(idx, mfg, g, alpha, None, rewards=r)
+        mfg.edata["rewards"] = r
+
+    def update_exp3_weights(self, idx, mfg, g, alpha=None):
+        """``bandit_sampler.py:195-249``: w[e] *= exp(min(1, r/P · δ/n)) then L1-normalise."""
+        if alpha is None:
+            alpha = self.calculate_alpha(mfg)
+        pg = self.process_group
+        if pg is not None and torch.distributed.get_world_size(pg) > 1:
+            self._update_distributed(idx, mfg, g, alpha, pg)
+        else:
+            self._reward_call(idx, mfg, g, alpha, self._w_csc[idx], l1=self._l1[idx:idx + 1])
+        self._updated[idx] = True
+        if self.normalize == "literal":
+            self._renormalize(idx)
+
+    def _update_distributed(self, idx, mfg, g, alpha, pg):
+        """Every rank sampled from the same frozen weights; all ranks apply all ranks' updates
+        (``w *= exp(x)`` commutes).  One all-gather of the sparse (CSC position, exponent) pairs."""
+        import torch.distributed as dist
+        E = mfg.num_edges()
+        x = torch.empty(E, dtype=torch.float32, device=mfg.device)
+        self._reward_call(idx, mfg, g, alpha, None, x_out=x)
+        world = dist.get_world_size(pg)
+        n_loc = torch.tensor([E], dtype=torch.int64, device=mfg.device)
+        sizes = [torch.zeros_like(n_loc) for _ in range(world)]
+        dist.all_gather(sizes, n_loc, group=pg)
+        sizes = [int(s.item()) for s in sizes]
+        cap = max(max(sizes), 1)
+        pos_pad = torch.zeros(cap, dtype=torch.int64, device=mfg.device)
+        x_pad = torch.zeros(cap, dtype=torch.float32, device=mfg.device)
+        pos_pad[:E] = mfg.csc_pos
+        x_pad[:E] = x
+        pos_all = [torch.empty_like(pos_pad) for _ in range(world)]
+        x_all = [torch.empty_like(x_pad) for _ in range(world)]
+        dist.all_gather(pos_all, pos_pad, group=pg)
+        dist.all_gather(x_all, x_pad, group=pg)
+        for r in range(world):
+            if sizes[r]:
+                N.check(N.lib().bliss_apply_updates(N.ptr(pos_all[r]), N.ptr(x_all[r]), sizes[r],
+                                                    N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]),
+                                                    N.stream()), "bliss_apply_updates")
+
+    def _renormalize(self, idx):
+        w = self._w_csc[idx]
+        L = N.lib()
+        N.check(L.bliss_l1_norm(N.ptr(w), w.numel(), N.ptr(self._norm_partial), N.ptr(self._l1[idx:idx + 1]),
+                                N.stream()), "bliss_l1_norm")
+        N.check(L.bliss_scale_by_inv(N.ptr(w), w.numel(), N.ptr(self._l1[idx:idx + 1]), 1e-12, N.stream()),
+                "bliss_scale_by_inv")
+        self._l1[idx] = 1.0
+
+    def exp3(self, mfgs, g):
+        """``bandit_sampler.py:251-267``: reward + weight update of every layer, one fused kernel each."""
+        self._bind(g)
+        for idx, mfg in enumerate(mfgs):
+            alpha = self.calculate_alpha(mfg)
+            self.update_exp3_weights(idx, mfg, g, alpha)
+        if self.normalize == "lazy":
+            self._updates_since_renorm += 1
+            if self._updates_since_renorm >= self.renorm_every:   # range safety: growth ≤ e per step
+                for idx in range(len(mfgs)):
+                    self._renormalize(idx)
+                self._updates_since_renorm = 0
+
+
+class PoissonBanditLadiesSampler(BanditLadiesSampler):
+    """``bandit_sampler.py:369-424``: Poisson (independent inclusion) variant — the CLI default."""
+
+    _poisson = True
+
+    def select_neighbors(self, prob: Frontier, num):
+        """``bandit_sampler.py:408-425``: ``bernoulli(P) == 1``  ⇔  ``u < P``."""
+        N.check(N.lib().bliss_select_poisson(prob.n_seeds, self.rng_seed, self.step, prob.layer,
+                                             self._u_ptr(prob.g, prob.layer), C.byref(prob.wsp.ws), N.stream()),
+                "bliss_select_poisson")
+        return prob
+
+
+class LadiesSampler(BanditLadiesSampler):
+    """``ladies_sampler.py:24-123``: static weights ``g.edata[weight]``, no bandit state."""
+
+    _mode = N.MODE_LADIES
+
+    def __init__(self, nodes_per_layer, importance_sampling=True, weight="w", out_weight="edge_weights",
+                 replace=False, allow_zero_in_degree=False, rng_seed: int = 0):
+        super().__init__(nodes_per_layer, importance_sampling, weight, out_weight, replace=replace,
+                         rng_seed=rng_seed)
+        self.allow_zero_in_degree = allow_zero_in_degree
+
+    def compute_prob(self, g, seed_nodes, weight, num):
+        """``ladies_sampler.py:34-52``: returns ``(prob, insg)`` (one Frontier handle twice)."""
+        wsp = self._bind(g)
+        n = int(seed_nodes.numel())
+        fr = Frontier(g, wsp, seed_nodes, n, self._layer, N.MODE_LADIES, weight)
+        N.check(N.lib().bliss_frontier_plan(C.byref(wsp.gview), N.ptr(seed_nodes), n, C.byref(wsp.ws), N.stream()),
+                "bliss_frontier_plan")
+        self._frontier_prob(fr)
+        N.check(N.lib().bliss_poisson_scale(n, int(num), float(self.eps), int(self._poisson), C.byref(wsp.ws),
+                                            N.stream()), "bliss_poisson_scale")
+        return fr, fr
+
+    def _attach(self, block, q_ij, node_prob):
+        pass                                                                     # ladies_sampler.py:99-106
+
+    def sample_blocks(self, g, seed_nodes, exclude_eids=None):
+        """``ladies_sampler.py:109-123``."""
+        self._bind(g)
+        seed_nodes = self._prep_seeds(g, seed_nodes)
+        output_nodes = seed_nodes
+        blocks = []
+        W = g.csc_edata(self.edge_weight)                                        # :114 (CSC order)
+        if W.dtype != torch.float32:
+            W = W.float()
+        if not hasattr(self, "_w_checked"):
+            if float(W.max()) > 1.0:
+                raise ValueError("LADIES edge weights must be <= 1 (fixed-point column sums; DESIGN.md §4)")
+            self._w_checked = True
+        for block_id in reversed(range(len(self.nodes_per_layer))):
+            self._layer = block_id
+            num = self.nodes_per_layer[block_id]
+            prob, insg = self.compute_prob(g, seed_nodes, W, num)                # :115
+            chosen = self.select_neighbors(prob, num)                            # :117
+            block = self.generate_block(insg, chosen, seed_nodes, prob, W)       # :118-120
+            seed_nodes = block.srcdata[NID]
+            blocks.insert(0, block)
+        self.step += 1
+        return seed_nodes, output_nodes, blocks
+
+    def exp3(self, mfgs, g):
+        raise AttributeError("LadiesSampler has no bandit state (train_lightning.py:469 only calls exp3 for bandit samplers)")
+
+
+class PoissonLadiesSampler(LadiesSampler):
+    """``ladies_sampler.py:125-183``."""
+
+    _poisson = True
+
+    def __init__(self, nodes_per_layer, importance_sampling=True, weight="w", out_weight="edge_weights",
+                 allow_zero_in_degree=False, rng_seed: int = 0):
+        # the reference forwards allow_zero_in_degree into the ``replace`` slot (:134-136); the value
+        # is False on every CLI path, so it is simply kept as an attribute here
+        super().__init__(nodes_per_layer, importance_sampling, weight, out_weight, replace=False,
+                         allow_zero_in_degree=allow_zero_in_degree, rng_seed=rng_seed)
+
+    select_neighbors = PoissonBanditLadiesSampler.select_neighbors

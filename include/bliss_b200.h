@@ -1,0 +1,205 @@
+/* bliss_b200.h — C ABI of the B200-native BLISS sample-and-aggregate hot path.
+ *
+ * Every entry point replaces a group of DGL FFI calls / torch glue the reference reaches from
+ * Python (the reference has no native code of its own; citations are into /root/reference):
+ * raw device pointers, element counts, scalars and a CUDA stream go in; an int comes back
+ * (0 = ok, <0 = bad argument, >0 = cudaError_t of the launch).  No entry point allocates,
+ * synchronises or keeps global state: the caller owns every buffer (sizes below), data-dependent
+ * sizes are written to the device-side bliss_counters block and read back by the caller when it
+ * needs them.  All kernels run on `stream` (pass torch's current stream).
+ *
+ * Data layout: the graph is CSC — indptr int64 [V+1], indices int32 [E] (source
+ * of each in-edge, column = destination, self-loop last in its column), per-edge arrays
+ * (EXP3 weights, static weights `w`) are stored in CSC order so they stream with `indices`.
+ */
+#ifndef BLISS_B200_H
+#define BLISS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLISS_B200_VERSION 100
+
+/* importance modes of bliss_frontier_prob */
+#define BLISS_MODE_BANDIT 0   /* q_ij from EXP3 weights, p_j = sqrt(sum_i (q_ij/sum_k q_ik)^2)  bandit_sampler.py:47-82,101-138 */
+#define BLISS_MODE_LADIES 1   /* p_j = sqrt(sum_i w_ij^2) with static w                         ladies_sampler.py:34-52 */
+#define BLISS_MODE_UNIFORM 2  /* flag OR-ed onto the above: importance_sampling=0, p_j = 1 for nodes with an out-edge  bandit_sampler.py:77-81 */
+
+/* aggregation modes of bliss_spmm */
+#define BLISS_AGG_SUM 0
+#define BLISS_AGG_MEAN 1      /* divide by max(in_degree, 1)  (fn.mean, dglnn.SAGEConv 'mean') */
+
+typedef struct bliss_graph {
+  int64_t num_nodes;
+  int64_t num_edges;
+  const int64_t* indptr;   /* [num_nodes + 1] */
+  const int32_t* indices;  /* [num_edges]     */
+  const int32_t* eid;      /* [num_edges] CSC position -> original edge id (may be NULL) */
+} bliss_graph;
+
+/* Device-resident per-layer counters; the host reads this block back once per layer. */
+typedef struct bliss_counters {
+  int32_t n_seeds;     /* rows of this layer                                     */
+  int32_t n_cand;      /* |seeds ∪ sources|  (insg.num_nodes(), :392)            */
+  int32_t n_sel;       /* selected non-seed candidates                           */
+  int32_t n_src;       /* block source nodes = n_seeds + n_sel                   */
+  int32_t n_heavy;     /* rows handled by a whole CTA                            */
+  int32_t n_light;     /* rows handled by one warp                               */
+  int32_t take_all;    /* 1 when n_cand <= fanout (:392-393)                     */
+  int32_t iters;       /* scale-search iterations used (:396)                    */
+  int64_t e_in;        /* in-edges of the seeds (insg.num_edges())               */
+  int64_t n_edges;     /* block edges E_b                                        */
+  double  c;           /* Poisson scale                                          */
+  double  s_last;      /* last S = sum min(c p, 1)                               */
+  int32_t queue[4];    /* dynamic row-queue cursors of the three row passes      */
+  int32_t error;       /* non-zero: a capacity was exceeded (see BLISS_ERR_*)    */
+  int32_t pad;
+} bliss_counters;
+
+#define BLISS_ERR_SEL_CAPACITY 1
+#define BLISS_ERR_EDGE_CAPACITY 2
+
+/* Per-sampler workspace (device pointers; V = num_nodes, S = max seeds of a layer,
+ * C = capacity of selected nodes).  Invariant between layers: acc == 0, first_pos == ~0,
+ * node_info[v].x == -1, sel_bits == 0 — bliss_block_finish restores it for every node a layer
+ * touched, so nothing |V|-sized is cleared per step. */
+typedef struct bliss_workspace {
+  uint64_t* acc;        /* [V]  fixed-point column accumulator, bit 63 = "registered"     */
+  uint64_t* first_pos;  /* [V]  first occurrence key of a selected source                 */
+  int32_t*  node_info;  /* [2V] (local id | -1, float bits of inclusion prob P) per node  */
+  uint32_t* sel_bits;   /* [(V+31)/32] bitmap: node is selected                           */
+  int32_t*  cand;       /* [V]  candidate list: seeds first, then sources unordered       */
+  float*    p_cand;     /* [V]  raw probability per candidate slot                        */
+  int32_t*  sel;        /* [C]  selected non-seed candidates, unordered                   */
+  int32_t*  row_list;   /* [S]  heavy rows from the front, light rows from the back       */
+  float*    row_w;      /* [S]  sum_j w_ij  per seed                                      */
+  float*    row_q;      /* [S]  sum_j q_ij  per seed                                      */
+  int32_t*  row_cnt;    /* [S]  kept in-edges per seed                                    */
+  double*   row_t;      /* [S]  sum of unnormalised block weights per seed                */
+  int64_t   cap_seeds;  /* S */
+  int64_t   cap_sel;    /* C */
+  bliss_counters* ctr;  /* one counters block                                             */
+} bliss_workspace;
+
+/* Outputs of one sampled layer (device pointers, capacities checked against the counters). */
+typedef struct bliss_block_out {
+  int32_t* indptr;      /* [n_seeds + 1] destination-major CSR                            */
+  int32_t* edge_src;    /* [E_b] local source id                                          */
+  int32_t* edge_dst;    /* [E_b] local destination id                                     */
+  int64_t* csc_pos;     /* [E_b] position of the edge in the graph CSC                    */
+  int32_t* eid;         /* [E_b] original edge id (NULL to skip)                          */
+  float*   q_ij;        /* [E_b] edge probability q_ij (NULL for LADIES)                  */
+  float*   edge_w;      /* [E_b] block weight W~ (bandit_sampler.py:314-320)              */
+  int32_t* src_nid;     /* [n_src] global id of each block source                         */
+  float*   node_prob;   /* [n_src] inclusion probability P (bandit_sampler.py:328)        */
+  int32_t* out_deg;     /* [n_src] block out-degree of each source (NULL to skip)         */
+  int64_t  cap_edges;
+  int64_t  cap_src;
+} bliss_block_out;
+
+int bliss_version(void);
+
+/* Fill the workspace invariant (once, after allocation). */
+int bliss_workspace_init(const bliss_workspace* ws, int64_t num_nodes, void* stream);
+
+/* ---- (1) layer-importance probabilities ------------------------------------------------
+ * replaces dgl.in_subgraph + compact_graphs + 3x copy_e_sum + e_div_v/e_div_u/v_add_e
+ * (bandit_sampler.py:123-137, :67-75; ladies_sampler.py:42-48).                            */
+int bliss_frontier_plan(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                        const bliss_workspace* ws, void* stream);
+int bliss_frontier_prob(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                        const float* edge_weight_csc, float eta, int32_t mode,
+                        const bliss_workspace* ws, void* stream);
+
+/* ---- (2) inclusion probabilities + selection ---------------------------------------------
+ * Poisson: scale search bandit_sampler.py:391-406 on the device (no host round trips), then
+ * u < P with u = Philox4x32-10(key = seed, ctr = (nid, layer, step)) or u_inject[nid].
+ * Top-k: torch.multinomial(prob, k, replacement=False) == topk(p / -log1p(-u)), :84-99.    */
+int bliss_poisson_scale(int32_t n_seeds, int32_t fanout, double eps, int32_t poisson,
+                        const bliss_workspace* ws, void* stream);
+int bliss_select_poisson(int32_t n_seeds, uint64_t seed, uint64_t step, uint32_t layer,
+                         const float* u_inject, const bliss_workspace* ws, void* stream);
+int bliss_select_topk(int32_t n_seeds, int32_t fanout, uint64_t seed, uint64_t step, uint32_t layer,
+                      const float* u_inject, float* key_scratch, const bliss_workspace* ws,
+                      void* stream);
+int bliss_philox_fill(uint64_t seed, uint64_t step, uint32_t layer, const int32_t* nids,
+                      int64_t n, float* out, void* stream);   /* test hook */
+
+/* ---- (3) block construction ---------------------------------------------------------------
+ * replaces insg.subgraph + edge_subgraph + to_block + e_div_u/copy_e_sum/e_mul_v
+ * (bandit_sampler.py:285-337; ladies_sampler.py:81-106).                                    */
+int bliss_block_count(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                      const bliss_workspace* ws, void* stream);
+int bliss_block_index(const int32_t* seeds, int32_t n_seeds, const bliss_workspace* ws,
+                      const bliss_block_out* out, void* stream);
+int bliss_block_fill(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                     const float* edge_weight_csc, float eta, int32_t mode,
+                     const bliss_workspace* ws, const bliss_block_out* out, void* stream);
+int bliss_block_finish(int32_t n_seeds, int32_t mode, const bliss_workspace* ws,
+                       const bliss_block_out* out, void* stream);
+/* source-major transpose of a block (backward SpMM): t_indptr[n_src+1], t_dst[E], t_perm[E]
+ * (edge ids ascending inside every source row, so backward sums are deterministic). */
+int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
+                          int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor /* [n_src] */,
+                          int32_t* t_scratch /* [E] */, int32_t* t_dst, int32_t* t_perm, void* stream);
+
+/* ---- (5) aggregation ------------------------------------------------------------------------
+ * replaces DGL g-SpMM u_mul_e/sum (+ fn.mean), g-SDDMM u_add_v, edge_softmax, th.norm and the
+ * lazy feature gather (model.py:82-98,318-329,425-436; train_lightning.py:138).              */
+int bliss_gather_rows(const float* table, const int32_t* nid, int64_t n_rows, int32_t dim,
+                      float* out, float* row_norm /* may be NULL */, void* stream);
+int bliss_row_norm(const float* x, int64_t n_rows, int32_t dim, float* out, void* stream);
+/* y[i,:] = dscale_i * sum_{e in row i} w[perm? perm[e] : e] * sscale[col[e]] * x[col[e], :] */
+int bliss_spmm(const int32_t* indptr, const int32_t* col, const int32_t* perm, const float* w,
+               const float* sscale, const float* dscale, int32_t agg, const float* x,
+               int32_t n_rows, int32_t dim, float* y, void* stream);
+int bliss_gatv2_fwd(const int32_t* indptr, const int32_t* col, const float* feat /* [n_src,H,D] */,
+                    const float* attn /* [H,D] */, const float* drop_mask /* [E,H] or NULL */,
+                    float negative_slope, int32_t n_dst, int32_t heads, int32_t dim,
+                    float* out /* [n_dst,H,D] */, float* logits /* [E,H] */,
+                    float* row_max /* [n_dst,H] */, float* row_sum /* [n_dst,H] */, void* stream);
+int bliss_gatv2_bwd_dst(const int32_t* indptr, const int32_t* col, const float* feat, const float* attn,
+                        const float* drop_mask, const float* logits, const float* row_max,
+                        const float* row_sum, const float* out, const float* grad_out,
+                        float negative_slope, int32_t n_dst, int32_t heads, int32_t dim,
+                        float* grad_logit /* [E,H] */, float* grad_feat /* [n_src,H,D], dst part */,
+                        float* grad_attn /* [H,D], accumulated */, void* stream);
+int bliss_gatv2_bwd_src(const int32_t* t_indptr, const int32_t* t_dst, const int32_t* t_perm,
+                        const float* feat, const float* attn, const float* drop_mask,
+                        const float* logits, const float* row_max, const float* row_sum,
+                        const float* grad_out, const float* grad_logit, float negative_slope,
+                        int32_t n_src, int32_t n_dst, int32_t heads, int32_t dim,
+                        float* grad_feat /* in: dst-term rows [0,n_dst) from bwd_dst; out: full */,
+                        void* stream);
+
+/* ---- (4) bandit reward / weight update -----------------------------------------------------
+ * replaces calculate_alpha / calculate_rewards / update_exp3_weights
+ * (bandit_sampler.py:140-249).  alpha_mode 0: alpha = static w (SAGE/GCN); 1: GAT (a_ij, q_ij). */
+int bliss_gat_alpha_sums(const int32_t* blk_indptr, const float* a_ij, const float* q_ij,
+                         int32_t n_dst, float* asum, float* qsum, void* stream);
+int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const int32_t* edge_src,
+                        const int32_t* edge_dst, const int64_t* csc_pos, const int32_t* dst_nid,
+                        const float* q_ij, const float* node_prob, const float* embed_norm,
+                        const float* w_static_csc, const float* a_ij, const float* asum,
+                        const float* qsum, int32_t alpha_mode, float delta, int32_t n_dst,
+                        int64_t n_edges, float* exp3_w_csc /* NULL: only emit */,
+                        float* rewards /* [E_b] or NULL */,
+                        float* x_out /* [E_b] clamped exponent, or NULL */,
+                        double* l1_delta /* [1] accumulated sum(w_new - w_old), or NULL */,
+                        void* stream);
+/* apply gathered updates from other ranks: w[pos[k]] *= exp(x[k]) */
+int bliss_apply_updates(const int64_t* pos, const float* x, int64_t n, float* exp3_w_csc,
+                        double* l1_delta, void* stream);
+/* literal F.normalize(p=1) of one layer's weights (bandit_sampler.py:249): two launches. */
+int bliss_l1_norm(const float* w, int64_t n, double* partial /* [1024] */, double* out /* [1] */,
+                  void* stream);
+int bliss_scale_by_inv(float* w, int64_t n, const double* norm, double eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLISS_B200_H */

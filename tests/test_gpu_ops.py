@@ -1,0 +1,195 @@
+"""GPU parity tests of the aggregation kernels and the drop-in models against the CPU oracle
+(plain torch fp32, autograd for the backward).  Tolerance: 1e-5 relative (north-star; summation
+order differs), measured against the largest magnitude of the compared tensor so cancelling
+sums do not produce false alarms."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import model as omodel
+from oracle import samplers as osamp
+from tests.util import philox_uniform_fn, random_graph
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _close(a, b, rtol=RTOL, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    scale = b.abs().max().clamp(min=1e-30)
+    err = ((a - b).abs().max() / scale).item()
+    assert err <= rtol, f"{what}: max err / max|ref| = {err}"
+
+
+def _sample(model="sage", fan=(128, 64, 32), V=1500, E=9000, batch=24, hubs=3, hub_degree=600):
+    from bliss_gnn_b200.sampler import PoissonBanditLadiesSampler
+    g = random_graph(V, E, seed=13, hubs=hubs, hub_degree=hub_degree)
+    seeds = torch.randperm(V, generator=torch.Generator().manual_seed(2))[:batch]
+    ora = osamp.PoissonBanditLadiesSampler(list(fan), eta=0.1, model=model, accum="contract",
+                                           uniform_fn=philox_uniform_fn(7, 0))
+    _, _, ob = ora.sample_blocks(g, seeds)
+    gd = g.to(_dev())
+    dev = PoissonBanditLadiesSampler(list(fan), eta=0.1, model=model, rng_seed=7)
+    _, _, db = dev.sample_blocks(gd, seeds)
+    return g, gd, ob, db
+
+
+@pytest.mark.parametrize("dim", [1, 7, 41, 64, 256, 602, 1433])
+def test_gather_rows_and_norm(native_lib, dim):
+    from bliss_gnn_b200 import ops
+    dev = _dev()
+    table = torch.randn(1000, dim, device=dev)
+    nid = torch.randint(0, 1000, (333,), device=dev, dtype=torch.int32)
+    out, norm = ops.gather_rows(table, nid, with_norm=True)
+    assert torch.equal(out, table[nid.long()])                      # a copy: bit-exact
+    _close(norm, torch.linalg.norm(table[nid.long()], dim=1), what="row norm")
+    _close(ops.row_norm(table), torch.linalg.norm(table, dim=1), what="row_norm")
+
+
+@pytest.mark.parametrize("dim", [1, 7, 41, 64, 256, 300, 1030])
+def test_spmm_forward_backward(native_lib, dim):
+    from bliss_gnn_b200 import ops
+    g, gd, ob, db = _sample()
+    for blk, oblk in zip(db, ob):
+        x = torch.randn(blk.num_src_nodes(), dim, device=gd.device, requires_grad=True)
+        w = blk.edata["edge_weights"]
+        ss = torch.rand(blk.num_src_nodes(), device=gd.device) + 0.5
+        ds = torch.rand(blk.num_dst_nodes(), device=gd.device) + 0.5
+        y = ops.spmm(blk, x, w, src_scale=ss, dst_scale=ds)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        xr = x.detach().cpu().clone().requires_grad_(True)
+        src, dst = blk.edge_src.cpu().long(), blk.edge_dst.cpu().long()
+        m = xr[src] * (w.cpu() * ss.cpu()[src]).unsqueeze(1)
+        yr = torch.zeros(blk.num_dst_nodes(), dim).index_add(0, dst, m) * ds.cpu().unsqueeze(1)
+        yr.backward(gy.cpu())
+        _close(y, yr, what=f"spmm fwd D={dim}")
+        _close(x.grad, xr.grad, what=f"spmm bwd D={dim}")
+
+
+def test_block_transpose_is_sorted(native_lib):
+    from bliss_gnn_b200 import ops
+    _, gd, _, db = _sample()
+    for blk in db:
+        t_indptr, t_dst, t_perm = ops.block_transpose(blk)
+        assert int(t_indptr[-1]) == blk.num_edges()
+        src_of = blk.edge_src[t_perm.long()]
+        rows = torch.repeat_interleave(torch.arange(blk.num_src_nodes(), device=gd.device),
+                                       (t_indptr[1:] - t_indptr[:-1]).long())
+        assert torch.equal(src_of.long(), rows)                     # grouped by source
+        assert torch.equal(blk.edge_dst[t_perm.long()], t_dst)
+        key = rows * (blk.num_edges() + 1) + t_perm.long()          # ascending edge id inside each row
+        assert torch.all(key[1:] > key[:-1])
+
+
+def _copy_params(dst_model, src_model):
+    sd = {k: v.detach().cpu().clone() for k, v in src_model.state_dict().items()}
+    missing = dst_model.load_state_dict(sd, strict=False)
+    assert not [k for k in missing.missing_keys if "fc_dst" not in k], missing
+
+
+@pytest.mark.parametrize("kind", ["sage", "gcn"])
+def test_sage_gcn_models_forward_backward(native_lib, kind):
+    from bliss_gnn_b200 import model as M
+    g, gd, ob, db = _sample()
+    in_f, hid, ncls = 37, 64, 5          # in < hidden -> aggregate first; hidden > classes -> project first
+    torch.manual_seed(0)
+    feats = torch.randn(g.num_nodes(), in_f)
+    dmodel = (M.SAGE if kind == "sage" else M.GCN)(in_f, hid, ncls, 3, F.relu, 0.0).to(gd.device)
+    omod = (omodel.SAGE if kind == "sage" else omodel.GCN)(in_f, hid, ncls, 3, F.relu, 0.0)
+    _copy_params(omod, dmodel)
+    xd = feats.to(gd.device)[db[0].srcdata["_ID"].long()]
+    xo = feats[ob[0].srcdata["_ID"].long()]
+    yd = dmodel(db, xd)
+    yo = omod(ob, xo)
+    _close(yd, yo, what=f"{kind} logits")
+    for a, b in zip(db, ob):
+        _close(a.srcdata["embed_norm"], b.srcdata["embed_norm"], what="embed_norm")
+    labels = torch.randint(0, ncls, (yo.shape[0],))
+    F.cross_entropy(yd, labels.to(gd.device)).backward()
+    F.cross_entropy(yo, labels).backward()
+    for (n, p), (_, q) in zip(dmodel.named_parameters(), omod.named_parameters()):
+        _close(p.grad, q.grad, rtol=5e-5, what=f"{kind} grad {n}")
+
+
+@pytest.mark.parametrize("residual", [False, True])
+def test_gatv2_model_forward_backward(native_lib, residual):
+    from bliss_gnn_b200 import model as M
+    g, gd, ob, db = _sample(model="gat")
+    in_f, hid, ncls, heads = 19, 48, 6, [4, 4, 1]
+    torch.manual_seed(1)
+    feats = torch.randn(g.num_nodes(), in_f)
+    args = (3, in_f, hid, ncls, heads, F.elu, 0.0, 0.0, 0.2, residual)
+    dmodel = M.GATv2(*args).to(gd.device)
+    omod = omodel.GATv2(*args)
+    _copy_params(omod, dmodel)
+    yd = dmodel(db, feats.to(gd.device)[db[0].srcdata["_ID"].long()])
+    yo = omod(ob, feats[ob[0].srcdata["_ID"].long()])
+    _close(yd, yo, what="gat logits")
+    for a, b in zip(db, ob):
+        assert torch.equal(a.edge_src.cpu().long(), b.src)          # same native edge order
+        _close(a.edata["a_ij"], b.edata["a_ij"], what="a_ij (head-mean logits)")
+    labels = torch.randint(0, ncls, (yo.shape[0],))
+    F.cross_entropy(yd, labels.to(gd.device)).backward()
+    F.cross_entropy(yo, labels).backward()
+    dgrads = dict(dmodel.named_parameters())
+    for n, q in omod.named_parameters():
+        _close(dgrads[n].grad, q.grad, rtol=5e-5, what=f"gat grad {n}")
+
+
+def test_gatv2_attention_dropout_mask(native_lib):
+    """attn_drop (model.py:88-90) enters the fused kernel as a pre-scaled keep mask."""
+    from bliss_gnn_b200 import ops
+    from oracle import dglops
+    _, gd, ob, db = _sample(model="gat")
+    blk, oblk = db[0], ob[0]
+    H, D = 2, 40
+    torch.manual_seed(3)
+    feat = torch.randn(blk.num_src_nodes(), H, D)
+    attn = torch.randn(1, H, D)
+    mask = (torch.rand(blk.num_edges(), H) < 0.8).float() / 0.8
+    fd = feat.to(gd.device).requires_grad_(True)
+    ad = attn.to(gd.device).requires_grad_(True)
+    out, logits = ops.gatv2_attention(blk, fd, ad, 0.2, mask.to(gd.device))
+    fo, ao = feat.clone().requires_grad_(True), attn.clone().requires_grad_(True)
+    e = F.leaky_relu(fo[oblk.src] + fo[: oblk.num_dst_nodes()][oblk.dst], 0.2)
+    e = (e * ao).sum(-1)
+    a = dglops.edge_softmax(oblk, e) * mask
+    ref = torch.zeros(oblk.num_dst_nodes(), H, D).index_add(0, oblk.dst, fo[oblk.src] * a.unsqueeze(-1))
+    _close(out, ref, what="gat out with dropout mask")
+    _close(logits, e, what="gat logits")
+    go = torch.randn_like(ref)
+    out.backward(go.to(gd.device))
+    ref.backward(go)
+    _close(fd.grad, fo.grad, rtol=5e-5, what="gat grad feat")
+    _close(ad.grad, ao.grad, rtol=5e-5, what="gat grad attn")
+
+
+def test_full_graph_inference(native_lib):
+    """model.inference: layer-wise full-neighbour pass (model.py:335-383) == oracle on the whole graph."""
+    from bliss_gnn_b200 import model as M
+    from oracle import dglops
+    g = random_graph(700, 4000, seed=4)
+    feats = torch.randn(700, 24, generator=torch.Generator().manual_seed(5))
+    g.ndata["features"] = feats
+    gd = g.to(_dev())
+    dmodel = M.SAGE(24, 32, 4, 3, F.relu, 0.0).to(gd.device)
+    omod = omodel.SAGE(24, 32, 4, 3, F.relu, 0.0)
+    _copy_params(omod, dmodel)
+    pred = dmodel.inference(gd, gd.device, 128)
+    src, dst = g.coo()
+    order = torch.sort(dst, stable=True).indices
+    full = dglops.OBlock(src[order], dst[order], 700, 700)
+    h = feats
+    with torch.no_grad():
+        for l, layer in enumerate(omod.layers):
+            h = layer(full, h)
+            if l < 2:
+                h = F.relu(h)
+    _close(pred, h, what="full-graph inference")

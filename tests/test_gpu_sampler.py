@@ -1,0 +1,254 @@
+"""GPU parity tests of the sampling path (C ABI kernels) against the CPU oracle.
+
+Bar (north-star): sampled node sets, relabelling, block CSR and edge ids bit-exact given identical
+uniform draws and bandit state; probabilities / weights within 1e-5 relative in fp32 (tolerance
+written at each assert).  Against the oracle's ``accum='contract'`` mode (the device's numeric
+contract) values are expected bit-exact up to 1 ulp in a few entries; against ``accum='native'``
+(torch-order sums) the tie band around P is excluded by the draw generator (tests/util.SafeDraws).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import samplers as osamp
+from oracle import philox
+from tests.util import SafeDraws, assert_blocks_equal, philox_uniform_fn, random_graph
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "toy_kat.json")
+RTOL = 1e-5   # north-star tolerance for fp32 values
+
+
+def _dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _device_sampler(cls_name, fanouts, **kw):
+    from bliss_gnn_b200 import sampler as S
+    return getattr(S, cls_name)(fanouts, **kw)
+
+
+def test_philox_matches_oracle(native_lib):
+    from bliss_gnn_b200 import _native as N
+    dev = _dev()
+    nids = torch.arange(0, 5000, 7, dtype=torch.int32, device=dev)
+    out = torch.empty(nids.numel(), dtype=torch.float32, device=dev)
+    seed, step, layer = 0x1234_5678_9ABC_DEF0, (1 << 33) + 5, 2
+    N.check(native_lib.bliss_philox_fill(seed, step, layer, N.ptr(nids), nids.numel(), N.ptr(out), N.stream()), "philox")
+    ref = philox.uniform_for_nodes(seed, step, layer, nids.cpu().numpy())
+    assert np.array_equal(out.cpu().numpy(), ref)          # bit-exact
+    assert ref.min() >= 0.0 and ref.max() < 1.0
+
+
+def test_toy_known_answer(native_lib):
+    """The hand-derived toy vector (tests/golden/toy_kat.json) through the device path."""
+    from bliss_gnn_b200.graph import toy_graph, normalized_edata
+    kat = json.load(open(GOLDEN))
+    g = toy_graph()
+    g.edata["w"] = normalized_edata(g)
+    g = g.to(_dev())
+    s = _device_sampler("PoissonBanditLadiesSampler", [kat["fanout"]], eta=kat["eta"])
+    s.inject_uniforms = torch.tensor(kat["u_inject"], dtype=torch.float32, device=g.device)
+    inp, outn, blocks = s.sample_blocks(g, torch.tensor(kat["seeds"]))
+    b = blocks[0]
+    kb = kat["block"]
+    assert b.srcdata["_ID"].tolist() == kb["src_nid"] and inp.tolist() == kb["src_nid"]
+    assert b.dstdata["_ID"].tolist() == kb["dst_nid"] and outn.tolist() == kb["dst_nid"]
+    assert b.edge_src.tolist() == kb["edge_src_local"]      # insg-filtered order == native order
+    assert b.edge_dst.tolist() == kb["edge_dst_local"]
+    assert b.edata["_ID"].tolist() == kb["eid"]
+    ctr = s.last_counters[0]
+    assert abs(ctr.c - kat["c"]) <= 1e-6 * kat["c"] and ctr.iters == kat["iters"]
+    np.testing.assert_allclose(b.edata["q_ij"].cpu().numpy(), kb["q_ij"], rtol=RTOL)
+    np.testing.assert_allclose(b.edata["edge_weights"].cpu().numpy(), kb["edge_weights"], rtol=RTOL)
+    np.testing.assert_allclose(b.srcdata["node_prob"].cpu().numpy(), kb["node_prob"], rtol=RTOL)
+    np.testing.assert_allclose(b.edata["w"].cpu().numpy(), [kat["w_static"][e] for e in kb["eid"]], rtol=1e-6)
+    b.srcdata["embed_norm"] = torch.ones(b.num_src_nodes(), device=g.device)
+    s.calculate_rewards(0, b, g, s.calculate_alpha(b))
+    np.testing.assert_allclose(b.edata["rewards"].cpu().numpy(), kat["rewards"], rtol=RTOL)
+    s.exp3(blocks, g)
+    np.testing.assert_allclose(s.exp3_weights[0].cpu().numpy(), kat["exp3_after"], rtol=RTOL)
+
+
+GRAPHS = {
+    # name: (nodes, edges, hubs, hub_degree, batch, fanouts)
+    "light": (400, 1500, 0, 0, 16, [64, 32, 16]),                 # every row handled by a warp
+    "heavy": (3000, 20000, 6, 1500, 48, [512, 256, 128]),         # CTA rows staged in shared memory
+    "huge_row": (12000, 30000, 2, 9500, 32, [1024, 512, 64]),     # rows beyond the 8192-float stage
+}
+
+
+def _oracle_and_device(gname, cls_name, accum, step=3, seed=11, eta=0.1, draws="philox", **kw):
+    V, E, hubs, hdeg, batch, fan = GRAPHS[gname]
+    g = random_graph(V, E, seed=5, hubs=hubs, hub_degree=hdeg)
+    seeds = torch.randperm(V, generator=torch.Generator().manual_seed(1))[:batch]
+    if hubs:
+        seeds[:hubs] = torch.arange(hubs)       # make sure the hub rows are in the first frontier
+    is_bandit = "Bandit" in cls_name
+    okw = dict(eta=eta) if is_bandit else {}
+    safe = SafeDraws(V, seed, step) if draws == "safe" else None
+    ora = getattr(osamp, cls_name)(fan, accum=accum, uniform_fn=safe or philox_uniform_fn(seed, step), **okw, **kw)
+    o_in, o_out, o_blocks = ora.sample_blocks(g, seeds)
+    gd = g.to(_dev())
+    dev = _device_sampler(cls_name, fan, rng_seed=seed, **okw, **kw)
+    dev.step = step
+    if safe is not None:
+        dev.inject_uniforms = {l: u.to(gd.device) for l, u in safe.per_layer.items()}
+    d_in, d_out, d_blocks = dev.sample_blocks(gd, seeds)
+    return g, gd, ora, dev, (o_in, o_out, o_blocks), (d_in, d_out, d_blocks)
+
+
+@pytest.mark.parametrize("gname", list(GRAPHS))
+def test_poisson_bandit_contract_parity(native_lib, gname):
+    """Device vs oracle under the same numeric contract: structure bit-exact, values ~1 ulp."""
+    g, gd, ora, dev, (o_in, _, o_blocks), (d_in, d_out, d_blocks) = _oracle_and_device(
+        gname, "PoissonBanditLadiesSampler", "contract")
+    assert torch.equal(d_in.cpu().long(), o_in)
+    for l, (db, ob) in enumerate(zip(d_blocks, o_blocks)):
+        st = assert_blocks_equal(db, ob, rtol=1e-6)
+        ctr = dev.last_counters[l]
+        assert ctr.n_cand == ora.trace["prob"][l][0].numel()
+        if l in ora.trace.get("c", {}):
+            c, it = ora.trace["c"][l]
+            # fp64 row sums are order-dependent in their last bits: a few p differ by 1 ulp -> c by ~1e-9
+            assert ctr.iters == it and abs(ctr.c - c) <= 1e-7 * c
+        else:
+            assert ctr.take_all == 1
+        # row sums of the normalised block weights equal the kept in-degree (bandit_sampler.py:316-320)
+        rs = torch.zeros(db.num_dst_nodes(), dtype=torch.float64, device=gd.device).index_add_(
+            0, db.edge_dst.long(), db.edata["edge_weights"].double())
+        torch.testing.assert_close(rs, db.in_degrees().double(), rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("gname", ["light", "heavy"])
+def test_poisson_bandit_native_parity_safe_draws(native_lib, gname):
+    """Device vs the torch-order oracle: sets bit-exact once ties are excluded, values within 1e-5."""
+    *_, (o_in, _, o_blocks), (d_in, _, d_blocks) = _oracle_and_device(
+        gname, "PoissonBanditLadiesSampler", "native", draws="safe")
+    assert torch.equal(d_in.cpu().long(), o_in)
+    for db, ob in zip(d_blocks, o_blocks):
+        assert_blocks_equal(db, ob, rtol=RTOL)
+
+
+@pytest.mark.parametrize("cls_name", ["PoissonLadiesSampler", "LadiesSampler", "BanditLadiesSampler"])
+@pytest.mark.parametrize("gname", ["light", "heavy"])
+def test_other_samplers_parity(native_lib, cls_name, gname):
+    *_, (o_in, _, o_blocks), (d_in, _, d_blocks) = _oracle_and_device(gname, cls_name, "contract")
+    assert torch.equal(d_in.cpu().long(), o_in)
+    for db, ob in zip(d_blocks, o_blocks):
+        assert_blocks_equal(db, ob, rtol=RTOL, check=("edge_weights", "q_ij"))
+        if "Bandit" not in cls_name:
+            assert "q_ij" not in dict.keys(db.edata)        # ladies_sampler.py:99-106 attaches neither
+            assert "node_prob" not in dict.keys(db.srcdata)
+
+
+def test_take_all_branch(native_lib):
+    """N_c <= fanout: P = 1 for every candidate, block = full in-neighbourhood (bandit_sampler.py:392-393)."""
+    g = random_graph(300, 900, seed=2)
+    seeds = torch.arange(0, 40)
+    dev = _device_sampler("PoissonBanditLadiesSampler", [100000], eta=0.1)
+    gd = g.to(_dev())
+    _, _, blocks = dev.sample_blocks(gd, seeds)
+    b = blocks[0]
+    assert dev.last_counters[0].take_all == 1
+    assert b.num_edges() == int(g.in_degrees(seeds).sum())
+    assert torch.all(b.srcdata["node_prob"] == 1)
+    ora = osamp.PoissonBanditLadiesSampler([100000], eta=0.1, accum="contract", uniform_fn=philox_uniform_fn(0, 0))
+    _, _, ob = ora.sample_blocks(g, seeds)
+    assert_blocks_equal(b, ob[0], rtol=1e-6)
+
+
+def test_importance_sampling_off(native_lib):
+    g = random_graph(500, 3000, seed=8)
+    seeds = torch.arange(10, 40)
+    kw = dict(eta=0.2, importance_sampling=False)
+    ora = osamp.PoissonBanditLadiesSampler([64, 32], accum="contract", uniform_fn=philox_uniform_fn(4, 0), **kw)
+    _, _, ob = ora.sample_blocks(g, seeds)
+    dev = _device_sampler("PoissonBanditLadiesSampler", [64, 32], rng_seed=4, **kw)
+    _, _, db = dev.sample_blocks(g.to(_dev()), seeds)
+    for a, b in zip(db, ob):
+        assert_blocks_equal(a, b, rtol=RTOL)
+
+
+def test_workspace_invariant_and_determinism(native_lib):
+    g = random_graph(3000, 20000, seed=5, hubs=4, hub_degree=1200).to(_dev())
+    seeds = torch.arange(0, 64)
+    dev = _device_sampler("PoissonBanditLadiesSampler", [256, 128, 64], eta=0.1, rng_seed=3)
+    _, _, b1 = dev.sample_blocks(g, seeds)
+    w = dev._wsp
+    assert int(w.acc.count_nonzero()) == 0 and int((w.first_pos != -1).sum()) == 0
+    assert int((w.node_info[0::2] != -1).sum()) == 0 and int(w.sel_bits.count_nonzero()) == 0
+    dev.step = 0                       # same Philox counters -> identical blocks, bit for bit
+    _, _, b2 = dev.sample_blocks(g, seeds)
+    for x, y in zip(b1, b2):
+        assert torch.equal(x.edge_src, y.edge_src) and torch.equal(x.indptr, y.indptr)
+        assert torch.equal(x.edata["edge_weights"], y.edata["edge_weights"])
+        assert torch.equal(x.srcdata["node_prob"], y.srcdata["node_prob"])
+    dev.step = 1
+    _, _, b3 = dev.sample_blocks(g, seeds)
+    assert not torch.equal(b1[0].srcdata["_ID"], b3[0].srcdata["_ID"]) or b1[0].num_src_nodes() != b3[0].num_src_nodes()
+
+
+@pytest.mark.parametrize("normalize", ["lazy", "literal"])
+def test_exp3_update_parity_three_steps(native_lib, normalize):
+    """sample → (fake forward: embed_norm) → exp3, three times; bandit weights within 1e-5 of the oracle."""
+    V, E, hubs, hdeg, batch, fan = GRAPHS["heavy"]
+    g = random_graph(V, E, seed=5, hubs=hubs, hub_degree=hdeg)
+    gd = g.to(_dev())
+    seed = 21
+    ora = osamp.PoissonBanditLadiesSampler(fan, eta=0.1, accum="contract")
+    dev = _device_sampler("PoissonBanditLadiesSampler", fan, eta=0.1, rng_seed=seed, normalize=normalize)
+    gen = torch.Generator().manual_seed(0)
+    for step in range(3):
+        seeds = torch.randperm(V, generator=gen)[:batch]
+        ora.uniform_fn = philox_uniform_fn(seed, step)
+        _, _, ob = ora.sample_blocks(g, seeds)
+        _, _, db = dev.sample_blocks(gd, seeds)
+        for a, b in zip(db, ob):
+            assert_blocks_equal(a, b, rtol=RTOL)
+            emb = torch.rand(b.num_src_nodes(), generator=gen) * 3 + 0.1
+            b.srcdata["embed_norm"] = emb
+            a.srcdata["embed_norm"] = emb.to(gd.device)
+        ora.exp3(ob, g)
+        dev.exp3(db, gd)
+        w_dev = dev.exp3_weights.cpu().double()
+        w_ora = ora.exp3_weights.double()
+        rel = ((w_dev - w_ora).abs() / w_ora).max().item()
+        assert rel <= RTOL, f"step {step}: exp3 weights max rel err {rel}"
+        torch.testing.assert_close(w_dev.sum(dim=1), torch.ones(3, dtype=torch.float64), rtol=1e-6, atol=0)
+
+
+def test_gat_alpha_rewards(native_lib):
+    """GAT alpha path of the bandit (bandit_sampler.py:146-154) with random a_ij."""
+    g = random_graph(800, 5000, seed=9)
+    gd = g.to(_dev())
+    seeds = torch.arange(0, 32)
+    ora = osamp.PoissonBanditLadiesSampler([128, 64], eta=0.1, model="gat", accum="contract",
+                                           uniform_fn=philox_uniform_fn(2, 0))
+    dev = _device_sampler("PoissonBanditLadiesSampler", [128, 64], eta=0.1, model="gat", rng_seed=2)
+    _, _, ob = ora.sample_blocks(g, seeds)
+    _, _, db = dev.sample_blocks(gd, seeds)
+    gen = torch.Generator().manual_seed(3)
+    for a, b in zip(db, ob):
+        assert_blocks_equal(a, b, rtol=RTOL)
+        emb = torch.rand(b.num_src_nodes(), generator=gen) + 0.5
+        att = torch.randn(b.num_edges(), generator=gen)
+        b.srcdata["embed_norm"], b.edata["a_ij"] = emb, att
+        # the device block's native edge order equals the oracle's (insg order filtered)
+        assert torch.equal(a.edge_src.cpu().long(), b.src)
+        a.srcdata["embed_norm"], a.edata["a_ij"] = emb.to(gd.device), att.to(gd.device)
+    for l, (a, b) in enumerate(zip(db, ob)):
+        al = ora.calculate_alpha(b)
+        ora.calculate_rewards(l, b, g, al)
+        dev.calculate_rewards(l, a, gd, dev.calculate_alpha(a))
+        r_d, r_o = a.edata["rewards"].cpu().double(), b.edata["rewards"].double()
+        # sums of signed attention logits cancel: compare with an absolute floor
+        assert ((r_d - r_o).abs() <= 1e-4 * r_o.abs() + 1e-9).all()
+    ora.exp3(ob, g)
+    dev.exp3(db, gd)
+    w_dev, w_ora = dev.exp3_weights.cpu().double(), ora.exp3_weights.double()
+    assert ((w_dev - w_ora).abs() / w_ora).max().item() <= 1e-4
