@@ -148,6 +148,47 @@ class BlissNativeError(RuntimeError):
     pass
 
 
+#: kernels each entry point launches (for the ``gpu_launches`` count of bench.py)
+LAUNCHES = {"bliss_select_topk": 3, "bliss_block_transpose": 4, "bliss_l1_norm": 2, "bliss_version": 0}
+
+
+class _Stats:
+    """Launch counter and optional per-entry-point CUDA-event timing (bench.py roofline)."""
+
+    def __init__(self):
+        self.launches = 0
+        self.timing = False
+        self.events = {}
+
+    def reset(self, timing=False):
+        self.launches = 0
+        self.timing = timing
+        self.events = {}
+
+    def elapsed_ms(self):
+        """{entry point: (calls, total ms)} — call after a synchronize."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.events.items()}
+
+
+STATS = _Stats()
+
+
+def call(name: str, *args):
+    """Invoke one C-ABI entry point on the current stream; raises on any non-zero return."""
+    fn = getattr(lib(), name)
+    if STATS.timing:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        STATS.events.setdefault(name, []).append((e0, e1))
+    else:
+        rc = fn(*args)
+    STATS.launches += LAUNCHES.get(name, 1)
+    check(rc, name)
+
+
 def check(rc: int, what: str):
     if rc != 0:
         kind = "bad argument" if rc < 0 else "cudaError"

@@ -126,6 +126,9 @@ class Graph:
             g.ndata[k] = v.to(device)
         for k, v in self.edata.items():
             g.edata[k] = v.to(device)
+        for attr in ("n_classes", "multilabel"):
+            if hasattr(self, attr):
+                setattr(g, attr, getattr(self, attr))
         return g
 
     def int(self) -> "Graph":

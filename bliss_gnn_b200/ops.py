@@ -34,8 +34,7 @@ def gather_rows(table: torch.Tensor, nid: torch.Tensor, with_norm: bool = False)
     n, d = nid.numel(), table.shape[1]
     out = torch.empty((n, d), dtype=torch.float32, device=table.device)
     norm = torch.empty(n, dtype=torch.float32, device=table.device) if with_norm else None
-    N.check(N.lib().bliss_gather_rows(N.ptr(table), N.ptr(nid), n, d, N.ptr(out), N.ptr(norm), N.stream()),
-            "bliss_gather_rows")
+    N.call("bliss_gather_rows", N.ptr(table), N.ptr(nid), n, d, N.ptr(out), N.ptr(norm), N.stream())
     return (out, norm) if with_norm else out
 
 
@@ -44,7 +43,7 @@ def row_norm(x: torch.Tensor) -> torch.Tensor:
     x = _req(x.detach(), name="x")
     x2 = x.reshape(x.shape[0], -1)
     out = torch.empty(x2.shape[0], dtype=torch.float32, device=x.device)
-    N.check(N.lib().bliss_row_norm(N.ptr(x2), x2.shape[0], x2.shape[1], N.ptr(out), N.stream()), "bliss_row_norm")
+    N.call("bliss_row_norm", N.ptr(x2), x2.shape[0], x2.shape[1], N.ptr(out), N.stream())
     return out
 
 
@@ -58,9 +57,9 @@ def block_transpose(block):
         t_scratch = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         t_dst = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         t_perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
-        N.check(N.lib().bliss_block_transpose(N.ptr(block.edge_src), N.ptr(block.edge_dst), E, n_src, n_dst,
+        N.call("bliss_block_transpose", N.ptr(block.edge_src), N.ptr(block.edge_dst), E, n_src, n_dst,
                                               N.ptr(t_indptr), N.ptr(t_cursor), N.ptr(t_scratch), N.ptr(t_dst),
-                                              N.ptr(t_perm), N.stream()), "bliss_block_transpose")
+                                              N.ptr(t_perm), N.stream())
         block._transpose = (t_indptr, t_dst[:E], t_perm[:E])
     return block._transpose
 
@@ -68,8 +67,8 @@ def block_transpose(block):
 def _spmm_raw(indptr, col, perm, w, sscale, dscale, agg, x, n_rows):
     d = x.shape[1]
     y = torch.empty((n_rows, d), dtype=torch.float32, device=x.device)
-    N.check(N.lib().bliss_spmm(N.ptr(indptr), N.ptr(col), N.ptr(perm), N.ptr(w), N.ptr(sscale), N.ptr(dscale),
-                               agg, N.ptr(x), n_rows, d, N.ptr(y), N.stream()), "bliss_spmm")
+    N.call("bliss_spmm", N.ptr(indptr), N.ptr(col), N.ptr(perm), N.ptr(w), N.ptr(sscale), N.ptr(dscale),
+                               agg, N.ptr(x), n_rows, d, N.ptr(y), N.stream())
     return y
 
 
@@ -123,9 +122,9 @@ class _GATv2(torch.autograd.Function):
         logits = torch.empty((E, H), dtype=torch.float32, device=dev)
         rmax = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
         rsum = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
-        N.check(N.lib().bliss_gatv2_fwd(N.ptr(block.indptr), N.ptr(block.edge_src), N.ptr(feat), N.ptr(attn_c),
+        N.call("bliss_gatv2_fwd", N.ptr(block.indptr), N.ptr(block.edge_src), N.ptr(feat), N.ptr(attn_c),
                                         N.ptr(drop_mask), slope, n_dst, H, D, N.ptr(out), N.ptr(logits),
-                                        N.ptr(rmax), N.ptr(rsum), N.stream()), "bliss_gatv2_fwd")
+                                        N.ptr(rmax), N.ptr(rsum), N.stream())
         ctx.save_for_backward(feat, attn_c, logits, rmax, rsum, out)
         ctx.block, ctx.drop_mask, ctx.slope, ctx.attn_shape = block, drop_mask, slope, attn.shape
         ctx.mark_non_differentiable(logits)
@@ -143,15 +142,14 @@ class _GATv2(torch.autograd.Function):
         gattn = torch.zeros_like(attn_c)
         glogit = torch.empty((max(E, 1), H), dtype=torch.float32, device=dev)
         L = N.lib()
-        N.check(L.bliss_gatv2_bwd_dst(N.ptr(block.indptr), N.ptr(block.edge_src), N.ptr(feat), N.ptr(attn_c),
+        N.call("bliss_gatv2_bwd_dst", N.ptr(block.indptr), N.ptr(block.edge_src), N.ptr(feat), N.ptr(attn_c),
                                       N.ptr(mask), N.ptr(logits), N.ptr(rmax), N.ptr(rsum), N.ptr(out),
                                       N.ptr(gout), slope, n_dst, H, D, N.ptr(glogit), N.ptr(gfeat),
-                                      N.ptr(gattn), N.stream()), "bliss_gatv2_bwd_dst")
+                                      N.ptr(gattn), N.stream())
         t_indptr, t_dst, t_perm = block_transpose(block)
-        N.check(L.bliss_gatv2_bwd_src(N.ptr(t_indptr), N.ptr(t_dst), N.ptr(t_perm), N.ptr(feat), N.ptr(attn_c),
+        N.call("bliss_gatv2_bwd_src", N.ptr(t_indptr), N.ptr(t_dst), N.ptr(t_perm), N.ptr(feat), N.ptr(attn_c),
                                       N.ptr(mask), N.ptr(logits), N.ptr(rmax), N.ptr(rsum), N.ptr(gout),
-                                      N.ptr(glogit), slope, n_src, n_dst, H, D, N.ptr(gfeat), N.stream()),
-                "bliss_gatv2_bwd_src")
+                                      N.ptr(glogit), slope, n_src, n_dst, H, D, N.ptr(gfeat), N.stream())
         return gfeat, gattn.reshape(ctx.attn_shape), None, None, None
 
 

@@ -63,7 +63,7 @@ class _Workspace:
         self.gview = N.Graph(num_nodes=V, num_edges=g.num_edges(), indptr=N.ptr(g.indptr),
                              indices=N.ptr(g.indices), eid=N.ptr(g.eid))
         self._keep = (g.indptr, g.indices, g.eid)
-        N.check(N.lib().bliss_workspace_init(C.byref(self.ws), V, N.stream()), "bliss_workspace_init")
+        N.call("bliss_workspace_init", C.byref(self.ws), V, N.stream())
 
     def read_counters(self) -> N.Counters:
         self.ctr_host.copy_(self.ctr, non_blocking=True)
@@ -189,22 +189,20 @@ class BanditLadiesSampler:
         wsp = self._bind(g)
         n = int(seed_nodes.numel())
         fr = Frontier(g, wsp, seed_nodes, n, idx, self._mode, self._w_csc[idx])
-        N.check(N.lib().bliss_frontier_plan(C.byref(wsp.gview), N.ptr(seed_nodes), n, C.byref(wsp.ws), N.stream()),
-                "bliss_frontier_plan")
+        N.call("bliss_frontier_plan", C.byref(wsp.gview), N.ptr(seed_nodes), n, C.byref(wsp.ws), N.stream())
         return fr, fr
 
     # ---- stage 2: node probabilities ---------------------------------------------------------
     def _frontier_prob(self, fr: Frontier):
         mode = fr.mode | (0 if self.importance_sampling else N.MODE_UNIFORM)
-        N.check(N.lib().bliss_frontier_prob(C.byref(fr.wsp.gview), N.ptr(fr.seeds), fr.n_seeds, N.ptr(fr.weights),
-                                            float(self.eta), mode, C.byref(fr.wsp.ws), N.stream()),
-                "bliss_frontier_prob")
+        N.call("bliss_frontier_prob", C.byref(fr.wsp.gview), N.ptr(fr.seeds), fr.n_seeds, N.ptr(fr.weights),
+                                            float(self.eta), mode, C.byref(fr.wsp.ws), N.stream())
 
     def compute_prob(self, insg: Frontier, seed_nodes, edge_prob, num):
         """``bandit_sampler.py:47-82`` (+ the Poisson scale search ``:381-406`` in the subclass)."""
         self._frontier_prob(insg)
-        N.check(N.lib().bliss_poisson_scale(insg.n_seeds, int(num), float(self.eps), int(self._poisson),
-                                            C.byref(insg.wsp.ws), N.stream()), "bliss_poisson_scale")
+        N.call("bliss_poisson_scale", insg.n_seeds, int(num), float(self.eps), int(self._poisson),
+                                            C.byref(insg.wsp.ws), N.stream())
         return insg
 
     # ---- stage 3: selection -------------------------------------------------------------------
@@ -223,9 +221,9 @@ class BanditLadiesSampler:
         wsp = prob.wsp
         if wsp.key_scratch is None:
             wsp.key_scratch = torch.empty(prob.g.num_nodes() + 4, dtype=torch.float32, device=prob.g.device)
-        N.check(N.lib().bliss_select_topk(prob.n_seeds, int(num), self.rng_seed, self.step, prob.layer,
+        N.call("bliss_select_topk", prob.n_seeds, int(num), self.rng_seed, self.step, prob.layer,
                                           self._u_ptr(prob.g, prob.layer), N.ptr(wsp.key_scratch), C.byref(wsp.ws),
-                                          N.stream()), "bliss_select_topk")
+                                          N.stream())
         return prob
 
     # ---- stage 4: block construction ------------------------------------------------------------
@@ -238,8 +236,8 @@ class BanditLadiesSampler:
         indptr = torch.empty(n_s + 1, dtype=torch.int32, device=dev)
         out = N.BlockOut(indptr=N.ptr(indptr), src_nid=N.ptr(wsp.src_nid), node_prob=N.ptr(wsp.node_prob),
                          cap_edges=0, cap_src=g.num_nodes())
-        N.check(L.bliss_block_count(C.byref(wsp.gview), N.ptr(fr.seeds), n_s, C.byref(wsp.ws), st), "bliss_block_count")
-        N.check(L.bliss_block_index(N.ptr(fr.seeds), n_s, C.byref(wsp.ws), C.byref(out), st), "bliss_block_index")
+        N.call("bliss_block_count", C.byref(wsp.gview), N.ptr(fr.seeds), n_s, C.byref(wsp.ws), st)
+        N.call("bliss_block_index", N.ptr(fr.seeds), n_s, C.byref(wsp.ws), C.byref(out), st)
         ctr = wsp.read_counters()            # the one host read of this layer: n_src, E_b
         if ctr.error:
             raise RuntimeError(f"BLISS sampler capacity error {ctr.error} in layer {fr.layer}")
@@ -256,9 +254,9 @@ class BanditLadiesSampler:
         out.eid, out.edge_w, out.q_ij = N.ptr(eid), N.ptr(edge_w), N.ptr(q_ij)
         out.cap_edges = E
         if E > 0:
-            N.check(L.bliss_block_fill(C.byref(wsp.gview), N.ptr(fr.seeds), n_s, N.ptr(fr.weights), float(self.eta),
-                                       fr.mode, C.byref(wsp.ws), C.byref(out), st), "bliss_block_fill")
-        N.check(L.bliss_block_finish(n_s, fr.mode, C.byref(wsp.ws), C.byref(out), st), "bliss_block_finish")
+            N.call("bliss_block_fill", C.byref(wsp.gview), N.ptr(fr.seeds), n_s, N.ptr(fr.weights), float(self.eta),
+                                       fr.mode, C.byref(wsp.ws), C.byref(out), st)
+        N.call("bliss_block_finish", n_s, fr.mode, C.byref(wsp.ws), C.byref(out), st)
         src_nid = wsp.src_nid[:n_src].clone()
         block = Block(indptr, edge_src, edge_dst, src_nid, fr.seeds, graph=g, csc_pos=csc_pos)
         block.edata[EID] = eid                                                   # :337
@@ -302,8 +300,8 @@ class BanditLadiesSampler:
             asum = torch.empty(n_dst, dtype=torch.float32, device=mfg.device)
             qsum = torch.empty(n_dst, dtype=torch.float32, device=mfg.device)
             a = mfg.edata["a_ij"].detach().contiguous()
-            N.check(N.lib().bliss_gat_alpha_sums(N.ptr(mfg.indptr), N.ptr(a), N.ptr(mfg.edata["q_ij"]), n_dst,
-                                                 N.ptr(asum), N.ptr(qsum), N.stream()), "bliss_gat_alpha_sums")
+            N.call("bliss_gat_alpha_sums", N.ptr(mfg.indptr), N.ptr(a), N.ptr(mfg.edata["q_ij"]), n_dst,
+                                                 N.ptr(asum), N.ptr(qsum), N.stream())
             return ("gat", a, asum, qsum)
         return ("static", None, None, None)
 
@@ -315,12 +313,12 @@ class BanditLadiesSampler:
         emb = emb.detach()
         if emb.dtype != torch.float32:
             emb = emb.float()
-        N.check(N.lib().bliss_reward_update(
+        N.call("bliss_reward_update", 
             C.byref(wsp.gview), N.ptr(mfg.indptr), N.ptr(mfg.edge_src), N.ptr(mfg.edge_dst), N.ptr(mfg.csc_pos),
             N.ptr(mfg.dstdata[NID]), N.ptr(mfg.edata["q_ij"]), N.ptr(mfg.srcdata[self.node_prob]),
             N.ptr(emb.contiguous()), N.ptr(w_static), N.ptr(a), N.ptr(asum), N.ptr(qsum),
             1 if kind == "gat" else 0, 0.01, mfg.num_dst_nodes(), mfg.num_edges(), N.ptr(weights),
-            N.ptr(rewards), N.ptr(x_out), N.ptr(l1), N.stream()), "bliss_reward_update")
+            N.ptr(rewards), N.ptr(x_out), N.ptr(l1), N.stream())
 
     def calculate_rewards(self, idx, mfg, g, alpha):
         """``bandit_sampler.py:160-193``: stores ``mfg.edata['rewards']`` (emit-only kernel call)."""
@@ -364,17 +362,16 @@ class BanditLadiesSampler:
         dist.all_gather(x_all, x_pad, group=pg)
         for r in range(world):
             if sizes[r]:
-                N.check(N.lib().bliss_apply_updates(N.ptr(pos_all[r]), N.ptr(x_all[r]), sizes[r],
+                N.call("bliss_apply_updates", N.ptr(pos_all[r]), N.ptr(x_all[r]), sizes[r],
                                                     N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]),
-                                                    N.stream()), "bliss_apply_updates")
+                                                    N.stream())
 
     def _renormalize(self, idx):
         w = self._w_csc[idx]
         L = N.lib()
-        N.check(L.bliss_l1_norm(N.ptr(w), w.numel(), N.ptr(self._norm_partial), N.ptr(self._l1[idx:idx + 1]),
-                                N.stream()), "bliss_l1_norm")
-        N.check(L.bliss_scale_by_inv(N.ptr(w), w.numel(), N.ptr(self._l1[idx:idx + 1]), 1e-12, N.stream()),
-                "bliss_scale_by_inv")
+        N.call("bliss_l1_norm", N.ptr(w), w.numel(), N.ptr(self._norm_partial), N.ptr(self._l1[idx:idx + 1]),
+                                N.stream())
+        N.call("bliss_scale_by_inv", N.ptr(w), w.numel(), N.ptr(self._l1[idx:idx + 1]), 1e-12, N.stream())
         self._l1[idx] = 1.0
 
     def exp3(self, mfgs, g):
@@ -398,9 +395,8 @@ class PoissonBanditLadiesSampler(BanditLadiesSampler):
 
     def select_neighbors(self, prob: Frontier, num):
         """``bandit_sampler.py:408-425``: ``bernoulli(P) == 1``  ⇔  ``u < P``."""
-        N.check(N.lib().bliss_select_poisson(prob.n_seeds, self.rng_seed, self.step, prob.layer,
-                                             self._u_ptr(prob.g, prob.layer), C.byref(prob.wsp.ws), N.stream()),
-                "bliss_select_poisson")
+        N.call("bliss_select_poisson", prob.n_seeds, self.rng_seed, self.step, prob.layer,
+                                             self._u_ptr(prob.g, prob.layer), C.byref(prob.wsp.ws), N.stream())
         return prob
 
 
@@ -420,11 +416,10 @@ class LadiesSampler(BanditLadiesSampler):
         wsp = self._bind(g)
         n = int(seed_nodes.numel())
         fr = Frontier(g, wsp, seed_nodes, n, self._layer, N.MODE_LADIES, weight)
-        N.check(N.lib().bliss_frontier_plan(C.byref(wsp.gview), N.ptr(seed_nodes), n, C.byref(wsp.ws), N.stream()),
-                "bliss_frontier_plan")
+        N.call("bliss_frontier_plan", C.byref(wsp.gview), N.ptr(seed_nodes), n, C.byref(wsp.ws), N.stream())
         self._frontier_prob(fr)
-        N.check(N.lib().bliss_poisson_scale(n, int(num), float(self.eps), int(self._poisson), C.byref(wsp.ws),
-                                            N.stream()), "bliss_poisson_scale")
+        N.call("bliss_poisson_scale", n, int(num), float(self.eps), int(self._poisson), C.byref(wsp.ws),
+                                            N.stream())
         return fr, fr
 
     def _attach(self, block, q_ij, node_prob):

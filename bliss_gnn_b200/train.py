@@ -1,0 +1,308 @@
+"""The caller of the hot path: data module, training step and CLI with the reference's flags.
+
+Replaces ``train_lightning.py`` of the reference without Lightning / DGL:
+* :class:`DataModule`  — ``train_lightning.py:307-422``: dataset, self-loops, ``--undirected``, static
+  edge weights ``w``, sampler factory by ``--sampler``, seed-batch iterators (shuffle + drop_last for
+  training, in-order for validation).
+* :class:`Trainer.training_step` — ``train_lightning.py:100-168`` + ``BatchSizeCallback.on_train_batch_end``
+  (``:463-471``): sample → lazy feature / label gather → forward → loss → backward → Adam → ``exp3``.
+* data-parallel over one process per GPU (``torchrun``): every rank samples and aggregates its own
+  seed batches over the replicated graph; NCCL all-reduces one flat gradient buffer and all-gathers
+  the sparse bandit updates (``sampler._update_distributed``).  The reference is single-device.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import time
+from typing import Iterator, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .graph import NID, Graph, add_self_loops_and_build, load_dataset, normalized_edata
+from .model import GCN, SAGE, GATv2
+from .sampler import BanditLadiesSampler, LadiesSampler, PoissonBanditLadiesSampler, PoissonLadiesSampler
+
+
+def make_sampler(name: str, fanouts, importance_sampling=1, eta=0.1, num_steps=-1, model="sage", rng_seed=0,
+                 normalize="lazy"):
+    """Sampler factory with the reference's flag semantics (``train_lightning.py:349-370``)."""
+    if name in ("full", "neighbor"):
+        raise NotImplementedError(f"--sampler {name} is outside the BLISS hot path (SURVEY.md §8f row 4)")
+    if "ladies" in name:
+        return (PoissonLadiesSampler if "poisson" in name else LadiesSampler)(fanouts, rng_seed=rng_seed)
+    if "bandit" in name:
+        cls = PoissonBanditLadiesSampler if "poisson" in name else BanditLadiesSampler
+        return cls(fanouts, importance_sampling=importance_sampling, node_embedding="features",
+                   num_steps=num_steps, eta=eta, model=model, rng_seed=rng_seed, normalize=normalize)
+    raise ValueError(f"unknown sampler {name}")
+
+
+class DataModule:
+    """``train_lightning.py:307-422`` over the plain :class:`Graph` container."""
+
+    def __init__(self, dataset_name, undirected=False, data_cpu=False, use_uva=False, fan_out=(128, 256), eta=0.4,
+                 device=torch.device("cpu"), batch_size=64, num_workers=0, sampler="bandit",
+                 importance_sampling=1, cache_size=0, num_steps=500, model="sage", seed=0, rank=0, world_size=1,
+                 graph: Optional[Graph] = None, normalize="lazy"):
+        self.sampler_name, self.num_steps, self.eta = sampler, num_steps, eta
+        if graph is None:
+            g, n_classes, multilabel = load_dataset(dataset_name, device=device, seed=seed)
+        else:
+            g, n_classes, multilabel = graph, graph.n_classes, graph.multilabel
+        if undirected:                                                           # :337-339
+            src, dst = g.coo()
+            feats = dict(g.ndata)
+            g = add_self_loops_and_build(torch.cat([src, dst]), torch.cat([dst, src]), g.num_nodes())
+            g.ndata.update(feats)
+        g = g.to(device)
+        self.train_nid = torch.nonzero(g.ndata["train_mask"], as_tuple=True)[0].to(torch.int32)   # :344-346
+        self.val_nid = torch.nonzero(g.ndata["val_mask"], as_tuple=True)[0].to(torch.int32)
+        self.test_nid = torch.nonzero(g.ndata["test_mask"], as_tuple=True)[0].to(torch.int32)
+        g.edata["w"] = normalized_edata(g)                                       # :359,362
+        fanouts = [int(_) for _ in fan_out]
+        # every rank draws its own stream: the Philox key carries the rank
+        self.sampler = make_sampler(sampler, fanouts, importance_sampling, eta, num_steps, model,
+                                    rng_seed=(seed + 2) + (rank << 32), normalize=normalize)
+        self.g = g
+        self.device = device
+        self.batch_size = batch_size
+        self.in_feats = g.ndata["features"].shape[1]
+        self.n_classes, self.multilabel = n_classes, multilabel
+        self.rank, self.world_size = rank, world_size
+        self._epoch = 0
+        self._seed = seed + 1
+
+    def train_batches(self) -> Iterator[torch.Tensor]:
+        """shuffle=True, drop_last=True (``:396-408``); rank r takes batches r, r+R, … of the shared
+        epoch permutation."""
+        gen = torch.Generator().manual_seed(self._seed + self._epoch)
+        self._epoch += 1
+        perm = self.train_nid[torch.randperm(self.train_nid.numel(), generator=gen).to(self.train_nid.device)]
+        n_batches = perm.numel() // self.batch_size
+        n_batches -= n_batches % self.world_size
+        for b in range(self.rank, n_batches, self.world_size):
+            yield perm[b * self.batch_size:(b + 1) * self.batch_size]
+
+    def val_batches(self) -> Iterator[torch.Tensor]:
+        """shuffle=False, drop_last=False (``:410-422``)."""
+        for b in range(0, self.val_nid.numel(), self.batch_size):
+            yield self.val_nid[b:b + self.batch_size]
+
+
+def micro_f1(pred: torch.Tensor, labels: torch.Tensor, multilabel: bool) -> float:
+    """torchmetrics Multiclass/MultilabelF1Score(average='micro') (``train_lightning.py:68-72``)."""
+    if multilabel:
+        p = (torch.sigmoid(pred) > 0.5)
+        y = labels > 0.5
+        tp = (p & y).sum().item()
+        return 2 * tp / max(p.sum().item() + y.sum().item(), 1)
+    return (pred.argmax(1) == labels).float().mean().item()
+
+
+def build_model(name: str, in_feats, n_hidden, n_classes, n_layers, dropout=0.1, num_in_heads=4, num_out_heads=1,
+                attn_dropout=0.1, negative_slope=0.2, residual=False, faithful_gcn_quirk=True):
+    """Model factory of ``train_lightning.py:581-618``.  The reference builds a **SAGE** module for
+    ``--model gcn`` (``:597-607``); ``faithful_gcn_quirk=False`` builds the real GCN (``GCNLightning``)."""
+    name = name.lower()
+    if "gat" in name:
+        heads = ([num_in_heads] * (n_layers - 1)) + [num_out_heads]              # :247
+        return GATv2(n_layers, in_feats, n_hidden, n_classes, heads, F.elu, dropout, attn_dropout,
+                     negative_slope, residual)
+    if "gcn" in name and not faithful_gcn_quirk:
+        return GCN(in_feats, n_hidden, n_classes, n_layers, F.relu, dropout)
+    return SAGE(in_feats, n_hidden, n_classes, n_layers, F.relu, dropout)
+
+
+class Trainer:
+    """One training step = the hot path end to end (``train_lightning.py:100-168,463-471``)."""
+
+    def __init__(self, datamodule: DataModule, model: nn.Module, lr=0.002, process_group=None):
+        self.dm, self.model, self.pg = datamodule, model, process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.loss_fn = nn.BCEWithLogitsLoss() if datamodule.multilabel else nn.CrossEntropyLoss()   # :77-79
+        params = [p for p in model.parameters() if p.requires_grad]
+        # one flat gradient buffer: a single all-reduce per step (~0.46 M parameters for SAGE/Reddit)
+        self._flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
+        off = 0
+        for p in params:
+            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        fused = params[0].is_cuda
+        self.optimizer = torch.optim.Adam(params, lr=lr, fused=fused)            # :206
+        self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, gamma=0.01, step_size=5)   # :208 (per epoch)
+        if process_group is not None and hasattr(datamodule.sampler, "process_group"):
+            datamodule.sampler.process_group = process_group
+        self.num_steps = 0
+        self.w = 0.99
+        n_layers = len(datamodule.sampler.nodes_per_layer)
+        self.cum_sampled_nodes = [0.0] * (n_layers + 1)
+        self.cum_sampled_edges = [0.0] * n_layers
+        self.last_blocks = None
+
+    def _ema(self, mfgs):
+        """EMA sampled nodes / edges per layer (``train_lightning.py:104-136``)."""
+        self.num_steps += 1
+        for i, mfg in enumerate(mfgs):
+            self.cum_sampled_nodes[i] = self.cum_sampled_nodes[i] * self.w + mfg.num_src_nodes()
+            self.cum_sampled_edges[i] = self.cum_sampled_edges[i] * self.w + mfg.num_edges()
+        self.cum_sampled_nodes[len(mfgs)] = self.cum_sampled_nodes[len(mfgs)] * self.w + mfgs[-1].num_dst_nodes()
+
+    def num_sampled_edges(self, i):
+        return self.cum_sampled_edges[i] * (1 - self.w) / (1 - self.w ** self.num_steps)
+
+    def num_sampled_nodes(self, i):
+        return self.cum_sampled_nodes[i] * (1 - self.w) / (1 - self.w ** self.num_steps)
+
+    def training_step(self, seeds: torch.Tensor) -> torch.Tensor:
+        dm, g = self.dm, self.dm.g
+        input_nodes, output_nodes, mfgs = dm.sampler.sample_blocks(g, seeds)
+        self._ema(mfgs)
+        batch_inputs = mfgs[0].srcdata["features"]                               # :138  (gather kernel)
+        batch_labels = mfgs[-1].dstdata["labels"]                                # :139
+        batch_pred = self.model(mfgs, batch_inputs)                              # :141
+        loss = self.loss_fn(batch_pred, batch_labels)                            # :142
+        self._flat_grad.zero_()
+        loss.backward()
+        if self.world > 1:
+            torch.distributed.all_reduce(self._flat_grad, group=self.pg)
+            self._flat_grad.div_(self.world)
+        self.optimizer.step()
+        if "bandit" in dm.sampler_name:                                          # :469-471
+            dm.sampler.exp3(mfgs, g)
+        self.last_blocks, self.last_pred, self.last_labels = mfgs, batch_pred, batch_labels
+        return loss
+
+    @torch.no_grad()
+    def validate(self) -> float:
+        """Per-epoch validation with the same stochastic sampler (``train_lightning.py:179-203,410-422``)."""
+        self.model.eval()
+        correct, total = 0.0, 0
+        for seeds in self.dm.val_batches():
+            _, _, mfgs = self.dm.sampler.sample_blocks(self.dm.g, seeds)
+            pred = self.model(mfgs, mfgs[0].srcdata["features"])
+            y = mfgs[-1].dstdata["labels"]
+            correct += micro_f1(pred, y, self.dm.multilabel) * y.shape[0]
+            total += y.shape[0]
+        self.model.train()
+        return correct / max(total, 1)
+
+
+def build_argparser() -> argparse.ArgumentParser:
+    """The reference's 30 flags, names and defaults verbatim (``train_lightning.py:489-552``), plus
+    ``--seed`` and ``--normalize``; ``--dataset`` also accepts ``synthetic:<name>[:scale]``."""
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpu", type=int, default=0 if torch.cuda.is_available() else -1)
+    ap.add_argument("--model", type=str, default="sage", choices=["sage", "gcn", "gat"])
+    ap.add_argument("--dataset", type=str, default="cora")
+    ap.add_argument("--num-epochs", type=int, default=-1)
+    ap.add_argument("--num-steps", type=int, default=-1)
+    ap.add_argument("--min-steps", type=int, default=0)
+    ap.add_argument("--num-hidden", type=int, default=256)
+    ap.add_argument("--num-layers", type=int, default=3)
+    ap.add_argument("--num-in-heads", type=int, default=4)
+    ap.add_argument("--num-out-heads", type=int, default=1)
+    ap.add_argument("--attn-dropout", type=float, default=0.1)
+    ap.add_argument("--negative-slope", type=float, default=0.2)
+    ap.add_argument("--residual", action="store_true", default=False)
+    ap.add_argument("--allow-zero-in-degree", action="store_true", default=False)
+    ap.add_argument("--fan-out", type=str, default="16384,8192,4096")
+    ap.add_argument("--eta", type=float, default=0.1)
+    ap.add_argument("--batch-size", type=int, default=1024)
+    ap.add_argument("--lr", type=float, default=0.002)
+    ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--num-workers", type=int, default=0)
+    ap.add_argument("--data-cpu", action="store_true")
+    ap.add_argument("--sampler", type=str, default="poisson-bandit",
+                    choices=["full", "neighbor", "bandit", "poisson-bandit", "ladies", "poisson-ladies"])
+    ap.add_argument("--importance-sampling", type=int, default=1)
+    ap.add_argument("--logdir", type=str, default="tb_logs")
+    ap.add_argument("--vertex-limit", type=int, default=-1)
+    ap.add_argument("--use-uva", action="store_true")
+    ap.add_argument("--cache-size", type=int, default=0)
+    ap.add_argument("--undirected", action="store_true")
+    ap.add_argument("--val-acc-target", type=float, default=1)
+    ap.add_argument("--early-stopping-patience", type=int, default=1000)
+    ap.add_argument("--disable-checkpoint", action="store_true")
+    ap.add_argument("--precision", type=str, default="medium")
+    ap.add_argument("--k-runs", type=int, default=1)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--normalize", type=str, default="lazy", choices=["lazy", "literal"])
+    return ap
+
+
+def main(argv=None):
+    args = build_argparser().parse_args(argv)
+    if args.gpu < 0 or not torch.cuda.is_available():
+        raise SystemExit("this build runs the BLISS hot path on a CUDA device only (--gpu >= 0); "
+                         "the CPU restatement lives in oracle/ and is test infrastructure")
+    if args.precision != "highest":
+        torch.set_float32_matmul_precision(args.precision)                       # :554-555
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", args.gpu))
+    pg = None
+    if world > 1:
+        torch.distributed.init_process_group("nccl")
+        pg = torch.distributed.group.WORLD
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    results = []
+    for run in range(args.k_runs):                                               # :562
+        if rank == 0:
+            print("=" * 20 + f"run_{run + 1} for eta_{args.eta}" + "=" * 20)
+        dm = DataModule(args.dataset, args.undirected, args.data_cpu, args.use_uva,
+                        [int(_) for _ in args.fan_out.split(",")], args.eta, device, args.batch_size,
+                        args.num_workers, args.sampler, args.importance_sampling, args.cache_size, args.num_steps,
+                        args.model, seed=args.seed + run, rank=rank, world_size=world, normalize=args.normalize)
+        torch.manual_seed(args.seed + 3 + run)
+        model = build_model(args.model, dm.in_feats, args.num_hidden, dm.n_classes, args.num_layers, args.dropout,
+                            args.num_in_heads, args.num_out_heads, args.attn_dropout, args.negative_slope,
+                            args.residual).to(device)
+        tr = Trainer(dm, model, args.lr, pg)
+        step, epoch, best_val, done = 0, 0, -1.0, False
+        t_prev = time.time()
+        while not done:
+            for seeds in dm.train_batches():
+                loss = tr.training_step(seeds)
+                step += 1
+                if rank == 0 and (step % 50 == 0 or step == 1):
+                    acc = micro_f1(tr.last_pred.detach(), tr.last_labels, dm.multilabel)
+                    t = time.time()
+                    edges = sum(tr.num_sampled_edges(i) for i in range(len(tr.cum_sampled_edges)))
+                    print(f"step {step} loss {loss.item():.4f} train_acc {acc:.4f} iter_time {(t - t_prev):.4f} "
+                          f"num_edges {edges:.0f}")
+                    t_prev = t
+                if 0 < args.num_steps <= step:
+                    done = True
+                    break
+            epoch += 1
+            tr.scheduler.step()
+            if dm.val_nid.numel():
+                val = tr.validate()
+                best_val = max(best_val, val)
+                if rank == 0:
+                    print(f"epoch {epoch} val_acc {val:.4f}")
+                if val >= args.val_acc_target and step >= args.min_steps:       # EarlyStopping threshold :627-634
+                    done = True
+            if 0 < args.num_epochs <= epoch:
+                done = True
+        with torch.no_grad():                                                    # :686-705
+            pred = model.inference(dm.g, device, 128, args.use_uva, args.num_workers)
+            out = {}
+            for nid, split in zip([dm.train_nid, dm.val_nid, dm.test_nid], ["Train", "Validation", "Test"]):
+                if nid.numel():
+                    out[split] = micro_f1(pred[nid.long()], dm.g.ndata["labels"][nid.long()], dm.multilabel)
+                    if rank == 0:
+                        print(f"{split} accuracy: {out[split]}")
+        results.append(out)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return results
+
+
+if __name__ == "__main__":
+    main()

@@ -82,7 +82,7 @@ GRAPHS = {
 }
 
 
-def _oracle_and_device(gname, cls_name, accum, step=3, seed=11, eta=0.1, draws="philox", **kw):
+def _oracle_and_device(gname, cls_name, accum, step=3, seed=11, eta=0.1, draws="philox", ora_kw=None, **kw):
     V, E, hubs, hdeg, batch, fan = GRAPHS[gname]
     g = random_graph(V, E, seed=5, hubs=hubs, hub_degree=hdeg)
     seeds = torch.randperm(V, generator=torch.Generator().manual_seed(1))[:batch]
@@ -91,8 +91,12 @@ def _oracle_and_device(gname, cls_name, accum, step=3, seed=11, eta=0.1, draws="
     is_bandit = "Bandit" in cls_name
     okw = dict(eta=eta) if is_bandit else {}
     safe = SafeDraws(V, seed, step) if draws == "safe" else None
-    ora = getattr(osamp, cls_name)(fan, accum=accum, uniform_fn=safe or philox_uniform_fn(seed, step), **okw, **kw)
+    ora = getattr(osamp, cls_name)(fan, accum=accum, uniform_fn=safe or philox_uniform_fn(seed, step), **okw,
+                                   **(ora_kw or {}), **kw)
+    if ora_kw and "dtype" in ora_kw:
+        g.edata["w"] = g.edata["w"].to(ora_kw["dtype"])
     o_in, o_out, o_blocks = ora.sample_blocks(g, seeds)
+    g.edata["w"] = g.edata["w"].float()
     gd = g.to(_dev())
     dev = _device_sampler(cls_name, fan, rng_seed=seed, **okw, **kw)
     dev.step = step
@@ -124,14 +128,18 @@ def test_poisson_bandit_contract_parity(native_lib, gname):
         torch.testing.assert_close(rs, db.in_degrees().double(), rtol=1e-5, atol=0)
 
 
-@pytest.mark.parametrize("gname", ["light", "heavy"])
-def test_poisson_bandit_native_parity_safe_draws(native_lib, gname):
-    """Device vs the torch-order oracle: sets bit-exact once ties are excluded, values within 1e-5."""
+@pytest.mark.parametrize("gname,dtype,rtol", [("light", torch.float32, RTOL), ("heavy", torch.float64, RTOL),
+                                              ("heavy", torch.float32, 1e-4)])
+def test_poisson_bandit_native_parity_safe_draws(native_lib, gname, dtype, rtol):
+    """Device vs the torch-order oracle: sets bit-exact once ties are excluded by the draw generator.
+    Values: within 1e-5 of the float64 oracle (the exact-arithmetic reference).  The float32
+    torch-order oracle itself is only good to ~2e-5 on 1,500-edge rows (sequential fp32 index_add_),
+    so against it the heavy graph is held to 1e-4; the device is the more accurate of the two."""
     *_, (o_in, _, o_blocks), (d_in, _, d_blocks) = _oracle_and_device(
-        gname, "PoissonBanditLadiesSampler", "native", draws="safe")
+        gname, "PoissonBanditLadiesSampler", "native", draws="safe", ora_kw=dict(dtype=dtype))
     assert torch.equal(d_in.cpu().long(), o_in)
     for db, ob in zip(d_blocks, o_blocks):
-        assert_blocks_equal(db, ob, rtol=RTOL)
+        assert_blocks_equal(db, ob, rtol=rtol)
 
 
 @pytest.mark.parametrize("cls_name", ["PoissonLadiesSampler", "LadiesSampler", "BanditLadiesSampler"])
