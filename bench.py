@@ -77,7 +77,7 @@ class ClockSampler(threading.Thread):
                 self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.05)     # NVML queries take driver locks: keep them sparse
 
     def stop(self):
         self._stop_evt.set()

@@ -20,7 +20,7 @@ SOURCES = ["sampler.cu", "aggregate.cu", "bandit.cu", "gat.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
-MODE_BANDIT, MODE_LADIES, MODE_UNIFORM = 0, 1, 2
+MODE_BANDIT, MODE_LADIES, MODE_UNIFORM, COLLECT_BITMAP = 0, 1, 2, 16
 AGG_SUM, AGG_MEAN = 0, 1
 
 
@@ -80,8 +80,8 @@ class Counters(C.Structure):
 
 class Workspace(C.Structure):
     _fields_ = [("acc", C.c_void_p), ("first_pos", C.c_void_p), ("node_info", C.c_void_p),
-                ("sel_bits", C.c_void_p), ("cand", C.c_void_p), ("p_cand", C.c_void_p), ("sel", C.c_void_p),
-                ("row_list", C.c_void_p), ("row_w", C.c_void_p), ("row_q", C.c_void_p),
+                ("sel_bits", C.c_void_p), ("cand_bits", C.c_void_p), ("cand", C.c_void_p), ("p_cand", C.c_void_p), ("sel", C.c_void_p),
+                ("row_list", C.c_void_p), ("pos_a", C.c_void_p), ("pos_d", C.c_void_p), ("row_w", C.c_void_p), ("row_q", C.c_void_p),
                 ("row_cnt", C.c_void_p), ("row_t", C.c_void_p), ("cap_seeds", C.c_int64),
                 ("cap_sel", C.c_int64), ("ctr", C.c_void_p)]
 
@@ -90,7 +90,7 @@ class BlockOut(C.Structure):
     _fields_ = [("indptr", C.c_void_p), ("edge_src", C.c_void_p), ("edge_dst", C.c_void_p),
                 ("csc_pos", C.c_void_p), ("eid", C.c_void_p), ("q_ij", C.c_void_p), ("edge_w", C.c_void_p),
                 ("src_nid", C.c_void_p), ("node_prob", C.c_void_p), ("out_deg", C.c_void_p),
-                ("cap_edges", C.c_int64), ("cap_src", C.c_int64)]
+                ("heavy_rows", C.c_void_p), ("cap_edges", C.c_int64), ("cap_src", C.c_int64)]
 
 
 _P, _I32, _I64, _U32, _U64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_double
@@ -104,16 +104,17 @@ PROTOTYPES = {
     "bliss_frontier_prob": [_GP, _P, _I32, _P, _F, _I32, _WP, _P],
     "bliss_poisson_scale": [_I32, _I32, _D, _I32, _WP, _P],
     "bliss_select_poisson": [_I32, _U64, _U64, _U32, _P, _WP, _P],
+    "bliss_poisson_select": [_I32, _I32, _D, _U64, _U64, _U32, _P, _WP, _P],
     "bliss_select_topk": [_I32, _I32, _U64, _U64, _U32, _P, _P, _WP, _P],
     "bliss_philox_fill": [_U64, _U64, _U32, _P, _I64, _P, _P],
     "bliss_block_count": [_GP, _P, _I32, _WP, _P],
     "bliss_block_index": [_P, _I32, _WP, _BP, _P],
     "bliss_block_fill": [_GP, _P, _I32, _P, _F, _I32, _WP, _BP, _P],
     "bliss_block_finish": [_I32, _I32, _WP, _BP, _P],
-    "bliss_block_transpose": [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P],
+    "bliss_block_transpose": [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P],
     "bliss_gather_rows": [_P, _P, _I64, _I32, _P, _P, _P],
     "bliss_row_norm": [_P, _I64, _I32, _P, _P],
-    "bliss_spmm": [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P],
+    "bliss_spmm": [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P, _P],
     "bliss_gatv2_fwd": [_P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "bliss_gatv2_bwd_dst": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P],
     "bliss_gatv2_bwd_src": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _P],
@@ -149,7 +150,7 @@ class BlissNativeError(RuntimeError):
 
 
 #: kernels each entry point launches (for the ``gpu_launches`` count of bench.py)
-LAUNCHES = {"bliss_select_topk": 3, "bliss_block_transpose": 4, "bliss_l1_norm": 2, "bliss_version": 0}
+LAUNCHES = {"bliss_frontier_prob": 2, "bliss_select_topk": 3, "bliss_block_transpose": 4, "bliss_l1_norm": 2, "bliss_version": 0}
 
 
 class _Stats:

@@ -63,51 +63,91 @@ __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ t
 }
 
 // y[r, c0:c0+W] = dscale_r * Σ_{e in row r} w_e * sscale[col_e] * x[col_e, c0:c0+W]
-// One warp per (row, column tile); accumulators NCH*VEC floats per lane.
+// Light rows: one warp per (row, column tile), accumulators NCH*VEC floats per lane.
+// Heavy rows (> BLISS_SPMM_HEAVY edges, listed in `heavy`): one CTA per row, the 8 warps take
+// interleaved 32-edge chunks and their partial sums are combined through shared memory in warp
+// order — a hub row no longer serialises on one warp and the result stays deterministic.
+template <int VEC, int NCH>
+__device__ __forceinline__ void spmm_chunk(float (&acc)[NCH][VEC], int e0, int b, int lane, int c0, int dim,
+                                           const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+                                           const float* __restrict__ w, const float* __restrict__ sscale,
+                                           const float* __restrict__ x) {
+  const int e = e0 + lane;
+  int my_c = 0;
+  float my_w = 0.0f;
+  if (e < b) {
+    my_c = __ldg(col + e);
+    my_w = w ? __ldg(w + (perm ? __ldg(perm + e) : e)) : 1.0f;
+    if (sscale) my_w *= __ldg(sscale + my_c);
+  }
+  const int n = min(32, b - e0);
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) {
+    const int c = __shfl_sync(0xffffffffu, my_c, j);
+    const float ww = __shfl_sync(0xffffffffu, my_w, j);
+    const float* __restrict__ xr = x + (int64_t)c * dim + c0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int cc = (ch * 32 + lane) * VEC;
+      if (c0 + cc < dim) {
+        float v[VEC];
+        vload<VEC>(v, xr + cc);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(ww, v[i], acc[ch][i]);
+      }
+    }
+  }
+}
+
 template <int VEC, int NCH>
 __global__ void __launch_bounds__(256) k_spmm(const int32_t* __restrict__ indptr, const int32_t* __restrict__ col,
                                              const int32_t* __restrict__ perm, const float* __restrict__ w,
                                              const float* __restrict__ sscale, const float* __restrict__ dscale,
                                              int agg, const float* __restrict__ x, int n_rows, int dim,
-                                             float* __restrict__ y) {
+                                             const int32_t* __restrict__ heavy, float* __restrict__ y) {
+  extern __shared__ float s_part[];  // [8 warps][TILE] partial sums of a heavy row
+  constexpr int TILE = 32 * VEC * NCH;
   const int lane = lane_id();
-  const int c0 = blockIdx.y * (32 * VEC * NCH);
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int r = warp; r < n_rows; r += nwarps) {
+  const int c0 = blockIdx.y * TILE;
+  const int n_heavy = heavy ? heavy[0] : 0;
+
+  for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+    const int r = heavy[1 + h];
     const int a = indptr[r], b = indptr[r + 1];
     float acc[NCH][VEC];
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.0f;
-    for (int e0 = a; e0 < b; e0 += 32) {
-      const int e = e0 + lane;
-      int my_c = 0;
-      float my_w = 0.0f;
-      if (e < b) {
-        my_c = __ldg(col + e);
-        my_w = w ? __ldg(w + (perm ? __ldg(perm + e) : e)) : 1.0f;
-        if (sscale) my_w *= __ldg(sscale + my_c);
-      }
-      const int n = min(32, b - e0);
-#pragma unroll 4
-      for (int j = 0; j < n; ++j) {
-        const int c = __shfl_sync(0xffffffffu, my_c, j);
-        const float ww = __shfl_sync(0xffffffffu, my_w, j);
-        const float* __restrict__ xr = x + (int64_t)c * dim + c0;
+    for (int e0 = a + 32 * warp_id(); e0 < b; e0 += 32 * 8)
+      spmm_chunk<VEC, NCH>(acc, e0, b, lane, c0, dim, col, perm, w, sscale, x);
+    __syncthreads();
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          const int cc = (ch * 32 + lane) * VEC;
-          if (c0 + cc < dim) {
-            float v[VEC];
-            vload<VEC>(v, xr + cc);
+    for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(ww, v[i], acc[ch][i]);
-          }
-        }
-      }
+      for (int i = 0; i < VEC; ++i) s_part[warp_id() * TILE + (ch * 32 + lane) * VEC + i] = acc[ch][i];
+    __syncthreads();
+    float s = dscale ? dscale[r] : 1.0f;
+    if (agg == BLISS_AGG_MEAN) s = s / (float)max(b - a, 1);
+    for (int cc = threadIdx.x; cc < TILE && c0 + cc < dim; cc += blockDim.x) {
+      float t = 0.0f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) t += s_part[wv * TILE + cc];
+      y[(int64_t)r * dim + c0 + cc] = t * s;
     }
+  }
+
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < n_rows; r += nwarps) {
+    const int a = indptr[r], b = indptr[r + 1];
+    if (heavy && b - a > BLISS_SPMM_HEAVY) continue;
+    float acc[NCH][VEC];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.0f;
+    for (int e0 = a; e0 < b; e0 += 32) spmm_chunk<VEC, NCH>(acc, e0, b, lane, c0, dim, col, perm, w, sscale, x);
     float s = dscale ? dscale[r] : 1.0f;
     if (agg == BLISS_AGG_MEAN) s = s / (float)max(b - a, 1);
     float* __restrict__ yr = y + (int64_t)r * dim + c0;
@@ -138,15 +178,17 @@ static inline int blocks_for_rows(int64_t n_rows, int max_blocks) {
 template <int VEC>
 static int launch_spmm(const int32_t* indptr, const int32_t* col, const int32_t* perm, const float* w,
                        const float* sscale, const float* dscale, int agg, const float* x, int n_rows,
-                       int dim, float* y, cudaStream_t st) {
+                       int dim, const int32_t* heavy, float* y, cudaStream_t st) {
   const int per_lane = (dim + 32 * VEC - 1) / (32 * VEC);
   int nch = 1;
   while (nch < per_lane && nch < 8) nch <<= 1;
   const int tile = 32 * VEC * nch;
   dim3 grid(blocks_for_rows(n_rows, BLISS_SM_COUNT * 16), (dim + tile - 1) / tile);
-#define BLISS_SPMM_CASE(N)                                                                              \
-  case N:                                                                                               \
-    k_spmm<VEC, N><<<grid, 256, 0, st>>>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, y); \
+  const size_t smem = heavy ? (size_t)8 * tile * sizeof(float) : 0;
+#define BLISS_SPMM_CASE(N)                                                                               \
+  case N:                                                                                                \
+    k_spmm<VEC, N><<<grid, 256, smem, st>>>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim,  \
+                                            heavy, y);                                                   \
     break;
   switch (nch) {
     BLISS_SPMM_CASE(1)
@@ -185,15 +227,15 @@ int bliss_row_norm(const float* x, int64_t n_rows, int32_t dim, float* out, void
 
 int bliss_spmm(const int32_t* indptr, const int32_t* col, const int32_t* perm, const float* w,
                const float* sscale, const float* dscale, int32_t agg, const float* x, int32_t n_rows,
-               int32_t dim, float* y, void* stream) {
+               int32_t dim, const int32_t* heavy, float* y, void* stream) {
   if (n_rows < 0 || dim <= 0 || !indptr || !y) return -1;
   if (n_rows == 0) return 0;
   if (!col || !x) return -1;
   cudaStream_t st = (cudaStream_t)stream;
   const bool al16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
-  if (dim % 4 == 0 && al16) return launch_spmm<4>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, y, st);
-  if (dim % 2 == 0) return launch_spmm<2>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, y, st);
-  return launch_spmm<1>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, y, st);
+  if (dim % 4 == 0 && al16) return launch_spmm<4>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, heavy, y, st);
+  if (dim % 2 == 0) return launch_spmm<2>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, heavy, y, st);
+  return launch_spmm<1>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, heavy, y, st);
 }
 
 }  // extern "C"

@@ -6,6 +6,7 @@
 // fixed-point integers (order independent -> bit-reproducible with atomics).
 #pragma once
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include "../../include/bliss_b200.h"
 
@@ -15,7 +16,9 @@
 #define BLISS_LIGHT_MAX 256                    // rows up to this degree are handled by one warp
 #define BLISS_CTA 256                          // threads per CTA of the row kernels
 #define BLISS_WARPS (BLISS_CTA / 32)
-#define BLISS_STAGE_CAP 8192                   // floats of a heavy row staged in shared memory
+#define BLISS_STAGE_CAP 6144                   // floats of a heavy row staged in shared memory (24 KB)
+#define BLISS_PROB_CTAS_PER_SM 6
+#define BLISS_SPMM_HEAVY 256                    // block rows with more edges are aggregated by a whole CTA
 
 #define BLISS_CHECK_LAUNCH()                      \
   do {                                            \

@@ -9,7 +9,10 @@
 // into heavy rows (one 256-thread CTA each, weights staged once in shared memory for the three
 // passes) and light rows (one warp each, values kept in registers); CTAs pull items from a
 // device-side queue, so no size ever travels to the host inside a layer.
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace bliss {
 
@@ -41,38 +44,63 @@ __device__ __forceinline__ void append_candidate(bool first, int src, const blis
 }
 
 // ------------------------------------------------------------------------------------------
-// plan: register the seeds, split rows into heavy / light, reset the counters.  One CTA.
+// plan: register the seeds, order the rows heavy-first (by log2 degree bucket, so the longest
+// rows start first and the tail is short), store every row's CSC start / degree by processing
+// position (one independent load per item, no pointer chase), reset the counters.  One CTA.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32_t* __restrict__ seeds,
                                                        int n_seeds, bliss_workspace ws) {
   __shared__ int s_scan[40];
   __shared__ unsigned long long s_e[32];
+  __shared__ int s_bucket[32], s_cursor[32];
   bliss_counters* ctr = ws.ctr;
-  int heavy_base = 0, light_base = 0;
+  if (threadIdx.x < 32) s_bucket[threadIdx.x] = 0;
+  __syncthreads();
   unsigned long long e_in = 0;
-  for (int base = 0; base < n_seeds; base += blockDim.x) {
-    int i = base + threadIdx.x;
-    bool valid = i < n_seeds;
-    int s = 0;
-    long long d = 0;
-    if (valid) {
-      s = seeds[i];
-      d = g.indptr[s + 1] - g.indptr[s];
-      e_in += (unsigned long long)d;
-      ws.acc[s] = BLISS_REG_BIT;
-      ws.cand[i] = s;
-      ws.node_info[2 * s] = i;
-      ws.node_info[2 * s + 1] = __float_as_int(1.0f);
-      atomicOr(&ws.sel_bits[s >> 5], 1u << (s & 31));
+  for (int i = threadIdx.x; i < n_seeds; i += blockDim.x) {
+    const int s = seeds[i];
+    const long long a = g.indptr[s];
+    const long long d = g.indptr[s + 1] - a;
+    e_in += (unsigned long long)d;
+    ws.cand[i] = s;
+    ws.node_info[2 * s] = i;
+    ws.node_info[2 * s + 1] = __float_as_int(1.0f);
+    atomicOr(&ws.sel_bits[s >> 5], 1u << (s & 31));
+    if (d > BLISS_LIGHT_MAX) atomicAdd(&s_bucket[31 - __clz((int)min(d, (long long)INT_MAX))], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // heaviest bucket first
+    int base = 0;
+    for (int bk = 31; bk >= 0; --bk) {
+      s_cursor[bk] = base;
+      base += s_bucket[bk];
     }
-    int is_heavy = valid && d > BLISS_LIGHT_MAX;
-    int is_light = valid && !is_heavy;
-    int th, tl;
-    int ph = block_excl_scan(is_heavy, s_scan, &th);
-    int pl = block_excl_scan(is_light, s_scan, &tl);
-    if (is_heavy) ws.row_list[heavy_base + ph] = i;
-    if (is_light) ws.row_list[n_seeds - 1 - (light_base + pl)] = i;
-    heavy_base += th;
+    s_scan[39] = base;
+  }
+  __syncthreads();
+  const int n_heavy = s_scan[39];
+  __syncthreads();
+  int light_base = 0;
+  for (int base = 0; base < n_seeds; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const bool valid = i < n_seeds;
+    long long a = 0, d = 0;
+    if (valid) {
+      const int s = seeds[i];
+      a = g.indptr[s];
+      d = g.indptr[s + 1] - a;
+    }
+    const bool heavy = valid && d > BLISS_LIGHT_MAX;
+    int tl;
+    const int pl = block_excl_scan((valid && !heavy) ? 1 : 0, s_scan, &tl);
+    int pos = -1;
+    if (heavy) pos = atomicAdd(&s_cursor[31 - __clz((int)min(d, (long long)INT_MAX))], 1);
+    else if (valid) pos = n_seeds - 1 - (light_base + pl);
+    if (pos >= 0) {
+      ws.row_list[pos] = i;
+      ws.pos_a[pos] = a;
+      ws.pos_d[pos] = (int)min(d, (long long)INT_MAX);
+    }
     light_base += tl;
   }
   e_in = block_sum(e_in, s_e);
@@ -81,8 +109,8 @@ __global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32
     ctr->n_cand = n_seeds;
     ctr->n_sel = 0;
     ctr->n_src = n_seeds;
-    ctr->n_heavy = heavy_base;
-    ctr->n_light = light_base;
+    ctr->n_heavy = n_heavy;
+    ctr->n_light = n_seeds - n_heavy;
     ctr->take_all = 0;
     ctr->iters = 0;
     ctr->e_in = (int64_t)e_in;
@@ -99,50 +127,66 @@ __global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32
 //   BANDIT: W_i = Σ_j w_ij ; q_ij = η/n_i + (1-η) w_ij/W_i ; Q_i = Σ_j q_ij ;
 //           acc[src] += fx((q_ij/Q_i)^2)                          bandit_sampler.py:129-137,67-73
 //   LADIES: acc[src] += fx(w_ij^2)                                ladies_sampler.py:46-47
-//   UNIFORM: acc[src] |= fx(1)                                    bandit_sampler.py:79-81
-// The first thread to touch acc[src] (old == 0) appends src to the candidate list.
+//   UNIFORM flag: acc[src] |= fx(1)                               bandit_sampler.py:79-81
+// The scatter is a fire-and-forget 64-bit integer reduction (RED: order independent, nothing to
+// wait for).  The candidate list is collected afterwards (k_collect_candidates): a dense scan of
+// the accumulators when |V| is moderate (BLISS_COLLECT_BITMAP clear), else from a candidate
+// bitmap the scatter marks with a second fire-and-forget RED.OR.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void scatter_term(bool uniform, float t, int src, double fx_scale,
-                                             const bliss_workspace& ws, bool valid) {
-  bool first = false;
-  if (valid) {
-    unsigned long long old;
-    if (uniform)
-      old = atomicOr((unsigned long long*)&ws.acc[src], (unsigned long long)fx_scale);
-    else
-      old = atomicAdd((unsigned long long*)&ws.acc[src], fx_term(t, fx_scale));
-    first = (old == 0ull);
+__device__ __forceinline__ void scatter_term(bool uniform, bool bitmap, float t, int src, double fx_scale,
+                                             const bliss_workspace& ws) {
+  if (uniform)
+    atomicOr((unsigned long long*)&ws.acc[src], (unsigned long long)fx_scale);
+  else
+    atomicAdd((unsigned long long*)&ws.acc[src], fx_term(t, fx_scale));
+  if (bitmap) {  // sparse-frontier mode: mark the candidate bit unless L2 already shows it set
+    const unsigned bit = 1u << (src & 31);
+    if (!(__ldcg(&ws.cand_bits[src >> 5]) & bit)) atomicOr(&ws.cand_bits[src >> 5], bit);
   }
-  append_candidate(first, src, ws);
 }
 
-__global__ void __launch_bounds__(BLISS_CTA) k_frontier_prob(GraphView g, const int32_t* __restrict__ seeds,
-                                                            const float* __restrict__ W, float eta,
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__global__ void __launch_bounds__(BLISS_CTA, BLISS_PROB_CTAS_PER_SM) k_frontier_prob(GraphView g, const float* __restrict__ W, float eta,
                                                             float one_minus_eta, int mode_flags,
                                                             bliss_workspace ws, double fx_scale) {
   const int mode = mode_flags & 1;                         // BANDIT / LADIES arithmetic
   const bool uniform = (mode_flags & BLISS_MODE_UNIFORM);  // importance_sampling = 0
+  const bool bitmap = (mode_flags & BLISS_COLLECT_BITMAP);
   extern __shared__ float s_row[];  // BLISS_STAGE_CAP floats
   __shared__ double s_red[32];
-  __shared__ int s_item;
   bliss_counters* ctr = ws.ctr;
   const int n_seeds = ctr->n_seeds, n_heavy = ctr->n_heavy, n_light = ctr->n_light;
   const int n_items = n_heavy + (n_light + BLISS_WARPS - 1) / BLISS_WARPS;
   const int tid = threadIdx.x;
 
-  for (;;) {
-    int item = next_item(&ctr->queue[0], n_items, &s_item);
-    if (item < 0) break;
+  // static round-robin over the heavy-first item list; the next heavy item's metadata is loaded
+  // (and its first lines pulled into L2) while the current row is processed
+  int item = blockIdx.x;
+  int64_t na = 0;
+  int nd = 0, nrow = 0;
+  if (item < n_heavy) {
+    na = ws.pos_a[item];
+    nd = ws.pos_d[item];
+    nrow = ws.row_list[item];
+  }
+  for (; item < n_items; item += gridDim.x) {
     if (item < n_heavy) {
       // ---------------- heavy row: whole CTA ----------------
-      const int row = ws.row_list[item];
-      const int s = seeds[row];
-      const int64_t a = g.indptr[s];
-      const int d = (int)(g.indptr[s + 1] - a);
+      const int row = nrow;
+      const int64_t a = na;
+      const int d = nd;
+      const int nxt = item + gridDim.x;
+      if (nxt < n_heavy) {
+        na = ws.pos_a[nxt];
+        nd = ws.pos_d[nxt];
+        nrow = ws.row_list[nxt];
+      }
       const int32_t* __restrict__ idx = g.indices + a;
       const float* __restrict__ wr = W + a;
-      const int d_pad = (d + BLISS_CTA - 1) / BLISS_CTA * BLISS_CTA;
       float row_q = 1.0f, row_w = 1.0f, eta_n = 0.0f;
+      // warm L2 with this row's source ids for the scatter pass
+      for (int l = tid; l * 32 < d; l += BLISS_CTA) prefetch_l2(idx + l * 32);
       if (mode == BLISS_MODE_BANDIT) {
         // pass A: stream the weights once from HBM (128-bit loads), stage them, row sum in fp64
         double acc = 0.0;
@@ -173,9 +217,9 @@ __global__ void __launch_bounds__(BLISS_CTA) k_frontier_prob(GraphView g, const 
           if (tail0 + tid < BLISS_STAGE_CAP) s_row[tail0 + tid] = w;
           acc += (double)w;
         }
-        // warm L2 with this row's source ids for pass C
-        for (int l = tid; l * 32 < d; l += BLISS_CTA)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(idx + l * 32));
+        // while the reduction runs, pull the next row's weights towards L2
+        if (nxt < n_heavy)
+          for (int l = tid; l * 32 < nd; l += BLISS_CTA) prefetch_l2(W + na + l * 32);
         row_w = __double2float_rn(block_sum(acc, s_red));
         eta_n = __fdiv_rn(eta, (float)d);
         // pass B: q_ij, row sum of q
@@ -193,33 +237,31 @@ __global__ void __launch_bounds__(BLISS_CTA) k_frontier_prob(GraphView g, const 
         }
       }
       // pass C: scatter the squared normalised edge probabilities to the column accumulator
-      for (int k = tid; k < d_pad; k += BLISS_CTA) {
-        bool valid = k < d;
-        int src = 0;
+#pragma unroll 4
+      for (int k = tid; k < d; k += BLISS_CTA) {
+        const int src = __ldg(idx + k);
         float t = 0.0f;
-        if (valid) {
-          src = __ldg(idx + k);
-          if (uniform) {
-          } else if (mode == BLISS_MODE_BANDIT) {
-            float q = (k < BLISS_STAGE_CAP) ? s_row[k] : edge_q(__ldg(wr + k), row_w, eta_n, one_minus_eta);
-            float r = __fdiv_rn(q, row_q);
-            t = __fmul_rn(r, r);
-          } else {
-            float w = __ldg(wr + k);
-            t = __fmul_rn(w, w);
-          }
+        if (uniform) {
+        } else if (mode == BLISS_MODE_BANDIT) {
+          float q = (k < BLISS_STAGE_CAP) ? s_row[k] : edge_q(__ldg(wr + k), row_w, eta_n, one_minus_eta);
+          float r = __fdiv_rn(q, row_q);
+          t = __fmul_rn(r, r);
+        } else {
+          float w = __ldg(wr + k);
+          t = __fmul_rn(w, w);
         }
-        scatter_term(uniform, t, src, fx_scale, ws, valid);
+        scatter_term(uniform, bitmap, t, src, fx_scale, ws);
       }
+      __syncthreads();  // s_row is reused by the next row
     } else {
       // ---------------- light rows: one warp per row, values in registers ----------------
       const int li = (item - n_heavy) * BLISS_WARPS + warp_id();
       if (li < n_light) {
         const int lane = lane_id();
-        const int row = ws.row_list[n_seeds - 1 - li];
-        const int s = seeds[row];
-        const int64_t a = g.indptr[s];
-        const int d = (int)(g.indptr[s + 1] - a);
+        const int pos = n_seeds - 1 - li;
+        const int row = ws.row_list[pos];
+        const int64_t a = ws.pos_a[pos];
+        const int d = ws.pos_d[pos];
         const int32_t* __restrict__ idx = g.indices + a;
         constexpr int R = BLISS_LIGHT_MAX / 32;
         float v[R];
@@ -252,8 +294,8 @@ __global__ void __launch_bounds__(BLISS_CTA) k_frontier_prob(GraphView g, const 
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (32 * r < d) {  // warp-uniform
-            int k = lane + 32 * r;
+          int k = lane + 32 * r;
+          if (k < d) {
             float t = 0.0f;
             if (uniform) {
             } else if (mode == BLISS_MODE_BANDIT) {
@@ -262,11 +304,41 @@ __global__ void __launch_bounds__(BLISS_CTA) k_frontier_prob(GraphView g, const 
             } else {
               t = __fmul_rn(v[r], v[r]);
             }
-            scatter_term(uniform, t, src[r], fx_scale, ws, k < d);
+            scatter_term(uniform, bitmap, t, src[r], fx_scale, ws);
           }
         }
       }
     }
+  }
+}
+
+// Candidate list = seeds (already listed by the plan) ++ every non-seed node that received a
+// scatter.  Dense mode: a node is a candidate iff its accumulator is non-zero (one coalesced scan
+// of |V| x 8 B).  Bitmap mode: iterate the set bits of cand_bits (|V| / 8 B) and clear them.
+__global__ void __launch_bounds__(256) k_collect_candidates(int64_t num_nodes, int bitmap, bliss_workspace ws) {
+  const int lane = lane_id();
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_words = (num_nodes + 31) >> 5;
+  for (int64_t w = warp; w < n_words; w += nwarps) {
+    const int64_t v = (w << 5) + lane;
+    bool hit;
+    if (bitmap) {
+      const unsigned word = ws.cand_bits[w];  // warp-uniform
+      if (word == 0u) continue;
+      __syncwarp();
+      if (lane == 0) ws.cand_bits[w] = 0u;
+      hit = (word >> lane) & 1u;
+    } else {
+      hit = v < num_nodes && ws.acc[v] != 0ull;
+    }
+    const bool is_new = hit && ws.node_info[2 * v] < 0;  // seeds are listed already
+    const unsigned m = __ballot_sync(0xffffffffu, is_new);
+    if (m == 0u) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&ws.ctr->n_cand, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (is_new) ws.cand[base + __popc(m & ((1u << lane) - 1u))] = (int)v;
   }
 }
 
@@ -337,6 +409,117 @@ __device__ __forceinline__ void push_selected(bool sel, int nid, const bliss_wor
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// (2a+2b fused) candidate probabilities + Poisson scale search + selection in ONE launch of a
+// single thread-block cluster (16 CTAs x 1024 threads, 8 if 16 is not schedulable).  Every
+// thread keeps up to NREG candidates (p and node id) in registers, so one search iteration is
+// NREG multiplies per thread + a CTA reduction + a DSMEM exchange of one 64-bit partial per CTA
+// and one cluster barrier — no global memory traffic and no host round trip inside the search
+// (the reference does up to 50 .item() syncs per layer, bandit_sampler.py:396-401).
+// Candidates beyond NREG per thread are re-read from p_cand (L2) each iteration.
+// ------------------------------------------------------------------------------------------
+#define BLISS_SCALE_NREG 16
+#define BLISS_SCALE_MAX_CLUSTER 16
+__global__ void __launch_bounds__(1024, 1) k_scale_select(int n_seeds, int fanout, double eps,
+                                                         unsigned long long seed, unsigned long long step,
+                                                         unsigned layer, const float* __restrict__ u_inject,
+                                                         bliss_workspace ws, double fx_inv_scale) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const unsigned nblk = cluster.num_blocks();
+  __shared__ unsigned long long s_red[32];
+  __shared__ unsigned long long s_parts[2][BLISS_SCALE_MAX_CLUSTER];
+  bliss_counters* ctr = ws.ctr;
+  const int n_cand = ctr->n_cand;
+  const int gtid = rank * blockDim.x + threadIdx.x;
+  const int nthreads = nblk * blockDim.x;
+
+  float preg[BLISS_SCALE_NREG];
+#pragma unroll
+  for (int r = 0; r < BLISS_SCALE_NREG; ++r) {
+    const int j = gtid + r * nthreads;
+    preg[r] = 0.0f;
+    if (j < n_cand) {
+      const float p = fx_to_prob(ws.acc[ws.cand[j]], fx_inv_scale);
+      ws.p_cand[j] = p;
+      preg[r] = p;
+    }
+  }
+  for (int j = gtid + BLISS_SCALE_NREG * nthreads; j < n_cand; j += nthreads)
+    ws.p_cand[j] = fx_to_prob(ws.acc[ws.cand[j]], fx_inv_scale);
+
+  const bool take_all = n_cand <= fanout;  // "prob.shape[0] <= num: return one"  (:392-393)
+  double c = 1.0, S = 0.0;
+  int it = 0;
+  if (!take_all) {
+    const float s_scale = 1099511627776.0f;  // 2^40: v * 2^40 is exact in fp32, so is its integer rounding
+    const double s_inv = 1.0 / 1099511627776.0;
+    const double num = (double)fanout;
+    for (int i = 0; i < 50; ++i) {
+      it = i + 1;
+      const float cf = (float)c;
+      unsigned long long part = 0;
+#pragma unroll
+      for (int r = 0; r < BLISS_SCALE_NREG; ++r)
+        part += __float2ull_rn(__fmul_rn(fminf(__fmul_rn(preg[r], cf), 1.0f), s_scale));
+      for (int j = gtid + BLISS_SCALE_NREG * nthreads; j < n_cand; j += nthreads)
+        part += __float2ull_rn(__fmul_rn(fminf(__fmul_rn(ws.p_cand[j], cf), 1.0f), s_scale));
+      const unsigned long long tot = block_sum(part, s_red);
+      if (threadIdx.x < nblk)  // publish this CTA's partial into every CTA of the cluster
+        *cluster.map_shared_rank(&s_parts[i & 1][rank], threadIdx.x) = tot;
+      cluster.sync();
+      unsigned long long all = 0;
+      for (unsigned b = 0; b < nblk; ++b) all += s_parts[i & 1][b];
+      S = __ull2double_rn(all) * s_inv;
+      if (fmin(S, num) / fmax(S, num) >= eps) break;   // :398
+      c *= num / S;                                    // :401
+    }
+  }
+  if (gtid == 0) {
+    ctr->c = c;
+    ctr->iters = it;
+    ctr->s_last = S;
+    ctr->take_all = take_all ? 1 : 0;
+  }
+  // selection: u < P, seeds forced to P = 1 (:403-406, :422-424)
+  const float cf = (float)c;
+#pragma unroll
+  for (int r = 0; r < BLISS_SCALE_NREG; ++r) {
+    if (r * nthreads < n_cand) {  // uniform across the cluster
+      const int j = gtid + r * nthreads;
+      bool sel = false;
+      int nid = 0;
+      if (j >= n_seeds && j < n_cand) {
+        nid = ws.cand[j];
+        const float P = take_all ? 1.0f : fminf(__fmul_rn(preg[r], cf), 1.0f);
+        const float u = u_inject ? u_inject[nid] : philox_uniform(seed, step, layer, (unsigned)nid);
+        sel = u < P;
+        ws.node_info[2 * nid] = sel ? -2 : -1;
+        ws.node_info[2 * nid + 1] = __float_as_int(P);
+      }
+      push_selected(sel, nid, ws);
+    }
+  }
+  const int rest0 = BLISS_SCALE_NREG * nthreads;
+  const int n_pad = (n_cand + 31) & ~31;
+  for (int j = gtid + rest0; j < n_pad; j += nthreads) {
+    bool sel = false;
+    int nid = 0;
+    if (j < n_cand) {
+      nid = ws.cand[j];
+      const float P = take_all ? 1.0f : fminf(__fmul_rn(ws.p_cand[j], cf), 1.0f);
+      const float u = u_inject ? u_inject[nid] : philox_uniform(seed, step, layer, (unsigned)nid);
+      sel = (j >= n_seeds) && (u < P);
+      if (j >= n_seeds) {
+        ws.node_info[2 * nid] = sel ? -2 : -1;
+        ws.node_info[2 * nid + 1] = __float_as_int(P);
+      }
+    }
+    push_selected(sel, nid, ws);
+  }
+  cluster.sync();  // no CTA may exit while its shared memory can still be written remotely
 }
 
 __global__ void __launch_bounds__(256) k_select_poisson(int n_seeds, unsigned long long seed,
@@ -485,9 +668,8 @@ __global__ void __launch_bounds__(BLISS_CTA) k_block_count(GraphView g, const in
     if (item < 0) break;
     if (item < n_heavy) {
       const int row = ws.row_list[item];
-      const int s = seeds[row];
-      const int64_t a = g.indptr[s];
-      const int d = (int)(g.indptr[s + 1] - a);
+      const int64_t a = ws.pos_a[item];
+      const int d = ws.pos_d[item];
       const int32_t* __restrict__ idx = g.indices + a;
       const unsigned long long key_hi = (unsigned long long)(row + 1) << 32;
       int cnt = 0;
@@ -505,9 +687,8 @@ __global__ void __launch_bounds__(BLISS_CTA) k_block_count(GraphView g, const in
       const int li = (item - n_heavy) * BLISS_WARPS + warp_id();
       if (li < n_light) {
         const int row = ws.row_list[n_seeds - 1 - li];
-        const int s = seeds[row];
-        const int64_t a = g.indptr[s];
-        const int d = (int)(g.indptr[s + 1] - a);
+        const int64_t a = ws.pos_a[n_seeds - 1 - li];
+        const int d = ws.pos_d[n_seeds - 1 - li];
         const int32_t* __restrict__ idx = g.indices + a;
         const unsigned long long key_hi = (unsigned long long)(row + 1) << 32;
         int cnt = 0;
@@ -538,7 +719,7 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
   bliss_counters* ctr = ws.ctr;
   const int n_sel = min(ctr->n_sel, (int)ws.cap_sel);
   if (blockIdx.x == 0) {
-    int base = 0;
+    int base = 0, hbase = 0;
     for (int b = 0; b < n_seeds; b += blockDim.x) {
       int i = b + threadIdx.x;
       int v = (i < n_seeds) ? ws.row_cnt[i] : 0;
@@ -546,8 +727,15 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
       int p = block_excl_scan(v, s_scan, &tot);
       if (i < n_seeds) out.indptr[i] = base + p;
       base += tot;
+      if (out.heavy_rows) {  // rows the aggregation kernels split across a whole CTA
+        int hv = v > BLISS_SPMM_HEAVY, ht;
+        int hp = block_excl_scan(hv, s_scan, &ht);
+        if (hv) out.heavy_rows[1 + hbase + hp] = i;
+        hbase += ht;
+      }
     }
     if (threadIdx.x == 0) {
+      if (out.heavy_rows) out.heavy_rows[0] = hbase;
       out.indptr[n_seeds] = base;
       ctr->n_edges = base;
       ctr->n_src = n_seeds + n_sel;
@@ -638,22 +826,33 @@ __global__ void __launch_bounds__(BLISS_CTA) k_block_fill(FillCtx c, const int32
     if (item < 0) break;
     if (item < n_heavy) {
       const int row = ws.row_list[item];
-      const int s = seeds[row];
-      const int64_t a = c.g.indptr[s];
-      const int d = (int)(c.g.indptr[s + 1] - a);
+      const int64_t a = ws.pos_a[item];
+      const int d = ws.pos_d[item];
       const int32_t* __restrict__ idx = c.g.indices + a;
       const float row_w = needs_row_w ? ws.row_w[row] : 1.0f;
       const float eta_n = __fdiv_rn(c.eta, (float)d);
+      // each warp owns one contiguous segment of the row: count its kept edges (bitmap test,
+      // sel_bits is L1 resident), one CTA scan of the 8 counts, then a sync-free ordered
+      // compaction per warp with ballots.
+      const int seg = (((d + BLISS_WARPS - 1) / BLISS_WARPS) + 31) & ~31;
+      const int k_lo = min(d, warp_id() * seg), k_hi = min(d, k_lo + seg);
+      int cnt = 0;
+      for (int k = k_lo + lane_id(); k < k_hi; k += 32) cnt += test_bit(ws.sel_bits, __ldg(idx + k)) ? 1 : 0;
+      cnt = warp_sum(cnt);
+      __syncthreads();
+      if (lane_id() == 0) s_scan[warp_id()] = cnt;
+      __syncthreads();
       int base = out.indptr[row];
+      for (int w = 0; w < warp_id(); ++w) base += s_scan[w];
       double acc = 0.0;
-      const int d_pad = (d + BLISS_CTA - 1) / BLISS_CTA * BLISS_CTA;
-      for (int k = tid; k < d_pad; k += BLISS_CTA) {
-        int src = (k < d) ? __ldg(idx + k) : 0;
-        int keep = (k < d) && test_bit(ws.sel_bits, src);
-        int tot;
-        int p = block_excl_scan(keep, s_scan, &tot);
-        if (keep) acc += fill_edge(c, ws, out, a + k, src, row, base + p, row_w, eta_n);
-        base += tot;
+      for (int k0 = k_lo; k0 < k_hi; k0 += 32) {
+        const int k = k0 + lane_id();
+        const int src = (k < k_hi) ? __ldg(idx + k) : 0;
+        const bool keep = (k < k_hi) && test_bit(ws.sel_bits, src);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep)
+          acc += fill_edge(c, ws, out, a + k, src, row, base + __popc(m & ((1u << lane_id()) - 1u)), row_w, eta_n);
+        base += __popc(m);
       }
       acc = block_sum(acc, s_red);
       if (tid == 0) ws.row_t[row] = acc;
@@ -662,9 +861,8 @@ __global__ void __launch_bounds__(BLISS_CTA) k_block_fill(FillCtx c, const int32
       if (li < n_light) {
         const int lane = lane_id();
         const int row = ws.row_list[n_seeds - 1 - li];
-        const int s = seeds[row];
-        const int64_t a = c.g.indptr[s];
-        const int d = (int)(c.g.indptr[s + 1] - a);
+        const int64_t a = ws.pos_a[n_seeds - 1 - li];
+        const int d = ws.pos_d[n_seeds - 1 - li];
         const int32_t* __restrict__ idx = c.g.indices + a;
         const float row_w = (needs_row_w && d > 0) ? ws.row_w[row] : 1.0f;
         const float eta_n = __fdiv_rn(c.eta, (float)d);
@@ -719,7 +917,10 @@ __global__ void k_ws_init(bliss_workspace ws, int64_t n) {
     ws.first_pos[v] = ~0ull;
     ws.node_info[2 * v] = -1;
     ws.node_info[2 * v + 1] = 0;
-    if ((v & 31) == 0) ws.sel_bits[v >> 5] = 0u;
+    if ((v & 31) == 0) {
+      ws.sel_bits[v >> 5] = 0u;
+      ws.cand_bits[v >> 5] = 0u;
+    }
   }
 }
 
@@ -732,11 +933,12 @@ __global__ void k_t_count(const int32_t* __restrict__ edge_src, int64_t n_edges,
     atomicAdd(&cnt[edge_src[e]], 1);
 }
 // cnt_cursor holds the per-source counts on entry and the fill cursors (= row starts) on exit.
-__global__ void __launch_bounds__(1024) k_t_scan(int32_t* cnt_cursor, int n, int32_t* __restrict__ indptr) {
+__global__ void __launch_bounds__(1024) k_t_scan(int32_t* cnt_cursor, int n, int32_t* __restrict__ indptr,
+                                                int32_t* __restrict__ heavy) {
   const int32_t* cnt = cnt_cursor;
   int32_t* cursor = cnt_cursor;
   __shared__ int s_scan[40];
-  int base = 0;
+  int base = 0, hbase = 0;
   for (int b = 0; b < n; b += blockDim.x) {
     int i = b + threadIdx.x;
     int v = (i < n) ? cnt[i] : 0;
@@ -744,9 +946,18 @@ __global__ void __launch_bounds__(1024) k_t_scan(int32_t* cnt_cursor, int n, int
     int p = block_excl_scan(v, s_scan, &tot);
     if (i < n) indptr[i] = base + p;
     base += tot;
+    if (heavy) {
+      int hv = v > BLISS_SPMM_HEAVY, ht;
+      int hp = block_excl_scan(hv, s_scan, &ht);
+      if (hv) heavy[1 + hbase + hp] = i;
+      hbase += ht;
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) indptr[n] = base;
+  if (threadIdx.x == 0) {
+    indptr[n] = base;
+    if (heavy) heavy[0] = hbase;
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) cursor[i] = indptr[i];
 }
 // Edges of a source land in arbitrary order inside its segment; k_t_sort restores ascending edge
@@ -863,6 +1074,7 @@ int bliss_frontier_prob(const bliss_graph* g, const int32_t* seeds, int32_t n_se
                         const bliss_workspace* ws, void* stream) {
   if (!g || !seeds || !ws || n_seeds < 0) return -1;
   if (!edge_weight_csc) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = BLISS_STAGE_CAP * sizeof(float);
   if (!g_prob_smem_set) {
     cudaError_t e = cudaFuncSetAttribute(k_frontier_prob, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -871,9 +1083,13 @@ int bliss_frontier_prob(const bliss_graph* g, const int32_t* seeds, int32_t n_se
   }
   const double fx_scale = (double)(1ull << fx_bits_for(n_seeds));
   const float one_minus_eta = (float)(1.0 - (double)eta);
-  int blocks = grid_for((int64_t)n_seeds * 32, BLISS_CTA, BLISS_SM_COUNT * 6);
-  k_frontier_prob<<<blocks, BLISS_CTA, smem, (cudaStream_t)stream>>>(view_of(g), seeds, edge_weight_csc, eta,
-                                                                    one_minus_eta, mode, *ws, fx_scale);
+  // persistent grid, static round-robin over the heavy-first item list
+  int blocks = grid_for((int64_t)n_seeds * BLISS_CTA, BLISS_CTA, BLISS_SM_COUNT * BLISS_PROB_CTAS_PER_SM);
+  k_frontier_prob<<<blocks, BLISS_CTA, smem, st>>>(view_of(g), edge_weight_csc, eta, one_minus_eta, mode, *ws,
+                                                  fx_scale);
+  BLISS_CHECK_LAUNCH();
+  k_collect_candidates<<<grid_for(g->num_nodes, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(
+      g->num_nodes, (mode & BLISS_COLLECT_BITMAP) ? 1 : 0, *ws);
   BLISS_CHECK_LAUNCH();
   return 0;
 }
@@ -892,6 +1108,53 @@ int bliss_select_poisson(int32_t n_seeds, uint64_t seed, uint64_t step, uint32_t
   if (!ws) return -1;
   k_select_poisson<<<BLISS_SM_COUNT * 4, 256, 0, (cudaStream_t)stream>>>(n_seeds, seed, step, layer, u_inject, *ws);
   BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+static int g_cluster_size = 0;  // 16, 8, or -1 (clusters unavailable)
+
+int bliss_poisson_select(int32_t n_seeds, int32_t fanout, double eps, uint64_t seed, uint64_t step,
+                         uint32_t layer, const float* u_inject, const bliss_workspace* ws, void* stream) {
+  if (!ws || fanout < 0) return -1;
+  if (g_cluster_size == 0) {
+    g_cluster_size = -1;
+    if (cudaFuncSetAttribute(k_scale_select, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      for (int cs = BLISS_SCALE_MAX_CLUSTER; cs >= 8 && g_cluster_size < 0; cs >>= 1) {
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(cs);
+        q.blockDim = dim3(1024);
+        cudaLaunchAttribute a[1];
+        a[0].id = cudaLaunchAttributeClusterDimension;
+        a[0].val.clusterDim.x = cs;
+        a[0].val.clusterDim.y = a[0].val.clusterDim.z = 1;
+        q.attrs = a;
+        q.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, k_scale_select, &q) == cudaSuccess && n > 0) g_cluster_size = cs;
+      }
+    }
+    (void)cudaGetLastError();
+  }
+  if (g_cluster_size < 0) {  // no cluster support: the two-launch path
+    int rc = bliss_poisson_scale(n_seeds, fanout, eps, 1, ws, stream);
+    if (rc) return rc;
+    return bliss_select_poisson(n_seeds, seed, step, layer, u_inject, ws, stream);
+  }
+  const double fx_inv = 1.0 / (double)(1ull << fx_bits_for(n_seeds));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g_cluster_size);
+  cfg.blockDim = dim3(1024);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = g_cluster_size;
+  attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_scale_select, (int)n_seeds, (int)fanout, eps,
+                                     (unsigned long long)seed, (unsigned long long)step, (unsigned)layer, u_inject,
+                                     *ws, fx_inv);
+  if (e != cudaSuccess) return (int)e;
   return 0;
 }
 
@@ -923,7 +1186,7 @@ int bliss_philox_fill(uint64_t seed, uint64_t step, uint32_t layer, const int32_
 int bliss_block_count(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
                       const bliss_workspace* ws, void* stream) {
   if (!g || !seeds || !ws) return -1;
-  int blocks = grid_for((int64_t)n_seeds * 32, BLISS_CTA, BLISS_SM_COUNT * 8);
+  int blocks = grid_for((int64_t)n_seeds * BLISS_CTA, BLISS_CTA, BLISS_SM_COUNT * 8);
   k_block_count<<<blocks, BLISS_CTA, 0, (cudaStream_t)stream>>>(view_of(g), seeds, *ws);
   BLISS_CHECK_LAUNCH();
   return 0;
@@ -948,7 +1211,7 @@ int bliss_block_fill(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds
   c.eta = eta;
   c.one_minus_eta = (float)(1.0 - (double)eta);
   c.mode = mode & 1;
-  int blocks = grid_for((int64_t)n_seeds * 32, BLISS_CTA, BLISS_SM_COUNT * 8);
+  int blocks = grid_for((int64_t)n_seeds * BLISS_CTA, BLISS_CTA, BLISS_SM_COUNT * 5);
   k_block_fill<<<blocks, BLISS_CTA, 0, (cudaStream_t)stream>>>(c, seeds, *ws, *out);
   BLISS_CHECK_LAUNCH();
   return 0;
@@ -965,7 +1228,8 @@ int bliss_block_finish(int32_t n_seeds, int32_t mode, const bliss_workspace* ws,
 
 int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                           int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor,
-                          int32_t* t_scratch, int32_t* t_dst, int32_t* t_perm, void* stream) {
+                          int32_t* t_scratch, int32_t* t_dst, int32_t* t_perm, int32_t* t_heavy,
+                          void* stream) {
   if (n_edges < 0 || n_src < 0 || !t_indptr || !t_cursor) return -1;
   if (n_edges > 0 && (!edge_src || !edge_dst || !t_scratch || !t_dst || !t_perm)) return -1;
   cudaStream_t st = (cudaStream_t)stream;
@@ -975,7 +1239,7 @@ int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int6
     k_t_count<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, t_cursor);
     BLISS_CHECK_LAUNCH();
   }
-  k_t_scan<<<1, 1024, 0, st>>>(t_cursor, n_src, t_indptr);
+  k_t_scan<<<1, 1024, 0, st>>>(t_cursor, n_src, t_indptr, t_heavy);
   BLISS_CHECK_LAUNCH();
   if (n_edges == 0) return 0;
   k_t_fill<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, t_cursor, t_scratch);

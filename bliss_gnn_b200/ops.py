@@ -57,18 +57,19 @@ def block_transpose(block):
         t_scratch = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         t_dst = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         t_perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        t_heavy = torch.empty(n_src + 1, dtype=torch.int32, device=dev)
         N.call("bliss_block_transpose", N.ptr(block.edge_src), N.ptr(block.edge_dst), E, n_src, n_dst,
-                                              N.ptr(t_indptr), N.ptr(t_cursor), N.ptr(t_scratch), N.ptr(t_dst),
-                                              N.ptr(t_perm), N.stream())
-        block._transpose = (t_indptr, t_dst[:E], t_perm[:E])
+               N.ptr(t_indptr), N.ptr(t_cursor), N.ptr(t_scratch), N.ptr(t_dst), N.ptr(t_perm), N.ptr(t_heavy),
+               N.stream())
+        block._transpose = (t_indptr, t_dst[:E], t_perm[:E], t_heavy)
     return block._transpose
 
 
-def _spmm_raw(indptr, col, perm, w, sscale, dscale, agg, x, n_rows):
+def _spmm_raw(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, heavy=None):
     d = x.shape[1]
     y = torch.empty((n_rows, d), dtype=torch.float32, device=x.device)
     N.call("bliss_spmm", N.ptr(indptr), N.ptr(col), N.ptr(perm), N.ptr(w), N.ptr(sscale), N.ptr(dscale),
-                               agg, N.ptr(x), n_rows, d, N.ptr(y), N.stream())
+           agg, N.ptr(x), n_rows, d, N.ptr(heavy), N.ptr(y), N.stream())
     return y
 
 
@@ -78,16 +79,16 @@ class _SpMM(torch.autograd.Function):
         x = _req(x, name="x")
         ctx.block, ctx.w, ctx.sscale, ctx.dscale = block, w, sscale, dscale
         return _spmm_raw(block.indptr, block.edge_src, None, w, sscale, dscale, N.AGG_SUM, x,
-                         block.num_dst_nodes())
+                         block.num_dst_nodes(), getattr(block, "heavy_rows", None))
 
     @staticmethod
     def backward(ctx, gy):
         block = ctx.block
-        t_indptr, t_dst, t_perm = block_transpose(block)
+        t_indptr, t_dst, t_perm, t_heavy = block_transpose(block)
         gy = _req(gy, name="grad")
         # dx_c = sscale_c * Σ_{e: src_e = c} w_e * dscale_{dst_e} * dy_{dst_e}
         gx = _spmm_raw(t_indptr, t_dst, t_perm, ctx.w, ctx.dscale, ctx.sscale, N.AGG_SUM, gy,
-                       block.num_src_nodes())
+                       block.num_src_nodes(), t_heavy)
         return gx, None, None, None, None
 
 
@@ -146,7 +147,7 @@ class _GATv2(torch.autograd.Function):
                                       N.ptr(mask), N.ptr(logits), N.ptr(rmax), N.ptr(rsum), N.ptr(out),
                                       N.ptr(gout), slope, n_dst, H, D, N.ptr(glogit), N.ptr(gfeat),
                                       N.ptr(gattn), N.stream())
-        t_indptr, t_dst, t_perm = block_transpose(block)
+        t_indptr, t_dst, t_perm, _ = block_transpose(block)
         N.call("bliss_gatv2_bwd_src", N.ptr(t_indptr), N.ptr(t_dst), N.ptr(t_perm), N.ptr(feat), N.ptr(attn_c),
                                       N.ptr(mask), N.ptr(logits), N.ptr(rmax), N.ptr(rsum), N.ptr(gout),
                                       N.ptr(glogit), slope, n_src, n_dst, H, D, N.ptr(gfeat), N.stream())

@@ -19,6 +19,7 @@ Same class names, constructor signatures, public attributes and method names as 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import torch
@@ -42,6 +43,9 @@ class _Workspace:
         self.first_pos = torch.empty(V, dtype=torch.int64, device=dev)
         self.node_info = torch.empty(2 * V, **i32)
         self.sel_bits = torch.empty((V + 31) // 32, **i32)
+        self.cand_bits = torch.empty((V + 31) // 32, **i32)
+        self.pos_a = torch.empty(V, dtype=torch.int64, device=dev)
+        self.pos_d = torch.empty(V, **i32)
         self.cand = torch.empty(V, **i32)
         self.p_cand = torch.empty(V, dtype=torch.float32, device=dev)
         self.sel = torch.empty(V, **i32)
@@ -57,8 +61,8 @@ class _Workspace:
         self.ctr_host = torch.zeros(C.sizeof(N.Counters), dtype=torch.uint8).pin_memory()
         self.ws = N.Workspace(
             acc=N.ptr(self.acc), first_pos=N.ptr(self.first_pos), node_info=N.ptr(self.node_info),
-            sel_bits=N.ptr(self.sel_bits), cand=N.ptr(self.cand), p_cand=N.ptr(self.p_cand), sel=N.ptr(self.sel),
-            row_list=N.ptr(self.row_list), row_w=N.ptr(self.row_w), row_q=N.ptr(self.row_q),
+            sel_bits=N.ptr(self.sel_bits), cand_bits=N.ptr(self.cand_bits), cand=N.ptr(self.cand), p_cand=N.ptr(self.p_cand), sel=N.ptr(self.sel),
+            row_list=N.ptr(self.row_list), pos_a=N.ptr(self.pos_a), pos_d=N.ptr(self.pos_d), row_w=N.ptr(self.row_w), row_q=N.ptr(self.row_q),
             row_cnt=N.ptr(self.row_cnt), row_t=N.ptr(self.row_t), cap_seeds=V, cap_sel=V, ctr=N.ptr(self.ctr))
         self.gview = N.Graph(num_nodes=V, num_edges=g.num_edges(), indptr=N.ptr(g.indptr),
                              indices=N.ptr(g.indices), eid=N.ptr(g.eid))
@@ -85,6 +89,7 @@ class BanditLadiesSampler:
 
     _poisson = False
     _mode = N.MODE_BANDIT
+    DENSE_COLLECT_MAX = 1 << 22   # up to 4 M nodes the 8 B/node accumulator scan is cheaper than marking bits
 
     def __init__(self, nodes_per_layer, importance_sampling=True, weight="w", out_weight="edge_weights",
                  node_embedding="nfeat", node_prob="node_prob", replace=False, eta=0.4, num_steps=5000,
@@ -109,6 +114,7 @@ class BanditLadiesSampler:
         self.normalize = normalize
         self.renorm_every = int(renorm_every)
         self.inject_uniforms = None   # dense [|V|] float32 (or {layer: tensor}), test hook
+        self.collect = "auto"         # candidate collection: 'dense' scan, 'bitmap', or by |V| ('auto')
         self.process_group = None                              # set for data-parallel bandit exchange
         self._w_csc: Optional[torch.Tensor] = None             # [L, |E|] un-normalised, CSC order
         self._l1: Optional[torch.Tensor] = None                # [L] float64 running L1 norms
@@ -195,14 +201,18 @@ class BanditLadiesSampler:
     # ---- stage 2: node probabilities ---------------------------------------------------------
     def _frontier_prob(self, fr: Frontier):
         mode = fr.mode | (0 if self.importance_sampling else N.MODE_UNIFORM)
+        if self.collect == 'bitmap' or (self.collect == 'auto' and fr.g.num_nodes() > self.DENSE_COLLECT_MAX):
+            mode |= N.COLLECT_BITMAP
         N.call("bliss_frontier_prob", C.byref(fr.wsp.gview), N.ptr(fr.seeds), fr.n_seeds, N.ptr(fr.weights),
                                             float(self.eta), mode, C.byref(fr.wsp.ws), N.stream())
 
     def compute_prob(self, insg: Frontier, seed_nodes, edge_prob, num):
         """``bandit_sampler.py:47-82`` (+ the Poisson scale search ``:381-406`` in the subclass)."""
         self._frontier_prob(insg)
-        N.call("bliss_poisson_scale", insg.n_seeds, int(num), float(self.eps), int(self._poisson),
-                                            C.byref(insg.wsp.ws), N.stream())
+        if not self._poisson:      # candidate probabilities for the top-k selection
+            N.call("bliss_poisson_scale", insg.n_seeds, int(num), float(self.eps), 0, C.byref(insg.wsp.ws),
+                   N.stream())
+        insg.fanout = int(num)
         return insg
 
     # ---- stage 3: selection -------------------------------------------------------------------
@@ -234,8 +244,9 @@ class BanditLadiesSampler:
         n_s = fr.n_seeds
         dev = g.device
         indptr = torch.empty(n_s + 1, dtype=torch.int32, device=dev)
+        heavy = torch.empty(n_s + 1, dtype=torch.int32, device=dev)
         out = N.BlockOut(indptr=N.ptr(indptr), src_nid=N.ptr(wsp.src_nid), node_prob=N.ptr(wsp.node_prob),
-                         cap_edges=0, cap_src=g.num_nodes())
+                         heavy_rows=N.ptr(heavy), cap_edges=0, cap_src=g.num_nodes())
         N.call("bliss_block_count", C.byref(wsp.gview), N.ptr(fr.seeds), n_s, C.byref(wsp.ws), st)
         N.call("bliss_block_index", N.ptr(fr.seeds), n_s, C.byref(wsp.ws), C.byref(out), st)
         ctr = wsp.read_counters()            # the one host read of this layer: n_src, E_b
@@ -259,6 +270,7 @@ class BanditLadiesSampler:
         N.call("bliss_block_finish", n_s, fr.mode, C.byref(wsp.ws), C.byref(out), st)
         src_nid = wsp.src_nid[:n_src].clone()
         block = Block(indptr, edge_src, edge_dst, src_nid, fr.seeds, graph=g, csc_pos=csc_pos)
+        block.heavy_rows = heavy
         block.edata[EID] = eid                                                   # :337
         block.edata[self.output_weight] = edge_w                                 # :324
         self._attach(block, q_ij, wsp.node_prob[:n_src].clone())
@@ -395,8 +407,9 @@ class PoissonBanditLadiesSampler(BanditLadiesSampler):
 
     def select_neighbors(self, prob: Frontier, num):
         """``bandit_sampler.py:408-425``: ``bernoulli(P) == 1``  ⇔  ``u < P``."""
-        N.call("bliss_select_poisson", prob.n_seeds, self.rng_seed, self.step, prob.layer,
-                                             self._u_ptr(prob.g, prob.layer), C.byref(prob.wsp.ws), N.stream())
+        # scale search (:391-406) + selection in one thread-block-cluster launch
+        N.call("bliss_poisson_select", prob.n_seeds, int(num), float(self.eps), self.rng_seed, self.step,
+               prob.layer, self._u_ptr(prob.g, prob.layer), C.byref(prob.wsp.ws), N.stream())
         return prob
 
 
@@ -418,8 +431,8 @@ class LadiesSampler(BanditLadiesSampler):
         fr = Frontier(g, wsp, seed_nodes, n, self._layer, N.MODE_LADIES, weight)
         N.call("bliss_frontier_plan", C.byref(wsp.gview), N.ptr(seed_nodes), n, C.byref(wsp.ws), N.stream())
         self._frontier_prob(fr)
-        N.call("bliss_poisson_scale", n, int(num), float(self.eps), int(self._poisson), C.byref(wsp.ws),
-                                            N.stream())
+        if not self._poisson:
+            N.call("bliss_poisson_scale", n, int(num), float(self.eps), 0, C.byref(wsp.ws), N.stream())
         return fr, fr
 
     def _attach(self, block, q_ij, node_prob):

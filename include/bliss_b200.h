@@ -29,6 +29,9 @@ extern "C" {
 #define BLISS_MODE_LADIES 1   /* p_j = sqrt(sum_i w_ij^2) with static w                         ladies_sampler.py:34-52 */
 #define BLISS_MODE_UNIFORM 2  /* flag OR-ed onto the above: importance_sampling=0, p_j = 1 for nodes with an out-edge  bandit_sampler.py:77-81 */
 
+#define BLISS_COLLECT_BITMAP 16 /* flag OR-ed onto the mode: collect candidates from a bitmap the scatter marks
+                                  (sparse frontiers in huge graphs) instead of a dense scan of the |V| accumulators */
+
 /* aggregation modes of bliss_spmm */
 #define BLISS_AGG_SUM 0
 #define BLISS_AGG_MEAN 1      /* divide by max(in_degree, 1)  (fn.mean, dglnn.SAGEConv 'mean') */
@@ -65,17 +68,20 @@ typedef struct bliss_counters {
 
 /* Per-sampler workspace (device pointers; V = num_nodes, S = max seeds of a layer,
  * C = capacity of selected nodes).  Invariant between layers: acc == 0, first_pos == ~0,
- * node_info[v].x == -1, sel_bits == 0 — bliss_block_finish restores it for every node a layer
+ * node_info[v].x == -1, sel_bits == cand_bits == 0 — bliss_block_finish restores it for every node a layer
  * touched, so nothing |V|-sized is cleared per step. */
 typedef struct bliss_workspace {
-  uint64_t* acc;        /* [V]  fixed-point column accumulator, bit 63 = "registered"     */
+  uint64_t* acc;        /* [V]  fixed-point column accumulator (sum of squared edge terms)  */
   uint64_t* first_pos;  /* [V]  first occurrence key of a selected source                 */
   int32_t*  node_info;  /* [2V] (local id | -1, float bits of inclusion prob P) per node  */
   uint32_t* sel_bits;   /* [(V+31)/32] bitmap: node is selected                           */
+  uint32_t* cand_bits;  /* [(V+31)/32] candidate bitmap (BLISS_COLLECT_BITMAP mode only)    */
   int32_t*  cand;       /* [V]  candidate list: seeds first, then sources unordered       */
   float*    p_cand;     /* [V]  raw probability per candidate slot                        */
   int32_t*  sel;        /* [C]  selected non-seed candidates, unordered                   */
-  int32_t*  row_list;   /* [S]  heavy rows from the front, light rows from the back       */
+  int32_t*  row_list;   /* [S]  heavy rows from the front (longest first), light from the back */
+  int64_t*  pos_a;      /* [S]  CSC start of the row at each row_list position            */
+  int32_t*  pos_d;      /* [S]  in-degree of the row at each row_list position            */
   float*    row_w;      /* [S]  sum_j w_ij  per seed                                      */
   float*    row_q;      /* [S]  sum_j q_ij  per seed                                      */
   int32_t*  row_cnt;    /* [S]  kept in-edges per seed                                    */
@@ -97,6 +103,7 @@ typedef struct bliss_block_out {
   int32_t* src_nid;     /* [n_src] global id of each block source                         */
   float*   node_prob;   /* [n_src] inclusion probability P (bandit_sampler.py:328)        */
   int32_t* out_deg;     /* [n_src] block out-degree of each source (NULL to skip)         */
+  int32_t* heavy_rows;  /* [n_seeds+1] [0]=count, then destinations with > 256 edges (NULL ok) */
   int64_t  cap_edges;
   int64_t  cap_src;
 } bliss_block_out;
@@ -123,6 +130,10 @@ int bliss_poisson_scale(int32_t n_seeds, int32_t fanout, double eps, int32_t poi
                         const bliss_workspace* ws, void* stream);
 int bliss_select_poisson(int32_t n_seeds, uint64_t seed, uint64_t step, uint32_t layer,
                          const float* u_inject, const bliss_workspace* ws, void* stream);
+/* scale search + selection fused in one thread-block-cluster launch (the Poisson fast path) */
+int bliss_poisson_select(int32_t n_seeds, int32_t fanout, double eps, uint64_t seed, uint64_t step,
+                         uint32_t layer, const float* u_inject, const bliss_workspace* ws,
+                         void* stream);
 int bliss_select_topk(int32_t n_seeds, int32_t fanout, uint64_t seed, uint64_t step, uint32_t layer,
                       const float* u_inject, float* key_scratch, const bliss_workspace* ws,
                       void* stream);
@@ -145,7 +156,9 @@ int bliss_block_finish(int32_t n_seeds, int32_t mode, const bliss_workspace* ws,
  * (edge ids ascending inside every source row, so backward sums are deterministic). */
 int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                           int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor /* [n_src] */,
-                          int32_t* t_scratch /* [E] */, int32_t* t_dst, int32_t* t_perm, void* stream);
+                          int32_t* t_scratch /* [E] */, int32_t* t_dst, int32_t* t_perm,
+                          int32_t* t_heavy /* [n_src+1] heavy source rows, [0]=count; may be NULL */,
+                          void* stream);
 
 /* ---- (5) aggregation ------------------------------------------------------------------------
  * replaces DGL g-SpMM u_mul_e/sum (+ fn.mean), g-SDDMM u_add_v, edge_softmax, th.norm and the
@@ -153,10 +166,12 @@ int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int6
 int bliss_gather_rows(const float* table, const int32_t* nid, int64_t n_rows, int32_t dim,
                       float* out, float* row_norm /* may be NULL */, void* stream);
 int bliss_row_norm(const float* x, int64_t n_rows, int32_t dim, float* out, void* stream);
-/* y[i,:] = dscale_i * sum_{e in row i} w[perm? perm[e] : e] * sscale[col[e]] * x[col[e], :] */
+/* y[i,:] = dscale_i * sum_{e in row i} w[perm? perm[e] : e] * sscale[col[e]] * x[col[e], :]
+ * heavy (may be NULL): [0] = count, then the rows with > 256 edges — those are split over the 8
+ * warps of a CTA and combined in shared memory in a fixed order; the rest is warp-per-row. */
 int bliss_spmm(const int32_t* indptr, const int32_t* col, const int32_t* perm, const float* w,
                const float* sscale, const float* dscale, int32_t agg, const float* x,
-               int32_t n_rows, int32_t dim, float* y, void* stream);
+               int32_t n_rows, int32_t dim, const int32_t* heavy, float* y, void* stream);
 int bliss_gatv2_fwd(const int32_t* indptr, const int32_t* col, const float* feat /* [n_src,H,D] */,
                     const float* attn /* [H,D] */, const float* drop_mask /* [E,H] or NULL */,
                     float negative_slope, int32_t n_dst, int32_t heads, int32_t dim,

@@ -77,7 +77,7 @@ def test_block_transpose_is_sorted(native_lib):
     from bliss_gnn_b200 import ops
     _, gd, _, db = _sample()
     for blk in db:
-        t_indptr, t_dst, t_perm = ops.block_transpose(blk)
+        t_indptr, t_dst, t_perm, _ = ops.block_transpose(blk)
         assert int(t_indptr[-1]) == blk.num_edges()
         src_of = blk.edge_src[t_perm.long()]
         rows = torch.repeat_interleave(torch.arange(blk.num_src_nodes(), device=gd.device),

@@ -154,6 +154,21 @@ def test_other_samplers_parity(native_lib, cls_name, gname):
             assert "node_prob" not in dict.keys(db.srcdata)
 
 
+def test_bitmap_candidate_collection_matches_dense(native_lib):
+    """Both candidate-collection modes (dense accumulator scan / RED.OR bitmap) yield the same blocks."""
+    g = random_graph(3000, 20000, seed=5, hubs=4, hub_degree=1200).to(_dev())
+    seeds = torch.arange(0, 64)
+    out = {}
+    for mode in ("dense", "bitmap"):
+        dev = _device_sampler("PoissonBanditLadiesSampler", [256, 128, 64], eta=0.1, rng_seed=3)
+        dev.collect = mode
+        _, _, out[mode] = dev.sample_blocks(g, seeds)
+        assert int(dev._wsp.cand_bits.count_nonzero()) == 0 and int(dev._wsp.acc.count_nonzero()) == 0
+    for x, y in zip(out["dense"], out["bitmap"]):
+        assert torch.equal(x.srcdata["_ID"], y.srcdata["_ID"]) and torch.equal(x.edge_src, y.edge_src)
+        assert torch.equal(x.edata["edge_weights"], y.edata["edge_weights"])
+
+
 def test_take_all_branch(native_lib):
     """N_c <= fanout: P = 1 for every candidate, block = full in-neighbourhood (bandit_sampler.py:392-393)."""
     g = random_graph(300, 900, seed=2)
@@ -190,6 +205,7 @@ def test_workspace_invariant_and_determinism(native_lib):
     w = dev._wsp
     assert int(w.acc.count_nonzero()) == 0 and int((w.first_pos != -1).sum()) == 0
     assert int((w.node_info[0::2] != -1).sum()) == 0 and int(w.sel_bits.count_nonzero()) == 0
+    assert int(w.cand_bits.count_nonzero()) == 0
     dev.step = 0                       # same Philox counters -> identical blocks, bit for bit
     _, _, b2 = dev.sample_blocks(g, seeds)
     for x, y in zip(b1, b2):

@@ -34,15 +34,33 @@ def test_library_exports_every_declared_symbol(native_lib):
     assert native_lib.bliss_version() == 100
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """ctypes mirrors vs the real header: compile a C probe with gcc and compare sizeof/offsetof."""
+    import subprocess
     from bliss_gnn_b200 import _native as N
-    assert ctypes.sizeof(N.Counters) == 88 and ctypes.sizeof(N.Graph) == 40
-    assert ctypes.sizeof(N.Workspace) == 15 * 8 and ctypes.sizeof(N.BlockOut) == 12 * 8
+    probe = tmp_path / "probe.c"
+    probe.write_text(r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "bliss_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(bliss_graph), sizeof(bliss_counters), sizeof(bliss_workspace),
+         sizeof(bliss_block_out), offsetof(bliss_counters, c), offsetof(bliss_counters, error),
+         offsetof(bliss_workspace, ctr), offsetof(bliss_block_out, cap_edges));
+  return 0;
+}
+""")
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(N.Graph), ctypes.sizeof(N.Counters), ctypes.sizeof(N.Workspace), ctypes.sizeof(N.BlockOut),
+            N.Counters.c.offset, N.Counters.error.offset, N.Workspace.ctr.offset, N.BlockOut.cap_edges.offset]
+    assert got == want
 
 
 def test_bad_arguments_are_rejected_without_a_gpu(native_lib):
     assert native_lib.bliss_philox_fill(0, 0, 0, None, -1, None, None) < 0
-    assert native_lib.bliss_spmm(None, None, None, None, None, None, 0, None, -1, 8, None, None) < 0
+    assert native_lib.bliss_spmm(None, None, None, None, None, None, 0, None, -1, 8, None, None, None) < 0
     assert native_lib.bliss_gather_rows(None, None, 4, 8, None, None, None) < 0
 
 
