@@ -279,6 +279,7 @@ def main():
 
     # ---- (3) per-entry-point CUDA-event timing over the same kind of steps (roofline) ----
     n_prof = min(args.steps, 50)
+    dm.sampler.force_stage_path = True     # one FFI call per kernel, so each is bracketed by its own events
     N.STATS.reset(timing=True)
     sizes = []
     for _ in range(n_prof):
@@ -287,6 +288,7 @@ def main():
     torch.cuda.synchronize()
     per_fn = N.STATS.elapsed_ms()
     N.STATS.reset(timing=False)
+    dm.sampler.force_stage_path = False
     top = max(per_fn.items(), key=lambda kv: kv[1][1])
     name, (calls, t_ms) = top
     peak, peak_src = _peaks()
@@ -297,7 +299,7 @@ def main():
                 alg += 16.0 * n_s + 8.0 * e_in + 8.0 * n_s + 12.0 * n_c
             elif name in ("bliss_block_count",):
                 alg += 16.0 * n_s + 4.0 * e_in + 4.0 * n_s
-            elif name == "bliss_block_fill":
+            elif name in ("bliss_block_fill", "bliss_sample_layer_back"):
                 alg += 16.0 * n_s + 4.0 * e_in + 28.0 * e_b + 8.0 * n_s
             elif name == "bliss_spmm":           # fwd+bwd of one layer at hidden width
                 alg += 2 * (8.0 * e_b + 4.0 * (n_s + 1) + 4.0 * HIDDEN * (n_src + n_s))

@@ -725,7 +725,10 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
       int v = (i < n_seeds) ? ws.row_cnt[i] : 0;
       int tot;
       int p = block_excl_scan(v, s_scan, &tot);
-      if (i < n_seeds) out.indptr[i] = base + p;
+      if (i < n_seeds) {
+        out.indptr[i] = base + p;
+        if (out.inv_deg) out.inv_deg[i] = 1.0f / (float)max(v, 1);   // fn.mean divisor
+      }
       base += tot;
       if (out.heavy_rows) {  // rows the aggregation kernels split across a whole CTA
         int hv = v > BLISS_SPMM_HEAVY, ht;
@@ -1255,6 +1258,41 @@ int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int6
                                                                                   t_scratch, t_perm, t_dst);
   BLISS_CHECK_LAUNCH();
   return 0;
+}
+
+// One call per layer phase for the host fast path (fewer FFI crossings, same kernels):
+// front = plan -> probabilities (+ candidate collection) -> selection -> kept-edge count -> index.
+int bliss_sample_layer_front(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                             const float* edge_weight_csc, float eta, int32_t mode, int32_t fanout, double eps,
+                             int32_t poisson, uint64_t seed, uint64_t step, uint32_t layer, const float* u_inject,
+                             float* key_scratch, const bliss_workspace* ws, const bliss_block_out* out,
+                             void* stream) {
+  int rc = bliss_frontier_plan(g, seeds, n_seeds, ws, stream);
+  if (rc) return rc;
+  rc = bliss_frontier_prob(g, seeds, n_seeds, edge_weight_csc, eta, mode, ws, stream);
+  if (rc) return rc;
+  if (poisson) {
+    rc = bliss_poisson_select(n_seeds, fanout, eps, seed, step, layer, u_inject, ws, stream);
+  } else {
+    rc = bliss_poisson_scale(n_seeds, fanout, eps, 0, ws, stream);
+    if (rc) return rc;
+    rc = bliss_select_topk(n_seeds, fanout, seed, step, layer, u_inject, key_scratch, ws, stream);
+  }
+  if (rc) return rc;
+  rc = bliss_block_count(g, seeds, n_seeds, ws, stream);
+  if (rc) return rc;
+  return bliss_block_index(seeds, n_seeds, ws, out, stream);
+}
+
+// back = fill -> normalise + workspace restore.
+int bliss_sample_layer_back(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                            const float* edge_weight_csc, float eta, int32_t mode, const bliss_workspace* ws,
+                            const bliss_block_out* out, void* stream) {
+  if (out && out->cap_edges > 0) {
+    int rc = bliss_block_fill(g, seeds, n_seeds, edge_weight_csc, eta, mode, ws, out, stream);
+    if (rc) return rc;
+  }
+  return bliss_block_finish(n_seeds, mode, ws, out, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,62 @@
+"""Data-parallel host logic (one process per GPU, replicated graph) — backend agnostic, so the same
+code runs over NCCL on the B200s and over gloo in the CPU tests.
+
+The reference is single-device (``train_lightning.py:648-651``); this is new work required by the
+north-star: every rank samples and aggregates its own seed batches, and only (1) the gradients and
+(2) the sparse bandit updates are exchanged.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_batches(n_batches: int, rank: int, world: int) -> range:
+    """Rank r takes batches r, r+R, … of the shared epoch permutation; the tail that does not fill a
+    whole round is dropped so every rank runs the same number of steps."""
+    usable = n_batches - (n_batches % world)
+    return range(rank, usable, world)
+
+
+class FlatGrads:
+    """All parameter gradients as views of one flat buffer: a single all-reduce per step."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=self.params[0].dtype, device=self.params[0].device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce_mean_(self, group=None):
+        world = dist.get_world_size(group) if group is not None else 1
+        if world > 1:
+            dist.all_reduce(self.flat, group=group)
+            self.flat.div_(world)
+
+
+def gather_updates(pos: torch.Tensor, x: torch.Tensor, group) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+    """All-gather every rank's sparse bandit update ``(csc position, clamped exponent)`` of one layer.
+    Lengths differ per rank: sizes are gathered first, payloads are padded to the maximum."""
+    world = dist.get_world_size(group)
+    n_loc = torch.tensor([pos.numel()], dtype=torch.int64, device=pos.device)
+    sizes = [torch.zeros_like(n_loc) for _ in range(world)]
+    dist.all_gather(sizes, n_loc, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    pos_pad = torch.zeros(cap, dtype=torch.int64, device=pos.device)
+    x_pad = torch.zeros(cap, dtype=torch.float32, device=pos.device)
+    pos_pad[:pos.numel()] = pos
+    x_pad[:x.numel()] = x
+    pos_all = [torch.empty_like(pos_pad) for _ in range(world)]
+    x_all = [torch.empty_like(x_pad) for _ in range(world)]
+    dist.all_gather(pos_all, pos_pad, group=group)
+    dist.all_gather(x_all, x_pad, group=group)
+    return [(pos_all[r][:sizes[r]], x_all[r][:sizes[r]]) for r in range(world)]

@@ -239,41 +239,55 @@ class BanditLadiesSampler:
     # ---- stage 4: block construction ------------------------------------------------------------
     def generate_block(self, insg: Frontier, neighbor_nodes_idx, seed_nodes, P_sg=None, W_sg=None):
         """``bandit_sampler.py:269-339`` (``ladies_sampler.py:71-107``)."""
-        fr, wsp, g = insg, insg.wsp, insg.g
-        L, st = N.lib(), N.stream()
-        n_s = fr.n_seeds
-        dev = g.device
-        indptr = torch.empty(n_s + 1, dtype=torch.int32, device=dev)
-        heavy = torch.empty(n_s + 1, dtype=torch.int32, device=dev)
+        fr, wsp = insg, insg.wsp
+        out, bufs = self._block_out(fr)
+        N.call("bliss_block_count", C.byref(wsp.gview), N.ptr(fr.seeds), fr.n_seeds, C.byref(wsp.ws), N.stream())
+        N.call("bliss_block_index", N.ptr(fr.seeds), fr.n_seeds, C.byref(wsp.ws), C.byref(out), N.stream())
+        return self._finish_block(fr, out, bufs)
+
+    def _block_out(self, fr: Frontier):
+        """Output descriptor of one layer: indptr / heavy list / mean divisor are sized by the seeds,
+        source arrays go to |V|-sized scratch until the counts are known."""
+        wsp, dev, n_s = fr.wsp, fr.g.device, fr.n_seeds
+        meta = torch.empty(3 * (n_s + 1), dtype=torch.int32, device=dev)   # indptr | heavy | inv_deg (as f32)
+        indptr, heavy, inv_deg = meta[:n_s + 1], meta[n_s + 1:2 * (n_s + 1)], meta[2 * (n_s + 1):].view(torch.float32)
         out = N.BlockOut(indptr=N.ptr(indptr), src_nid=N.ptr(wsp.src_nid), node_prob=N.ptr(wsp.node_prob),
-                         heavy_rows=N.ptr(heavy), cap_edges=0, cap_src=g.num_nodes())
-        N.call("bliss_block_count", C.byref(wsp.gview), N.ptr(fr.seeds), n_s, C.byref(wsp.ws), st)
-        N.call("bliss_block_index", N.ptr(fr.seeds), n_s, C.byref(wsp.ws), C.byref(out), st)
-        ctr = wsp.read_counters()            # the one host read of this layer: n_src, E_b
+                         heavy_rows=N.ptr(heavy), inv_deg=N.ptr(inv_deg), cap_edges=0, cap_src=fr.g.num_nodes())
+        return out, (indptr, heavy, inv_deg[:n_s])
+
+    def _finish_block(self, fr: Frontier, out, bufs):
+        """Read the layer's counters (the one host sync), size the edge arrays, fill + finish."""
+        wsp, g, dev, n_s = fr.wsp, fr.g, fr.g.device, fr.n_seeds
+        indptr, heavy, inv_deg = bufs
+        ctr = wsp.read_counters()
         if ctr.error:
             raise RuntimeError(f"BLISS sampler capacity error {ctr.error} in layer {fr.layer}")
         fr.counters = ctr
         self.last_counters[fr.layer] = ctr
         n_src, E = int(ctr.n_src), int(ctr.n_edges)
-        edge_src = torch.empty(E, dtype=torch.int32, device=dev)
-        edge_dst = torch.empty(E, dtype=torch.int32, device=dev)
+        bandit = fr.mode == N.MODE_BANDIT
+        # one allocation for the 4-byte edge arrays, one for the 8-byte CSC positions
+        e32 = torch.empty((5 if bandit else 4, max(E, 1)), dtype=torch.int32, device=dev)
+        edge_src, edge_dst, eid = e32[0, :E], e32[1, :E], e32[2, :E]
+        edge_w = e32[3, :E].view(torch.float32)
+        q_ij = e32[4, :E].view(torch.float32) if bandit else None
         csc_pos = torch.empty(E, dtype=torch.int64, device=dev)
-        eid = torch.empty(E, dtype=torch.int32, device=dev)
-        edge_w = torch.empty(E, dtype=torch.float32, device=dev)
-        q_ij = torch.empty(E, dtype=torch.float32, device=dev) if fr.mode == N.MODE_BANDIT else None
         out.edge_src, out.edge_dst, out.csc_pos = N.ptr(edge_src), N.ptr(edge_dst), N.ptr(csc_pos)
         out.eid, out.edge_w, out.q_ij = N.ptr(eid), N.ptr(edge_w), N.ptr(q_ij)
         out.cap_edges = E
-        if E > 0:
-            N.call("bliss_block_fill", C.byref(wsp.gview), N.ptr(fr.seeds), n_s, N.ptr(fr.weights), float(self.eta),
-                                       fr.mode, C.byref(wsp.ws), C.byref(out), st)
-        N.call("bliss_block_finish", n_s, fr.mode, C.byref(wsp.ws), C.byref(out), st)
-        src_nid = wsp.src_nid[:n_src].clone()
+        N.call("bliss_sample_layer_back", C.byref(wsp.gview), N.ptr(fr.seeds), n_s, N.ptr(fr.weights),
+               float(self.eta), fr.mode, C.byref(wsp.ws), C.byref(out), N.stream())
+        src = torch.empty(2 * n_src, dtype=torch.int32, device=dev)
+        src_nid = src[:n_src]
+        node_prob = src[n_src:].view(torch.float32)
+        src_nid.copy_(wsp.src_nid[:n_src])
+        node_prob.copy_(wsp.node_prob[:n_src])
         block = Block(indptr, edge_src, edge_dst, src_nid, fr.seeds, graph=g, csc_pos=csc_pos)
         block.heavy_rows = heavy
+        block._mean_scale = inv_deg
         block.edata[EID] = eid                                                   # :337
         block.edata[self.output_weight] = edge_w                                 # :324
-        self._attach(block, q_ij, wsp.node_prob[:n_src].clone())
+        self._attach(block, q_ij, node_prob)
         return block
 
     def _attach(self, block, q_ij, node_prob):
@@ -293,8 +307,14 @@ class BanditLadiesSampler:
         seed_nodes = self._prep_seeds(g, seed_nodes)
         output_nodes = seed_nodes
         blocks = []
+        fused = self._stages_not_overridden()
         for block_id in reversed(range(len(self.nodes_per_layer))):              # :350
             num = self.nodes_per_layer[block_id]
+            if fused:   # same kernels, two FFI calls per layer instead of eight
+                block = self._sample_layer_fused(g, seed_nodes, block_id, num, self._w_csc[block_id])
+                seed_nodes = block.srcdata[NID]
+                blocks.insert(0, block)
+                continue
             edge_prob, insg = self.exp3_probabilities(block_id, g, seed_nodes)   # :354
             node_prob = self.compute_prob(insg, seed_nodes, edge_prob, num)      # :356
             chosen = self.select_neighbors(node_prob, num)                       # :360
@@ -303,6 +323,30 @@ class BanditLadiesSampler:
             blocks.insert(0, block)                                              # :366
         self.step += 1
         return seed_nodes, output_nodes, blocks
+
+    _STAGES = ("exp3_probabilities", "compute_prob", "select_neighbors", "generate_block")
+
+    def _stages_not_overridden(self) -> bool:
+        """The stage methods are the reference's extension points; when a subclass overrides one, the
+        per-stage path runs so the override is honoured."""
+        if getattr(self, "force_stage_path", False):      # bench.py: time every kernel on its own
+            return False
+        return all(getattr(type(self), m).__module__ == __name__ for m in self._STAGES)
+
+    def _sample_layer_fused(self, g, seed_nodes, block_id, num, weights):
+        wsp = self._wsp
+        n = int(seed_nodes.numel())
+        fr = Frontier(g, wsp, seed_nodes, n, block_id, self._mode, weights)
+        mode = fr.mode | (0 if self.importance_sampling else N.MODE_UNIFORM)
+        if self.collect == "bitmap" or (self.collect == "auto" and g.num_nodes() > self.DENSE_COLLECT_MAX):
+            mode |= N.COLLECT_BITMAP
+        if not self._poisson and wsp.key_scratch is None:
+            wsp.key_scratch = torch.empty(g.num_nodes() + 4, dtype=torch.float32, device=g.device)
+        out, bufs = self._block_out(fr)
+        N.call("bliss_sample_layer_front", C.byref(wsp.gview), N.ptr(seed_nodes), n, N.ptr(weights), float(self.eta),
+               mode, int(num), float(self.eps), int(self._poisson), self.rng_seed, self.step, block_id,
+               self._u_ptr(g, block_id), N.ptr(wsp.key_scratch), C.byref(wsp.ws), C.byref(out), N.stream())
+        return self._finish_block(fr, out, bufs)
 
     # ---- bandit update ------------------------------------------------------------------------
     def calculate_alpha(self, mfg):
@@ -354,29 +398,13 @@ class BanditLadiesSampler:
     def _update_distributed(self, idx, mfg, g, alpha, pg):
         """Every rank sampled from the same frozen weights; all ranks apply all ranks' updates
         (``w *= exp(x)`` commutes).  One all-gather of the sparse (CSC position, exponent) pairs."""
-        import torch.distributed as dist
-        E = mfg.num_edges()
-        x = torch.empty(E, dtype=torch.float32, device=mfg.device)
+        from .parallel import gather_updates
+        x = torch.empty(mfg.num_edges(), dtype=torch.float32, device=mfg.device)
         self._reward_call(idx, mfg, g, alpha, None, x_out=x)
-        world = dist.get_world_size(pg)
-        n_loc = torch.tensor([E], dtype=torch.int64, device=mfg.device)
-        sizes = [torch.zeros_like(n_loc) for _ in range(world)]
-        dist.all_gather(sizes, n_loc, group=pg)
-        sizes = [int(s.item()) for s in sizes]
-        cap = max(max(sizes), 1)
-        pos_pad = torch.zeros(cap, dtype=torch.int64, device=mfg.device)
-        x_pad = torch.zeros(cap, dtype=torch.float32, device=mfg.device)
-        pos_pad[:E] = mfg.csc_pos
-        x_pad[:E] = x
-        pos_all = [torch.empty_like(pos_pad) for _ in range(world)]
-        x_all = [torch.empty_like(x_pad) for _ in range(world)]
-        dist.all_gather(pos_all, pos_pad, group=pg)
-        dist.all_gather(x_all, x_pad, group=pg)
-        for r in range(world):
-            if sizes[r]:
-                N.call("bliss_apply_updates", N.ptr(pos_all[r]), N.ptr(x_all[r]), sizes[r],
-                                                    N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]),
-                                                    N.stream())
+        for pos_r, x_r in gather_updates(mfg.csc_pos, x, pg):
+            if pos_r.numel():
+                N.call("bliss_apply_updates", N.ptr(pos_r), N.ptr(x_r), pos_r.numel(), N.ptr(self._w_csc[idx]),
+                       N.ptr(self._l1[idx:idx + 1]), N.stream())
 
     def _renormalize(self, idx):
         w = self._w_csc[idx]
@@ -451,9 +479,15 @@ class LadiesSampler(BanditLadiesSampler):
             if float(W.max()) > 1.0:
                 raise ValueError("LADIES edge weights must be <= 1 (fixed-point column sums; DESIGN.md §4)")
             self._w_checked = True
+        fused = self._stages_not_overridden()
         for block_id in reversed(range(len(self.nodes_per_layer))):
             self._layer = block_id
             num = self.nodes_per_layer[block_id]
+            if fused:
+                block = self._sample_layer_fused(g, seed_nodes, block_id, num, W)
+                seed_nodes = block.srcdata[NID]
+                blocks.insert(0, block)
+                continue
             prob, insg = self.compute_prob(g, seed_nodes, W, num)                # :115
             chosen = self.select_neighbors(prob, num)                            # :117
             block = self.generate_block(insg, chosen, seed_nodes, prob, W)       # :118-120

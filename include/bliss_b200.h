@@ -104,6 +104,7 @@ typedef struct bliss_block_out {
   float*   node_prob;   /* [n_src] inclusion probability P (bandit_sampler.py:328)        */
   int32_t* out_deg;     /* [n_src] block out-degree of each source (NULL to skip)         */
   int32_t* heavy_rows;  /* [n_seeds+1] [0]=count, then destinations with > 256 edges (NULL ok) */
+  float*   inv_deg;     /* [n_seeds] 1 / max(block in-degree, 1)  (fn.mean divisor; NULL ok)  */
   int64_t  cap_edges;
   int64_t  cap_src;
 } bliss_block_out;
@@ -152,6 +153,16 @@ int bliss_block_fill(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds
                      const bliss_workspace* ws, const bliss_block_out* out, void* stream);
 int bliss_block_finish(int32_t n_seeds, int32_t mode, const bliss_workspace* ws,
                        const bliss_block_out* out, void* stream);
+/* The two calls of the host fast path: the same kernels as the stage entry points above, launched
+ * back to back (front: plan, probabilities, selection, count, index; back: fill, finish). */
+int bliss_sample_layer_front(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                             const float* edge_weight_csc, float eta, int32_t mode, int32_t fanout,
+                             double eps, int32_t poisson, uint64_t seed, uint64_t step, uint32_t layer,
+                             const float* u_inject, float* key_scratch /* top-k only */,
+                             const bliss_workspace* ws, const bliss_block_out* out, void* stream);
+int bliss_sample_layer_back(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                            const float* edge_weight_csc, float eta, int32_t mode,
+                            const bliss_workspace* ws, const bliss_block_out* out, void* stream);
 /* source-major transpose of a block (backward SpMM): t_indptr[n_src+1], t_dst[E], t_perm[E]
  * (edge ids ascending inside every source row, so backward sums are deterministic). */
 int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,

@@ -169,6 +169,32 @@ def test_bitmap_candidate_collection_matches_dense(native_lib):
         assert torch.equal(x.edata["edge_weights"], y.edata["edge_weights"])
 
 
+@pytest.mark.parametrize("cls_name", ["PoissonBanditLadiesSampler", "BanditLadiesSampler", "PoissonLadiesSampler"])
+def test_overridden_stage_method_takes_the_stage_path(native_lib, cls_name):
+    """The reference's stage methods stay extension points: a subclass override switches from the fused
+    two-call fast path to the per-stage entry points, with bit-identical blocks."""
+    from bliss_gnn_b200 import sampler as S
+    g = random_graph(3000, 20000, seed=5, hubs=4, hub_degree=1200).to(_dev())
+    seeds = torch.arange(0, 64)
+    base = getattr(S, cls_name)
+    calls = []
+
+    class Sub(base):
+        def select_neighbors(self, prob, num):
+            calls.append(num)
+            return super().select_neighbors(prob, num)
+
+    kw = dict(eta=0.1) if "Bandit" in cls_name else {}
+    a, b = base([256, 128, 64], rng_seed=3, **kw), Sub([256, 128, 64], rng_seed=3, **kw)
+    assert a._stages_not_overridden() and not b._stages_not_overridden()
+    _, _, ba = a.sample_blocks(g, seeds)
+    _, _, bb = b.sample_blocks(g, seeds)
+    assert calls == [64, 128, 256]
+    for x, y in zip(ba, bb):
+        assert torch.equal(x.srcdata["_ID"], y.srcdata["_ID"]) and torch.equal(x.edge_src, y.edge_src)
+        assert torch.equal(x.edata["edge_weights"], y.edata["edge_weights"]) and torch.equal(x.indptr, y.indptr)
+
+
 def test_take_all_branch(native_lib):
     """N_c <= fanout: P = 1 for every candidate, block = full in-neighbourhood (bandit_sampler.py:392-393)."""
     g = random_graph(300, 900, seed=2)
