@@ -160,28 +160,29 @@ __global__ void __launch_bounds__(BLISS_CTA, BLISS_PROB_CTAS_PER_SM) k_frontier_
   const int n_items = n_heavy + (n_light + BLISS_WARPS - 1) / BLISS_WARPS;
   const int tid = threadIdx.x;
 
-  // static round-robin over the heavy-first item list; the next heavy item's metadata is loaded
-  // (and its first lines pulled into L2) while the current row is processed
-  int item = blockIdx.x;
-  int64_t na = 0;
-  int nd = 0, nrow = 0;
+  // dynamic longest-first queue (rows are ordered heavy-first by the plan): a CTA that finishes
+  // early pulls the next item, so the tail is one row, not one CTA's share.  Two items are known
+  // ahead (the first two rounds are static), and the queue cursor for the item after next is
+  // fetched while the current row is processed, so neither its round trip nor the next row's
+  // metadata loads sit on the critical path.
+  __shared__ int s_next[2];
+  int item = blockIdx.x, nxt = gridDim.x + blockIdx.x, iter = 0;
+  int64_t a = 0, na = 0;
+  int d = 0, nd = 0, row = 0, nrow = 0;
   if (item < n_heavy) {
-    na = ws.pos_a[item];
-    nd = ws.pos_d[item];
-    nrow = ws.row_list[item];
+    a = ws.pos_a[item];
+    d = ws.pos_d[item];
+    row = ws.row_list[item];
   }
-  for (; item < n_items; item += gridDim.x) {
+  for (; item < n_items; ++iter) {
+    if (tid == 0) s_next[iter & 1] = 2 * gridDim.x + atomicAdd(&ctr->queue[0], 1);
+    if (nxt < n_heavy) {
+      na = ws.pos_a[nxt];
+      nd = ws.pos_d[nxt];
+      nrow = ws.row_list[nxt];
+    }
     if (item < n_heavy) {
       // ---------------- heavy row: whole CTA ----------------
-      const int row = nrow;
-      const int64_t a = na;
-      const int d = nd;
-      const int nxt = item + gridDim.x;
-      if (nxt < n_heavy) {
-        na = ws.pos_a[nxt];
-        nd = ws.pos_d[nxt];
-        nrow = ws.row_list[nxt];
-      }
       const int32_t* __restrict__ idx = g.indices + a;
       const float* __restrict__ wr = W + a;
       float row_q = 1.0f, row_w = 1.0f, eta_n = 0.0f;
@@ -222,14 +223,18 @@ __global__ void __launch_bounds__(BLISS_CTA, BLISS_PROB_CTAS_PER_SM) k_frontier_
           for (int l = tid; l * 32 < nd; l += BLISS_CTA) prefetch_l2(W + na + l * 32);
         row_w = __double2float_rn(block_sum(acc, s_red));
         eta_n = __fdiv_rn(eta, (float)d);
-        // pass B: q_ij, row sum of q
+        // pass B: q_ij, row sum of q (staged part from shared memory; the part of a giant row beyond
+        // the stage is re-read from L2 with 8 independent loads in flight per thread)
         double accq = 0.0;
-        for (int k = tid; k < d; k += BLISS_CTA) {
-          float w = (k < BLISS_STAGE_CAP) ? s_row[k] : __ldg(wr + k);
-          float q = edge_q(w, row_w, eta_n, one_minus_eta);
-          if (k < BLISS_STAGE_CAP) s_row[k] = q;
+        const int d_st = min(d, BLISS_STAGE_CAP);
+        for (int k = tid; k < d_st; k += BLISS_CTA) {
+          float q = edge_q(s_row[k], row_w, eta_n, one_minus_eta);
+          s_row[k] = q;
           accq += (double)q;
         }
+#pragma unroll 8
+        for (int k = BLISS_STAGE_CAP + tid; k < d; k += BLISS_CTA)
+          accq += (double)edge_q(__ldg(wr + k), row_w, eta_n, one_minus_eta);
         row_q = __double2float_rn(block_sum(accq, s_red));
         if (tid == 0) {
           ws.row_w[row] = row_w;
@@ -237,22 +242,32 @@ __global__ void __launch_bounds__(BLISS_CTA, BLISS_PROB_CTAS_PER_SM) k_frontier_
         }
       }
       // pass C: scatter the squared normalised edge probabilities to the column accumulator
+      if (mode == BLISS_MODE_BANDIT && !uniform) {
+        const int d_st = min(d, BLISS_STAGE_CAP);
 #pragma unroll 4
-      for (int k = tid; k < d; k += BLISS_CTA) {
-        const int src = __ldg(idx + k);
-        float t = 0.0f;
-        if (uniform) {
-        } else if (mode == BLISS_MODE_BANDIT) {
-          float q = (k < BLISS_STAGE_CAP) ? s_row[k] : edge_q(__ldg(wr + k), row_w, eta_n, one_minus_eta);
-          float r = __fdiv_rn(q, row_q);
-          t = __fmul_rn(r, r);
-        } else {
-          float w = __ldg(wr + k);
-          t = __fmul_rn(w, w);
+        for (int k = tid; k < d_st; k += BLISS_CTA) {
+          const int src = __ldg(idx + k);
+          const float r = __fdiv_rn(s_row[k], row_q);
+          scatter_term(false, bitmap, __fmul_rn(r, r), src, fx_scale, ws);
         }
-        scatter_term(uniform, bitmap, t, src, fx_scale, ws);
+#pragma unroll 8
+        for (int k = BLISS_STAGE_CAP + tid; k < d; k += BLISS_CTA) {
+          const int src = __ldg(idx + k);
+          const float r = __fdiv_rn(edge_q(__ldg(wr + k), row_w, eta_n, one_minus_eta), row_q);
+          scatter_term(false, bitmap, __fmul_rn(r, r), src, fx_scale, ws);
+        }
+      } else {
+#pragma unroll 8
+        for (int k = tid; k < d; k += BLISS_CTA) {
+          const int src = __ldg(idx + k);
+          float t = 0.0f;
+          if (!uniform) {
+            const float w = __ldg(wr + k);
+            t = __fmul_rn(w, w);
+          }
+          scatter_term(uniform, bitmap, t, src, fx_scale, ws);
+        }
       }
-      __syncthreads();  // s_row is reused by the next row
     } else {
       // ---------------- light rows: one warp per row, values in registers ----------------
       const int li = (item - n_heavy) * BLISS_WARPS + warp_id();
@@ -309,6 +324,12 @@ __global__ void __launch_bounds__(BLISS_CTA, BLISS_PROB_CTAS_PER_SM) k_frontier_
         }
       }
     }
+    __syncthreads();  // s_row is reused by the next row; s_next[iter & 1] is complete
+    item = nxt;
+    a = na;
+    d = nd;
+    row = nrow;
+    nxt = s_next[iter & 1];
   }
 }
 
