@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink |V|,|E| (debug only; the metric is scale 1.0)")
     ap.add_argument("--normalize", type=str, default="lazy", choices=["lazy", "literal"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="disable the static-shape CUDA-graph replay of fwd/bwd/Adam")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -186,6 +187,7 @@ def main():
     config = {"workload": f"{workload}, 3-layer SAGE, poisson-bandit, batch {BATCH}/rank, fan-out 4096/2048/1024",
               "sampler": "poisson-bandit", "batch_per_rank": BATCH, "fan_out": FANOUT, "hidden": HIDDEN,
               "eta": ETA, "normalize": args.normalize, "parallelism": f"dp{world}",
+              "model_step": "eager" if args.eager else "cuda-graph replay over capacity-padded blocks",
               "l2": "inputs (CSC + 3 EXP3 weight layers + features ≈ 2.4 GB, random rows per step) exceed the 126 MB L2"}
 
     # ---------------- reference arm: the CPU path only ----------------
@@ -228,8 +230,8 @@ def main():
                     model="sage", seed=0, rank=rank, world_size=world, graph=g, normalize=args.normalize)
     torch.manual_seed(3)
     model = build_model("sage", dm.in_feats, HIDDEN, dm.n_classes, 3, DROPOUT).to(device)
-    tr = Trainer(dm, model, LR, pg)
-    n_need = args.warmup + 3 * args.steps + 8
+    tr = Trainer(dm, model, LR, pg, static_graph=not args.eager)
+    n_need = args.warmup + 3 * args.steps + 24
     host_batches = [b.pin_memory() for b in seed_batches_for(g, rank, world, n_need)]
     dev_batches = [b.to(device) for b in host_batches]
     it = iter(range(n_need))
@@ -239,7 +241,7 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3) + (0 if args.eager else tr.eager_warmup + 2)):   # + pool sizing and graph capture
         tr.training_step(dev_batches[next(it)])
 
     # ---- (1) device-resident throughput: EXACTLY `steps` steps between two events ----
@@ -317,7 +319,7 @@ def main():
            "sampled_edges_per_s": world * edges / (ms_total / 1e3), "clocks": clock_info,
            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": BATCH * 4 * world,
                    "d2h_bytes_per_step": (4 + 3 * 88) * world},
-           "gpu_launches": launches, "roofline": roofline}
+           "gpu_launches": launches, "graph_replays": tr.graph_replays, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         g_cpu = g.to("cpu")

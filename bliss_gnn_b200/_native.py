@@ -90,7 +90,7 @@ class BlockOut(C.Structure):
     _fields_ = [("indptr", C.c_void_p), ("edge_src", C.c_void_p), ("edge_dst", C.c_void_p),
                 ("csc_pos", C.c_void_p), ("eid", C.c_void_p), ("q_ij", C.c_void_p), ("edge_w", C.c_void_p),
                 ("src_nid", C.c_void_p), ("node_prob", C.c_void_p), ("out_deg", C.c_void_p),
-                ("heavy_rows", C.c_void_p), ("inv_deg", C.c_void_p), ("cap_edges", C.c_int64), ("cap_src", C.c_int64)]
+                ("heavy_rows", C.c_void_p), ("inv_deg", C.c_void_p), ("cap_edges", C.c_int64), ("cap_src", C.c_int64), ("pad_rows", C.c_int64)]
 
 
 _P, _I32, _I64, _U32, _U64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_double

@@ -758,6 +758,10 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
         hbase += ht;
       }
     }
+    // capacity padding (static-shape replay): rows beyond n_seeds are empty, their mean divisor is 1
+    for (int64_t i = n_seeds + 1 + threadIdx.x; i <= out.pad_rows; i += blockDim.x) out.indptr[i] = base;
+    if (out.inv_deg)
+      for (int64_t i = n_seeds + threadIdx.x; i < out.pad_rows; i += blockDim.x) out.inv_deg[i] = 1.0f;
     if (threadIdx.x == 0) {
       if (out.heavy_rows) out.heavy_rows[0] = hbase;
       out.indptr[n_seeds] = base;

@@ -69,10 +69,17 @@ class GraphConv(nn.Module):
     def forward(self, graph, feat, weight=None, edge_weight=None):
         src_norm = getattr(graph, "_gcn_src_norm", None)
         if src_norm is None:
-            src_norm = graph.out_degrees().to(torch.float32).clamp(min=1).pow(-0.5)
+            if getattr(graph, "csc_pos", None) is not None:   # sampled block: out-degrees from the transpose (no host sync)
+                t_indptr = ops.block_transpose(graph)[0]
+                out_deg = t_indptr[1:] - t_indptr[:-1]
+            else:                                             # whole-graph inference block
+                out_deg = graph.out_degrees()
+            src_norm = out_deg.to(torch.float32).clamp(min=1).pow(-0.5)
             dst_norm = graph.in_degrees().to(torch.float32).clamp(min=1).pow(-0.5)
-            graph._gcn_src_norm, graph._gcn_dst_norm = src_norm, dst_norm
-        dst_norm = graph._gcn_dst_norm
+            if graph.num_src_nodes() == src_norm.numel() and not getattr(graph, "_static_padded", False):
+                graph._gcn_src_norm, graph._gcn_dst_norm = src_norm, dst_norm
+        else:
+            dst_norm = graph._gcn_dst_norm
         w = self.weight
         if self._in_feats > self._out_feats:
             rst = ops.spmm(graph, torch.matmul(feat, w), edge_weight, src_scale=src_norm, dst_scale=dst_norm)

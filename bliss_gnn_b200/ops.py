@@ -47,6 +47,16 @@ def row_norm(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def block_transpose_into(block, pool):
+    """Build the transpose of ``block`` (exact sizes) into a LayerPool's capacity buffers: running the
+    scan over ``cap_src`` rows leaves the padded source rows empty (t_indptr tail = E_b)."""
+    E, n_dst = block.num_edges(), block.num_dst_nodes()
+    N.call("bliss_block_transpose", N.ptr(block.edge_src), N.ptr(block.edge_dst), E, pool.cap_src, n_dst,
+           N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_scratch), N.ptr(pool.t_dst), N.ptr(pool.t_perm),
+           N.ptr(pool.t_heavy), N.stream())
+    block._transpose = (pool.t_indptr[:block.num_src_nodes() + 1], pool.t_dst[:E], pool.t_perm[:E], pool.t_heavy)
+
+
 def block_transpose(block):
     """Source-major CSR of a block (cached on the block) for the backward aggregation."""
     if block._transpose is None:

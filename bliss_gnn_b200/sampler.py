@@ -75,6 +75,37 @@ class _Workspace:
         return N.Counters.from_buffer_copy(self.ctr_host.numpy().tobytes())
 
 
+class LayerPool:
+    """Persistent capacity-sized buffers of one layer's block (static addresses, so the model's
+    forward / backward over the *padded* block can be captured once in a CUDA graph and replayed).
+    Rows beyond the sampled counts are valid padding: empty destination rows (indptr tail = E_b,
+    mean divisor 1), source ids that stay valid node ids, edge slots beyond E_b never referenced."""
+
+    def __init__(self, device, cap_dst: int, cap_src: int, cap_edges: int, bandit: bool = True):
+        self.cap_dst, self.cap_src, self.cap_edges, self.bandit = int(cap_dst), int(cap_src), int(cap_edges), bandit
+        i32 = dict(dtype=torch.int32, device=device)
+        self.meta = torch.zeros(3 * (self.cap_dst + 1), **i32)
+        n = self.cap_dst + 1
+        self.indptr, self.heavy = self.meta[:n], self.meta[n:2 * n]
+        self.inv_deg = self.meta[2 * n:].view(torch.float32)[:self.cap_dst]
+        self.inv_deg.fill_(1.0)
+        self.e32 = torch.zeros((5, self.cap_edges), **i32)
+        self.csc_pos = torch.zeros(self.cap_edges, dtype=torch.int64, device=device)
+        self.src = torch.zeros(2 * self.cap_src, **i32)
+        self.src_nid = self.src[:self.cap_src]
+        self.node_prob = self.src[self.cap_src:].view(torch.float32)
+        self.t_indptr = torch.zeros(self.cap_src + 1, **i32)
+        self.t_cursor = torch.zeros(self.cap_src, **i32)
+        self.t_scratch = torch.zeros(self.cap_edges, **i32)
+        self.t_dst = torch.zeros(self.cap_edges, **i32)
+        self.t_perm = torch.zeros(self.cap_edges, **i32)
+        self.t_heavy = torch.zeros(self.cap_src + 1, **i32)
+        self.padded = None      # the capacity-sized Block the captured graph runs on
+
+    def fits(self, n_dst, n_src, n_edges) -> bool:
+        return n_dst <= self.cap_dst and n_src <= self.cap_src and n_edges <= self.cap_edges
+
+
 class Frontier:
     """What ``exp3_probabilities`` / ``compute_prob`` hand on (the reference's ``insg`` + ``edge_prob``)."""
 
@@ -245,17 +276,23 @@ class BanditLadiesSampler:
         N.call("bliss_block_index", N.ptr(fr.seeds), fr.n_seeds, C.byref(wsp.ws), C.byref(out), N.stream())
         return self._finish_block(fr, out, bufs)
 
-    def _block_out(self, fr: Frontier):
+    def _block_out(self, fr: Frontier, pool: Optional[LayerPool] = None):
         """Output descriptor of one layer: indptr / heavy list / mean divisor are sized by the seeds,
-        source arrays go to |V|-sized scratch until the counts are known."""
+        source arrays go to |V|-sized scratch until the counts are known.  With a :class:`LayerPool`
+        the arrays are the pool's persistent capacity buffers and indptr is padded to the capacity."""
         wsp, dev, n_s = fr.wsp, fr.g.device, fr.n_seeds
+        if pool is not None and n_s <= pool.cap_dst:
+            out = N.BlockOut(indptr=N.ptr(pool.indptr), src_nid=N.ptr(wsp.src_nid), node_prob=N.ptr(wsp.node_prob),
+                             heavy_rows=N.ptr(pool.heavy), inv_deg=N.ptr(pool.inv_deg), cap_edges=0,
+                             cap_src=fr.g.num_nodes(), pad_rows=pool.cap_dst)
+            return out, (pool.indptr[:n_s + 1], pool.heavy, pool.inv_deg[:n_s])
         meta = torch.empty(3 * (n_s + 1), dtype=torch.int32, device=dev)   # indptr | heavy | inv_deg (as f32)
         indptr, heavy, inv_deg = meta[:n_s + 1], meta[n_s + 1:2 * (n_s + 1)], meta[2 * (n_s + 1):].view(torch.float32)
         out = N.BlockOut(indptr=N.ptr(indptr), src_nid=N.ptr(wsp.src_nid), node_prob=N.ptr(wsp.node_prob),
                          heavy_rows=N.ptr(heavy), inv_deg=N.ptr(inv_deg), cap_edges=0, cap_src=fr.g.num_nodes())
         return out, (indptr, heavy, inv_deg[:n_s])
 
-    def _finish_block(self, fr: Frontier, out, bufs):
+    def _finish_block(self, fr: Frontier, out, bufs, pool: Optional[LayerPool] = None):
         """Read the layer's counters (the one host sync), size the edge arrays, fill + finish."""
         wsp, g, dev, n_s = fr.wsp, fr.g, fr.g.device, fr.n_seeds
         indptr, heavy, inv_deg = bufs
@@ -266,20 +303,31 @@ class BanditLadiesSampler:
         self.last_counters[fr.layer] = ctr
         n_src, E = int(ctr.n_src), int(ctr.n_edges)
         bandit = fr.mode == N.MODE_BANDIT
+        pooled = pool is not None and out.pad_rows > 0 and pool.fits(n_s, n_src, E)
+        if pool is not None and not pooled:
+            self.pool_overflow = True          # the caller grows the pool and re-captures
+            if out.pad_rows > 0:               # indptr lives in the pool but the block does not fit: detach it
+                indptr, heavy, inv_deg = indptr.clone(), heavy[:n_s + 1].clone(), inv_deg.clone()
         # one allocation for the 4-byte edge arrays, one for the 8-byte CSC positions
-        e32 = torch.empty((5 if bandit else 4, max(E, 1)), dtype=torch.int32, device=dev)
+        if pooled:
+            e32, csc_pos = pool.e32, pool.csc_pos[:E]
+        else:
+            e32 = torch.empty((5 if bandit else 4, max(E, 1)), dtype=torch.int32, device=dev)
+            csc_pos = torch.empty(E, dtype=torch.int64, device=dev)
         edge_src, edge_dst, eid = e32[0, :E], e32[1, :E], e32[2, :E]
         edge_w = e32[3, :E].view(torch.float32)
         q_ij = e32[4, :E].view(torch.float32) if bandit else None
-        csc_pos = torch.empty(E, dtype=torch.int64, device=dev)
         out.edge_src, out.edge_dst, out.csc_pos = N.ptr(edge_src), N.ptr(edge_dst), N.ptr(csc_pos)
         out.eid, out.edge_w, out.q_ij = N.ptr(eid), N.ptr(edge_w), N.ptr(q_ij)
         out.cap_edges = E
         N.call("bliss_sample_layer_back", C.byref(wsp.gview), N.ptr(fr.seeds), n_s, N.ptr(fr.weights),
                float(self.eta), fr.mode, C.byref(wsp.ws), C.byref(out), N.stream())
-        src = torch.empty(2 * n_src, dtype=torch.int32, device=dev)
-        src_nid = src[:n_src]
-        node_prob = src[n_src:].view(torch.float32)
+        if pooled:
+            src_nid, node_prob = pool.src_nid[:n_src], pool.node_prob[:n_src]
+        else:
+            src = torch.empty(2 * n_src, dtype=torch.int32, device=dev)
+            src_nid = src[:n_src]
+            node_prob = src[n_src:].view(torch.float32)
         src_nid.copy_(wsp.src_nid[:n_src])
         node_prob.copy_(wsp.node_prob[:n_src])
         block = Block(indptr, edge_src, edge_dst, src_nid, fr.seeds, graph=g, csc_pos=csc_pos)
@@ -301,17 +349,21 @@ class BanditLadiesSampler:
             s = (s.pin_memory() if s.device.type == "cpu" and not s.is_pinned() else s).to(g.device, non_blocking=True)
         return s.to(torch.int32).contiguous()
 
-    def sample_blocks(self, g, seed_nodes, exclude_eids=None):
-        """``bandit_sampler.py:341-367``."""
+    def sample_blocks(self, g, seed_nodes, exclude_eids=None, pools=None):
+        """``bandit_sampler.py:341-367``.  ``pools`` (one :class:`LayerPool` per layer, optional) makes
+        the blocks views of persistent capacity buffers (static-shape CUDA-graph replay, train.py)."""
         self._bind(g)
         seed_nodes = self._prep_seeds(g, seed_nodes)
         output_nodes = seed_nodes
         blocks = []
+        self.pool_overflow = False
         fused = self._stages_not_overridden()
+        self.pool_used = bool(fused and pools)
         for block_id in reversed(range(len(self.nodes_per_layer))):              # :350
             num = self.nodes_per_layer[block_id]
             if fused:   # same kernels, two FFI calls per layer instead of eight
-                block = self._sample_layer_fused(g, seed_nodes, block_id, num, self._w_csc[block_id])
+                block = self._sample_layer_fused(g, seed_nodes, block_id, num, self._w_csc[block_id],
+                                                 pools[block_id] if pools else None)
                 seed_nodes = block.srcdata[NID]
                 blocks.insert(0, block)
                 continue
@@ -333,7 +385,7 @@ class BanditLadiesSampler:
             return False
         return all(getattr(type(self), m).__module__ == __name__ for m in self._STAGES)
 
-    def _sample_layer_fused(self, g, seed_nodes, block_id, num, weights):
+    def _sample_layer_fused(self, g, seed_nodes, block_id, num, weights, pool: Optional[LayerPool] = None):
         wsp = self._wsp
         n = int(seed_nodes.numel())
         fr = Frontier(g, wsp, seed_nodes, n, block_id, self._mode, weights)
@@ -342,11 +394,11 @@ class BanditLadiesSampler:
             mode |= N.COLLECT_BITMAP
         if not self._poisson and wsp.key_scratch is None:
             wsp.key_scratch = torch.empty(g.num_nodes() + 4, dtype=torch.float32, device=g.device)
-        out, bufs = self._block_out(fr)
+        out, bufs = self._block_out(fr, pool)
         N.call("bliss_sample_layer_front", C.byref(wsp.gview), N.ptr(seed_nodes), n, N.ptr(weights), float(self.eta),
                mode, int(num), float(self.eps), int(self._poisson), self.rng_seed, self.step, block_id,
                self._u_ptr(g, block_id), N.ptr(wsp.key_scratch), C.byref(wsp.ws), C.byref(out), N.stream())
-        return self._finish_block(fr, out, bufs)
+        return self._finish_block(fr, out, bufs, pool)
 
     # ---- bandit update ------------------------------------------------------------------------
     def calculate_alpha(self, mfg):

@@ -121,8 +121,17 @@ def build_model(name: str, in_feats, n_hidden, n_classes, n_layers, dropout=0.1,
 class Trainer:
     """One training step = the hot path end to end (``train_lightning.py:100-168,463-471``)."""
 
-    def __init__(self, datamodule: DataModule, model: nn.Module, lr=0.002, process_group=None):
+    def __init__(self, datamodule: DataModule, model: nn.Module, lr=0.002, process_group=None,
+                 static_graph: bool = False, eager_warmup: int = 4):
+        """``static_graph=True``: after ``eager_warmup`` ordinary steps the blocks are built into
+        capacity-padded persistent buffers (``sampler.LayerPool``) and the model's forward, backward
+        and Adam step run as ONE replayed CUDA graph — the step stops being bound by Python dispatch.
+        Sampling and the bandit update stay eager (their sizes are data dependent)."""
         self.dm, self.model, self.pg = datamodule, model, process_group
+        self.static_graph, self.eager_warmup = bool(static_graph), int(eager_warmup)
+        self._graph, self._pools, self._padded = None, None, None
+        self._max_src, self._max_edges = None, None
+        self.graph_replays = 0
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.loss_fn = nn.BCEWithLogitsLoss() if datamodule.multilabel else nn.CrossEntropyLoss()   # :77-79
         # one flat gradient buffer: a single all-reduce per step (~0.46 M parameters for SAGE/Reddit)
@@ -130,7 +139,8 @@ class Trainer:
         params = self.grads.params
         self._flat_grad = self.grads.flat
         fused = params[0].is_cuda
-        self.optimizer = torch.optim.Adam(params, lr=lr, fused=fused)            # :206
+        self.optimizer = torch.optim.Adam(params, lr=lr, fused=fused,
+                                          capturable=bool(static_graph and fused))   # :206
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, gamma=0.01, step_size=5)   # :208 (per epoch)
         if process_group is not None and hasattr(datamodule.sampler, "process_group"):
             datamodule.sampler.process_group = process_group
@@ -156,8 +166,14 @@ class Trainer:
         return self.cum_sampled_nodes[i] * (1 - self.w) / (1 - self.w ** self.num_steps)
 
     def training_step(self, seeds: torch.Tensor) -> torch.Tensor:
+        if self.static_graph:
+            return self._training_step_static(seeds)
         dm, g = self.dm, self.dm.g
         input_nodes, output_nodes, mfgs = dm.sampler.sample_blocks(g, seeds)
+        return self._eager_rest(mfgs)
+
+    def _eager_rest(self, mfgs):
+        dm, g = self.dm, self.dm.g
         self._ema(mfgs)
         batch_inputs = mfgs[0].srcdata["features"]                               # :138  (gather kernel)
         batch_labels = mfgs[-1].dstdata["labels"]                                # :139
@@ -169,8 +185,111 @@ class Trainer:
         self.optimizer.step()
         if "bandit" in dm.sampler_name:                                          # :469-471
             dm.sampler.exp3(mfgs, g)
-        self.last_blocks, self.last_pred, self.last_labels = mfgs, batch_pred, batch_labels
-        return loss
+        # detached: nothing may keep this step's autograd graph (and its AccumulateGrad nodes) alive,
+        # or a later CUDA-graph capture would see nodes bound to another stream
+        self.last_blocks, self.last_pred, self.last_labels = mfgs, batch_pred.detach(), batch_labels
+        return loss.detach()
+
+    # ---- static-shape path: padded blocks + one CUDA graph for forward/backward/Adam ---------------
+    def _alloc_pools(self):
+        from .sampler import LayerPool
+        from .graph import Block
+        dm, g = self.dm, self.dm.g
+        fan, L = dm.sampler.nodes_per_layer, len(dm.sampler.nodes_per_layer)
+        dev = g.device
+        self._seeds_static = torch.zeros(dm.batch_size, dtype=torch.int32, device=dev)
+        pools, cd = [None] * L, dm.batch_size
+        for l in reversed(range(L)):                       # output layer first: cap_dst[l] = cap_src[l+1]
+            cap_src = max(cd + int(1.3 * fan[l]) + 256, int(1.25 * self._max_src[l]) + 64)
+            cap_e = int(1.6 * self._max_edges[l]) + 4096
+            pools[l] = LayerPool(dev, cd, cap_src, cap_e, bandit="bandit" in dm.sampler_name)
+            cd = cap_src
+        padded = []
+        for l in range(L):
+            pool = pools[l]
+            dst_nid = pools[l + 1].src_nid if l < L - 1 else self._seeds_static
+            pb = Block(pool.indptr, pool.e32[0], pool.e32[1], pool.src_nid, dst_nid, graph=g, csc_pos=pool.csc_pos)
+            pb.heavy_rows, pb._mean_scale, pb._static_padded = pool.heavy, pool.inv_deg, True
+            pb.edata["edge_weights"] = pool.e32[3].view(torch.float32)
+            pb._transpose = (pool.t_indptr, pool.t_dst, pool.t_perm, pool.t_heavy)
+            pool.padded = pb
+            padded.append(pb)
+        self._pools, self._padded, self._graph = pools, padded, None
+
+    def _padded_fwd_bwd(self, step_optimizer: bool):
+        g = self.dm.g
+        x = ops.gather_rows(g.ndata["features"], self._pools[0].src_nid)
+        y = g.ndata["labels"][self._seeds_static.long()]
+        pred = self.model(self._padded, x)[: self.dm.batch_size]
+        loss = self.loss_fn(pred, y)
+        self._flat_grad.zero_()
+        loss.backward()
+        if step_optimizer:
+            self.optimizer.step()
+        return loss.detach(), pred.detach(), y
+
+    def _capture(self):
+        self.last_pred = None
+        for pb in self._padded:                            # drop tensors of earlier forward passes
+            for k in ("embed_norm",):
+                dict.pop(pb.srcdata, k, None)
+            dict.pop(pb.edata, "a_ij", None)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up off the default stream (no optimizer step)
+            for _ in range(2):
+                self._padded_fwd_bwd(False)
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss, self._static_pred, self._static_y = self._padded_fwd_bwd(self.world == 1)
+
+    def _training_step_static(self, seeds: torch.Tensor) -> torch.Tensor:
+        dm, g, smp = self.dm, self.dm.g, self.dm.sampler
+        L = len(smp.nodes_per_layer)
+        if self._pools is None:
+            if self.num_steps < self.eager_warmup or seeds.numel() != dm.batch_size:
+                _, _, mfgs = smp.sample_blocks(g, seeds)
+                if self._max_src is None:
+                    self._max_src, self._max_edges = [0] * L, [0] * L
+                for l, b in enumerate(mfgs):
+                    self._max_src[l] = max(self._max_src[l], b.num_src_nodes())
+                    self._max_edges[l] = max(self._max_edges[l], b.num_edges())
+                return self._eager_rest(mfgs)
+            self._alloc_pools()
+        if seeds.numel() != dm.batch_size:                  # ragged last batch: ordinary path
+            _, _, mfgs = smp.sample_blocks(g, seeds)
+            return self._eager_rest(mfgs)
+        self._seeds_static.copy_(seeds, non_blocking=True)
+        _, _, mfgs = smp.sample_blocks(g, self._seeds_static, pools=self._pools)
+        if not smp.pool_used:                               # per-stage sampler path (overridden stage / profiling)
+            return self._eager_rest(mfgs)
+        if smp.pool_overflow:                               # rare: grow the capacities, re-capture next step
+            for l, b in enumerate(mfgs):
+                self._max_src[l] = max(self._max_src[l], b.num_src_nodes())
+                self._max_edges[l] = max(self._max_edges[l], b.num_edges())
+            loss = self._eager_rest(mfgs)
+            self._alloc_pools()
+            return loss
+        for l, b in enumerate(mfgs):
+            ops.block_transpose_into(b, self._pools[l])
+        if self._graph is None:
+            self._capture()
+        self._ema(mfgs)
+        self._graph.replay()
+        self.graph_replays += 1
+        if self.world > 1:
+            self.grads.all_reduce_mean_(self.pg)
+            self.optimizer.step()
+        for l, b in enumerate(mfgs):                        # what exp3 reads from the forward pass
+            pb = self._padded[l]
+            b.srcdata["embed_norm"] = pb.srcdata["embed_norm"][: b.num_src_nodes()]
+            if "a_ij" in dict.keys(pb.edata):
+                b.edata["a_ij"] = pb.edata["a_ij"][: b.num_edges()]
+        if "bandit" in dm.sampler_name:
+            smp.exp3(mfgs, g)
+        self.last_blocks, self.last_pred, self.last_labels = mfgs, self._static_pred, self._static_y
+        return self._static_loss
 
     @torch.no_grad()
     def validate(self) -> float:

@@ -107,6 +107,8 @@ typedef struct bliss_block_out {
   float*   inv_deg;     /* [n_seeds] 1 / max(block in-degree, 1)  (fn.mean divisor; NULL ok)  */
   int64_t  cap_edges;
   int64_t  cap_src;
+  int64_t  pad_rows;    /* > n_seeds: indptr[n_seeds+1..pad_rows] = E_b, inv_deg[n_seeds..pad_rows) = 1
+                           (capacity-padded blocks for CUDA-graph replay); 0 = no padding          */
 } bliss_block_out;
 
 int bliss_version(void);
