@@ -124,6 +124,7 @@ PROTOTYPES = {
     "bliss_reward_update": [_GP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _I32, _I64,
                             _P, _P, _P, _P, _P],
     "bliss_apply_updates": [_P, _P, _I64, _P, _P, _P],
+    "bliss_apply_updates_packed": [_P, _I64, _I32, _I64, _I64, _I64, _I64, _P, _P, _P],
     "bliss_l1_norm": [_P, _I64, _P, _P, _P],
     "bliss_scale_by_inv": [_P, _I64, _P, _D, _P],
 }

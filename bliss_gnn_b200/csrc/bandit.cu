@@ -130,6 +130,40 @@ __global__ void __launch_bounds__(256) k_apply_updates(const int64_t* __restrict
   }
 }
 
+// Apply every rank's update of one layer straight from the all-gathered exchange buffer:
+// per rank a header of int64 counts, then per layer int64 positions and fp32 exponents.
+__global__ void __launch_bounds__(256) k_apply_updates_packed(const unsigned char* __restrict__ recv,
+                                                             int64_t rank_stride, int world, int64_t count_off,
+                                                             int64_t pos_off, int64_t x_off, int64_t cap,
+                                                             float* exp3_w, double* l1_delta) {
+  __shared__ double s_red[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t total = (int64_t)world * cap;
+  double dsum = 0.0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int r = (int)(t / cap);
+    const int64_t k = t - (int64_t)r * cap;
+    const unsigned char* base = recv + (int64_t)r * rank_stride;
+    const int64_t n = *reinterpret_cast<const int64_t*>(base + count_off);
+    if (k >= n) continue;
+    const int64_t pos = reinterpret_cast<const int64_t*>(base + pos_off)[k];
+    const float f = expf(reinterpret_cast<const float*>(base + x_off)[k]);
+    float* addr = exp3_w + pos;
+    unsigned old = __float_as_uint(*addr), assumed;
+    do {  // two ranks may have sampled the same edge: multiplicative update through a CAS loop
+      assumed = old;
+      old = atomicCAS(reinterpret_cast<unsigned*>(addr), assumed,
+                      __float_as_uint(__fmul_rn(__uint_as_float(assumed), f)));
+    } while (old != assumed);
+    const float w_old = __uint_as_float(old);
+    dsum += (double)__fmul_rn(w_old, f) - (double)w_old;
+  }
+  if (l1_delta) {
+    dsum = block_sum(dsum, s_red);
+    if (threadIdx.x == 0 && dsum != 0.0) atomicAdd(l1_delta, dsum);
+  }
+}
+
 // literal F.normalize(w, p=1): fixed two-level tree -> deterministic
 #define BLISS_NORM_BLOCKS 1024
 __global__ void __launch_bounds__(256) k_l1_partial(const float* __restrict__ w, int64_t n, double* __restrict__ partial) {
@@ -236,6 +270,18 @@ int bliss_apply_updates(const int64_t* pos, const float* x, int64_t n, float* ex
   if (n == 0) return 0;
   if (!pos || !x) return -1;
   k_apply_updates<<<grid_for(n, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(pos, x, n, exp3_w_csc, l1_delta);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_apply_updates_packed(const void* recv, int64_t rank_stride_bytes, int32_t world, int64_t count_off,
+                               int64_t pos_off, int64_t x_off, int64_t cap, float* exp3_w_csc, double* l1_delta,
+                               void* stream) {
+  if (!recv || !exp3_w_csc || world <= 0 || cap < 0 || rank_stride_bytes <= 0) return -1;
+  if ((count_off | pos_off) & 7 || (x_off & 3)) return -1;
+  if (cap == 0) return 0;
+  k_apply_updates_packed<<<grid_for((int64_t)world * cap, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(
+      (const unsigned char*)recv, rank_stride_bytes, world, count_off, pos_off, x_off, cap, exp3_w_csc, l1_delta);
   BLISS_CHECK_LAUNCH();
   return 0;
 }

@@ -60,3 +60,40 @@ def gather_updates(pos: torch.Tensor, x: torch.Tensor, group) -> List[Tuple[torc
     dist.all_gather(pos_all, pos_pad, group=group)
     dist.all_gather(x_all, x_pad, group=group)
     return [(pos_all[r][:sizes[r]], x_all[r][:sizes[r]]) for r in range(world)]
+
+
+class BanditExchange:
+    """One all-gather per step for the sparse bandit updates of all layers.
+
+    Send buffer of a rank: ``[int64 count per layer (64 B header) | layer 0: int64 pos[cap0], fp32 x[cap0] |
+    layer 1 … ]``.  ``pos[l]`` doubles as the block's ``csc_pos`` array (the sampler writes it in place) and the
+    reward kernel writes ``x[l]`` in place, so nothing is packed or copied before the collective, and the apply
+    kernel reads the counts from the gathered headers — no host-side sizes, no host sync."""
+
+    HEADER = 64
+
+    def __init__(self, caps, world, device, group):
+        self.caps, self.world, self.group = [int(c) for c in caps], int(world), group
+        assert len(caps) * 8 <= self.HEADER
+        off, self.pos_off, self.x_off = self.HEADER, [], []
+        for c in self.caps:
+            self.pos_off.append(off)
+            off += 8 * c
+            self.x_off.append(off)
+            off += 4 * c
+            off = (off + 15) // 16 * 16
+        self.stride = off
+        self.send = torch.zeros(off, dtype=torch.uint8, device=device)
+        self.recv = torch.zeros(self.world * off, dtype=torch.uint8, device=device)
+        self.header = self.send[:self.HEADER].view(torch.int64)
+        self.pos = [self.send[o:o + 8 * c].view(torch.int64) for o, c in zip(self.pos_off, self.caps)]
+        self.x = [self.send[o:o + 4 * c].view(torch.float32) for o, c in zip(self.x_off, self.caps)]
+        self._hdr_host = torch.zeros(self.HEADER // 8, dtype=torch.int64)
+        if device.type == "cuda":
+            self._hdr_host = self._hdr_host.pin_memory()
+
+    def exchange(self, counts):
+        for l, c in enumerate(counts):
+            self._hdr_host[l] = int(c)
+        self.header.copy_(self._hdr_host, non_blocking=True)
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)

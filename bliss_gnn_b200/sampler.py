@@ -81,7 +81,7 @@ class LayerPool:
     Rows beyond the sampled counts are valid padding: empty destination rows (indptr tail = E_b,
     mean divisor 1), source ids that stay valid node ids, edge slots beyond E_b never referenced."""
 
-    def __init__(self, device, cap_dst: int, cap_src: int, cap_edges: int, bandit: bool = True):
+    def __init__(self, device, cap_dst: int, cap_src: int, cap_edges: int, bandit: bool = True, csc_pos=None):
         self.cap_dst, self.cap_src, self.cap_edges, self.bandit = int(cap_dst), int(cap_src), int(cap_edges), bandit
         i32 = dict(dtype=torch.int32, device=device)
         self.meta = torch.zeros(3 * (self.cap_dst + 1), **i32)
@@ -90,7 +90,9 @@ class LayerPool:
         self.inv_deg = self.meta[2 * n:].view(torch.float32)[:self.cap_dst]
         self.inv_deg.fill_(1.0)
         self.e32 = torch.zeros((5, self.cap_edges), **i32)
-        self.csc_pos = torch.zeros(self.cap_edges, dtype=torch.int64, device=device)
+        # in data-parallel runs csc_pos is the position array of the bandit exchange's send buffer
+        self.csc_pos = csc_pos if csc_pos is not None else torch.zeros(self.cap_edges, dtype=torch.int64, device=device)
+        assert self.csc_pos.numel() == self.cap_edges and self.csc_pos.dtype == torch.int64
         self.src = torch.zeros(2 * self.cap_src, **i32)
         self.src_nid = self.src[:self.cap_src]
         self.node_prob = self.src[self.cap_src:].view(torch.float32)
@@ -466,12 +468,28 @@ class BanditLadiesSampler:
         N.call("bliss_scale_by_inv", N.ptr(w), w.numel(), N.ptr(self._l1[idx:idx + 1]), 1e-12, N.stream())
         self._l1[idx] = 1.0
 
-    def exp3(self, mfgs, g):
-        """``bandit_sampler.py:251-267``: reward + weight update of every layer, one fused kernel each."""
+    def exp3(self, mfgs, g, exchange=None):
+        """``bandit_sampler.py:251-267``: reward + weight update of every layer, one fused kernel each.
+        ``exchange`` (a ``parallel.BanditExchange``) selects the data-parallel fast path: exponents are
+        written into the exchange's send buffer, ONE all-gather moves all layers, one kernel per layer
+        applies every rank's update."""
         self._bind(g)
-        for idx, mfg in enumerate(mfgs):
-            alpha = self.calculate_alpha(mfg)
-            self.update_exp3_weights(idx, mfg, g, alpha)
+        if exchange is not None and all(m.csc_pos.data_ptr() == exchange.pos[i].data_ptr() and
+                                        m.num_edges() <= exchange.caps[i] for i, m in enumerate(mfgs)):
+            for idx, mfg in enumerate(mfgs):
+                self._reward_call(idx, mfg, g, self.calculate_alpha(mfg), None, x_out=exchange.x[idx])
+            exchange.exchange([m.num_edges() for m in mfgs])
+            for idx in range(len(mfgs)):
+                N.call("bliss_apply_updates_packed", N.ptr(exchange.recv), exchange.stride, exchange.world,
+                       8 * idx, exchange.pos_off[idx], exchange.x_off[idx], exchange.caps[idx],
+                       N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]), N.stream())
+                self._updated[idx] = True
+                if self.normalize == "literal":
+                    self._renormalize(idx)
+        else:
+            for idx, mfg in enumerate(mfgs):
+                alpha = self.calculate_alpha(mfg)
+                self.update_exp3_weights(idx, mfg, g, alpha)
         if self.normalize == "lazy":
             self._updates_since_renorm += 1
             if self._updates_since_renorm >= self.renorm_every:   # range safety: growth ≤ e per step

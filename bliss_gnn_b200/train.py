@@ -129,7 +129,7 @@ class Trainer:
         Sampling and the bandit update stay eager (their sizes are data dependent)."""
         self.dm, self.model, self.pg = datamodule, model, process_group
         self.static_graph, self.eager_warmup = bool(static_graph), int(eager_warmup)
-        self._graph, self._pools, self._padded = None, None, None
+        self._graph, self._pools, self._padded, self._exchange = None, None, None, None
         self._max_src, self._max_edges = None, None
         self.graph_replays = 0
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
@@ -198,11 +198,20 @@ class Trainer:
         fan, L = dm.sampler.nodes_per_layer, len(dm.sampler.nodes_per_layer)
         dev = g.device
         self._seeds_static = torch.zeros(dm.batch_size, dtype=torch.int32, device=dev)
+        bandit = "bandit" in dm.sampler_name
+        cap_e = [int(1.6 * self._max_edges[l]) + 4096 for l in range(L)]
+        self._exchange = None
+        if self.world > 1 and bandit:                       # ranks must agree on the exchange layout
+            from .parallel import BanditExchange
+            t = torch.tensor(cap_e, dtype=torch.int64, device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+            cap_e = [int(v) for v in t.tolist()]
+            self._exchange = BanditExchange(cap_e, self.world, dev, self.pg)
         pools, cd = [None] * L, dm.batch_size
         for l in reversed(range(L)):                       # output layer first: cap_dst[l] = cap_src[l+1]
             cap_src = max(cd + int(1.3 * fan[l]) + 256, int(1.25 * self._max_src[l]) + 64)
-            cap_e = int(1.6 * self._max_edges[l]) + 4096
-            pools[l] = LayerPool(dev, cd, cap_src, cap_e, bandit="bandit" in dm.sampler_name)
+            pools[l] = LayerPool(dev, cd, cap_src, cap_e[l], bandit=bandit,
+                                 csc_pos=self._exchange.pos[l] if self._exchange is not None else None)
             cd = cap_src
         padded = []
         for l in range(L):
@@ -287,7 +296,7 @@ class Trainer:
             if "a_ij" in dict.keys(pb.edata):
                 b.edata["a_ij"] = pb.edata["a_ij"][: b.num_edges()]
         if "bandit" in dm.sampler_name:
-            smp.exp3(mfgs, g)
+            smp.exp3(mfgs, g, exchange=self._exchange)
         self.last_blocks, self.last_pred, self.last_labels = mfgs, self._static_pred, self._static_y
         return self._static_loss
 

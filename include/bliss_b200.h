@@ -222,6 +222,13 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
 /* apply gathered updates from other ranks: w[pos[k]] *= exp(x[k]) */
 int bliss_apply_updates(const int64_t* pos, const float* x, int64_t n, float* exp3_w_csc,
                         double* l1_delta, void* stream);
+/* data-parallel fast path: apply all ranks' updates of one layer straight from the all-gathered
+ * exchange buffer (per rank: int64 count at count_off, int64 pos[cap] at pos_off, fp32 x[cap] at
+ * x_off; offsets in bytes).  The reward kernel wrote x into the send buffer, the block's csc_pos
+ * array is the send buffer's pos array — no packing pass, no host-side sizes. */
+int bliss_apply_updates_packed(const void* recv, int64_t rank_stride_bytes, int32_t world,
+                               int64_t count_off, int64_t pos_off, int64_t x_off, int64_t cap,
+                               float* exp3_w_csc, double* l1_delta, void* stream);
 /* literal F.normalize(p=1) of one layer's weights (bandit_sampler.py:249): two launches. */
 int bliss_l1_norm(const float* w, int64_t n, double* partial /* [1024] */, double* out /* [1] */,
                   void* stream);

@@ -302,3 +302,36 @@ def test_gat_alpha_rewards(native_lib):
     dev.exp3(db, gd)
     w_dev, w_ora = dev.exp3_weights.cpu().double(), ora.exp3_weights.double()
     assert ((w_dev - w_ora).abs() / w_ora).max().item() <= 1e-4
+
+
+def test_packed_exchange_apply_matches_sequential_updates(native_lib):
+    """The data-parallel apply kernel on a hand-built 2-rank exchange buffer (no NCCL needed): every
+    rank's (position, exponent) list multiplies into the weights, shared positions included."""
+    from bliss_gnn_b200 import _native as N
+    from bliss_gnn_b200.parallel import BanditExchange
+    dev = _dev()
+    E, caps, world = 5000, [700, 300], 2
+    ex = BanditExchange(caps, world, dev, group=None)
+    gen = torch.Generator().manual_seed(0)
+    w = [torch.rand(E, generator=gen) + 0.5 for _ in caps]
+    w_dev = [x.to(dev).clone() for x in w]
+    l1 = torch.zeros(len(caps), dtype=torch.float64, device=dev)
+    expect = [x.double().clone() for x in w]
+    for r in range(world):
+        base = ex.recv[r * ex.stride:(r + 1) * ex.stride]
+        for l, cap in enumerate(caps):
+            n = cap - 50 * (r + 1)
+            pos = torch.randperm(E, generator=gen)[:n]
+            if r == 1:
+                pos[:20] = torch.arange(20)           # positions both ranks may hit
+            xs = torch.rand(n, generator=gen) * 0.01
+            base[:64].view(torch.int64)[l] = n
+            base[ex.pos_off[l]:ex.pos_off[l] + 8 * n].view(torch.int64).copy_(pos)
+            base[ex.x_off[l]:ex.x_off[l] + 4 * n].view(torch.float32).copy_(xs)
+            expect[l][pos] = expect[l][pos] * torch.exp(xs.double())
+    for l in range(len(caps)):
+        N.call("bliss_apply_updates_packed", N.ptr(ex.recv), ex.stride, world, 8 * l, ex.pos_off[l], ex.x_off[l],
+               caps[l], N.ptr(w_dev[l]), N.ptr(l1[l:l + 1]), N.stream())
+        torch.testing.assert_close(w_dev[l].cpu().double(), expect[l], rtol=1e-6, atol=0)
+        delta = float(l1[l].item())
+        assert abs(delta - float((expect[l] - w[l].double()).sum())) <= 1e-5 * abs(delta)

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from bliss_gnn_b200.parallel import FlatGrads, gather_updates, shard_batches
+from bliss_gnn_b200.parallel import BanditExchange, FlatGrads, gather_updates, shard_batches
 from oracle import samplers as osamp
 from tests.util import philox_uniform_fn, random_graph
 
@@ -64,6 +64,23 @@ def _worker(rank, init_file, result_file):
         for eid_r, x_r in gather_updates(eid, xe.float(), dist.group.WORLD):
             w[l, eid_r] = w[l, eid_r] * torch.exp(x_r)               # edge ids are unique within a rank's block
         w[l] = w[l] / w[l].double().sum().float()
+    # (4) the packed one-collective exchange carries exactly the same (position, exponent) lists
+    caps = [max(int(e.numel()) for e, _ in upd) + 7 + rank * 0] * len(upd)
+    t = torch.tensor(caps)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ex = BanditExchange(t.tolist(), WORLD, torch.device("cpu"), dist.group.WORLD)
+    for l, (eid, xe) in enumerate(upd):
+        ex.pos[l][:eid.numel()] = eid
+        ex.x[l][:eid.numel()] = xe.float()
+    ex.exchange([e.numel() for e, _ in upd])
+    for l, (eid, xe) in enumerate(upd):
+        ref = gather_updates(eid, xe.float(), dist.group.WORLD)
+        for r in range(WORLD):
+            base = ex.recv[r * ex.stride:(r + 1) * ex.stride]
+            n = int(base[:64].view(torch.int64)[l])
+            pos_r = base[ex.pos_off[l]:ex.pos_off[l] + 8 * n].view(torch.int64)
+            x_r = base[ex.x_off[l]:ex.x_off[l] + 4 * n].view(torch.float32)
+            assert n == ref[r][0].numel() and torch.equal(pos_r, ref[r][0]) and torch.equal(x_r, ref[r][1])
     if rank == 0:
         torch.save(w, result_file)
     dist.barrier()
