@@ -131,7 +131,7 @@ class Trainer:
         self.static_graph, self.eager_warmup = bool(static_graph), int(eager_warmup)
         self._graph, self._pools, self._padded, self._exchange = None, None, None, None
         self._max_src, self._max_edges = None, None
-        self.graph_replays = 0
+        self.graph_replays, self.graph_kernels = 0, 0
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.loss_fn = nn.BCEWithLogitsLoss() if datamodule.multilabel else nn.CrossEntropyLoss()   # :77-79
         # one flat gradient buffer: a single all-reduce per step (~0.46 M parameters for SAGE/Reddit)
@@ -249,9 +249,13 @@ class Trainer:
             for _ in range(2):
                 self._padded_fwd_bwd(False)
         torch.cuda.current_stream().wait_stream(side)
+        from . import _native
+        before = _native.STATS.launches
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_loss, self._static_pred, self._static_y = self._padded_fwd_bwd(self.world == 1)
+        self.graph_kernels = _native.STATS.launches - before    # hand-written kernels inside one replay
+        _native.STATS.launches = before
 
     def _training_step_static(self, seeds: torch.Tensor) -> torch.Tensor:
         dm, g, smp = self.dm, self.dm.g, self.dm.sampler
