@@ -80,7 +80,7 @@ class Counters(C.Structure):
 
 class Workspace(C.Structure):
     _fields_ = [("acc", C.c_void_p), ("first_pos", C.c_void_p), ("node_info", C.c_void_p),
-                ("sel_bits", C.c_void_p), ("cand_bits", C.c_void_p), ("cand", C.c_void_p), ("p_cand", C.c_void_p), ("sel", C.c_void_p),
+                ("sel_bits", C.c_void_p), ("cand_bits", C.c_void_p), ("keep_bits", C.c_void_p), ("cand", C.c_void_p), ("p_cand", C.c_void_p), ("sel", C.c_void_p),
                 ("row_list", C.c_void_p), ("pos_a", C.c_void_p), ("pos_d", C.c_void_p), ("row_w", C.c_void_p), ("row_q", C.c_void_p),
                 ("row_cnt", C.c_void_p), ("row_t", C.c_void_p), ("cap_seeds", C.c_int64),
                 ("cap_sel", C.c_int64), ("ctr", C.c_void_p)]

@@ -676,54 +676,106 @@ __device__ __forceinline__ void note_first(int src, unsigned long long key, cons
   }
 }
 
+// One keep-bit per CSC edge position.  A warp handles one globally aligned 32-position word at a
+// time (perfectly coalesced index loads); interior words are plain stores, the first / last word
+// of a row is shared with the neighbouring CSC columns and is updated with and/or atomics.
+// Kept edges are sparse in a row (~8 % of the bits), so the dependent random accesses of
+// note_first (node_info -> first_pos -> atomicMin) are not done inside the word loop, where only
+// 2-3 lanes per warp would be active: the kept (position, source) pairs go to a shared-memory
+// list and are processed densely afterwards, one pair per thread.
+#define BLISS_LIST_CAP 2048
 __global__ void __launch_bounds__(BLISS_CTA) k_block_count(GraphView g, const int32_t* __restrict__ seeds,
                                                           bliss_workspace ws) {
   __shared__ int s_red[32];
-  __shared__ int s_item;
+  __shared__ int s_next[2];
+  __shared__ int s_k[BLISS_LIST_CAP], s_src[BLISS_LIST_CAP];
+  __shared__ int s_cnt;
   bliss_counters* ctr = ws.ctr;
   const int n_seeds = ctr->n_seeds, n_heavy = ctr->n_heavy, n_light = ctr->n_light;
   const int n_items = n_heavy + (n_light + BLISS_WARPS - 1) / BLISS_WARPS;
-  const int tid = threadIdx.x;
-  for (;;) {
-    int item = next_item(&ctr->queue[1], n_items, &s_item);
-    if (item < 0) break;
-    if (item < n_heavy) {
-      const int row = ws.row_list[item];
-      const int64_t a = ws.pos_a[item];
-      const int d = ws.pos_d[item];
-      const int32_t* __restrict__ idx = g.indices + a;
+  const int tid = threadIdx.x, lane = lane_id();
+  constexpr int LIGHT_CAP = BLISS_LIST_CAP / BLISS_WARPS;   // 256 = BLISS_LIGHT_MAX
+  // same longest-first dynamic queue with two-item look-ahead as k_frontier_prob
+  int item = blockIdx.x, nxt = gridDim.x + blockIdx.x, iter = 0;
+  for (; item < n_items; ++iter) {
+    if (tid == 0) {
+      s_next[iter & 1] = 2 * gridDim.x + atomicAdd(&ctr->queue[1], 1);
+      s_cnt = 0;
+    }
+    __syncthreads();
+    const bool heavy = item < n_heavy;
+    const int li = heavy ? 0 : (item - n_heavy) * BLISS_WARPS + warp_id();
+    if (heavy || li < n_light) {
+      const int pos = heavy ? item : n_seeds - 1 - li;
+      const int row = ws.row_list[pos];
+      const int64_t a = ws.pos_a[pos];
+      const int64_t end = a + ws.pos_d[pos];
       const unsigned long long key_hi = (unsigned long long)(row + 1) << 32;
+      const int64_t w_lo = a >> 5, w_hi = (end + 31) >> 5;   // [w_lo, w_hi)
       int cnt = 0;
-#pragma unroll 4
-      for (int k = tid; k < d; k += BLISS_CTA) {
-        int src = __ldg(idx + k);
-        if (test_bit(ws.sel_bits, src)) {
-          ++cnt;
-          note_first(src, key_hi | (unsigned)k, ws);
+      const int wstep = heavy ? BLISS_WARPS : 1;
+      int* lk = heavy ? s_k : s_k + warp_id() * LIGHT_CAP;
+      int* ls = heavy ? s_src : s_src + warp_id() * LIGHT_CAP;
+      const int cap = heavy ? BLISS_LIST_CAP : LIGHT_CAP;
+      constexpr int U = 4;   // words in flight per warp: the index loads and bitmap tests are independent
+      for (int64_t w0 = w_lo + (heavy ? warp_id() : 0); w0 < w_hi; w0 += (int64_t)U * wstep) {
+        int srcv[U];
+        bool inr[U], kp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t p = ((w0 + (int64_t)u * wstep) << 5) + lane;
+          inr[u] = p >= a && p < end;      // false for words beyond the row
+          srcv[u] = inr[u] ? __ldg(g.indices + p) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) kp[u] = inr[u] && test_bit(ws.sel_bits, srcv[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t w = w0 + (int64_t)u * wstep;
+          if (w >= w_hi) break;            // warp-uniform
+          const int64_t p = (w << 5) + lane;
+          const int src = srcv[u];
+          const bool keep = kp[u];
+          const unsigned bits = __ballot_sync(0xffffffffu, keep);
+          const unsigned range = __ballot_sync(0xffffffffu, inr[u]);
+          int off = 0;
+          if (lane == 0) {
+            if (range == 0xffffffffu) {
+              ws.keep_bits[w] = bits;
+            } else {  // boundary word, shared with the neighbouring column(s)
+              atomicAnd(&ws.keep_bits[w], ~range);
+              atomicOr(&ws.keep_bits[w], bits);
+            }
+            if (bits) off = heavy ? atomicAdd(&s_cnt, __popc(bits)) : cnt;
+          }
+          off = __shfl_sync(0xffffffffu, off, 0);
+          if (keep) {
+            const int j = off + __popc(bits & ((1u << lane) - 1u));
+            if (j < cap) {
+              lk[j] = (int)(p - a);
+              ls[j] = src;
+            } else {
+              note_first(src, key_hi | (unsigned)(p - a), ws);   // list full (hub row): the slow inline path
+            }
+          }
+          cnt += __popc(bits);
         }
       }
-      cnt = block_sum(cnt, s_red);
-      if (tid == 0) ws.row_cnt[row] = cnt;
-    } else {
-      const int li = (item - n_heavy) * BLISS_WARPS + warp_id();
-      if (li < n_light) {
-        const int row = ws.row_list[n_seeds - 1 - li];
-        const int64_t a = ws.pos_a[n_seeds - 1 - li];
-        const int d = ws.pos_d[n_seeds - 1 - li];
-        const int32_t* __restrict__ idx = g.indices + a;
-        const unsigned long long key_hi = (unsigned long long)(row + 1) << 32;
-        int cnt = 0;
-        for (int k = lane_id(); k < d; k += 32) {
-          int src = __ldg(idx + k);
-          if (test_bit(ws.sel_bits, src)) {
-            ++cnt;
-            note_first(src, key_hi | (unsigned)k, ws);
-          }
-        }
-        cnt = warp_sum(cnt);
-        if (lane_id() == 0) ws.row_cnt[row] = cnt;
+      if (heavy) {
+        cnt = block_sum(lane == 0 ? cnt : 0, s_red);
+        if (tid == 0) ws.row_cnt[row] = cnt;
+        const int n = min(cnt, cap);
+        for (int j = tid; j < n; j += BLISS_CTA) note_first(ls[j], key_hi | (unsigned)lk[j], ws);
+      } else {
+        if (lane == 0) ws.row_cnt[row] = cnt;
+        __syncwarp();
+        const int n = min(cnt, cap);
+        for (int j = lane; j < n; j += 32) note_first(ls[j], key_hi | (unsigned)lk[j], ws);
       }
     }
+    __syncthreads();
+    item = nxt;
+    nxt = s_next[iter & 1];
   }
 }
 
@@ -777,9 +829,14 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
     }
     __syncthreads();
   }
-  const int n_chunks = (n_sel + blockDim.x - 1) / blockDim.x;
+  // ranking: 4 adjacent lanes share one key and each counts a quarter of every tile, so a CTA
+  // handles 64 keys and 4x more CTAs take part (the counting loop is the serial part)
+  constexpr int SUB = 4;
+  const int keys_per_cta = blockDim.x / SUB;
+  const int n_chunks = (n_sel + keys_per_cta - 1) / keys_per_cta;
+  const int sub = threadIdx.x & (SUB - 1);
   for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int j = chunk * blockDim.x + threadIdx.x;
+    const int j = chunk * keys_per_cta + (threadIdx.x / SUB);
     const bool valid = j < n_sel;
     const int nid = valid ? ws.sel[j] : 0;
     const unsigned long long key = valid ? ws.first_pos[nid] : 0ull;
@@ -791,10 +848,12 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
       __syncthreads();
       if (valid) {
 #pragma unroll 8
-        for (int t = 0; t < tn; ++t) rank += (s_keys[t] < key);
+        for (int t = sub; t < tn; t += SUB) rank += (s_keys[t] < key);
       }
     }
-    if (valid) {
+    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+    if (valid && sub == 0) {
       const int local = n_seeds + rank;
       ws.node_info[2 * nid] = local;
       if (local < out.cap_src) {
@@ -838,96 +897,133 @@ __device__ __forceinline__ double fill_edge(const FillCtx& c, const bliss_worksp
   return (double)wt;
 }
 
+__device__ __forceinline__ unsigned keep_word(const bliss_workspace& ws, int64_t w, int64_t a, int64_t end) {
+  // bits of word w that belong to the row [a, end)
+  unsigned bits = ws.keep_bits[w];
+  const int64_t p0 = w << 5;
+  if (p0 < a) bits &= 0xffffffffu << (int)(a - p0);
+  if (p0 + 32 > end) bits &= 0xffffffffu >> (int)(p0 + 32 - end);
+  return bits;
+}
+
+// Rescale this row's block weights once its sum is known:  W~ *= d / ΣW~  (bandit_sampler.py:316-320)
+// or  W~ *= d  (ladies_sampler.py:97).  The slots were written by this very group of threads.
+__device__ __forceinline__ void rescale_row(const FillCtx& c, const bliss_block_out& out, int base, int cnt,
+                                            double row_t, int t, int nt) {
+  const float d = (float)cnt;
+  const float f = (c.mode == BLISS_MODE_LADIES) ? d : __fdiv_rn(d, __double2float_rn(row_t));
+  for (int k = t; k < cnt; k += nt) out.edge_w[base + k] = __fmul_rn(out.edge_w[base + k], f);
+}
+
 __global__ void __launch_bounds__(BLISS_CTA) k_block_fill(FillCtx c, const int32_t* __restrict__ seeds,
                                                          bliss_workspace ws, bliss_block_out out) {
   __shared__ double s_red[32];
   __shared__ int s_scan[40];
-  __shared__ int s_item;
+  __shared__ int s_next[2];
+  __shared__ int s_k[BLISS_LIST_CAP];   // row-relative positions of the kept edges, in block order
   bliss_counters* ctr = ws.ctr;
   const int n_seeds = ctr->n_seeds, n_heavy = ctr->n_heavy, n_light = ctr->n_light;
   const int n_items = n_heavy + (n_light + BLISS_WARPS - 1) / BLISS_WARPS;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = lane_id();
   const bool needs_row_w = (c.mode != BLISS_MODE_LADIES);
+  constexpr int LIGHT_CAP = BLISS_LIST_CAP / BLISS_WARPS;
   if (ctr->n_edges > out.cap_edges) return;  // capacity error already flagged
-  for (;;) {
-    int item = next_item(&ctr->queue[2], n_items, &s_item);
-    if (item < 0) break;
+  int item = blockIdx.x, nxt = gridDim.x + blockIdx.x, iter = 0;
+  for (; item < n_items; ++iter) {
+    if (tid == 0) s_next[iter & 1] = 2 * gridDim.x + atomicAdd(&ctr->queue[2], 1);
     if (item < n_heavy) {
       const int row = ws.row_list[item];
       const int64_t a = ws.pos_a[item];
       const int d = ws.pos_d[item];
-      const int32_t* __restrict__ idx = c.g.indices + a;
+      const int64_t end = a + d;
       const float row_w = needs_row_w ? ws.row_w[row] : 1.0f;
       const float eta_n = __fdiv_rn(c.eta, (float)d);
-      // each warp owns one contiguous segment of the row: count its kept edges (bitmap test,
-      // sel_bits is L1 resident), one CTA scan of the 8 counts, then a sync-free ordered
-      // compaction per warp with ballots.
-      const int seg = (((d + BLISS_WARPS - 1) / BLISS_WARPS) + 31) & ~31;
-      const int k_lo = min(d, warp_id() * seg), k_hi = min(d, k_lo + seg);
+      const int row_base = out.indptr[row];
+      // every warp owns a contiguous run of the row's keep-words: popcount the run, one scan of the
+      // 8 run totals, ordered compaction of the kept positions into shared memory, then one kept
+      // edge per thread (all random accesses independent and in flight together)
+      const int64_t w_lo = a >> 5, w_hi = (end + 31) >> 5;
+      const int64_t run = (w_hi - w_lo + BLISS_WARPS - 1) / BLISS_WARPS;
+      const int64_t r_lo = min(w_hi, w_lo + warp_id() * run), r_hi = min(w_hi, r_lo + run);
       int cnt = 0;
-      for (int k = k_lo + lane_id(); k < k_hi; k += 32) cnt += test_bit(ws.sel_bits, __ldg(idx + k)) ? 1 : 0;
+      for (int64_t w = r_lo + lane; w < r_hi; w += 32) cnt += __popc(keep_word(ws, w, a, end));
       cnt = warp_sum(cnt);
       __syncthreads();
-      if (lane_id() == 0) s_scan[warp_id()] = cnt;
+      if (lane == 0) s_scan[warp_id()] = cnt;
       __syncthreads();
-      int base = out.indptr[row];
-      for (int w = 0; w < warp_id(); ++w) base += s_scan[w];
-      double acc = 0.0;
-      for (int k0 = k_lo; k0 < k_hi; k0 += 32) {
-        const int k = k0 + lane_id();
-        const int src = (k < k_hi) ? __ldg(idx + k) : 0;
-        const bool keep = (k < k_hi) && test_bit(ws.sel_bits, src);
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep)
-          acc += fill_edge(c, ws, out, a + k, src, row, base + __popc(m & ((1u << lane_id()) - 1u)), row_w, eta_n);
-        base += __popc(m);
+      int rel0 = 0, total = 0;
+      for (int wv = 0; wv < BLISS_WARPS; ++wv) {
+        if (wv < warp_id()) rel0 += s_scan[wv];
+        total += s_scan[wv];
       }
-      acc = block_sum(acc, s_red);
+      double acc = 0.0;
+      for (int b0 = 0; b0 < total; b0 += BLISS_LIST_CAP) {   // one pass unless a hub row keeps > 2048 edges
+        int rel = rel0;
+        for (int64_t w = r_lo; w < r_hi; ++w) {
+          const unsigned bits = keep_word(ws, w, a, end);
+          if ((bits >> lane) & 1u) {
+            const int j = rel + __popc(bits & ((1u << lane) - 1u)) - b0;
+            if (j >= 0 && j < BLISS_LIST_CAP) s_k[j] = (int)((w << 5) + lane - a);
+          }
+          rel += __popc(bits);
+        }
+        __syncthreads();
+        const int n = min(BLISS_LIST_CAP, total - b0);
+        for (int j = tid; j < n; j += BLISS_CTA) {
+          const int64_t p = a + s_k[j];
+          acc += fill_edge(c, ws, out, p, __ldg(c.g.indices + p), row, row_base + b0 + j, row_w, eta_n);
+        }
+        __syncthreads();
+      }
+      acc = block_sum(acc, s_red);   // also orders the edge_w writes before the rescale below
       if (tid == 0) ws.row_t[row] = acc;
+      rescale_row(c, out, row_base, total, acc, tid, BLISS_CTA);
     } else {
       const int li = (item - n_heavy) * BLISS_WARPS + warp_id();
       if (li < n_light) {
-        const int lane = lane_id();
-        const int row = ws.row_list[n_seeds - 1 - li];
-        const int64_t a = ws.pos_a[n_seeds - 1 - li];
-        const int d = ws.pos_d[n_seeds - 1 - li];
-        const int32_t* __restrict__ idx = c.g.indices + a;
+        const int pos = n_seeds - 1 - li;
+        const int row = ws.row_list[pos];
+        const int64_t a = ws.pos_a[pos];
+        const int d = ws.pos_d[pos];
+        const int64_t end = a + d;
         const float row_w = (needs_row_w && d > 0) ? ws.row_w[row] : 1.0f;
         const float eta_n = __fdiv_rn(c.eta, (float)d);
-        int base = out.indptr[row];
+        const int row_base = out.indptr[row];
+        int* lk = s_k + warp_id() * LIGHT_CAP;   // d <= 256 = LIGHT_CAP
+        int cnt = 0;
+        for (int64_t w = a >> 5; w < ((end + 31) >> 5); ++w) {
+          const unsigned bits = keep_word(ws, w, a, end);
+          if ((bits >> lane) & 1u) lk[cnt + __popc(bits & ((1u << lane) - 1u))] = (int)((w << 5) + lane - a);
+          cnt += __popc(bits);
+        }
+        __syncwarp();
         double acc = 0.0;
-        for (int k0 = 0; k0 < d; k0 += 32) {
-          int k = k0 + lane;
-          int src = (k < d) ? __ldg(idx + k) : 0;
-          bool keep = (k < d) && test_bit(ws.sel_bits, src);
-          unsigned m = __ballot_sync(0xffffffffu, keep);
-          if (keep)
-            acc += fill_edge(c, ws, out, a + k, src, row, base + __popc(m & ((1u << lane) - 1u)), row_w, eta_n);
-          base += __popc(m);
+        for (int j = lane; j < cnt; j += 32) {
+          const int64_t p = a + lk[j];
+          acc += fill_edge(c, ws, out, p, __ldg(c.g.indices + p), row, row_base + j, row_w, eta_n);
         }
         acc = warp_sum(acc);
         if (lane == 0) ws.row_t[row] = acc;
+        __syncwarp();
+        rescale_row(c, out, row_base, cnt, acc, lane, 32);
       }
     }
+    __syncthreads();
+    item = nxt;
+    nxt = s_next[iter & 1];
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// (3d) finish: W~_e *= d_i / ΣW~ (bandit :316-320) or *= d_i (ladies :97); restore the
-//      workspace invariant for every node this layer touched.
+// (3d) finish: restore the workspace invariant for every node this layer touched (the block
+//      weights were already normalised row by row in k_block_fill).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_block_finish(int mode, bliss_workspace ws, bliss_block_out out) {
   bliss_counters* ctr = ws.ctr;
-  const int64_t n_edges = (ctr->n_edges <= out.cap_edges) ? ctr->n_edges : 0;
   const int n_cand = ctr->n_cand;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  for (int64_t e = t0; e < n_edges; e += stride) {
-    int i = out.edge_dst[e];
-    float d = (float)(out.indptr[i + 1] - out.indptr[i]);
-    float f = (mode == BLISS_MODE_LADIES) ? d : __fdiv_rn(d, __double2float_rn(ws.row_t[i]));
-    out.edge_w[e] = __fmul_rn(out.edge_w[e], f);
-  }
+  (void)mode;  // the rows are normalised by k_block_fill itself; this kernel only restores the workspace
   for (int64_t j = t0; j < n_cand; j += stride) {
     int nid = ws.cand[j];
     ws.acc[nid] = 0ull;

@@ -44,6 +44,7 @@ class _Workspace:
         self.node_info = torch.empty(2 * V, **i32)
         self.sel_bits = torch.empty((V + 31) // 32, **i32)
         self.cand_bits = torch.empty((V + 31) // 32, **i32)
+        self.keep_bits = torch.zeros(g.num_edges() // 32 + 2, **i32)
         self.pos_a = torch.empty(V, dtype=torch.int64, device=dev)
         self.pos_d = torch.empty(V, **i32)
         self.cand = torch.empty(V, **i32)
@@ -61,7 +62,7 @@ class _Workspace:
         self.ctr_host = torch.zeros(C.sizeof(N.Counters), dtype=torch.uint8).pin_memory()
         self.ws = N.Workspace(
             acc=N.ptr(self.acc), first_pos=N.ptr(self.first_pos), node_info=N.ptr(self.node_info),
-            sel_bits=N.ptr(self.sel_bits), cand_bits=N.ptr(self.cand_bits), cand=N.ptr(self.cand), p_cand=N.ptr(self.p_cand), sel=N.ptr(self.sel),
+            sel_bits=N.ptr(self.sel_bits), cand_bits=N.ptr(self.cand_bits), keep_bits=N.ptr(self.keep_bits), cand=N.ptr(self.cand), p_cand=N.ptr(self.p_cand), sel=N.ptr(self.sel),
             row_list=N.ptr(self.row_list), pos_a=N.ptr(self.pos_a), pos_d=N.ptr(self.pos_d), row_w=N.ptr(self.row_w), row_q=N.ptr(self.row_q),
             row_cnt=N.ptr(self.row_cnt), row_t=N.ptr(self.row_t), cap_seeds=V, cap_sel=V, ctr=N.ptr(self.ctr))
         self.gview = N.Graph(num_nodes=V, num_edges=g.num_edges(), indptr=N.ptr(g.indptr),

@@ -76,6 +76,8 @@ typedef struct bliss_workspace {
   int32_t*  node_info;  /* [2V] (local id | -1, float bits of inclusion prob P) per node  */
   uint32_t* sel_bits;   /* [(V+31)/32] bitmap: node is selected                           */
   uint32_t* cand_bits;  /* [(V+31)/32] candidate bitmap (BLISS_COLLECT_BITMAP mode only)    */
+  uint32_t* keep_bits;  /* [E/32+1] one bit per CSC edge position: edge kept in the block; rows
+                           rewrite their own range, so it is never cleared                  */
   int32_t*  cand;       /* [V]  candidate list: seeds first, then sources unordered       */
   float*    p_cand;     /* [V]  raw probability per candidate slot                        */
   int32_t*  sel;        /* [C]  selected non-seed candidates, unordered                   */

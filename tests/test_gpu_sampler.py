@@ -317,13 +317,16 @@ def test_packed_exchange_apply_matches_sequential_updates(native_lib):
     w_dev = [x.to(dev).clone() for x in w]
     l1 = torch.zeros(len(caps), dtype=torch.float64, device=dev)
     expect = [x.double().clone() for x in w]
+    first_pos = {}
     for r in range(world):
         base = ex.recv[r * ex.stride:(r + 1) * ex.stride]
         for l, cap in enumerate(caps):
             n = cap - 50 * (r + 1)
-            pos = torch.randperm(E, generator=gen)[:n]
-            if r == 1:
-                pos[:20] = torch.arange(20)           # positions both ranks may hit
+            pos = torch.randperm(E, generator=gen)
+            if r == 1:                                # make sure both ranks hit some common positions
+                pos = torch.cat([first_pos[l][:20], pos[~torch.isin(pos, first_pos[l][:20])]])
+            pos = pos[:n]                             # unique within a rank (a block has no duplicate edges)
+            first_pos.setdefault(l, pos)
             xs = torch.rand(n, generator=gen) * 0.01
             base[:64].view(torch.int64)[l] = n
             base[ex.pos_off[l]:ex.pos_off[l] + 8 * n].view(torch.int64).copy_(pos)
