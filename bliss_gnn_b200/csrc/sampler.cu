@@ -814,6 +814,8 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
     for (int64_t i = n_seeds + 1 + threadIdx.x; i <= out.pad_rows; i += blockDim.x) out.indptr[i] = base;
     if (out.inv_deg)
       for (int64_t i = n_seeds + threadIdx.x; i < out.pad_rows; i += blockDim.x) out.inv_deg[i] = 1.0f;
+    if (out.out_deg)   // padded sources have no edges (their counts feed the transpose scan)
+      for (int64_t i = n_seeds + n_sel + threadIdx.x; i < out.pad_src; i += blockDim.x) out.out_deg[i] = 0;
     if (threadIdx.x == 0) {
       if (out.heavy_rows) out.heavy_rows[0] = hbase;
       out.indptr[n_seeds] = base;
@@ -859,8 +861,8 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
       if (local < out.cap_src) {
         out.src_nid[local] = nid;
         out.node_prob[local] = __int_as_float(ws.node_info[2 * nid + 1]);
-        if (out.out_deg) out.out_deg[local] = 0;
       }
+      if (out.out_deg && (out.pad_src == 0 || local < out.pad_src)) out.out_deg[local] = 0;
     }
   }
 }
@@ -1353,15 +1355,18 @@ int bliss_block_finish(int32_t n_seeds, int32_t mode, const bliss_workspace* ws,
 int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                           int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor,
                           int32_t* t_scratch, int32_t* t_dst, int32_t* t_perm, int32_t* t_heavy,
-                          void* stream) {
+                          int32_t have_counts, void* stream) {
   if (n_edges < 0 || n_src < 0 || !t_indptr || !t_cursor) return -1;
   if (n_edges > 0 && (!edge_src || !edge_dst || !t_scratch || !t_dst || !t_perm)) return -1;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(t_cursor, 0, sizeof(int32_t) * (size_t)(n_src > 0 ? n_src : 1), st);
-  if (e != cudaSuccess) return (int)e;
-  if (n_edges > 0) {
-    k_t_count<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, t_cursor);
-    BLISS_CHECK_LAUNCH();
+  cudaError_t e = cudaSuccess;
+  if (!have_counts) {   // otherwise t_cursor already holds the per-source counts (bliss_block_out.out_deg)
+    e = cudaMemsetAsync(t_cursor, 0, sizeof(int32_t) * (size_t)(n_src > 0 ? n_src : 1), st);
+    if (e != cudaSuccess) return (int)e;
+    if (n_edges > 0) {
+      k_t_count<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, t_cursor);
+      BLISS_CHECK_LAUNCH();
+    }
   }
   k_t_scan<<<1, 1024, 0, st>>>(t_cursor, n_src, t_indptr, t_heavy);
   BLISS_CHECK_LAUNCH();

@@ -285,9 +285,11 @@ class BanditLadiesSampler:
         the arrays are the pool's persistent capacity buffers and indptr is padded to the capacity."""
         wsp, dev, n_s = fr.wsp, fr.g.device, fr.n_seeds
         if pool is not None and n_s <= pool.cap_dst:
+            # out_deg -> the pool's transpose cursor: the fill kernel counts every source's block edges,
+            # so the transpose starts from its scan (no separate count pass)
             out = N.BlockOut(indptr=N.ptr(pool.indptr), src_nid=N.ptr(wsp.src_nid), node_prob=N.ptr(wsp.node_prob),
-                             heavy_rows=N.ptr(pool.heavy), inv_deg=N.ptr(pool.inv_deg), cap_edges=0,
-                             cap_src=fr.g.num_nodes(), pad_rows=pool.cap_dst)
+                             heavy_rows=N.ptr(pool.heavy), inv_deg=N.ptr(pool.inv_deg), out_deg=N.ptr(pool.t_cursor),
+                             cap_edges=0, cap_src=fr.g.num_nodes(), pad_src=pool.cap_src, pad_rows=pool.cap_dst)
             return out, (pool.indptr[:n_s + 1], pool.heavy, pool.inv_deg[:n_s])
         meta = torch.empty(3 * (n_s + 1), dtype=torch.int32, device=dev)   # indptr | heavy | inv_deg (as f32)
         indptr, heavy, inv_deg = meta[:n_s + 1], meta[n_s + 1:2 * (n_s + 1)], meta[2 * (n_s + 1):].view(torch.float32)
@@ -309,6 +311,7 @@ class BanditLadiesSampler:
         pooled = pool is not None and out.pad_rows > 0 and pool.fits(n_s, n_src, E)
         if pool is not None and not pooled:
             self.pool_overflow = True          # the caller grows the pool and re-captures
+            out.out_deg = None
             if out.pad_rows > 0:               # indptr lives in the pool but the block does not fit: detach it
                 indptr, heavy, inv_deg = indptr.clone(), heavy[:n_s + 1].clone(), inv_deg.clone()
         # one allocation for the 4-byte edge arrays, one for the 8-byte CSC positions

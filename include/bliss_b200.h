@@ -109,6 +109,7 @@ typedef struct bliss_block_out {
   float*   inv_deg;     /* [n_seeds] 1 / max(block in-degree, 1)  (fn.mean divisor; NULL ok)  */
   int64_t  cap_edges;
   int64_t  cap_src;
+  int64_t  pad_src;     /* > n_src: out_deg[n_src..pad_src) = 0 (capacity padding)                */
   int64_t  pad_rows;    /* > n_seeds: indptr[n_seeds+1..pad_rows] = E_b, inv_deg[n_seeds..pad_rows) = 1
                            (capacity-padded blocks for CUDA-graph replay); 0 = no padding          */
 } bliss_block_out;
@@ -173,6 +174,7 @@ int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int6
                           int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor /* [n_src] */,
                           int32_t* t_scratch /* [E] */, int32_t* t_dst, int32_t* t_perm,
                           int32_t* t_heavy /* [n_src+1] heavy source rows, [0]=count; may be NULL */,
+                          int32_t have_counts /* t_cursor already holds out-degrees (block_out.out_deg) */,
                           void* stream);
 
 /* ---- (5) aggregation ------------------------------------------------------------------------
