@@ -105,7 +105,7 @@ typedef struct bliss_block_out {
   int32_t* src_nid;     /* [n_src] global id of each block source                         */
   float*   node_prob;   /* [n_src] inclusion probability P (bandit_sampler.py:328)        */
   int32_t* out_deg;     /* [n_src] block out-degree of each source (NULL to skip)         */
-  int32_t* heavy_rows;  /* [n_seeds+1] [0]=count, then destinations with > 256 edges (NULL ok) */
+  int32_t* heavy_rows;  /* [n_seeds+1] [0]=count, then destinations with > 64 edges (NULL ok)  */
   float*   inv_deg;     /* [n_seeds] 1 / max(block in-degree, 1)  (fn.mean divisor; NULL ok)  */
   int64_t  cap_edges;
   int64_t  cap_src;
@@ -184,7 +184,7 @@ int bliss_gather_rows(const float* table, const int32_t* nid, int64_t n_rows, in
                       float* out, float* row_norm /* may be NULL */, void* stream);
 int bliss_row_norm(const float* x, int64_t n_rows, int32_t dim, float* out, void* stream);
 /* y[i,:] = dscale_i * sum_{e in row i} w[perm? perm[e] : e] * sscale[col[e]] * x[col[e], :]
- * heavy (may be NULL): [0] = count, then the rows with > 256 edges — those are split over the 8
+ * heavy (may be NULL): [0] = count, then the rows with > 64 edges — those are split over the 8
  * warps of a CTA and combined in shared memory in a fixed order; the rest is warp-per-row. */
 int bliss_spmm(const int32_t* indptr, const int32_t* col, const int32_t* perm, const float* w,
                const float* sscale, const float* dscale, int32_t agg, const float* x,
