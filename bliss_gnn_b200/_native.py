@@ -75,15 +75,17 @@ class Counters(C.Structure):
     _fields_ = [("n_seeds", C.c_int32), ("n_cand", C.c_int32), ("n_sel", C.c_int32), ("n_src", C.c_int32),
                 ("n_heavy", C.c_int32), ("n_light", C.c_int32), ("take_all", C.c_int32), ("iters", C.c_int32),
                 ("e_in", C.c_int64), ("n_edges", C.c_int64), ("c", C.c_double), ("s_last", C.c_double),
-                ("queue", C.c_int32 * 4), ("error", C.c_int32), ("pad", C.c_int32)]
+                ("queue", C.c_int32 * 4), ("error", C.c_int32), ("n_chunks", C.c_int32)]
 
 
 class Workspace(C.Structure):
     _fields_ = [("acc", C.c_void_p), ("first_pos", C.c_void_p), ("node_info", C.c_void_p),
                 ("sel_bits", C.c_void_p), ("cand_bits", C.c_void_p), ("keep_bits", C.c_void_p), ("cand", C.c_void_p), ("p_cand", C.c_void_p), ("sel", C.c_void_p),
-                ("row_list", C.c_void_p), ("pos_a", C.c_void_p), ("pos_d", C.c_void_p), ("row_w", C.c_void_p), ("row_q", C.c_void_p),
+                ("row_list", C.c_void_p), ("pos_a", C.c_void_p), ("pos_d", C.c_void_p), ("row_a", C.c_void_p), ("row_d", C.c_void_p),
+                ("chunk_first", C.c_void_p), ("chunk_row", C.c_void_p), ("part_w", C.c_void_p), ("part_q", C.c_void_p),
+                ("row_w", C.c_void_p), ("row_q", C.c_void_p),
                 ("row_cnt", C.c_void_p), ("row_t", C.c_void_p), ("cap_seeds", C.c_int64),
-                ("cap_sel", C.c_int64), ("ctr", C.c_void_p)]
+                ("cap_sel", C.c_int64), ("ctr", C.c_void_p), ("n_seeds_dev", C.c_void_p), ("step_dev", C.c_void_p)]
 
 
 class BlockOut(C.Structure):
@@ -113,7 +115,7 @@ PROTOTYPES = {
     "bliss_block_finish": [_I32, _I32, _WP, _BP, _P],
     "bliss_sample_layer_front": [_GP, _P, _I32, _P, _F, _I32, _I32, _D, _I32, _U64, _U64, _U32, _P, _P, _WP, _BP, _P],
     "bliss_sample_layer_back": [_GP, _P, _I32, _P, _F, _I32, _WP, _BP, _P],
-    "bliss_block_transpose": [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P],
+    "bliss_block_transpose": [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P],
     "bliss_gather_rows": [_P, _P, _I64, _I32, _P, _P, _P],
     "bliss_row_norm": [_P, _I64, _I32, _P, _P],
     "bliss_spmm": [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P, _P],
@@ -122,7 +124,7 @@ PROTOTYPES = {
     "bliss_gatv2_bwd_src": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _P],
     "bliss_gat_alpha_sums": [_P, _P, _P, _I32, _P, _P, _P],
     "bliss_reward_update": [_GP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _I32, _I64,
-                            _P, _P, _P, _P, _P],
+                            _P, _P, _P, _P, _P, _P, _P],
     "bliss_apply_updates": [_P, _P, _I64, _P, _P, _P],
     "bliss_apply_updates_packed": [_P, _I64, _I32, _I64, _I64, _I64, _I64, _P, _P, _P],
     "bliss_l1_norm": [_P, _I64, _P, _P, _P],
@@ -153,7 +155,7 @@ class BlissNativeError(RuntimeError):
 
 
 #: kernels each entry point launches (for the ``gpu_launches`` count of bench.py)
-LAUNCHES = {"bliss_frontier_prob": 2, "bliss_sample_layer_front": 6, "bliss_sample_layer_back": 2,
+LAUNCHES = {"bliss_frontier_prob": 4, "bliss_sample_layer_front": 8, "bliss_sample_layer_back": 2,
             "bliss_select_topk": 3, "bliss_block_transpose": 3, "bliss_l1_norm": 2, "bliss_version": 0}
 
 

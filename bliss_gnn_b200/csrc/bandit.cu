@@ -59,6 +59,8 @@ struct RewardArgs {
   int alpha_mode;
   float delta;
   int64_t n_edges;
+  const int64_t* n_edges_dev;   // true edge count on the device (n_edges is then the capacity)
+  int64_t* count_out;           // data-parallel exchange header slot (or NULL)
   float* exp3_w;
   float* rewards;
   float* x_out;
@@ -69,7 +71,9 @@ __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
   __shared__ double s_red[32];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   double dsum = 0.0;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < p.n_edges; e += stride) {
+  const int64_t n_edges = p.n_edges_dev ? min(p.n_edges, *p.n_edges_dev) : p.n_edges;
+  if (p.count_out && blockIdx.x == 0 && threadIdx.x == 0) *p.count_out = n_edges;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += stride) {
     const int i = p.edge_dst[e];
     const int u = p.edge_src[e];
     const int64_t pos = p.csc_pos[e];
@@ -232,7 +236,8 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
                         const float* q_ij, const float* node_prob, const float* embed_norm,
                         const float* w_static_csc, const float* a_ij, const float* asum, const float* qsum,
                         int32_t alpha_mode, float delta, int32_t n_dst, int64_t n_edges, float* exp3_w_csc,
-                        float* rewards, float* x_out, double* l1_delta, void* stream) {
+                        float* rewards, float* x_out, double* l1_delta, const int64_t* n_edges_dev,
+                        int64_t* count_out, void* stream) {
   if (!g || n_edges < 0 || n_dst < 0) return -1;
   if (n_edges == 0) return 0;
   if (!blk_indptr || !edge_src || !edge_dst || !csc_pos || !dst_nid || !q_ij || !node_prob || !embed_norm) return -1;
@@ -255,6 +260,8 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
   p.alpha_mode = alpha_mode;
   p.delta = delta;
   p.n_edges = n_edges;
+  p.n_edges_dev = n_edges_dev;
+  p.count_out = count_out;
   p.exp3_w = exp3_w_csc;
   p.rewards = rewards;
   p.x_out = x_out;

@@ -17,7 +17,7 @@
 #define BLISS_CTA 256                          // threads per CTA of the row kernels
 #define BLISS_WARPS (BLISS_CTA / 32)
 #define BLISS_STAGE_CAP 6144                   // floats of a heavy row staged in shared memory (24 KB)
-#define BLISS_PROB_CTAS_PER_SM 6
+#define BLISS_CHUNK 256                        // edges per warp-chunk of the probability passes
 #define BLISS_SPMM_HEAVY 64                     // block rows with more edges are aggregated by a whole CTA
 
 #define BLISS_CHECK_LAUNCH()                      \

@@ -54,6 +54,9 @@ __global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32
   __shared__ unsigned long long s_e[32];
   __shared__ int s_bucket[32], s_cursor[32];
   bliss_counters* ctr = ws.ctr;
+  // sync-free chaining of layers: the true seed count may live on the device (the previous
+  // layer's n_src); the host value is then only the capacity
+  if (ws.n_seeds_dev) n_seeds = min(n_seeds, *ws.n_seeds_dev);
   if (threadIdx.x < 32) s_bucket[threadIdx.x] = 0;
   __syncthreads();
   unsigned long long e_in = 0;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32
   __syncthreads();
   const int n_heavy = s_scan[39];
   __syncthreads();
-  int light_base = 0;
+  int light_base = 0, chunk_base = 0;
   for (int base = 0; base < n_seeds; base += blockDim.x) {
     const int i = base + threadIdx.x;
     const bool valid = i < n_seeds;
@@ -90,6 +93,16 @@ __global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32
       a = g.indptr[s];
       d = g.indptr[s + 1] - a;
     }
+    // chunk table of the probability passes: every row is cut into 256-edge warp-chunks
+    const int nch = valid ? max(1, (int)((min(d, (long long)INT_MAX) + BLISS_CHUNK - 1) / BLISS_CHUNK)) : 0;
+    int tc;
+    const int pc = block_excl_scan(nch, s_scan, &tc);
+    if (valid) {
+      ws.row_a[i] = a;
+      ws.row_d[i] = (int)min(d, (long long)INT_MAX);
+      ws.chunk_first[i] = chunk_base + pc;
+    }
+    chunk_base += tc;
     const bool heavy = valid && d > BLISS_LIGHT_MAX;
     int tl;
     const int pl = block_excl_scan((valid && !heavy) ? 1 : 0, s_scan, &tl);
@@ -102,6 +115,13 @@ __global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32
       ws.pos_d[pos] = (int)min(d, (long long)INT_MAX);
     }
     light_base += tl;
+  }
+  __syncthreads();
+  // chunk -> row table, one warp per row (a 20 K-edge row owns ~80 consecutive entries)
+  for (int i = warp_id(); i < n_seeds; i += blockDim.x / 32) {
+    const int first = ws.chunk_first[i];
+    const int nch = max(1, (ws.row_d[i] + BLISS_CHUNK - 1) / BLISS_CHUNK);
+    for (int c = lane_id(); c < nch; c += 32) ws.chunk_row[first + c] = i;
   }
   e_in = block_sum(e_in, s_e);
   if (threadIdx.x == 0) {
@@ -119,6 +139,8 @@ __global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32
     ctr->s_last = 0.0;
     ctr->queue[0] = ctr->queue[1] = ctr->queue[2] = ctr->queue[3] = 0;
     ctr->error = 0;
+    ctr->n_chunks = chunk_base;
+    ws.chunk_first[n_seeds] = chunk_base;
   }
 }
 
@@ -147,189 +169,126 @@ __device__ __forceinline__ void scatter_term(bool uniform, bool bitmap, float t,
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__global__ void __launch_bounds__(BLISS_CTA, BLISS_PROB_CTAS_PER_SM) k_frontier_prob(GraphView g, const float* __restrict__ W, float eta,
-                                                            float one_minus_eta, int mode_flags,
-                                                            bliss_workspace ws, double fx_scale) {
-  const int mode = mode_flags & 1;                         // BANDIT / LADIES arithmetic
-  const bool uniform = (mode_flags & BLISS_MODE_UNIFORM);  // importance_sampling = 0
-  const bool bitmap = (mode_flags & BLISS_COLLECT_BITMAP);
-  extern __shared__ float s_row[];  // BLISS_STAGE_CAP floats
-  __shared__ double s_red[32];
-  bliss_counters* ctr = ws.ctr;
-  const int n_seeds = ctr->n_seeds, n_heavy = ctr->n_heavy, n_light = ctr->n_light;
-  const int n_items = n_heavy + (n_light + BLISS_WARPS - 1) / BLISS_WARPS;
-  const int tid = threadIdx.x;
+// The three probability passes work on fixed 256-edge warp-chunks (one warp per chunk, 8 values
+// per lane in registers, no CTA barrier anywhere): perfectly balanced whatever the degree
+// distribution, no per-row chain of dependent round trips, no giant-row tail.  A row's sum is the
+// fixed-order fp64 sum of its chunks' partials, so the result is deterministic.
+//   pass 1  partW[c] = Σ w                       (weights streamed once from HBM)
+//   pass 2  W_i = Σ_c partW ; q = η/n + (1-η) w / W_i ; partQ[c] = Σ q      (weights from L2)
+//   pass 3  Q_i = Σ_c partQ ; RED acc[src] += fx((q / Q_i)^2)              (indices from HBM)
+struct ChunkRef {
+  int row, k0, len;
+  int64_t a;
+  int d, c_first, c_last;  // chunk range of the row [c_first, c_last)
+};
+__device__ __forceinline__ ChunkRef chunk_ref(const bliss_workspace& ws, int c) {
+  ChunkRef r;
+  r.row = ws.chunk_row[c];
+  r.a = ws.row_a[r.row];
+  r.d = ws.row_d[r.row];
+  r.c_first = ws.chunk_first[r.row];
+  r.c_last = ws.chunk_first[r.row + 1];
+  r.k0 = (c - r.c_first) * BLISS_CHUNK;
+  r.len = min(BLISS_CHUNK, r.d - r.k0);
+  return r;
+}
+__device__ __forceinline__ float row_total(const double* __restrict__ part, int c_first, int c_last) {
+  double t = 0.0;
+  for (int c = c_first; c < c_last; ++c) t += part[c];   // fixed order, every lane the same value
+  return __double2float_rn(t);
+}
 
-  // dynamic longest-first queue (rows are ordered heavy-first by the plan): a CTA that finishes
-  // early pulls the next item, so the tail is one row, not one CTA's share.  Two items are known
-  // ahead (the first two rounds are static), and the queue cursor for the item after next is
-  // fetched while the current row is processed, so neither its round trip nor the next row's
-  // metadata loads sit on the critical path.
-  __shared__ int s_next[2];
-  int item = blockIdx.x, nxt = gridDim.x + blockIdx.x, iter = 0;
-  int64_t a = 0, na = 0;
-  int d = 0, nd = 0, row = 0, nrow = 0;
-  if (item < n_heavy) {
-    a = ws.pos_a[item];
-    d = ws.pos_d[item];
-    row = ws.row_list[item];
+__global__ void __launch_bounds__(256) k_prob_pass1(const float* __restrict__ W, bliss_workspace ws) {
+  const int lane = lane_id();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_chunks = ws.ctr->n_chunks;
+  for (int c = warp; c < n_chunks; c += nwarps) {
+    const ChunkRef r = chunk_ref(ws, c);
+    const float* __restrict__ wr = W + r.a + r.k0;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
+      const int k = lane + 32 * j;
+      acc += (k < r.len) ? (double)__ldg(wr + k) : 0.0;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) ws.part_w[c] = acc;
   }
-  for (; item < n_items; ++iter) {
-    if (tid == 0) s_next[iter & 1] = 2 * gridDim.x + atomicAdd(&ctr->queue[0], 1);
-    if (nxt < n_heavy) {
-      na = ws.pos_a[nxt];
-      nd = ws.pos_d[nxt];
-      nrow = ws.row_list[nxt];
+}
+
+__global__ void __launch_bounds__(256) k_prob_pass2(const float* __restrict__ W, float eta, float one_minus_eta,
+                                                   bliss_workspace ws) {
+  const int lane = lane_id();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_chunks = ws.ctr->n_chunks;
+  for (int c = warp; c < n_chunks; c += nwarps) {
+    const ChunkRef r = chunk_ref(ws, c);
+    const float* __restrict__ wr = W + r.a + r.k0;
+    float v[BLISS_CHUNK / 32];
+#pragma unroll
+    for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
+      const int k = lane + 32 * j;
+      v[j] = (k < r.len) ? __ldg(wr + k) : 0.0f;
     }
-    if (item < n_heavy) {
-      // ---------------- heavy row: whole CTA ----------------
-      const int32_t* __restrict__ idx = g.indices + a;
-      const float* __restrict__ wr = W + a;
-      float row_q = 1.0f, row_w = 1.0f, eta_n = 0.0f;
-      // warm L2 with this row's source ids for the scatter pass
-      for (int l = tid; l * 32 < d; l += BLISS_CTA) prefetch_l2(idx + l * 32);
-      if (mode == BLISS_MODE_BANDIT) {
-        // pass A: stream the weights once from HBM (128-bit loads), stage them, row sum in fp64
-        double acc = 0.0;
-        const int head = min(d, (int)(((16 - ((uintptr_t)wr & 15)) & 15) >> 2));
-        if (tid < head) {
-          float w = __ldg(wr + tid);
-          s_row[tid] = w;  // head < 4 <= STAGE_CAP
-          acc += (double)w;
-        }
-        const int nvec = (d - head) >> 2;
-        const float4* __restrict__ wv = reinterpret_cast<const float4*>(wr + head);
-#pragma unroll 4
-        for (int v = tid; v < nvec; v += BLISS_CTA) {
-          float4 w4 = __ldg(wv + v);
-          int k = head + 4 * v;
-          if (k + 3 < BLISS_STAGE_CAP) {
-            s_row[k] = w4.x; s_row[k + 1] = w4.y; s_row[k + 2] = w4.z; s_row[k + 3] = w4.w;
-          } else {
-            if (k < BLISS_STAGE_CAP) s_row[k] = w4.x;
-            if (k + 1 < BLISS_STAGE_CAP) s_row[k + 1] = w4.y;
-            if (k + 2 < BLISS_STAGE_CAP) s_row[k + 2] = w4.z;
-          }
-          acc += ((double)w4.x + (double)w4.y) + ((double)w4.z + (double)w4.w);
-        }
-        const int tail0 = head + 4 * nvec;
-        if (tail0 + tid < d) {
-          float w = __ldg(wr + tail0 + tid);
-          if (tail0 + tid < BLISS_STAGE_CAP) s_row[tail0 + tid] = w;
-          acc += (double)w;
-        }
-        // while the reduction runs, pull the next row's weights towards L2
-        if (nxt < n_heavy)
-          for (int l = tid; l * 32 < nd; l += BLISS_CTA) prefetch_l2(W + na + l * 32);
-        row_w = __double2float_rn(block_sum(acc, s_red));
-        eta_n = __fdiv_rn(eta, (float)d);
-        // pass B: q_ij, row sum of q (staged part from shared memory; the part of a giant row beyond
-        // the stage is re-read from L2 with 8 independent loads in flight per thread)
-        double accq = 0.0;
-        const int d_st = min(d, BLISS_STAGE_CAP);
-        for (int k = tid; k < d_st; k += BLISS_CTA) {
-          float q = edge_q(s_row[k], row_w, eta_n, one_minus_eta);
-          s_row[k] = q;
-          accq += (double)q;
-        }
-#pragma unroll 8
-        for (int k = BLISS_STAGE_CAP + tid; k < d; k += BLISS_CTA)
-          accq += (double)edge_q(__ldg(wr + k), row_w, eta_n, one_minus_eta);
-        row_q = __double2float_rn(block_sum(accq, s_red));
-        if (tid == 0) {
-          ws.row_w[row] = row_w;
-          ws.row_q[row] = row_q;
-        }
-      }
-      // pass C: scatter the squared normalised edge probabilities to the column accumulator
-      if (mode == BLISS_MODE_BANDIT && !uniform) {
-        const int d_st = min(d, BLISS_STAGE_CAP);
-#pragma unroll 4
-        for (int k = tid; k < d_st; k += BLISS_CTA) {
-          const int src = __ldg(idx + k);
-          const float r = __fdiv_rn(s_row[k], row_q);
-          scatter_term(false, bitmap, __fmul_rn(r, r), src, fx_scale, ws);
-        }
-#pragma unroll 8
-        for (int k = BLISS_STAGE_CAP + tid; k < d; k += BLISS_CTA) {
-          const int src = __ldg(idx + k);
-          const float r = __fdiv_rn(edge_q(__ldg(wr + k), row_w, eta_n, one_minus_eta), row_q);
-          scatter_term(false, bitmap, __fmul_rn(r, r), src, fx_scale, ws);
-        }
-      } else {
-#pragma unroll 8
-        for (int k = tid; k < d; k += BLISS_CTA) {
-          const int src = __ldg(idx + k);
-          float t = 0.0f;
-          if (!uniform) {
-            const float w = __ldg(wr + k);
-            t = __fmul_rn(w, w);
-          }
-          scatter_term(uniform, bitmap, t, src, fx_scale, ws);
-        }
-      }
-    } else {
-      // ---------------- light rows: one warp per row, values in registers ----------------
-      const int li = (item - n_heavy) * BLISS_WARPS + warp_id();
-      if (li < n_light) {
-        const int lane = lane_id();
-        const int pos = n_seeds - 1 - li;
-        const int row = ws.row_list[pos];
-        const int64_t a = ws.pos_a[pos];
-        const int d = ws.pos_d[pos];
-        const int32_t* __restrict__ idx = g.indices + a;
-        constexpr int R = BLISS_LIGHT_MAX / 32;
-        float v[R];
-        int src[R];
+    const float row_w = row_total(ws.part_w, r.c_first, r.c_last);
+    const float eta_n = __fdiv_rn(eta, (float)r.d);
+    double acc = 0.0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          int k = lane + 32 * r;
-          src[r] = (k < d) ? __ldg(idx + k) : 0;
-          v[r] = (k < d) ? __ldg(W + a + k) : 0.0f;
-        }
-        float row_q = 1.0f;
-        if (mode == BLISS_MODE_BANDIT) {
-          double acc = 0.0;
+    for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
+      const int k = lane + 32 * j;
+      acc += (k < r.len) ? (double)edge_q(v[j], row_w, eta_n, one_minus_eta) : 0.0;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      ws.part_q[c] = acc;
+      if (c == r.c_first) ws.row_w[r.row] = row_w;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_prob_pass3(GraphView g, const float* __restrict__ W, float eta,
+                                                   float one_minus_eta, int mode_flags, bliss_workspace ws) {
+  const int mode = mode_flags & 1;
+  const bool uniform = (mode_flags & BLISS_MODE_UNIFORM);
+  const bool bitmap = (mode_flags & BLISS_COLLECT_BITMAP);
+  const int lane = lane_id();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_chunks = ws.ctr->n_chunks;
+  const double fx_scale = (double)(1ull << fx_bits_for(ws.ctr->n_seeds));
+  for (int c = warp; c < n_chunks; c += nwarps) {
+    const ChunkRef r = chunk_ref(ws, c);
+    const float* __restrict__ wr = W + r.a + r.k0;
+    const int32_t* __restrict__ idx = g.indices + r.a + r.k0;
+    float v[BLISS_CHUNK / 32];
+    int src[BLISS_CHUNK / 32];
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc += (double)v[r];
-          float row_w = __double2float_rn(warp_sum(acc));
-          float eta_n = __fdiv_rn(eta, (float)d);
-          double accq = 0.0;
+    for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
+      const int k = lane + 32 * j;
+      src[j] = (k < r.len) ? __ldg(idx + k) : 0;
+      v[j] = (k < r.len && !uniform) ? __ldg(wr + k) : 0.0f;
+    }
+    float row_w = 1.0f, row_q = 1.0f, eta_n = 0.0f;
+    if (mode == BLISS_MODE_BANDIT && !uniform) {
+      row_w = row_total(ws.part_w, r.c_first, r.c_last);
+      row_q = row_total(ws.part_q, r.c_first, r.c_last);
+      eta_n = __fdiv_rn(eta, (float)r.d);
+      if (lane == 0 && c == r.c_first) ws.row_q[r.row] = row_q;
+    }
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            int k = lane + 32 * r;
-            v[r] = (k < d) ? edge_q(v[r], row_w, eta_n, one_minus_eta) : 0.0f;
-            accq += (double)v[r];
-          }
-          row_q = __double2float_rn(warp_sum(accq));
-          if (lane == 0) {
-            ws.row_w[row] = row_w;
-            ws.row_q[row] = row_q;
-          }
+    for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
+      const int k = lane + 32 * j;
+      if (k < r.len) {
+        float t = 0.0f;
+        if (uniform) {
+        } else if (mode == BLISS_MODE_BANDIT) {
+          const float q = __fdiv_rn(edge_q(v[j], row_w, eta_n, one_minus_eta), row_q);
+          t = __fmul_rn(q, q);
+        } else {
+          t = __fmul_rn(v[j], v[j]);
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          int k = lane + 32 * r;
-          if (k < d) {
-            float t = 0.0f;
-            if (uniform) {
-            } else if (mode == BLISS_MODE_BANDIT) {
-              float q = __fdiv_rn(v[r], row_q);
-              t = __fmul_rn(q, q);
-            } else {
-              t = __fmul_rn(v[r], v[r]);
-            }
-            scatter_term(uniform, bitmap, t, src[r], fx_scale, ws);
-          }
-        }
+        scatter_term(uniform, bitmap, t, src[j], fx_scale, ws);
       }
     }
-    __syncthreads();  // s_row is reused by the next row; s_next[iter & 1] is complete
-    item = nxt;
-    a = na;
-    d = nd;
-    row = nrow;
-    nxt = s_next[iter & 1];
   }
 }
 
@@ -369,6 +328,8 @@ __global__ void __launch_bounds__(256) k_collect_candidates(int64_t num_nodes, i
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_poisson_scale(int n_seeds, int fanout, double eps, int poisson,
                                                        bliss_workspace ws, double fx_inv_scale) {
+  n_seeds = ws.ctr->n_seeds;   // the plan's (possibly device-side) count, not the host capacity
+  fx_inv_scale = 1.0 / (double)(1ull << fx_bits_for(n_seeds));
   __shared__ unsigned long long s_red[32];
   bliss_counters* ctr = ws.ctr;
   const int n_cand = ctr->n_cand;
@@ -447,6 +408,9 @@ __global__ void __launch_bounds__(1024, 1) k_scale_select(int n_seeds, int fanou
                                                          unsigned long long seed, unsigned long long step,
                                                          unsigned layer, const float* __restrict__ u_inject,
                                                          bliss_workspace ws, double fx_inv_scale) {
+  n_seeds = ws.ctr->n_seeds;   // the plan's (possibly device-side) count, not the host capacity
+  fx_inv_scale = 1.0 / (double)(1ull << fx_bits_for(n_seeds));
+  if (ws.step_dev) step = *ws.step_dev;   // Philox step counter kept on the device (CUDA-graph replay)
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
   const unsigned nblk = cluster.num_blocks();
@@ -547,6 +511,8 @@ __global__ void __launch_bounds__(256) k_select_poisson(int n_seeds, unsigned lo
                                                        unsigned long long step, unsigned layer,
                                                        const float* __restrict__ u_inject,
                                                        bliss_workspace ws) {
+  n_seeds = ws.ctr->n_seeds;   // the plan's (possibly device-side) count, not the host capacity
+  if (ws.step_dev) step = *ws.step_dev;
   bliss_counters* ctr = ws.ctr;
   const int n_cand = ctr->n_cand;
   const float cf = (float)ctr->c;
@@ -574,6 +540,8 @@ __global__ void __launch_bounds__(256) k_select_poisson(int n_seeds, unsigned lo
 __global__ void __launch_bounds__(256) k_topk_keys(int n_seeds, unsigned long long seed, unsigned long long step,
                                                   unsigned layer, const float* __restrict__ u_inject,
                                                   float* __restrict__ keys, bliss_workspace ws) {
+  n_seeds = ws.ctr->n_seeds;   // the plan's (possibly device-side) count, not the host capacity
+  if (ws.step_dev) step = *ws.step_dev;
   const int n_cand = ws.ctr->n_cand;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_cand; j += gridDim.x * blockDim.x) {
     int nid = ws.cand[j];
@@ -632,6 +600,7 @@ __global__ void __launch_bounds__(1024) k_topk_threshold(int fanout, const float
 // keys > T are selected; among keys == T the `need` lowest candidate slots (deterministic).
 __global__ void __launch_bounds__(1024) k_topk_mark(int n_seeds, const float* __restrict__ keys,
                                                    unsigned* __restrict__ thr, bliss_workspace ws) {
+  n_seeds = ws.ctr->n_seeds;   // the plan's (possibly device-side) count, not the host capacity
   // single CTA so ties are taken in slot order
   __shared__ int s_scan[40];
   const int n_cand = ws.ctr->n_cand;
@@ -787,6 +756,7 @@ __global__ void __launch_bounds__(BLISS_CTA) k_block_count(GraphView g, const in
 #define BLISS_RANK_TILE 2048
 __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__ seeds, int n_seeds,
                                                     bliss_workspace ws, bliss_block_out out) {
+  n_seeds = ws.ctr->n_seeds;   // the plan's (possibly device-side) count, not the host capacity
   __shared__ unsigned long long s_keys[BLISS_RANK_TILE];
   __shared__ int s_scan[40];
   bliss_counters* ctr = ws.ctr;
@@ -821,6 +791,7 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
       out.indptr[n_seeds] = base;
       ctr->n_edges = base;
       ctr->n_src = n_seeds + n_sel;
+      if (n_seeds + n_sel > out.cap_src) ctr->error |= BLISS_ERR_SEL_CAPACITY;
       if (base > out.cap_edges && out.cap_edges > 0) ctr->error |= BLISS_ERR_EDGE_CAPACITY;
     }
     for (int i = threadIdx.x; i < n_seeds; i += blockDim.x) {
@@ -929,7 +900,7 @@ __global__ void __launch_bounds__(BLISS_CTA) k_block_fill(FillCtx c, const int32
   const int tid = threadIdx.x, lane = lane_id();
   const bool needs_row_w = (c.mode != BLISS_MODE_LADIES);
   constexpr int LIGHT_CAP = BLISS_LIST_CAP / BLISS_WARPS;
-  if (ctr->n_edges > out.cap_edges) return;  // capacity error already flagged
+  if (ctr->n_edges > out.cap_edges || ctr->error) return;  // capacity error already flagged by the index kernel
   int item = blockIdx.x, nxt = gridDim.x + blockIdx.x, iter = 0;
   for (; item < n_items; ++iter) {
     if (tid == 0) s_next[iter & 1] = 2 * gridDim.x + atomicAdd(&ctr->queue[2], 1);
@@ -1088,8 +1059,9 @@ __global__ void __launch_bounds__(1024) k_t_scan(int32_t* cnt_cursor, int n, int
 }
 // Edges of a source land in arbitrary order inside its segment; k_t_sort restores ascending edge
 // id so the backward sums are run-to-run deterministic.
-__global__ void k_t_fill(const int32_t* __restrict__ edge_src, int64_t n_edges, int32_t* __restrict__ cursor,
-                         int32_t* __restrict__ t_perm) {
+__global__ void k_t_fill(const int32_t* __restrict__ edge_src, int64_t n_edges, const int64_t* __restrict__ n_edges_dev,
+                         int32_t* __restrict__ cursor, int32_t* __restrict__ t_perm) {
+  if (n_edges_dev) n_edges = min(n_edges, *n_edges_dev);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += stride) {
     int slot = atomicAdd(&cursor[edge_src[e]], 1);
@@ -1174,7 +1146,6 @@ static inline int grid_for(int64_t n, int threads, int max_blocks) {
   if (b > max_blocks) b = max_blocks;
   return (int)b;
 }
-static int g_prob_smem_set = 0;
 
 extern "C" {
 
@@ -1201,18 +1172,17 @@ int bliss_frontier_prob(const bliss_graph* g, const int32_t* seeds, int32_t n_se
   if (!g || !seeds || !ws || n_seeds < 0) return -1;
   if (!edge_weight_csc) return -1;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = BLISS_STAGE_CAP * sizeof(float);
-  if (!g_prob_smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_frontier_prob, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    g_prob_smem_set = 1;
-  }
-  const double fx_scale = (double)(1ull << fx_bits_for(n_seeds));
   const float one_minus_eta = (float)(1.0 - (double)eta);
-  // persistent grid, static round-robin over the heavy-first item list
-  int blocks = grid_for((int64_t)n_seeds * BLISS_CTA, BLISS_CTA, BLISS_SM_COUNT * BLISS_PROB_CTAS_PER_SM);
-  k_frontier_prob<<<blocks, BLISS_CTA, smem, st>>>(view_of(g), edge_weight_csc, eta, one_minus_eta, mode, *ws,
-                                                  fx_scale);
+  // persistent grids of warps over the plan's chunk table (count read on the device)
+  const int blocks = grid_for((int64_t)n_seeds * 256 * 4, 256, BLISS_SM_COUNT * 8);
+  const bool bandit = (mode & 1) == BLISS_MODE_BANDIT;
+  if (bandit) {   // the row sums are also needed by the block fill when importance sampling is off
+    k_prob_pass1<<<blocks, 256, 0, st>>>(edge_weight_csc, *ws);
+    BLISS_CHECK_LAUNCH();
+    k_prob_pass2<<<blocks, 256, 0, st>>>(edge_weight_csc, eta, one_minus_eta, *ws);
+    BLISS_CHECK_LAUNCH();
+  }
+  k_prob_pass3<<<blocks, 256, 0, st>>>(view_of(g), edge_weight_csc, eta, one_minus_eta, mode, *ws);
   BLISS_CHECK_LAUNCH();
   k_collect_candidates<<<grid_for(g->num_nodes, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(
       g->num_nodes, (mode & BLISS_COLLECT_BITMAP) ? 1 : 0, *ws);
@@ -1355,7 +1325,7 @@ int bliss_block_finish(int32_t n_seeds, int32_t mode, const bliss_workspace* ws,
 int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                           int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor,
                           int32_t* t_scratch, int32_t* t_dst, int32_t* t_perm, int32_t* t_heavy,
-                          int32_t have_counts, void* stream) {
+                          int32_t have_counts, const int64_t* n_edges_dev, void* stream) {
   if (n_edges < 0 || n_src < 0 || !t_indptr || !t_cursor) return -1;
   if (n_edges > 0 && (!edge_src || !edge_dst || !t_scratch || !t_dst || !t_perm)) return -1;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1371,7 +1341,7 @@ int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int6
   k_t_scan<<<1, 1024, 0, st>>>(t_cursor, n_src, t_indptr, t_heavy);
   BLISS_CHECK_LAUNCH();
   if (n_edges == 0) return 0;
-  k_t_fill<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, t_cursor, t_scratch);
+  k_t_fill<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, n_edges_dev, t_cursor, t_scratch);
   BLISS_CHECK_LAUNCH();
   const int n_words = (n_dst + 31) / 32;
   const size_t smem = (size_t)BLISS_WARPS * 2 * n_words * sizeof(unsigned);

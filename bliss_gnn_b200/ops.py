@@ -53,7 +53,7 @@ def block_transpose_into(block, pool):
     E, n_dst = block.num_edges(), block.num_dst_nodes()
     N.call("bliss_block_transpose", N.ptr(block.edge_src), N.ptr(block.edge_dst), E, pool.cap_src, n_dst,
            N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_scratch), N.ptr(pool.t_dst), N.ptr(pool.t_perm),
-           N.ptr(pool.t_heavy), 1, N.stream())          # counts were accumulated by the fill kernel (out_deg)
+           N.ptr(pool.t_heavy), 1, None, N.stream())    # counts were accumulated by the fill kernel (out_deg)
     block._transpose = (pool.t_indptr[:block.num_src_nodes() + 1], pool.t_dst[:E], pool.t_perm[:E], pool.t_heavy)
 
 
@@ -70,7 +70,7 @@ def block_transpose(block):
         t_heavy = torch.empty(n_src + 1, dtype=torch.int32, device=dev)
         N.call("bliss_block_transpose", N.ptr(block.edge_src), N.ptr(block.edge_dst), E, n_src, n_dst,
                N.ptr(t_indptr), N.ptr(t_cursor), N.ptr(t_scratch), N.ptr(t_dst), N.ptr(t_perm), N.ptr(t_heavy),
-               0, N.stream())
+               0, None, N.stream())
         block._transpose = (t_indptr, t_dst[:E], t_perm[:E], t_heavy)
     return block._transpose
 

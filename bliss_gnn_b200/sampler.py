@@ -47,6 +47,13 @@ class _Workspace:
         self.keep_bits = torch.zeros(g.num_edges() // 32 + 2, **i32)
         self.pos_a = torch.empty(V, dtype=torch.int64, device=dev)
         self.pos_d = torch.empty(V, **i32)
+        n_chunk_cap = g.num_edges() // 256 + V + 8          # every column cut into 256-edge chunks
+        self.row_a = torch.empty(V, dtype=torch.int64, device=dev)
+        self.row_d = torch.empty(V, **i32)
+        self.chunk_first = torch.empty(V + 1, **i32)
+        self.chunk_row = torch.empty(n_chunk_cap, **i32)
+        self.part_w = torch.empty(n_chunk_cap, dtype=torch.float64, device=dev)
+        self.part_q = torch.empty(n_chunk_cap, dtype=torch.float64, device=dev)
         self.cand = torch.empty(V, **i32)
         self.p_cand = torch.empty(V, dtype=torch.float32, device=dev)
         self.sel = torch.empty(V, **i32)
@@ -58,17 +65,42 @@ class _Workspace:
         self.src_nid = torch.empty(V, **i32)
         self.node_prob = torch.empty(V, dtype=torch.float32, device=dev)
         self.key_scratch = None
-        self.ctr = torch.zeros(C.sizeof(N.Counters), dtype=torch.uint8, device=dev)
-        self.ctr_host = torch.zeros(C.sizeof(N.Counters), dtype=torch.uint8).pin_memory()
+        self.MAX_LAYERS = 16
+        csz = C.sizeof(N.Counters)
+        self.ctr_all = torch.zeros(self.MAX_LAYERS, csz, dtype=torch.uint8, device=dev)   # one block per layer
+        self.ctr = self.ctr_all[0]
+        self.ctr_host = torch.zeros(csz, dtype=torch.uint8).pin_memory()
+        self.ctr_all_host = torch.zeros(self.MAX_LAYERS, csz, dtype=torch.uint8).pin_memory()
         self.ws = N.Workspace(
             acc=N.ptr(self.acc), first_pos=N.ptr(self.first_pos), node_info=N.ptr(self.node_info),
             sel_bits=N.ptr(self.sel_bits), cand_bits=N.ptr(self.cand_bits), keep_bits=N.ptr(self.keep_bits), cand=N.ptr(self.cand), p_cand=N.ptr(self.p_cand), sel=N.ptr(self.sel),
-            row_list=N.ptr(self.row_list), pos_a=N.ptr(self.pos_a), pos_d=N.ptr(self.pos_d), row_w=N.ptr(self.row_w), row_q=N.ptr(self.row_q),
+            row_list=N.ptr(self.row_list), pos_a=N.ptr(self.pos_a), pos_d=N.ptr(self.pos_d), row_a=N.ptr(self.row_a), row_d=N.ptr(self.row_d),
+            chunk_first=N.ptr(self.chunk_first), chunk_row=N.ptr(self.chunk_row), part_w=N.ptr(self.part_w),
+            part_q=N.ptr(self.part_q), row_w=N.ptr(self.row_w), row_q=N.ptr(self.row_q),
             row_cnt=N.ptr(self.row_cnt), row_t=N.ptr(self.row_t), cap_seeds=V, cap_sel=V, ctr=N.ptr(self.ctr))
         self.gview = N.Graph(num_nodes=V, num_edges=g.num_edges(), indptr=N.ptr(g.indptr),
                              indices=N.ptr(g.indices), eid=N.ptr(g.eid))
         self._keep = (g.indptr, g.indices, g.eid)
         N.call("bliss_workspace_init", C.byref(self.ws), V, N.stream())
+
+    def ws_layer(self, layer: int, n_seeds_dev=None, step_dev=None) -> "N.Workspace":
+        """The workspace descriptor with layer ``layer``'s own counters block and, for sync-free
+        chaining, the device addresses the kernels read the seed count / Philox step from."""
+        ws = N.Workspace.from_buffer_copy(self.ws)
+        ws.ctr = self.ctr_all[layer].data_ptr()
+        ws.n_seeds_dev = n_seeds_dev
+        ws.step_dev = step_dev
+        return ws
+
+    def counter_ptr(self, layer: int, field: str) -> int:
+        return self.ctr_all[layer].data_ptr() + getattr(N.Counters, field).offset
+
+    def read_all_counters(self, n_layers: int):
+        """One D2H copy + one stream sync for all layers' counters (end of a sync-free step)."""
+        self.ctr_all_host.copy_(self.ctr_all, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        raw = self.ctr_all_host.numpy()
+        return [N.Counters.from_buffer_copy(raw[l].tobytes()) for l in range(n_layers)]
 
     def read_counters(self) -> N.Counters:
         self.ctr_host.copy_(self.ctr, non_blocking=True)
@@ -406,6 +438,44 @@ class BanditLadiesSampler:
                self._u_ptr(g, block_id), N.ptr(wsp.key_scratch), C.byref(wsp.ws), C.byref(out), N.stream())
         return self._finish_block(fr, out, bufs, pool)
 
+    # ---- sync-free path (CUDA-graph capture of the whole step) -----------------------------------
+    def enqueue_static(self, g, seeds_static, pools, step_dev):
+        """Enqueue the sampling of every layer into the capacity pools with NO host synchronisation:
+        each layer reads its true seed count from the previous layer's device counters, the Philox
+        step from ``step_dev``, and the transpose its edge count from the counters.  Capturable in a
+        CUDA graph; the caller reads all counters once per step (``_Workspace.read_all_counters``)."""
+        wsp = self._bind(g)
+        L = len(self.nodes_per_layer)
+        bandit = self._mode == N.MODE_BANDIT
+        weights_static = None if bandit else g.csc_edata(self.edge_weight)
+        for block_id in reversed(range(L)):
+            pool, top = pools[block_id], block_id == L - 1
+            seeds = seeds_static if top else pools[block_id + 1].src_nid
+            n_cap = pool.cap_dst
+            ws = wsp.ws_layer(block_id, None if top else wsp.counter_ptr(block_id + 1, "n_src"), N.ptr(step_dev))
+            weights = self._w_csc[block_id] if bandit else weights_static
+            mode = self._mode | (0 if self.importance_sampling else N.MODE_UNIFORM)
+            if self.collect == "bitmap" or (self.collect == "auto" and g.num_nodes() > self.DENSE_COLLECT_MAX):
+                mode |= N.COLLECT_BITMAP
+            if not self._poisson and wsp.key_scratch is None:
+                wsp.key_scratch = torch.empty(g.num_nodes() + 4, dtype=torch.float32, device=g.device)
+            e32 = pool.e32
+            out = N.BlockOut(indptr=N.ptr(pool.indptr), edge_src=N.ptr(e32[0]), edge_dst=N.ptr(e32[1]),
+                             csc_pos=N.ptr(pool.csc_pos), eid=N.ptr(e32[2]), q_ij=N.ptr(e32[4]) if bandit else None,
+                             edge_w=N.ptr(e32[3]), src_nid=N.ptr(pool.src_nid), node_prob=N.ptr(pool.node_prob),
+                             out_deg=N.ptr(pool.t_cursor), heavy_rows=N.ptr(pool.heavy), inv_deg=N.ptr(pool.inv_deg),
+                             cap_edges=pool.cap_edges, cap_src=pool.cap_src, pad_src=pool.cap_src,
+                             pad_rows=pool.cap_dst)
+            st = N.stream()
+            N.call("bliss_sample_layer_front", C.byref(wsp.gview), N.ptr(seeds), n_cap, N.ptr(weights), float(self.eta),
+                   mode, int(self.nodes_per_layer[block_id]), float(self.eps), int(self._poisson), self.rng_seed,
+                   0, block_id, self._u_ptr(g, block_id), N.ptr(wsp.key_scratch), C.byref(ws), C.byref(out), st)
+            N.call("bliss_sample_layer_back", C.byref(wsp.gview), N.ptr(seeds), n_cap, N.ptr(weights), float(self.eta),
+                   self._mode, C.byref(ws), C.byref(out), st)
+            N.call("bliss_block_transpose", N.ptr(e32[0]), N.ptr(e32[1]), pool.cap_edges, pool.cap_src, pool.cap_dst,
+                   N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_scratch), N.ptr(pool.t_dst),
+                   N.ptr(pool.t_perm), N.ptr(pool.t_heavy), 1, wsp.counter_ptr(block_id, "n_edges"), st)
+
     # ---- bandit update ------------------------------------------------------------------------
     def calculate_alpha(self, mfg):
         """``bandit_sampler.py:140-158``.  SAGE/GCN: the static edge weight; GAT: from a_ij, q_ij."""
@@ -419,7 +489,8 @@ class BanditLadiesSampler:
             return ("gat", a, asum, qsum)
         return ("static", None, None, None)
 
-    def _reward_call(self, idx, mfg, g, alpha, weights, rewards=None, x_out=None, l1=None):
+    def _reward_call(self, idx, mfg, g, alpha, weights, rewards=None, x_out=None, l1=None, n_edges_dev=None,
+                     count_out=None):
         kind, a, asum, qsum = alpha
         wsp = self._bind(g)
         w_static = g.csc_edata(self.edge_weight) if kind == "static" else None
@@ -427,12 +498,14 @@ class BanditLadiesSampler:
         emb = emb.detach()
         if emb.dtype != torch.float32:
             emb = emb.float()
-        N.call("bliss_reward_update", 
+        if n_edges_dev is None:
+            n_edges_dev = getattr(mfg, "_n_edges_dev", None)     # capacity-padded block: true count on the device
+        N.call("bliss_reward_update",
             C.byref(wsp.gview), N.ptr(mfg.indptr), N.ptr(mfg.edge_src), N.ptr(mfg.edge_dst), N.ptr(mfg.csc_pos),
             N.ptr(mfg.dstdata[NID]), N.ptr(mfg.edata["q_ij"]), N.ptr(mfg.srcdata[self.node_prob]),
             N.ptr(emb.contiguous()), N.ptr(w_static), N.ptr(a), N.ptr(asum), N.ptr(qsum),
             1 if kind == "gat" else 0, 0.01, mfg.num_dst_nodes(), mfg.num_edges(), N.ptr(weights),
-            N.ptr(rewards), N.ptr(x_out), N.ptr(l1), N.stream())
+            N.ptr(rewards), N.ptr(x_out), N.ptr(l1), n_edges_dev, count_out, N.stream())
 
     def calculate_rewards(self, idx, mfg, g, alpha):
         """``bandit_sampler.py:160-193``: stores ``mfg.edata['rewards']`` (emit-only kernel call)."""
@@ -472,7 +545,18 @@ class BanditLadiesSampler:
         N.call("bliss_scale_by_inv", N.ptr(w), w.numel(), N.ptr(self._l1[idx:idx + 1]), 1e-12, N.stream())
         self._l1[idx] = 1.0
 
-    def exp3(self, mfgs, g, exchange=None):
+    def tick_renorm(self, n_layers: int):
+        """Lazy mode's range safety: physically re-normalise every ``renorm_every`` updates (a weight
+        grows by at most e per update, ``bandit_sampler.py:244-246``)."""
+        if self.normalize != "lazy":
+            return
+        self._updates_since_renorm += 1
+        if self._updates_since_renorm >= self.renorm_every:
+            for idx in range(n_layers):
+                self._renormalize(idx)
+            self._updates_since_renorm = 0
+
+    def exp3(self, mfgs, g, exchange=None, count_renorm=True):
         """``bandit_sampler.py:251-267``: reward + weight update of every layer, one fused kernel each.
         ``exchange`` (a ``parallel.BanditExchange``) selects the data-parallel fast path: exponents are
         written into the exchange's send buffer, ONE all-gather moves all layers, one kernel per layer
@@ -494,12 +578,8 @@ class BanditLadiesSampler:
             for idx, mfg in enumerate(mfgs):
                 alpha = self.calculate_alpha(mfg)
                 self.update_exp3_weights(idx, mfg, g, alpha)
-        if self.normalize == "lazy":
-            self._updates_since_renorm += 1
-            if self._updates_since_renorm >= self.renorm_every:   # range safety: growth ≤ e per step
-                for idx in range(len(mfgs)):
-                    self._renormalize(idx)
-                self._updates_since_renorm = 0
+        if count_renorm:
+            self.tick_renorm(len(mfgs))
 
 
 class PoissonBanditLadiesSampler(BanditLadiesSampler):

@@ -167,7 +167,9 @@ class Trainer:
 
     def training_step(self, seeds: torch.Tensor) -> torch.Tensor:
         if self.static_graph:
-            return self._training_step_static(seeds)
+            if self.world == 1 and self._full_graph_ok():
+                return self._training_step_full_graph(seeds)
+            return self._training_step_static_partial(seeds)
         dm, g = self.dm, self.dm.g
         input_nodes, output_nodes, mfgs = dm.sampler.sample_blocks(g, seeds)
         return self._eager_rest(mfgs)
@@ -257,7 +259,9 @@ class Trainer:
         self.graph_kernels = _native.STATS.launches - before    # hand-written kernels inside one replay
         _native.STATS.launches = before
 
-    def _training_step_static(self, seeds: torch.Tensor) -> torch.Tensor:
+    def _training_step_static_partial(self, seeds: torch.Tensor) -> torch.Tensor:
+        """Eager sampling into the pools + replayed forward/backward(/Adam): the data-parallel variant
+        (the collectives sit between the sampler and the optimizer)."""
         dm, g, smp = self.dm, self.dm.g, self.dm.sampler
         L = len(smp.nodes_per_layer)
         if self._pools is None:
@@ -304,6 +308,106 @@ class Trainer:
         self.last_blocks, self.last_pred, self.last_labels = mfgs, self._static_pred, self._static_y
         return self._static_loss
 
+    # ---- whole step in one CUDA graph (single rank): sampling included, one host sync per step ------
+    def _full_graph_ok(self) -> bool:
+        smp = self.dm.sampler
+        return smp._stages_not_overridden() and smp.inject_uniforms is None
+
+    def _training_step_full_graph(self, seeds: torch.Tensor) -> torch.Tensor:
+        dm, g, smp = self.dm, self.dm.g, self.dm.sampler
+        L = len(smp.nodes_per_layer)
+        if self._pools is None or seeds.numel() != dm.batch_size:
+            if self.num_steps < self.eager_warmup or seeds.numel() != dm.batch_size:
+                _, _, mfgs = smp.sample_blocks(g, seeds)           # ordinary steps: size the pools
+                if self._max_src is None:
+                    self._max_src, self._max_edges = [0] * L, [0] * L
+                for l, b in enumerate(mfgs):
+                    self._max_src[l] = max(self._max_src[l], b.num_src_nodes())
+                    self._max_edges[l] = max(self._max_edges[l], b.num_edges())
+                return self._eager_rest(mfgs)
+            self._alloc_pools()
+        if self._graph is None:
+            self._capture_full()
+        self._seeds_static.copy_(seeds, non_blocking=True)
+        self._graph.replay()
+        self.graph_replays += 1
+        ctrs = smp._wsp.read_all_counters(L)                   # the step's single host sync
+        smp.step += 1
+        smp.tick_renorm(L)
+        grow = False
+        for l, c in enumerate(ctrs):
+            if c.error:
+                raise RuntimeError(f"static step: capacity of layer {l} exceeded (n_src {c.n_src}/{self._pools[l].cap_src}, "
+                                   f"edges {c.n_edges}/{self._pools[l].cap_edges}); the step is invalid — "
+                                   "raise the pool margins (Trainer.pool_margin) or use static_graph=False")
+            self._max_src[l] = max(self._max_src[l], c.n_src)
+            self._max_edges[l] = max(self._max_edges[l], c.n_edges)
+            grow |= c.n_src > 0.92 * self._pools[l].cap_src or c.n_edges > 0.85 * self._pools[l].cap_edges
+        smp.last_counters = ctrs
+        self.num_steps += 1
+        for i, c in enumerate(ctrs):
+            self.cum_sampled_nodes[i] = self.cum_sampled_nodes[i] * self.w + c.n_src
+            self.cum_sampled_edges[i] = self.cum_sampled_edges[i] * self.w + c.n_edges
+        self.cum_sampled_nodes[L] = self.cum_sampled_nodes[L] * self.w + dm.batch_size
+        self.last_blocks = _CounterBlocks(ctrs)
+        self.last_pred, self.last_labels = self._static_pred, self._static_y
+        if grow:                                               # high-water mark: re-size before it can overflow
+            self._alloc_pools()
+        return self._static_loss
+
+    def _capture_full(self):
+        from . import _native
+        dm, g, smp = self.dm, self.dm.g, self.dm.sampler
+        smp._bind(g)
+        if getattr(self, "_step_dev", None) is None:
+            self._step_dev = torch.zeros(1, dtype=torch.int64, device=g.device)
+        self._step_dev.fill_(smp.step)
+        for l, pb in enumerate(self._padded):
+            pool = self._pools[l]
+            pb._n_edges_dev = smp._wsp.counter_ptr(l, "n_edges")
+            if smp._mode == _native.MODE_BANDIT:
+                pb.edata["q_ij"] = pool.e32[4].view(torch.float32)
+                pb.srcdata[smp.node_prob] = pool.node_prob
+            dict.pop(pb.srcdata, "embed_norm", None)
+            dict.pop(pb.edata, "a_ij", None)
+        self.last_pred = None
+
+        def body():
+            smp.enqueue_static(g, self._seeds_static, self._pools, self._step_dev)
+            loss, pred, y = self._padded_fwd_bwd(True)
+            if "bandit" in dm.sampler_name:
+                smp.exp3(self._padded, g, count_renorm=False)
+            self._step_dev.add_(1)
+            return loss, pred, y
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        state = (smp.state_dict()["exp3_w_csc"].clone(), smp._l1.clone()) if smp._w_csc is not None else None
+        opt_state = None
+        with torch.cuda.stream(side):                       # warm-up replays off the default stream …
+            import copy
+            opt_state = copy.deepcopy(self.optimizer.state_dict())
+            params = [p.detach().clone() for p in self.grads.params]
+            self._seeds_static.copy_(self.dm.train_nid[: dm.batch_size])
+            for _ in range(2):
+                body()
+            # … must not change the training state: restore parameters, Adam moments, bandit weights
+            for p, q in zip(self.grads.params, params):
+                p.data.copy_(q)
+            self.optimizer.load_state_dict(opt_state)
+            if state is not None:
+                for l, w in enumerate(state[0]):
+                    smp._w_csc[l].copy_(w)
+                smp._l1.copy_(state[1])
+            self._step_dev.fill_(smp.step)
+        torch.cuda.current_stream().wait_stream(side)
+        before = _native.STATS.launches
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss, self._static_pred, self._static_y = body()
+        self.graph_kernels = _native.STATS.launches - before
+        _native.STATS.launches = before
+
     @torch.no_grad()
     def validate(self) -> float:
         """Per-epoch validation with the same stochastic sampler (``train_lightning.py:179-203,410-422``)."""
@@ -317,6 +421,27 @@ class Trainer:
             total += y.shape[0]
         self.model.train()
         return correct / max(total, 1)
+
+
+class _CounterBlocks(list):
+    """What ``Trainer.last_blocks`` holds after a whole-step graph replay: the per-layer sizes (the
+    blocks themselves live in the capacity pools)."""
+
+    class _B:
+        def __init__(self, c):
+            self._c = c
+
+        def num_src_nodes(self):
+            return int(self._c.n_src)
+
+        def num_dst_nodes(self):
+            return int(self._c.n_seeds)
+
+        def num_edges(self):
+            return int(self._c.n_edges)
+
+    def __init__(self, ctrs):
+        super().__init__(self._B(c) for c in ctrs)
 
 
 def build_argparser() -> argparse.ArgumentParser:

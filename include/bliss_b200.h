@@ -60,7 +60,7 @@ typedef struct bliss_counters {
   double  s_last;      /* last S = sum min(c p, 1)                               */
   int32_t queue[4];    /* dynamic row-queue cursors of the three row passes      */
   int32_t error;       /* non-zero: a capacity was exceeded (see BLISS_ERR_*)    */
-  int32_t pad;
+  int32_t n_chunks;    /* 256-edge warp-chunks of the probability passes         */
 } bliss_counters;
 
 #define BLISS_ERR_SEL_CAPACITY 1
@@ -84,6 +84,12 @@ typedef struct bliss_workspace {
   int32_t*  row_list;   /* [S]  heavy rows from the front (longest first), light from the back */
   int64_t*  pos_a;      /* [S]  CSC start of the row at each row_list position            */
   int32_t*  pos_d;      /* [S]  in-degree of the row at each row_list position            */
+  int64_t*  row_a;      /* [S]  CSC start of every seed's column (by seed rank)           */
+  int32_t*  row_d;      /* [S]  in-degree of every seed                                   */
+  int32_t*  chunk_first;/* [S+1] first 256-edge chunk of every seed's column (prefix)     */
+  int32_t*  chunk_row;  /* [E/256+V] seed rank of every chunk                             */
+  double*   part_w;     /* [E/256+V] per-chunk partial of sum_j w_ij                      */
+  double*   part_q;     /* [E/256+V] per-chunk partial of sum_j q_ij                      */
   float*    row_w;      /* [S]  sum_j w_ij  per seed                                      */
   float*    row_q;      /* [S]  sum_j q_ij  per seed                                      */
   int32_t*  row_cnt;    /* [S]  kept in-edges per seed                                    */
@@ -91,6 +97,10 @@ typedef struct bliss_workspace {
   int64_t   cap_seeds;  /* S */
   int64_t   cap_sel;    /* C */
   bliss_counters* ctr;  /* one counters block                                             */
+  /* sync-free operation (CUDA-graph replay): values the kernels read from the device instead of
+   * taking them from the host arguments, which then only give capacities.  NULL = use the host value. */
+  const int32_t*  n_seeds_dev;  /* true seed count of this layer (e.g. the previous layer's n_src) */
+  const uint64_t* step_dev;     /* Philox step counter                                            */
 } bliss_workspace;
 
 /* Outputs of one sampled layer (device pointers, capacities checked against the counters). */
@@ -175,6 +185,7 @@ int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int6
                           int32_t* t_scratch /* [E] */, int32_t* t_dst, int32_t* t_perm,
                           int32_t* t_heavy /* [n_src+1] heavy source rows, [0]=count; may be NULL */,
                           int32_t have_counts /* t_cursor already holds out-degrees (block_out.out_deg) */,
+                          const int64_t* n_edges_dev /* true edge count on the device, or NULL */,
                           void* stream);
 
 /* ---- (5) aggregation ------------------------------------------------------------------------
@@ -222,6 +233,8 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
                         float* rewards /* [E_b] or NULL */,
                         float* x_out /* [E_b] clamped exponent, or NULL */,
                         double* l1_delta /* [1] accumulated sum(w_new - w_old), or NULL */,
+                        const int64_t* n_edges_dev /* true edge count on the device (n_edges = capacity), or NULL */,
+                        int64_t* count_out /* where to store the edge count (exchange header), or NULL */,
                         void* stream);
 /* apply gathered updates from other ranks: w[pos[k]] *= exp(x[k]) */
 int bliss_apply_updates(const int64_t* pos, const float* x, int64_t n, float* exp3_w_csc,
