@@ -545,6 +545,24 @@ class BanditLadiesSampler:
         N.call("bliss_scale_by_inv", N.ptr(w), w.numel(), N.ptr(self._l1[idx:idx + 1]), 1e-12, N.stream())
         self._l1[idx] = 1.0
 
+    def exp3_emit(self, mfgs, g, exchange):
+        """Data-parallel, sync-free: compute every layer's clamped exponents into the exchange's send
+        buffer (whose position arrays are the blocks' ``csc_pos``) and the edge counts into its header."""
+        for idx, mfg in enumerate(mfgs):
+            assert mfg.csc_pos.data_ptr() == exchange.pos[idx].data_ptr()
+            self._reward_call(idx, mfg, g, self.calculate_alpha(mfg), None, x_out=exchange.x[idx],
+                              count_out=exchange.header.data_ptr() + 8 * idx)
+
+    def exp3_apply(self, exchange, n_layers: int):
+        """Apply all ranks' gathered updates (one kernel per layer, counts read from the headers)."""
+        for idx in range(n_layers):
+            N.call("bliss_apply_updates_packed", N.ptr(exchange.recv), exchange.stride, exchange.world,
+                   8 * idx, exchange.pos_off[idx], exchange.x_off[idx], exchange.caps[idx],
+                   N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]), N.stream())
+            self._updated[idx] = True
+            if self.normalize == "literal":
+                self._renormalize(idx)
+
     def tick_renorm(self, n_layers: int):
         """Lazy mode's range safety: physically re-normalise every ``renorm_every`` updates (a weight
         grows by at most e per update, ``bandit_sampler.py:244-246``)."""

@@ -129,6 +129,9 @@ class Trainer:
         Sampling and the bandit update stay eager (their sizes are data dependent)."""
         self.dm, self.model, self.pg = datamodule, model, process_group
         self.static_graph, self.eager_warmup = bool(static_graph), int(eager_warmup)
+        # the data-parallel code path (two graphs with the collectives in between) can be forced on a
+        # single rank, so it is testable on one GPU
+        self._force_dp = bool(os.environ.get("BLISS_FORCE_DP_PATH")) and process_group is not None
         self._graph, self._pools, self._padded, self._exchange = None, None, None, None
         self._max_src, self._max_edges = None, None
         self.graph_replays, self.graph_kernels = 0, 0
@@ -167,7 +170,7 @@ class Trainer:
 
     def training_step(self, seeds: torch.Tensor) -> torch.Tensor:
         if self.static_graph:
-            if self.world == 1 and self._full_graph_ok():
+            if self._full_graph_ok():
                 return self._training_step_full_graph(seeds)
             return self._training_step_static_partial(seeds)
         dm, g = self.dm, self.dm.g
@@ -203,7 +206,7 @@ class Trainer:
         bandit = "bandit" in dm.sampler_name
         cap_e = [int(1.6 * self._max_edges[l]) + 4096 for l in range(L)]
         self._exchange = None
-        if self.world > 1 and bandit:                       # ranks must agree on the exchange layout
+        if (self.world > 1 or self._force_dp) and bandit:   # ranks must agree on the exchange layout
             from .parallel import BanditExchange
             t = torch.tensor(cap_e, dtype=torch.int64, device=dev)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.pg)
@@ -330,6 +333,11 @@ class Trainer:
             self._capture_full()
         self._seeds_static.copy_(seeds, non_blocking=True)
         self._graph.replay()
+        if self.world > 1 or self._force_dp:      # the only exchanges of a data-parallel step, between the two graphs
+            self.grads.all_reduce_mean_(self.pg)
+            if self._exchange is not None:
+                torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send, group=self.pg)
+            self._graph_b.replay()
         self.graph_replays += 1
         ctrs = smp._wsp.read_all_counters(L)                   # the step's single host sync
         smp.step += 1
@@ -351,6 +359,13 @@ class Trainer:
         self.cum_sampled_nodes[L] = self.cum_sampled_nodes[L] * self.w + dm.batch_size
         self.last_blocks = _CounterBlocks(ctrs)
         self.last_pred, self.last_labels = self._static_pred, self._static_y
+        if self.world > 1:        # re-sizing allocates collectively: agree on it, every 32 steps
+            self._grow_pending = getattr(self, "_grow_pending", False) or grow
+            grow = False
+            if self.num_steps % 32 == 0:
+                flag = torch.tensor([1.0 if self._grow_pending else 0.0], device=g.device)
+                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+                grow, self._grow_pending = bool(flag.item() > 0), False
         if grow:                                               # high-water mark: re-size before it can overflow
             self._alloc_pools()
         return self._static_loss
@@ -358,6 +373,7 @@ class Trainer:
     def _capture_full(self):
         from . import _native
         dm, g, smp = self.dm, self.dm.g, self.dm.sampler
+        L = len(smp.nodes_per_layer)
         smp._bind(g)
         if getattr(self, "_step_dev", None) is None:
             self._step_dev = torch.zeros(1, dtype=torch.int64, device=g.device)
@@ -372,13 +388,25 @@ class Trainer:
             dict.pop(pb.edata, "a_ij", None)
         self.last_pred = None
 
-        def body():
+        dp = self.world > 1 or self._force_dp
+        bandit = "bandit" in dm.sampler_name
+
+        def body():          # graph A (the whole step on a single rank)
             smp.enqueue_static(g, self._seeds_static, self._pools, self._step_dev)
-            loss, pred, y = self._padded_fwd_bwd(True)
-            if "bandit" in dm.sampler_name:
+            loss, pred, y = self._padded_fwd_bwd(not dp)
+            if bandit and not dp:
                 smp.exp3(self._padded, g, count_renorm=False)
-            self._step_dev.add_(1)
+            elif bandit:     # data parallel: emit the exponents + counts into the exchange's send buffer
+                smp.exp3_emit(self._padded, g, self._exchange)
+            if not dp:
+                self._step_dev.add_(1)
             return loss, pred, y
+
+        def body_b():        # graph B (data parallel): after the all-reduce / all-gather
+            self.optimizer.step()
+            if bandit:
+                smp.exp3_apply(self._exchange, L)
+            self._step_dev.add_(1)
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -391,6 +419,8 @@ class Trainer:
             self._seeds_static.copy_(self.dm.train_nid[: dm.batch_size])
             for _ in range(2):
                 body()
+                if dp:
+                    body_b()
             # … must not change the training state: restore parameters, Adam moments, bandit weights
             for p, q in zip(self.grads.params, params):
                 p.data.copy_(q)
@@ -405,6 +435,10 @@ class Trainer:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_loss, self._static_pred, self._static_y = body()
+        if dp:
+            self._graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_b):
+                body_b()
         self.graph_kernels = _native.STATS.launches - before
         _native.STATS.launches = before
 

@@ -225,3 +225,34 @@ def test_static_graph_step_matches_eager(native_lib, kind):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(a)), (losses[False], losses[True])
     # GAT's alpha divides by sums of signed logits: padded-vs-exact GEMM rounding is amplified there
     torch.testing.assert_close(w_static, w_eager, rtol=2e-3 if kind == "gat" else 1e-4, atol=0)
+
+
+def test_data_parallel_graph_path_on_one_rank(native_lib, monkeypatch):
+    """The data-parallel step (graph A: sample+fwd+bwd+reward emit -> NCCL all-reduce / all-gather ->
+    graph B: Adam + packed apply) forced on a 1-rank NCCL group follows the single-graph trajectory."""
+    import torch.distributed as dist
+    from bliss_gnn_b200.graph import synthetic_graph
+    from bliss_gnn_b200.train import DataModule, Trainer, build_model
+    dev = _dev()
+    g = synthetic_graph("flickr", seed=0, scale=0.05).to(dev)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29571", rank=0, world_size=1, device_id=dev)
+    try:
+        res = {}
+        for dp in (False, True):
+            if dp:
+                monkeypatch.setenv("BLISS_FORCE_DP_PATH", "1")
+            dm = DataModule("flickr", fan_out=[128, 64, 32], eta=0.1, device=dev, batch_size=32,
+                            sampler="poisson-bandit", model="sage", seed=0, graph=g)
+            torch.manual_seed(3)
+            model = build_model("sage", dm.in_feats, 64, dm.n_classes, 3, dropout=0.0).to(dev)
+            tr = Trainer(dm, model, 0.002, process_group=dist.group.WORLD if dp else None, static_graph=True,
+                         eager_warmup=3)
+            losses = [float(tr.training_step(s).item()) for _, s in zip(range(12), dm.train_batches())]
+            assert tr.graph_replays >= 7 and (tr._exchange is not None) == dp
+            res[dp] = (losses, dm.sampler.exp3_weights.clone())
+        for a, b in zip(res[False][0], res[True][0]):
+            assert abs(a - b) <= 2e-4 * max(1.0, abs(a)), (res[False][0], res[True][0])
+        torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-4, atol=0)
+    finally:
+        dist.destroy_process_group()
