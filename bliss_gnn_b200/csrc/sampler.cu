@@ -116,13 +116,6 @@ __global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32
     }
     light_base += tl;
   }
-  __syncthreads();
-  // chunk -> row table, one warp per row (a 20 K-edge row owns ~80 consecutive entries)
-  for (int i = warp_id(); i < n_seeds; i += blockDim.x / 32) {
-    const int first = ws.chunk_first[i];
-    const int nch = max(1, (ws.row_d[i] + BLISS_CHUNK - 1) / BLISS_CHUNK);
-    for (int c = lane_id(); c < nch; c += 32) ws.chunk_row[first + c] = i;
-  }
   e_in = block_sum(e_in, s_e);
   if (threadIdx.x == 0) {
     ctr->n_seeds = n_seeds;
@@ -181,9 +174,16 @@ struct ChunkRef {
   int64_t a;
   int d, c_first, c_last;  // chunk range of the row [c_first, c_last)
 };
-__device__ __forceinline__ ChunkRef chunk_ref(const bliss_workspace& ws, int c) {
+__device__ __forceinline__ ChunkRef chunk_ref(const bliss_workspace& ws, int c, int n_seeds) {
   ChunkRef r;
-  r.row = ws.chunk_row[c];
+  // row of chunk c = last i with chunk_first[i] <= c: warp-uniform binary search over the prefix
+  // array (a few KB, L1 resident) instead of a materialised chunk->row table
+  int lo = 0, hi = n_seeds - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(ws.chunk_first + mid) <= c) lo = mid; else hi = mid - 1;
+  }
+  r.row = lo;
   r.a = ws.row_a[r.row];
   r.d = ws.row_d[r.row];
   r.c_first = ws.chunk_first[r.row];
@@ -201,9 +201,10 @@ __device__ __forceinline__ float row_total(const double* __restrict__ part, int 
 __global__ void __launch_bounds__(256) k_prob_pass1(const float* __restrict__ W, bliss_workspace ws) {
   const int lane = lane_id();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_seeds = ws.ctr->n_seeds;
   const int n_chunks = ws.ctr->n_chunks;
   for (int c = warp; c < n_chunks; c += nwarps) {
-    const ChunkRef r = chunk_ref(ws, c);
+    const ChunkRef r = chunk_ref(ws, c, n_seeds);
     const float* __restrict__ wr = W + r.a + r.k0;
     double acc = 0.0;
 #pragma unroll
@@ -220,9 +221,10 @@ __global__ void __launch_bounds__(256) k_prob_pass2(const float* __restrict__ W,
                                                    bliss_workspace ws) {
   const int lane = lane_id();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_seeds = ws.ctr->n_seeds;
   const int n_chunks = ws.ctr->n_chunks;
   for (int c = warp; c < n_chunks; c += nwarps) {
-    const ChunkRef r = chunk_ref(ws, c);
+    const ChunkRef r = chunk_ref(ws, c, n_seeds);
     const float* __restrict__ wr = W + r.a + r.k0;
     float v[BLISS_CHUNK / 32];
 #pragma unroll
@@ -253,10 +255,11 @@ __global__ void __launch_bounds__(256) k_prob_pass3(GraphView g, const float* __
   const bool bitmap = (mode_flags & BLISS_COLLECT_BITMAP);
   const int lane = lane_id();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_seeds = ws.ctr->n_seeds;
   const int n_chunks = ws.ctr->n_chunks;
   const double fx_scale = (double)(1ull << fx_bits_for(ws.ctr->n_seeds));
   for (int c = warp; c < n_chunks; c += nwarps) {
-    const ChunkRef r = chunk_ref(ws, c);
+    const ChunkRef r = chunk_ref(ws, c, n_seeds);
     const float* __restrict__ wr = W + r.a + r.k0;
     const int32_t* __restrict__ idx = g.indices + r.a + r.k0;
     float v[BLISS_CHUNK / 32];
@@ -763,22 +766,32 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
   const int n_sel = min(ctr->n_sel, (int)ws.cap_sel);
   if (blockIdx.x == 0) {
     int base = 0, hbase = 0;
-    for (int b = 0; b < n_seeds; b += blockDim.x) {
-      int i = b + threadIdx.x;
-      int v = (i < n_seeds) ? ws.row_cnt[i] : 0;
-      int tot;
-      int p = block_excl_scan(v, s_scan, &tot);
-      if (i < n_seeds) {
-        out.indptr[i] = base + p;
-        if (out.inv_deg) out.inv_deg[i] = 1.0f / (float)max(v, 1);   // fn.mean divisor
+    constexpr int IT = 4;   // rows per thread and iteration: 4x fewer CTA-wide scans
+    for (int b = 0; b < n_seeds; b += blockDim.x * IT) {
+      const int i0 = b + threadIdx.x * IT;
+      int v[IT], hv[IT], vsum = 0, hsum = 0;
+#pragma unroll
+      for (int u = 0; u < IT; ++u) {
+        v[u] = (i0 + u < n_seeds) ? ws.row_cnt[i0 + u] : 0;
+        hv[u] = v[u] > BLISS_SPMM_HEAVY;
+        vsum += v[u];
+        hsum += hv[u];
+      }
+      int tot, ht = 0;
+      int p = block_excl_scan(vsum, s_scan, &tot);
+      int hp = out.heavy_rows ? block_excl_scan(hsum, s_scan, &ht) : 0;
+#pragma unroll
+      for (int u = 0; u < IT; ++u) {
+        if (i0 + u < n_seeds) {
+          out.indptr[i0 + u] = base + p;
+          if (out.inv_deg) out.inv_deg[i0 + u] = 1.0f / (float)max(v[u], 1);   // fn.mean divisor
+          if (out.heavy_rows && hv[u]) out.heavy_rows[1 + hbase + hp] = i0 + u;   // rows the aggregation splits over a CTA
+        }
+        p += v[u];
+        hp += hv[u];
       }
       base += tot;
-      if (out.heavy_rows) {  // rows the aggregation kernels split across a whole CTA
-        int hv = v > BLISS_SPMM_HEAVY, ht;
-        int hp = block_excl_scan(hv, s_scan, &ht);
-        if (hv) out.heavy_rows[1 + hbase + hp] = i;
-        hbase += ht;
-      }
+      hbase += ht;
     }
     // capacity padding (static-shape replay): rows beyond n_seeds are empty, their mean divisor is 1
     for (int64_t i = n_seeds + 1 + threadIdx.x; i <= out.pad_rows; i += blockDim.x) out.indptr[i] = base;

@@ -17,6 +17,16 @@ from . import ops
 from .graph import Graph
 
 
+def _linear(x, lin: nn.Linear):
+    """``lin(x)``; when the feature table's rows were zero-padded to a 16-byte multiple
+    (``train.DataModule(pad_features=True)``: 602 -> 604 columns keeps cuBLAS off its unaligned
+    kernels, ~2-3x on the input-layer GEMMs) the weight is zero-padded to match — same result."""
+    extra = x.shape[-1] - lin.in_features
+    if extra == 0:
+        return lin(x)
+    return torch.nn.functional.linear(x, torch.nn.functional.pad(lin.weight, (0, extra)), lin.bias)
+
+
 class SAGEConv(nn.Module):
     """``dglnn.SAGEConv(in_feats, out_feats, 'mean')`` with ``edge_weight``."""
 
@@ -40,11 +50,11 @@ class SAGEConv(nn.Module):
         feat_src = self.feat_drop(feat)
         feat_dst = feat_src[: graph.number_of_dst_nodes()]
         lin_before_mp = self._in_src_feats > self._out_feats
-        h = self.fc_neigh(feat_src) if lin_before_mp else feat_src
+        h = _linear(feat_src, self.fc_neigh) if lin_before_mp else feat_src
         h_neigh = ops.spmm(graph, h, edge_weight, dst_scale=ops.mean_scale(graph))   # u_mul_e + fn.mean
         if not lin_before_mp:
-            h_neigh = self.fc_neigh(h_neigh)
-        return self.fc_self(feat_dst) + h_neigh
+            h_neigh = _linear(h_neigh, self.fc_neigh)
+        return _linear(feat_dst, self.fc_self) + h_neigh
 
 
 class GraphConv(nn.Module):
@@ -81,6 +91,8 @@ class GraphConv(nn.Module):
         else:
             dst_norm = graph._gcn_dst_norm
         w = self.weight
+        if feat.shape[-1] > self._in_feats:       # zero-padded feature rows (see _linear)
+            w = torch.nn.functional.pad(w, (0, 0, 0, feat.shape[-1] - self._in_feats))
         if self._in_feats > self._out_feats:
             rst = ops.spmm(graph, torch.matmul(feat, w), edge_weight, src_scale=src_norm, dst_scale=dst_norm)
         else:
@@ -130,7 +142,7 @@ class custom_GATv2Conv(nn.Module):
         if not self._allow_zero_in_degree and bool((graph.in_degrees() == 0).any()):
             raise RuntimeError("There are 0-in-degree nodes in the graph (model.py:49-61)")
         h_src = h_dst = self.feat_drop(feat)                                              # :69
-        feat_src = self.fc_src(h_src).view(-1, self._num_heads, self._out_feats)          # :70
+        feat_src = _linear(h_src, self.fc_src).view(-1, self._num_heads, self._out_feats)  # :70
         h_dst = h_dst[: graph.number_of_dst_nodes()]                                      # :79
         mask = None
         if self.training and self.attn_drop.p > 0:                                        # :88 attn_drop
@@ -138,7 +150,8 @@ class custom_GATv2Conv(nn.Module):
             mask = (torch.rand(graph.num_edges(), self._num_heads, device=feat.device) < keep).float() / keep
         rst, e = ops.gatv2_attention(graph, feat_src, self.attn, self.negative_slope, mask)   # :80-98
         if self.res_fc is not None:
-            rst = rst + self.res_fc(h_dst).view(h_dst.shape[0], -1, self._out_feats)      # :101-103
+            res = _linear(h_dst, self.res_fc) if isinstance(self.res_fc, nn.Linear) else self.res_fc(h_dst)
+            rst = rst + res.view(h_dst.shape[0], -1, self._out_feats)                     # :101-103
         if self.activation:
             rst = self.activation(rst)                                                    # :105-106
         return (rst, e.unsqueeze(-1)) if get_attention else rst                           # :108-112

@@ -49,7 +49,7 @@ class DataModule:
     def __init__(self, dataset_name, undirected=False, data_cpu=False, use_uva=False, fan_out=(128, 256), eta=0.4,
                  device=torch.device("cpu"), batch_size=64, num_workers=0, sampler="bandit",
                  importance_sampling=1, cache_size=0, num_steps=500, model="sage", seed=0, rank=0, world_size=1,
-                 graph: Optional[Graph] = None, normalize="lazy"):
+                 graph: Optional[Graph] = None, normalize="lazy", pad_features: bool = True):
         self.sampler_name, self.num_steps, self.eta = sampler, num_steps, eta
         if graph is None:
             g, n_classes, multilabel = load_dataset(dataset_name, device=device, seed=seed)
@@ -73,6 +73,10 @@ class DataModule:
         self.device = device
         self.batch_size = batch_size
         self.in_feats = g.ndata["features"].shape[1]
+        if pad_features and g.device.type == "cuda" and self.in_feats % 4:
+            # rows of the feature table start 16-byte aligned: 128-bit gather loads and aligned GEMM
+            # operands for the input layer (the models zero-pad their first weight view to match)
+            g.ndata["features"] = F.pad(g.ndata["features"], (0, 4 - self.in_feats % 4)).contiguous()
         self.n_classes, self.multilabel = n_classes, multilabel
         self.rank, self.world_size = rank, world_size
         self._epoch = 0

@@ -256,3 +256,28 @@ def test_data_parallel_graph_path_on_one_rank(native_lib, monkeypatch):
         torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-4, atol=0)
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["sage", "gcn", "gat"])
+def test_padded_feature_rows_give_the_same_model_output(native_lib, kind):
+    """DataModule pads the feature rows to a 16-byte multiple; the models zero-pad their first weight
+    view — logits and gradients are unchanged."""
+    from bliss_gnn_b200 import model as M
+    g, gd, ob, db = _sample(model=kind if kind == "gat" else "sage")
+    in_f, hid, ncls = 37, 64, 5
+    torch.manual_seed(0)
+    feats = torch.randn(g.num_nodes(), in_f, device=gd.device)
+    if kind == "gat":
+        mdl = M.GATv2(3, in_f, hid, ncls, [2, 2, 1], F.elu, 0.0, 0.0, 0.2, True).to(gd.device)
+    else:
+        mdl = (M.SAGE if kind == "sage" else M.GCN)(in_f, hid, ncls, 3, F.relu, 0.0).to(gd.device)
+    nid = db[0].srcdata["_ID"].long()
+    y0 = mdl(db, feats[nid])
+    y0.sum().backward()
+    g0 = [p.grad.clone() for p in mdl.parameters()]
+    mdl.zero_grad()
+    y1 = mdl(db, F.pad(feats, (0, 3))[nid])
+    y1.sum().backward()
+    _close(y1, y0, what="padded logits")
+    for a, b in zip(mdl.parameters(), g0):
+        _close(a.grad, b, rtol=2e-5, what="padded grads")
