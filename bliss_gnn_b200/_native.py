@@ -75,16 +75,16 @@ class Counters(C.Structure):
     _fields_ = [("n_seeds", C.c_int32), ("n_cand", C.c_int32), ("n_sel", C.c_int32), ("n_src", C.c_int32),
                 ("n_heavy", C.c_int32), ("n_light", C.c_int32), ("take_all", C.c_int32), ("iters", C.c_int32),
                 ("e_in", C.c_int64), ("n_edges", C.c_int64), ("c", C.c_double), ("s_last", C.c_double),
-                ("queue", C.c_int32 * 4), ("error", C.c_int32), ("n_chunks", C.c_int32)]
+                ("queue", C.c_int32 * 8), ("error", C.c_int32), ("n_chunks", C.c_int32)]
 
 
 class Workspace(C.Structure):
     _fields_ = [("acc", C.c_void_p), ("first_pos", C.c_void_p), ("node_info", C.c_void_p),
                 ("sel_bits", C.c_void_p), ("cand_bits", C.c_void_p), ("keep_bits", C.c_void_p), ("cand", C.c_void_p), ("p_cand", C.c_void_p), ("sel", C.c_void_p),
-                ("row_list", C.c_void_p), ("pos_a", C.c_void_p), ("pos_d", C.c_void_p), ("row_a", C.c_void_p), ("row_d", C.c_void_p),
-                ("chunk_first", C.c_void_p), ("chunk_row", C.c_void_p), ("part_w", C.c_void_p), ("part_q", C.c_void_p),
+                ("row_a", C.c_void_p), ("row_d", C.c_void_p),
+                ("chunk_first", C.c_void_p), ("part_w", C.c_void_p), ("part_q", C.c_void_p),
                 ("row_w", C.c_void_p), ("row_q", C.c_void_p),
-                ("row_cnt", C.c_void_p), ("row_t", C.c_void_p), ("cap_seeds", C.c_int64),
+                ("row_cnt", C.c_void_p), ("part_cnt", C.c_void_p), ("part_t", C.c_void_p), ("cap_seeds", C.c_int64),
                 ("cap_sel", C.c_int64), ("ctr", C.c_void_p), ("n_seeds_dev", C.c_void_p), ("step_dev", C.c_void_p)]
 
 
@@ -109,7 +109,7 @@ PROTOTYPES = {
     "bliss_poisson_select": [_I32, _I32, _D, _U64, _U64, _U32, _P, _WP, _P],
     "bliss_select_topk": [_I32, _I32, _U64, _U64, _U32, _P, _P, _WP, _P],
     "bliss_philox_fill": [_U64, _U64, _U32, _P, _I64, _P, _P],
-    "bliss_block_count": [_GP, _P, _I32, _WP, _P],
+    "bliss_block_count": [_GP, _P, _I32, _P, _F, _I32, _WP, _P],
     "bliss_block_index": [_P, _I32, _WP, _BP, _P],
     "bliss_block_fill": [_GP, _P, _I32, _P, _F, _I32, _WP, _BP, _P],
     "bliss_block_finish": [_I32, _I32, _WP, _BP, _P],

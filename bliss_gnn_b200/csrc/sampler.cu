@@ -23,98 +23,59 @@ struct GraphView {
   int64_t num_nodes;
 };
 
-__device__ __forceinline__ int next_item(int* cursor, int n_items, int* s_item) {
-  __syncthreads();
-  if (threadIdx.x == 0) *s_item = atomicAdd(cursor, 1);
-  __syncthreads();
-  int it = *s_item;
-  return it < n_items ? it : -1;
-}
-
-// Every lane of the warp must call this (uniform control flow).
-__device__ __forceinline__ void append_candidate(bool first, int src, const bliss_workspace& ws) {
-  unsigned m = __ballot_sync(0xffffffffu, first);
-  if (m) {
-    int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane_id() == leader) base = atomicAdd(&ws.ctr->n_cand, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (first) ws.cand[base + __popc(m & ((1u << lane_id()) - 1u))] = src;
-  }
-}
-
 // ------------------------------------------------------------------------------------------
-// plan: register the seeds, order the rows heavy-first (by log2 degree bucket, so the longest
-// rows start first and the tail is short), store every row's CSC start / degree by processing
-// position (one independent load per item, no pointer chase), reset the counters.  One CTA.
+// plan: register the seeds (candidate slots 0..n_s-1, local id = seed rank, P = 1, selected bit),
+// store every row's CSC start / degree, cut every row into 256-edge warp-chunks (prefix array
+// chunk_first) and reset the layer's counters.  One CTA, four rows per thread and iteration, so
+// a layer of up to 4096 seeds is one round of independent loads and one CTA scan.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32_t* __restrict__ seeds,
                                                        int n_seeds, bliss_workspace ws) {
   __shared__ int s_scan[40];
   __shared__ unsigned long long s_e[32];
-  __shared__ int s_bucket[32], s_cursor[32];
   bliss_counters* ctr = ws.ctr;
   // sync-free chaining of layers: the true seed count may live on the device (the previous
   // layer's n_src); the host value is then only the capacity
   if (ws.n_seeds_dev) n_seeds = min(n_seeds, *ws.n_seeds_dev);
-  if (threadIdx.x < 32) s_bucket[threadIdx.x] = 0;
-  __syncthreads();
+  constexpr int IT = 4;
   unsigned long long e_in = 0;
-  for (int i = threadIdx.x; i < n_seeds; i += blockDim.x) {
-    const int s = seeds[i];
-    const long long a = g.indptr[s];
-    const long long d = g.indptr[s + 1] - a;
-    e_in += (unsigned long long)d;
-    ws.cand[i] = s;
-    ws.node_info[2 * s] = i;
-    ws.node_info[2 * s + 1] = __float_as_int(1.0f);
-    atomicOr(&ws.sel_bits[s >> 5], 1u << (s & 31));
-    if (d > BLISS_LIGHT_MAX) atomicAdd(&s_bucket[31 - __clz((int)min(d, (long long)INT_MAX))], 1);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {  // heaviest bucket first
-    int base = 0;
-    for (int bk = 31; bk >= 0; --bk) {
-      s_cursor[bk] = base;
-      base += s_bucket[bk];
+  int chunk_base = 0;
+  for (int b = 0; b < n_seeds; b += blockDim.x * IT) {
+    const int i0 = b + threadIdx.x * IT;
+    int s[IT], nch[IT], dd[IT], sum = 0;
+    long long a[IT];
+#pragma unroll
+    for (int u = 0; u < IT; ++u) s[u] = (i0 + u < n_seeds) ? seeds[i0 + u] : -1;
+#pragma unroll
+    for (int u = 0; u < IT; ++u) {
+      a[u] = 0;
+      long long d = 0;
+      if (s[u] >= 0) {
+        a[u] = g.indptr[s[u]];
+        d = g.indptr[s[u] + 1] - a[u];
+      }
+      dd[u] = (int)min(d, (long long)INT_MAX);
+      nch[u] = (s[u] >= 0) ? max(1, (dd[u] + BLISS_CHUNK - 1) / BLISS_CHUNK) : 0;
+      sum += nch[u];
+      e_in += (unsigned long long)d;
     }
-    s_scan[39] = base;
-  }
-  __syncthreads();
-  const int n_heavy = s_scan[39];
-  __syncthreads();
-  int light_base = 0, chunk_base = 0;
-  for (int base = 0; base < n_seeds; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    const bool valid = i < n_seeds;
-    long long a = 0, d = 0;
-    if (valid) {
-      const int s = seeds[i];
-      a = g.indptr[s];
-      d = g.indptr[s + 1] - a;
-    }
-    // chunk table of the probability passes: every row is cut into 256-edge warp-chunks
-    const int nch = valid ? max(1, (int)((min(d, (long long)INT_MAX) + BLISS_CHUNK - 1) / BLISS_CHUNK)) : 0;
     int tc;
-    const int pc = block_excl_scan(nch, s_scan, &tc);
-    if (valid) {
-      ws.row_a[i] = a;
-      ws.row_d[i] = (int)min(d, (long long)INT_MAX);
-      ws.chunk_first[i] = chunk_base + pc;
+    int pc = block_excl_scan(sum, s_scan, &tc);
+#pragma unroll
+    for (int u = 0; u < IT; ++u) {
+      if (s[u] >= 0) {
+        const int i = i0 + u;
+        ws.cand[i] = s[u];
+        *reinterpret_cast<int2*>(&ws.node_info[2 * s[u]]) = make_int2(i, __float_as_int(1.0f));
+        atomicOr(&ws.sel_bits[s[u] >> 5], 1u << (s[u] & 31));
+        ws.row_a[i] = a[u];
+        ws.row_d[i] = dd[u];
+        ws.row_cnt[i] = 0;
+        ws.chunk_first[i] = chunk_base + pc;
+        pc += nch[u];
+      }
     }
     chunk_base += tc;
-    const bool heavy = valid && d > BLISS_LIGHT_MAX;
-    int tl;
-    const int pl = block_excl_scan((valid && !heavy) ? 1 : 0, s_scan, &tl);
-    int pos = -1;
-    if (heavy) pos = atomicAdd(&s_cursor[31 - __clz((int)min(d, (long long)INT_MAX))], 1);
-    else if (valid) pos = n_seeds - 1 - (light_base + pl);
-    if (pos >= 0) {
-      ws.row_list[pos] = i;
-      ws.pos_a[pos] = a;
-      ws.pos_d[pos] = (int)min(d, (long long)INT_MAX);
-    }
-    light_base += tl;
   }
   e_in = block_sum(e_in, s_e);
   if (threadIdx.x == 0) {
@@ -122,15 +83,16 @@ __global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32
     ctr->n_cand = n_seeds;
     ctr->n_sel = 0;
     ctr->n_src = n_seeds;
-    ctr->n_heavy = n_heavy;
-    ctr->n_light = n_seeds - n_heavy;
+    ctr->n_heavy = 0;
+    ctr->n_light = 0;
     ctr->take_all = 0;
     ctr->iters = 0;
     ctr->e_in = (int64_t)e_in;
     ctr->n_edges = 0;
     ctr->c = 1.0;
     ctr->s_last = 0.0;
-    ctr->queue[0] = ctr->queue[1] = ctr->queue[2] = ctr->queue[3] = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ctr->queue[q] = 0;
     ctr->error = 0;
     ctr->n_chunks = chunk_base;
     ws.chunk_first[n_seeds] = chunk_base;
@@ -160,15 +122,16 @@ __device__ __forceinline__ void scatter_term(bool uniform, bool bitmap, float t,
   }
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// The three probability passes work on fixed 256-edge warp-chunks (one warp per chunk, 8 values
-// per lane in registers, no CTA barrier anywhere): perfectly balanced whatever the degree
-// distribution, no per-row chain of dependent round trips, no giant-row tail.  A row's sum is the
-// fixed-order fp64 sum of its chunks' partials, so the result is deterministic.
+// Every edge pass of a layer (three probability passes, kept-edge count, block fill) works on
+// fixed 256-edge warp-chunks of the frontier's rows: one warp per chunk, 8 values per lane in
+// registers, no CTA barrier inside a chunk — perfectly balanced whatever the degree distribution,
+// no per-row chain of dependent round trips, no giant-row tail.  A row quantity (Σw, Σq, kept
+// count, ΣW~) is the fixed-order sum of its chunks' partials, so results are deterministic.
 //   pass 1  partW[c] = Σ w                       (weights streamed once from HBM)
 //   pass 2  W_i = Σ_c partW ; q = η/n + (1-η) w / W_i ; partQ[c] = Σ q      (weights from L2)
 //   pass 3  Q_i = Σ_c partQ ; RED acc[src] += fx((q / Q_i)^2)              (indices from HBM)
+// CTAs pull groups of 8 consecutive chunks from a device-side queue (one atomic per group, issued
+// at the top of an iteration and consumed at its end, so its latency hides behind the chunk).
 struct ChunkRef {
   int row, k0, len;
   int64_t a;
@@ -192,18 +155,42 @@ __device__ __forceinline__ ChunkRef chunk_ref(const bliss_workspace& ws, int c, 
   r.len = min(BLISS_CHUNK, r.d - r.k0);
   return r;
 }
+// Σ of a row's chunk partials: lanes take the chunks round-robin, then a butterfly — a fixed
+// order (deterministic), every lane ends with the same bits.
 __device__ __forceinline__ float row_total(const double* __restrict__ part, int c_first, int c_last) {
   double t = 0.0;
-  for (int c = c_first; c < c_last; ++c) t += part[c];   // fixed order, every lane the same value
-  return __double2float_rn(t);
+  for (int c = c_first + lane_id(); c < c_last; c += 32) t += part[c];
+  return __double2float_rn(warp_sum(t));
 }
 
-__global__ void __launch_bounds__(256) k_prob_pass1(const float* __restrict__ W, bliss_workspace ws) {
+// for (ChunkLoop q(...); q.more(); q.next()) { const int c = q.chunk(); if (c < n_chunks) ... }
+struct ChunkLoop {
+  int* cursor;
+  int* s_next;   // 2 ints of shared memory
+  int n_chunks, item, iter;
+  __device__ __forceinline__ ChunkLoop(int* cursor_, int* s_next_, int n_chunks_)
+      : cursor(cursor_), s_next(s_next_), n_chunks(n_chunks_), item(blockIdx.x), iter(0) {}
+  __device__ __forceinline__ bool more() {
+    if (item * BLISS_WARPS >= n_chunks) return false;   // CTA-uniform
+    if (threadIdx.x == 0) s_next[iter & 1] = gridDim.x + atomicAdd(cursor, 1);
+    return true;
+  }
+  __device__ __forceinline__ int chunk() const { return item * BLISS_WARPS + warp_id(); }
+  __device__ __forceinline__ void next() {
+    __syncthreads();
+    item = s_next[iter & 1];
+    ++iter;
+  }
+};
+
+__global__ void __launch_bounds__(BLISS_CTA, 6) k_prob_pass1(const float* __restrict__ W, bliss_workspace ws) {
+  __shared__ int s_next[2];
   const int lane = lane_id();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n_seeds = ws.ctr->n_seeds;
   const int n_chunks = ws.ctr->n_chunks;
-  for (int c = warp; c < n_chunks; c += nwarps) {
+  for (ChunkLoop q(&ws.ctr->queue[0], s_next, n_chunks); q.more(); q.next()) {
+    const int c = q.chunk();
+    if (c >= n_chunks) continue;
     const ChunkRef r = chunk_ref(ws, c, n_seeds);
     const float* __restrict__ wr = W + r.a + r.k0;
     double acc = 0.0;
@@ -217,13 +204,15 @@ __global__ void __launch_bounds__(256) k_prob_pass1(const float* __restrict__ W,
   }
 }
 
-__global__ void __launch_bounds__(256) k_prob_pass2(const float* __restrict__ W, float eta, float one_minus_eta,
-                                                   bliss_workspace ws) {
+__global__ void __launch_bounds__(BLISS_CTA, 6) k_prob_pass2(const float* __restrict__ W, float eta, float one_minus_eta,
+                                                         bliss_workspace ws) {
+  __shared__ int s_next[2];
   const int lane = lane_id();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n_seeds = ws.ctr->n_seeds;
   const int n_chunks = ws.ctr->n_chunks;
-  for (int c = warp; c < n_chunks; c += nwarps) {
+  for (ChunkLoop q(&ws.ctr->queue[1], s_next, n_chunks); q.more(); q.next()) {
+    const int c = q.chunk();
+    if (c >= n_chunks) continue;
     const ChunkRef r = chunk_ref(ws, c, n_seeds);
     const float* __restrict__ wr = W + r.a + r.k0;
     float v[BLISS_CHUNK / 32];
@@ -248,17 +237,19 @@ __global__ void __launch_bounds__(256) k_prob_pass2(const float* __restrict__ W,
   }
 }
 
-__global__ void __launch_bounds__(256) k_prob_pass3(GraphView g, const float* __restrict__ W, float eta,
-                                                   float one_minus_eta, int mode_flags, bliss_workspace ws) {
+__global__ void __launch_bounds__(BLISS_CTA, 5) k_prob_pass3(GraphView g, const float* __restrict__ W, float eta,
+                                                         float one_minus_eta, int mode_flags, bliss_workspace ws) {
+  __shared__ int s_next[2];
   const int mode = mode_flags & 1;
   const bool uniform = (mode_flags & BLISS_MODE_UNIFORM);
   const bool bitmap = (mode_flags & BLISS_COLLECT_BITMAP);
   const int lane = lane_id();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n_seeds = ws.ctr->n_seeds;
   const int n_chunks = ws.ctr->n_chunks;
   const double fx_scale = (double)(1ull << fx_bits_for(ws.ctr->n_seeds));
-  for (int c = warp; c < n_chunks; c += nwarps) {
+  for (ChunkLoop q(&ws.ctr->queue[2], s_next, n_chunks); q.more(); q.next()) {
+    const int c = q.chunk();
+    if (c >= n_chunks) continue;
     const ChunkRef r = chunk_ref(ws, c, n_seeds);
     const float* __restrict__ wr = W + r.a + r.k0;
     const int32_t* __restrict__ idx = g.indices + r.a + r.k0;
@@ -284,8 +275,8 @@ __global__ void __launch_bounds__(256) k_prob_pass3(GraphView g, const float* __
         float t = 0.0f;
         if (uniform) {
         } else if (mode == BLISS_MODE_BANDIT) {
-          const float q = __fdiv_rn(edge_q(v[j], row_w, eta_n, one_minus_eta), row_q);
-          t = __fmul_rn(q, q);
+          const float qn = __fdiv_rn(edge_q(v[j], row_w, eta_n, one_minus_eta), row_q);
+          t = __fmul_rn(qn, qn);
         } else {
           t = __fmul_rn(v[j], v[j]);
         }
@@ -298,30 +289,51 @@ __global__ void __launch_bounds__(256) k_prob_pass3(GraphView g, const float* __
 // Candidate list = seeds (already listed by the plan) ++ every non-seed node that received a
 // scatter.  Dense mode: a node is a candidate iff its accumulator is non-zero (one coalesced scan
 // of |V| x 8 B).  Bitmap mode: iterate the set bits of cand_bits (|V| / 8 B) and clear them.
+// A CTA handles 4 words (128 nodes) per warp and appends its candidates with ONE atomic on the
+// shared counter (thousands of same-address atomics would serialise in L2).
+#define BLISS_COLLECT_WORDS 4
 __global__ void __launch_bounds__(256) k_collect_candidates(int64_t num_nodes, int bitmap, bliss_workspace ws) {
+  __shared__ int s_scan[40];
+  __shared__ int s_base;
   const int lane = lane_id();
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n_words = (num_nodes + 31) >> 5;
-  for (int64_t w = warp; w < n_words; w += nwarps) {
-    const int64_t v = (w << 5) + lane;
-    bool hit;
-    if (bitmap) {
-      const unsigned word = ws.cand_bits[w];  // warp-uniform
-      if (word == 0u) continue;
-      __syncwarp();
-      if (lane == 0) ws.cand_bits[w] = 0u;
-      hit = (word >> lane) & 1u;
-    } else {
-      hit = v < num_nodes && ws.acc[v] != 0ull;
+  const int64_t words_per_cta = (int64_t)BLISS_COLLECT_WORDS * (blockDim.x >> 5);
+  for (int64_t w0 = blockIdx.x * words_per_cta; w0 < n_words; w0 += gridDim.x * words_per_cta) {
+    unsigned m[BLISS_COLLECT_WORDS];
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < BLISS_COLLECT_WORDS; ++u) {
+      const int64_t w = w0 + (int64_t)warp_id() * BLISS_COLLECT_WORDS + u;
+      const int64_t v = (w << 5) + lane;
+      bool hit = false;
+      if (w < n_words) {
+        if (bitmap) {
+          const unsigned word = ws.cand_bits[w];  // warp-uniform
+          __syncwarp();
+          if (word != 0u && lane == 0) ws.cand_bits[w] = 0u;
+          hit = (word >> lane) & 1u;
+        } else {
+          hit = v < num_nodes && ws.acc[v] != 0ull;
+        }
+      }
+      const bool is_new = hit && ws.node_info[2 * v] < 0;  // seeds are listed already
+      m[u] = __ballot_sync(0xffffffffu, is_new);
+      cnt += __popc(m[u]);
     }
-    const bool is_new = hit && ws.node_info[2 * v] < 0;  // seeds are listed already
-    const unsigned m = __ballot_sync(0xffffffffu, is_new);
-    if (m == 0u) continue;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&ws.ctr->n_cand, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (is_new) ws.cand[base + __popc(m & ((1u << lane) - 1u))] = (int)v;
+    int tot;
+    int off = block_excl_scan(lane == 0 ? cnt : 0, s_scan, &tot);   // lane 0 of each warp carries the warp's count
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (tot == 0) continue;   // CTA-uniform
+    if (threadIdx.x == 0) s_base = atomicAdd(&ws.ctr->n_cand, tot);
+    __syncthreads();
+    int pos = s_base + off;
+#pragma unroll
+    for (int u = 0; u < BLISS_COLLECT_WORDS; ++u) {
+      const int64_t v = ((w0 + (int64_t)warp_id() * BLISS_COLLECT_WORDS + u) << 5) + lane;
+      if ((m[u] >> lane) & 1u) ws.cand[pos + __popc(m[u] & ((1u << lane) - 1u))] = (int)v;
+      pos += __popc(m[u]);
+    }
+    __syncthreads();   // s_base is rewritten by the next round
   }
 }
 
@@ -471,23 +483,44 @@ __global__ void __launch_bounds__(1024, 1) k_scale_select(int n_seeds, int fanou
     ctr->s_last = S;
     ctr->take_all = take_all ? 1 : 0;
   }
-  // selection: u < P, seeds forced to P = 1 (:403-406, :422-424)
+  // selection: u < P, seeds forced to P = 1 (:403-406, :422-424).  The register-resident candidates
+  // of a CTA are appended with ONE atomic on the shared counter (flags -> CTA scan -> base).
   const float cf = (float)c;
+  unsigned selmask = 0;
 #pragma unroll
   for (int r = 0; r < BLISS_SCALE_NREG; ++r) {
-    if (r * nthreads < n_cand) {  // uniform across the cluster
-      const int j = gtid + r * nthreads;
-      bool sel = false;
-      int nid = 0;
-      if (j >= n_seeds && j < n_cand) {
-        nid = ws.cand[j];
-        const float P = take_all ? 1.0f : fminf(__fmul_rn(preg[r], cf), 1.0f);
-        const float u = u_inject ? u_inject[nid] : philox_uniform(seed, step, layer, (unsigned)nid);
-        sel = u < P;
-        ws.node_info[2 * nid] = sel ? -2 : -1;
-        ws.node_info[2 * nid + 1] = __float_as_int(P);
+    const int j = gtid + r * nthreads;
+    if (j >= n_seeds && j < n_cand) {
+      const int nid = ws.cand[j];
+      const float P = take_all ? 1.0f : fminf(__fmul_rn(preg[r], cf), 1.0f);
+      const float u = u_inject ? u_inject[nid] : philox_uniform(seed, step, layer, (unsigned)nid);
+      const bool sel = u < P;
+      *reinterpret_cast<int2*>(&ws.node_info[2 * nid]) = make_int2(sel ? -2 : -1, __float_as_int(P));
+      if (sel) selmask |= 1u << r;
+    }
+  }
+  {
+    __shared__ int s_scan[40];
+    __shared__ int s_base;
+    int tot;
+    int off = block_excl_scan(__popc(selmask), s_scan, &tot);
+    if (threadIdx.x == 0 && tot > 0) s_base = atomicAdd(&ctr->n_sel, tot);
+    __syncthreads();
+    if (selmask) {
+      int slot = s_base + off;
+#pragma unroll
+      for (int r = 0; r < BLISS_SCALE_NREG; ++r) {
+        if ((selmask >> r) & 1u) {
+          if (slot < ws.cap_sel) {
+            const int nid = ws.cand[gtid + r * nthreads];   // L1/L2 hit: read a moment ago
+            ws.sel[slot] = nid;
+            atomicOr(&ws.sel_bits[nid >> 5], 1u << (nid & 31));
+          } else {
+            ctr->error = BLISS_ERR_SEL_CAPACITY;
+          }
+          ++slot;
+        }
       }
-      push_selected(sel, nid, ws);
     }
   }
   const int rest0 = BLISS_SCALE_NREG * nthreads;
@@ -638,116 +671,81 @@ __global__ void k_philox_fill(unsigned long long seed, unsigned long long step, 
 }
 
 // ------------------------------------------------------------------------------------------
-// (3a) count kept in-edges per seed (source selected) and record the first occurrence of every
-//      selected non-seed source: key = (row+1, position in row).   bandit_sampler.py:289-298
+// (3a) kept in-edges (source selected) of every 256-edge chunk of the frontier: keep bits, kept
+//      count and — bandit mode — the chunk's partial of ΣW~ (W~ = q_ij / P_src); first occurrence
+//      of every selected non-seed source: key = (row+1, position in row).  bandit_sampler.py:289-314
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void note_first(int src, unsigned long long key, const bliss_workspace& ws) {
-  if (ws.node_info[2 * src] < 0) {  // selected non-seed (-2); seeds hold their rank >= 0
+struct FillCtx {
+  GraphView g;
+  const float* __restrict__ W;
+  float eta, one_minus_eta;
+  int mode;
+};
+
+__device__ __forceinline__ void note_first(int src, int local, unsigned long long key, const bliss_workspace& ws) {
+  if (local < 0) {  // selected non-seed (-2); seeds hold their rank >= 0
     unsigned long long cur = __ldcg((const unsigned long long*)&ws.first_pos[src]);
     if (key < cur) atomicMin((unsigned long long*)&ws.first_pos[src], key);
   }
 }
 
-// One keep-bit per CSC edge position.  A warp handles one globally aligned 32-position word at a
-// time (perfectly coalesced index loads); interior words are plain stores, the first / last word
-// of a row is shared with the neighbouring CSC columns and is updated with and/or atomics.
-// Kept edges are sparse in a row (~8 % of the bits), so the dependent random accesses of
-// note_first (node_info -> first_pos -> atomicMin) are not done inside the word loop, where only
-// 2-3 lanes per warp would be active: the kept (position, source) pairs go to a shared-memory
-// list and are processed densely afterwards, one pair per thread.
-#define BLISS_LIST_CAP 2048
-__global__ void __launch_bounds__(BLISS_CTA) k_block_count(GraphView g, const int32_t* __restrict__ seeds,
-                                                          bliss_workspace ws) {
-  __shared__ int s_red[32];
+// Kept edges are sparse in a chunk (~8 % of the bits at Reddit fan-outs), so the dependent random
+// accesses (node_info -> first_pos -> atomicMin, weight -> q -> W~) are not done inside the word
+// loop, where only 2-3 lanes per warp would be active: the kept positions go to a per-warp
+// shared-memory list and are processed densely afterwards, one kept edge per lane.
+__global__ void __launch_bounds__(BLISS_CTA, 6) k_block_count(FillCtx c, bliss_workspace ws) {
   __shared__ int s_next[2];
-  __shared__ int s_k[BLISS_LIST_CAP], s_src[BLISS_LIST_CAP];
-  __shared__ int s_cnt;
+  __shared__ unsigned char s_k[BLISS_WARPS][BLISS_CHUNK];   // chunk-relative positions of the kept edges
   bliss_counters* ctr = ws.ctr;
-  const int n_seeds = ctr->n_seeds, n_heavy = ctr->n_heavy, n_light = ctr->n_light;
-  const int n_items = n_heavy + (n_light + BLISS_WARPS - 1) / BLISS_WARPS;
-  const int tid = threadIdx.x, lane = lane_id();
-  constexpr int LIGHT_CAP = BLISS_LIST_CAP / BLISS_WARPS;   // 256 = BLISS_LIGHT_MAX
-  // same longest-first dynamic queue with two-item look-ahead as k_frontier_prob
-  int item = blockIdx.x, nxt = gridDim.x + blockIdx.x, iter = 0;
-  for (; item < n_items; ++iter) {
-    if (tid == 0) {
-      s_next[iter & 1] = 2 * gridDim.x + atomicAdd(&ctr->queue[1], 1);
-      s_cnt = 0;
+  const int n_seeds = ctr->n_seeds, n_chunks = ctr->n_chunks;
+  const int lane = lane_id();
+  const bool bandit = (c.mode == BLISS_MODE_BANDIT);
+  unsigned char* lk = s_k[warp_id()];
+  for (ChunkLoop q(&ctr->queue[3], s_next, n_chunks); q.more(); q.next()) {
+    const int ch = q.chunk();
+    if (ch >= n_chunks) continue;
+    const ChunkRef r = chunk_ref(ws, ch, n_seeds);
+    const int32_t* __restrict__ idx = c.g.indices + r.a + r.k0;
+    int src[BLISS_CHUNK / 32];
+#pragma unroll
+    for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
+      const int k = lane + 32 * j;
+      src[j] = (k < r.len) ? __ldg(idx + k) : -1;
     }
-    __syncthreads();
-    const bool heavy = item < n_heavy;
-    const int li = heavy ? 0 : (item - n_heavy) * BLISS_WARPS + warp_id();
-    if (heavy || li < n_light) {
-      const int pos = heavy ? item : n_seeds - 1 - li;
-      const int row = ws.row_list[pos];
-      const int64_t a = ws.pos_a[pos];
-      const int64_t end = a + ws.pos_d[pos];
-      const unsigned long long key_hi = (unsigned long long)(row + 1) << 32;
-      const int64_t w_lo = a >> 5, w_hi = (end + 31) >> 5;   // [w_lo, w_hi)
-      int cnt = 0;
-      const int wstep = heavy ? BLISS_WARPS : 1;
-      int* lk = heavy ? s_k : s_k + warp_id() * LIGHT_CAP;
-      int* ls = heavy ? s_src : s_src + warp_id() * LIGHT_CAP;
-      const int cap = heavy ? BLISS_LIST_CAP : LIGHT_CAP;
-      constexpr int U = 4;   // words in flight per warp: the index loads and bitmap tests are independent
-      for (int64_t w0 = w_lo + (heavy ? warp_id() : 0); w0 < w_hi; w0 += (int64_t)U * wstep) {
-        int srcv[U];
-        bool inr[U], kp[U];
+    int cnt = 0;
+    unsigned myword = 0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int64_t p = ((w0 + (int64_t)u * wstep) << 5) + lane;
-          inr[u] = p >= a && p < end;      // false for words beyond the row
-          srcv[u] = inr[u] ? __ldg(g.indices + p) : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) kp[u] = inr[u] && test_bit(ws.sel_bits, srcv[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int64_t w = w0 + (int64_t)u * wstep;
-          if (w >= w_hi) break;            // warp-uniform
-          const int64_t p = (w << 5) + lane;
-          const int src = srcv[u];
-          const bool keep = kp[u];
-          const unsigned bits = __ballot_sync(0xffffffffu, keep);
-          const unsigned range = __ballot_sync(0xffffffffu, inr[u]);
-          int off = 0;
-          if (lane == 0) {
-            if (range == 0xffffffffu) {
-              ws.keep_bits[w] = bits;
-            } else {  // boundary word, shared with the neighbouring column(s)
-              atomicAnd(&ws.keep_bits[w], ~range);
-              atomicOr(&ws.keep_bits[w], bits);
-            }
-            if (bits) off = heavy ? atomicAdd(&s_cnt, __popc(bits)) : cnt;
-          }
-          off = __shfl_sync(0xffffffffu, off, 0);
-          if (keep) {
-            const int j = off + __popc(bits & ((1u << lane) - 1u));
-            if (j < cap) {
-              lk[j] = (int)(p - a);
-              ls[j] = src;
-            } else {
-              note_first(src, key_hi | (unsigned)(p - a), ws);   // list full (hub row): the slow inline path
-            }
-          }
-          cnt += __popc(bits);
-        }
-      }
-      if (heavy) {
-        cnt = block_sum(lane == 0 ? cnt : 0, s_red);
-        if (tid == 0) ws.row_cnt[row] = cnt;
-        const int n = min(cnt, cap);
-        for (int j = tid; j < n; j += BLISS_CTA) note_first(ls[j], key_hi | (unsigned)lk[j], ws);
-      } else {
-        if (lane == 0) ws.row_cnt[row] = cnt;
-        __syncwarp();
-        const int n = min(cnt, cap);
-        for (int j = lane; j < n; j += 32) note_first(ls[j], key_hi | (unsigned)lk[j], ws);
+    for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
+      const bool keep = src[j] >= 0 && test_bit(ws.sel_bits, src[j]);
+      const unsigned bits = __ballot_sync(0xffffffffu, keep);
+      if (keep) lk[cnt + __popc(bits & ((1u << lane) - 1u))] = (unsigned char)(lane + 32 * j);
+      if (lane == j) myword = bits;
+      cnt += __popc(bits);
+    }
+    if (lane < BLISS_CHUNK / 32) ws.keep_bits[(int64_t)ch * (BLISS_CHUNK / 32) + lane] = myword;
+    __syncwarp();
+    double t = 0.0;
+    if (cnt) {
+      const unsigned long long key_hi = (unsigned long long)(r.row + 1) << 32;
+      const float row_w = (bandit && r.d > 0) ? ws.row_w[r.row] : 1.0f;
+      const float eta_n = __fdiv_rn(c.eta, (float)r.d);
+      for (int j = lane; j < cnt; j += 32) {
+        const int k = lk[j];
+        const int sj = __ldg(idx + k);
+        const int2 info = *reinterpret_cast<const int2*>(&ws.node_info[2 * sj]);
+        note_first(sj, info.x, key_hi | (unsigned)(r.k0 + k), ws);
+        if (bandit)   // also with importance_sampling=0: q_ij is still built from W (:354-358)
+          t += (double)__fdiv_rn(edge_q(__ldg(c.W + r.a + r.k0 + k), row_w, eta_n, c.one_minus_eta),
+                                 __int_as_float(info.y));
       }
     }
-    __syncthreads();
-    item = nxt;
-    nxt = s_next[iter & 1];
+    if (bandit) t = warp_sum(t);
+    if (lane == 0) {
+      ws.part_cnt[ch] = cnt;
+      if (bandit) ws.part_t[ch] = t;
+      if (cnt) atomicAdd(&ws.row_cnt[r.row], cnt);
+    }
+    __syncwarp();   // the list is rewritten by the warp's next chunk
   }
 }
 
@@ -766,7 +764,7 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
   const int n_sel = min(ctr->n_sel, (int)ws.cap_sel);
   if (blockIdx.x == 0) {
     int base = 0, hbase = 0;
-    constexpr int IT = 4;   // rows per thread and iteration: 4x fewer CTA-wide scans
+    constexpr int IT = 8;   // rows per thread and iteration: few CTA-wide scans
     for (int b = 0; b < n_seeds; b += blockDim.x * IT) {
       const int i0 = b + threadIdx.x * IT;
       int v[IT], hv[IT], vsum = 0, hsum = 0;
@@ -818,6 +816,7 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
   // ranking: 4 adjacent lanes share one key and each counts a quarter of every tile, so a CTA
   // handles 64 keys and 4x more CTAs take part (the counting loop is the serial part)
   constexpr int SUB = 4;
+  constexpr int PER_T = BLISS_RANK_TILE / 256;
   const int keys_per_cta = blockDim.x / SUB;
   const int n_chunks = (n_sel + keys_per_cta - 1) / keys_per_cta;
   const int sub = threadIdx.x & (SUB - 1);
@@ -830,7 +829,18 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
     for (int t0 = 0; t0 < n_sel; t0 += BLISS_RANK_TILE) {
       const int tn = min(BLISS_RANK_TILE, n_sel - t0);
       __syncthreads();
-      for (int t = threadIdx.x; t < tn; t += blockDim.x) s_keys[t] = ws.first_pos[ws.sel[t0 + t]];
+      // the tile's keys are two dependent gathers (sel -> first_pos): all 8 per thread in flight together
+      int tn_id[PER_T];
+      unsigned long long tk[PER_T];
+#pragma unroll
+      for (int u = 0; u < PER_T; ++u) {
+        const int t = threadIdx.x + u * 256;
+        tn_id[u] = (t < tn) ? ws.sel[t0 + t] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < PER_T; ++u) tk[u] = (tn_id[u] >= 0) ? ws.first_pos[tn_id[u]] : ~0ull;
+#pragma unroll
+      for (int u = 0; u < PER_T; ++u) s_keys[threadIdx.x + u * 256] = tk[u];
       __syncthreads();
       if (valid) {
 #pragma unroll 8
@@ -852,151 +862,68 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// (3c) fill: ordered compaction of the kept in-edges of every seed into the block CSR with
-//      relabelled sources, q_ij, W~ = q_ij / P_src and Σ W~ per row.   bandit_sampler.py:306-316
+// (3c) fill: ordered compaction of the kept in-edges into the block CSR, chunk by chunk — a
+//      chunk's first slot is the row's start plus the kept counts of the row's earlier chunks —
+//      with relabelled sources, q_ij and the final block weight
+//      W~ = (q_ij / P_src) * d / ΣW~  (bandit_sampler.py:306-320)  or  (w / P_src) * d  (ladies_sampler.py:97).
 // ------------------------------------------------------------------------------------------
-struct FillCtx {
-  GraphView g;
-  const float* __restrict__ W;
-  float eta, one_minus_eta;
-  int mode;
-};
-
-__device__ __forceinline__ double fill_edge(const FillCtx& c, const bliss_workspace& ws,
-                                            const bliss_block_out& out, int64_t pos, int src, int row,
-                                            int slot, float row_w, float eta_n) {
-  const int2 info = *reinterpret_cast<const int2*>(&ws.node_info[2 * src]);
-  const float P = __int_as_float(info.y);
-  float base;
-  if (c.mode == BLISS_MODE_BANDIT)  // also with importance_sampling=0: q_ij is still W (:354-358)
-    base = edge_q(__ldg(c.W + pos), row_w, eta_n, c.one_minus_eta);
-  else
-    base = __ldg(c.W + pos);
-  const float wt = __fdiv_rn(base, P);
-  out.edge_src[slot] = info.x;
-  out.edge_dst[slot] = row;
-  out.csc_pos[slot] = pos;
-  if (out.eid) out.eid[slot] = c.g.eid ? c.g.eid[pos] : (int32_t)pos;
-  if (out.q_ij) out.q_ij[slot] = base;
-  out.edge_w[slot] = wt;
-  if (out.out_deg) atomicAdd(&out.out_deg[info.x], 1);
-  return (double)wt;
-}
-
-__device__ __forceinline__ unsigned keep_word(const bliss_workspace& ws, int64_t w, int64_t a, int64_t end) {
-  // bits of word w that belong to the row [a, end)
-  unsigned bits = ws.keep_bits[w];
-  const int64_t p0 = w << 5;
-  if (p0 < a) bits &= 0xffffffffu << (int)(a - p0);
-  if (p0 + 32 > end) bits &= 0xffffffffu >> (int)(p0 + 32 - end);
-  return bits;
-}
-
-// Rescale this row's block weights once its sum is known:  W~ *= d / ΣW~  (bandit_sampler.py:316-320)
-// or  W~ *= d  (ladies_sampler.py:97).  The slots were written by this very group of threads.
-__device__ __forceinline__ void rescale_row(const FillCtx& c, const bliss_block_out& out, int base, int cnt,
-                                            double row_t, int t, int nt) {
-  const float d = (float)cnt;
-  const float f = (c.mode == BLISS_MODE_LADIES) ? d : __fdiv_rn(d, __double2float_rn(row_t));
-  for (int k = t; k < cnt; k += nt) out.edge_w[base + k] = __fmul_rn(out.edge_w[base + k], f);
-}
-
-__global__ void __launch_bounds__(BLISS_CTA) k_block_fill(FillCtx c, const int32_t* __restrict__ seeds,
-                                                         bliss_workspace ws, bliss_block_out out) {
-  __shared__ double s_red[32];
-  __shared__ int s_scan[40];
+__global__ void __launch_bounds__(BLISS_CTA, 6) k_block_fill(FillCtx c, bliss_workspace ws, bliss_block_out out) {
   __shared__ int s_next[2];
-  __shared__ int s_k[BLISS_LIST_CAP];   // row-relative positions of the kept edges, in block order
+  __shared__ unsigned char s_k[BLISS_WARPS][BLISS_CHUNK];
   bliss_counters* ctr = ws.ctr;
-  const int n_seeds = ctr->n_seeds, n_heavy = ctr->n_heavy, n_light = ctr->n_light;
-  const int n_items = n_heavy + (n_light + BLISS_WARPS - 1) / BLISS_WARPS;
-  const int tid = threadIdx.x, lane = lane_id();
-  const bool needs_row_w = (c.mode != BLISS_MODE_LADIES);
-  constexpr int LIGHT_CAP = BLISS_LIST_CAP / BLISS_WARPS;
+  const int n_seeds = ctr->n_seeds, n_chunks = ctr->n_chunks;
+  const int lane = lane_id();
+  const bool bandit = (c.mode == BLISS_MODE_BANDIT);
   if (ctr->n_edges > out.cap_edges || ctr->error) return;  // capacity error already flagged by the index kernel
-  int item = blockIdx.x, nxt = gridDim.x + blockIdx.x, iter = 0;
-  for (; item < n_items; ++iter) {
-    if (tid == 0) s_next[iter & 1] = 2 * gridDim.x + atomicAdd(&ctr->queue[2], 1);
-    if (item < n_heavy) {
-      const int row = ws.row_list[item];
-      const int64_t a = ws.pos_a[item];
-      const int d = ws.pos_d[item];
-      const int64_t end = a + d;
-      const float row_w = needs_row_w ? ws.row_w[row] : 1.0f;
-      const float eta_n = __fdiv_rn(c.eta, (float)d);
-      const int row_base = out.indptr[row];
-      // every warp owns a contiguous run of the row's keep-words: popcount the run, one scan of the
-      // 8 run totals, ordered compaction of the kept positions into shared memory, then one kept
-      // edge per thread (all random accesses independent and in flight together)
-      const int64_t w_lo = a >> 5, w_hi = (end + 31) >> 5;
-      const int64_t run = (w_hi - w_lo + BLISS_WARPS - 1) / BLISS_WARPS;
-      const int64_t r_lo = min(w_hi, w_lo + warp_id() * run), r_hi = min(w_hi, r_lo + run);
-      int cnt = 0;
-      for (int64_t w = r_lo + lane; w < r_hi; w += 32) cnt += __popc(keep_word(ws, w, a, end));
-      cnt = warp_sum(cnt);
-      __syncthreads();
-      if (lane == 0) s_scan[warp_id()] = cnt;
-      __syncthreads();
-      int rel0 = 0, total = 0;
-      for (int wv = 0; wv < BLISS_WARPS; ++wv) {
-        if (wv < warp_id()) rel0 += s_scan[wv];
-        total += s_scan[wv];
-      }
-      double acc = 0.0;
-      for (int b0 = 0; b0 < total; b0 += BLISS_LIST_CAP) {   // one pass unless a hub row keeps > 2048 edges
-        int rel = rel0;
-        for (int64_t w = r_lo; w < r_hi; ++w) {
-          const unsigned bits = keep_word(ws, w, a, end);
-          if ((bits >> lane) & 1u) {
-            const int j = rel + __popc(bits & ((1u << lane) - 1u)) - b0;
-            if (j >= 0 && j < BLISS_LIST_CAP) s_k[j] = (int)((w << 5) + lane - a);
-          }
-          rel += __popc(bits);
-        }
-        __syncthreads();
-        const int n = min(BLISS_LIST_CAP, total - b0);
-        for (int j = tid; j < n; j += BLISS_CTA) {
-          const int64_t p = a + s_k[j];
-          acc += fill_edge(c, ws, out, p, __ldg(c.g.indices + p), row, row_base + b0 + j, row_w, eta_n);
-        }
-        __syncthreads();
-      }
-      acc = block_sum(acc, s_red);   // also orders the edge_w writes before the rescale below
-      if (tid == 0) ws.row_t[row] = acc;
-      rescale_row(c, out, row_base, total, acc, tid, BLISS_CTA);
-    } else {
-      const int li = (item - n_heavy) * BLISS_WARPS + warp_id();
-      if (li < n_light) {
-        const int pos = n_seeds - 1 - li;
-        const int row = ws.row_list[pos];
-        const int64_t a = ws.pos_a[pos];
-        const int d = ws.pos_d[pos];
-        const int64_t end = a + d;
-        const float row_w = (needs_row_w && d > 0) ? ws.row_w[row] : 1.0f;
-        const float eta_n = __fdiv_rn(c.eta, (float)d);
-        const int row_base = out.indptr[row];
-        int* lk = s_k + warp_id() * LIGHT_CAP;   // d <= 256 = LIGHT_CAP
-        int cnt = 0;
-        for (int64_t w = a >> 5; w < ((end + 31) >> 5); ++w) {
-          const unsigned bits = keep_word(ws, w, a, end);
-          if ((bits >> lane) & 1u) lk[cnt + __popc(bits & ((1u << lane) - 1u))] = (int)((w << 5) + lane - a);
-          cnt += __popc(bits);
-        }
-        __syncwarp();
-        double acc = 0.0;
-        for (int j = lane; j < cnt; j += 32) {
-          const int64_t p = a + lk[j];
-          acc += fill_edge(c, ws, out, p, __ldg(c.g.indices + p), row, row_base + j, row_w, eta_n);
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) ws.row_t[row] = acc;
-        __syncwarp();
-        rescale_row(c, out, row_base, cnt, acc, lane, 32);
-      }
+  unsigned char* lk = s_k[warp_id()];
+  for (ChunkLoop q(&ctr->queue[4], s_next, n_chunks); q.more(); q.next()) {
+    const int ch = q.chunk();
+    if (ch >= n_chunks) continue;
+    const int cnt = ws.part_cnt[ch];
+    if (cnt == 0) continue;   // warp-uniform
+    const ChunkRef r = chunk_ref(ws, ch, n_seeds);
+    // kept edges of the row before this chunk, of the whole row, and the row's ΣW~
+    int pre = 0, tot = 0;
+    double t = 0.0;
+    for (int cc = r.c_first + lane; cc < r.c_last; cc += 32) {
+      const int n = ws.part_cnt[cc];
+      tot += n;
+      if (cc < ch) pre += n;
+      if (bandit) t += ws.part_t[cc];
     }
-    __syncthreads();
-    item = nxt;
-    nxt = s_next[iter & 1];
+    pre = warp_sum(pre);
+    tot = warp_sum(tot);
+    float f = (float)tot;                                   // ladies: W~ *= d
+    if (bandit) f = __fdiv_rn(f, __double2float_rn(warp_sum(t)));   // bandit: W~ *= d / ΣW~
+    const unsigned myword = (lane < BLISS_CHUNK / 32) ? ws.keep_bits[(int64_t)ch * (BLISS_CHUNK / 32) + lane] : 0u;
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
+      const unsigned bits = __shfl_sync(0xffffffffu, myword, j);
+      if ((bits >> lane) & 1u) lk[n + __popc(bits & ((1u << lane) - 1u))] = (unsigned char)(lane + 32 * j);
+      n += __popc(bits);
+    }
+    __syncwarp();
+    const float row_w = (bandit && r.d > 0) ? ws.row_w[r.row] : 1.0f;
+    const float eta_n = __fdiv_rn(c.eta, (float)r.d);
+    const int base = out.indptr[r.row] + pre;
+    for (int j = lane; j < cnt; j += 32) {
+      const int64_t p = r.a + r.k0 + lk[j];
+      const int src = __ldg(c.g.indices + p);
+      const int2 info = *reinterpret_cast<const int2*>(&ws.node_info[2 * src]);
+      const float wv = __ldg(c.W + p);
+      const float qv = bandit ? edge_q(wv, row_w, eta_n, c.one_minus_eta) : wv;
+      const float wt = __fmul_rn(__fdiv_rn(qv, __int_as_float(info.y)), f);
+      const int slot = base + j;
+      out.edge_src[slot] = info.x;
+      out.edge_dst[slot] = r.row;
+      out.csc_pos[slot] = p;
+      if (out.eid) out.eid[slot] = c.g.eid ? c.g.eid[p] : (int32_t)p;
+      if (out.q_ij) out.q_ij[slot] = qv;
+      out.edge_w[slot] = wt;
+      if (out.out_deg) atomicAdd(&out.out_deg[info.x], 1);
+    }
+    __syncwarp();
   }
 }
 
@@ -1045,30 +972,37 @@ __global__ void k_t_count(const int32_t* __restrict__ edge_src, int64_t n_edges,
 // cnt_cursor holds the per-source counts on entry and the fill cursors (= row starts) on exit.
 __global__ void __launch_bounds__(1024) k_t_scan(int32_t* cnt_cursor, int n, int32_t* __restrict__ indptr,
                                                 int32_t* __restrict__ heavy) {
-  const int32_t* cnt = cnt_cursor;
-  int32_t* cursor = cnt_cursor;
   __shared__ int s_scan[40];
+  constexpr int IT = 8;   // rows per thread and iteration
   int base = 0, hbase = 0;
-  for (int b = 0; b < n; b += blockDim.x) {
-    int i = b + threadIdx.x;
-    int v = (i < n) ? cnt[i] : 0;
-    int tot;
-    int p = block_excl_scan(v, s_scan, &tot);
-    if (i < n) indptr[i] = base + p;
-    base += tot;
-    if (heavy) {
-      int hv = v > BLISS_SPMM_HEAVY, ht;
-      int hp = block_excl_scan(hv, s_scan, &ht);
-      if (hv) heavy[1 + hbase + hp] = i;
-      hbase += ht;
+  for (int b = 0; b < n; b += blockDim.x * IT) {
+    const int i0 = b + threadIdx.x * IT;
+    int v[IT], vsum = 0, hsum = 0;
+#pragma unroll
+    for (int u = 0; u < IT; ++u) {
+      v[u] = (i0 + u < n) ? cnt_cursor[i0 + u] : 0;
+      vsum += v[u];
+      hsum += v[u] > BLISS_SPMM_HEAVY;
     }
+    int tot, ht = 0;
+    int p = block_excl_scan(vsum, s_scan, &tot);
+    int hp = heavy ? block_excl_scan(hsum, s_scan, &ht) : 0;
+#pragma unroll
+    for (int u = 0; u < IT; ++u) {
+      if (i0 + u < n) {
+        indptr[i0 + u] = base + p;
+        cnt_cursor[i0 + u] = base + p;
+        if (heavy && v[u] > BLISS_SPMM_HEAVY) heavy[1 + hbase + hp++] = i0 + u;
+      }
+      p += v[u];
+    }
+    base += tot;
+    hbase += ht;
   }
-  __syncthreads();
   if (threadIdx.x == 0) {
     indptr[n] = base;
     if (heavy) heavy[0] = hbase;
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) cursor[i] = indptr[i];
 }
 // Edges of a source land in arbitrary order inside its segment; k_t_sort restores ascending edge
 // id so the backward sums are run-to-run deterministic.
@@ -1153,6 +1087,15 @@ static inline GraphView view_of(const bliss_graph* g) {
   v.num_nodes = g->num_nodes;
   return v;
 }
+// Grid of the chunk passes: the chunk count lives on the device, so the grid is sized from the
+// host's bound on the rows (a CTA takes 8 chunks per round; CTAs that find the queue empty exit at
+// once) and capped at what is resident at once (6 CTAs of 256 threads per SM at <= 40 registers).
+static inline int chunk_grid(int64_t n_seeds, int per_sm = 6) {
+  int64_t b = 4 * n_seeds + 8;
+  if (b < 1) b = 1;
+  if (b > BLISS_SM_COUNT * per_sm) b = BLISS_SM_COUNT * per_sm;
+  return (int)b;
+}
 static inline int grid_for(int64_t n, int threads, int max_blocks) {
   int64_t b = (n + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -1186,8 +1129,9 @@ int bliss_frontier_prob(const bliss_graph* g, const int32_t* seeds, int32_t n_se
   if (!edge_weight_csc) return -1;
   cudaStream_t st = (cudaStream_t)stream;
   const float one_minus_eta = (float)(1.0 - (double)eta);
-  // persistent grids of warps over the plan's chunk table (count read on the device)
-  const int blocks = grid_for((int64_t)n_seeds * 256 * 4, 256, BLISS_SM_COUNT * 8);
+  // persistent grids over the plan's chunks (count read on the device): every resident CTA pulls
+  // groups of 8 chunks from the layer's queue
+  const int blocks = chunk_grid(n_seeds);
   const bool bandit = (mode & 1) == BLISS_MODE_BANDIT;
   if (bandit) {   // the row sums are also needed by the block fill when importance sampling is off
     k_prob_pass1<<<blocks, 256, 0, st>>>(edge_weight_csc, *ws);
@@ -1195,9 +1139,9 @@ int bliss_frontier_prob(const bliss_graph* g, const int32_t* seeds, int32_t n_se
     k_prob_pass2<<<blocks, 256, 0, st>>>(edge_weight_csc, eta, one_minus_eta, *ws);
     BLISS_CHECK_LAUNCH();
   }
-  k_prob_pass3<<<blocks, 256, 0, st>>>(view_of(g), edge_weight_csc, eta, one_minus_eta, mode, *ws);
+  k_prob_pass3<<<chunk_grid(n_seeds, 5), 256, 0, st>>>(view_of(g), edge_weight_csc, eta, one_minus_eta, mode, *ws);
   BLISS_CHECK_LAUNCH();
-  k_collect_candidates<<<grid_for(g->num_nodes, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(
+  k_collect_candidates<<<grid_for(g->num_nodes, 32 * BLISS_COLLECT_WORDS * 8, BLISS_SM_COUNT * 8), 256, 0, st>>>(
       g->num_nodes, (mode & BLISS_COLLECT_BITMAP) ? 1 : 0, *ws);
   BLISS_CHECK_LAUNCH();
   return 0;
@@ -1293,10 +1237,16 @@ int bliss_philox_fill(uint64_t seed, uint64_t step, uint32_t layer, const int32_
 }
 
 int bliss_block_count(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                      const float* edge_weight_csc, float eta, int32_t mode,
                       const bliss_workspace* ws, void* stream) {
-  if (!g || !seeds || !ws) return -1;
-  int blocks = grid_for((int64_t)n_seeds * BLISS_CTA, BLISS_CTA, BLISS_SM_COUNT * 8);
-  k_block_count<<<blocks, BLISS_CTA, 0, (cudaStream_t)stream>>>(view_of(g), seeds, *ws);
+  if (!g || !seeds || !ws || !edge_weight_csc) return -1;
+  FillCtx c;
+  c.g = view_of(g);
+  c.W = edge_weight_csc;
+  c.eta = eta;
+  c.one_minus_eta = (float)(1.0 - (double)eta);
+  c.mode = mode & 1;
+  k_block_count<<<chunk_grid(n_seeds), BLISS_CTA, 0, (cudaStream_t)stream>>>(c, *ws);
   BLISS_CHECK_LAUNCH();
   return 0;
 }
@@ -1320,8 +1270,7 @@ int bliss_block_fill(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds
   c.eta = eta;
   c.one_minus_eta = (float)(1.0 - (double)eta);
   c.mode = mode & 1;
-  int blocks = grid_for((int64_t)n_seeds * BLISS_CTA, BLISS_CTA, BLISS_SM_COUNT * 5);
-  k_block_fill<<<blocks, BLISS_CTA, 0, (cudaStream_t)stream>>>(c, seeds, *ws, *out);
+  k_block_fill<<<chunk_grid(n_seeds), BLISS_CTA, 0, (cudaStream_t)stream>>>(c, *ws, *out);
   BLISS_CHECK_LAUNCH();
   return 0;
 }
@@ -1388,7 +1337,7 @@ int bliss_sample_layer_front(const bliss_graph* g, const int32_t* seeds, int32_t
     rc = bliss_select_topk(n_seeds, fanout, seed, step, layer, u_inject, key_scratch, ws, stream);
   }
   if (rc) return rc;
-  rc = bliss_block_count(g, seeds, n_seeds, ws, stream);
+  rc = bliss_block_count(g, seeds, n_seeds, edge_weight_csc, eta, mode, ws, stream);
   if (rc) return rc;
   return bliss_block_index(seeds, n_seeds, ws, out, stream);
 }

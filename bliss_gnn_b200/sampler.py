@@ -44,24 +44,21 @@ class _Workspace:
         self.node_info = torch.empty(2 * V, **i32)
         self.sel_bits = torch.empty((V + 31) // 32, **i32)
         self.cand_bits = torch.empty((V + 31) // 32, **i32)
-        self.keep_bits = torch.zeros(g.num_edges() // 32 + 2, **i32)
-        self.pos_a = torch.empty(V, dtype=torch.int64, device=dev)
-        self.pos_d = torch.empty(V, **i32)
         n_chunk_cap = g.num_edges() // 256 + V + 8          # every column cut into 256-edge chunks
+        self.keep_bits = torch.zeros(8 * n_chunk_cap, **i32)
         self.row_a = torch.empty(V, dtype=torch.int64, device=dev)
         self.row_d = torch.empty(V, **i32)
         self.chunk_first = torch.empty(V + 1, **i32)
-        self.chunk_row = torch.empty(n_chunk_cap, **i32)
         self.part_w = torch.empty(n_chunk_cap, dtype=torch.float64, device=dev)
         self.part_q = torch.empty(n_chunk_cap, dtype=torch.float64, device=dev)
         self.cand = torch.empty(V, **i32)
         self.p_cand = torch.empty(V, dtype=torch.float32, device=dev)
         self.sel = torch.empty(V, **i32)
-        self.row_list = torch.empty(V, **i32)
         self.row_w = torch.empty(V, dtype=torch.float32, device=dev)
         self.row_q = torch.empty(V, dtype=torch.float32, device=dev)
         self.row_cnt = torch.empty(V, **i32)
-        self.row_t = torch.empty(V, dtype=torch.float64, device=dev)
+        self.part_cnt = torch.empty(n_chunk_cap, **i32)
+        self.part_t = torch.empty(n_chunk_cap, dtype=torch.float64, device=dev)
         self.src_nid = torch.empty(V, **i32)
         self.node_prob = torch.empty(V, dtype=torch.float32, device=dev)
         self.key_scratch = None
@@ -74,10 +71,10 @@ class _Workspace:
         self.ws = N.Workspace(
             acc=N.ptr(self.acc), first_pos=N.ptr(self.first_pos), node_info=N.ptr(self.node_info),
             sel_bits=N.ptr(self.sel_bits), cand_bits=N.ptr(self.cand_bits), keep_bits=N.ptr(self.keep_bits), cand=N.ptr(self.cand), p_cand=N.ptr(self.p_cand), sel=N.ptr(self.sel),
-            row_list=N.ptr(self.row_list), pos_a=N.ptr(self.pos_a), pos_d=N.ptr(self.pos_d), row_a=N.ptr(self.row_a), row_d=N.ptr(self.row_d),
-            chunk_first=N.ptr(self.chunk_first), chunk_row=N.ptr(self.chunk_row), part_w=N.ptr(self.part_w),
+            row_a=N.ptr(self.row_a), row_d=N.ptr(self.row_d),
+            chunk_first=N.ptr(self.chunk_first), part_w=N.ptr(self.part_w),
             part_q=N.ptr(self.part_q), row_w=N.ptr(self.row_w), row_q=N.ptr(self.row_q),
-            row_cnt=N.ptr(self.row_cnt), row_t=N.ptr(self.row_t), cap_seeds=V, cap_sel=V, ctr=N.ptr(self.ctr))
+            row_cnt=N.ptr(self.row_cnt), part_cnt=N.ptr(self.part_cnt), part_t=N.ptr(self.part_t), cap_seeds=V, cap_sel=V, ctr=N.ptr(self.ctr))
         self.gview = N.Graph(num_nodes=V, num_edges=g.num_edges(), indptr=N.ptr(g.indptr),
                              indices=N.ptr(g.indices), eid=N.ptr(g.eid))
         self._keep = (g.indptr, g.indices, g.eid)
@@ -307,7 +304,8 @@ class BanditLadiesSampler:
         """``bandit_sampler.py:269-339`` (``ladies_sampler.py:71-107``)."""
         fr, wsp = insg, insg.wsp
         out, bufs = self._block_out(fr)
-        N.call("bliss_block_count", C.byref(wsp.gview), N.ptr(fr.seeds), fr.n_seeds, C.byref(wsp.ws), N.stream())
+        N.call("bliss_block_count", C.byref(wsp.gview), N.ptr(fr.seeds), fr.n_seeds, N.ptr(fr.weights),
+               float(self.eta), fr.mode, C.byref(wsp.ws), N.stream())
         N.call("bliss_block_index", N.ptr(fr.seeds), fr.n_seeds, C.byref(wsp.ws), C.byref(out), N.stream())
         return self._finish_block(fr, out, bufs)
 

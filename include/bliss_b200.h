@@ -50,17 +50,17 @@ typedef struct bliss_counters {
   int32_t n_cand;      /* |seeds ∪ sources|  (insg.num_nodes(), :392)            */
   int32_t n_sel;       /* selected non-seed candidates                           */
   int32_t n_src;       /* block source nodes = n_seeds + n_sel                   */
-  int32_t n_heavy;     /* rows handled by a whole CTA                            */
-  int32_t n_light;     /* rows handled by one warp                               */
+  int32_t n_heavy;     /* reserved (0)                                           */
+  int32_t n_light;     /* reserved (0)                                           */
   int32_t take_all;    /* 1 when n_cand <= fanout (:392-393)                     */
   int32_t iters;       /* scale-search iterations used (:396)                    */
   int64_t e_in;        /* in-edges of the seeds (insg.num_edges())               */
   int64_t n_edges;     /* block edges E_b                                        */
   double  c;           /* Poisson scale                                          */
   double  s_last;      /* last S = sum min(c p, 1)                               */
-  int32_t queue[4];    /* dynamic row-queue cursors of the three row passes      */
+  int32_t queue[8];    /* work-queue cursors of the chunk passes (prob 1-3, count, fill) */
   int32_t error;       /* non-zero: a capacity was exceeded (see BLISS_ERR_*)    */
-  int32_t n_chunks;    /* 256-edge warp-chunks of the probability passes         */
+  int32_t n_chunks;    /* 256-edge warp-chunks of the frontier's rows            */
 } bliss_counters;
 
 #define BLISS_ERR_SEL_CAPACITY 1
@@ -76,24 +76,20 @@ typedef struct bliss_workspace {
   int32_t*  node_info;  /* [2V] (local id | -1, float bits of inclusion prob P) per node  */
   uint32_t* sel_bits;   /* [(V+31)/32] bitmap: node is selected                           */
   uint32_t* cand_bits;  /* [(V+31)/32] candidate bitmap (BLISS_COLLECT_BITMAP mode only)    */
-  uint32_t* keep_bits;  /* [E/32+1] one bit per CSC edge position: edge kept in the block; rows
-                           rewrite their own range, so it is never cleared                  */
+  uint32_t* keep_bits;  /* [8 * (E/256+V)] one bit per edge of every chunk: edge kept in the block */
   int32_t*  cand;       /* [V]  candidate list: seeds first, then sources unordered       */
   float*    p_cand;     /* [V]  raw probability per candidate slot                        */
   int32_t*  sel;        /* [C]  selected non-seed candidates, unordered                   */
-  int32_t*  row_list;   /* [S]  heavy rows from the front (longest first), light from the back */
-  int64_t*  pos_a;      /* [S]  CSC start of the row at each row_list position            */
-  int32_t*  pos_d;      /* [S]  in-degree of the row at each row_list position            */
   int64_t*  row_a;      /* [S]  CSC start of every seed's column (by seed rank)           */
   int32_t*  row_d;      /* [S]  in-degree of every seed                                   */
   int32_t*  chunk_first;/* [S+1] first 256-edge chunk of every seed's column (prefix)     */
-  int32_t*  chunk_row;  /* [E/256+V] seed rank of every chunk                             */
   double*   part_w;     /* [E/256+V] per-chunk partial of sum_j w_ij                      */
   double*   part_q;     /* [E/256+V] per-chunk partial of sum_j q_ij                      */
   float*    row_w;      /* [S]  sum_j w_ij  per seed                                      */
   float*    row_q;      /* [S]  sum_j q_ij  per seed                                      */
   int32_t*  row_cnt;    /* [S]  kept in-edges per seed                                    */
-  double*   row_t;      /* [S]  sum of unnormalised block weights per seed                */
+  int32_t*  part_cnt;   /* [E/256+V] kept in-edges per chunk                              */
+  double*   part_t;     /* [E/256+V] per-chunk partial of the unnormalised block weights  */
   int64_t   cap_seeds;  /* S */
   int64_t   cap_sel;    /* C */
   bliss_counters* ctr;  /* one counters block                                             */
@@ -160,6 +156,7 @@ int bliss_philox_fill(uint64_t seed, uint64_t step, uint32_t layer, const int32_
  * replaces insg.subgraph + edge_subgraph + to_block + e_div_u/copy_e_sum/e_mul_v
  * (bandit_sampler.py:285-337; ladies_sampler.py:81-106).                                    */
 int bliss_block_count(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
+                      const float* edge_weight_csc, float eta, int32_t mode,
                       const bliss_workspace* ws, void* stream);
 int bliss_block_index(const int32_t* seeds, int32_t n_seeds, const bliss_workspace* ws,
                       const bliss_block_out* out, void* stream);

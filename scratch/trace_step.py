@@ -1,0 +1,56 @@
+"""Timeline of one replayed training step (CUPTI through torch.profiler): per-kernel start, duration and
+the idle gap before it.  usage: python scratch/trace_step.py [out.txt] [n_gpus_ignored]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from bliss_gnn_b200 import _native as N  # noqa: E402
+from bliss_gnn_b200.train import DataModule, Trainer, build_model  # noqa: E402
+
+out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "trace_step.txt")
+N.build()
+dev = torch.device("cuda:0")
+torch.set_float32_matmul_precision("medium")
+g = bench.build_graph("reddit", 1.0, dev)
+dm = DataModule("reddit", fan_out=bench.FANOUT, eta=bench.ETA, device=dev, batch_size=bench.BATCH,
+                sampler="poisson-bandit", model="sage", seed=0, graph=g)
+torch.manual_seed(3)
+model = build_model("sage", dm.in_feats, bench.HIDDEN, dm.n_classes, 3, bench.DROPOUT).to(dev)
+tr = Trainer(dm, model, bench.LR, None, static_graph=True)
+batches = [b.to(dev) for b in bench.seed_batches_for(g, 0, 1, 64)]
+for i in range(20):
+    tr.training_step(batches[i])
+torch.cuda.synchronize()
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for i in range(20, 26):
+        tr.training_step(batches[i])
+    torch.cuda.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+ev.sort(key=lambda e: e.time_range.start)
+# split into steps at k_frontier_plan triples: a step starts at every third plan kernel
+starts = [i for i, e in enumerate(ev) if "k_frontier_plan" in e.name]
+with open(out_path, "w") as f:
+    if len(starts) >= 6:
+        a, b = starts[-6], starts[-3]
+        seg = ev[a:b]
+        t0 = seg[0].time_range.start
+        prev_end = t0
+        busy = 0.0
+        for e in seg:
+            s, d = e.time_range.start - t0, e.time_range.end - e.time_range.start
+            gap = e.time_range.start - prev_end
+            busy += d
+            prev_end = max(prev_end, e.time_range.end)
+            f.write(f"{s:9.1f} {d:8.1f} gap {gap:6.1f}  {e.name[:100]}\n")
+        f.write(f"# step span {ev[b].time_range.start - t0:.1f} us, busy {busy:.1f} us, kernels {len(seg)}\n")
+    else:
+        f.write(f"# could not split steps: {len(ev)} device events, {len(starts)} plan kernels\n")
+        for e in ev[:400]:
+            f.write(f"{e.time_range.start:.1f} {e.time_range.end - e.time_range.start:.1f} {e.name[:100]}\n")
+print(open(out_path).read()[-3000:])
