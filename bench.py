@@ -250,16 +250,18 @@ def main():
     clocks = ClockSampler(_visible_index(local))
     N.STATS.reset(timing=False)
     replays0 = tr.graph_replays
+    tr.flush()
     barrier()
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    edges = 0
+    edges0 = tr.total_sampled_edges
     e0.record()
     for _ in range(args.steps):
         tr.training_step(dev_batches[next(it)])
-        edges += sum(b.num_edges() for b in tr.last_blocks)
+    tr.flush()               # the last step's counters (sizes, capacity flags) are consumed inside the timed region
     e1.record()
     barrier()
+    edges = tr.total_sampled_edges - edges0
     clock_info = clocks.stop()
     # kernels launched eagerly + the hand-written kernels inside every CUDA-graph replay
     launches = N.STATS.launches + (tr.graph_replays - replays0) * tr.graph_kernels
@@ -270,14 +272,27 @@ def main():
     value = world * args.steps / (ms_total / 1e3)
 
     # ---- (2) end to end: seeds from pinned host memory every step, loss read back every step ----
+    # The loss of every step is copied to pinned host memory stream-ordered and consumed one step later
+    # (like the step's counters), so the host never stalls the device inside the loop.
     barrier()
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    losses = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         loss = tr.training_step(host_batches[next(it)])
-        _ = loss.item()
+        loss_host[i & 1].copy_(loss.reshape(1), non_blocking=True)
+        loss_ev[i & 1].record()
+        if i:
+            loss_ev[(i - 1) & 1].synchronize()
+            losses.append(float(loss_host[(i - 1) & 1]))
+    loss_ev[(args.steps - 1) & 1].synchronize()
+    losses.append(float(loss_host[(args.steps - 1) & 1]))
+    tr.flush()
     e1.record()
     barrier()
+    assert len(losses) == args.steps and all(l == l for l in losses), "e2e: a loss did not come back"
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
         torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
@@ -285,6 +300,7 @@ def main():
 
     # ---- (3) per-entry-point CUDA-event timing over the same kind of steps (roofline) ----
     n_prof = min(args.steps, 50)
+    tr.flush()
     dm.sampler.force_stage_path = True     # one FFI call per kernel, so each is bracketed by its own events
     N.STATS.reset(timing=True)
     sizes = []
@@ -340,7 +356,9 @@ def main():
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
            "sampled_edges_per_s": world * edges / (ms_total / 1e3), "clocks": clock_info,
            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": BATCH * 4 * world,
-                   "d2h_bytes_per_step": (4 + 3 * 88) * world},
+                   "d2h_bytes_per_step": (4 + dm.sampler._wsp.ctr_all.numel()) * world,
+                   "note": "seeds H2D from pinned memory every step; loss + per-layer counters D2H every step, "
+                           "copied stream-ordered and consumed one step later"},
            "gpu_launches": launches, "graph_replays": tr.graph_replays, "roofline": roofline,
            "roofline_sampling": roofline_sampling}
 

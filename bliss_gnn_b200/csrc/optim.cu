@@ -1,0 +1,79 @@
+// optim.cu — the optimizer step of the BLISS training step on sm_100a: Adam over ONE flat parameter
+// buffer (train_lightning.py:206, torch.optim.Adam(lr) with the default betas / eps, no weight
+// decay).  Every parameter, gradient and moment tensor of the model is a view into four flat fp32
+// buffers, so the whole update is one coalesced 128-bit streaming kernel (28 B per parameter)
+// instead of a multi-tensor launch per parameter list; the kernel also clears the gradient buffer
+// for the next backward pass.  lr and the step count live on the device, so the launch is
+// CUDA-graph replayable while a scheduler changes lr between replays.
+#include "common.cuh"
+
+namespace bliss {
+
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                             float* __restrict__ v, int64_t n, const float* __restrict__ lr_dev,
+                                             float beta1, float beta2, float eps, const int64_t* __restrict__ step_dev,
+                                             int zero_grad) {
+  __shared__ float s_c[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)(*step_dev + 1);
+    const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+    s_c[0] = (float)((double)*lr_dev / bc1);   // step size
+    s_c[1] = (float)sqrt(bc2);                 // sqrt of the second-moment bias correction
+  }
+  __syncthreads();
+  const float step_size = s_c[0], bc2_sqrt = s_c[1];
+  const float w1 = 1.0f - beta1, w2 = 1.0f - beta2;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* pf = reinterpret_cast<float*>(&pp);
+    float* gf = reinterpret_cast<float*>(&gg);
+    float* mf = reinterpret_cast<float*>(&mm);
+    float* vf = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mf[k] = mf[k] + w1 * (gf[k] - mf[k]);                 // exp_avg.lerp_(grad, 1 - beta1)
+      vf[k] = beta2 * vf[k] + w2 * gf[k] * gf[k];           // exp_avg_sq = beta2 v + (1 - beta2) g^2
+      pf[k] -= step_size * mf[k] / (sqrtf(vf[k]) / bc2_sqrt + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i];
+    const float mi = m[i] + w1 * (gi - m[i]);
+    const float vi = beta2 * v[i] + w2 * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+__global__ void k_adam_tick(int64_t* step_dev) { *step_dev += 1; }
+
+}  // namespace bliss
+
+extern "C" int bliss_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                               const float* lr_dev, float beta1, float beta2, float eps, int64_t* step_dev,
+                               int32_t zero_grad, void* stream) {
+  if (n < 0 || !lr_dev || !step_dev) return -1;
+  if (n > 0 && (!params || !grads || !exp_avg || !exp_avg_sq)) return -1;
+  if (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) return -2;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > 0) {
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > BLISS_SM_COUNT * 8) blocks = BLISS_SM_COUNT * 8;
+    bliss::k_adam<<<(int)blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps,
+                                               step_dev, zero_grad);
+    BLISS_CHECK_LAUNCH();
+  }
+  bliss::k_adam_tick<<<1, 1, 0, st>>>(step_dev);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}

@@ -97,3 +97,60 @@ class BanditExchange:
             self._hdr_host[l] = int(c)
         self.header.copy_(self._hdr_host, non_blocking=True)
         dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+
+
+class FlatAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam(params, lr)`` (``train_lightning.py:206``) over flat buffers: the parameters are
+    re-homed as views of one flat fp32 tensor (like the gradients of :class:`FlatGrads`), the moments are
+    flat too, and ``step()`` is ONE launch of ``bliss_adam_step`` that also clears the gradients.  ``lr``
+    and the step count are device scalars, so a captured step keeps following ``param_groups[0]['lr']``
+    (``StepLR``): call :meth:`sync_lr` before replaying."""
+
+    def __init__(self, flat_grads: FlatGrads, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        params = flat_grads.params
+        if not params or not params[0].is_cuda:
+            raise RuntimeError("FlatAdam runs on CUDA parameters only (torch.optim.Adam covers the CPU tests)")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        dev = params[0].device
+        self.flat_g = flat_grads.flat
+        self.flat_p = torch.empty_like(self.flat_g)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off:off + n].view_as(p)
+                off += n
+        self.exp_avg = torch.zeros_like(self.flat_g)
+        self.exp_avg_sq = torch.zeros_like(self.flat_g)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self._lr_host = float(lr)
+
+    def sync_lr(self):
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_host:
+            self.lr_dev.fill_(lr)
+            self._lr_host = lr
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from . import _native as N
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
+        g = self.param_groups[0]
+        N.call("bliss_adam_step", N.ptr(self.flat_p), N.ptr(self.flat_g), N.ptr(self.exp_avg), N.ptr(self.exp_avg_sq),
+               self.flat_p.numel(), N.ptr(self.lr_dev), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+               N.ptr(self.step_dev), 1, N.stream())
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_dev.clone(),
+                "lr": float(self.param_groups[0]["lr"])}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_dev.copy_(sd["step"])
+        self.param_groups[0]["lr"] = sd["lr"]
+        self._lr_host = None
+        self.sync_lr()

@@ -68,6 +68,9 @@ class _Workspace:
         self.ctr = self.ctr_all[0]
         self.ctr_host = torch.zeros(csz, dtype=torch.uint8).pin_memory()
         self.ctr_all_host = torch.zeros(self.MAX_LAYERS, csz, dtype=torch.uint8).pin_memory()
+        # two more pinned copies + events: a step's counters can be read while the next step runs
+        self._ctr_slots = [torch.zeros(self.MAX_LAYERS, csz, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._ctr_events = [torch.cuda.Event() for _ in range(2)]
         self.ws = N.Workspace(
             acc=N.ptr(self.acc), first_pos=N.ptr(self.first_pos), node_info=N.ptr(self.node_info),
             sel_bits=N.ptr(self.sel_bits), cand_bits=N.ptr(self.cand_bits), keep_bits=N.ptr(self.keep_bits), cand=N.ptr(self.cand), p_cand=N.ptr(self.p_cand), sel=N.ptr(self.sel),
@@ -97,6 +100,17 @@ class _Workspace:
         self.ctr_all_host.copy_(self.ctr_all, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         raw = self.ctr_all_host.numpy()
+        return [N.Counters.from_buffer_copy(raw[l].tobytes()) for l in range(n_layers)]
+
+    def enqueue_counter_read(self, slot: int):
+        """Stream-ordered D2H copy of all layers' counters into pinned slot ``slot`` (no host wait)."""
+        self._ctr_slots[slot].copy_(self.ctr_all, non_blocking=True)
+        self._ctr_events[slot].record()
+
+    def finish_counter_read(self, slot: int, n_layers: int):
+        """Wait for :meth:`enqueue_counter_read` of ``slot`` and parse the counters."""
+        self._ctr_events[slot].synchronize()
+        raw = self._ctr_slots[slot].numpy()
         return [N.Counters.from_buffer_copy(raw[l].tobytes()) for l in range(n_layers)]
 
     def read_counters(self) -> N.Counters:

@@ -25,7 +25,7 @@ import torch.nn.functional as F
 from . import ops
 from .graph import NID, Graph, add_self_loops_and_build, load_dataset, normalized_edata
 from .model import GCN, SAGE, GATv2
-from .parallel import FlatGrads, shard_batches
+from .parallel import FlatAdam, FlatGrads, shard_batches
 from .sampler import BanditLadiesSampler, LadiesSampler, PoissonBanditLadiesSampler, PoissonLadiesSampler
 
 
@@ -126,13 +126,17 @@ class Trainer:
     """One training step = the hot path end to end (``train_lightning.py:100-168,463-471``)."""
 
     def __init__(self, datamodule: DataModule, model: nn.Module, lr=0.002, process_group=None,
-                 static_graph: bool = False, eager_warmup: int = 4):
+                 static_graph: bool = False, eager_warmup: int = 4, pipeline: bool = True):
         """``static_graph=True``: after ``eager_warmup`` ordinary steps the blocks are built into
-        capacity-padded persistent buffers (``sampler.LayerPool``) and the model's forward, backward
-        and Adam step run as ONE replayed CUDA graph — the step stops being bound by Python dispatch.
-        Sampling and the bandit update stay eager (their sizes are data dependent)."""
+        capacity-padded persistent buffers (``sampler.LayerPool``) and the whole step (sampling, model
+        forward / backward, Adam, bandit update) runs as ONE replayed CUDA graph — the step stops being
+        bound by Python dispatch.  ``pipeline=True``: the step's device counters (sizes, capacity flags)
+        are copied to pinned memory stream-ordered and consumed while the NEXT step runs, so the host
+        never waits inside a step; ``flush()`` consumes the outstanding read."""
         self.dm, self.model, self.pg = datamodule, model, process_group
         self.static_graph, self.eager_warmup = bool(static_graph), int(eager_warmup)
+        self.pipeline, self._pending = bool(pipeline), None
+        self.total_sampled_edges = 0        # Σ block edges over all consumed steps (bench.py's edges/s)
         # the data-parallel code path (two graphs with the collectives in between) can be forced on a
         # single rank, so it is testable on one GPU
         self._force_dp = bool(os.environ.get("BLISS_FORCE_DP_PATH")) and process_group is not None
@@ -145,9 +149,11 @@ class Trainer:
         self.grads = FlatGrads(model.parameters())
         params = self.grads.params
         self._flat_grad = self.grads.flat
-        fused = params[0].is_cuda
-        self.optimizer = torch.optim.Adam(params, lr=lr, fused=fused,
-                                          capturable=bool(static_graph and fused))   # :206
+        self._grads_clean = False
+        if params[0].is_cuda:     # one flat Adam launch per step (csrc/optim.cu); it also clears the gradients
+            self.optimizer = FlatAdam(self.grads, lr=lr)
+        else:                     # host-logic tests (gloo): the product path refuses CPU graphs anyway
+            self.optimizer = torch.optim.Adam(params, lr=lr)                         # :206
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, gamma=0.01, step_size=5)   # :208 (per epoch)
         if process_group is not None and hasattr(datamodule.sampler, "process_group"):
             datamodule.sampler.process_group = process_group
@@ -161,6 +167,7 @@ class Trainer:
     def _ema(self, mfgs):
         """EMA sampled nodes / edges per layer (``train_lightning.py:104-136``)."""
         self.num_steps += 1
+        self.total_sampled_edges += sum(m.num_edges() for m in mfgs)
         for i, mfg in enumerate(mfgs):
             self.cum_sampled_nodes[i] = self.cum_sampled_nodes[i] * self.w + mfg.num_src_nodes()
             self.cum_sampled_edges[i] = self.cum_sampled_edges[i] * self.w + mfg.num_edges()
@@ -188,16 +195,32 @@ class Trainer:
         batch_labels = mfgs[-1].dstdata["labels"]                                # :139
         batch_pred = self.model(mfgs, batch_inputs)                              # :141
         loss = self.loss_fn(batch_pred, batch_labels)                            # :142
-        self._flat_grad.zero_()
+        self._zero_grads()
         loss.backward()
         self.grads.all_reduce_mean_(self.pg)
-        self.optimizer.step()
+        self._optimizer_step()
         if "bandit" in dm.sampler_name:                                          # :469-471
             dm.sampler.exp3(mfgs, g)
         # detached: nothing may keep this step's autograd graph (and its AccumulateGrad nodes) alive,
         # or a later CUDA-graph capture would see nodes bound to another stream
         self.last_blocks, self.last_pred, self.last_labels = mfgs, batch_pred.detach(), batch_labels
         return loss.detach()
+
+    def _zero_grads(self):
+        """The flat Adam launch leaves the gradient buffer cleared; zero it only when something else
+        (a backward pass without a step) has written to it since."""
+        if not self._grads_clean:
+            self._flat_grad.zero_()
+        self._grads_clean = False
+
+    def _sync_lr(self):
+        """A captured step reads lr from a device scalar: refresh it when the scheduler changed it."""
+        if isinstance(self.optimizer, FlatAdam):
+            self.optimizer.sync_lr()
+
+    def _optimizer_step(self):
+        self.optimizer.step()
+        self._grads_clean = isinstance(self.optimizer, FlatAdam)
 
     # ---- static-shape path: padded blocks + one CUDA graph for forward/backward/Adam ---------------
     def _alloc_pools(self):
@@ -240,10 +263,10 @@ class Trainer:
         y = g.ndata["labels"][self._seeds_static.long()]
         pred = self.model(self._padded, x)[: self.dm.batch_size]
         loss = self.loss_fn(pred, y)
-        self._flat_grad.zero_()
+        self._zero_grads()
         loss.backward()
         if step_optimizer:
-            self.optimizer.step()
+            self._optimizer_step()
         return loss.detach(), pred.detach(), y
 
     def _capture(self):
@@ -300,11 +323,12 @@ class Trainer:
         if self._graph is None:
             self._capture()
         self._ema(mfgs)
+        self._sync_lr()
         self._graph.replay()
         self.graph_replays += 1
         if self.world > 1:
             self.grads.all_reduce_mean_(self.pg)
-            self.optimizer.step()
+            self._optimizer_step()
         for l, b in enumerate(mfgs):                        # what exp3 reads from the forward pass
             pb = self._padded[l]
             b.srcdata["embed_norm"] = pb.srcdata["embed_norm"][: b.num_src_nodes()]
@@ -336,16 +360,35 @@ class Trainer:
         if self._graph is None:
             self._capture_full()
         self._seeds_static.copy_(seeds, non_blocking=True)
+        self._sync_lr()
         self._graph.replay()
         if self.world > 1 or self._force_dp:      # the only exchanges of a data-parallel step, between the two graphs
             self.grads.all_reduce_mean_(self.pg)
             if self._exchange is not None:
                 torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send, group=self.pg)
             self._graph_b.replay()
+        slot = self.graph_replays & 1
         self.graph_replays += 1
-        ctrs = smp._wsp.read_all_counters(L)                   # the step's single host sync
+        smp._wsp.enqueue_counter_read(slot)                    # stream-ordered D2H, no host wait
         smp.step += 1
         smp.tick_renorm(L)
+        if self.pipeline:                                      # consume the PREVIOUS step's counters
+            prev, self._pending = self._pending, slot
+            if prev is None:
+                return self._static_loss
+            slot = prev
+        self._consume_counters(smp._wsp.finish_counter_read(slot, L))
+        return self._static_loss
+
+    def flush(self):
+        """Consume the counters of the last enqueued step (pipelined mode)."""
+        if self._pending is not None:
+            slot, self._pending = self._pending, None
+            self._consume_counters(self.dm.sampler._wsp.finish_counter_read(slot, len(self.dm.sampler.nodes_per_layer)))
+
+    def _consume_counters(self, ctrs):
+        dm, g, smp = self.dm, self.dm.g, self.dm.sampler
+        L = len(smp.nodes_per_layer)
         grow = False
         for l, c in enumerate(ctrs):
             if c.error:
@@ -361,6 +404,7 @@ class Trainer:
             self.cum_sampled_nodes[i] = self.cum_sampled_nodes[i] * self.w + c.n_src
             self.cum_sampled_edges[i] = self.cum_sampled_edges[i] * self.w + c.n_edges
         self.cum_sampled_nodes[L] = self.cum_sampled_nodes[L] * self.w + dm.batch_size
+        self.total_sampled_edges += sum(int(c.n_edges) for c in ctrs)
         self.last_blocks = _CounterBlocks(ctrs)
         self.last_pred, self.last_labels = self._static_pred, self._static_y
         if self.world > 1:        # re-sizing allocates collectively: agree on it, every 32 steps
@@ -372,7 +416,6 @@ class Trainer:
                 grow, self._grow_pending = bool(flag.item() > 0), False
         if grow:                                               # high-water mark: re-size before it can overflow
             self._alloc_pools()
-        return self._static_loss
 
     def _capture_full(self):
         from . import _native
@@ -407,7 +450,7 @@ class Trainer:
             return loss, pred, y
 
         def body_b():        # graph B (data parallel): after the all-reduce / all-gather
-            self.optimizer.step()
+            self._optimizer_step()
             if bandit:
                 smp.exp3_apply(self._exchange, L)
             self._step_dev.add_(1)

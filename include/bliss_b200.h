@@ -248,6 +248,17 @@ int bliss_l1_norm(const float* w, int64_t n, double* partial /* [1024] */, doubl
                   void* stream);
 int bliss_scale_by_inv(float* w, int64_t n, const double* norm, double eps, void* stream);
 
+
+/* ---- optimizer step ------------------------------------------------------------------------
+ * replaces torch.optim.Adam(params, lr).step() (train_lightning.py:205-216; betas / eps given by the
+ * caller, no weight decay, no amsgrad) over flat, 16-byte aligned fp32 buffers: parameters, gradients
+ * and both moments of the whole model.  lr and the step count are device scalars (CUDA-graph replay:
+ * a scheduler changes lr between replays); the call advances *step_dev by one and, with zero_grad,
+ * clears the gradient buffer for the next backward pass. */
+int bliss_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    const float* lr_dev, float beta1, float beta2, float eps, int64_t* step_dev,
+                    int32_t zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

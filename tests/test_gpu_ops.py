@@ -215,6 +215,9 @@ def test_static_graph_step_matches_eager(native_lib, kind):
         for step, seeds in zip(range(12), dm.train_batches()):
             out.append(float(tr.training_step(seeds).item()))
         assert len(out) == 12
+        if static:
+            tr.flush()                       # pipelined counters: the last step's are still outstanding
+        assert tr.num_steps == 12 and tr.total_sampled_edges > 0
         losses[static] = out
         if static:
             assert tr.graph_replays >= 7
@@ -281,3 +284,32 @@ def test_padded_feature_rows_give_the_same_model_output(native_lib, kind):
     _close(y1, y0, what="padded logits")
     for a, b in zip(mdl.parameters(), g0):
         _close(a.grad, b, rtol=2e-5, what="padded grads")
+
+
+def test_flat_adam_matches_torch_adam(native_lib):
+    """``parallel.FlatAdam`` (one ``bliss_adam_step`` launch over flat buffers) follows
+    ``torch.optim.Adam`` — the reference's optimizer, ``train_lightning.py:206`` — step by step,
+    including an lr change between steps and the cleared gradient buffer."""
+    from bliss_gnn_b200.parallel import FlatAdam, FlatGrads
+    dev = _dev()
+    torch.manual_seed(0)
+    shapes = [(37, 19), (19,), (5, 37), (1,), (64, 64)]
+    ref_p = [torch.randn(s, device=dev, requires_grad=True) for s in shapes]
+    my_p = [p.detach().clone().requires_grad_(True) for p in ref_p]
+    ref_opt = torch.optim.Adam(ref_p, lr=0.002)
+    fg = FlatGrads(my_p)
+    my_opt = FlatAdam(fg, lr=0.002)
+    for step in range(25):
+        if step == 10:
+            for o in (ref_opt, my_opt):
+                o.param_groups[0]["lr"] = 0.0007
+        grads = [torch.randn(s, device=dev) * (0.1 + step) for s in shapes]
+        for p, q, g in zip(ref_p, my_p, grads):
+            p.grad = g.clone()
+            q.grad.add_(g)                      # accumulate into the (cleared) flat buffer like autograd does
+        ref_opt.step()
+        my_opt.step()
+        assert float(fg.flat.abs().max()) == 0.0, "the step must leave the gradient buffer cleared"
+        for p, q in zip(ref_p, my_p):
+            _close(q.detach(), p.detach(), rtol=2e-6, what=f"adam step {step}")
+    assert int(my_opt.step_dev.item()) == 25
