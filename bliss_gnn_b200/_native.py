@@ -92,7 +92,7 @@ class BlockOut(C.Structure):
     _fields_ = [("indptr", C.c_void_p), ("edge_src", C.c_void_p), ("edge_dst", C.c_void_p),
                 ("csc_pos", C.c_void_p), ("eid", C.c_void_p), ("q_ij", C.c_void_p), ("edge_w", C.c_void_p),
                 ("src_nid", C.c_void_p), ("node_prob", C.c_void_p), ("out_deg", C.c_void_p),
-                ("heavy_rows", C.c_void_p), ("inv_deg", C.c_void_p), ("cap_edges", C.c_int64), ("cap_src", C.c_int64), ("pad_src", C.c_int64), ("pad_rows", C.c_int64)]
+                ("seg_ptr", C.c_void_p), ("inv_deg", C.c_void_p), ("cap_edges", C.c_int64), ("cap_src", C.c_int64), ("pad_src", C.c_int64), ("pad_rows", C.c_int64)]
 
 
 _P, _I32, _I64, _U32, _U64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_double
@@ -118,7 +118,7 @@ PROTOTYPES = {
     "bliss_block_transpose": [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P],
     "bliss_gather_rows": [_P, _P, _I64, _I32, _P, _P, _P],
     "bliss_row_norm": [_P, _I64, _I32, _P, _P],
-    "bliss_spmm": [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P, _P],
+    "bliss_spmm": [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P, _I64, _P, _P],
     "bliss_gatv2_fwd": [_P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "bliss_gatv2_bwd_dst": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P],
     "bliss_gatv2_bwd_src": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _P],
@@ -156,9 +156,9 @@ class BlissNativeError(RuntimeError):
 
 
 #: kernels each entry point launches (for the ``gpu_launches`` count of bench.py)
-LAUNCHES = {"bliss_frontier_prob": 4, "bliss_sample_layer_front": 8, "bliss_sample_layer_back": 2,
+LAUNCHES = {"bliss_frontier_prob": 4, "bliss_sample_layer_front": 9, "bliss_frontier_plan": 2, "bliss_sample_layer_back": 2,
             "bliss_select_topk": 3, "bliss_block_transpose": 3, "bliss_l1_norm": 2, "bliss_version": 0,
-            "bliss_adam_step": 2}
+            "bliss_adam_step": 2, "bliss_spmm": 2}
 
 
 class _Stats:

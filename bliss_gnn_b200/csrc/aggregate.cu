@@ -2,8 +2,9 @@
 // fused row norm, embed_norm, and the SpMM used by SAGE / GCN forward and (on the transposed
 // block) backward.  Replaces DGL g-SpMM u_mul_e/sum + fn.mean (model.py:321-329,428-436 through
 // dglnn.SAGEConv / GraphConv), th.norm (model.py:318,425) and the lazy DGL frame gather
-// (train_lightning.py:138).  All of it is HBM/L2-bound gather work: warp per row, 128-bit
-// loads along the feature dimension, edge metadata loaded coalesced and broadcast by shuffle.
+// (train_lightning.py:138).  All of it is HBM/L2-bound gather work: warp per row (or per 32-edge
+// row segment), 128-bit loads along the feature dimension, edge metadata loaded coalesced and
+// broadcast by shuffle.
 #include "common.cuh"
 
 namespace bliss {
@@ -63,15 +64,17 @@ __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ t
 }
 
 // y[r, c0:c0+W] = dscale_r * Σ_{e in row r} w_e * sscale[col_e] * x[col_e, c0:c0+W]
-// Light rows: one warp per (row, column tile), accumulators NCH*VEC floats per lane.
-// Heavy rows (> BLISS_SPMM_HEAVY edges, listed in `heavy`): one CTA per row, the 8 warps take
-// interleaved 32-edge chunks and their partial sums are combined through shared memory in warp
-// order — a hub row no longer serialises on one warp and the result stays deterministic.
+// One warp per (row or row segment, column tile), accumulators NCH*VEC floats per lane; the edge
+// metadata of 32 edges is loaded coalesced and broadcast by shuffle.
+// Up to 32 edges [e0, min(b, e0+32)): metadata loaded coalesced, then the source rows are gathered
+// MLP edges at a time with every load issued before the first use (a warp's gathers are a chain of
+// L2 round trips otherwise: ~1 us per 4 edges).
 template <int VEC, int NCH>
 __device__ __forceinline__ void spmm_chunk(float (&acc)[NCH][VEC], int e0, int b, int lane, int c0, int dim,
                                            const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
                                            const float* __restrict__ w, const float* __restrict__ sscale,
                                            const float* __restrict__ x) {
+  constexpr int MLP = (NCH * VEC <= 8) ? 4 : (NCH * VEC <= 16 ? 2 : 1);
   const int e = e0 + lane;
   int my_c = 0;
   float my_w = 0.0f;
@@ -81,21 +84,32 @@ __device__ __forceinline__ void spmm_chunk(float (&acc)[NCH][VEC], int e0, int b
     if (sscale) my_w *= __ldg(sscale + my_c);
   }
   const int n = min(32, b - e0);
-#pragma unroll 4
-  for (int j = 0; j < n; ++j) {
-    const int c = __shfl_sync(0xffffffffu, my_c, j);
-    const float ww = __shfl_sync(0xffffffffu, my_w, j);
-    const float* __restrict__ xr = x + (int64_t)c * dim + c0;
+  for (int j0 = 0; j0 < n; j0 += MLP) {
+    float v[MLP][NCH][VEC];
+    float ww[MLP];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      const int cc = (ch * 32 + lane) * VEC;
-      if (c0 + cc < dim) {
-        float v[VEC];
-        vload<VEC>(v, xr + cc);
+    for (int u = 0; u < MLP; ++u) {
+      // lanes beyond the chunk hold column 0 / weight 0: a harmless (cached) load that adds nothing
+      const int c = __shfl_sync(0xffffffffu, my_c, (j0 + u) & 31);
+      ww[u] = (j0 + u < n) ? __shfl_sync(0xffffffffu, my_w, (j0 + u) & 31) : 0.0f;
+      const float* __restrict__ xr = x + (int64_t)c * dim + c0;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(ww, v[i], acc[ch][i]);
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int cc = (ch * 32 + lane) * VEC;
+        if (c0 + cc < dim) {
+          vload<VEC>(v[u][ch], xr + cc);
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) v[u][ch][i] = 0.0f;
+        }
       }
     }
+#pragma unroll
+    for (int u = 0; u < MLP; ++u)
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(ww[u], v[u][ch][i], acc[ch][i]);
   }
 }
 
@@ -104,50 +118,172 @@ __global__ void __launch_bounds__(256) k_spmm(const int32_t* __restrict__ indptr
                                              const int32_t* __restrict__ perm, const float* __restrict__ w,
                                              const float* __restrict__ sscale, const float* __restrict__ dscale,
                                              int agg, const float* __restrict__ x, int n_rows, int dim,
-                                             const int32_t* __restrict__ heavy, float* __restrict__ y) {
-  extern __shared__ float s_part[];  // [8 warps][TILE] partial sums of a heavy row
+                                             float* __restrict__ y) {
   constexpr int TILE = 32 * VEC * NCH;
   const int lane = lane_id();
   const int c0 = blockIdx.y * TILE;
-  const int n_heavy = heavy ? heavy[0] : 0;
-
-  for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
-    const int r = heavy[1 + h];
-    const int a = indptr[r], b = indptr[r + 1];
-    float acc[NCH][VEC];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.0f;
-    for (int e0 = a + 32 * warp_id(); e0 < b; e0 += 32 * 8)
-      spmm_chunk<VEC, NCH>(acc, e0, b, lane, c0, dim, col, perm, w, sscale, x);
-    __syncthreads();
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) s_part[warp_id() * TILE + (ch * 32 + lane) * VEC + i] = acc[ch][i];
-    __syncthreads();
-    float s = dscale ? dscale[r] : 1.0f;
-    if (agg == BLISS_AGG_MEAN) s = s / (float)max(b - a, 1);
-    for (int cc = threadIdx.x; cc < TILE && c0 + cc < dim; cc += blockDim.x) {
-      float t = 0.0f;
-#pragma unroll
-      for (int wv = 0; wv < 8; ++wv) t += s_part[wv * TILE + cc];
-      y[(int64_t)r * dim + c0 + cc] = t * s;
-    }
-  }
-
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int r = warp; r < n_rows; r += nwarps) {
     const int a = indptr[r], b = indptr[r + 1];
-    if (heavy && b - a > BLISS_SPMM_HEAVY) continue;
     float acc[NCH][VEC];
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.0f;
     for (int e0 = a; e0 < b; e0 += 32) spmm_chunk<VEC, NCH>(acc, e0, b, lane, c0, dim, col, perm, w, sscale, x);
+    float s = dscale ? dscale[r] : 1.0f;
+    if (agg == BLISS_AGG_MEAN) s = s / (float)max(b - a, 1);
+    float* __restrict__ yr = y + (int64_t)r * dim + c0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int cc = (ch * 32 + lane) * VEC;
+      if (c0 + cc < dim) {
+        float v[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = acc[ch][i] * s;
+        vstore<VEC>(yr + cc, v);
+      }
+    }
+  }
+}
+
+// Balanced variant for sampled blocks: every row is cut into segments of BLISS_SPMM_SEG (32) edges
+// (seg_ptr = prefix of max(1, ceil(len / 32)) over the rows, built with the block).  A CTA takes 8
+// consecutive segments, one per warp, whatever rows they belong to; the partial sums meet in
+// shared memory and each run of segments of one row is added up in segment order by the run's
+// first warp.  A row that lies inside one group is finished there.  A hub row (thousands of edges:
+// a popular destination is linked to most sampled sources) spans many groups, so it no longer
+// streams megabytes through one SM: every group stores ONE partial per run (slot = the run's
+// first segment), and k_spmm_combine adds a row's partials in group order — a fixed order, so the
+// result is deterministic without atomics.
+template <int VEC, int NCH>
+__global__ void __launch_bounds__(256, 5) k_spmm_seg(const int32_t* __restrict__ indptr, const int32_t* __restrict__ seg_ptr,
+                                                 const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+                                                 const float* __restrict__ w, const float* __restrict__ sscale,
+                                                 const float* __restrict__ dscale, int agg, const float* __restrict__ x,
+                                                 int n_rows, int dim, float* __restrict__ partial, int64_t item_cap,
+                                                 float* __restrict__ y) {
+  constexpr int TILE = 32 * VEC * NCH;
+  using T = typename VecT<VEC>::T;
+  extern __shared__ float s_part[];   // [8 warps][TILE]
+  __shared__ int s_row[8];
+  const int lane = lane_id(), wid = warp_id();
+  const int c0 = blockIdx.y * TILE;
+  const int n_items = seg_ptr[n_rows];
+  const int n_groups = (n_items + 7) >> 3;
+  float* __restrict__ tile_partial = partial + (int64_t)blockIdx.y * item_cap * TILE;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int item = grp * 8 + wid;
+    const bool valid = item < n_items;
+    int r = -1, a = 0, b = 0, s0 = 0, nseg = 1;
+    float acc[NCH][VEC];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.0f;
+    if (valid) {
+      int lo = 0, hi = n_rows - 1;   // row of the item: last r with seg_ptr[r] <= item (warp-uniform search)
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(seg_ptr + mid) <= item) lo = mid; else hi = mid - 1;
+      }
+      r = lo;
+      a = indptr[r];
+      b = indptr[r + 1];
+      s0 = seg_ptr[r];
+      nseg = seg_ptr[r + 1] - s0;
+      const int e_lo = a + (item - s0) * BLISS_SPMM_SEG;
+      spmm_chunk<VEC, NCH>(acc, e_lo, min(b, e_lo + BLISS_SPMM_SEG), lane, c0, dim, col, perm, w, sscale, x);
+    }
+    if (lane == 0) s_row[wid] = r;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) vstore<VEC>(s_part + wid * TILE + (ch * 32 + lane) * VEC, acc[ch]);
+    __syncthreads();
+    if (valid && (wid == 0 || s_row[wid - 1] != r)) {   // first segment of this row's run in the group
+      int len = 1;
+      while (wid + len < 8 && s_row[wid + len] == r) ++len;
+      for (int k = 1; k < len; ++k) {                    // run total, segment order
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const T v = *reinterpret_cast<const T*>(s_part + (wid + k) * TILE + (ch * 32 + lane) * VEC);   // shared memory
+          const float* f = reinterpret_cast<const float*>(&v);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[ch][i] += f[i];
+        }
+      }
+      if (item == s0 && len == nseg) {                   // the whole row lies in this group
+        float s = dscale ? dscale[r] : 1.0f;
+        if (agg == BLISS_AGG_MEAN) s = s / (float)max(b - a, 1);
+        float* __restrict__ yr = y + (int64_t)r * dim + c0;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int cc = (ch * 32 + lane) * VEC;
+          if (c0 + cc < dim) {
+            float v[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) v[i] = acc[ch][i] * s;
+            vstore<VEC>(yr + cc, v);
+          }
+        }
+      } else {
+        float* __restrict__ pr = tile_partial + (int64_t)item * TILE;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) vstore<VEC>(pr + (ch * 32 + lane) * VEC, acc[ch]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Rows that span several groups of k_spmm_seg: add the runs' partials in group order.  Runs start
+// at the row's first segment s0 and at every multiple of 8 after it.  One warp per row.
+template <int VEC, int NCH>
+__global__ void __launch_bounds__(256) k_spmm_combine(const int32_t* __restrict__ indptr, const int32_t* __restrict__ seg_ptr,
+                                                     const float* __restrict__ dscale, int agg, int n_rows, int dim,
+                                                     const float* __restrict__ partial, int64_t item_cap,
+                                                     float* __restrict__ y) {
+  constexpr int TILE = 32 * VEC * NCH;
+  using T = typename VecT<VEC>::T;
+  const int lane = lane_id();
+  const int c0 = blockIdx.y * TILE;
+  const float* __restrict__ tile_partial = partial + (int64_t)blockIdx.y * item_cap * TILE;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < n_rows; r += nwarps) {
+    const int s0 = seg_ptr[r], s1 = seg_ptr[r + 1];
+    if ((s0 >> 3) == ((s1 - 1) >> 3)) continue;   // the row lies in one group: finished by k_spmm_seg
+    const int first_full = ((s0 >> 3) + 1) << 3;
+    const int n_runs = 1 + ((s1 - 1) >> 3) - (s0 >> 3);
+    float acc[NCH][VEC];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.0f;
+    constexpr int CU = (NCH * VEC <= 8) ? 8 : (NCH * VEC <= 16 ? 4 : 2);   // partials in flight
+    for (int k0 = 0; k0 < n_runs; k0 += CU) {
+      T pv[CU][NCH];
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        const int k = k0 + u;
+        const int64_t slot = (k == 0) ? s0 : first_full + 8 * (k - 1);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+          if (k < n_runs) pv[u][ch] = __ldg(reinterpret_cast<const T*>(tile_partial + slot * TILE + (ch * 32 + lane) * VEC));
+      }
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        if (k0 + u < n_runs) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            const float* f = reinterpret_cast<const float*>(&pv[u][ch]);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[ch][i] += f[i];
+          }
+        }
+      }
+    }
+    const int a = indptr[r], b = indptr[r + 1];
     float s = dscale ? dscale[r] : 1.0f;
     if (agg == BLISS_AGG_MEAN) s = s / (float)max(b - a, 1);
     float* __restrict__ yr = y + (int64_t)r * dim + c0;
@@ -178,17 +314,26 @@ static inline int blocks_for_rows(int64_t n_rows, int max_blocks) {
 template <int VEC>
 static int launch_spmm(const int32_t* indptr, const int32_t* col, const int32_t* perm, const float* w,
                        const float* sscale, const float* dscale, int agg, const float* x, int n_rows,
-                       int dim, const int32_t* heavy, float* y, cudaStream_t st) {
+                       int dim, const int32_t* seg_ptr, float* partial, int64_t item_cap, float* y,
+                       cudaStream_t st) {
   const int per_lane = (dim + 32 * VEC - 1) / (32 * VEC);
   int nch = 1;
   while (nch < per_lane && nch < 8) nch <<= 1;
   const int tile = 32 * VEC * nch;
-  dim3 grid(blocks_for_rows(n_rows, BLISS_SM_COUNT * 16), (dim + tile - 1) / tile);
-  const size_t smem = heavy ? (size_t)8 * tile * sizeof(float) : 0;
-#define BLISS_SPMM_CASE(N)                                                                               \
-  case N:                                                                                                \
-    k_spmm<VEC, N><<<grid, 256, smem, st>>>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim,  \
-                                            heavy, y);                                                   \
+  const int64_t units = seg_ptr ? item_cap : n_rows;   // one warp per unit
+  dim3 grid(blocks_for_rows(units, BLISS_SM_COUNT * 8), (dim + tile - 1) / tile);
+  dim3 grid_c(blocks_for_rows(n_rows, BLISS_SM_COUNT * 8), (dim + tile - 1) / tile);
+  const size_t smem = seg_ptr ? (size_t)8 * tile * sizeof(float) : 0;
+#define BLISS_SPMM_CASE(N)                                                                                    \
+  case N:                                                                                                     \
+    if (seg_ptr) {                                                                                            \
+      k_spmm_seg<VEC, N><<<grid, 256, smem, st>>>(indptr, seg_ptr, col, perm, w, sscale, dscale, agg, x,     \
+                                                  n_rows, dim, partial, item_cap, y);                        \
+      k_spmm_combine<VEC, N><<<grid_c, 256, 0, st>>>(indptr, seg_ptr, dscale, agg, n_rows, dim, partial,     \
+                                                     item_cap, y);                                            \
+    } else {                                                                                                  \
+      k_spmm<VEC, N><<<grid, 256, 0, st>>>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, y);    \
+    }                                                                                                         \
     break;
   switch (nch) {
     BLISS_SPMM_CASE(1)
@@ -227,15 +372,18 @@ int bliss_row_norm(const float* x, int64_t n_rows, int32_t dim, float* out, void
 
 int bliss_spmm(const int32_t* indptr, const int32_t* col, const int32_t* perm, const float* w,
                const float* sscale, const float* dscale, int32_t agg, const float* x, int32_t n_rows,
-               int32_t dim, const int32_t* heavy, float* y, void* stream) {
+               int32_t dim, const int32_t* seg_ptr, float* partial, int64_t item_cap, float* y, void* stream) {
   if (n_rows < 0 || dim <= 0 || !indptr || !y) return -1;
   if (n_rows == 0) return 0;
   if (!col || !x) return -1;
+  if (seg_ptr && (!partial || item_cap <= 0)) return -1;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool al16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
-  if (dim % 4 == 0 && al16) return launch_spmm<4>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, heavy, y, st);
-  if (dim % 2 == 0) return launch_spmm<2>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, heavy, y, st);
-  return launch_spmm<1>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, heavy, y, st);
+  const bool al16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!seg_ptr || (uintptr_t)partial % 16 == 0);
+  if (dim % 4 == 0 && al16)
+    return launch_spmm<4>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, seg_ptr, partial, item_cap, y, st);
+  if (dim % 2 == 0)
+    return launch_spmm<2>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, seg_ptr, partial, item_cap, y, st);
+  return launch_spmm<1>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, seg_ptr, partial, item_cap, y, st);
 }
 
 }  // extern "C"

@@ -18,7 +18,7 @@
 #define BLISS_WARPS (BLISS_CTA / 32)
 #define BLISS_STAGE_CAP 6144                   // floats of a heavy row staged in shared memory (24 KB)
 #define BLISS_CHUNK 256                        // edges per warp-chunk of the probability passes
-#define BLISS_SPMM_HEAVY 64                     // block rows with more edges are aggregated by a whole CTA
+#define BLISS_SPMM_SEG 32                       // edges per warp-segment of the balanced SpMM (rows are cut into segments)
 
 #define BLISS_CHECK_LAUNCH()                      \
   do {                                            \

@@ -24,57 +24,74 @@ struct GraphView {
 };
 
 // ------------------------------------------------------------------------------------------
-// plan: register the seeds (candidate slots 0..n_s-1, local id = seed rank, P = 1, selected bit),
-// store every row's CSC start / degree, cut every row into 256-edge warp-chunks (prefix array
-// chunk_first) and reset the layer's counters.  One CTA, four rows per thread and iteration, so
-// a layer of up to 4096 seeds is one round of independent loads and one CTA scan.
+// plan, two launches: (a) k_plan_rows, one thread per seed over as many CTAs as needed — a single
+// SM retires about one scattered sector per cycle, so registering thousands of seeds from one CTA
+// costs more than the three probability passes of a small layer — registers the seed (candidate
+// slot = local id = seed rank, P = 1, selected bit), stores the row's CSC start / degree and its
+// number of 256-edge warp-chunks; (b) k_plan_scan, one CTA, turns the chunk counts into the prefix
+// array chunk_first and resets the layer's counters.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_frontier_plan(GraphView g, const int32_t* __restrict__ seeds,
-                                                       int n_seeds, bliss_workspace ws) {
-  __shared__ int s_scan[40];
-  __shared__ unsigned long long s_e[32];
-  bliss_counters* ctr = ws.ctr;
+__global__ void __launch_bounds__(256) k_plan_rows(GraphView g, const int32_t* __restrict__ seeds, int n_seeds,
+                                                  bliss_workspace ws) {
   // sync-free chaining of layers: the true seed count may live on the device (the previous
   // layer's n_src); the host value is then only the capacity
   if (ws.n_seeds_dev) n_seeds = min(n_seeds, *ws.n_seeds_dev);
-  constexpr int IT = 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_seeds) return;
+  const int s = seeds[i];
+  const long long a = g.indptr[s];
+  const int d = (int)min((long long)(g.indptr[s + 1] - a), (long long)INT_MAX);
+  ws.cand[i] = s;
+  *reinterpret_cast<int2*>(&ws.node_info[2 * s]) = make_int2(i, __float_as_int(1.0f));
+  atomicOr(&ws.sel_bits[s >> 5], 1u << (s & 31));
+  ws.row_a[i] = a;
+  ws.row_d[i] = d;
+  ws.row_cnt[i] = 0;
+  ws.chunk_first[i] = max(1, (d + BLISS_CHUNK - 1) / BLISS_CHUNK);
+}
+
+// 4 consecutive ints per thread; 128-bit accesses when the array allows it (warp-uniform test)
+__device__ __forceinline__ void load4(const int32_t* __restrict__ p, int i0, int n, int (&v)[4]) {
+  if (i0 + 3 < n && (((uintptr_t)p) & 15) == 0) {
+    const int4 t = *reinterpret_cast<const int4*>(p + i0);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (i0 + u < n) ? p[i0 + u] : 0;
+  }
+}
+__device__ __forceinline__ void store4(int32_t* __restrict__ p, int i0, int n, const int (&v)[4]) {
+  if (i0 + 3 < n && (((uintptr_t)p) & 15) == 0) {
+    *reinterpret_cast<int4*>(p + i0) = make_int4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u < n) p[i0 + u] = v[u];
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_plan_scan(int n_seeds, bliss_workspace ws) {
+  __shared__ int s_scan[40];
+  __shared__ unsigned long long s_e[32];
+  bliss_counters* ctr = ws.ctr;
+  if (ws.n_seeds_dev) n_seeds = min(n_seeds, *ws.n_seeds_dev);
   unsigned long long e_in = 0;
   int chunk_base = 0;
-  for (int b = 0; b < n_seeds; b += blockDim.x * IT) {
-    const int i0 = b + threadIdx.x * IT;
-    int s[IT], nch[IT], dd[IT], sum = 0;
-    long long a[IT];
-#pragma unroll
-    for (int u = 0; u < IT; ++u) s[u] = (i0 + u < n_seeds) ? seeds[i0 + u] : -1;
-#pragma unroll
-    for (int u = 0; u < IT; ++u) {
-      a[u] = 0;
-      long long d = 0;
-      if (s[u] >= 0) {
-        a[u] = g.indptr[s[u]];
-        d = g.indptr[s[u] + 1] - a[u];
-      }
-      dd[u] = (int)min(d, (long long)INT_MAX);
-      nch[u] = (s[u] >= 0) ? max(1, (dd[u] + BLISS_CHUNK - 1) / BLISS_CHUNK) : 0;
-      sum += nch[u];
-      e_in += (unsigned long long)d;
-    }
+  for (int b = 0; b < n_seeds; b += blockDim.x * 4) {
+    const int i0 = b + threadIdx.x * 4;
+    int nch[4], d[4], pre[4];
+    load4(ws.chunk_first, i0, n_seeds, nch);
+    load4(ws.row_d, i0, n_seeds, d);
+    const int sum = nch[0] + nch[1] + nch[2] + nch[3];
+    e_in += (unsigned long long)d[0] + d[1] + d[2] + d[3];
     int tc;
-    int pc = block_excl_scan(sum, s_scan, &tc);
+    int pc = chunk_base + block_excl_scan(sum, s_scan, &tc);
 #pragma unroll
-    for (int u = 0; u < IT; ++u) {
-      if (s[u] >= 0) {
-        const int i = i0 + u;
-        ws.cand[i] = s[u];
-        *reinterpret_cast<int2*>(&ws.node_info[2 * s[u]]) = make_int2(i, __float_as_int(1.0f));
-        atomicOr(&ws.sel_bits[s[u] >> 5], 1u << (s[u] & 31));
-        ws.row_a[i] = a[u];
-        ws.row_d[i] = dd[u];
-        ws.row_cnt[i] = 0;
-        ws.chunk_first[i] = chunk_base + pc;
-        pc += nch[u];
-      }
+    for (int u = 0; u < 4; ++u) {
+      pre[u] = pc;
+      pc += nch[u];
     }
+    store4(ws.chunk_first, i0, n_seeds, pre);
     chunk_base += tc;
   }
   e_in = block_sum(e_in, s_e);
@@ -750,78 +767,85 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_count(FillCtx c, bliss_w
 }
 
 // ------------------------------------------------------------------------------------------
-// (3b) block indptr (CTA 0) + local ids of the selected sources by first occurrence (all CTAs):
+// (3b) block indptr + SpMM segment prefix (CTA 0, one scan round per 4096 rows) while all CTAs
+//      copy the seeds' ids / probabilities, write the capacity padding and rank the selected
+//      sources by first occurrence:
 //      src order = [seeds in seed order] ++ [selected non-seeds by first occurrence]
-//      (compact_graphs / to_block ordering).  Rank by counting over smem tiles.
+//      (compact_graphs / to_block ordering).  Rank by counting: one warp per key,
+//      the keys of all selected sources pass through shared memory in tiles.
 // ------------------------------------------------------------------------------------------
 #define BLISS_RANK_TILE 2048
-__global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__ seeds, int n_seeds,
-                                                    bliss_workspace ws, bliss_block_out out) {
+__global__ void __launch_bounds__(1024) k_block_index(const int32_t* __restrict__ seeds, int n_seeds,
+                                                     bliss_workspace ws, bliss_block_out out) {
   n_seeds = ws.ctr->n_seeds;   // the plan's (possibly device-side) count, not the host capacity
   __shared__ unsigned long long s_keys[BLISS_RANK_TILE];
   __shared__ int s_scan[40];
   bliss_counters* ctr = ws.ctr;
   const int n_sel = min(ctr->n_sel, (int)ws.cap_sel);
+  const int lane = lane_id();
   if (blockIdx.x == 0) {
-    int base = 0, hbase = 0;
-    constexpr int IT = 8;   // rows per thread and iteration: few CTA-wide scans
-    for (int b = 0; b < n_seeds; b += blockDim.x * IT) {
-      const int i0 = b + threadIdx.x * IT;
-      int v[IT], hv[IT], vsum = 0, hsum = 0;
+    int base = 0, sbase = 0;
+    for (int b = 0; b < n_seeds; b += blockDim.x * 4) {
+      const int i0 = b + threadIdx.x * 4;
+      int v[4], sg[4], pre[4], spre[4];
+      load4(ws.row_cnt, i0, n_seeds, v);
+      int vsum = 0, ssum = 0;
 #pragma unroll
-      for (int u = 0; u < IT; ++u) {
-        v[u] = (i0 + u < n_seeds) ? ws.row_cnt[i0 + u] : 0;
-        hv[u] = v[u] > BLISS_SPMM_HEAVY;
+      for (int u = 0; u < 4; ++u) {
+        sg[u] = (i0 + u < n_seeds) ? max(1, (v[u] + BLISS_SPMM_SEG - 1) / BLISS_SPMM_SEG) : 0;
         vsum += v[u];
-        hsum += hv[u];
+        ssum += sg[u];
       }
-      int tot, ht = 0;
-      int p = block_excl_scan(vsum, s_scan, &tot);
-      int hp = out.heavy_rows ? block_excl_scan(hsum, s_scan, &ht) : 0;
+      int tot, st = 0;
+      int p = base + block_excl_scan(vsum, s_scan, &tot);
+      int sp = sbase + (out.seg_ptr ? block_excl_scan(ssum, s_scan, &st) : 0);
 #pragma unroll
-      for (int u = 0; u < IT; ++u) {
-        if (i0 + u < n_seeds) {
-          out.indptr[i0 + u] = base + p;
-          if (out.inv_deg) out.inv_deg[i0 + u] = 1.0f / (float)max(v[u], 1);   // fn.mean divisor
-          if (out.heavy_rows && hv[u]) out.heavy_rows[1 + hbase + hp] = i0 + u;   // rows the aggregation splits over a CTA
-        }
+      for (int u = 0; u < 4; ++u) {
+        pre[u] = p;
+        spre[u] = sp;
         p += v[u];
-        hp += hv[u];
+        sp += sg[u];
+      }
+      store4(out.indptr, i0, n_seeds, pre);
+      if (out.seg_ptr) store4(out.seg_ptr, i0, n_seeds, spre);
+      if (out.inv_deg) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pre[u] = __float_as_int(1.0f / (float)max(v[u], 1));   // fn.mean divisor
+        store4(reinterpret_cast<int32_t*>(out.inv_deg), i0, n_seeds, pre);
       }
       base += tot;
-      hbase += ht;
+      sbase += st;
     }
-    // capacity padding (static-shape replay): rows beyond n_seeds are empty, their mean divisor is 1
-    for (int64_t i = n_seeds + 1 + threadIdx.x; i <= out.pad_rows; i += blockDim.x) out.indptr[i] = base;
-    if (out.inv_deg)
-      for (int64_t i = n_seeds + threadIdx.x; i < out.pad_rows; i += blockDim.x) out.inv_deg[i] = 1.0f;
-    if (out.out_deg)   // padded sources have no edges (their counts feed the transpose scan)
-      for (int64_t i = n_seeds + n_sel + threadIdx.x; i < out.pad_src; i += blockDim.x) out.out_deg[i] = 0;
+    // capacity padding (static-shape replay): rows beyond n_seeds are empty (one empty segment each)
+    for (int64_t i = n_seeds + threadIdx.x; i <= max((int64_t)n_seeds, out.pad_rows); i += blockDim.x) {
+      out.indptr[i] = base;
+      if (out.seg_ptr) out.seg_ptr[i] = sbase + (int)(i - n_seeds);
+    }
     if (threadIdx.x == 0) {
-      if (out.heavy_rows) out.heavy_rows[0] = hbase;
-      out.indptr[n_seeds] = base;
       ctr->n_edges = base;
       ctr->n_src = n_seeds + n_sel;
       if (n_seeds + n_sel > out.cap_src) ctr->error |= BLISS_ERR_SEL_CAPACITY;
       if (base > out.cap_edges && out.cap_edges > 0) ctr->error |= BLISS_ERR_EDGE_CAPACITY;
     }
-    for (int i = threadIdx.x; i < n_seeds; i += blockDim.x) {
-      int s = seeds[i];
+  }
+  {  // all CTAs: the seeds' rows of the source arrays and the padding that does not depend on the scan
+    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gn = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = gt; i < n_seeds; i += gn) {
+      const int s = seeds[i];
       out.src_nid[i] = s;
       out.node_prob[i] = __int_as_float(ws.node_info[2 * s + 1]);
       if (out.out_deg) out.out_deg[i] = 0;
     }
-    __syncthreads();
+    if (out.inv_deg)   // the mean divisor of a padded row is 1
+      for (int64_t i = n_seeds + gt; i < out.pad_rows; i += gn) out.inv_deg[i] = 1.0f;
+    if (out.out_deg)   // padded sources have no edges (their counts feed the transpose scan)
+      for (int64_t i = n_seeds + n_sel + gt; i < out.pad_src; i += gn) out.out_deg[i] = 0;
   }
-  // ranking: 4 adjacent lanes share one key and each counts a quarter of every tile, so a CTA
-  // handles 64 keys and 4x more CTAs take part (the counting loop is the serial part)
-  constexpr int SUB = 4;
-  constexpr int PER_T = BLISS_RANK_TILE / 256;
-  const int keys_per_cta = blockDim.x / SUB;
-  const int n_chunks = (n_sel + keys_per_cta - 1) / keys_per_cta;
-  const int sub = threadIdx.x & (SUB - 1);
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int j = chunk * keys_per_cta + (threadIdx.x / SUB);
+  // ranking: one warp per key, 32 keys per CTA round; every lane counts 1/32 of each tile
+  constexpr int PER_T = BLISS_RANK_TILE / 1024;
+  const int n_groups = (n_sel + 31) / 32;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int j = grp * 32 + warp_id();
     const bool valid = j < n_sel;
     const int nid = valid ? ws.sel[j] : 0;
     const unsigned long long key = valid ? ws.first_pos[nid] : 0ull;
@@ -829,27 +853,26 @@ __global__ void __launch_bounds__(256) k_block_index(const int32_t* __restrict__
     for (int t0 = 0; t0 < n_sel; t0 += BLISS_RANK_TILE) {
       const int tn = min(BLISS_RANK_TILE, n_sel - t0);
       __syncthreads();
-      // the tile's keys are two dependent gathers (sel -> first_pos): all 8 per thread in flight together
+      // the tile's keys are two dependent gathers (sel -> first_pos): both per thread in flight together
       int tn_id[PER_T];
       unsigned long long tk[PER_T];
 #pragma unroll
       for (int u = 0; u < PER_T; ++u) {
-        const int t = threadIdx.x + u * 256;
+        const int t = threadIdx.x + u * 1024;
         tn_id[u] = (t < tn) ? ws.sel[t0 + t] : -1;
       }
 #pragma unroll
       for (int u = 0; u < PER_T; ++u) tk[u] = (tn_id[u] >= 0) ? ws.first_pos[tn_id[u]] : ~0ull;
 #pragma unroll
-      for (int u = 0; u < PER_T; ++u) s_keys[threadIdx.x + u * 256] = tk[u];
+      for (int u = 0; u < PER_T; ++u) s_keys[threadIdx.x + u * 1024] = tk[u];
       __syncthreads();
       if (valid) {
 #pragma unroll 8
-        for (int t = sub; t < tn; t += SUB) rank += (s_keys[t] < key);
+        for (int t = lane; t < tn; t += 32) rank += (s_keys[t] < key);
       }
     }
-    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
-    if (valid && sub == 0) {
+    rank = warp_sum(rank);
+    if (valid && lane == 0) {
       const int local = n_seeds + rank;
       ws.node_info[2 * nid] = local;
       if (local < out.cap_src) {
@@ -969,39 +992,41 @@ __global__ void k_t_count(const int32_t* __restrict__ edge_src, int64_t n_edges,
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += stride)
     atomicAdd(&cnt[edge_src[e]], 1);
 }
-// cnt_cursor holds the per-source counts on entry and the fill cursors (= row starts) on exit.
+// cnt_cursor holds the per-source counts on entry and the fill cursors (= row starts) on exit;
+// seg (may be NULL) receives the 32-edge segment prefix of the source rows (balanced SpMM).
 __global__ void __launch_bounds__(1024) k_t_scan(int32_t* cnt_cursor, int n, int32_t* __restrict__ indptr,
-                                                int32_t* __restrict__ heavy) {
+                                                int32_t* __restrict__ seg) {
   __shared__ int s_scan[40];
-  constexpr int IT = 8;   // rows per thread and iteration
-  int base = 0, hbase = 0;
-  for (int b = 0; b < n; b += blockDim.x * IT) {
-    const int i0 = b + threadIdx.x * IT;
-    int v[IT], vsum = 0, hsum = 0;
+  int base = 0, sbase = 0;
+  for (int b = 0; b < n; b += blockDim.x * 4) {
+    const int i0 = b + threadIdx.x * 4;
+    int v[4], pre[4], spre[4];
+    load4(cnt_cursor, i0, n, v);
+    int vsum = 0, ssum = 0;
 #pragma unroll
-    for (int u = 0; u < IT; ++u) {
-      v[u] = (i0 + u < n) ? cnt_cursor[i0 + u] : 0;
+    for (int u = 0; u < 4; ++u) {
       vsum += v[u];
-      hsum += v[u] > BLISS_SPMM_HEAVY;
+      ssum += (i0 + u < n) ? max(1, (v[u] + BLISS_SPMM_SEG - 1) / BLISS_SPMM_SEG) : 0;
     }
-    int tot, ht = 0;
-    int p = block_excl_scan(vsum, s_scan, &tot);
-    int hp = heavy ? block_excl_scan(hsum, s_scan, &ht) : 0;
+    int tot, st = 0;
+    int p = base + block_excl_scan(vsum, s_scan, &tot);
+    int sp = sbase + (seg ? block_excl_scan(ssum, s_scan, &st) : 0);
 #pragma unroll
-    for (int u = 0; u < IT; ++u) {
-      if (i0 + u < n) {
-        indptr[i0 + u] = base + p;
-        cnt_cursor[i0 + u] = base + p;
-        if (heavy && v[u] > BLISS_SPMM_HEAVY) heavy[1 + hbase + hp++] = i0 + u;
-      }
+    for (int u = 0; u < 4; ++u) {
+      pre[u] = p;
+      spre[u] = sp;
       p += v[u];
+      sp += max(1, (v[u] + BLISS_SPMM_SEG - 1) / BLISS_SPMM_SEG);
     }
+    store4(indptr, i0, n, pre);
+    store4(cnt_cursor, i0, n, pre);
+    if (seg) store4(seg, i0, n, spre);
     base += tot;
-    hbase += ht;
+    sbase += st;
   }
   if (threadIdx.x == 0) {
     indptr[n] = base;
-    if (heavy) heavy[0] = hbase;
+    if (seg) seg[n] = sbase;
   }
 }
 // Edges of a source land in arbitrary order inside its segment; k_t_sort restores ascending edge
@@ -1117,7 +1142,12 @@ int bliss_workspace_init(const bliss_workspace* ws, int64_t num_nodes, void* str
 int bliss_frontier_plan(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
                         const bliss_workspace* ws, void* stream) {
   if (!g || !seeds || !ws || n_seeds < 0 || n_seeds > ws->cap_seeds) return -1;
-  k_frontier_plan<<<1, 1024, 0, (cudaStream_t)stream>>>(view_of(g), seeds, n_seeds, *ws);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_seeds > 0) {
+    k_plan_rows<<<(n_seeds + 255) / 256, 256, 0, st>>>(view_of(g), seeds, n_seeds, *ws);
+    BLISS_CHECK_LAUNCH();
+  }
+  k_plan_scan<<<1, 1024, 0, st>>>(n_seeds, *ws);
   BLISS_CHECK_LAUNCH();
   return 0;
 }
@@ -1254,7 +1284,7 @@ int bliss_block_count(const bliss_graph* g, const int32_t* seeds, int32_t n_seed
 int bliss_block_index(const int32_t* seeds, int32_t n_seeds, const bliss_workspace* ws,
                       const bliss_block_out* out, void* stream) {
   if (!seeds || !ws || !out || !out->indptr || !out->src_nid || !out->node_prob) return -1;
-  k_block_index<<<BLISS_SM_COUNT, 256, 0, (cudaStream_t)stream>>>(seeds, n_seeds, *ws, *out);
+  k_block_index<<<BLISS_SM_COUNT, 1024, 0, (cudaStream_t)stream>>>(seeds, n_seeds, *ws, *out);
   BLISS_CHECK_LAUNCH();
   return 0;
 }
@@ -1286,7 +1316,7 @@ int bliss_block_finish(int32_t n_seeds, int32_t mode, const bliss_workspace* ws,
 
 int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                           int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor,
-                          int32_t* t_scratch, int32_t* t_dst, int32_t* t_perm, int32_t* t_heavy,
+                          int32_t* t_scratch, int32_t* t_dst, int32_t* t_perm, int32_t* t_seg_ptr,
                           int32_t have_counts, const int64_t* n_edges_dev, void* stream) {
   if (n_edges < 0 || n_src < 0 || !t_indptr || !t_cursor) return -1;
   if (n_edges > 0 && (!edge_src || !edge_dst || !t_scratch || !t_dst || !t_perm)) return -1;
@@ -1300,7 +1330,7 @@ int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int6
       BLISS_CHECK_LAUNCH();
     }
   }
-  k_t_scan<<<1, 1024, 0, st>>>(t_cursor, n_src, t_indptr, t_heavy);
+  k_t_scan<<<1, 1024, 0, st>>>(t_cursor, n_src, t_indptr, t_seg_ptr);
   BLISS_CHECK_LAUNCH();
   if (n_edges == 0) return 0;
   k_t_fill<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, n_edges_dev, t_cursor, t_scratch);

@@ -289,6 +289,9 @@ class _WholeGraphBlock:
         self._n = n
         self.srcdata, self.dstdata, self.edata = {}, {}, {}
         self._transpose = None
+        # 32-edge row segments for the balanced SpMM (hub columns of a power-law graph hold 10^4 edges)
+        segs = ((g.in_degrees().long() + ops.SPMM_SEG - 1) // ops.SPMM_SEG).clamp(min=1)
+        self.seg_ptr = torch.cat([segs.new_zeros(1), segs.cumsum(0)]).to(torch.int32)
 
     def num_src_nodes(self):
         return self._n

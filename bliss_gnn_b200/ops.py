@@ -53,8 +53,9 @@ def block_transpose_into(block, pool):
     E, n_dst = block.num_edges(), block.num_dst_nodes()
     N.call("bliss_block_transpose", N.ptr(block.edge_src), N.ptr(block.edge_dst), E, pool.cap_src, n_dst,
            N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_scratch), N.ptr(pool.t_dst), N.ptr(pool.t_perm),
-           N.ptr(pool.t_heavy), 1, None, N.stream())    # counts were accumulated by the fill kernel (out_deg)
-    block._transpose = (pool.t_indptr[:block.num_src_nodes() + 1], pool.t_dst[:E], pool.t_perm[:E], pool.t_heavy)
+           N.ptr(pool.t_seg_ptr), 1, None, N.stream())    # counts were accumulated by the fill kernel (out_deg)
+    block._transpose = (pool.t_indptr[:block.num_src_nodes() + 1], pool.t_dst[:E], pool.t_perm[:E],
+                        pool.t_seg_ptr[:block.num_src_nodes() + 1])
 
 
 def block_transpose(block):
@@ -67,19 +68,47 @@ def block_transpose(block):
         t_scratch = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         t_dst = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         t_perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
-        t_heavy = torch.empty(n_src + 1, dtype=torch.int32, device=dev)
+        t_seg = torch.empty(n_src + 1, dtype=torch.int32, device=dev)
         N.call("bliss_block_transpose", N.ptr(block.edge_src), N.ptr(block.edge_dst), E, n_src, n_dst,
-               N.ptr(t_indptr), N.ptr(t_cursor), N.ptr(t_scratch), N.ptr(t_dst), N.ptr(t_perm), N.ptr(t_heavy),
+               N.ptr(t_indptr), N.ptr(t_cursor), N.ptr(t_scratch), N.ptr(t_dst), N.ptr(t_perm), N.ptr(t_seg),
                0, None, N.stream())
-        block._transpose = (t_indptr, t_dst[:E], t_perm[:E], t_heavy)
+        block._transpose = (t_indptr, t_dst[:E], t_perm[:E], t_seg)
     return block._transpose
 
 
-def _spmm_raw(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, heavy=None):
+SPMM_SEG = 32   # csrc/common.cuh BLISS_SPMM_SEG
+
+
+def _spmm_tiling(d: int):
+    """(padded row width of the partial-sum scratch, number of column tiles) that covers whichever vector
+    width ``bliss_spmm`` picks (``launch_spmm`` in csrc/aggregate.cu: tile = 32 * VEC * NCH, NCH <= 8)."""
+    width, tiles = 0, 0
+    for vec in (4, 2, 1):
+        if d % vec:
+            continue
+        per_lane = -(-d // (32 * vec))
+        nch = 1
+        while nch < per_lane and nch < 8:
+            nch *= 2
+        tile = 32 * vec * nch
+        n = -(-d // tile)
+        width, tiles = max(width, n * tile), max(tiles, n)
+    return width, tiles
+
+
+def _spmm_raw(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, seg_ptr=None):
+    """One ``bliss_spmm`` call.  With ``seg_ptr`` (sampled blocks) rows are cut into 32-edge segments, one
+    warp each, 8 consecutive segments per CTA; rows that span several CTAs combine their partials through
+    a scratch buffer sized from the host-side bound edges/32 + rows (no sync)."""
     d = x.shape[1]
     y = torch.empty((n_rows, d), dtype=torch.float32, device=x.device)
+    partial, item_cap = None, 0
+    if seg_ptr is not None:
+        width, _ = _spmm_tiling(d)
+        item_cap = int(col.numel()) // SPMM_SEG + n_rows + 1
+        partial = torch.empty(item_cap * width, dtype=torch.float32, device=x.device)
     N.call("bliss_spmm", N.ptr(indptr), N.ptr(col), N.ptr(perm), N.ptr(w), N.ptr(sscale), N.ptr(dscale),
-           agg, N.ptr(x), n_rows, d, N.ptr(heavy), N.ptr(y), N.stream())
+           agg, N.ptr(x), n_rows, d, N.ptr(seg_ptr), N.ptr(partial), item_cap, N.ptr(y), N.stream())
     return y
 
 
@@ -89,16 +118,16 @@ class _SpMM(torch.autograd.Function):
         x = _req(x, name="x")
         ctx.block, ctx.w, ctx.sscale, ctx.dscale = block, w, sscale, dscale
         return _spmm_raw(block.indptr, block.edge_src, None, w, sscale, dscale, N.AGG_SUM, x,
-                         block.num_dst_nodes(), getattr(block, "heavy_rows", None))
+                         block.num_dst_nodes(), getattr(block, "seg_ptr", None))
 
     @staticmethod
     def backward(ctx, gy):
         block = ctx.block
-        t_indptr, t_dst, t_perm, t_heavy = block_transpose(block)
+        t_indptr, t_dst, t_perm, t_seg = block_transpose(block)
         gy = _req(gy, name="grad")
         # dx_c = sscale_c * Σ_{e: src_e = c} w_e * dscale_{dst_e} * dy_{dst_e}
         gx = _spmm_raw(t_indptr, t_dst, t_perm, ctx.w, ctx.dscale, ctx.sscale, N.AGG_SUM, gy,
-                       block.num_src_nodes(), t_heavy)
+                       block.num_src_nodes(), t_seg)
         return gx, None, None, None, None
 
 

@@ -130,7 +130,7 @@ class LayerPool:
         i32 = dict(dtype=torch.int32, device=device)
         self.meta = torch.zeros(3 * (self.cap_dst + 1), **i32)
         n = self.cap_dst + 1
-        self.indptr, self.heavy = self.meta[:n], self.meta[n:2 * n]
+        self.indptr, self.seg_ptr = self.meta[:n], self.meta[n:2 * n]
         self.inv_deg = self.meta[2 * n:].view(torch.float32)[:self.cap_dst]
         self.inv_deg.fill_(1.0)
         self.e32 = torch.zeros((5, self.cap_edges), **i32)
@@ -145,7 +145,7 @@ class LayerPool:
         self.t_scratch = torch.zeros(self.cap_edges, **i32)
         self.t_dst = torch.zeros(self.cap_edges, **i32)
         self.t_perm = torch.zeros(self.cap_edges, **i32)
-        self.t_heavy = torch.zeros(self.cap_src + 1, **i32)
+        self.t_seg_ptr = torch.zeros(self.cap_src + 1, **i32)
         self.padded = None      # the capacity-sized Block the captured graph runs on
 
     def fits(self, n_dst, n_src, n_edges) -> bool:
@@ -324,7 +324,7 @@ class BanditLadiesSampler:
         return self._finish_block(fr, out, bufs)
 
     def _block_out(self, fr: Frontier, pool: Optional[LayerPool] = None):
-        """Output descriptor of one layer: indptr / heavy list / mean divisor are sized by the seeds,
+        """Output descriptor of one layer: indptr / SpMM segment prefix / mean divisor are sized by the seeds,
         source arrays go to |V|-sized scratch until the counts are known.  With a :class:`LayerPool`
         the arrays are the pool's persistent capacity buffers and indptr is padded to the capacity."""
         wsp, dev, n_s = fr.wsp, fr.g.device, fr.n_seeds
@@ -332,19 +332,19 @@ class BanditLadiesSampler:
             # out_deg -> the pool's transpose cursor: the fill kernel counts every source's block edges,
             # so the transpose starts from its scan (no separate count pass)
             out = N.BlockOut(indptr=N.ptr(pool.indptr), src_nid=N.ptr(wsp.src_nid), node_prob=N.ptr(wsp.node_prob),
-                             heavy_rows=N.ptr(pool.heavy), inv_deg=N.ptr(pool.inv_deg), out_deg=N.ptr(pool.t_cursor),
+                             seg_ptr=N.ptr(pool.seg_ptr), inv_deg=N.ptr(pool.inv_deg), out_deg=N.ptr(pool.t_cursor),
                              cap_edges=0, cap_src=fr.g.num_nodes(), pad_src=pool.cap_src, pad_rows=pool.cap_dst)
-            return out, (pool.indptr[:n_s + 1], pool.heavy, pool.inv_deg[:n_s])
-        meta = torch.empty(3 * (n_s + 1), dtype=torch.int32, device=dev)   # indptr | heavy | inv_deg (as f32)
-        indptr, heavy, inv_deg = meta[:n_s + 1], meta[n_s + 1:2 * (n_s + 1)], meta[2 * (n_s + 1):].view(torch.float32)
+            return out, (pool.indptr[:n_s + 1], pool.seg_ptr[:n_s + 1], pool.inv_deg[:n_s])
+        meta = torch.empty(3 * (n_s + 1), dtype=torch.int32, device=dev)   # indptr | seg_ptr | inv_deg (as f32)
+        indptr, seg_ptr, inv_deg = meta[:n_s + 1], meta[n_s + 1:2 * (n_s + 1)], meta[2 * (n_s + 1):].view(torch.float32)
         out = N.BlockOut(indptr=N.ptr(indptr), src_nid=N.ptr(wsp.src_nid), node_prob=N.ptr(wsp.node_prob),
-                         heavy_rows=N.ptr(heavy), inv_deg=N.ptr(inv_deg), cap_edges=0, cap_src=fr.g.num_nodes())
-        return out, (indptr, heavy, inv_deg[:n_s])
+                         seg_ptr=N.ptr(seg_ptr), inv_deg=N.ptr(inv_deg), cap_edges=0, cap_src=fr.g.num_nodes())
+        return out, (indptr, seg_ptr, inv_deg[:n_s])
 
     def _finish_block(self, fr: Frontier, out, bufs, pool: Optional[LayerPool] = None):
         """Read the layer's counters (the one host sync), size the edge arrays, fill + finish."""
         wsp, g, dev, n_s = fr.wsp, fr.g, fr.g.device, fr.n_seeds
-        indptr, heavy, inv_deg = bufs
+        indptr, seg_ptr, inv_deg = bufs
         ctr = wsp.read_counters()
         if ctr.error:
             raise RuntimeError(f"BLISS sampler capacity error {ctr.error} in layer {fr.layer}")
@@ -357,7 +357,7 @@ class BanditLadiesSampler:
             self.pool_overflow = True          # the caller grows the pool and re-captures
             out.out_deg = None
             if out.pad_rows > 0:               # indptr lives in the pool but the block does not fit: detach it
-                indptr, heavy, inv_deg = indptr.clone(), heavy[:n_s + 1].clone(), inv_deg.clone()
+                indptr, seg_ptr, inv_deg = indptr.clone(), seg_ptr[:n_s + 1].clone(), inv_deg.clone()
         # one allocation for the 4-byte edge arrays, one for the 8-byte CSC positions
         if pooled:
             e32, csc_pos = pool.e32, pool.csc_pos[:E]
@@ -381,7 +381,7 @@ class BanditLadiesSampler:
         src_nid.copy_(wsp.src_nid[:n_src])
         node_prob.copy_(wsp.node_prob[:n_src])
         block = Block(indptr, edge_src, edge_dst, src_nid, fr.seeds, graph=g, csc_pos=csc_pos)
-        block.heavy_rows = heavy
+        block.seg_ptr = seg_ptr
         block._mean_scale = inv_deg
         block.edata[EID] = eid                                                   # :337
         block.edata[self.output_weight] = edge_w                                 # :324
@@ -475,7 +475,7 @@ class BanditLadiesSampler:
             out = N.BlockOut(indptr=N.ptr(pool.indptr), edge_src=N.ptr(e32[0]), edge_dst=N.ptr(e32[1]),
                              csc_pos=N.ptr(pool.csc_pos), eid=N.ptr(e32[2]), q_ij=N.ptr(e32[4]) if bandit else None,
                              edge_w=N.ptr(e32[3]), src_nid=N.ptr(pool.src_nid), node_prob=N.ptr(pool.node_prob),
-                             out_deg=N.ptr(pool.t_cursor), heavy_rows=N.ptr(pool.heavy), inv_deg=N.ptr(pool.inv_deg),
+                             out_deg=N.ptr(pool.t_cursor), seg_ptr=N.ptr(pool.seg_ptr), inv_deg=N.ptr(pool.inv_deg),
                              cap_edges=pool.cap_edges, cap_src=pool.cap_src, pad_src=pool.cap_src,
                              pad_rows=pool.cap_dst)
             st = N.stream()
@@ -486,7 +486,7 @@ class BanditLadiesSampler:
                    self._mode, C.byref(ws), C.byref(out), st)
             N.call("bliss_block_transpose", N.ptr(e32[0]), N.ptr(e32[1]), pool.cap_edges, pool.cap_src, pool.cap_dst,
                    N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_scratch), N.ptr(pool.t_dst),
-                   N.ptr(pool.t_perm), N.ptr(pool.t_heavy), 1, wsp.counter_ptr(block_id, "n_edges"), st)
+                   N.ptr(pool.t_perm), N.ptr(pool.t_seg_ptr), 1, wsp.counter_ptr(block_id, "n_edges"), st)
 
     # ---- bandit update ------------------------------------------------------------------------
     def calculate_alpha(self, mfg):

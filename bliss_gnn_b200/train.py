@@ -250,9 +250,9 @@ class Trainer:
             pool = pools[l]
             dst_nid = pools[l + 1].src_nid if l < L - 1 else self._seeds_static
             pb = Block(pool.indptr, pool.e32[0], pool.e32[1], pool.src_nid, dst_nid, graph=g, csc_pos=pool.csc_pos)
-            pb.heavy_rows, pb._mean_scale, pb._static_padded = pool.heavy, pool.inv_deg, True
+            pb.seg_ptr, pb._mean_scale, pb._static_padded = pool.seg_ptr, pool.inv_deg, True
             pb.edata["edge_weights"] = pool.e32[3].view(torch.float32)
-            pb._transpose = (pool.t_indptr, pool.t_dst, pool.t_perm, pool.t_heavy)
+            pb._transpose = (pool.t_indptr, pool.t_dst, pool.t_perm, pool.t_seg_ptr)
             pool.padded = pb
             padded.append(pb)
         self._pools, self._padded, self._graph = pools, padded, None

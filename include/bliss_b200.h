@@ -111,7 +111,8 @@ typedef struct bliss_block_out {
   int32_t* src_nid;     /* [n_src] global id of each block source                         */
   float*   node_prob;   /* [n_src] inclusion probability P (bandit_sampler.py:328)        */
   int32_t* out_deg;     /* [n_src] block out-degree of each source (NULL to skip)         */
-  int32_t* heavy_rows;  /* [n_seeds+1] [0]=count, then destinations with > 64 edges (NULL ok)  */
+  int32_t* seg_ptr;     /* [n_seeds+1] prefix of max(1, ceil(in-degree/32)): the 32-edge row segments the
+                           balanced SpMM works on (padded rows count one segment each; NULL ok)       */
   float*   inv_deg;     /* [n_seeds] 1 / max(block in-degree, 1)  (fn.mean divisor; NULL ok)  */
   int64_t  cap_edges;
   int64_t  cap_src;
@@ -180,7 +181,7 @@ int bliss_sample_layer_back(const bliss_graph* g, const int32_t* seeds, int32_t 
 int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                           int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor /* [n_src] */,
                           int32_t* t_scratch /* [E] */, int32_t* t_dst, int32_t* t_perm,
-                          int32_t* t_heavy /* [n_src+1] heavy source rows, [0]=count; may be NULL */,
+                          int32_t* t_seg_ptr /* [n_src+1] 32-edge segment prefix of the source rows; may be NULL */,
                           int32_t have_counts /* t_cursor already holds out-degrees (block_out.out_deg) */,
                           const int64_t* n_edges_dev /* true edge count on the device, or NULL */,
                           void* stream);
@@ -192,11 +193,16 @@ int bliss_gather_rows(const float* table, const int32_t* nid, int64_t n_rows, in
                       float* out, float* row_norm /* may be NULL */, void* stream);
 int bliss_row_norm(const float* x, int64_t n_rows, int32_t dim, float* out, void* stream);
 /* y[i,:] = dscale_i * sum_{e in row i} w[perm? perm[e] : e] * sscale[col[e]] * x[col[e], :]
- * heavy (may be NULL): [0] = count, then the rows with > 64 edges — those are split over the 8
- * warps of a CTA and combined in shared memory in a fixed order; the rest is warp-per-row. */
+ * seg_ptr == NULL: one warp per row (whole-graph inference over short rows).
+ * seg_ptr != NULL: [n_rows+1] prefix of max(1, ceil(len/32)) — rows are cut into 32-edge segments, a
+ * CTA takes 8 consecutive segments (one per warp) and adds the runs that belong to one row in shared
+ * memory; rows that span several CTAs get one partial per run and a second launch adds them in order
+ * (deterministic, no atomics).  partial = scratch of item_cap * ceil(dim/tile)*tile floats
+ * (item_cap >= seg_ptr[n_rows]; tile = the column tile, <= 1024). */
 int bliss_spmm(const int32_t* indptr, const int32_t* col, const int32_t* perm, const float* w,
                const float* sscale, const float* dscale, int32_t agg, const float* x,
-               int32_t n_rows, int32_t dim, const int32_t* heavy, float* y, void* stream);
+               int32_t n_rows, int32_t dim, const int32_t* seg_ptr, float* partial, int64_t item_cap,
+               float* y, void* stream);
 int bliss_gatv2_fwd(const int32_t* indptr, const int32_t* col, const float* feat /* [n_src,H,D] */,
                     const float* attn /* [H,D] */, const float* drop_mask /* [E,H] or NULL */,
                     float negative_slope, int32_t n_dst, int32_t heads, int32_t dim,

@@ -34,7 +34,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 ev.sort(key=lambda e: e.time_range.start)
 # split into steps at k_frontier_plan triples: a step starts at every third plan kernel
-starts = [i for i, e in enumerate(ev) if "k_frontier_plan" in e.name]
+starts = [i for i, e in enumerate(ev) if "k_plan_rows" in e.name]
 with open(out_path, "w") as f:
     if len(starts) >= 6:
         a, b = starts[-6], starts[-3]

@@ -60,7 +60,8 @@ int main(void) {
 
 def test_bad_arguments_are_rejected_without_a_gpu(native_lib):
     assert native_lib.bliss_philox_fill(0, 0, 0, None, -1, None, None) < 0
-    assert native_lib.bliss_spmm(None, None, None, None, None, None, 0, None, -1, 8, None, None, None) < 0
+    assert native_lib.bliss_spmm(None, None, None, None, None, None, 0, None, -1, 8, None, None, 0, None, None) < 0
+    assert native_lib.bliss_adam_step(None, None, None, None, 4, None, 0.9, 0.999, 1e-8, None, 1, None) < 0
     assert native_lib.bliss_gather_rows(None, None, 4, 8, None, None, None) < 0
 
 
