@@ -92,6 +92,7 @@ class BlockOut(C.Structure):
     _fields_ = [("indptr", C.c_void_p), ("edge_src", C.c_void_p), ("edge_dst", C.c_void_p),
                 ("csc_pos", C.c_void_p), ("eid", C.c_void_p), ("q_ij", C.c_void_p), ("edge_w", C.c_void_p),
                 ("src_nid", C.c_void_p), ("node_prob", C.c_void_p), ("out_deg", C.c_void_p),
+                ("t_bits", C.c_void_p), ("t_words", C.c_int64),
                 ("seg_ptr", C.c_void_p), ("inv_deg", C.c_void_p), ("cap_edges", C.c_int64), ("cap_src", C.c_int64), ("pad_src", C.c_int64), ("pad_rows", C.c_int64)]
 
 
@@ -115,7 +116,7 @@ PROTOTYPES = {
     "bliss_block_finish": [_I32, _I32, _WP, _BP, _P],
     "bliss_sample_layer_front": [_GP, _P, _I32, _P, _F, _I32, _I32, _D, _I32, _U64, _U64, _U32, _P, _P, _WP, _BP, _P],
     "bliss_sample_layer_back": [_GP, _P, _I32, _P, _F, _I32, _WP, _BP, _P],
-    "bliss_block_transpose": [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P],
+    "bliss_block_transpose": [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _P, _P],
     "bliss_gather_rows": [_P, _P, _I64, _I32, _P, _P, _P],
     "bliss_row_norm": [_P, _I64, _I32, _P, _P],
     "bliss_spmm": [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P, _I64, _P, _P],

@@ -840,6 +840,11 @@ __global__ void __launch_bounds__(1024) k_block_index(const int32_t* __restrict_
       for (int64_t i = n_seeds + gt; i < out.pad_rows; i += gn) out.inv_deg[i] = 1.0f;
     if (out.out_deg)   // padded sources have no edges (their counts feed the transpose scan)
       for (int64_t i = n_seeds + n_sel + gt; i < out.pad_src; i += gn) out.out_deg[i] = 0;
+    if (out.t_bits) {  // source x destination bitmap of the block (transpose): clear this block's source rows
+      // (whole rows: an earlier, larger block may have left bits beyond this block's destinations)
+      const int64_t rows = min((int64_t)n_seeds + n_sel, out.pad_src > 0 ? out.pad_src : out.cap_src);
+      for (int64_t i = gt; i < rows * out.t_words; i += gn) out.t_bits[i] = 0u;
+    }
   }
   // ranking: one warp per key, 32 keys per CTA round; every lane counts 1/32 of each tile
   constexpr int PER_T = BLISS_RANK_TILE / 1024;
@@ -945,6 +950,7 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_fill(FillCtx c, bliss_wo
       if (out.q_ij) out.q_ij[slot] = qv;
       out.edge_w[slot] = wt;
       if (out.out_deg) atomicAdd(&out.out_deg[info.x], 1);
+      if (out.t_bits) atomicOr(&out.t_bits[(int64_t)info.x * out.t_words + (r.row >> 5)], 1u << (r.row & 31));
     }
     __syncwarp();
   }
@@ -1029,71 +1035,63 @@ __global__ void __launch_bounds__(1024) k_t_scan(int32_t* cnt_cursor, int n, int
     if (seg) seg[n] = sbase;
   }
 }
-// Edges of a source land in arbitrary order inside its segment; k_t_sort restores ascending edge
-// id so the backward sums are run-to-run deterministic.
-__global__ void k_t_fill(const int32_t* __restrict__ edge_src, int64_t n_edges, const int64_t* __restrict__ n_edges_dev,
-                         int32_t* __restrict__ cursor, int32_t* __restrict__ t_perm) {
-  if (n_edges_dev) n_edges = min(n_edges, *n_edges_dev);
+// The transpose is driven by a source x destination bitmap of the block (bits[s][d]: edge s->d is in
+// the block; a block is a simple graph, so a bit is an edge).  A source's row of the transpose is
+// its set bits in ascending destination = ascending edge id (block edges are destination-major), so
+// the backward sums are deterministic without a sort and without returning atomics:
+//   k_t_mark   bits[src_e][dst_e] = 1                      (eager path; the pooled path marks in k_block_fill)
+//   k_t_rows   per source: word prefix popcounts -> pre[s][w], and t_dst[t_indptr[s] + k] = k-th set bit
+//   k_t_place  per edge:   t_perm[t_indptr[s] + pre[s][d/32] + popc(bits[s][d/32] below d)] = e
+__global__ void k_t_mark(const int32_t* __restrict__ edge_src, const int32_t* __restrict__ edge_dst, int64_t n_edges,
+                         uint32_t* __restrict__ bits, int64_t t_words) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += stride) {
-    int slot = atomicAdd(&cursor[edge_src[e]], 1);
-    t_perm[slot] = (int32_t)e;
+    const int d = edge_dst[e];
+    atomicOr(&bits[(int64_t)edge_src[e] * t_words + (d >> 5)], 1u << (d & 31));
   }
 }
-// Warp per source row: the edges of one source go to distinct destinations and edge ids grow
-// with the destination (block edges are destination-major), so ascending edge id == ascending
-// destination.  Each warp builds a bitmap of the row's destinations in shared memory; the rank
-// of an edge is the number of set bits below its destination.  O(len + n_dst/32) per row.
-__global__ void __launch_bounds__(256) k_t_sort(const int32_t* __restrict__ t_indptr, int n_src, int n_words,
-                                               const int32_t* __restrict__ edge_dst,
-                                               const int32_t* __restrict__ perm_in,
-                                               int32_t* __restrict__ t_perm, int32_t* __restrict__ t_dst) {
-  extern __shared__ unsigned s_bits[];  // per warp: n_words bitmap + n_words prefix
-  unsigned* bits = s_bits + (size_t)warp_id() * 2 * n_words;
-  unsigned* pre = bits + n_words;
+__global__ void __launch_bounds__(256) k_t_rows(const int32_t* __restrict__ t_indptr, int n_src, int n_words,
+                                               const uint32_t* __restrict__ bits, int64_t t_words,
+                                               int32_t* __restrict__ pre, int32_t* __restrict__ t_dst) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int lane = lane_id();
-  for (int r = warp; r < n_src; r += nwarps) {
-    const int a = t_indptr[r], b = t_indptr[r + 1];
-    if (b - a == 1) {
-      if (lane == 0) {
-        int e = perm_in[a];
-        t_perm[a] = e;
-        t_dst[a] = edge_dst[e];
-      }
-      continue;
-    }
-    if (b == a) continue;
-    for (int w = lane; w < n_words; w += 32) bits[w] = 0u;
-    __syncwarp();
-    for (int k = a + lane; k < b; k += 32) {
-      int dst = edge_dst[perm_in[k]];
-      atomicOr(&bits[dst >> 5], 1u << (dst & 31));
-    }
-    __syncwarp();
-    int base = 0;
+  for (int s = warp; s < n_src; s += nwarps) {
+    const int a = t_indptr[s], b = t_indptr[s + 1];
+    if (a == b) continue;   // no edges: nothing reads this row's prefix
+    int base = a;
     for (int w0 = 0; w0 < n_words; w0 += 32) {
-      int w = w0 + lane;
-      int c = (w < n_words) ? __popc(bits[w]) : 0;
+      const int w = w0 + lane;
+      unsigned word = (w < n_words) ? bits[(int64_t)s * t_words + w] : 0u;
+      const int c = __popc(word);
       int incl = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
       }
-      if (w < n_words) pre[w] = base + incl - c;
+      int k = base + incl - c;
+      if (w < n_words) pre[(int64_t)s * t_words + w] = k - a;
+      while (word) {   // this lane's destinations, ascending
+        const int bit = __ffs(word) - 1;
+        word &= word - 1;
+        t_dst[k++] = (w << 5) + bit;
+      }
       base += __shfl_sync(0xffffffffu, incl, 31);
     }
-    __syncwarp();
-    for (int k = a + lane; k < b; k += 32) {
-      int e = perm_in[k];
-      int dst = edge_dst[e];
-      int rank = pre[dst >> 5] + __popc(bits[dst >> 5] & ((1u << (dst & 31)) - 1u));
-      t_perm[a + rank] = e;
-      t_dst[a + rank] = dst;
-    }
-    __syncwarp();
+  }
+}
+__global__ void k_t_place(const int32_t* __restrict__ edge_src, const int32_t* __restrict__ edge_dst, int64_t n_edges,
+                          const int64_t* __restrict__ n_edges_dev, const int32_t* __restrict__ t_indptr,
+                          const uint32_t* __restrict__ bits, const int32_t* __restrict__ pre, int64_t t_words,
+                          int32_t* __restrict__ t_perm) {
+  if (n_edges_dev) n_edges = min(n_edges, *n_edges_dev);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += stride) {
+    const int s = edge_src[e], d = edge_dst[e];
+    const int64_t wi = (int64_t)s * t_words + (d >> 5);
+    const int slot = t_indptr[s] + pre[wi] + __popc(bits[wi] & ((1u << (d & 31)) - 1u));
+    t_perm[slot] = (int32_t)e;
   }
 }
 
@@ -1316,34 +1314,34 @@ int bliss_block_finish(int32_t n_seeds, int32_t mode, const bliss_workspace* ws,
 
 int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                           int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor,
-                          int32_t* t_scratch, int32_t* t_dst, int32_t* t_perm, int32_t* t_seg_ptr,
-                          int32_t have_counts, const int64_t* n_edges_dev, void* stream) {
+                          uint32_t* t_bits, int32_t* t_pre, int64_t t_words, int32_t* t_dst, int32_t* t_perm,
+                          int32_t* t_seg_ptr, int32_t have_counts, const int64_t* n_edges_dev, void* stream) {
   if (n_edges < 0 || n_src < 0 || !t_indptr || !t_cursor) return -1;
-  if (n_edges > 0 && (!edge_src || !edge_dst || !t_scratch || !t_dst || !t_perm)) return -1;
+  if (n_edges > 0 && (!edge_src || !edge_dst || !t_bits || !t_pre || !t_dst || !t_perm)) return -1;
+  if (n_edges > 0 && t_words < (n_dst + 31) / 32) return -1;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-  if (!have_counts) {   // otherwise t_cursor already holds the per-source counts (bliss_block_out.out_deg)
+  if (!have_counts) {   // otherwise the block fill already counted (bliss_block_out.out_deg) and marked (t_bits)
     e = cudaMemsetAsync(t_cursor, 0, sizeof(int32_t) * (size_t)(n_src > 0 ? n_src : 1), st);
     if (e != cudaSuccess) return (int)e;
     if (n_edges > 0) {
+      e = cudaMemsetAsync(t_bits, 0, sizeof(uint32_t) * (size_t)n_src * (size_t)t_words, st);
+      if (e != cudaSuccess) return (int)e;
       k_t_count<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, t_cursor);
+      BLISS_CHECK_LAUNCH();
+      k_t_mark<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, edge_dst, n_edges, t_bits, t_words);
       BLISS_CHECK_LAUNCH();
     }
   }
   k_t_scan<<<1, 1024, 0, st>>>(t_cursor, n_src, t_indptr, t_seg_ptr);
   BLISS_CHECK_LAUNCH();
   if (n_edges == 0) return 0;
-  k_t_fill<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, n_edges_dev, t_cursor, t_scratch);
-  BLISS_CHECK_LAUNCH();
   const int n_words = (n_dst + 31) / 32;
-  const size_t smem = (size_t)BLISS_WARPS * 2 * n_words * sizeof(unsigned);
-  if (smem > 200 * 1024) return -2;  // n_dst > ~100K destinations per block: not supported
-  if (smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(k_t_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-  }
-  k_t_sort<<<grid_for((int64_t)n_src * 32, 256, BLISS_SM_COUNT * 4), 256, smem, st>>>(t_indptr, n_src, n_words, edge_dst,
-                                                                                  t_scratch, t_perm, t_dst);
+  k_t_rows<<<grid_for((int64_t)n_src * 32, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(t_indptr, n_src, n_words, t_bits, t_words,
+                                                                              t_pre, t_dst);
+  BLISS_CHECK_LAUNCH();
+  k_t_place<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, edge_dst, n_edges, n_edges_dev, t_indptr,
+                                                                   t_bits, t_pre, t_words, t_perm);
   BLISS_CHECK_LAUNCH();
   return 0;
 }

@@ -52,7 +52,8 @@ def block_transpose_into(block, pool):
     scan over ``cap_src`` rows leaves the padded source rows empty (t_indptr tail = E_b)."""
     E, n_dst = block.num_edges(), block.num_dst_nodes()
     N.call("bliss_block_transpose", N.ptr(block.edge_src), N.ptr(block.edge_dst), E, pool.cap_src, n_dst,
-           N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_scratch), N.ptr(pool.t_dst), N.ptr(pool.t_perm),
+           N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_bits), N.ptr(pool.t_pre), pool.t_words,
+           N.ptr(pool.t_dst), N.ptr(pool.t_perm),
            N.ptr(pool.t_seg_ptr), 1, None, N.stream())    # counts were accumulated by the fill kernel (out_deg)
     block._transpose = (pool.t_indptr[:block.num_src_nodes() + 1], pool.t_dst[:E], pool.t_perm[:E],
                         pool.t_seg_ptr[:block.num_src_nodes() + 1])
@@ -65,12 +66,15 @@ def block_transpose(block):
         dev = block.device
         t_indptr = torch.empty(n_src + 1, dtype=torch.int32, device=dev)
         t_cursor = torch.empty(max(n_src, 1), dtype=torch.int32, device=dev)
-        t_scratch = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        t_words = (n_dst + 31) // 32
+        t_bits = torch.empty(max(n_src * t_words, 1), dtype=torch.int32, device=dev)     # cleared by the call
+        t_pre = torch.empty(max(n_src * t_words, 1), dtype=torch.int32, device=dev)
         t_dst = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         t_perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         t_seg = torch.empty(n_src + 1, dtype=torch.int32, device=dev)
         N.call("bliss_block_transpose", N.ptr(block.edge_src), N.ptr(block.edge_dst), E, n_src, n_dst,
-               N.ptr(t_indptr), N.ptr(t_cursor), N.ptr(t_scratch), N.ptr(t_dst), N.ptr(t_perm), N.ptr(t_seg),
+               N.ptr(t_indptr), N.ptr(t_cursor), N.ptr(t_bits), N.ptr(t_pre), t_words, N.ptr(t_dst), N.ptr(t_perm),
+               N.ptr(t_seg),
                0, None, N.stream())
         block._transpose = (t_indptr, t_dst[:E], t_perm[:E], t_seg)
     return block._transpose

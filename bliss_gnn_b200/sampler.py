@@ -142,7 +142,10 @@ class LayerPool:
         self.node_prob = self.src[self.cap_src:].view(torch.float32)
         self.t_indptr = torch.zeros(self.cap_src + 1, **i32)
         self.t_cursor = torch.zeros(self.cap_src, **i32)
-        self.t_scratch = torch.zeros(self.cap_edges, **i32)
+        # source x destination bitmap of the block + word prefixes: the transpose is read off the bitmap
+        self.t_words = (self.cap_dst + 31) // 32
+        self.t_bits = torch.zeros(self.cap_src * self.t_words, **i32)
+        self.t_pre = torch.zeros(self.cap_src * self.t_words, **i32)
         self.t_dst = torch.zeros(self.cap_edges, **i32)
         self.t_perm = torch.zeros(self.cap_edges, **i32)
         self.t_seg_ptr = torch.zeros(self.cap_src + 1, **i32)
@@ -333,7 +336,7 @@ class BanditLadiesSampler:
             # so the transpose starts from its scan (no separate count pass)
             out = N.BlockOut(indptr=N.ptr(pool.indptr), src_nid=N.ptr(wsp.src_nid), node_prob=N.ptr(wsp.node_prob),
                              seg_ptr=N.ptr(pool.seg_ptr), inv_deg=N.ptr(pool.inv_deg), out_deg=N.ptr(pool.t_cursor),
-                             cap_edges=0, cap_src=fr.g.num_nodes(), pad_src=pool.cap_src, pad_rows=pool.cap_dst)
+                             t_bits=N.ptr(pool.t_bits), t_words=pool.t_words, cap_edges=0, cap_src=fr.g.num_nodes(), pad_src=pool.cap_src, pad_rows=pool.cap_dst)
             return out, (pool.indptr[:n_s + 1], pool.seg_ptr[:n_s + 1], pool.inv_deg[:n_s])
         meta = torch.empty(3 * (n_s + 1), dtype=torch.int32, device=dev)   # indptr | seg_ptr | inv_deg (as f32)
         indptr, seg_ptr, inv_deg = meta[:n_s + 1], meta[n_s + 1:2 * (n_s + 1)], meta[2 * (n_s + 1):].view(torch.float32)
@@ -355,7 +358,7 @@ class BanditLadiesSampler:
         pooled = pool is not None and out.pad_rows > 0 and pool.fits(n_s, n_src, E)
         if pool is not None and not pooled:
             self.pool_overflow = True          # the caller grows the pool and re-captures
-            out.out_deg = None
+            out.out_deg, out.t_bits = None, None
             if out.pad_rows > 0:               # indptr lives in the pool but the block does not fit: detach it
                 indptr, seg_ptr, inv_deg = indptr.clone(), seg_ptr[:n_s + 1].clone(), inv_deg.clone()
         # one allocation for the 4-byte edge arrays, one for the 8-byte CSC positions
@@ -475,7 +478,8 @@ class BanditLadiesSampler:
             out = N.BlockOut(indptr=N.ptr(pool.indptr), edge_src=N.ptr(e32[0]), edge_dst=N.ptr(e32[1]),
                              csc_pos=N.ptr(pool.csc_pos), eid=N.ptr(e32[2]), q_ij=N.ptr(e32[4]) if bandit else None,
                              edge_w=N.ptr(e32[3]), src_nid=N.ptr(pool.src_nid), node_prob=N.ptr(pool.node_prob),
-                             out_deg=N.ptr(pool.t_cursor), seg_ptr=N.ptr(pool.seg_ptr), inv_deg=N.ptr(pool.inv_deg),
+                             out_deg=N.ptr(pool.t_cursor), t_bits=N.ptr(pool.t_bits), t_words=pool.t_words,
+                             seg_ptr=N.ptr(pool.seg_ptr), inv_deg=N.ptr(pool.inv_deg),
                              cap_edges=pool.cap_edges, cap_src=pool.cap_src, pad_src=pool.cap_src,
                              pad_rows=pool.cap_dst)
             st = N.stream()
@@ -485,7 +489,7 @@ class BanditLadiesSampler:
             N.call("bliss_sample_layer_back", C.byref(wsp.gview), N.ptr(seeds), n_cap, N.ptr(weights), float(self.eta),
                    self._mode, C.byref(ws), C.byref(out), st)
             N.call("bliss_block_transpose", N.ptr(e32[0]), N.ptr(e32[1]), pool.cap_edges, pool.cap_src, pool.cap_dst,
-                   N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_scratch), N.ptr(pool.t_dst),
+                   N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_bits), N.ptr(pool.t_pre), pool.t_words, N.ptr(pool.t_dst),
                    N.ptr(pool.t_perm), N.ptr(pool.t_seg_ptr), 1, wsp.counter_ptr(block_id, "n_edges"), st)
 
     # ---- bandit update ------------------------------------------------------------------------

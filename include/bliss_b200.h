@@ -111,6 +111,9 @@ typedef struct bliss_block_out {
   int32_t* src_nid;     /* [n_src] global id of each block source                         */
   float*   node_prob;   /* [n_src] inclusion probability P (bandit_sampler.py:328)        */
   int32_t* out_deg;     /* [n_src] block out-degree of each source (NULL to skip)         */
+  uint32_t* t_bits;     /* [cap_src x t_words] source x destination bitmap of the block, marked by the
+                           fill for bliss_block_transpose (NULL to skip)                  */
+  int64_t  t_words;     /* row stride of t_bits in 32-bit words (>= ceil(n_seeds / 32))   */
   int32_t* seg_ptr;     /* [n_seeds+1] prefix of max(1, ceil(in-degree/32)): the 32-edge row segments the
                            balanced SpMM works on (padded rows count one segment each; NULL ok)       */
   float*   inv_deg;     /* [n_seeds] 1 / max(block in-degree, 1)  (fn.mean divisor; NULL ok)  */
@@ -177,12 +180,15 @@ int bliss_sample_layer_back(const bliss_graph* g, const int32_t* seeds, int32_t 
                             const float* edge_weight_csc, float eta, int32_t mode,
                             const bliss_workspace* ws, const bliss_block_out* out, void* stream);
 /* source-major transpose of a block (backward SpMM): t_indptr[n_src+1], t_dst[E], t_perm[E]
- * (edge ids ascending inside every source row, so backward sums are deterministic). */
+ * (edge ids ascending inside every source row, so backward sums are deterministic).  Driven by the
+ * source x destination bitmap t_bits [n_src x t_words] (+ t_pre of the same shape, word prefixes):
+ * have_counts = 0: out-degrees and bits are computed here from the edge list;
+ * have_counts = 1: t_cursor holds the out-degrees and t_bits the marks (bliss_block_out.out_deg / t_bits). */
 int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                           int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor /* [n_src] */,
-                          int32_t* t_scratch /* [E] */, int32_t* t_dst, int32_t* t_perm,
+                          uint32_t* t_bits, int32_t* t_pre, int64_t t_words, int32_t* t_dst, int32_t* t_perm,
                           int32_t* t_seg_ptr /* [n_src+1] 32-edge segment prefix of the source rows; may be NULL */,
-                          int32_t have_counts /* t_cursor already holds out-degrees (block_out.out_deg) */,
+                          int32_t have_counts,
                           const int64_t* n_edges_dev /* true edge count on the device, or NULL */,
                           void* stream);
 
