@@ -157,7 +157,7 @@ class BlissNativeError(RuntimeError):
 
 
 #: kernels each entry point launches (for the ``gpu_launches`` count of bench.py)
-LAUNCHES = {"bliss_frontier_prob": 4, "bliss_sample_layer_front": 9, "bliss_frontier_plan": 2, "bliss_sample_layer_back": 2,
+LAUNCHES = {"bliss_frontier_prob": 4, "bliss_sample_layer_front": 10, "bliss_poisson_select": 2, "bliss_frontier_plan": 2, "bliss_sample_layer_back": 2,
             "bliss_select_topk": 3, "bliss_block_transpose": 3, "bliss_l1_norm": 2, "bliss_version": 0,
             "bliss_adam_step": 2, "bliss_spmm": 2}
 

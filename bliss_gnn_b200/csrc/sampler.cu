@@ -315,22 +315,32 @@ __global__ void __launch_bounds__(256) k_collect_candidates(int64_t num_nodes, i
   const int lane = lane_id();
   const int64_t n_words = (num_nodes + 31) >> 5;
   const int64_t words_per_cta = (int64_t)BLISS_COLLECT_WORDS * (blockDim.x >> 5);
+  const int n_seeds = ws.ctr->n_seeds;
+  const double fx_inv_scale = 1.0 / (double)(1ull << fx_bits_for(n_seeds));
+  // the raw probability p_j = sqrt(acc_j) goes straight into the candidate's slot (the scan holds acc_j
+  // anyway), so the scale search starts from a coalesced array instead of |N_c| dependent gathers
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_seeds; i += (int64_t)gridDim.x * blockDim.x)
+    ws.p_cand[i] = fx_to_prob(ws.acc[ws.cand[i]], fx_inv_scale);
   for (int64_t w0 = blockIdx.x * words_per_cta; w0 < n_words; w0 += gridDim.x * words_per_cta) {
     unsigned m[BLISS_COLLECT_WORDS];
+    unsigned long long av[BLISS_COLLECT_WORDS];
     int cnt = 0;
 #pragma unroll
     for (int u = 0; u < BLISS_COLLECT_WORDS; ++u) {
       const int64_t w = w0 + (int64_t)warp_id() * BLISS_COLLECT_WORDS + u;
       const int64_t v = (w << 5) + lane;
       bool hit = false;
+      av[u] = 0ull;
       if (w < n_words) {
         if (bitmap) {
           const unsigned word = ws.cand_bits[w];  // warp-uniform
           __syncwarp();
           if (word != 0u && lane == 0) ws.cand_bits[w] = 0u;
           hit = (word >> lane) & 1u;
-        } else {
-          hit = v < num_nodes && ws.acc[v] != 0ull;
+          if (hit) av[u] = ws.acc[v];
+        } else if (v < num_nodes) {
+          av[u] = ws.acc[v];
+          hit = av[u] != 0ull;
         }
       }
       const bool is_new = hit && ws.node_info[2 * v] < 0;  // seeds are listed already
@@ -347,7 +357,11 @@ __global__ void __launch_bounds__(256) k_collect_candidates(int64_t num_nodes, i
 #pragma unroll
     for (int u = 0; u < BLISS_COLLECT_WORDS; ++u) {
       const int64_t v = ((w0 + (int64_t)warp_id() * BLISS_COLLECT_WORDS + u) << 5) + lane;
-      if ((m[u] >> lane) & 1u) ws.cand[pos + __popc(m[u] & ((1u << lane) - 1u))] = (int)v;
+      if ((m[u] >> lane) & 1u) {
+        const int slot = pos + __popc(m[u] & ((1u << lane) - 1u));
+        ws.cand[slot] = (int)v;
+        ws.p_cand[slot] = fx_to_prob(av[u], fx_inv_scale);
+      }
       pos += __popc(m[u]);
     }
     __syncthreads();   // s_base is rewritten by the next round
@@ -364,11 +378,8 @@ __global__ void __launch_bounds__(1024) k_poisson_scale(int n_seeds, int fanout,
   fx_inv_scale = 1.0 / (double)(1ull << fx_bits_for(n_seeds));
   __shared__ unsigned long long s_red[32];
   bliss_counters* ctr = ws.ctr;
-  const int n_cand = ctr->n_cand;
-  for (int j = threadIdx.x; j < n_cand; j += blockDim.x) {
-    int nid = ws.cand[j];
-    ws.p_cand[j] = fx_to_prob(ws.acc[nid], fx_inv_scale);
-  }
+  const int n_cand = ctr->n_cand;   // p_cand was filled by k_collect_candidates
+  (void)fx_inv_scale;
   if (!poisson) return;
   if (n_cand <= fanout) {  // "prob.shape[0] <= num: return one"
     if (threadIdx.x == 0) {
@@ -426,9 +437,9 @@ __device__ __forceinline__ void push_selected(bool sel, int nid, const bliss_wor
 }
 
 // ------------------------------------------------------------------------------------------
-// (2a+2b fused) candidate probabilities + Poisson scale search + selection in ONE launch of a
-// single thread-block cluster (16 CTAs x 1024 threads, 8 if 16 is not schedulable).  Every
-// thread keeps up to NREG candidates (p and node id) in registers, so one search iteration is
+// (2a) Poisson scale search in ONE launch of a single thread-block cluster (16 CTAs x 1024 threads,
+// 8 if 16 is not schedulable); the selection itself is the grid-wide k_select_poisson.  Every
+// thread keeps up to NREG candidate probabilities in registers, so one search iteration is
 // NREG multiplies per thread + a CTA reduction + a DSMEM exchange of one 64-bit partial per CTA
 // and one cluster barrier — no global memory traffic and no host round trip inside the search
 // (the reference does up to 50 .item() syncs per layer, bandit_sampler.py:396-401).
@@ -436,13 +447,7 @@ __device__ __forceinline__ void push_selected(bool sel, int nid, const bliss_wor
 // ------------------------------------------------------------------------------------------
 #define BLISS_SCALE_NREG 16
 #define BLISS_SCALE_MAX_CLUSTER 16
-__global__ void __launch_bounds__(1024, 1) k_scale_select(int n_seeds, int fanout, double eps,
-                                                         unsigned long long seed, unsigned long long step,
-                                                         unsigned layer, const float* __restrict__ u_inject,
-                                                         bliss_workspace ws, double fx_inv_scale) {
-  n_seeds = ws.ctr->n_seeds;   // the plan's (possibly device-side) count, not the host capacity
-  fx_inv_scale = 1.0 / (double)(1ull << fx_bits_for(n_seeds));
-  if (ws.step_dev) step = *ws.step_dev;   // Philox step counter kept on the device (CUDA-graph replay)
+__global__ void __launch_bounds__(1024, 1) k_scale_search(int fanout, double eps, bliss_workspace ws) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
   const unsigned nblk = cluster.num_blocks();
@@ -453,19 +458,12 @@ __global__ void __launch_bounds__(1024, 1) k_scale_select(int n_seeds, int fanou
   const int gtid = rank * blockDim.x + threadIdx.x;
   const int nthreads = nblk * blockDim.x;
 
-  float preg[BLISS_SCALE_NREG];
+  float preg[BLISS_SCALE_NREG];   // p_cand was filled by k_collect_candidates: coalesced loads
 #pragma unroll
   for (int r = 0; r < BLISS_SCALE_NREG; ++r) {
     const int j = gtid + r * nthreads;
-    preg[r] = 0.0f;
-    if (j < n_cand) {
-      const float p = fx_to_prob(ws.acc[ws.cand[j]], fx_inv_scale);
-      ws.p_cand[j] = p;
-      preg[r] = p;
-    }
+    preg[r] = (j < n_cand) ? ws.p_cand[j] : 0.0f;
   }
-  for (int j = gtid + BLISS_SCALE_NREG * nthreads; j < n_cand; j += nthreads)
-    ws.p_cand[j] = fx_to_prob(ws.acc[ws.cand[j]], fx_inv_scale);
 
   const bool take_all = n_cand <= fanout;  // "prob.shape[0] <= num: return one"  (:392-393)
   double c = 1.0, S = 0.0;
@@ -483,9 +481,14 @@ __global__ void __launch_bounds__(1024, 1) k_scale_select(int n_seeds, int fanou
         part += __float2ull_rn(__fmul_rn(fminf(__fmul_rn(preg[r], cf), 1.0f), s_scale));
       for (int j = gtid + BLISS_SCALE_NREG * nthreads; j < n_cand; j += nthreads)
         part += __float2ull_rn(__fmul_rn(fminf(__fmul_rn(ws.p_cand[j], cf), 1.0f), s_scale));
-      const unsigned long long tot = block_sum(part, s_red);
-      if (threadIdx.x < nblk)  // publish this CTA's partial into every CTA of the cluster
-        *cluster.map_shared_rank(&s_parts[i & 1][rank], threadIdx.x) = tot;
+      // warp totals -> warp 0 adds them and publishes this CTA's partial into every CTA of the cluster
+      part = warp_sum(part);
+      if (lane_id() == 0) s_red[warp_id()] = part;
+      __syncthreads();
+      if (warp_id() == 0) {
+        const unsigned long long tot = warp_sum(s_red[lane_id()]);
+        if (lane_id() < nblk) *cluster.map_shared_rank(&s_parts[i & 1][rank], lane_id()) = tot;
+      }
       cluster.sync();
       unsigned long long all = 0;
       for (unsigned b = 0; b < nblk; ++b) all += s_parts[i & 1][b];
@@ -500,89 +503,68 @@ __global__ void __launch_bounds__(1024, 1) k_scale_select(int n_seeds, int fanou
     ctr->s_last = S;
     ctr->take_all = take_all ? 1 : 0;
   }
-  // selection: u < P, seeds forced to P = 1 (:403-406, :422-424).  The register-resident candidates
-  // of a CTA are appended with ONE atomic on the shared counter (flags -> CTA scan -> base).
-  const float cf = (float)c;
-  unsigned selmask = 0;
-#pragma unroll
-  for (int r = 0; r < BLISS_SCALE_NREG; ++r) {
-    const int j = gtid + r * nthreads;
-    if (j >= n_seeds && j < n_cand) {
-      const int nid = ws.cand[j];
-      const float P = take_all ? 1.0f : fminf(__fmul_rn(preg[r], cf), 1.0f);
-      const float u = u_inject ? u_inject[nid] : philox_uniform(seed, step, layer, (unsigned)nid);
-      const bool sel = u < P;
-      *reinterpret_cast<int2*>(&ws.node_info[2 * nid]) = make_int2(sel ? -2 : -1, __float_as_int(P));
-      if (sel) selmask |= 1u << r;
-    }
-  }
-  {
-    __shared__ int s_scan[40];
-    __shared__ int s_base;
-    int tot;
-    int off = block_excl_scan(__popc(selmask), s_scan, &tot);
-    if (threadIdx.x == 0 && tot > 0) s_base = atomicAdd(&ctr->n_sel, tot);
-    __syncthreads();
-    if (selmask) {
-      int slot = s_base + off;
-#pragma unroll
-      for (int r = 0; r < BLISS_SCALE_NREG; ++r) {
-        if ((selmask >> r) & 1u) {
-          if (slot < ws.cap_sel) {
-            const int nid = ws.cand[gtid + r * nthreads];   // L1/L2 hit: read a moment ago
-            ws.sel[slot] = nid;
-            atomicOr(&ws.sel_bits[nid >> 5], 1u << (nid & 31));
-          } else {
-            ctr->error = BLISS_ERR_SEL_CAPACITY;
-          }
-          ++slot;
-        }
-      }
-    }
-  }
-  const int rest0 = BLISS_SCALE_NREG * nthreads;
-  const int n_pad = (n_cand + 31) & ~31;
-  for (int j = gtid + rest0; j < n_pad; j += nthreads) {
-    bool sel = false;
-    int nid = 0;
-    if (j < n_cand) {
-      nid = ws.cand[j];
-      const float P = take_all ? 1.0f : fminf(__fmul_rn(ws.p_cand[j], cf), 1.0f);
-      const float u = u_inject ? u_inject[nid] : philox_uniform(seed, step, layer, (unsigned)nid);
-      sel = (j >= n_seeds) && (u < P);
-      if (j >= n_seeds) {
-        ws.node_info[2 * nid] = sel ? -2 : -1;
-        ws.node_info[2 * nid + 1] = __float_as_int(P);
-      }
-    }
-    push_selected(sel, nid, ws);
-  }
   cluster.sync();  // no CTA may exit while its shared memory can still be written remotely
 }
 
+// Grid-wide: 4 candidates per thread and round; the selected ones of a CTA round are appended with ONE
+// atomic on the shared counter (flags -> CTA scan -> base).  Only selected nodes get their
+// (selected mark, P) pair written: nothing reads it for the others.
 __global__ void __launch_bounds__(256) k_select_poisson(int n_seeds, unsigned long long seed,
                                                        unsigned long long step, unsigned layer,
                                                        const float* __restrict__ u_inject,
                                                        bliss_workspace ws) {
+  __shared__ int s_scan[40];
+  __shared__ int s_base;
   n_seeds = ws.ctr->n_seeds;   // the plan's (possibly device-side) count, not the host capacity
-  if (ws.step_dev) step = *ws.step_dev;
+  if (ws.step_dev) step = *ws.step_dev;   // Philox step counter kept on the device (CUDA-graph replay)
   bliss_counters* ctr = ws.ctr;
   const int n_cand = ctr->n_cand;
   const float cf = (float)ctr->c;
   const int take_all = ctr->take_all;
-  const int n_pad = (n_cand + 31) & ~31;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pad; j += gridDim.x * blockDim.x) {
-    bool sel = false;
-    int nid = 0;
-    if (j >= n_seeds && j < n_cand) {
-      nid = ws.cand[j];
-      float P = take_all ? 1.0f : fminf(__fmul_rn(ws.p_cand[j], cf), 1.0f);
-      float u = u_inject ? u_inject[nid] : philox_uniform(seed, step, layer, (unsigned)nid);
-      sel = u < P;
-      ws.node_info[2 * nid] = sel ? -2 : -1;
-      ws.node_info[2 * nid + 1] = __float_as_int(P);
+  constexpr int PER = 4;
+  const int per_round = blockDim.x * PER;
+  for (int j0 = n_seeds + blockIdx.x * per_round; j0 < n_cand; j0 += gridDim.x * per_round) {
+    int nid[PER];
+    float P[PER];
+    unsigned mask = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int j = j0 + u * blockDim.x + threadIdx.x;
+      nid[u] = 0;
+      P[u] = 0.0f;
+      if (j < n_cand) {
+        nid[u] = ws.cand[j];
+        P[u] = take_all ? 1.0f : fminf(__fmul_rn(ws.p_cand[j], cf), 1.0f);
+      }
     }
-    push_selected(sel, nid, ws);
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int j = j0 + u * blockDim.x + threadIdx.x;
+      if (j < n_cand) {
+        const float uu = u_inject ? u_inject[nid[u]] : philox_uniform(seed, step, layer, (unsigned)nid[u]);
+        if (uu < P[u]) mask |= 1u << u;   // u < P  (:422-424)
+      }
+    }
+    int tot;
+    int off = block_excl_scan(__popc(mask), s_scan, &tot);
+    if (tot == 0) continue;   // CTA-uniform
+    if (threadIdx.x == 0) s_base = atomicAdd(&ctr->n_sel, tot);
+    __syncthreads();
+    int slot = s_base + off;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      if ((mask >> u) & 1u) {
+        if (slot < ws.cap_sel) {
+          ws.sel[slot] = nid[u];
+          *reinterpret_cast<int2*>(&ws.node_info[2 * nid[u]]) = make_int2(-2, __float_as_int(P[u]));
+          atomicOr(&ws.sel_bits[nid[u] >> 5], 1u << (nid[u] & 31));
+        } else {
+          ctr->error = BLISS_ERR_SEL_CAPACITY;
+        }
+        ++slot;
+      }
+    }
+    __syncthreads();   // s_base is rewritten by the next round
   }
 }
 
@@ -1187,7 +1169,7 @@ int bliss_poisson_scale(int32_t n_seeds, int32_t fanout, double eps, int32_t poi
 int bliss_select_poisson(int32_t n_seeds, uint64_t seed, uint64_t step, uint32_t layer,
                          const float* u_inject, const bliss_workspace* ws, void* stream) {
   if (!ws) return -1;
-  k_select_poisson<<<BLISS_SM_COUNT * 4, 256, 0, (cudaStream_t)stream>>>(n_seeds, seed, step, layer, u_inject, *ws);
+  k_select_poisson<<<BLISS_SM_COUNT * 2, 256, 0, (cudaStream_t)stream>>>(n_seeds, seed, step, layer, u_inject, *ws);
   BLISS_CHECK_LAUNCH();
   return 0;
 }
@@ -1199,7 +1181,7 @@ int bliss_poisson_select(int32_t n_seeds, int32_t fanout, double eps, uint64_t s
   if (!ws || fanout < 0) return -1;
   if (g_cluster_size == 0) {
     g_cluster_size = -1;
-    if (cudaFuncSetAttribute(k_scale_select, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    if (cudaFuncSetAttribute(k_scale_search, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
       for (int cs = BLISS_SCALE_MAX_CLUSTER; cs >= 8 && g_cluster_size < 0; cs >>= 1) {
         cudaLaunchConfig_t q = {};
         q.gridDim = dim3(cs);
@@ -1211,17 +1193,16 @@ int bliss_poisson_select(int32_t n_seeds, int32_t fanout, double eps, uint64_t s
         q.attrs = a;
         q.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, k_scale_select, &q) == cudaSuccess && n > 0) g_cluster_size = cs;
+        if (cudaOccupancyMaxActiveClusters(&n, k_scale_search, &q) == cudaSuccess && n > 0) g_cluster_size = cs;
       }
     }
     (void)cudaGetLastError();
   }
-  if (g_cluster_size < 0) {  // no cluster support: the two-launch path
+  if (g_cluster_size < 0) {  // no cluster support: the single-CTA search
     int rc = bliss_poisson_scale(n_seeds, fanout, eps, 1, ws, stream);
     if (rc) return rc;
     return bliss_select_poisson(n_seeds, seed, step, layer, u_inject, ws, stream);
   }
-  const double fx_inv = 1.0 / (double)(1ull << fx_bits_for(n_seeds));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g_cluster_size);
   cfg.blockDim = dim3(1024);
@@ -1232,11 +1213,9 @@ int bliss_poisson_select(int32_t n_seeds, int32_t fanout, double eps, uint64_t s
   attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_scale_select, (int)n_seeds, (int)fanout, eps,
-                                     (unsigned long long)seed, (unsigned long long)step, (unsigned)layer, u_inject,
-                                     *ws, fx_inv);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_scale_search, (int)fanout, eps, *ws);
   if (e != cudaSuccess) return (int)e;
-  return 0;
+  return bliss_select_poisson(n_seeds, seed, step, layer, u_inject, ws, stream);
 }
 
 int bliss_select_topk(int32_t n_seeds, int32_t fanout, uint64_t seed, uint64_t step, uint32_t layer,
