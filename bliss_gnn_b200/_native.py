@@ -82,7 +82,7 @@ class Workspace(C.Structure):
     _fields_ = [("acc", C.c_void_p), ("first_pos", C.c_void_p), ("node_info", C.c_void_p),
                 ("sel_bits", C.c_void_p), ("cand_bits", C.c_void_p), ("keep_bits", C.c_void_p), ("cand", C.c_void_p), ("p_cand", C.c_void_p), ("sel", C.c_void_p),
                 ("row_a", C.c_void_p), ("row_d", C.c_void_p),
-                ("chunk_first", C.c_void_p), ("part_w", C.c_void_p), ("part_q", C.c_void_p),
+                ("chunk_first", C.c_void_p), ("chunk_rec", C.c_void_p), ("part_w", C.c_void_p), ("part_q", C.c_void_p),
                 ("row_w", C.c_void_p), ("row_q", C.c_void_p),
                 ("row_cnt", C.c_void_p), ("part_cnt", C.c_void_p), ("part_t", C.c_void_p), ("cap_seeds", C.c_int64),
                 ("cap_sel", C.c_int64), ("ctr", C.c_void_p), ("n_seeds_dev", C.c_void_p), ("step_dev", C.c_void_p)]
@@ -157,7 +157,7 @@ class BlissNativeError(RuntimeError):
 
 
 #: kernels each entry point launches (for the ``gpu_launches`` count of bench.py)
-LAUNCHES = {"bliss_frontier_prob": 4, "bliss_sample_layer_front": 10, "bliss_poisson_select": 2, "bliss_frontier_plan": 2, "bliss_sample_layer_back": 2,
+LAUNCHES = {"bliss_frontier_prob": 4, "bliss_sample_layer_front": 11, "bliss_poisson_select": 2, "bliss_frontier_plan": 3, "bliss_sample_layer_back": 2,
             "bliss_select_topk": 3, "bliss_block_transpose": 3, "bliss_l1_norm": 2, "bliss_version": 0,
             "bliss_adam_step": 2, "bliss_spmm": 2}
 

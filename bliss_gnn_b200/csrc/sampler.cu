@@ -149,28 +149,45 @@ __device__ __forceinline__ void scatter_term(bool uniform, bool bitmap, float t,
 //   pass 3  Q_i = Σ_c partQ ; RED acc[src] += fx((q / Q_i)^2)              (indices from HBM)
 // CTAs pull groups of 8 consecutive chunks from a device-side queue (one atomic per group, issued
 // at the top of an iteration and consumed at its end, so its latency hides behind the chunk).
-struct ChunkRef {
-  int row, k0, len;
-  int64_t a;
-  int d, c_first, c_last;  // chunk range of the row [c_first, c_last)
+struct ChunkRef {   // == bliss_chunk_rec (32 bytes, written by k_plan_chunks): everything a pass needs about a chunk
+  int64_t a;        // CSC position of the chunk's first edge
+  int len;          // edges in the chunk (<= 256)
+  int row;          // seed rank
+  int d;            // in-degree of the row
+  int k0;           // offset of the chunk inside its row
+  int c_first, c_last;  // chunk range of the row [c_first, c_last)
 };
-__device__ __forceinline__ ChunkRef chunk_ref(const bliss_workspace& ws, int c, int n_seeds) {
+static_assert(sizeof(ChunkRef) == 32, "chunk record layout");
+__device__ __forceinline__ ChunkRef chunk_ref(const bliss_workspace& ws, int c) {
+  // one 32-byte record per chunk (two broadcast 128-bit loads) instead of a search plus four dependent loads
+  const int4* __restrict__ p = reinterpret_cast<const int4*>(ws.chunk_rec) + 2 * (int64_t)c;
+  const int4 lo = __ldg(p), hi = __ldg(p + 1);
   ChunkRef r;
-  // row of chunk c = last i with chunk_first[i] <= c: warp-uniform binary search over the prefix
-  // array (a few KB, L1 resident) instead of a materialised chunk->row table
-  int lo = 0, hi = n_seeds - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(ws.chunk_first + mid) <= c) lo = mid; else hi = mid - 1;
-  }
-  r.row = lo;
-  r.a = ws.row_a[r.row];
-  r.d = ws.row_d[r.row];
-  r.c_first = ws.chunk_first[r.row];
-  r.c_last = ws.chunk_first[r.row + 1];
-  r.k0 = (c - r.c_first) * BLISS_CHUNK;
-  r.len = min(BLISS_CHUNK, r.d - r.k0);
+  r.a = ((int64_t)(unsigned)lo.x) | ((int64_t)lo.y << 32);
+  r.len = lo.z;
+  r.row = lo.w;
+  r.d = hi.x;
+  r.k0 = hi.y;
+  r.c_first = hi.z;
+  r.c_last = hi.w;
   return r;
+}
+// one warp per row: the row's chunk records
+__global__ void __launch_bounds__(256) k_plan_chunks(bliss_workspace ws) {
+  const int n_seeds = ws.ctr->n_seeds;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < n_seeds; i += nwarps) {
+    const int64_t a = ws.row_a[i];
+    const int d = ws.row_d[i];
+    const int c_first = ws.chunk_first[i], c_last = ws.chunk_first[i + 1];
+    for (int c = c_first + lane_id(); c < c_last; c += 32) {
+      const int k0 = (c - c_first) * BLISS_CHUNK;
+      const int64_t pos = a + k0;
+      int4* p = reinterpret_cast<int4*>(ws.chunk_rec) + 2 * (int64_t)c;
+      p[0] = make_int4((int)(pos & 0xffffffffll), (int)(pos >> 32), min(BLISS_CHUNK, d - k0), i);
+      p[1] = make_int4(d, k0, c_first, c_last);
+    }
+  }
 }
 // Σ of a row's chunk partials: lanes take the chunks round-robin, then a butterfly — a fixed
 // order (deterministic), every lane ends with the same bits.
@@ -180,36 +197,25 @@ __device__ __forceinline__ float row_total(const double* __restrict__ part, int 
   return __double2float_rn(warp_sum(t));
 }
 
-// for (ChunkLoop q(...); q.more(); q.next()) { const int c = q.chunk(); if (c < n_chunks) ... }
+// for (ChunkLoop q(cursor, n_chunks); q.more(); q.next()) { const int c = q.chunk(); ... }
+// Chunks are dealt round-robin to the resident warps (chunks cost about the same, and thousands of
+// same-address queue atomics per pass serialise in L2 for longer than the imbalance they remove).
 struct ChunkLoop {
-  int* cursor;
-  int* s_next;   // 2 ints of shared memory
-  int n_chunks, item, iter;
-  __device__ __forceinline__ ChunkLoop(int* cursor_, int* s_next_, int n_chunks_)
-      : cursor(cursor_), s_next(s_next_), n_chunks(n_chunks_), item(blockIdx.x), iter(0) {}
-  __device__ __forceinline__ bool more() {
-    if (item * BLISS_WARPS >= n_chunks) return false;   // CTA-uniform
-    if (threadIdx.x == 0) s_next[iter & 1] = gridDim.x + atomicAdd(cursor, 1);
-    return true;
-  }
-  __device__ __forceinline__ int chunk() const { return item * BLISS_WARPS + warp_id(); }
-  __device__ __forceinline__ void next() {
-    __syncthreads();
-    item = s_next[iter & 1];
-    ++iter;
-  }
+  int n_chunks, item;
+  __device__ __forceinline__ ChunkLoop(int*, int n_chunks_)
+      : n_chunks(n_chunks_), item((blockIdx.x * blockDim.x + threadIdx.x) >> 5) {}
+  __device__ __forceinline__ bool more() const { return item < n_chunks; }   // warp-uniform
+  __device__ __forceinline__ int chunk() const { return item; }
+  __device__ __forceinline__ void next() { item += (gridDim.x * blockDim.x) >> 5; }
 };
 
 __global__ void __launch_bounds__(BLISS_CTA, 6) k_prob_pass1(const float* __restrict__ W, bliss_workspace ws) {
-  __shared__ int s_next[2];
   const int lane = lane_id();
-  const int n_seeds = ws.ctr->n_seeds;
   const int n_chunks = ws.ctr->n_chunks;
-  for (ChunkLoop q(&ws.ctr->queue[0], s_next, n_chunks); q.more(); q.next()) {
+  for (ChunkLoop q(&ws.ctr->queue[0], n_chunks); q.more(); q.next()) {
     const int c = q.chunk();
-    if (c >= n_chunks) continue;
-    const ChunkRef r = chunk_ref(ws, c, n_seeds);
-    const float* __restrict__ wr = W + r.a + r.k0;
+    const ChunkRef r = chunk_ref(ws, c);
+    const float* __restrict__ wr = W + r.a;
     double acc = 0.0;
 #pragma unroll
     for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
@@ -223,15 +229,12 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_prob_pass1(const float* __rest
 
 __global__ void __launch_bounds__(BLISS_CTA, 6) k_prob_pass2(const float* __restrict__ W, float eta, float one_minus_eta,
                                                          bliss_workspace ws) {
-  __shared__ int s_next[2];
   const int lane = lane_id();
-  const int n_seeds = ws.ctr->n_seeds;
   const int n_chunks = ws.ctr->n_chunks;
-  for (ChunkLoop q(&ws.ctr->queue[1], s_next, n_chunks); q.more(); q.next()) {
+  for (ChunkLoop q(&ws.ctr->queue[1], n_chunks); q.more(); q.next()) {
     const int c = q.chunk();
-    if (c >= n_chunks) continue;
-    const ChunkRef r = chunk_ref(ws, c, n_seeds);
-    const float* __restrict__ wr = W + r.a + r.k0;
+    const ChunkRef r = chunk_ref(ws, c);
+    const float* __restrict__ wr = W + r.a;
     float v[BLISS_CHUNK / 32];
 #pragma unroll
     for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
@@ -256,20 +259,17 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_prob_pass2(const float* __rest
 
 __global__ void __launch_bounds__(BLISS_CTA, 5) k_prob_pass3(GraphView g, const float* __restrict__ W, float eta,
                                                          float one_minus_eta, int mode_flags, bliss_workspace ws) {
-  __shared__ int s_next[2];
   const int mode = mode_flags & 1;
   const bool uniform = (mode_flags & BLISS_MODE_UNIFORM);
   const bool bitmap = (mode_flags & BLISS_COLLECT_BITMAP);
   const int lane = lane_id();
-  const int n_seeds = ws.ctr->n_seeds;
   const int n_chunks = ws.ctr->n_chunks;
   const double fx_scale = (double)(1ull << fx_bits_for(ws.ctr->n_seeds));
-  for (ChunkLoop q(&ws.ctr->queue[2], s_next, n_chunks); q.more(); q.next()) {
+  for (ChunkLoop q(&ws.ctr->queue[2], n_chunks); q.more(); q.next()) {
     const int c = q.chunk();
-    if (c >= n_chunks) continue;
-    const ChunkRef r = chunk_ref(ws, c, n_seeds);
-    const float* __restrict__ wr = W + r.a + r.k0;
-    const int32_t* __restrict__ idx = g.indices + r.a + r.k0;
+    const ChunkRef r = chunk_ref(ws, c);
+    const float* __restrict__ wr = W + r.a;
+    const int32_t* __restrict__ idx = g.indices + r.a;
     float v[BLISS_CHUNK / 32];
     int src[BLISS_CHUNK / 32];
 #pragma unroll
@@ -692,19 +692,29 @@ __device__ __forceinline__ void note_first(int src, int local, unsigned long lon
 // accesses (node_info -> first_pos -> atomicMin, weight -> q -> W~) are not done inside the word
 // loop, where only 2-3 lanes per warp would be active: the kept positions go to a per-warp
 // shared-memory list and are processed densely afterwards, one kept edge per lane.
-__global__ void __launch_bounds__(BLISS_CTA, 6) k_block_count(FillCtx c, bliss_workspace ws) {
-  __shared__ int s_next[2];
+// SMEM_BITS: the selected-node bitmap (|V| / 8 bytes) is copied into shared memory once per CTA — the
+// per-edge bit test is a 32-way gather, which an SM's L1 serves at one sector per cycle (it alone
+// would cost more than streaming the indices) but shared memory serves at bank speed.
+template <bool SMEM_BITS>
+__global__ void __launch_bounds__(BLISS_CTA, 6) k_block_count(FillCtx c, bliss_workspace ws, int bit_words) {
+  extern __shared__ uint32_t s_bits[];
   __shared__ unsigned char s_k[BLISS_WARPS][BLISS_CHUNK];   // chunk-relative positions of the kept edges
   bliss_counters* ctr = ws.ctr;
-  const int n_seeds = ctr->n_seeds, n_chunks = ctr->n_chunks;
+  const int n_chunks = ctr->n_chunks;
   const int lane = lane_id();
   const bool bandit = (c.mode == BLISS_MODE_BANDIT);
   unsigned char* lk = s_k[warp_id()];
-  for (ChunkLoop q(&ctr->queue[3], s_next, n_chunks); q.more(); q.next()) {
+  if (blockIdx.x * BLISS_WARPS >= n_chunks) return;   // CTA-uniform: no first chunk for any warp
+  if (SMEM_BITS) {
+    const int4* __restrict__ src4 = reinterpret_cast<const int4*>(ws.sel_bits);
+    for (int i = threadIdx.x; i < (bit_words >> 2); i += BLISS_CTA) reinterpret_cast<int4*>(s_bits)[i] = __ldg(src4 + i);
+    for (int i = (bit_words & ~3) + threadIdx.x; i < bit_words; i += BLISS_CTA) s_bits[i] = ws.sel_bits[i];
+    __syncthreads();
+  }
+  for (ChunkLoop q(&ctr->queue[3], n_chunks); q.more(); q.next()) {
     const int ch = q.chunk();
-    if (ch >= n_chunks) continue;
-    const ChunkRef r = chunk_ref(ws, ch, n_seeds);
-    const int32_t* __restrict__ idx = c.g.indices + r.a + r.k0;
+    const ChunkRef r = chunk_ref(ws, ch);
+    const int32_t* __restrict__ idx = c.g.indices + r.a;
     int src[BLISS_CHUNK / 32];
 #pragma unroll
     for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
@@ -715,7 +725,8 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_count(FillCtx c, bliss_w
     unsigned myword = 0;
 #pragma unroll
     for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
-      const bool keep = src[j] >= 0 && test_bit(ws.sel_bits, src[j]);
+      bool keep = false;
+      if (src[j] >= 0) keep = SMEM_BITS ? ((s_bits[src[j] >> 5] >> (src[j] & 31)) & 1u) : test_bit(ws.sel_bits, src[j]);
       const unsigned bits = __ballot_sync(0xffffffffu, keep);
       if (keep) lk[cnt + __popc(bits & ((1u << lane) - 1u))] = (unsigned char)(lane + 32 * j);
       if (lane == j) myword = bits;
@@ -734,7 +745,7 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_count(FillCtx c, bliss_w
         const int2 info = *reinterpret_cast<const int2*>(&ws.node_info[2 * sj]);
         note_first(sj, info.x, key_hi | (unsigned)(r.k0 + k), ws);
         if (bandit)   // also with importance_sampling=0: q_ij is still built from W (:354-358)
-          t += (double)__fdiv_rn(edge_q(__ldg(c.W + r.a + r.k0 + k), row_w, eta_n, c.one_minus_eta),
+          t += (double)__fdiv_rn(edge_q(__ldg(c.W + r.a + k), row_w, eta_n, c.one_minus_eta),
                                  __int_as_float(info.y));
       }
     }
@@ -878,20 +889,18 @@ __global__ void __launch_bounds__(1024) k_block_index(const int32_t* __restrict_
 //      W~ = (q_ij / P_src) * d / ΣW~  (bandit_sampler.py:306-320)  or  (w / P_src) * d  (ladies_sampler.py:97).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_fill(FillCtx c, bliss_workspace ws, bliss_block_out out) {
-  __shared__ int s_next[2];
   __shared__ unsigned char s_k[BLISS_WARPS][BLISS_CHUNK];
   bliss_counters* ctr = ws.ctr;
-  const int n_seeds = ctr->n_seeds, n_chunks = ctr->n_chunks;
+  const int n_chunks = ctr->n_chunks;
   const int lane = lane_id();
   const bool bandit = (c.mode == BLISS_MODE_BANDIT);
   if (ctr->n_edges > out.cap_edges || ctr->error) return;  // capacity error already flagged by the index kernel
   unsigned char* lk = s_k[warp_id()];
-  for (ChunkLoop q(&ctr->queue[4], s_next, n_chunks); q.more(); q.next()) {
+  for (ChunkLoop q(&ctr->queue[4], n_chunks); q.more(); q.next()) {
     const int ch = q.chunk();
-    if (ch >= n_chunks) continue;
     const int cnt = ws.part_cnt[ch];
     if (cnt == 0) continue;   // warp-uniform
-    const ChunkRef r = chunk_ref(ws, ch, n_seeds);
+    const ChunkRef r = chunk_ref(ws, ch);
     // kept edges of the row before this chunk, of the whole row, and the row's ΣW~
     int pre = 0, tot = 0;
     double t = 0.0;
@@ -918,7 +927,7 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_fill(FillCtx c, bliss_wo
     const float eta_n = __fdiv_rn(c.eta, (float)r.d);
     const int base = out.indptr[r.row] + pre;
     for (int j = lane; j < cnt; j += 32) {
-      const int64_t p = r.a + r.k0 + lk[j];
+      const int64_t p = r.a + lk[j];
       const int src = __ldg(c.g.indices + p);
       const int2 info = *reinterpret_cast<const int2*>(&ws.node_info[2 * src]);
       const float wv = __ldg(c.W + p);
@@ -1129,6 +1138,10 @@ int bliss_frontier_plan(const bliss_graph* g, const int32_t* seeds, int32_t n_se
   }
   k_plan_scan<<<1, 1024, 0, st>>>(n_seeds, *ws);
   BLISS_CHECK_LAUNCH();
+  if (n_seeds > 0) {
+    k_plan_chunks<<<grid_for((int64_t)n_seeds * 32, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(*ws);
+    BLISS_CHECK_LAUNCH();
+  }
   return 0;
 }
 
@@ -1253,7 +1266,14 @@ int bliss_block_count(const bliss_graph* g, const int32_t* seeds, int32_t n_seed
   c.eta = eta;
   c.one_minus_eta = (float)(1.0 - (double)eta);
   c.mode = mode & 1;
-  k_block_count<<<chunk_grid(n_seeds), BLISS_CTA, 0, (cudaStream_t)stream>>>(c, *ws);
+  // selected-node bitmap in shared memory when six CTAs of it fit an SM (|V| <= ~280 K), else tested in L1/L2
+  const int bit_words = (int)((g->num_nodes + 31) / 32);
+  const size_t smem = (size_t)bit_words * sizeof(uint32_t);
+  if (smem <= 35 * 1024) {
+    k_block_count<true><<<chunk_grid(n_seeds), BLISS_CTA, smem, (cudaStream_t)stream>>>(c, *ws, bit_words);
+  } else {
+    k_block_count<false><<<chunk_grid(n_seeds), BLISS_CTA, 0, (cudaStream_t)stream>>>(c, *ws, bit_words);
+  }
   BLISS_CHECK_LAUNCH();
   return 0;
 }

@@ -49,6 +49,7 @@ class _Workspace:
         self.row_a = torch.empty(V, dtype=torch.int64, device=dev)
         self.row_d = torch.empty(V, **i32)
         self.chunk_first = torch.empty(V + 1, **i32)
+        self.chunk_rec = torch.empty(n_chunk_cap * 8, **i32)      # 32-byte record per chunk
         self.part_w = torch.empty(n_chunk_cap, dtype=torch.float64, device=dev)
         self.part_q = torch.empty(n_chunk_cap, dtype=torch.float64, device=dev)
         self.cand = torch.empty(V, **i32)
@@ -75,7 +76,7 @@ class _Workspace:
             acc=N.ptr(self.acc), first_pos=N.ptr(self.first_pos), node_info=N.ptr(self.node_info),
             sel_bits=N.ptr(self.sel_bits), cand_bits=N.ptr(self.cand_bits), keep_bits=N.ptr(self.keep_bits), cand=N.ptr(self.cand), p_cand=N.ptr(self.p_cand), sel=N.ptr(self.sel),
             row_a=N.ptr(self.row_a), row_d=N.ptr(self.row_d),
-            chunk_first=N.ptr(self.chunk_first), part_w=N.ptr(self.part_w),
+            chunk_first=N.ptr(self.chunk_first), chunk_rec=N.ptr(self.chunk_rec), part_w=N.ptr(self.part_w),
             part_q=N.ptr(self.part_q), row_w=N.ptr(self.row_w), row_q=N.ptr(self.row_q),
             row_cnt=N.ptr(self.row_cnt), part_cnt=N.ptr(self.part_cnt), part_t=N.ptr(self.part_t), cap_seeds=V, cap_sel=V, ctr=N.ptr(self.ctr))
         self.gview = N.Graph(num_nodes=V, num_edges=g.num_edges(), indptr=N.ptr(g.indptr),

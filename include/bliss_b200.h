@@ -83,6 +83,7 @@ typedef struct bliss_workspace {
   int64_t*  row_a;      /* [S]  CSC start of every seed's column (by seed rank)           */
   int32_t*  row_d;      /* [S]  in-degree of every seed                                   */
   int32_t*  chunk_first;/* [S+1] first 256-edge chunk of every seed's column (prefix)     */
+  void*     chunk_rec;  /* [E/256+V] 32-byte record per chunk (CSC start, length, row, degree, offset, chunk range) */
   double*   part_w;     /* [E/256+V] per-chunk partial of sum_j w_ij                      */
   double*   part_q;     /* [E/256+V] per-chunk partial of sum_j q_ij                      */
   float*    row_w;      /* [S]  sum_j w_ij  per seed                                      */
