@@ -189,12 +189,20 @@ __global__ void __launch_bounds__(256) k_plan_chunks(bliss_workspace ws) {
     }
   }
 }
-// Σ of a row's chunk partials: lanes take the chunks round-robin, then a butterfly — a fixed
-// order (deterministic), every lane ends with the same bits.
+// Σ of a row's chunk partials: lanes take the chunks round-robin (the first three per lane are loaded
+// together: 96 chunks = 24 K edges cover all but the largest hubs in one round trip), then a
+// butterfly — a fixed order (deterministic), every lane ends with the same bits.
+__device__ __forceinline__ double row_partials(const double* __restrict__ part, int c_first, int c_last) {
+  const int c = c_first + lane_id();
+  const double v0 = (c < c_last) ? __ldg(part + c) : 0.0;
+  const double v1 = (c + 32 < c_last) ? __ldg(part + c + 32) : 0.0;
+  const double v2 = (c + 64 < c_last) ? __ldg(part + c + 64) : 0.0;
+  double t = (v0 + v1) + v2;
+  for (int cc = c + 96; cc < c_last; cc += 32) t += __ldg(part + cc);
+  return warp_sum(t);
+}
 __device__ __forceinline__ float row_total(const double* __restrict__ part, int c_first, int c_last) {
-  double t = 0.0;
-  for (int c = c_first + lane_id(); c < c_last; c += 32) t += part[c];
-  return __double2float_rn(warp_sum(t));
+  return __double2float_rn(row_partials(part, c_first, c_last));
 }
 
 // for (ChunkLoop q(cursor, n_chunks); q.more(); q.next()) { const int c = q.chunk(); ... }
@@ -681,13 +689,6 @@ struct FillCtx {
   int mode;
 };
 
-__device__ __forceinline__ void note_first(int src, int local, unsigned long long key, const bliss_workspace& ws) {
-  if (local < 0) {  // selected non-seed (-2); seeds hold their rank >= 0
-    unsigned long long cur = __ldcg((const unsigned long long*)&ws.first_pos[src]);
-    if (key < cur) atomicMin((unsigned long long*)&ws.first_pos[src], key);
-  }
-}
-
 // Kept edges are sparse in a chunk (~8 % of the bits at Reddit fan-outs), so the dependent random
 // accesses (node_info -> first_pos -> atomicMin, weight -> q -> W~) are not done inside the word
 // loop, where only 2-3 lanes per warp would be active: the kept positions go to a per-warp
@@ -737,16 +738,19 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_count(FillCtx c, bliss_w
     double t = 0.0;
     if (cnt) {
       const unsigned long long key_hi = (unsigned long long)(r.row + 1) << 32;
-      const float row_w = (bandit && r.d > 0) ? ws.row_w[r.row] : 1.0f;
+      const float row_w = (bandit && r.d > 0) ? __ldg(ws.row_w + r.row) : 1.0f;
       const float eta_n = __fdiv_rn(c.eta, (float)r.d);
       for (int j = lane; j < cnt; j += 32) {
         const int k = lk[j];
-        const int sj = __ldg(idx + k);
-        const int2 info = *reinterpret_cast<const int2*>(&ws.node_info[2 * sj]);
-        note_first(sj, info.x, key_hi | (unsigned)(r.k0 + k), ws);
+        const int sj = __ldg(idx + k);                       // L1 hit: this warp streamed it a moment ago
+        // independent loads, one round trip: (selected mark, P), current first-occurrence key, weight
+        const int2 info = __ldg(reinterpret_cast<const int2*>(ws.node_info) + sj);
+        const unsigned long long cur = __ldcg((const unsigned long long*)&ws.first_pos[sj]);
+        const float wv = bandit ? __ldg(c.W + r.a + k) : 0.0f;
+        const unsigned long long key = key_hi | (unsigned)(r.k0 + k);
+        if (info.x < 0 && key < cur) atomicMin((unsigned long long*)&ws.first_pos[sj], key);   // selected non-seed
         if (bandit)   // also with importance_sampling=0: q_ij is still built from W (:354-358)
-          t += (double)__fdiv_rn(edge_q(__ldg(c.W + r.a + k), row_w, eta_n, c.one_minus_eta),
-                                 __int_as_float(info.y));
+          t += (double)__fdiv_rn(edge_q(wv, row_w, eta_n, c.one_minus_eta), __int_as_float(info.y));
       }
     }
     if (bandit) t = warp_sum(t);
@@ -833,6 +837,28 @@ __global__ void __launch_bounds__(1024) k_block_index(const int32_t* __restrict_
       for (int64_t i = n_seeds + gt; i < out.pad_rows; i += gn) out.inv_deg[i] = 1.0f;
     if (out.out_deg)   // padded sources have no edges (their counts feed the transpose scan)
       for (int64_t i = n_seeds + n_sel + gt; i < out.pad_src; i += gn) out.out_deg[i] = 0;
+    // per row (one warp each): the kept-edge prefix of its chunks and its ΣW~, so the fill starts every
+    // chunk from two loads instead of re-adding the row's partials chunk by chunk
+    for (int i = (int)(gt >> 5); i < n_seeds; i += (int)(gn >> 5)) {
+      const int c_first = ws.chunk_first[i], c_last = ws.chunk_first[i + 1];
+      int run = 0;
+      double t = 0.0;
+      for (int c0 = c_first; c0 < c_last; c0 += 32) {
+        const int cix = c0 + lane;
+        const int n = (cix < c_last) ? __ldg(ws.part_cnt + cix) : 0;
+        if (cix < c_last) t += __ldg(ws.part_t + cix);   // not written by the LADIES count: unused there
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        if (cix < c_last) ws.chunk_pre[cix] = run + incl - n;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      t = warp_sum(t);
+      if (lane == 0) ws.row_t[i] = __double2float_rn(t);
+    }
     if (out.t_bits) {  // source x destination bitmap of the block (transpose): clear this block's source rows
       // (whole rows: an earlier, larger block may have left bits beyond this block's destinations)
       const int64_t rows = min((int64_t)n_seeds + n_sel, out.pad_src > 0 ? out.pad_src : out.cap_src);
@@ -898,23 +924,18 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_fill(FillCtx c, bliss_wo
   unsigned char* lk = s_k[warp_id()];
   for (ChunkLoop q(&ctr->queue[4], n_chunks); q.more(); q.next()) {
     const int ch = q.chunk();
-    const int cnt = ws.part_cnt[ch];
-    if (cnt == 0) continue;   // warp-uniform
+    // round trip 1: everything that depends on the chunk id only
+    const int cnt = __ldg(ws.part_cnt + ch);
     const ChunkRef r = chunk_ref(ws, ch);
-    // kept edges of the row before this chunk, of the whole row, and the row's ΣW~
-    int pre = 0, tot = 0;
-    double t = 0.0;
-    for (int cc = r.c_first + lane; cc < r.c_last; cc += 32) {
-      const int n = ws.part_cnt[cc];
-      tot += n;
-      if (cc < ch) pre += n;
-      if (bandit) t += ws.part_t[cc];
-    }
-    pre = warp_sum(pre);
-    tot = warp_sum(tot);
-    float f = (float)tot;                                   // ladies: W~ *= d
-    if (bandit) f = __fdiv_rn(f, __double2float_rn(warp_sum(t)));   // bandit: W~ *= d / ΣW~
-    const unsigned myword = (lane < BLISS_CHUNK / 32) ? ws.keep_bits[(int64_t)ch * (BLISS_CHUNK / 32) + lane] : 0u;
+    const unsigned myword = (lane < BLISS_CHUNK / 32) ? __ldg(ws.keep_bits + (int64_t)ch * (BLISS_CHUNK / 32) + lane) : 0u;
+    if (cnt == 0) continue;   // warp-uniform
+    const int pre = __ldg(ws.chunk_pre + ch);   // kept edges of the row before this chunk (k_block_index)
+    // round trip 2: the row's block offset, kept count and ΣW~, and this lane's first kept edge
+    // (index, weight, edge id) — all independent, issued together
+    const int row_base = __ldg(out.indptr + r.row);
+    const int tot = __ldg(ws.row_cnt + r.row);
+    const float row_t = bandit ? __ldg(ws.row_t + r.row) : 1.0f;
+    const float row_w = (bandit && r.d > 0) ? __ldg(ws.row_w + r.row) : 1.0f;
     int n = 0;
 #pragma unroll
     for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
@@ -923,21 +944,31 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_fill(FillCtx c, bliss_wo
       n += __popc(bits);
     }
     __syncwarp();
-    const float row_w = (bandit && r.d > 0) ? ws.row_w[r.row] : 1.0f;
+    int64_t p = r.a + ((lane < cnt) ? lk[lane] : 0);
+    int src = __ldg(c.g.indices + p);
+    float wv = __ldg(c.W + p);
+    int eidv = (out.eid && c.g.eid) ? __ldg(c.g.eid + p) : (int32_t)p;
+    // round trip 3: (local id, P) of the source
+    int2 info = __ldg(reinterpret_cast<const int2*>(ws.node_info) + src);
+    float f = (float)tot;                                   // ladies: W~ *= d
+    if (bandit) f = __fdiv_rn(f, row_t);                    // bandit: W~ *= d / ΣW~
     const float eta_n = __fdiv_rn(c.eta, (float)r.d);
-    const int base = out.indptr[r.row] + pre;
+    const int base = row_base + pre;
     for (int j = lane; j < cnt; j += 32) {
-      const int64_t p = r.a + lk[j];
-      const int src = __ldg(c.g.indices + p);
-      const int2 info = *reinterpret_cast<const int2*>(&ws.node_info[2 * src]);
-      const float wv = __ldg(c.W + p);
+      if (j >= 32) {   // chunks that keep more than 32 edges: the remaining ones, one round trip chain each
+        p = r.a + lk[j];
+        src = __ldg(c.g.indices + p);
+        wv = __ldg(c.W + p);
+        eidv = (out.eid && c.g.eid) ? __ldg(c.g.eid + p) : (int32_t)p;
+        info = __ldg(reinterpret_cast<const int2*>(ws.node_info) + src);
+      }
       const float qv = bandit ? edge_q(wv, row_w, eta_n, c.one_minus_eta) : wv;
       const float wt = __fmul_rn(__fdiv_rn(qv, __int_as_float(info.y)), f);
       const int slot = base + j;
       out.edge_src[slot] = info.x;
       out.edge_dst[slot] = r.row;
       out.csc_pos[slot] = p;
-      if (out.eid) out.eid[slot] = c.g.eid ? c.g.eid[p] : (int32_t)p;
+      if (out.eid) out.eid[slot] = eidv;
       if (out.q_ij) out.q_ij[slot] = qv;
       out.edge_w[slot] = wt;
       if (out.out_deg) atomicAdd(&out.out_deg[info.x], 1);

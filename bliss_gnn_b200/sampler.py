@@ -60,6 +60,8 @@ class _Workspace:
         self.row_cnt = torch.empty(V, **i32)
         self.part_cnt = torch.empty(n_chunk_cap, **i32)
         self.part_t = torch.empty(n_chunk_cap, dtype=torch.float64, device=dev)
+        self.chunk_pre = torch.empty(n_chunk_cap, **i32)
+        self.row_t = torch.empty(V, dtype=torch.float32, device=dev)
         self.src_nid = torch.empty(V, **i32)
         self.node_prob = torch.empty(V, dtype=torch.float32, device=dev)
         self.key_scratch = None
@@ -78,7 +80,8 @@ class _Workspace:
             row_a=N.ptr(self.row_a), row_d=N.ptr(self.row_d),
             chunk_first=N.ptr(self.chunk_first), chunk_rec=N.ptr(self.chunk_rec), part_w=N.ptr(self.part_w),
             part_q=N.ptr(self.part_q), row_w=N.ptr(self.row_w), row_q=N.ptr(self.row_q),
-            row_cnt=N.ptr(self.row_cnt), part_cnt=N.ptr(self.part_cnt), part_t=N.ptr(self.part_t), cap_seeds=V, cap_sel=V, ctr=N.ptr(self.ctr))
+            row_cnt=N.ptr(self.row_cnt), part_cnt=N.ptr(self.part_cnt), part_t=N.ptr(self.part_t), chunk_pre=N.ptr(self.chunk_pre),
+            row_t=N.ptr(self.row_t), cap_seeds=V, cap_sel=V, ctr=N.ptr(self.ctr))
         self.gview = N.Graph(num_nodes=V, num_edges=g.num_edges(), indptr=N.ptr(g.indptr),
                              indices=N.ptr(g.indices), eid=N.ptr(g.eid))
         self._keep = (g.indptr, g.indices, g.eid)

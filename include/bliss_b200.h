@@ -91,6 +91,8 @@ typedef struct bliss_workspace {
   int32_t*  row_cnt;    /* [S]  kept in-edges per seed                                    */
   int32_t*  part_cnt;   /* [E/256+V] kept in-edges per chunk                              */
   double*   part_t;     /* [E/256+V] per-chunk partial of the unnormalised block weights  */
+  int32_t*  chunk_pre;  /* [E/256+V] kept in-edges of the chunk's row before the chunk    */
+  float*    row_t;      /* [S]  sum of the unnormalised block weights per seed            */
   int64_t   cap_seeds;  /* S */
   int64_t   cap_sel;    /* C */
   bliss_counters* ctr;  /* one counters block                                             */
