@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libbliss_b200.so")
-SOURCES = ["sampler.cu", "aggregate.cu", "bandit.cu", "gat.cu", "optim.cu"]
+SOURCES = ["sampler.cu", "aggregate.cu", "bandit.cu", "gat.cu", "optim.cu", "epilogue.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -131,6 +131,9 @@ PROTOTYPES = {
     "bliss_l1_norm": [_P, _I64, _P, _P, _P],
     "bliss_scale_by_inv": [_P, _I64, _P, _D, _P],
     "bliss_adam_step": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _P, _I32, _P],
+    "bliss_sage_epilogue_parts": [],
+    "bliss_sage_epilogue_fwd": [_P, _P, _P, _I32, _I32, _I32, _F, _U64, _P, _U32, _P, _P, _P],
+    "bliss_sage_epilogue_bwd": [_P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P],
 }
 
 _lib = None
@@ -159,7 +162,8 @@ class BlissNativeError(RuntimeError):
 #: kernels each entry point launches (for the ``gpu_launches`` count of bench.py)
 LAUNCHES = {"bliss_frontier_prob": 4, "bliss_sample_layer_front": 11, "bliss_poisson_select": 2, "bliss_frontier_plan": 3, "bliss_sample_layer_back": 2,
             "bliss_select_topk": 3, "bliss_block_transpose": 3, "bliss_l1_norm": 2, "bliss_version": 0,
-            "bliss_adam_step": 2, "bliss_spmm": 2}
+            "bliss_adam_step": 2, "bliss_spmm": 2, "bliss_sage_epilogue_bwd": 2,
+            "bliss_sage_epilogue_parts": 0}
 
 
 class _Stats:

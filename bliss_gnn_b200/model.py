@@ -17,14 +17,14 @@ from . import ops
 from .graph import Graph
 
 
-def _linear(x, lin: nn.Linear):
+def _linear(x, lin: nn.Linear, use_bias: bool = True):
     """``lin(x)``; when the feature table's rows were zero-padded to a 16-byte multiple
     (``train.DataModule(pad_features=True)``: 602 -> 604 columns keeps cuBLAS off its unaligned
     kernels, ~2-3x on the input-layer GEMMs) the weight is zero-padded to match — same result."""
     extra = x.shape[-1] - lin.in_features
-    if extra == 0:
-        return lin(x)
-    return torch.nn.functional.linear(x, torch.nn.functional.pad(lin.weight, (0, extra)), lin.bias)
+    bias = lin.bias if use_bias else None
+    w = lin.weight if extra == 0 else torch.nn.functional.pad(lin.weight, (0, extra))
+    return torch.nn.functional.linear(x, w, bias)
 
 
 class SAGEConv(nn.Module):
@@ -46,7 +46,8 @@ class SAGEConv(nn.Module):
         nn.init.xavier_uniform_(self.fc_self.weight, gain=gain)
         nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
 
-    def forward(self, graph, feat, edge_weight=None):
+    def forward_parts(self, graph, feat, edge_weight=None, use_bias=False):
+        """The two summands of the layer output: ``(fc_self(h_dst) [without its bias], h_neigh)``."""
         feat_src = self.feat_drop(feat)
         feat_dst = feat_src[: graph.number_of_dst_nodes()]
         lin_before_mp = self._in_src_feats > self._out_feats
@@ -54,7 +55,11 @@ class SAGEConv(nn.Module):
         h_neigh = ops.spmm(graph, h, edge_weight, dst_scale=ops.mean_scale(graph))   # u_mul_e + fn.mean
         if not lin_before_mp:
             h_neigh = _linear(h_neigh, self.fc_neigh)
-        return _linear(feat_dst, self.fc_self) + h_neigh
+        return _linear(feat_dst, self.fc_self, use_bias=use_bias), h_neigh
+
+    def forward(self, graph, feat, edge_weight=None):
+        h_self, h_neigh = self.forward_parts(graph, feat, edge_weight, use_bias=True)
+        return h_self + h_neigh
 
 
 class GraphConv(nn.Module):
@@ -182,13 +187,34 @@ class SAGE(nn.Module):
         self.activation = activation
 
     def forward(self, blocks, x):
-        h = x
+        h, norm = x, None
+        fuse = self.activation is torch.nn.functional.relu and x.is_cuda
+        if fuse and self.training and self.dropout.p > 0:
+            self._drop_step(x.device).add_(1)           # one Philox step per forward pass (device scalar: replayable)
         for l, (layer, block) in enumerate(zip(self.layers, blocks)):
-            block.srcdata["embed_norm"] = ops.row_norm(h)                             # :318
+            block.srcdata["embed_norm"] = ops.row_norm(h) if norm is None else norm       # :318
+            norm = None
+            last = l == len(self.layers) - 1
+            if not last and fuse and layer._out_feats % 4 == 0 and layer._out_feats <= 1024:
+                # bias + relu + dropout (:330-332) and the next layer's embed_norm in one launch
+                h_self, h_neigh = layer.forward_parts(block, h, edge_weight=_edge_weights(block))   # :321-329
+                p = self.dropout.p if self.training else 0.0
+                h, norm = ops.sage_epilogue(h_self, h_neigh, layer.fc_self.bias, True, p, self._drop_seed,
+                                            self._drop_step(x.device) if p > 0 else None, l, True)
+                continue
             h = layer(block, h, edge_weight=_edge_weights(block))                         # :321-329
-            if l < len(self.layers) - 1:
+            if not last:
                 h = self.dropout(self.activation(h))                                      # :330-332
         return h
+
+    _drop_seed = 0x5EED
+
+    def _drop_step(self, device):
+        t = getattr(self, "_drop_step_t", None)
+        if t is None or t.device != device:
+            t = torch.zeros(1, dtype=torch.int64, device=device)
+            self._drop_step_t = t
+        return t
 
     def inference(self, g, device, batch_size, use_uva=False, num_workers=0):
         """``model.py:335-383``: layer-wise full-neighbour inference (no sampling, no edge weights).

@@ -207,3 +207,46 @@ def gatv2_attention(block, feat, attn, negative_slope, drop_mask=None):
     if drop_mask is not None:
         drop_mask = _req(drop_mask, name="drop_mask")
     return _GATv2.apply(feat, attn, block, drop_mask, float(negative_slope))
+
+
+class _SageEpilogue(torch.autograd.Function):
+    """``dropout(relu(a + b + bias))`` + row norms, one launch each way (``csrc/epilogue.cu``)."""
+
+    @staticmethod
+    def forward(ctx, a, b, bias, relu, p_drop, seed, step_dev, layer, want_norm):
+        a, b = _req(a, name="a"), _req(b, name="b")
+        n, d = a.shape
+        y = torch.empty_like(a)
+        norm = torch.empty(n, dtype=torch.float32, device=a.device) if want_norm else None
+        N.call("bliss_sage_epilogue_fwd", N.ptr(a), N.ptr(b), N.ptr(bias), n, d, int(relu), float(p_drop), int(seed),
+               N.ptr(step_dev), int(layer), N.ptr(y), N.ptr(norm), N.stream())
+        ctx.save_for_backward(y)
+        ctx.gate, ctx.p_drop, ctx.has_bias = bool(relu), float(p_drop), bias is not None
+        if norm is None:
+            norm = y.new_empty(0)
+        ctx.mark_non_differentiable(norm)
+        return y, norm
+
+    @staticmethod
+    def backward(ctx, gy, _gnorm):
+        (y,) = ctx.saved_tensors
+        gy = _req(gy, name="grad")
+        n, d = y.shape
+        gz = torch.empty_like(y)
+        gbias = partial = None
+        if ctx.has_bias:
+            partial = torch.empty((N.lib().bliss_sage_epilogue_parts(), d), dtype=torch.float32, device=y.device)
+            gbias = torch.empty(d, dtype=torch.float32, device=y.device)
+        if not ctx.gate and ctx.p_drop > 0:
+            raise RuntimeError("sage_epilogue: dropout without relu is not supported (the gate is read off y > 0)")
+        N.call("bliss_sage_epilogue_bwd", N.ptr(gy), N.ptr(y), n, d, int(ctx.gate), ctx.p_drop, N.ptr(gz),
+               N.ptr(partial), N.ptr(gbias), N.stream())
+        return gz, gz, gbias, None, None, None, None, None, None
+
+
+def sage_epilogue(a, b, bias, relu=True, p_drop=0.0, seed=0, step_dev=None, layer=0, want_norm=True):
+    """``y = dropout(relu(a + b + bias), p_drop)`` and ``||y_r||_2`` per row — the tail of a hidden SAGE layer
+    (``model.py:321-332``) and the next layer's ``embed_norm`` (``model.py:318``).  Differentiable w.r.t.
+    ``a``, ``b`` and ``bias``.  Dropout draws are Philox(seed; element, layer, ``*step_dev``)."""
+    y, norm = _SageEpilogue.apply(a, b, bias, relu, p_drop, seed, step_dev, layer, want_norm)
+    return (y, norm) if want_norm else (y, None)

@@ -264,6 +264,22 @@ int bliss_l1_norm(const float* w, int64_t n, double* partial /* [1024] */, doubl
 int bliss_scale_by_inv(float* w, int64_t n, const double* norm, double eps, void* stream);
 
 
+/* ---- hidden-layer epilogue (SAGE) ------------------------------------------------------------
+ * replaces `fc_self(h_dst) + h_neigh` bias add, `activation` = relu, `dropout` (model.py:321-332) and the
+ * next layer's `th.norm(h, dim=1)` (model.py:318) — and their backward passes plus the bias-gradient
+ * reduction — with one launch each way.  dim % 4 == 0, dim <= 1024, 16-byte aligned rows.
+ * Dropout: u = Philox4x32-10(key = seed, ctr = (element / 4, layer, step)) words -> [0,1); kept iff
+ * u < 1 - p, scaled by 1 / (1 - p); *step_dev is read on the device (CUDA-graph replay). */
+int bliss_sage_epilogue_parts(void);   /* rows of the bias_partial scratch (= CTAs of the backward launch) */
+int bliss_sage_epilogue_fwd(const float* a, const float* b, const float* bias /* [dim] or NULL */,
+                            int32_t n_rows, int32_t dim, int32_t relu, float p_drop, uint64_t seed,
+                            const int64_t* step_dev, uint32_t layer, float* y,
+                            float* row_norm /* [n_rows] or NULL */, void* stream);
+int bliss_sage_epilogue_bwd(const float* grad_y, const float* y, int32_t n_rows, int32_t dim,
+                            int32_t gate /* 1: grad_z = grad_y * [y > 0] / (1 - p); 0: grad_z = grad_y */,
+                            float p_drop, float* grad_z, float* bias_partial /* [parts, dim] or NULL */,
+                            float* grad_bias /* [dim] or NULL */, void* stream);
+
 /* ---- optimizer step ------------------------------------------------------------------------
  * replaces torch.optim.Adam(params, lr).step() (train_lightning.py:205-216; betas / eps given by the
  * caller, no weight decay, no amsgrad) over flat, 16-byte aligned fp32 buffers: parameters, gradients

@@ -313,3 +313,45 @@ def test_flat_adam_matches_torch_adam(native_lib):
         for p, q in zip(ref_p, my_p):
             _close(q.detach(), p.detach(), rtol=2e-6, what=f"adam step {step}")
     assert int(my_opt.step_dev.item()) == 25
+
+
+@pytest.mark.parametrize("dim,p", [(64, 0.0), (256, 0.0), (256, 0.3), (1024, 0.1), (36, 0.5)])
+def test_sage_epilogue_matches_torch(native_lib, dim, p):
+    """``ops.sage_epilogue`` = dropout(relu(a + b + bias)) with row norms (``model.py:321-332,318``): exact
+    against torch without dropout; with dropout the kept elements, the drop rate and the backward pass
+    (through the realised mask) are checked."""
+    from bliss_gnn_b200 import ops
+    dev = _dev()
+    torch.manual_seed(dim)
+    n = 777
+    a = torch.randn(n, dim, device=dev, requires_grad=True)
+    b = torch.randn(n, dim, device=dev, requires_grad=True)
+    bias = torch.randn(dim, device=dev, requires_grad=True)
+    step = torch.full((1,), 5, dtype=torch.int64, device=dev)
+    y, norm = ops.sage_epilogue(a, b, bias, True, p, seed=11, step_dev=step if p > 0 else None, layer=1)
+    z = torch.relu(a.detach() + b.detach() + bias.detach())
+    if p == 0.0:
+        assert torch.equal(y, z)
+        mask = torch.ones_like(z)
+    else:
+        mask = ((y != 0) | (z == 0)).float()
+        kept = mask.bool() & (z > 0)
+        _close(y[kept], z[kept] / (1 - p), rtol=2e-7, what="kept elements")
+        rate = 1.0 - mask[z > 0].mean().item()
+        assert abs(rate - p) < 0.02, rate
+        y2, _ = ops.sage_epilogue(a, b, bias, True, p, seed=11, step_dev=step, layer=1)
+        assert torch.equal(y, y2), "same (seed, step, layer) must give the same mask"
+        step.add_(1)
+        y3, _ = ops.sage_epilogue(a, b, bias, True, p, seed=11, step_dev=step, layer=1)
+        assert not torch.equal(y, y3)
+    _close(norm, y.detach().norm(dim=1), rtol=2e-6, what="row norms")
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    a2 = a.detach().clone().requires_grad_(True)
+    b2 = b.detach().clone().requires_grad_(True)
+    bias2 = bias.detach().clone().requires_grad_(True)
+    ref = torch.relu(a2 + b2 + bias2) * mask / (1 - p)
+    ref.backward(gy)
+    _close(a.grad, a2.grad, rtol=2e-7, what="grad a")
+    _close(b.grad, b2.grad, rtol=2e-7, what="grad b")
+    _close(bias.grad, bias2.grad, rtol=2e-5, what="grad bias")
