@@ -241,7 +241,10 @@ class Trainer:
             self._exchange = BanditExchange(cap_e, self.world, dev, self.pg)
         pools, cd = [None] * L, dm.batch_size
         for l in reversed(range(L)):                       # output layer first: cap_dst[l] = cap_src[l+1]
-            cap_src = max(cd + int(1.3 * fan[l]) + 256, int(1.25 * self._max_src[l]) + 64)
+            # sources = destinations + Poisson-selected nodes (mean <= fan-out, sigma <= sqrt(fan-out)); the high-water
+            # mark in _consume_counters re-sizes long before a capacity can be hit
+            cap_src = max(cd + fan[l] + int(6 * math.sqrt(fan[l])) + 64, int(1.12 * self._max_src[l]) + 64)
+            cap_src = (cap_src + 63) // 64 * 64            # row counts the split-K weight gradients divide evenly
             pools[l] = LayerPool(dev, cd, cap_src, cap_e[l], bandit=bandit,
                                  csc_pos=self._exchange.pos[l] if self._exchange is not None else None)
             cd = cap_src
