@@ -132,6 +132,7 @@ PROTOTYPES = {
     "bliss_scale_by_inv": [_P, _I64, _P, _D, _P],
     "bliss_adam_step": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _P, _I32, _P],
     "bliss_sage_epilogue_parts": [],
+    "bliss_xent_mean": [_P, _P, _I32, _I32, _P, _P, _P, _P],
     "bliss_sage_epilogue_fwd": [_P, _P, _P, _I32, _I32, _I32, _F, _U64, _P, _U32, _P, _P, _P],
     "bliss_sage_epilogue_bwd": [_P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P],
 }
@@ -163,7 +164,7 @@ class BlissNativeError(RuntimeError):
 LAUNCHES = {"bliss_frontier_prob": 4, "bliss_sample_layer_front": 11, "bliss_poisson_select": 2, "bliss_frontier_plan": 3, "bliss_sample_layer_back": 2,
             "bliss_select_topk": 3, "bliss_block_transpose": 3, "bliss_l1_norm": 2, "bliss_version": 0,
             "bliss_adam_step": 2, "bliss_spmm": 2, "bliss_sage_epilogue_bwd": 2,
-            "bliss_sage_epilogue_parts": 0}
+            "bliss_sage_epilogue_parts": 0, "bliss_xent_mean": 2}
 
 
 class _Stats:

@@ -106,12 +106,60 @@ __global__ void __launch_bounds__(256) k_sage_epilogue_bwd(const float* __restri
   }
 }
 
-__global__ void k_colsum_final(const float* __restrict__ partial, int n_parts, int dim, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= dim) return;
+// out[c] = Σ_k partial[k][c], k ascending within each of 8 interleaved groups, groups added in order
+// (a fixed order).  A CTA takes 32 columns x 8 groups, so the ~150 partials of a column are read as
+// 19 independent loads per thread instead of one serial chain.
+__global__ void __launch_bounds__(256) k_colsum_final(const float* __restrict__ partial, int n_parts, int dim,
+                                                     float* __restrict__ out) {
+  __shared__ float s_g[8][33];
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float t = 0.0f;
-  for (int k = 0; k < n_parts; ++k) t += partial[(int64_t)k * dim + c];
-  out[c] = t;
+  if (c < dim)
+    for (int k = g; k < n_parts; k += 8) t += __ldg(partial + (int64_t)k * dim + c);
+  s_g[g][cl] = t;
+  __syncthreads();
+  if (g == 0 && c < dim) {
+    float r = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += s_g[w][cl];
+    out[c] = r;
+  }
+}
+
+// Cross-entropy with mean reduction over the seed batch (train_lightning.py:77-79,142: nn.CrossEntropyLoss())
+// and its gradient in one pass: one warp per row, loss = mean_r (logsumexp(x_r) - x_r[y_r]),
+// grad = (softmax(x_r) - onehot(y_r)) / n.  The row losses are added in row order by one warp
+// (deterministic); the gradient is scaled by the upstream scalar in the backward wrapper.
+__global__ void __launch_bounds__(256) k_xent(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                             int n_rows, int n_cls, float* __restrict__ row_loss,
+                                             float* __restrict__ grad) {
+  const int lane = lane_id();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float inv_n = 1.0f / (float)n_rows;
+  for (int r = warp; r < n_rows; r += nwarps) {
+    const float* __restrict__ x = logits + (int64_t)r * n_cls;
+    float m = -INFINITY;
+    for (int c = lane; c < n_cls; c += 32) m = fmaxf(m, x[c]);
+    m = warp_max(m);
+    float s = 0.0f;
+    for (int c = lane; c < n_cls; c += 32) s += expf(x[c] - m);
+    s = warp_sum(s);
+    const int y = (int)labels[r];
+    if (lane == 0) row_loss[r] = (logf(s) + m) - x[y];
+    const float inv_s = 1.0f / s;
+    for (int c = lane; c < n_cls; c += 32)
+      grad[(int64_t)r * n_cls + c] = (expf(x[c] - m) * inv_s - (c == y ? 1.0f : 0.0f)) * inv_n;
+  }
+}
+__global__ void __launch_bounds__(32) k_xent_mean(const float* __restrict__ row_loss, int n_rows, float* __restrict__ loss) {
+  float t = 0.0f;
+  for (int r0 = 0; r0 < n_rows; r0 += 32) {   // row order within a lane, lanes by butterfly: fixed
+    const int r = r0 + lane_id();
+    t += (r < n_rows) ? row_loss[r] : 0.0f;
+  }
+  t = warp_sum(t);
+  if (lane_id() == 0) *loss = t / (float)n_rows;
 }
 
 }  // namespace bliss
@@ -150,9 +198,23 @@ int bliss_sage_epilogue_bwd(const float* grad_y, const float* y, int32_t n_rows,
   k_sage_epilogue_bwd<<<BLISS_SM_COUNT, 256, smem, st>>>(grad_y, y, n_rows, dim, gate, scale, grad_z, bias_partial);
   BLISS_CHECK_LAUNCH();
   if (grad_bias) {
-    k_colsum_final<<<(dim + 255) / 256, 256, 0, st>>>(bias_partial, BLISS_SM_COUNT, dim, grad_bias);
+    k_colsum_final<<<(dim + 31) / 32, 256, 0, st>>>(bias_partial, BLISS_SM_COUNT, dim, grad_bias);
     BLISS_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+
+int bliss_xent_mean(const float* logits, const int64_t* labels, int32_t n_rows, int32_t n_cls, float* row_loss,
+                    float* loss, float* grad, void* stream) {
+  if (n_rows <= 0 || n_cls <= 0 || !logits || !labels || !row_loss || !loss || !grad) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (n_rows + 7) / 8;
+  if (blocks > BLISS_SM_COUNT * 8) blocks = BLISS_SM_COUNT * 8;
+  k_xent<<<blocks, 256, 0, st>>>(logits, labels, n_rows, n_cls, row_loss, grad);
+  BLISS_CHECK_LAUNCH();
+  k_xent_mean<<<1, 32, 0, st>>>(row_loss, n_rows, loss);
+  BLISS_CHECK_LAUNCH();
   return 0;
 }
 

@@ -250,3 +250,28 @@ def sage_epilogue(a, b, bias, relu=True, p_drop=0.0, seed=0, step_dev=None, laye
     ``a``, ``b`` and ``bias``.  Dropout draws are Philox(seed; element, layer, ``*step_dev``)."""
     y, norm = _SageEpilogue.apply(a, b, bias, relu, p_drop, seed, step_dev, layer, want_norm)
     return (y, norm) if want_norm else (y, None)
+
+
+class _XentMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        logits = _req(logits, name="logits")
+        labels = _req(labels, torch.int64, "labels")
+        n, c = logits.shape
+        row = torch.empty(n, dtype=torch.float32, device=logits.device)
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        grad = torch.empty_like(logits)
+        N.call("bliss_xent_mean", N.ptr(logits), N.ptr(labels), n, c, N.ptr(row), N.ptr(loss), N.ptr(grad), N.stream())
+        ctx.save_for_backward(grad)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None
+
+
+def cross_entropy_mean(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """``nn.CrossEntropyLoss()(logits, labels)`` (``train_lightning.py:77-79,142``) with the gradient produced in
+    the forward launch."""
+    return _XentMean.apply(logits, labels)

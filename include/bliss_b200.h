@@ -280,6 +280,13 @@ int bliss_sage_epilogue_bwd(const float* grad_y, const float* y, int32_t n_rows,
                             float p_drop, float* grad_z, float* bias_partial /* [parts, dim] or NULL */,
                             float* grad_bias /* [dim] or NULL */, void* stream);
 
+/* ---- loss ------------------------------------------------------------------------------------
+ * replaces nn.CrossEntropyLoss() (mean reduction; train_lightning.py:77-79,142) forward AND backward:
+ * loss[0] = mean_r(logsumexp(x_r) - x_r[y_r]),  grad = (softmax(x_r) - onehot(y_r)) / n_rows. */
+int bliss_xent_mean(const float* logits /* [n_rows, n_cls] */, const int64_t* labels, int32_t n_rows,
+                    int32_t n_cls, float* row_loss /* [n_rows] scratch */, float* loss /* [1] */,
+                    float* grad /* [n_rows, n_cls] */, void* stream);
+
 /* ---- optimizer step ------------------------------------------------------------------------
  * replaces torch.optim.Adam(params, lr).step() (train_lightning.py:205-216; betas / eps given by the
  * caller, no weight decay, no amsgrad) over flat, 16-byte aligned fp32 buffers: parameters, gradients

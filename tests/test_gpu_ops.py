@@ -355,3 +355,20 @@ def test_sage_epilogue_matches_torch(native_lib, dim, p):
     _close(a.grad, a2.grad, rtol=2e-7, what="grad a")
     _close(b.grad, b2.grad, rtol=2e-7, what="grad b")
     _close(bias.grad, bias2.grad, rtol=2e-5, what="grad bias")
+
+
+@pytest.mark.parametrize("n,c", [(256, 41), (32, 7), (1000, 100), (5, 3)])
+def test_cross_entropy_mean_matches_torch(native_lib, n, c):
+    """``ops.cross_entropy_mean`` == ``nn.CrossEntropyLoss()`` (``train_lightning.py:77-79``), value and gradient."""
+    from bliss_gnn_b200 import ops
+    dev = _dev()
+    torch.manual_seed(n + c)
+    x = (torch.randn(n, c, device=dev) * 3).requires_grad_(True)
+    y = torch.randint(0, c, (n,), device=dev)
+    loss = ops.cross_entropy_mean(x, y)
+    (loss * 1.7).backward()
+    x2 = x.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(x2, y)
+    (ref * 1.7).backward()
+    _close(loss.reshape(1), ref.reshape(1), rtol=2e-6, what="loss")
+    _close(x.grad, x2.grad, rtol=2e-6, what="grad")
