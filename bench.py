@@ -223,6 +223,7 @@ def main():
     torch.cuda.set_device(device)
     pg = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         torch.distributed.init_process_group("nccl", device_id=device)
         pg = torch.distributed.group.WORLD
     torch.set_float32_matmul_precision("medium")      # the reference's --precision default (train_lightning.py:550)
