@@ -458,7 +458,7 @@ class BanditLadiesSampler:
         return self._finish_block(fr, out, bufs, pool)
 
     # ---- sync-free path (CUDA-graph capture of the whole step) -----------------------------------
-    def enqueue_static(self, g, seeds_static, pools, step_dev):
+    def enqueue_static(self, g, seeds_static, pools, step_dev, transpose_stream=None):
         """Enqueue the sampling of every layer into the capacity pools with NO host synchronisation:
         each layer reads its true seed count from the previous layer's device counters, the Philox
         step from ``step_dev``, and the transpose its edge count from the counters.  Capturable in a
@@ -492,9 +492,15 @@ class BanditLadiesSampler:
                    0, block_id, self._u_ptr(g, block_id), N.ptr(wsp.key_scratch), C.byref(ws), C.byref(out), st)
             N.call("bliss_sample_layer_back", C.byref(wsp.gview), N.ptr(seeds), n_cap, N.ptr(weights), float(self.eta),
                    self._mode, C.byref(ws), C.byref(out), st)
+            # the transpose is read by the backward pass only: with ``transpose_stream`` it is forked off (the caller
+            # joins that stream before the backward pass) and runs beside the next layer's sampling
+            ts = st
+            if transpose_stream is not None:
+                transpose_stream.wait_stream(torch.cuda.current_stream())
+                ts = transpose_stream.cuda_stream
             N.call("bliss_block_transpose", N.ptr(e32[0]), N.ptr(e32[1]), pool.cap_edges, pool.cap_src, pool.cap_dst,
                    N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_bits), N.ptr(pool.t_pre), pool.t_words, N.ptr(pool.t_dst),
-                   N.ptr(pool.t_perm), N.ptr(pool.t_seg_ptr), 1, wsp.counter_ptr(block_id, "n_edges"), st)
+                   N.ptr(pool.t_perm), N.ptr(pool.t_seg_ptr), 1, wsp.counter_ptr(block_id, "n_edges"), ts)
 
     # ---- bandit update ------------------------------------------------------------------------
     def calculate_alpha(self, mfg):

@@ -262,13 +262,19 @@ class Trainer:
             padded.append(pb)
         self._pools, self._padded, self._graph = pools, padded, None
 
-    def _padded_fwd_bwd(self, step_optimizer: bool):
+    def _padded_fwd_bwd(self, step_optimizer: bool, after_forward=None, before_backward=None):
+        """``after_forward`` / ``before_backward``: hooks of the whole-step graph — work that only needs the
+        forward pass is forked onto side streams there, work the backward pass needs is joined."""
         g = self.dm.g
         x = ops.gather_rows(g.ndata["features"], self._pools[0].src_nid)
         y = g.ndata["labels"][self._seeds_static.long()]
         pred = self.model(self._padded, x)[: self.dm.batch_size]
         loss = self.loss_fn(pred, y)
+        if after_forward is not None:
+            after_forward()
         self._zero_grads()
+        if before_backward is not None:
+            before_backward()
         loss.backward()
         if step_optimizer:
             self._optimizer_step()
@@ -448,13 +454,28 @@ class Trainer:
         dp = self.world > 1 or self._force_dp
         bandit = "bandit" in dm.sampler_name
 
+        # Two side branches of the step's graph keep short kernels off the critical path: the block transposes
+        # (only the backward pass reads them) run beside the next layer's sampling / the forward pass, and the
+        # bandit update (needs embed_norm of the forward pass only) runs beside the backward pass and Adam.
+        if getattr(self, "_side_t", None) is None:
+            self._side_t, self._side_b = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def bandit_update():
+            main = torch.cuda.current_stream()
+            self._side_b.wait_stream(main)
+            with torch.cuda.stream(self._side_b):
+                if not dp:
+                    smp.exp3(self._padded, g, count_renorm=False)
+                else:        # data parallel: emit the exponents + counts into the exchange's send buffer
+                    smp.exp3_emit(self._padded, g, self._exchange)
+
         def body():          # graph A (the whole step on a single rank)
-            smp.enqueue_static(g, self._seeds_static, self._pools, self._step_dev)
-            loss, pred, y = self._padded_fwd_bwd(not dp)
-            if bandit and not dp:
-                smp.exp3(self._padded, g, count_renorm=False)
-            elif bandit:     # data parallel: emit the exponents + counts into the exchange's send buffer
-                smp.exp3_emit(self._padded, g, self._exchange)
+            main = torch.cuda.current_stream()
+            smp.enqueue_static(g, self._seeds_static, self._pools, self._step_dev, transpose_stream=self._side_t)
+            loss, pred, y = self._padded_fwd_bwd(not dp, after_forward=bandit_update if bandit else None,
+                                                 before_backward=lambda: main.wait_stream(self._side_t))
+            if bandit:
+                main.wait_stream(self._side_b)
             if not dp:
                 self._step_dev.add_(1)
             return loss, pred, y
@@ -501,232 +522,6 @@ class Trainer:
             with torch.cuda.graph(self._graph_b):
                 body_b()
         self.graph_kernels = _native.STATS.launches - before    # hand-written kernels inside one replay
-        _native.STATS.launches = before
-
-    def _training_step_static_partial(self, seeds: torch.Tensor) -> torch.Tensor:
-        """Eager sampling into the pools + replayed forward/backward(/Adam): the data-parallel variant
-        (the collectives sit between the sampler and the optimizer)."""
-        dm, g, smp = self.dm, self.dm.g, self.dm.sampler
-        L = len(smp.nodes_per_layer)
-        if self._pools is None:
-            if self.num_steps < self.eager_warmup or seeds.numel() != dm.batch_size:
-                _, _, mfgs = smp.sample_blocks(g, seeds)
-                if self._max_src is None:
-                    self._max_src, self._max_edges = [0] * L, [0] * L
-                for l, b in enumerate(mfgs):
-                    self._max_src[l] = max(self._max_src[l], b.num_src_nodes())
-                    self._max_edges[l] = max(self._max_edges[l], b.num_edges())
-                return self._eager_rest(mfgs)
-            self._alloc_pools()
-        if seeds.numel() != dm.batch_size:                  # ragged last batch: ordinary path
-            _, _, mfgs = smp.sample_blocks(g, seeds)
-            return self._eager_rest(mfgs)
-        self._seeds_static.copy_(seeds, non_blocking=True)
-        _, _, mfgs = smp.sample_blocks(g, self._seeds_static, pools=self._pools)
-        if not smp.pool_used:                               # per-stage sampler path (overridden stage / profiling)
-            return self._eager_rest(mfgs)
-        if smp.pool_overflow:                               # rare: grow the capacities, re-capture next step
-            for l, b in enumerate(mfgs):
-                self._max_src[l] = max(self._max_src[l], b.num_src_nodes())
-                self._max_edges[l] = max(self._max_edges[l], b.num_edges())
-            loss = self._eager_rest(mfgs)
-            self._alloc_pools()
-            return loss
-        for l, b in enumerate(mfgs):
-            ops.block_transpose_into(b, self._pools[l])
-        if self._graph is None:
-            self._capture()
-        self._ema(mfgs)
-        self._sync_lr()
-        self._graph.replay()
-        self.graph_replays += 1
-        if self.world > 1:
-            self.grads.all_reduce_mean_(self.pg)
-            self._optimizer_step()
-        for l, b in enumerate(mfgs):                        # what exp3 reads from the forward pass
-            pb = self._padded[l]
-            b.srcdata["embed_norm"] = pb.srcdata["embed_norm"][: b.num_src_nodes()]
-            if "a_ij" in dict.keys(pb.edata):
-                b.edata["a_ij"] = pb.edata["a_ij"][: b.num_edges()]
-        if "bandit" in dm.sampler_name:
-            smp.exp3(mfgs, g, exchange=self._exchange)
-        self.last_blocks, self.last_pred, self.last_labels = mfgs, self._static_pred, self._static_y
-        return self._static_loss
-
-    # ---- whole step in one CUDA graph (single rank): sampling included, one host sync per step ------
-    def _full_graph_ok(self) -> bool:
-        smp = self.dm.sampler
-        return smp._stages_not_overridden() and smp.inject_uniforms is None
-
-    def _training_step_full_graph(self, seeds: torch.Tensor) -> torch.Tensor:
-        dm, g, smp = self.dm, self.dm.g, self.dm.sampler
-        L = len(smp.nodes_per_layer)
-        if self._pools is None or seeds.numel() != dm.batch_size:
-            if self.num_steps < self.eager_warmup or seeds.numel() != dm.batch_size:
-                _, _, mfgs = smp.sample_blocks(g, seeds)           # ordinary steps: size the pools
-                if self._max_src is None:
-                    self._max_src, self._max_edges = [0] * L, [0] * L
-                for l, b in enumerate(mfgs):
-                    self._max_src[l] = max(self._max_src[l], b.num_src_nodes())
-                    self._max_edges[l] = max(self._max_edges[l], b.num_edges())
-                return self._eager_rest(mfgs)
-            self._alloc_pools()
-        if self._graph is None:
-            self._capture_full()
-        self._seeds_static.copy_(seeds, non_blocking=True)
-        self._sync_lr()
-        self._graph.replay()
-        if self._graph_b is not None:             # data parallel, two-graph form: the exchanges sit between the graphs
-            self._dp_exchange()
-            self._graph_b.replay()
-        slot = self.graph_replays & 1
-        self.graph_replays += 1
-        smp._wsp.enqueue_counter_read(slot)                    # stream-ordered D2H, no host wait
-        smp.step += 1
-        smp.tick_renorm(L)
-        if self.pipeline:                                      # consume the PREVIOUS step's counters
-            prev, self._pending = self._pending, slot
-            if prev is None:
-                return self._static_loss
-            slot = prev
-        self._consume_counters(smp._wsp.finish_counter_read(slot, L))
-        return self._static_loss
-
-    def flush(self):
-        """Consume the counters of the last enqueued step (pipelined mode)."""
-        if self._pending is not None:
-            slot, self._pending = self._pending, None
-            self._consume_counters(self.dm.sampler._wsp.finish_counter_read(slot, len(self.dm.sampler.nodes_per_layer)))
-
-    def _consume_counters(self, ctrs):
-        dm, g, smp = self.dm, self.dm.g, self.dm.sampler
-        L = len(smp.nodes_per_layer)
-        grow = False
-        for l, c in enumerate(ctrs):
-            if c.error:
-                raise RuntimeError(f"static step: capacity of layer {l} exceeded (n_src {c.n_src}/{self._pools[l].cap_src}, "
-                                   f"edges {c.n_edges}/{self._pools[l].cap_edges}); the step is invalid — "
-                                   "raise the pool margins (Trainer.pool_margin) or use static_graph=False")
-            self._max_src[l] = max(self._max_src[l], c.n_src)
-            self._max_edges[l] = max(self._max_edges[l], c.n_edges)
-            grow |= c.n_src > 0.92 * self._pools[l].cap_src or c.n_edges > 0.85 * self._pools[l].cap_edges
-        smp.last_counters = ctrs
-        self.num_steps += 1
-        for i, c in enumerate(ctrs):
-            self.cum_sampled_nodes[i] = self.cum_sampled_nodes[i] * self.w + c.n_src
-            self.cum_sampled_edges[i] = self.cum_sampled_edges[i] * self.w + c.n_edges
-        self.cum_sampled_nodes[L] = self.cum_sampled_nodes[L] * self.w + dm.batch_size
-        self.total_sampled_edges += sum(int(c.n_edges) for c in ctrs)
-        self.last_blocks = _CounterBlocks(ctrs)
-        self.last_pred, self.last_labels = self._static_pred, self._static_y
-        if self.world > 1:        # re-sizing allocates collectively: agree on it, every 32 steps
-            self._grow_pending = getattr(self, "_grow_pending", False) or grow
-            grow = False
-            if self.num_steps % 32 == 0:
-                flag = torch.tensor([1.0 if self._grow_pending else 0.0], device=g.device)
-                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX, group=self.pg)
-                grow, self._grow_pending = bool(flag.item() > 0), False
-        if grow:                                               # high-water mark: re-size before it can overflow
-            self._alloc_pools()
-
-    def _dp_exchange(self):
-        """The only exchanges of a data-parallel step: one all-reduce of the flat gradient buffer and one
-        all-gather of the packed sparse bandit updates."""
-        self.grads.all_reduce_mean_(self.pg)
-        if self._exchange is not None:
-            torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send, group=self.pg)
-
-    def _capture_full(self):
-        from . import _native
-        dm, g, smp = self.dm, self.dm.g, self.dm.sampler
-        L = len(smp.nodes_per_layer)
-        smp._bind(g)
-        if getattr(self, "_step_dev", None) is None:
-            self._step_dev = torch.zeros(1, dtype=torch.int64, device=g.device)
-        self._step_dev.fill_(smp.step)
-        for l, pb in enumerate(self._padded):
-            pool = self._pools[l]
-            pb._n_edges_dev = smp._wsp.counter_ptr(l, "n_edges")
-            if smp._mode == _native.MODE_BANDIT:
-                pb.edata["q_ij"] = pool.e32[4].view(torch.float32)
-                pb.srcdata[smp.node_prob] = pool.node_prob
-            dict.pop(pb.srcdata, "embed_norm", None)
-            dict.pop(pb.edata, "a_ij", None)
-        self.last_pred = None
-
-        dp = self.world > 1 or self._force_dp
-        bandit = "bandit" in dm.sampler_name
-
-        def body():          # graph A (the whole step on a single rank)
-            smp.enqueue_static(g, self._seeds_static, self._pools, self._step_dev)
-            loss, pred, y = self._padded_fwd_bwd(not dp)
-            if bandit and not dp:
-                smp.exp3(self._padded, g, count_renorm=False)
-            elif bandit:     # data parallel: emit the exponents + counts into the exchange's send buffer
-                smp.exp3_emit(self._padded, g, self._exchange)
-            if not dp:
-                self._step_dev.add_(1)
-            return loss, pred, y
-
-        def body_b():        # graph B (data parallel): after the all-reduce / all-gather
-            self._optimizer_step()
-            if bandit:
-                smp.exp3_apply(self._exchange, L)
-            self._step_dev.add_(1)
-
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        state = (smp.state_dict()["exp3_w_csc"].clone(), smp._l1.clone()) if smp._w_csc is not None else None
-        opt_state = None
-        with torch.cuda.stream(side):                       # warm-up replays off the default stream …
-            import copy
-            opt_state = copy.deepcopy(self.optimizer.state_dict())
-            params = [p.detach().clone() for p in self.grads.params]
-            self._seeds_static.copy_(self.dm.train_nid[: dm.batch_size])
-            for _ in range(2):
-                body()
-                if dp:
-                    self._dp_exchange()
-                    body_b()
-            # … must not change the training state: restore parameters, Adam moments, bandit weights
-            for p, q in zip(self.grads.params, params):
-                p.data.copy_(q)
-            self.optimizer.load_state_dict(opt_state)
-            if state is not None:
-                for l, w in enumerate(state[0]):
-                    smp._w_csc[l].copy_(w)
-                smp._l1.copy_(state[1])
-            self._step_dev.fill_(smp.step)
-        torch.cuda.current_stream().wait_stream(side)
-        before = _native.STATS.launches
-        self._graph_b = None
-        captured = False
-        if dp and not os.environ.get("BLISS_DP_TWO_GRAPHS"):
-            # one graph for the whole data-parallel step: NCCL's all-reduce / all-gather are captured between
-            # the two halves, so a step is a single replay with no host-side launch gap around the collectives
-            try:
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    out = body()
-                    self._dp_exchange()
-                    body_b()
-                self._graph, captured = graph, True
-                self._static_loss, self._static_pred, self._static_y = out
-            except Exception as e:                       # capture of the collectives not supported: two graphs
-                import warnings
-                warnings.warn(f"single-graph data-parallel capture failed ({type(e).__name__}: {e}); "
-                              "using two graphs with the collectives in between")
-                torch.cuda.synchronize()
-                _native.STATS.launches = before
-        if not captured:
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self._static_loss, self._static_pred, self._static_y = body()
-            if dp:
-                self._graph_b = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph_b):
-                    body_b()
-        self.graph_kernels = _native.STATS.launches - before
         _native.STATS.launches = before
 
     @torch.no_grad()
