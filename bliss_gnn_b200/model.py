@@ -60,6 +60,16 @@ def _linear(x, lin: nn.Linear, use_bias: bool = True):
     return torch.nn.functional.linear(x, w, bias)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    s = _SIDE_STREAMS.get(device)
+    if s is None:
+        s = _SIDE_STREAMS[device] = torch.cuda.Stream(device)
+    return s
+
+
 class SAGEConv(nn.Module):
     """``dglnn.SAGEConv(in_feats, out_feats, 'mean')`` with ``edge_weight``."""
 
@@ -84,11 +94,24 @@ class SAGEConv(nn.Module):
         feat_src = self.feat_drop(feat)
         feat_dst = feat_src[: graph.number_of_dst_nodes()]
         lin_before_mp = self._in_src_feats > self._out_feats
+        # the self projection does not depend on the aggregation: on CUDA it runs on a side stream beside the
+        # (L2-bandwidth-bound) SpMM, and autograd replays its weight-gradient GEMM on that stream too
+        side = _side_stream(feat.device) if feat.is_cuda else None
+        if side is not None:
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                h_self = _linear(feat_dst, self.fc_self, use_bias=use_bias)
         h = _linear(feat_src, self.fc_neigh) if lin_before_mp else feat_src
         h_neigh = ops.spmm(graph, h, edge_weight, dst_scale=ops.mean_scale(graph))   # u_mul_e + fn.mean
         if not lin_before_mp:
             h_neigh = _linear(h_neigh, self.fc_neigh)
-        return _linear(feat_dst, self.fc_self, use_bias=use_bias), h_neigh
+        if side is not None:
+            main.wait_stream(side)
+            h_self.record_stream(main)
+        else:
+            h_self = _linear(feat_dst, self.fc_self, use_bias=use_bias)
+        return h_self, h_neigh
 
     def forward(self, graph, feat, edge_weight=None):
         h_self, h_neigh = self.forward_parts(graph, feat, edge_weight, use_bias=True)
