@@ -131,6 +131,7 @@ PROTOTYPES = {
     "bliss_l1_norm": [_P, _I64, _P, _P, _P],
     "bliss_scale_by_inv": [_P, _I64, _P, _D, _P],
     "bliss_adam_step": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _P, _I32, _P],
+    "bliss_splitk_accumulate": [_P, _I32, _I32, _I32, _I32, _P, _P],
     "bliss_sage_epilogue_parts": [],
     "bliss_xent_mean": [_P, _P, _I32, _I32, _P, _P, _P, _P],
     "bliss_sage_epilogue_fwd": [_P, _P, _P, _I32, _I32, _I32, _F, _U64, _P, _U32, _P, _P, _P],

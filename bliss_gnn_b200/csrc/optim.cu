@@ -56,7 +56,35 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __re
 
 __global__ void k_adam_tick(int64_t* step_dev) { *step_dev += 1; }
 
+// grad[r, c] += Σ_s part[s][r][c]  for c < cols (part rows are cols_pad wide): the chunk partials of a split-K
+// weight gradient are added in chunk order (deterministic) straight into the flat gradient buffer — one
+// launch instead of a reduction, a slice copy and an accumulate.
+__global__ void __launch_bounds__(256) k_splitk_accumulate(const float* __restrict__ part, int n_parts, int rows,
+                                                          int cols_pad, int cols, float* __restrict__ grad) {
+  const int64_t plane = (int64_t)rows * cols_pad;
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float* __restrict__ p = part + (int64_t)r * cols_pad + c;
+    float t = 0.0f;
+#pragma unroll 8
+    for (int s = 0; s < n_parts; ++s) t += __ldg(p + s * plane);
+    grad[i] += t;
+  }
+}
+
 }  // namespace bliss
+
+extern "C" int bliss_splitk_accumulate(const float* part, int32_t n_parts, int32_t rows, int32_t cols_pad, int32_t cols,
+                                       float* grad, void* stream) {
+  if (n_parts <= 0 || rows <= 0 || cols <= 0 || cols_pad < cols || !part || !grad) return -1;
+  const int64_t n = (int64_t)rows * cols;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > BLISS_SM_COUNT * 8) blocks = BLISS_SM_COUNT * 8;
+  bliss::k_splitk_accumulate<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(part, n_parts, rows, cols_pad, cols, grad);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int bliss_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                                const float* lr_dev, float beta1, float beta2, float eps, int64_t* step_dev,

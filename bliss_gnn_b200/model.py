@@ -18,21 +18,26 @@ from .graph import Graph
 
 
 class _LinearSplitK(torch.autograd.Function):
-    """``F.linear`` whose weight gradient ``G^T X`` (a [out, in] result reduced over thousands of rows: a
-    handful of output tiles for 148 SMs) is computed as a batched GEMM over row chunks and summed in chunk
-    order — deterministic, same torch GEMMs, 2-3x shorter than the single skinny GEMM."""
+    """``F.linear(x, pad(weight), bias)`` whose weight gradient ``G^T X`` (an [out, in] result reduced over
+    thousands of rows: a handful of output tiles for 148 SMs) is computed as a batched GEMM over row chunks;
+    the chunk partials are added in chunk order (deterministic) by ``bliss_splitk_accumulate`` straight into
+    ``weight.grad`` when that buffer exists (the flat gradient buffer of ``parallel.FlatGrads``), else summed
+    and returned.  ``weight`` is the un-padded parameter; ``x`` may carry zero-padded extra columns."""
 
     SPLIT, MIN_ROWS = 32, 2048
 
     @staticmethod
-    def forward(ctx, x, w, bias):
+    def forward(ctx, x, weight, bias):
+        extra = x.shape[1] - weight.shape[1]
+        w = weight if extra == 0 else torch.nn.functional.pad(weight, (0, extra))
         ctx.save_for_backward(x, w)
-        ctx.has_bias = bias is not None
+        ctx.weight, ctx.has_bias = weight, bias is not None
         return torch.nn.functional.linear(x, w, bias)
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
+        weight = ctx.weight
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = gy @ w
@@ -40,9 +45,18 @@ class _LinearSplitK(torch.autograd.Function):
             S = _LinearSplitK.SPLIT
             k = (x.shape[0] // S) * S
             gyc, xc = gy.contiguous(), x.contiguous()
-            gw = torch.bmm(gyc[:k].view(S, k // S, -1).transpose(1, 2), xc[:k].view(S, k // S, -1)).sum(0)
-            if k < x.shape[0]:
-                gw = gw + gyc[k:].t() @ xc[k:]
+            n_out, n_in_pad, n_in = gyc.shape[1], xc.shape[1], weight.shape[1]
+            rem = k < x.shape[0]
+            part = torch.empty((S + int(rem), n_out, n_in_pad), dtype=gyc.dtype, device=gyc.device)
+            torch.bmm(gyc[:k].view(S, k // S, -1).transpose(1, 2), xc[:k].view(S, k // S, -1), out=part[:S])
+            if rem:
+                torch.mm(gyc[k:].t(), xc[k:], out=part[S])
+            g = weight.grad
+            if g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.is_cuda:
+                ops.N.call("bliss_splitk_accumulate", ops.N.ptr(part), part.shape[0], n_out, n_in_pad, n_in,
+                           ops.N.ptr(g), ops.N.stream())       # accumulated in place: nothing to return
+            else:
+                gw = part.sum(0)[:, :n_in]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy.sum(0)
         return gx, gw, gb
@@ -54,9 +68,9 @@ def _linear(x, lin: nn.Linear, use_bias: bool = True):
     kernels, ~2-3x on the input-layer GEMMs) the weight is zero-padded to match — same result."""
     extra = x.shape[-1] - lin.in_features
     bias = lin.bias if use_bias else None
-    w = lin.weight if extra == 0 else torch.nn.functional.pad(lin.weight, (0, extra))
     if x.is_cuda and x.dim() == 2 and x.shape[0] >= _LinearSplitK.MIN_ROWS and torch.is_grad_enabled():
-        return _LinearSplitK.apply(x, w, bias)
+        return _LinearSplitK.apply(x, lin.weight, bias)
+    w = lin.weight if extra == 0 else torch.nn.functional.pad(lin.weight, (0, extra))
     return torch.nn.functional.linear(x, w, bias)
 
 

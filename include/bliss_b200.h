@@ -293,6 +293,10 @@ int bliss_xent_mean(const float* logits /* [n_rows, n_cls] */, const int64_t* la
  * and both moments of the whole model.  lr and the step count are device scalars (CUDA-graph replay:
  * a scheduler changes lr between replays); the call advances *step_dev by one and, with zero_grad,
  * clears the gradient buffer for the next backward pass. */
+/* grad[r, c] += sum_s part[s][r][c], c < cols: ordered reduction of the row-chunk partials of a split-K weight
+ * gradient ([n_parts, rows, cols_pad], e.g. from a batched GEMM) straight into the parameter's gradient. */
+int bliss_splitk_accumulate(const float* part, int32_t n_parts, int32_t rows, int32_t cols_pad, int32_t cols,
+                            float* grad, void* stream);
 int bliss_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                     const float* lr_dev, float beta1, float beta2, float eps, int64_t* step_dev,
                     int32_t zero_grad, void* stream);

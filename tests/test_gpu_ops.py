@@ -372,3 +372,30 @@ def test_cross_entropy_mean_matches_torch(native_lib, n, c):
     (ref * 1.7).backward()
     _close(loss.reshape(1), ref.reshape(1), rtol=2e-6, what="loss")
     _close(x.grad, x2.grad, rtol=2e-6, what="grad")
+
+
+@pytest.mark.parametrize("rows,in_f,pad", [(4096, 602, 2), (3001, 256, 0), (2048, 37, 3)])
+def test_linear_splitk_matches_plain(native_lib, rows, in_f, pad):
+    """``model._linear`` on >= 2048 rows: the split-K weight gradient (batched GEMM over row chunks +
+    ``bliss_splitk_accumulate`` into an existing ``weight.grad``, or a returned sum when there is none) equals
+    the plain ``F.linear`` autograd result, with and without zero-padded input columns."""
+    from bliss_gnn_b200 import model as M
+    dev = _dev()
+    torch.manual_seed(rows)
+    lin = torch.nn.Linear(in_f, 64).to(dev)
+    x = torch.randn(rows, in_f, device=dev)
+    xp = F.pad(x, (0, pad)) if pad else x
+    gy = torch.randn(rows, 64, device=dev)
+    ref = F.linear(x, lin.weight, lin.bias)
+    ref.backward(gy)
+    gw_ref, gb_ref = lin.weight.grad.clone(), lin.bias.grad.clone()
+    for preset in (False, True):
+        lin.weight.grad = torch.full_like(lin.weight, 0.5) if preset else None     # accumulate into an existing buffer
+        lin.bias.grad = None
+        xin = xp.clone().requires_grad_(True)
+        y = M._linear(xin, lin)
+        _close(y, ref, rtol=2e-6, what="forward")
+        y.backward(gy)
+        _close(lin.weight.grad - (0.5 if preset else 0.0), gw_ref, rtol=3e-5, what=f"weight grad (preset={preset})")
+        _close(lin.bias.grad, gb_ref, rtol=2e-5, what="bias grad")
+        _close(xin.grad[:, :in_f], gy @ lin.weight.detach(), rtol=2e-5, what="input grad")
