@@ -318,19 +318,22 @@ def main():
     except Exception:
         traffic_tab = {}
 
+    layer_dims = [HIDDEN, HIDDEN, dm.n_classes]          # width the aggregation runs at in each layer (SAGE, lin_before_mp)
+
     def alg_bytes(name):
-        """Algorithmic (compulsory) bytes of one entry point over the profiled steps."""
+        """Algorithmic (compulsory) bytes of one entry point over the profiled steps: every distinct
+        input read once, every output written once."""
         total = 0.0
         for step_sizes in sizes:
-            for (n_s, e_in, n_c, n_src, e_b) in step_sizes:
-                if name == "bliss_frontier_prob":    # indptr pair + (index, weight) per in-edge + row sums + candidates
-                    total += 16.0 * n_s + 8.0 * e_in + 8.0 * n_s + 12.0 * n_c
-                elif name == "bliss_block_count":
-                    total += 16.0 * n_s + 4.0 * e_in + 4.0 * n_s
+            for l, (n_s, e_in, n_c, n_src, e_b) in enumerate(step_sizes):
+                if name == "bliss_frontier_prob":    # (index, weight) per in-edge + chunk records/partials + |V| accumulator scan + candidates
+                    total += 8.0 * e_in + 64.0 * (e_in / 256.0 + n_s) + 8.0 * g.num_nodes() + 8.0 * n_c
+                elif name == "bliss_block_count":    # indices + chunk records + keep bits + per kept edge (info, weight, first key)
+                    total += 4.0 * e_in + 76.0 * (e_in / 256.0 + n_s) + 20.0 * e_b
                 elif name in ("bliss_block_fill", "bliss_sample_layer_back"):
-                    total += 16.0 * n_s + e_in / 8.0 + 36.0 * e_b + 8.0 * n_s
-                elif name == "bliss_spmm":           # forward + backward of one layer at hidden width
-                    total += 2 * (8.0 * e_b + 4.0 * (n_s + 1) + 4.0 * HIDDEN * (n_src + n_s))
+                    total += 80.0 * (e_in / 256.0 + n_s) + 16.0 * e_b + 36.0 * e_b + 36.0 * n_c
+                elif name == "bliss_spmm":           # forward + backward of the layer at its aggregation width
+                    total += 2 * (8.0 * e_b + 8.0 * (n_s + 1) + 4.0 * layer_dims[l] * (n_src + n_s))
                 else:
                     total += 8.0 * e_in
         return total
@@ -345,12 +348,21 @@ def main():
                 "note": note}
 
     name = max(per_fn.items(), key=lambda kv: kv[1][1])[0]
-    roofline = roofline_of(name, "entry point with the largest total CUDA-event time over the profiled steps; "
-                                 "SpMM gathers L2-resident feature rows (L2 traffic 4*D*E_b bytes), so its HBM "
-                                 "fraction by compulsory bytes is low by construction (DESIGN.md section 3)")
+    roofline = roofline_of(name, "entry point with the largest total CUDA-event time over the profiled steps. The SpMM "
+                                 "gathers source rows that are L2-resident (<= 8 K rows x 1 KB), so its DRAM traffic is "
+                                 "about its compulsory bytes and the HBM fraction is low by construction: the kernel is "
+                                 "bound by L2->SM gather bandwidth, reported as l2_gather (DESIGN.md section 3)")
     roofline["per_entry_point_ms_per_step"] = {k: v[1] / n_prof for k, v in sorted(per_fn.items())}
-    roofline_sampling = roofline_of("bliss_frontier_prob", "the HBM-streaming sampling kernel the north-star names "
-                                    "(k_frontier_prob + k_collect_candidates)") if "bliss_frontier_prob" in per_fn else None
+    if "bliss_spmm" in per_fn:      # the bound that actually applies: bytes gathered through L2 per second
+        gathered = sum(2 * 4.0 * layer_dims[l] * e_b for st in sizes for l, (_, _, _, _, e_b) in enumerate(st))
+        t_ms = per_fn["bliss_spmm"][1]
+        roofline["l2_gather"] = {"achieved_gbs": gathered / 1e9 / (t_ms / 1e3),
+                                 "peak_gbs": 12000.0, "peak_source": "chip-level L2->SM throughput ~6300 B/clk "
+                                 "(/opt/skills/guides/B300_MICROARCH.md, TMA/LDG chip-throughput) x 1.9 GHz",
+                                 "bytes_per_step": gathered / n_prof}
+    roofline_sampling = roofline_of("bliss_frontier_prob", "the HBM-streaming sampling passes the north-star names "
+                                    "(three chunk passes + candidate scan); the scatter pass is bound by L2 atomic "
+                                    "throughput (one 64-bit RED per in-edge), not by HBM") if "bliss_frontier_prob" in per_fn else None
 
     out = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
