@@ -5,10 +5,10 @@
 //       normalisation.
 // Replaces bandit_sampler.py:47-138,269-425 and ladies_sampler.py:34-183 of the reference
 // (which reach DGL in_subgraph/compact_graphs/g-SpMM/g-SDDMM/to_block and torch sort/unique/
-// bernoulli).  Work distribution: the frontier's rows (in-edge lists of the seeds) are split
-// into heavy rows (one 256-thread CTA each, weights staged once in shared memory for the three
-// passes) and light rows (one warp each, values kept in registers); CTAs pull items from a
-// device-side queue, so no size ever travels to the host inside a layer.
+// bernoulli).  Work distribution: the frontier's rows (in-edge lists of the seeds) are cut into
+// 256-edge chunks with a 32-byte record each; every edge pass gives one warp one chunk, dealt
+// round-robin to the resident warps.  All sizes live in device counters, so no size ever travels to
+// the host inside a layer (or a step: the whole training step replays as one CUDA graph).
 #include <cooperative_groups.h>
 #include "common.cuh"
 
