@@ -252,6 +252,7 @@ def main():
     N.STATS.reset(timing=False)
     replays0 = tr.graph_replays
     tr.flush()
+    resizes0 = tr.pool_resizes
     barrier()
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -372,7 +373,8 @@ def main():
                    "d2h_bytes_per_step": (4 + dm.sampler._wsp.ctr_all.numel()) * world,
                    "note": "seeds H2D from pinned memory every step; loss + per-layer counters D2H every step, "
                            "copied stream-ordered and consumed one step later"},
-           "gpu_launches": launches, "graph_replays": tr.graph_replays, "roofline": roofline,
+           "gpu_launches": launches, "graph_replays": tr.graph_replays,
+           "pool_resizes_in_timed_regions": tr.pool_resizes - resizes0, "roofline": roofline,
            "roofline_sampling": roofline_sampling}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

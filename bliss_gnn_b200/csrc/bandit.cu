@@ -61,6 +61,7 @@ struct RewardArgs {
   int64_t n_edges;
   const int64_t* n_edges_dev;   // true edge count on the device (n_edges is then the capacity)
   int64_t* count_out;           // data-parallel exchange header slot (or NULL)
+  int32_t* pos_out;             // data-parallel exchange: CSC position of every edge as int32 (or NULL)
   float* exp3_w;
   float* rewards;
   float* x_out;
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
     float x = __fmul_rn(r_hat, __fdiv_rn(p.delta, n_i));                         // :242
     if (x > 1.0f) x = 1.0f;                                                      // :244
     if (p.x_out) p.x_out[e] = x;
+    if (p.pos_out) p.pos_out[e] = (int32_t)pos;
     if (p.exp3_w) {
       const float w_old = p.exp3_w[pos];
       const float w_new = __fmul_rn(w_old, expf(x));                             // :246-248
@@ -135,7 +137,8 @@ __global__ void __launch_bounds__(256) k_apply_updates(const int64_t* __restrict
 }
 
 // Apply every rank's update of one layer straight from the all-gathered exchange buffer:
-// per rank a header of int64 counts, then per layer int64 positions and fp32 exponents.
+// per rank a header of int64 counts, then per layer int32 positions and fp32 exponents (8 bytes per
+// sampled edge on the wire).
 __global__ void __launch_bounds__(256) k_apply_updates_packed(const unsigned char* __restrict__ recv,
                                                              int64_t rank_stride, int world, int64_t count_off,
                                                              int64_t pos_off, int64_t x_off, int64_t cap,
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(256) k_apply_updates_packed(const unsigned cha
     const unsigned char* base = recv + (int64_t)r * rank_stride;
     const int64_t n = *reinterpret_cast<const int64_t*>(base + count_off);
     if (k >= n) continue;
-    const int64_t pos = reinterpret_cast<const int64_t*>(base + pos_off)[k];
+    const int64_t pos = reinterpret_cast<const int32_t*>(base + pos_off)[k];
     const float f = expf(reinterpret_cast<const float*>(base + x_off)[k]);
     float* addr = exp3_w + pos;
     unsigned old = __float_as_uint(*addr), assumed;
@@ -237,7 +240,7 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
                         const float* w_static_csc, const float* a_ij, const float* asum, const float* qsum,
                         int32_t alpha_mode, float delta, int32_t n_dst, int64_t n_edges, float* exp3_w_csc,
                         float* rewards, float* x_out, double* l1_delta, const int64_t* n_edges_dev,
-                        int64_t* count_out, void* stream) {
+                        int64_t* count_out, int32_t* pos_out, void* stream) {
   if (!g || n_edges < 0 || n_dst < 0) return -1;
   if (n_edges == 0) return 0;
   if (!blk_indptr || !edge_src || !edge_dst || !csc_pos || !dst_nid || !q_ij || !node_prob || !embed_norm) return -1;
@@ -262,6 +265,7 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
   p.n_edges = n_edges;
   p.n_edges_dev = n_edges_dev;
   p.count_out = count_out;
+  p.pos_out = pos_out;
   p.exp3_w = exp3_w_csc;
   p.rewards = rewards;
   p.x_out = x_out;
@@ -285,7 +289,7 @@ int bliss_apply_updates_packed(const void* recv, int64_t rank_stride_bytes, int3
                                int64_t pos_off, int64_t x_off, int64_t cap, float* exp3_w_csc, double* l1_delta,
                                void* stream) {
   if (!recv || !exp3_w_csc || world <= 0 || cap < 0 || rank_stride_bytes <= 0) return -1;
-  if ((count_off | pos_off) & 7 || (x_off & 3)) return -1;
+  if ((count_off & 7) || (pos_off & 3) || (x_off & 3)) return -1;
   if (cap == 0) return 0;
   k_apply_updates_packed<<<grid_for((int64_t)world * cap, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(
       (const unsigned char*)recv, rank_stride_bytes, world, count_off, pos_off, x_off, cap, exp3_w_csc, l1_delta);

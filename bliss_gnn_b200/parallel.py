@@ -65,10 +65,11 @@ def gather_updates(pos: torch.Tensor, x: torch.Tensor, group) -> List[Tuple[torc
 class BanditExchange:
     """One all-gather per step for the sparse bandit updates of all layers.
 
-    Send buffer of a rank: ``[int64 count per layer (64 B header) | layer 0: int64 pos[cap0], fp32 x[cap0] |
-    layer 1 … ]``.  ``pos[l]`` doubles as the block's ``csc_pos`` array (the sampler writes it in place) and the
-    reward kernel writes ``x[l]`` in place, so nothing is packed or copied before the collective, and the apply
-    kernel reads the counts from the gathered headers — no host-side sizes, no host sync."""
+    Send buffer of a rank: ``[int64 count per layer (64 B header) | layer 0: int32 pos[cap0], fp32 x[cap0] |
+    layer 1 … ]`` — 8 bytes per sampled edge on the wire.  The reward kernel writes ``pos[l]`` (the edge's CSC
+    position; the graph must have fewer than 2^31 edges) and ``x[l]`` in place, so nothing is packed or copied
+    before the collective, and the apply kernel reads the counts from the gathered headers — no host-side sizes,
+    no host sync."""
 
     HEADER = 64
 
@@ -78,7 +79,7 @@ class BanditExchange:
         off, self.pos_off, self.x_off = self.HEADER, [], []
         for c in self.caps:
             self.pos_off.append(off)
-            off += 8 * c
+            off += 4 * c
             self.x_off.append(off)
             off += 4 * c
             off = (off + 15) // 16 * 16
@@ -86,7 +87,7 @@ class BanditExchange:
         self.send = torch.zeros(off, dtype=torch.uint8, device=device)
         self.recv = torch.zeros(self.world * off, dtype=torch.uint8, device=device)
         self.header = self.send[:self.HEADER].view(torch.int64)
-        self.pos = [self.send[o:o + 8 * c].view(torch.int64) for o, c in zip(self.pos_off, self.caps)]
+        self.pos = [self.send[o:o + 4 * c].view(torch.int32) for o, c in zip(self.pos_off, self.caps)]
         self.x = [self.send[o:o + 4 * c].view(torch.float32) for o, c in zip(self.x_off, self.caps)]
         self._hdr_host = torch.zeros(self.HEADER // 8, dtype=torch.int64)
         if device.type == "cuda":

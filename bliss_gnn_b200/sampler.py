@@ -129,7 +129,7 @@ class LayerPool:
     Rows beyond the sampled counts are valid padding: empty destination rows (indptr tail = E_b,
     mean divisor 1), source ids that stay valid node ids, edge slots beyond E_b never referenced."""
 
-    def __init__(self, device, cap_dst: int, cap_src: int, cap_edges: int, bandit: bool = True, csc_pos=None):
+    def __init__(self, device, cap_dst: int, cap_src: int, cap_edges: int, bandit: bool = True):
         self.cap_dst, self.cap_src, self.cap_edges, self.bandit = int(cap_dst), int(cap_src), int(cap_edges), bandit
         i32 = dict(dtype=torch.int32, device=device)
         self.meta = torch.zeros(3 * (self.cap_dst + 1), **i32)
@@ -138,9 +138,7 @@ class LayerPool:
         self.inv_deg = self.meta[2 * n:].view(torch.float32)[:self.cap_dst]
         self.inv_deg.fill_(1.0)
         self.e32 = torch.zeros((5, self.cap_edges), **i32)
-        # in data-parallel runs csc_pos is the position array of the bandit exchange's send buffer
-        self.csc_pos = csc_pos if csc_pos is not None else torch.zeros(self.cap_edges, dtype=torch.int64, device=device)
-        assert self.csc_pos.numel() == self.cap_edges and self.csc_pos.dtype == torch.int64
+        self.csc_pos = torch.zeros(self.cap_edges, dtype=torch.int64, device=device)
         self.src = torch.zeros(2 * self.cap_src, **i32)
         self.src_nid = self.src[:self.cap_src]
         self.node_prob = self.src[self.cap_src:].view(torch.float32)
@@ -516,7 +514,7 @@ class BanditLadiesSampler:
         return ("static", None, None, None)
 
     def _reward_call(self, idx, mfg, g, alpha, weights, rewards=None, x_out=None, l1=None, n_edges_dev=None,
-                     count_out=None):
+                     count_out=None, pos_out=None):
         kind, a, asum, qsum = alpha
         wsp = self._bind(g)
         w_static = g.csc_edata(self.edge_weight) if kind == "static" else None
@@ -531,7 +529,7 @@ class BanditLadiesSampler:
             N.ptr(mfg.dstdata[NID]), N.ptr(mfg.edata["q_ij"]), N.ptr(mfg.srcdata[self.node_prob]),
             N.ptr(emb.contiguous()), N.ptr(w_static), N.ptr(a), N.ptr(asum), N.ptr(qsum),
             1 if kind == "gat" else 0, 0.01, mfg.num_dst_nodes(), mfg.num_edges(), N.ptr(weights),
-            N.ptr(rewards), N.ptr(x_out), N.ptr(l1), n_edges_dev, count_out, N.stream())
+            N.ptr(rewards), N.ptr(x_out), N.ptr(l1), n_edges_dev, count_out, N.ptr(pos_out), N.stream())
 
     def calculate_rewards(self, idx, mfg, g, alpha):
         """``bandit_sampler.py:160-193``: stores ``mfg.edata['rewards']`` (emit-only kernel call)."""
@@ -573,11 +571,13 @@ class BanditLadiesSampler:
 
     def exp3_emit(self, mfgs, g, exchange):
         """Data-parallel, sync-free: compute every layer's clamped exponents into the exchange's send
-        buffer (whose position arrays are the blocks' ``csc_pos``) and the edge counts into its header."""
+        buffer (positions as int32 + exponents) and the edge counts into its header."""
+        if g.num_edges() >= 2 ** 31:
+            raise NotImplementedError("the packed bandit exchange carries int32 CSC positions: |E| must be < 2^31")
         for idx, mfg in enumerate(mfgs):
-            assert mfg.csc_pos.data_ptr() == exchange.pos[idx].data_ptr()
+            assert mfg.num_edges() <= exchange.caps[idx]
             self._reward_call(idx, mfg, g, self.calculate_alpha(mfg), None, x_out=exchange.x[idx],
-                              count_out=exchange.header.data_ptr() + 8 * idx)
+                              count_out=exchange.header.data_ptr() + 8 * idx, pos_out=exchange.pos[idx])
 
     def exp3_apply(self, exchange, n_layers: int):
         """Apply all ranks' gathered updates (one kernel per layer, counts read from the headers)."""
@@ -606,10 +606,11 @@ class BanditLadiesSampler:
         written into the exchange's send buffer, ONE all-gather moves all layers, one kernel per layer
         applies every rank's update."""
         self._bind(g)
-        if exchange is not None and all(m.csc_pos.data_ptr() == exchange.pos[i].data_ptr() and
-                                        m.num_edges() <= exchange.caps[i] for i, m in enumerate(mfgs)):
+        if (exchange is not None and g.num_edges() < 2 ** 31
+                and all(m.num_edges() <= exchange.caps[i] for i, m in enumerate(mfgs))):
             for idx, mfg in enumerate(mfgs):
-                self._reward_call(idx, mfg, g, self.calculate_alpha(mfg), None, x_out=exchange.x[idx])
+                self._reward_call(idx, mfg, g, self.calculate_alpha(mfg), None, x_out=exchange.x[idx],
+                                  pos_out=exchange.pos[idx])
             exchange.exchange([m.num_edges() for m in mfgs])
             for idx in range(len(mfgs)):
                 N.call("bliss_apply_updates_packed", N.ptr(exchange.recv), exchange.stride, exchange.world,

@@ -247,14 +247,15 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
                         double* l1_delta /* [1] accumulated sum(w_new - w_old), or NULL */,
                         const int64_t* n_edges_dev /* true edge count on the device (n_edges = capacity), or NULL */,
                         int64_t* count_out /* where to store the edge count (exchange header), or NULL */,
+                        int32_t* pos_out /* [E_b] CSC positions as int32 (exchange send buffer; |E| < 2^31), or NULL */,
                         void* stream);
 /* apply gathered updates from other ranks: w[pos[k]] *= exp(x[k]) */
 int bliss_apply_updates(const int64_t* pos, const float* x, int64_t n, float* exp3_w_csc,
                         double* l1_delta, void* stream);
 /* data-parallel fast path: apply all ranks' updates of one layer straight from the all-gathered
- * exchange buffer (per rank: int64 count at count_off, int64 pos[cap] at pos_off, fp32 x[cap] at
- * x_off; offsets in bytes).  The reward kernel wrote x into the send buffer, the block's csc_pos
- * array is the send buffer's pos array — no packing pass, no host-side sizes. */
+ * exchange buffer (per rank: int64 count at count_off, int32 pos[cap] at pos_off, fp32 x[cap] at
+ * x_off; offsets in bytes).  The reward kernel wrote pos and x straight into the send buffer — no
+ * packing pass, no host-side sizes; 8 bytes per sampled edge on the wire. */
 int bliss_apply_updates_packed(const void* recv, int64_t rank_stride_bytes, int32_t world,
                                int64_t count_off, int64_t pos_off, int64_t x_off, int64_t cap,
                                float* exp3_w_csc, double* l1_delta, void* stream);

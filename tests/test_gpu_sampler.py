@@ -329,7 +329,7 @@ def test_packed_exchange_apply_matches_sequential_updates(native_lib):
             first_pos.setdefault(l, pos)
             xs = torch.rand(n, generator=gen) * 0.01
             base[:64].view(torch.int64)[l] = n
-            base[ex.pos_off[l]:ex.pos_off[l] + 8 * n].view(torch.int64).copy_(pos)
+            base[ex.pos_off[l]:ex.pos_off[l] + 4 * n].view(torch.int32).copy_(pos.to(torch.int32))
             base[ex.x_off[l]:ex.x_off[l] + 4 * n].view(torch.float32).copy_(xs)
             expect[l][pos] = expect[l][pos] * torch.exp(xs.double())
     for l in range(len(caps)):

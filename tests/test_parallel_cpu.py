@@ -70,7 +70,7 @@ def _worker(rank, init_file, result_file):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ex = BanditExchange(t.tolist(), WORLD, torch.device("cpu"), dist.group.WORLD)
     for l, (eid, xe) in enumerate(upd):
-        ex.pos[l][:eid.numel()] = eid
+        ex.pos[l][:eid.numel()] = eid.to(torch.int32)
         ex.x[l][:eid.numel()] = xe.float()
     ex.exchange([e.numel() for e, _ in upd])
     for l, (eid, xe) in enumerate(upd):
@@ -78,7 +78,7 @@ def _worker(rank, init_file, result_file):
         for r in range(WORLD):
             base = ex.recv[r * ex.stride:(r + 1) * ex.stride]
             n = int(base[:64].view(torch.int64)[l])
-            pos_r = base[ex.pos_off[l]:ex.pos_off[l] + 8 * n].view(torch.int64)
+            pos_r = base[ex.pos_off[l]:ex.pos_off[l] + 4 * n].view(torch.int32).long()
             x_r = base[ex.x_off[l]:ex.x_off[l] + 4 * n].view(torch.float32)
             assert n == ref[r][0].numel() and torch.equal(pos_r, ref[r][0]) and torch.equal(x_r, ref[r][1])
     if rank == 0:
