@@ -233,7 +233,7 @@ def main():
                     model="sage", seed=0, rank=rank, world_size=world, graph=g, normalize=args.normalize)
     torch.manual_seed(3)
     model = build_model("sage", dm.in_feats, HIDDEN, dm.n_classes, 3, DROPOUT).to(device)
-    tr = Trainer(dm, model, LR, pg, static_graph=not args.eager)
+    tr = Trainer(dm, model, LR, pg, static_graph=not args.eager, eager_warmup=8)   # 8 ordinary steps size the pools
     n_need = args.warmup + 3 * args.steps + 24
     host_batches = [b.pin_memory() for b in seed_batches_for(g, rank, world, n_need)]
     dev_batches = [b.to(device) for b in host_batches]
