@@ -61,6 +61,7 @@ def block_transpose_into(block, pool):
 
 def block_transpose(block):
     """Source-major CSR of a block (cached on the block) for the backward aggregation."""
+    _wait_ready(block, "_t_ready")
     if block._transpose is None:
         E, n_src, n_dst = block.num_edges(), block.num_src_nodes(), block.num_dst_nodes()
         dev = block.device
@@ -116,10 +117,19 @@ def _spmm_raw(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, seg_ptr=None
     return y
 
 
+def _wait_ready(block, what="_ready"):
+    """A block of the whole-step graph is filled (``_ready``) and transposed (``_t_ready``) on a side stream
+    (``sampler.enqueue_static``): the first kernel that reads its edges / its transpose waits for the event."""
+    ev = getattr(block, what, None)
+    if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)
+
+
 class _SpMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, block, w, sscale, dscale):
         x = _req(x, name="x")
+        _wait_ready(block)
         ctx.block, ctx.w, ctx.sscale, ctx.dscale = block, w, sscale, dscale
         return _spmm_raw(block.indptr, block.edge_src, None, w, sscale, dscale, N.AGG_SUM, x,
                          block.num_dst_nodes(), getattr(block, "seg_ptr", None))
@@ -158,6 +168,7 @@ class _GATv2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, attn, block, drop_mask, slope):
         feat = _req(feat, name="feat")          # [n_src, H, D]
+        _wait_ready(block)
         attn_c = _req(attn, name="attn").reshape(attn.shape[-2], attn.shape[-1])
         n_src, H, D = feat.shape
         n_dst, E = block.num_dst_nodes(), block.num_edges()

@@ -87,11 +87,13 @@ class _Workspace:
         self._keep = (g.indptr, g.indices, g.eid)
         N.call("bliss_workspace_init", C.byref(self.ws), V, N.stream())
 
-    def ws_layer(self, layer: int, n_seeds_dev=None, step_dev=None) -> "N.Workspace":
+    def ws_layer(self, layer: int, n_seeds_dev=None, step_dev=None, counters=None) -> "N.Workspace":
         """The workspace descriptor with layer ``layer``'s own counters block and, for sync-free
-        chaining, the device addresses the kernels read the seed count / Philox step from."""
+        chaining, the device addresses the kernels read the seed count / Philox step from.
+        ``counters``: the workspace whose per-layer counters blocks to use (the step's second workspace
+        shares the first one's)."""
         ws = N.Workspace.from_buffer_copy(self.ws)
-        ws.ctr = self.ctr_all[layer].data_ptr()
+        ws.ctr = (counters or self).ctr_all[layer].data_ptr()
         ws.n_seeds_dev = n_seeds_dev
         ws.step_dev = step_dev
         return ws
@@ -465,17 +467,25 @@ class BanditLadiesSampler:
         L = len(self.nodes_per_layer)
         bandit = self._mode == N.MODE_BANDIT
         weights_static = None if bandit else g.csc_edata(self.edge_weight)
+        side = transpose_stream
+        if side is not None and getattr(self, "_wsp2", None) is None:
+            # Consecutive layers alternate between two workspaces, so a layer's back half (fill, workspace restore,
+            # transpose) can run on the side stream while the next layer's front half already samples: the next
+            # layer only needs this layer's source list and counters, which the front half produced.
+            self._wsp2 = _Workspace(g)
+        done = {}                                   # layer -> event: its back half (and workspace) is finished
         for block_id in reversed(range(L)):
             pool, top = pools[block_id], block_id == L - 1
+            w = wsp if (side is None or (L - 1 - block_id) % 2 == 0) else self._wsp2
             seeds = seeds_static if top else pools[block_id + 1].src_nid
             n_cap = pool.cap_dst
-            ws = wsp.ws_layer(block_id, None if top else wsp.counter_ptr(block_id + 1, "n_src"), N.ptr(step_dev))
+            ws = w.ws_layer(block_id, None if top else wsp.counter_ptr(block_id + 1, "n_src"), N.ptr(step_dev), counters=wsp)
             weights = self._w_csc[block_id] if bandit else weights_static
             mode = self._mode | (0 if self.importance_sampling else N.MODE_UNIFORM)
             if self.collect == "bitmap" or (self.collect == "auto" and g.num_nodes() > self.DENSE_COLLECT_MAX):
                 mode |= N.COLLECT_BITMAP
-            if not self._poisson and wsp.key_scratch is None:
-                wsp.key_scratch = torch.empty(g.num_nodes() + 4, dtype=torch.float32, device=g.device)
+            if not self._poisson and w.key_scratch is None:
+                w.key_scratch = torch.empty(g.num_nodes() + 4, dtype=torch.float32, device=g.device)
             e32 = pool.e32
             out = N.BlockOut(indptr=N.ptr(pool.indptr), edge_src=N.ptr(e32[0]), edge_dst=N.ptr(e32[1]),
                              csc_pos=N.ptr(pool.csc_pos), eid=N.ptr(e32[2]), q_ij=N.ptr(e32[4]) if bandit else None,
@@ -484,21 +494,34 @@ class BanditLadiesSampler:
                              seg_ptr=N.ptr(pool.seg_ptr), inv_deg=N.ptr(pool.inv_deg),
                              cap_edges=pool.cap_edges, cap_src=pool.cap_src, pad_src=pool.cap_src,
                              pad_rows=pool.cap_dst)
-            st = N.stream()
-            N.call("bliss_sample_layer_front", C.byref(wsp.gview), N.ptr(seeds), n_cap, N.ptr(weights), float(self.eta),
+            main = torch.cuda.current_stream()
+            if block_id + 2 in done:                # this workspace was last used two layers ago: its restore must be done
+                main.wait_event(done[block_id + 2])
+            N.call("bliss_sample_layer_front", C.byref(w.gview), N.ptr(seeds), n_cap, N.ptr(weights), float(self.eta),
                    mode, int(self.nodes_per_layer[block_id]), float(self.eps), int(self._poisson), self.rng_seed,
-                   0, block_id, self._u_ptr(g, block_id), N.ptr(wsp.key_scratch), C.byref(ws), C.byref(out), st)
-            N.call("bliss_sample_layer_back", C.byref(wsp.gview), N.ptr(seeds), n_cap, N.ptr(weights), float(self.eta),
-                   self._mode, C.byref(ws), C.byref(out), st)
-            # the transpose is read by the backward pass only: with ``transpose_stream`` it is forked off (the caller
-            # joins that stream before the backward pass) and runs beside the next layer's sampling
-            ts = st
-            if transpose_stream is not None:
-                transpose_stream.wait_stream(torch.cuda.current_stream())
-                ts = transpose_stream.cuda_stream
-            N.call("bliss_block_transpose", N.ptr(e32[0]), N.ptr(e32[1]), pool.cap_edges, pool.cap_src, pool.cap_dst,
-                   N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_bits), N.ptr(pool.t_pre), pool.t_words, N.ptr(pool.t_dst),
-                   N.ptr(pool.t_perm), N.ptr(pool.t_seg_ptr), 1, wsp.counter_ptr(block_id, "n_edges"), ts)
+                   0, block_id, self._u_ptr(g, block_id), N.ptr(w.key_scratch), C.byref(ws), C.byref(out), N.stream())
+            back = side if side is not None else main
+            if side is not None:
+                side.wait_stream(main)
+            with torch.cuda.stream(back):
+                N.call("bliss_block_fill", C.byref(w.gview), N.ptr(seeds), n_cap, N.ptr(weights), float(self.eta),
+                       self._mode, C.byref(ws), C.byref(out), N.stream())
+                if side is not None:                # the forward aggregation over this block waits for this event only
+                    pool.ready = torch.cuda.Event()
+                    pool.ready.record(back)
+                    if pool.padded is not None:
+                        pool.padded._ready = pool.ready
+                N.call("bliss_block_finish", n_cap, self._mode, C.byref(ws), C.byref(out), N.stream())
+                # the transpose is read by the backward pass only (the caller joins ``transpose_stream`` before it)
+                N.call("bliss_block_transpose", N.ptr(e32[0]), N.ptr(e32[1]), pool.cap_edges, pool.cap_src, pool.cap_dst,
+                       N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_bits), N.ptr(pool.t_pre), pool.t_words,
+                       N.ptr(pool.t_dst), N.ptr(pool.t_perm), N.ptr(pool.t_seg_ptr), 1,
+                       wsp.counter_ptr(block_id, "n_edges"), N.stream())
+                if side is not None:
+                    done[block_id] = torch.cuda.Event()
+                    done[block_id].record(back)
+                    if pool.padded is not None:     # readers of the transpose (backward pass, GCN out-degrees) wait for this
+                        pool.padded._t_ready = done[block_id]
 
     # ---- bandit update ------------------------------------------------------------------------
     def calculate_alpha(self, mfg):
