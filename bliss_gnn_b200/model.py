@@ -262,6 +262,8 @@ class SAGE(nn.Module):
         if fuse and self.training and self.dropout.p > 0:
             self._drop_step(x.device).add_(1)           # one Philox step per forward pass (device scalar: replayable)
         for l, (layer, block) in enumerate(zip(self.layers, blocks)):
+            if l == 0 and norm is None:
+                norm = getattr(x, "_bliss_row_norm", None)       # came with the feature gather (train._padded_fwd_bwd)
             block.srcdata["embed_norm"] = ops.row_norm(h) if norm is None else norm       # :318
             norm = None
             last = l == len(self.layers) - 1

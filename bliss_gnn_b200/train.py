@@ -268,8 +268,9 @@ class Trainer:
         """``after_forward`` / ``before_backward``: hooks of the whole-step graph — work that only needs the
         forward pass is forked onto side streams there, work the backward pass needs is joined."""
         g = self.dm.g
-        x = ops.gather_rows(g.ndata["features"], self._pools[0].src_nid)
-        y = g.ndata["labels"][self._seeds_static.long()]
+        x, norm = ops.gather_rows(g.ndata["features"], self._pools[0].src_nid, with_norm=True)
+        x._bliss_row_norm = norm                       # layer 0's embed_norm comes with the gather (model.SAGE/GCN/GATv2)
+        y = torch.index_select(g.ndata["labels"], 0, self._seeds_static)
         pred = self.model(self._padded, x)[: self.dm.batch_size]
         loss = self.loss_fn(pred, y)
         if after_forward is not None:
@@ -461,7 +462,10 @@ class Trainer:
         # (only the backward pass reads them) run beside the next layer's sampling / the forward pass, and the
         # bandit update (needs embed_norm of the forward pass only) runs beside the backward pass and Adam.
         if getattr(self, "_side_t", None) is None:
+            # the step's critical path is captured on a high-priority stream, the side branches on normal-priority
+            # ones: their kernels fill idle SMs instead of competing with the bandwidth-bound aggregation
             self._side_t, self._side_b = torch.cuda.Stream(), torch.cuda.Stream()
+            self._main_hp = torch.cuda.Stream(priority=-5)
 
         def bandit_update():
             main = torch.cuda.current_stream()
@@ -518,7 +522,7 @@ class Trainer:
         # two replays with the collectives launched in between, and the process hung in NCCL teardown.)
         self._graph_b = None
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, stream=self._main_hp):
             self._static_loss, self._static_pred, self._static_y = body()
         if dp:
             self._graph_b = torch.cuda.CUDAGraph()
