@@ -267,7 +267,7 @@ class SAGE(nn.Module):
     def forward(self, blocks, x):
         h, norm = x, None
         fuse = self.activation is torch.nn.functional.relu and x.is_cuda
-        if fuse and self.training and self.dropout.p > 0:
+        if fuse and self.training and self.dropout.p > 0 and not getattr(self, "_external_drop_step", False):
             self._drop_step(x.device).add_(1)           # one Philox step per forward pass (device scalar: replayable)
         for l, (layer, block) in enumerate(zip(self.layers, blocks)):
             if l == 0 and norm is None:

@@ -270,7 +270,7 @@ class Trainer:
         g = self.dm.g
         x, norm = ops.gather_rows(g.ndata["features"], self._pools[0].src_nid, with_norm=True)
         x._bliss_row_norm = norm                       # layer 0's embed_norm comes with the gather (model.SAGE/GCN/GATv2)
-        y = torch.index_select(g.ndata["labels"], 0, self._seeds_static)
+        y = self._gather_labels(g.ndata["labels"], self._seeds_static)
         pred = self.model(self._padded, x)[: self.dm.batch_size]
         loss = self.loss_fn(pred, y)
         if after_forward is not None:
@@ -282,6 +282,15 @@ class Trainer:
         if step_optimizer:
             self._optimizer_step()
         return loss.detach(), pred.detach(), y
+
+    @staticmethod
+    def _gather_labels(labels, nid32):
+        """``labels[nid]`` in one launch: int64 class ids ride through the row-gather kernel as 2-float rows
+        (torch's index / index_select paths cost 2-3 launches or a slow generic gather here)."""
+        if labels.dim() == 1 and labels.dtype == torch.int64 and labels.is_contiguous():
+            out = ops.gather_rows(labels.view(torch.float32).view(-1, 2), nid32)
+            return out.view(torch.int64).view(-1)
+        return labels[nid32.long()]
 
     def _capture(self):
         self.last_pred = None
@@ -445,6 +454,8 @@ class Trainer:
         if getattr(self, "_step_dev", None) is None:
             self._step_dev = torch.zeros(1, dtype=torch.int64, device=g.device)
         self._step_dev.fill_(smp.step)
+        if hasattr(self.model, "_drop_step"):       # dropout's Philox step = the trainer's device step counter
+            self.model._drop_step_t, self.model._external_drop_step = self._step_dev, True
         for l, pb in enumerate(self._padded):
             pool = self._pools[l]
             pb._n_edges_dev = smp._wsp.counter_ptr(l, "n_edges")
