@@ -458,7 +458,7 @@ class BanditLadiesSampler:
         return self._finish_block(fr, out, bufs, pool)
 
     # ---- sync-free path (CUDA-graph capture of the whole step) -----------------------------------
-    def enqueue_static(self, g, seeds_static, pools, step_dev, transpose_stream=None):
+    def enqueue_static(self, g, seeds_static, pools, step_dev, transpose_stream=None, defer_last_transpose=False):
         """Enqueue the sampling of every layer into the capacity pools with NO host synchronisation:
         each layer reads its true seed count from the previous layer's device counters, the Philox
         step from ``step_dev``, and the transpose its edge count from the counters.  Capturable in a
@@ -473,7 +473,8 @@ class BanditLadiesSampler:
             # transpose) can run on the side stream while the next layer's front half already samples: the next
             # layer only needs this layer's source list and counters, which the front half produced.
             self._wsp2 = _Workspace(g)
-        done = {}                                   # layer -> event: its back half (and workspace) is finished
+        done = {}                                   # layer -> event: its fill and workspace restore are finished
+        deferred = []                               # transposes the caller launches later (``defer_last_transpose``)
         for block_id in reversed(range(L)):
             pool, top = pools[block_id], block_id == L - 1
             w = wsp if (side is None or (L - 1 - block_id) % 2 == 0) else self._wsp2
@@ -512,16 +513,31 @@ class BanditLadiesSampler:
                     if pool.padded is not None:
                         pool.padded._ready = pool.ready
                 N.call("bliss_block_finish", n_cap, self._mode, C.byref(ws), C.byref(out), N.stream())
-                # the transpose is read by the backward pass only (the caller joins ``transpose_stream`` before it)
-                N.call("bliss_block_transpose", N.ptr(e32[0]), N.ptr(e32[1]), pool.cap_edges, pool.cap_src, pool.cap_dst,
-                       N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_bits), N.ptr(pool.t_pre), pool.t_words,
-                       N.ptr(pool.t_dst), N.ptr(pool.t_perm), N.ptr(pool.t_seg_ptr), 1,
-                       wsp.counter_ptr(block_id, "n_edges"), N.stream())
-                if side is not None:
+
+            def transpose(pool=pool, e32=e32, block_id=block_id):
+                # read by the backward pass only (the caller joins ``transpose_stream`` before it)
+                with torch.cuda.stream(back):
+                    N.call("bliss_block_transpose", N.ptr(e32[0]), N.ptr(e32[1]), pool.cap_edges, pool.cap_src,
+                           pool.cap_dst, N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_bits), N.ptr(pool.t_pre),
+                           pool.t_words, N.ptr(pool.t_dst), N.ptr(pool.t_perm), N.ptr(pool.t_seg_ptr), 1,
+                           wsp.counter_ptr(block_id, "n_edges"), N.stream())
+                    if side is not None:            # readers of the transpose (backward pass, GCN out-degrees) wait for this
+                        ev = torch.cuda.Event()
+                        ev.record(back)
+                        if pool.padded is not None:
+                            pool.padded._t_ready = ev
+
+            if side is not None:
+                with torch.cuda.stream(back):
                     done[block_id] = torch.cuda.Event()
                     done[block_id].record(back)
-                    if pool.padded is not None:     # readers of the transpose (backward pass, GCN out-degrees) wait for this
-                        pool.padded._t_ready = done[block_id]
+            if side is not None and block_id == 0 and defer_last_transpose:
+                # the input layer's transpose would run beside the first (bandwidth-bound) aggregation of the forward
+                # pass: the caller launches it after the forward pass instead
+                deferred.append(transpose)
+            else:
+                transpose()
+        return deferred
 
     # ---- bandit update ------------------------------------------------------------------------
     def calculate_alpha(self, mfg):

@@ -489,9 +489,21 @@ class Trainer:
 
         def body():          # graph A (the whole step on a single rank)
             main = torch.cuda.current_stream()
-            smp.enqueue_static(g, self._seeds_static, self._pools, self._step_dev, transpose_stream=self._side_t)
-            loss, pred, y = self._padded_fwd_bwd(not dp, after_forward=bandit_update if bandit else None,
-                                                 before_backward=lambda: main.wait_stream(self._side_t))
+            deferred = smp.enqueue_static(g, self._seeds_static, self._pools, self._step_dev,
+                                          transpose_stream=self._side_t,
+                                          defer_last_transpose=not isinstance(self.model, GCN))   # GCN reads out-degrees in forward
+
+            def after_forward():
+                self._side_t.wait_stream(main)       # the input layer's transpose: beside the backward pass of the upper layers
+                for launch in deferred:
+                    launch()
+                if bandit:
+                    bandit_update()
+
+            # no global join before the backward pass: every reader of a transpose waits for that block's own
+            # event (ops.block_transpose), so the upper layers' backward does not wait for the input layer's transpose
+            loss, pred, y = self._padded_fwd_bwd(not dp, after_forward=after_forward)
+            main.wait_stream(self._side_t)
             if bandit:
                 main.wait_stream(self._side_b)
             if not dp:
