@@ -223,12 +223,21 @@ class Block:
 
 
 class _LazyFrame(_Frame):
-    """Frame that falls back to gathering rows of the parent graph's ``ndata``/``edata``."""
+    """Frame that falls back to gathering rows of the parent graph's ``ndata``/``edata``.
+    ``on_set[key]`` (optional callables) fire after ``frame[key] = value``: the data-parallel step starts a
+    layer's bandit exchange as soon as the model has stored that layer's ``embed_norm``."""
 
     def __init__(self, block: Block, kind: str):
         super().__init__()
         self._block = block
         self._kind = kind
+        self.on_set = {}
+
+    def __setitem__(self, key, value):
+        dict.__setitem__(self, key, value)
+        hook = self.on_set.get(key) if self.on_set else None
+        if hook is not None:
+            hook()
 
     def __missing__(self, key):
         g = self._block._graph

@@ -614,9 +614,13 @@ class BanditLadiesSampler:
         if g.num_edges() >= 2 ** 31:
             raise NotImplementedError("the packed bandit exchange carries int32 CSC positions: |E| must be < 2^31")
         for idx, mfg in enumerate(mfgs):
-            assert mfg.num_edges() <= exchange.caps[idx]
-            self._reward_call(idx, mfg, g, self.calculate_alpha(mfg), None, x_out=exchange.x[idx],
-                              count_out=exchange.header.data_ptr() + 8 * idx, pos_out=exchange.pos[idx])
+            self.exp3_emit_layer(idx, mfg, g, exchange)
+
+    def exp3_emit_layer(self, idx, mfg, g, exchange):
+        """One layer of :meth:`exp3_emit` (needs the layer's ``embed_norm`` — and ``a_ij`` for GAT — only)."""
+        assert mfg.num_edges() <= exchange.caps[idx]
+        self._reward_call(idx, mfg, g, self.calculate_alpha(mfg), None, x_out=exchange.x[idx],
+                          count_out=exchange.header.data_ptr() + 8 * idx, pos_out=exchange.pos[idx])
 
     def exp3_apply(self, exchange, n_layers: int):
         """Apply all ranks' gathered updates (one kernel per layer, counts read from the headers)."""

@@ -292,6 +292,14 @@ class Trainer:
             return out.view(torch.int64).view(-1)
         return labels[nid32.long()]
 
+    def _padded_fwd(self):
+        g = self.dm.g
+        x, norm = ops.gather_rows(g.ndata["features"], self._pools[0].src_nid, with_norm=True)
+        x._bliss_row_norm = norm
+        y = self._gather_labels(g.ndata["labels"], self._seeds_static)
+        pred = self.model(self._padded, x)[: self.dm.batch_size]
+        return self.loss_fn(pred, y), pred.detach(), y
+
     def _capture(self):
         self.last_pred = None
         for pb in self._padded:                            # drop tensors of earlier forward passes
@@ -385,8 +393,20 @@ class Trainer:
         self._seeds_static.copy_(seeds, non_blocking=True)
         self._sync_lr()
         self._graph.replay()
-        if self._graph_b is not None:             # data parallel, two-graph form: the exchanges sit between the graphs
-            self._dp_exchange()
+        if self._graph_b is not None:             # data parallel: see _capture_full for the four graphs
+            main = torch.cuda.current_stream()
+            work = None
+            if self._exchange is not None:        # the bandit all-gather runs on NCCL's stream beside the backward pass
+                work = torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send, group=self.pg,
+                                                                async_op=True)
+            self._graph_a2.replay()
+            if work is not None:                  # … and so does the apply pass over all ranks' updates
+                with torch.cuda.stream(self._side_apply):
+                    work.wait()                   # (the all-gather itself was ordered after A1 when it was issued)
+                    self._graph_b1.replay()
+            self.grads.all_reduce_mean_(self.pg)
+            if work is not None:
+                main.wait_stream(self._side_apply)
             self._graph_b.replay()
         slot = self.graph_replays & 1
         self.graph_replays += 1
@@ -510,10 +530,59 @@ class Trainer:
                 self._step_dev.add_(1)
             return loss, pred, y
 
-        def body_b():        # graph B (data parallel): after the all-reduce / all-gather
-            self._optimizer_step()
+        # Data parallel: four graphs, so that the bandit all-gather and its apply pass overlap the backward pass:
+        #   A1 sampling + forward (+ every layer's exponents emitted as soon as its embed_norm exists)
+        #   -> all_gather (NCCL stream)  ||  A2 backward (+ the input layer's transpose on the side branch)
+        #   -> B1 apply all ranks' updates (side stream, after the all-gather)  ||  all_reduce of the gradients
+        #   -> B2 Adam + step counter.
+        early_emit = bandit and smp.model != "gat"      # GAT's alpha needs a_ij: emitted after the forward pass
+
+        def body_a1():
+            main = torch.cuda.current_stream()
+            self._dp_deferred = smp.enqueue_static(g, self._seeds_static, self._pools, self._step_dev,
+                                                   transpose_stream=self._side_t,
+                                                   defer_last_transpose=not isinstance(self.model, GCN))
+            if early_emit:
+                def make(l, pb):
+                    def hook():
+                        self._side_b.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(self._side_b):
+                            ops._wait_ready(pb)                      # the block's fill (side branch of the sampler)
+                            smp.exp3_emit_layer(l, pb, g, self._exchange)
+                    return hook
+                for l, pb in enumerate(self._padded):
+                    pb.srcdata.on_set["embed_norm"] = make(l, pb)
+            try:
+                loss, pred, y = self._padded_fwd()
+            finally:
+                for pb in self._padded:
+                    pb.srcdata.on_set.pop("embed_norm", None)
+            if bandit and not early_emit:
+                self._side_b.wait_stream(main)
+                with torch.cuda.stream(self._side_b):
+                    smp.exp3_emit(self._padded, g, self._exchange)
+            main.wait_stream(self._side_t)
+            if bandit:
+                main.wait_stream(self._side_b)
+            return loss, pred.detach(), y
+
+        def body_a2(loss):
+            main = torch.cuda.current_stream()
+            for pb in self._padded:       # A1 is complete in stream order; its events belong to another capture
+                pb._ready = pb._t_ready = None
+            self._side_t.wait_stream(main)
+            for launch in self._dp_deferred:                        # the input layer's transpose, beside the upper layers' backward
+                launch()
+            self._zero_grads()
+            loss.backward()
+            main.wait_stream(self._side_t)
+
+        def body_b1():
             if bandit:
                 smp.exp3_apply(self._exchange, L)
+
+        def body_b2():
+            self._optimizer_step()
             self._step_dev.add_(1)
 
         side = torch.cuda.Stream()
@@ -526,10 +595,15 @@ class Trainer:
             params = [p.detach().clone() for p in self.grads.params]
             self._seeds_static.copy_(self.dm.train_nid[: dm.batch_size])
             for _ in range(2):
-                body()
                 if dp:
+                    loss_w, _, _ = body_a1()
+                    body_a2(loss_w)
                     self._dp_exchange()
-                    body_b()
+                    body_b1()
+                    body_b2()
+                    del loss_w
+                else:
+                    body()
             # … must not change the training state: restore parameters, Adam moments, bandit weights
             for p, q in zip(self.grads.params, params):
                 p.data.copy_(q)
@@ -543,14 +617,27 @@ class Trainer:
         before = _native.STATS.launches
         # (Capturing NCCL's collectives into ONE graph with both halves was measured at N=2: no faster than
         # two replays with the collectives launched in between, and the process hung in NCCL teardown.)
-        self._graph_b = None
+        self._graph_b = self._graph_a2 = self._graph_b1 = None
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph, stream=self._main_hp):
-            self._static_loss, self._static_pred, self._static_y = body()
-        if dp:
+        if not dp:
+            with torch.cuda.graph(self._graph, stream=self._main_hp):
+                self._static_loss, self._static_pred, self._static_y = body()
+        else:
+            with torch.cuda.graph(self._graph, stream=self._main_hp):
+                loss, self._static_pred, self._static_y = body_a1()
+            self._static_loss = loss.detach()
+            self._graph_a2 = torch.cuda.CUDAGraph()     # the backward pass of A1's autograd graph: same memory pool
+            with torch.cuda.graph(self._graph_a2, pool=self._graph.pool(), stream=self._main_hp):
+                body_a2(loss)
+            del loss
+            self._graph_b1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_b1):
+                body_b1()
             self._graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph_b):
-                body_b()
+                body_b2()
+            if getattr(self, "_side_apply", None) is None:
+                self._side_apply = torch.cuda.Stream()
         self.graph_kernels = _native.STATS.launches - before    # hand-written kernels inside one replay
         _native.STATS.launches = before
 
