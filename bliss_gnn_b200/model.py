@@ -38,6 +38,8 @@ class _LinearSplitK(torch.autograd.Function):
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
             w = weight if extra == 0 else torch.nn.functional.pad(weight, (0, extra))
             y = torch.nn.functional.linear(x, w, bias)
+        if side is not None and w is not weight:
+            w.record_stream(torch.cuda.current_stream())     # allocated on the side stream, read by backward on this one
         ctx.save_for_backward(x, w)
         ctx.weight, ctx.has_bias = weight, bias is not None
         return y
