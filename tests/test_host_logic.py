@@ -1,0 +1,69 @@
+"""CPU tests of the host-side logic around the C ABI (no CUDA needed): scratch sizing of the balanced SpMM,
+the packed bandit-exchange layout, the block-frame hooks of the data-parallel step, flag parsing."""
+import torch
+
+from bliss_gnn_b200 import ops
+from bliss_gnn_b200.graph import Block, toy_graph
+from bliss_gnn_b200.parallel import BanditExchange, shard_batches
+from bliss_gnn_b200.train import Trainer, build_argparser
+
+
+def test_spmm_tiling_covers_every_vector_width():
+    """``ops._spmm_tiling`` must size the partial-sum scratch for whichever (VEC, NCH) ``launch_spmm`` picks
+    (csrc/aggregate.cu: VEC in {4,2,1} by divisibility/alignment, NCH = next power of two <= 8)."""
+    for d in (1, 7, 41, 64, 256, 300, 602, 604, 1030, 4096):
+        width, tiles = ops._spmm_tiling(d)
+        for vec in (4, 2, 1):
+            if d % vec:
+                continue
+            per_lane = -(-d // (32 * vec))
+            nch = 1
+            while nch < per_lane and nch < 8:
+                nch *= 2
+            tile = 32 * vec * nch
+            n = -(-d // tile)
+            assert width >= n * tile and tiles >= n and width >= d
+
+
+def test_exchange_layout_is_8_bytes_per_edge_and_aligned():
+    caps = [1000, 333, 7]
+    ex = BanditExchange(caps, world=3, device=torch.device("cpu"), group=None)
+    assert ex.recv.numel() == 3 * ex.stride and ex.stride % 16 == 0
+    end = BanditExchange.HEADER
+    for l, c in enumerate(caps):
+        assert ex.pos_off[l] >= end and ex.pos_off[l] % 4 == 0 and ex.x_off[l] == ex.pos_off[l] + 4 * c
+        assert ex.pos[l].dtype == torch.int32 and ex.x[l].dtype == torch.float32
+        assert ex.pos[l].numel() == c and ex.x[l].numel() == c
+        end = ex.x_off[l] + 4 * c
+    assert ex.stride - BanditExchange.HEADER <= 8 * sum(caps) + 16 * len(caps)
+    ex.pos[1][:3] = torch.tensor([5, 6, 7], dtype=torch.int32)            # views alias the send buffer
+    assert ex.send[ex.pos_off[1]:ex.pos_off[1] + 12].view(torch.int32).tolist() == [5, 6, 7]
+
+
+def test_block_frame_hook_fires_on_assignment():
+    idx = torch.zeros(1, dtype=torch.int32)
+    b = Block(torch.tensor([0, 0], dtype=torch.int32), idx[:0], idx[:0], idx, idx)
+    seen = []
+    b.srcdata.on_set["embed_norm"] = lambda: seen.append(b.srcdata["embed_norm"].item())
+    b.srcdata["embed_norm"] = torch.tensor(3.0)
+    b.srcdata["other"] = torch.tensor(1.0)
+    assert seen == [3.0]
+    b.srcdata.on_set.pop("embed_norm")
+    b.srcdata["embed_norm"] = torch.tensor(4.0)
+    assert seen == [3.0]
+
+
+def test_label_gather_plain_path_and_sharding():
+    labels = torch.arange(10) * 3
+    nid = torch.tensor([4, 0, 9], dtype=torch.int32)
+    assert Trainer._gather_labels(labels.float(), nid).tolist() == [12.0, 0.0, 27.0]   # non-int64: plain indexing
+    assert list(shard_batches(11, 1, 4)) == [1, 5] and list(shard_batches(3, 0, 4)) == []
+
+
+def test_cli_flags_match_the_reference_defaults():
+    """``train_lightning.py:489-552``: flag names and defaults."""
+    a = build_argparser().parse_args([])
+    assert (a.model, a.sampler, a.fan_out, a.batch_size, a.num_hidden, a.num_layers) == \
+        ("sage", "poisson-bandit", "16384,8192,4096", 1024, 256, 3)
+    assert (a.eta, a.lr, a.dropout, a.importance_sampling, a.precision) == (0.1, 0.002, 0.1, 1, "medium")
+    assert toy_graph().num_nodes() == 5
