@@ -825,8 +825,11 @@ __global__ void __launch_bounds__(1024) k_block_index(const int32_t* __restrict_
       if (base > out.cap_edges && out.cap_edges > 0) ctr->error |= BLISS_ERR_EDGE_CAPACITY;
     }
   }
-  {  // all CTAs: the seeds' rows of the source arrays and the padding that does not depend on the scan
-    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gn = (int64_t)gridDim.x * blockDim.x;
+  // CTA 0 only scans (it is the longest single piece); the other CTAs share everything else
+  if (blockIdx.x == 0 && gridDim.x > 1) return;
+  const int wb = (gridDim.x > 1) ? blockIdx.x - 1 : 0, wn = (gridDim.x > 1) ? gridDim.x - 1 : 1;   // worker CTA index / count
+  {  // the seeds' rows of the source arrays and the padding that does not depend on the scan
+    const int64_t gt = wb * (int64_t)blockDim.x + threadIdx.x, gn = (int64_t)wn * blockDim.x;
     for (int64_t i = gt; i < n_seeds; i += gn) {
       const int s = seeds[i];
       out.src_nid[i] = s;
@@ -868,7 +871,7 @@ __global__ void __launch_bounds__(1024) k_block_index(const int32_t* __restrict_
   // ranking: one warp per key, 32 keys per CTA round; every lane counts 1/32 of each tile
   constexpr int PER_T = BLISS_RANK_TILE / 1024;
   const int n_groups = (n_sel + 31) / 32;
-  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+  for (int grp = wb; grp < n_groups; grp += wn) {
     const int j = grp * 32 + warp_id();
     const bool valid = j < n_sel;
     const int nid = valid ? ws.sel[j] : 0;

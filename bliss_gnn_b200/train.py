@@ -271,7 +271,9 @@ class Trainer:
         x, norm = ops.gather_rows(g.ndata["features"], self._pools[0].src_nid, with_norm=True)
         x._bliss_row_norm = norm                       # layer 0's embed_norm comes with the gather (model.SAGE/GCN/GATv2)
         y = self._gather_labels(g.ndata["labels"], self._seeds_static)
-        pred = self.model(self._padded, x)[: self.dm.batch_size]
+        pred = self.model(self._padded, x)
+        if pred.shape[0] != self.dm.batch_size:          # (the top layer's capacity is the batch size: usually a no-op)
+            pred = pred[: self.dm.batch_size]
         loss = self.loss_fn(pred, y)
         if after_forward is not None:
             after_forward()
@@ -297,7 +299,9 @@ class Trainer:
         x, norm = ops.gather_rows(g.ndata["features"], self._pools[0].src_nid, with_norm=True)
         x._bliss_row_norm = norm
         y = self._gather_labels(g.ndata["labels"], self._seeds_static)
-        pred = self.model(self._padded, x)[: self.dm.batch_size]
+        pred = self.model(self._padded, x)
+        if pred.shape[0] != self.dm.batch_size:          # (the top layer's capacity is the batch size: usually a no-op)
+            pred = pred[: self.dm.batch_size]
         return self.loss_fn(pred, y), pred.detach(), y
 
     def _capture(self):
