@@ -116,7 +116,7 @@ PROTOTYPES = {
     "bliss_block_finish": [_I32, _I32, _WP, _BP, _P],
     "bliss_sample_layer_front": [_GP, _P, _I32, _P, _F, _I32, _I32, _D, _I32, _U64, _U64, _U32, _P, _P, _WP, _BP, _P],
     "bliss_sample_layer_back": [_GP, _P, _I32, _P, _F, _I32, _WP, _BP, _P],
-    "bliss_block_transpose": [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _P, _P],
+    "bliss_block_transpose": [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _P, _P, _P, _P],
     "bliss_gather_rows": [_P, _P, _I64, _I32, _P, _P, _P],
     "bliss_row_norm": [_P, _I64, _I32, _P, _P],
     "bliss_spmm": [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P, _I64, _P, _P],

@@ -1109,7 +1109,7 @@ __global__ void __launch_bounds__(256) k_t_rows(const int32_t* __restrict__ t_in
 __global__ void k_t_place(const int32_t* __restrict__ edge_src, const int32_t* __restrict__ edge_dst, int64_t n_edges,
                           const int64_t* __restrict__ n_edges_dev, const int32_t* __restrict__ t_indptr,
                           const uint32_t* __restrict__ bits, const int32_t* __restrict__ pre, int64_t t_words,
-                          int32_t* __restrict__ t_perm) {
+                          int32_t* __restrict__ t_perm, const float* __restrict__ edge_w, float* __restrict__ t_w) {
   if (n_edges_dev) n_edges = min(n_edges, *n_edges_dev);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += stride) {
@@ -1117,6 +1117,7 @@ __global__ void k_t_place(const int32_t* __restrict__ edge_src, const int32_t* _
     const int64_t wi = (int64_t)s * t_words + (d >> 5);
     const int slot = t_indptr[s] + pre[wi] + __popc(bits[wi] & ((1u << (d & 31)) - 1u));
     t_perm[slot] = (int32_t)e;
+    if (t_w) t_w[slot] = edge_w[e];   // block weights in transpose order: the backward SpMM streams them
   }
 }
 
@@ -1348,8 +1349,10 @@ int bliss_block_finish(int32_t n_seeds, int32_t mode, const bliss_workspace* ws,
 int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                           int32_t n_src, int32_t n_dst, int32_t* t_indptr, int32_t* t_cursor,
                           uint32_t* t_bits, int32_t* t_pre, int64_t t_words, int32_t* t_dst, int32_t* t_perm,
-                          int32_t* t_seg_ptr, int32_t have_counts, const int64_t* n_edges_dev, void* stream) {
+                          int32_t* t_seg_ptr, int32_t have_counts, const int64_t* n_edges_dev, const float* edge_w,
+                          float* t_w, void* stream) {
   if (n_edges < 0 || n_src < 0 || !t_indptr || !t_cursor) return -1;
+  if ((edge_w == nullptr) != (t_w == nullptr)) return -1;
   if (n_edges > 0 && (!edge_src || !edge_dst || !t_bits || !t_pre || !t_dst || !t_perm)) return -1;
   if (n_edges > 0 && t_words < (n_dst + 31) / 32) return -1;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1374,7 +1377,7 @@ int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int6
                                                                               t_pre, t_dst);
   BLISS_CHECK_LAUNCH();
   k_t_place<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, edge_dst, n_edges, n_edges_dev, t_indptr,
-                                                                   t_bits, t_pre, t_words, t_perm);
+                                                                   t_bits, t_pre, t_words, t_perm, edge_w, t_w);
   BLISS_CHECK_LAUNCH();
   return 0;
 }

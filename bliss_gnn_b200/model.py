@@ -26,7 +26,7 @@ class _LinearSplitK(torch.autograd.Function):
     ``weight.grad`` when that buffer exists (the flat gradient buffer of ``parallel.FlatGrads``), else summed
     and returned.  ``weight`` is the un-padded parameter; ``x`` may carry zero-padded extra columns."""
 
-    SPLIT, MIN_ROWS = 32, 2048
+    SPLIT, MIN_ROWS = 16, 2048
 
     @staticmethod
     def forward(ctx, x, weight, bias, side=None):

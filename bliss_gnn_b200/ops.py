@@ -54,7 +54,7 @@ def block_transpose_into(block, pool):
     N.call("bliss_block_transpose", N.ptr(block.edge_src), N.ptr(block.edge_dst), E, pool.cap_src, n_dst,
            N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_bits), N.ptr(pool.t_pre), pool.t_words,
            N.ptr(pool.t_dst), N.ptr(pool.t_perm),
-           N.ptr(pool.t_seg_ptr), 1, None, N.stream())    # counts were accumulated by the fill kernel (out_deg)
+           N.ptr(pool.t_seg_ptr), 1, None, None, None, N.stream())    # counts were accumulated by the fill kernel (out_deg)
     block._transpose = (pool.t_indptr[:block.num_src_nodes() + 1], pool.t_dst[:E], pool.t_perm[:E],
                         pool.t_seg_ptr[:block.num_src_nodes() + 1])
 
@@ -76,7 +76,7 @@ def block_transpose(block):
         N.call("bliss_block_transpose", N.ptr(block.edge_src), N.ptr(block.edge_dst), E, n_src, n_dst,
                N.ptr(t_indptr), N.ptr(t_cursor), N.ptr(t_bits), N.ptr(t_pre), t_words, N.ptr(t_dst), N.ptr(t_perm),
                N.ptr(t_seg),
-               0, None, N.stream())
+               0, None, None, None, N.stream())
         block._transpose = (t_indptr, t_dst[:E], t_perm[:E], t_seg)
     return block._transpose
 
@@ -139,8 +139,12 @@ class _SpMM(torch.autograd.Function):
         block = ctx.block
         t_indptr, t_dst, t_perm, t_seg = block_transpose(block)
         gy = _req(gy, name="grad")
+        w, perm = ctx.w, t_perm
+        t_w = getattr(block, "_t_w", None)
+        if t_w is not None and w is not None and w.data_ptr() == t_w[0]:
+            w, perm = t_w[1], None            # the transpose carries these weights in its own order: no gather through perm
         # dx_c = sscale_c * Σ_{e: src_e = c} w_e * dscale_{dst_e} * dy_{dst_e}
-        gx = _spmm_raw(t_indptr, t_dst, t_perm, ctx.w, ctx.dscale, ctx.sscale, N.AGG_SUM, gy,
+        gx = _spmm_raw(t_indptr, t_dst, perm, w, ctx.dscale, ctx.sscale, N.AGG_SUM, gy,
                        block.num_src_nodes(), t_seg)
         return gx, None, None, None, None
 

@@ -153,6 +153,7 @@ class LayerPool:
         self.t_dst = torch.zeros(self.cap_edges, **i32)
         self.t_perm = torch.zeros(self.cap_edges, **i32)
         self.t_seg_ptr = torch.zeros(self.cap_src + 1, **i32)
+        self.t_w = torch.zeros(self.cap_edges, dtype=torch.float32, device=device)   # block weights in transpose order
         self.padded = None      # the capacity-sized Block the captured graph runs on
 
     def fits(self, n_dst, n_src, n_edges) -> bool:
@@ -520,7 +521,9 @@ class BanditLadiesSampler:
                     N.call("bliss_block_transpose", N.ptr(e32[0]), N.ptr(e32[1]), pool.cap_edges, pool.cap_src,
                            pool.cap_dst, N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_bits), N.ptr(pool.t_pre),
                            pool.t_words, N.ptr(pool.t_dst), N.ptr(pool.t_perm), N.ptr(pool.t_seg_ptr), 1,
-                           wsp.counter_ptr(block_id, "n_edges"), N.stream())
+                           wsp.counter_ptr(block_id, "n_edges"), N.ptr(e32[3]), N.ptr(pool.t_w), N.stream())
+                    if pool.padded is not None:     # (weights tensor it was built from, transposed copy)
+                        pool.padded._t_w = (e32[3].data_ptr(), pool.t_w)
                     if side is not None:            # readers of the transpose (backward pass, GCN out-degrees) wait for this
                         ev = torch.cuda.Event()
                         ev.record(back)

@@ -193,6 +193,8 @@ int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int6
                           int32_t* t_seg_ptr /* [n_src+1] 32-edge segment prefix of the source rows; may be NULL */,
                           int32_t have_counts,
                           const int64_t* n_edges_dev /* true edge count on the device, or NULL */,
+                          const float* edge_w /* [E] block weights, or NULL */,
+                          float* t_w /* [E] the same weights in transpose order (t_w[k] = edge_w[t_perm[k]]), or NULL */,
                           void* stream);
 
 /* ---- (5) aggregation ------------------------------------------------------------------------
