@@ -195,17 +195,19 @@ def test_full_graph_inference(native_lib):
     _close(pred, h, what="full-graph inference")
 
 
-@pytest.mark.parametrize("kind", ["sage", "gcn", "gat"])
-def test_static_graph_step_matches_eager(native_lib, kind):
-    """Trainer(static_graph=True) — padded blocks + one replayed CUDA graph for fwd/bwd/Adam — follows
-    the same loss trajectory as the eager step (same seeds, same Philox draws, dropout off)."""
+@pytest.mark.parametrize("kind,sampler", [("sage", "poisson-bandit"), ("gcn", "poisson-bandit"), ("gat", "poisson-bandit"),
+                                          ("sage", "bandit"), ("sage", "ladies"), ("sage", "poisson-ladies")])
+def test_static_graph_step_matches_eager(native_lib, kind, sampler):
+    """Trainer(static_graph=True) — the whole step (sampling with every sampler of the CLI, forward, backward,
+    Adam, bandit update) as one replayed CUDA graph over capacity-padded blocks — follows the same loss
+    trajectory as the eager step (same seeds, same Philox draws, dropout off)."""
     from bliss_gnn_b200.graph import synthetic_graph
     from bliss_gnn_b200.train import DataModule, Trainer, build_model
     dev = _dev()
     g = synthetic_graph("flickr", seed=0, scale=0.05).to(dev)      # 4.5 K nodes, half of them training nodes
     losses = {}
     for static in (False, True):
-        dm = DataModule("flickr", fan_out=[128, 64, 32], eta=0.1, device=dev, batch_size=32, sampler="poisson-bandit",
+        dm = DataModule("flickr", fan_out=[128, 64, 32], eta=0.1, device=dev, batch_size=32, sampler=sampler,
                         model=kind, seed=0, graph=g)
         torch.manual_seed(3)
         model = build_model(kind, dm.in_feats, 64, dm.n_classes, 3, dropout=0.0, attn_dropout=0.0,
@@ -219,15 +221,17 @@ def test_static_graph_step_matches_eager(native_lib, kind):
             tr.flush()                       # pipelined counters: the last step's are still outstanding
         assert tr.num_steps == 12 and tr.total_sampled_edges > 0
         losses[static] = out
+        bandit = "bandit" in sampler
         if static:
             assert tr.graph_replays >= 7
-            w_static = dm.sampler.exp3_weights.clone()
+            w_static = dm.sampler.exp3_weights.clone() if bandit else None
         else:
-            w_eager = dm.sampler.exp3_weights.clone()
+            w_eager = dm.sampler.exp3_weights.clone() if bandit else None
     for a, b in zip(losses[False], losses[True]):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(a)), (losses[False], losses[True])
-    # GAT's alpha divides by sums of signed logits: padded-vs-exact GEMM rounding is amplified there
-    torch.testing.assert_close(w_static, w_eager, rtol=2e-3 if kind == "gat" else 1e-4, atol=0)
+    if bandit:
+        # GAT's alpha divides by sums of signed logits: padded-vs-exact GEMM rounding is amplified there
+        torch.testing.assert_close(w_static, w_eager, rtol=2e-3 if kind == "gat" else 1e-4, atol=0)
 
 
 def test_data_parallel_graph_path_on_one_rank(native_lib, monkeypatch):
