@@ -609,7 +609,7 @@ class BanditLadiesSampler:
         N.call("bliss_l1_norm", N.ptr(w), w.numel(), N.ptr(self._norm_partial), N.ptr(self._l1[idx:idx + 1]),
                                 N.stream())
         N.call("bliss_scale_by_inv", N.ptr(w), w.numel(), N.ptr(self._l1[idx:idx + 1]), 1e-12, N.stream())
-        self._l1[idx] = 1.0
+        self._l1[idx:idx + 1].fill_(1.0)      # (a fill launch: capturable, unlike assigning a Python scalar)
 
     def exp3_emit(self, mfgs, g, exchange):
         """Data-parallel, sync-free: compute every layer's clamped exponents into the exchange's send

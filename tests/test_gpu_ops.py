@@ -196,7 +196,8 @@ def test_full_graph_inference(native_lib):
 
 
 @pytest.mark.parametrize("kind,sampler", [("sage", "poisson-bandit"), ("gcn", "poisson-bandit"), ("gat", "poisson-bandit"),
-                                          ("sage", "bandit"), ("sage", "ladies"), ("sage", "poisson-ladies")])
+                                          ("sage", "bandit"), ("sage", "ladies"), ("sage", "poisson-ladies"),
+                                          ("sage", "poisson-bandit/literal")])
 def test_static_graph_step_matches_eager(native_lib, kind, sampler):
     """Trainer(static_graph=True) — the whole step (sampling with every sampler of the CLI, forward, backward,
     Adam, bandit update) as one replayed CUDA graph over capacity-padded blocks — follows the same loss
@@ -206,9 +207,10 @@ def test_static_graph_step_matches_eager(native_lib, kind, sampler):
     dev = _dev()
     g = synthetic_graph("flickr", seed=0, scale=0.05).to(dev)      # 4.5 K nodes, half of them training nodes
     losses = {}
+    sampler, _, normalize = sampler.partition("/")       # "<sampler>/literal": dense L1 renormalisation after every update
     for static in (False, True):
         dm = DataModule("flickr", fan_out=[128, 64, 32], eta=0.1, device=dev, batch_size=32, sampler=sampler,
-                        model=kind, seed=0, graph=g)
+                        model=kind, seed=0, graph=g, normalize=normalize or "lazy")
         torch.manual_seed(3)
         model = build_model(kind, dm.in_feats, 64, dm.n_classes, 3, dropout=0.0, attn_dropout=0.0,
                             faithful_gcn_quirk=False).to(dev)
