@@ -138,6 +138,7 @@ class Trainer:
         self.pipeline, self._pending = bool(pipeline), None
         self.total_sampled_edges = 0        # Σ block edges over all consumed steps (bench.py's edges/s)
         self.pool_resizes = 0               # capacity re-sizings (each one re-captures the step graph)
+        self._dev_step_mirror = None        # host's view of the device-side Philox step counter
         # the data-parallel code path (two graphs with the collectives in between) can be forced on a
         # single rank, so it is testable on one GPU
         self._force_dp = bool(os.environ.get("BLISS_FORCE_DP_PATH")) and process_group is not None
@@ -396,7 +397,10 @@ class Trainer:
             self._capture_full()
         self._seeds_static.copy_(seeds, non_blocking=True)
         self._sync_lr()
+        if smp.step != self._dev_step_mirror:     # eager sampling in between (validation, ragged batch) advanced the
+            self._step_dev.fill_(smp.step)        # host's Philox step: the device counter follows, draws never repeat
         self._graph.replay()
+        self._dev_step_mirror = smp.step + 1
         if self._graph_b is not None:             # data parallel: see _capture_full for the four graphs
             main = torch.cuda.current_stream()
             work = None
@@ -617,6 +621,7 @@ class Trainer:
                     smp._w_csc[l].copy_(w)
                 smp._l1.copy_(state[1])
             self._step_dev.fill_(smp.step)
+            self._dev_step_mirror = smp.step
         torch.cuda.current_stream().wait_stream(side)
         before = _native.STATS.launches
         # (Capturing NCCL's collectives into ONE graph with both halves was measured at N=2: no faster than
@@ -751,7 +756,7 @@ def main(argv=None):
         model = build_model(args.model, dm.in_feats, args.num_hidden, dm.n_classes, args.num_layers, args.dropout,
                             args.num_in_heads, args.num_out_heads, args.attn_dropout, args.negative_slope,
                             args.residual).to(device)
-        tr = Trainer(dm, model, args.lr, pg)
+        tr = Trainer(dm, model, args.lr, pg, static_graph=True)     # whole-step CUDA graph (ragged batches run eagerly)
         step, epoch, best_val, done = 0, 0, -1.0, False
         t_prev = time.time()
         while not done:
