@@ -11,12 +11,10 @@
 #include "../../include/bliss_b200.h"
 
 #define BLISS_SM_COUNT 148
-#define BLISS_REG_BIT 0x8000000000000000ull   // acc[v] bit 63: node registered as candidate
+#define BLISS_REG_BIT 0x8000000000000000ull   // acc[v] bit 63: reserved flag bit (masked off when acc is read)
 #define BLISS_S_FIX_BITS 40                    // fixed point of the scale-search sum
-#define BLISS_LIGHT_MAX 256                    // rows up to this degree are handled by one warp
 #define BLISS_CTA 256                          // threads per CTA of the row kernels
 #define BLISS_WARPS (BLISS_CTA / 32)
-#define BLISS_STAGE_CAP 6144                   // floats of a heavy row staged in shared memory (24 KB)
 #define BLISS_CHUNK 256                        // edges per warp-chunk of the probability passes
 #define BLISS_SPMM_SEG 32                       // edges per warp-segment of the balanced SpMM (rows are cut into segments)
 
