@@ -26,6 +26,15 @@
 
 namespace bliss {
 
+// Programmatic dependent launch: a kernel launched with launch_pdl() may become resident while its
+// predecessor in the stream is still draining; pdl_wait() (first statement, before any read of the
+// predecessor's output) blocks until the predecessor grid has completed and its writes are visible;
+// pdl_trigger() lets the successor be scheduled as soon as every CTA of this grid has started.  Every
+// kernel of the sampling chain is at most one wave, so the waiting CTAs never hold a slot this grid
+// still needs.  Without a programmatic edge both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 

@@ -33,6 +33,8 @@ struct GraphView {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_plan_rows(GraphView g, const int32_t* __restrict__ seeds, int n_seeds,
                                                   bliss_workspace ws) {
+  pdl_wait();
+  pdl_trigger();
   // sync-free chaining of layers: the true seed count may live on the device (the previous
   // layer's n_src); the host value is then only the capacity
   if (ws.n_seeds_dev) n_seeds = min(n_seeds, *ws.n_seeds_dev);
@@ -71,6 +73,8 @@ __device__ __forceinline__ void store4(int32_t* __restrict__ p, int i0, int n, c
 }
 
 __global__ void __launch_bounds__(1024) k_plan_scan(int n_seeds, bliss_workspace ws) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ int s_scan[40];
   __shared__ unsigned long long s_e[32];
   bliss_counters* ctr = ws.ctr;
@@ -174,6 +178,8 @@ __device__ __forceinline__ ChunkRef chunk_ref(const bliss_workspace& ws, int c) 
 }
 // one warp per row: the row's chunk records
 __global__ void __launch_bounds__(256) k_plan_chunks(bliss_workspace ws) {
+  pdl_wait();
+  pdl_trigger();
   const int n_seeds = ws.ctr->n_seeds;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int i = warp; i < n_seeds; i += nwarps) {
@@ -218,6 +224,8 @@ struct ChunkLoop {
 };
 
 __global__ void __launch_bounds__(BLISS_CTA, 6) k_prob_pass1(const float* __restrict__ W, bliss_workspace ws) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = lane_id();
   const int n_chunks = ws.ctr->n_chunks;
   for (ChunkLoop q(&ws.ctr->queue[0], n_chunks); q.more(); q.next()) {
@@ -237,6 +245,8 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_prob_pass1(const float* __rest
 
 __global__ void __launch_bounds__(BLISS_CTA, 6) k_prob_pass2(const float* __restrict__ W, float eta, float one_minus_eta,
                                                          bliss_workspace ws) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = lane_id();
   const int n_chunks = ws.ctr->n_chunks;
   for (ChunkLoop q(&ws.ctr->queue[1], n_chunks); q.more(); q.next()) {
@@ -267,6 +277,8 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_prob_pass2(const float* __rest
 
 __global__ void __launch_bounds__(BLISS_CTA, 5) k_prob_pass3(GraphView g, const float* __restrict__ W, float eta,
                                                          float one_minus_eta, int mode_flags, bliss_workspace ws) {
+  pdl_wait();
+  pdl_trigger();
   const int mode = mode_flags & 1;
   const bool uniform = (mode_flags & BLISS_MODE_UNIFORM);
   const bool bitmap = (mode_flags & BLISS_COLLECT_BITMAP);
@@ -318,6 +330,8 @@ __global__ void __launch_bounds__(BLISS_CTA, 5) k_prob_pass3(GraphView g, const 
 // shared counter (thousands of same-address atomics would serialise in L2).
 #define BLISS_COLLECT_WORDS 4
 __global__ void __launch_bounds__(256) k_collect_candidates(int64_t num_nodes, int bitmap, bliss_workspace ws) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ int s_scan[40];
   __shared__ int s_base;
   const int lane = lane_id();
@@ -456,6 +470,8 @@ __device__ __forceinline__ void push_selected(bool sel, int nid, const bliss_wor
 #define BLISS_SCALE_NREG 16
 #define BLISS_SCALE_MAX_CLUSTER 16
 __global__ void __launch_bounds__(1024, 1) k_scale_search(int fanout, double eps, bliss_workspace ws) {
+  pdl_wait();
+  pdl_trigger();
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
   const unsigned nblk = cluster.num_blocks();
@@ -521,6 +537,8 @@ __global__ void __launch_bounds__(256) k_select_poisson(int n_seeds, unsigned lo
                                                        unsigned long long step, unsigned layer,
                                                        const float* __restrict__ u_inject,
                                                        bliss_workspace ws) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ int s_scan[40];
   __shared__ int s_base;
   n_seeds = ws.ctr->n_seeds;   // the plan's (possibly device-side) count, not the host capacity
@@ -698,6 +716,8 @@ struct FillCtx {
 // would cost more than streaming the indices) but shared memory serves at bank speed.
 template <bool SMEM_BITS>
 __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_count(FillCtx c, bliss_workspace ws, int bit_words) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ uint32_t s_bits[];
   __shared__ unsigned char s_k[BLISS_WARPS][BLISS_CHUNK];   // chunk-relative positions of the kept edges
   bliss_counters* ctr = ws.ctr;
@@ -774,6 +794,8 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_count(FillCtx c, bliss_w
 #define BLISS_RANK_TILE 2048
 __global__ void __launch_bounds__(1024) k_block_index(const int32_t* __restrict__ seeds, int n_seeds,
                                                      bliss_workspace ws, bliss_block_out out) {
+  pdl_wait();
+  pdl_trigger();
   n_seeds = ws.ctr->n_seeds;   // the plan's (possibly device-side) count, not the host capacity
   __shared__ unsigned long long s_keys[BLISS_RANK_TILE];
   __shared__ int s_scan[40];
@@ -1128,6 +1150,36 @@ __global__ void k_t_place(const int32_t* __restrict__ edge_src, const int32_t* _
 // ==========================================================================================
 using namespace bliss;
 
+// Launch with a programmatic edge to the previous kernel of the stream (see pdl_wait in common.cuh).
+// BLISS_PDL=0 in the environment falls back to ordinary stream order.
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("BLISS_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define BLISS_LAUNCH_PDL(...)                       \
+  do {                                              \
+    cudaError_t e__ = launch_pdl(__VA_ARGS__);      \
+    if (e__ != cudaSuccess) return (int)e__;        \
+  } while (0)
+
 static inline GraphView view_of(const bliss_graph* g) {
   GraphView v;
   v.indptr = g->indptr;
@@ -1168,14 +1220,11 @@ int bliss_frontier_plan(const bliss_graph* g, const int32_t* seeds, int32_t n_se
   if (!g || !seeds || !ws || n_seeds < 0 || n_seeds > ws->cap_seeds) return -1;
   cudaStream_t st = (cudaStream_t)stream;
   if (n_seeds > 0) {
-    k_plan_rows<<<(n_seeds + 255) / 256, 256, 0, st>>>(view_of(g), seeds, n_seeds, *ws);
-    BLISS_CHECK_LAUNCH();
+    BLISS_LAUNCH_PDL(k_plan_rows, dim3((n_seeds + 255) / 256), dim3(256), 0, st, view_of(g), seeds, n_seeds, *ws);
   }
-  k_plan_scan<<<1, 1024, 0, st>>>(n_seeds, *ws);
-  BLISS_CHECK_LAUNCH();
+  BLISS_LAUNCH_PDL(k_plan_scan, dim3(1), dim3(1024), 0, st, n_seeds, *ws);
   if (n_seeds > 0) {
-    k_plan_chunks<<<grid_for((int64_t)n_seeds * 32, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(*ws);
-    BLISS_CHECK_LAUNCH();
+    BLISS_LAUNCH_PDL(k_plan_chunks, dim3(grid_for((int64_t)n_seeds * 32, 256, BLISS_SM_COUNT * 8)), dim3(256), 0, st, *ws);
   }
   return 0;
 }
@@ -1192,16 +1241,13 @@ int bliss_frontier_prob(const bliss_graph* g, const int32_t* seeds, int32_t n_se
   const int blocks = chunk_grid(n_seeds);
   const bool bandit = (mode & 1) == BLISS_MODE_BANDIT;
   if (bandit) {   // the row sums are also needed by the block fill when importance sampling is off
-    k_prob_pass1<<<blocks, 256, 0, st>>>(edge_weight_csc, *ws);
-    BLISS_CHECK_LAUNCH();
-    k_prob_pass2<<<blocks, 256, 0, st>>>(edge_weight_csc, eta, one_minus_eta, *ws);
-    BLISS_CHECK_LAUNCH();
+    BLISS_LAUNCH_PDL(k_prob_pass1, dim3(blocks), dim3(256), 0, st, edge_weight_csc, *ws);
+    BLISS_LAUNCH_PDL(k_prob_pass2, dim3(blocks), dim3(256), 0, st, edge_weight_csc, eta, one_minus_eta, *ws);
   }
-  k_prob_pass3<<<chunk_grid(n_seeds, 5), 256, 0, st>>>(view_of(g), edge_weight_csc, eta, one_minus_eta, mode, *ws);
-  BLISS_CHECK_LAUNCH();
-  k_collect_candidates<<<grid_for(g->num_nodes, 32 * BLISS_COLLECT_WORDS * 8, BLISS_SM_COUNT * 8), 256, 0, st>>>(
-      g->num_nodes, (mode & BLISS_COLLECT_BITMAP) ? 1 : 0, *ws);
-  BLISS_CHECK_LAUNCH();
+  BLISS_LAUNCH_PDL(k_prob_pass3, dim3(chunk_grid(n_seeds, 5)), dim3(256), 0, st, view_of(g), edge_weight_csc, eta,
+                   one_minus_eta, (int)mode, *ws);
+  BLISS_LAUNCH_PDL(k_collect_candidates, dim3(grid_for(g->num_nodes, 32 * BLISS_COLLECT_WORDS * 8, BLISS_SM_COUNT * 8)),
+                   dim3(256), 0, st, (int64_t)g->num_nodes, (mode & BLISS_COLLECT_BITMAP) ? 1 : 0, *ws);
   return 0;
 }
 
@@ -1217,8 +1263,8 @@ int bliss_poisson_scale(int32_t n_seeds, int32_t fanout, double eps, int32_t poi
 int bliss_select_poisson(int32_t n_seeds, uint64_t seed, uint64_t step, uint32_t layer,
                          const float* u_inject, const bliss_workspace* ws, void* stream) {
   if (!ws) return -1;
-  k_select_poisson<<<BLISS_SM_COUNT * 2, 256, 0, (cudaStream_t)stream>>>(n_seeds, seed, step, layer, u_inject, *ws);
-  BLISS_CHECK_LAUNCH();
+  BLISS_LAUNCH_PDL(k_select_poisson, dim3(BLISS_SM_COUNT * 2), dim3(256), 0, (cudaStream_t)stream, (int)n_seeds,
+                   (unsigned long long)seed, (unsigned long long)step, (unsigned)layer, u_inject, *ws);
   return 0;
 }
 
@@ -1255,12 +1301,14 @@ int bliss_poisson_select(int32_t n_seeds, int32_t fanout, double eps, uint64_t s
   cfg.gridDim = dim3(g_cluster_size);
   cfg.blockDim = dim3(1024);
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = g_cluster_size;
   attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, k_scale_search, (int)fanout, eps, *ws);
   if (e != cudaSuccess) return (int)e;
   return bliss_select_poisson(n_seeds, seed, step, layer, u_inject, ws, stream);
@@ -1305,19 +1353,19 @@ int bliss_block_count(const bliss_graph* g, const int32_t* seeds, int32_t n_seed
   const int bit_words = (int)((g->num_nodes + 31) / 32);
   const size_t smem = (size_t)bit_words * sizeof(uint32_t);
   if (smem <= 35 * 1024) {
-    k_block_count<true><<<chunk_grid(n_seeds), BLISS_CTA, smem, (cudaStream_t)stream>>>(c, *ws, bit_words);
+    BLISS_LAUNCH_PDL(k_block_count<true>, dim3(chunk_grid(n_seeds)), dim3(BLISS_CTA), smem, (cudaStream_t)stream, c, *ws,
+                     bit_words);
   } else {
-    k_block_count<false><<<chunk_grid(n_seeds), BLISS_CTA, 0, (cudaStream_t)stream>>>(c, *ws, bit_words);
+    BLISS_LAUNCH_PDL(k_block_count<false>, dim3(chunk_grid(n_seeds)), dim3(BLISS_CTA), 0, (cudaStream_t)stream, c, *ws,
+                     bit_words);
   }
-  BLISS_CHECK_LAUNCH();
   return 0;
 }
 
 int bliss_block_index(const int32_t* seeds, int32_t n_seeds, const bliss_workspace* ws,
                       const bliss_block_out* out, void* stream) {
   if (!seeds || !ws || !out || !out->indptr || !out->src_nid || !out->node_prob) return -1;
-  k_block_index<<<BLISS_SM_COUNT, 1024, 0, (cudaStream_t)stream>>>(seeds, n_seeds, *ws, *out);
-  BLISS_CHECK_LAUNCH();
+  BLISS_LAUNCH_PDL(k_block_index, dim3(BLISS_SM_COUNT), dim3(1024), 0, (cudaStream_t)stream, seeds, (int)n_seeds, *ws, *out);
   return 0;
 }
 
