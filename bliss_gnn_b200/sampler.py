@@ -213,6 +213,7 @@ class BanditLadiesSampler:
     def _bind(self, g: Graph):
         if self._g is not g:
             self._wsp = _Workspace(g)
+            self._wsp2 = None          # the whole-step graph's second workspace belongs to the previous graph
             self._g = g
             self._w_csc = None
         if self._w_csc is None and self._mode == N.MODE_BANDIT:
@@ -463,7 +464,12 @@ class BanditLadiesSampler:
         """Enqueue the sampling of every layer into the capacity pools with NO host synchronisation:
         each layer reads its true seed count from the previous layer's device counters, the Philox
         step from ``step_dev``, and the transpose its edge count from the counters.  Capturable in a
-        CUDA graph; the caller reads all counters once per step (``_Workspace.read_all_counters``)."""
+        CUDA graph; the caller reads all counters once per step (``_Workspace.read_all_counters``).
+
+        ``transpose_stream``: side stream for every layer's back half (fill, workspace restore, transpose); the
+        padded blocks get ``_ready`` / ``_t_ready`` events their readers wait for, and the caller must join the
+        stream before the step ends.  ``defer_last_transpose``: do not launch the input layer's transpose here but
+        return it (a list of callables) for the caller to launch after the forward pass."""
         wsp = self._bind(g)
         L = len(self.nodes_per_layer)
         bandit = self._mode == N.MODE_BANDIT
