@@ -308,6 +308,7 @@ class Trainer:
     def _capture(self):
         self.last_pred = None
         for pb in self._padded:                            # drop tensors of earlier forward passes
+            pb._ready = pb._t_ready = pb._t_w = None       # (and side-branch events of a whole-step capture)
             for k in ("embed_norm",):
                 dict.pop(pb.srcdata, k, None)
             dict.pop(pb.edata, "a_ij", None)
