@@ -257,18 +257,19 @@ class BanditLadiesSampler:
         v = value.to(device=g.device, dtype=torch.float32)
         for l in range(v.shape[0]):
             self._w_csc[l].copy_(v[l, g.eid.long()])
-        self._l1 = torch.stack([w.double().abs().sum() for w in self._w_csc])
+        self._l1.copy_(torch.stack([w.double().abs().sum() for w in self._w_csc]))   # in place (captured graphs)
         self._updated = [True] * v.shape[0]
 
     def state_dict(self):
-        return {"exp3_w_csc": torch.stack(list(self._w_csc)), "l1": self._l1, "updated": self._updated, "step": self.step,
-                "rng_seed": self.rng_seed}
+        return {"exp3_w_csc": torch.stack(list(self._w_csc)), "l1": self._l1.clone(), "updated": list(self._updated),
+                "step": self.step, "rng_seed": self.rng_seed, "updates_since_renorm": self._updates_since_renorm}
 
     def load_state_dict(self, sd, g: Graph):
         self._bind(g)
         for l, w in enumerate(sd["exp3_w_csc"]):
             self._w_csc[l].copy_(w)
-        self._l1 = sd["l1"].to(g.device).clone()
+        self._l1.copy_(sd["l1"])          # in place: a captured step graph holds this buffer's address
+        self._updates_since_renorm = int(sd.get("updates_since_renorm", 0))
         self._updated = list(sd["updated"])
         self.step = int(sd["step"])
         self.rng_seed = int(sd["rng_seed"])

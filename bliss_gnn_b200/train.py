@@ -139,6 +139,7 @@ class Trainer:
         self.total_sampled_edges = 0        # Σ block edges over all consumed steps (bench.py's edges/s)
         self.pool_resizes = 0               # capacity re-sizings (each one re-captures the step graph)
         self._dev_step_mirror = None        # host's view of the device-side Philox step counter
+        self._sizing_steps = 0              # ordinary (eager) steps seen so far: they size the capacity pools
         # the data-parallel code path (two graphs with the collectives in between) can be forced on a
         # single rank, so it is testable on one GPU
         self._force_dp = bool(os.environ.get("BLISS_FORCE_DP_PATH")) and process_group is not None
@@ -332,8 +333,9 @@ class Trainer:
         dm, g, smp = self.dm, self.dm.g, self.dm.sampler
         L = len(smp.nodes_per_layer)
         if self._pools is None:
-            if self.num_steps < self.eager_warmup or seeds.numel() != dm.batch_size:
+            if self._sizing_steps < self.eager_warmup or seeds.numel() != dm.batch_size:
                 _, _, mfgs = smp.sample_blocks(g, seeds)
+                self._sizing_steps += 1
                 if self._max_src is None:
                     self._max_src, self._max_edges = [0] * L, [0] * L
                 for l, b in enumerate(mfgs):
@@ -385,8 +387,9 @@ class Trainer:
         dm, g, smp = self.dm, self.dm.g, self.dm.sampler
         L = len(smp.nodes_per_layer)
         if self._pools is None or seeds.numel() != dm.batch_size:
-            if self.num_steps < self.eager_warmup or seeds.numel() != dm.batch_size:
+            if self._sizing_steps < self.eager_warmup or self._max_src is None or seeds.numel() != dm.batch_size:
                 _, _, mfgs = smp.sample_blocks(g, seeds)           # ordinary steps: size the pools
+                self._sizing_steps += 1
                 if self._max_src is None:
                     self._max_src, self._max_edges = [0] * L, [0] * L
                 for l, b in enumerate(mfgs):
@@ -650,6 +653,36 @@ class Trainer:
                 self._side_apply = torch.cuda.Stream()
         self.graph_kernels = _native.STATS.launches - before    # hand-written kernels inside one replay
         _native.STATS.launches = before
+
+    # ---- checkpoint / resume (the reference checkpoints the model only; the bandit state is part of training) ----
+    def state_dict(self):
+        """Everything a resumed run needs to continue the same trajectory: parameters, Adam moments and step,
+        lr schedule, the sampler's EXP3 weights / L1 norms / Philox step, and the step counters."""
+        self.flush()
+        smp = self.dm.sampler
+        return {"model": {k: v.detach().clone() for k, v in self.model.state_dict().items()},
+                "optimizer": self.optimizer.state_dict(), "scheduler": self.scheduler.state_dict(),
+                "sampler": smp.state_dict() if getattr(smp, "_w_csc", None) is not None else {"step": smp.step},
+                "num_steps": self.num_steps, "cum_nodes": list(self.cum_sampled_nodes),
+                "cum_edges": list(self.cum_sampled_edges), "epoch": self.dm._epoch}
+
+    def load_state_dict(self, sd):
+        """In place: parameters, moments and bandit weights keep their addresses, so a captured step graph
+        stays valid; the device-side Philox step follows at the next step."""
+        self.flush()
+        smp = self.dm.sampler
+        self.model.load_state_dict(sd["model"])
+        self.optimizer.load_state_dict(sd["optimizer"])
+        self.scheduler.load_state_dict(sd["scheduler"])
+        if "exp3_w_csc" in sd["sampler"]:
+            smp.load_state_dict(sd["sampler"], self.dm.g)
+        else:
+            smp.step = int(sd["sampler"]["step"])
+        self.num_steps = int(sd["num_steps"])
+        self.cum_sampled_nodes, self.cum_sampled_edges = list(sd["cum_nodes"]), list(sd["cum_edges"])
+        self.dm._epoch = int(sd["epoch"])
+        self._grads_clean = False
+        self._dev_step_mirror = None
 
     @torch.no_grad()
     def validate(self) -> float:

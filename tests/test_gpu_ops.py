@@ -405,3 +405,37 @@ def test_linear_splitk_matches_plain(native_lib, rows, in_f, pad):
         _close(lin.weight.grad - (0.5 if preset else 0.0), gw_ref, rtol=3e-5, what=f"weight grad (preset={preset})")
         _close(lin.bias.grad, gb_ref, rtol=2e-5, what="bias grad")
         _close(xin.grad[:, :in_f], gy @ lin.weight.detach(), rtol=2e-5, what="input grad")
+
+
+def test_trainer_checkpoint_resume_continues_the_trajectory(native_lib):
+    """``Trainer.state_dict`` / ``load_state_dict`` (model, flat Adam, lr schedule, EXP3 weights + L1 norms, Philox
+    step): restoring into the SAME trainer (its step graph already captured: everything is restored in place)
+    and into a FRESH one reproduces the losses of the original run."""
+    from bliss_gnn_b200.graph import synthetic_graph
+    from bliss_gnn_b200.train import DataModule, Trainer, build_model
+    dev = _dev()
+    g = synthetic_graph("flickr", seed=0, scale=0.05).to(dev)
+
+    def make():
+        dm = DataModule("flickr", fan_out=[128, 64, 32], eta=0.1, device=dev, batch_size=32, sampler="poisson-bandit",
+                        model="sage", seed=0, graph=g)
+        torch.manual_seed(3)
+        model = build_model("sage", dm.in_feats, 64, dm.n_classes, 3, dropout=0.0).to(dev)
+        return dm, Trainer(dm, model, 0.002, static_graph=True, eager_warmup=3)
+
+    dm, tr = make()
+    batches = [b for _, b in zip(range(14), dm.train_batches())]
+    for b in batches[:8]:
+        tr.training_step(b)
+    assert tr.graph_replays >= 3
+    sd = tr.state_dict()
+    ref = [float(tr.training_step(b).item()) for b in batches[8:]]
+    tr.load_state_dict(sd)                                   # back in time, graph stays captured
+    again = [float(tr.training_step(b).item()) for b in batches[8:]]
+    for a, b in zip(ref, again):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (ref, again)
+    _, tr2 = make()
+    tr2.load_state_dict(sd)                                  # fresh process: eager sizing steps first
+    fresh = [float(tr2.training_step(b).item()) for b in batches[8:]]
+    for a, b in zip(ref, fresh):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(a)), (ref, fresh)
