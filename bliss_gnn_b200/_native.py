@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out.decode(), file=sys.stderr)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out.decode()}")
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs, "-lcudart"]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if out.returncode != 0:
         raise RuntimeError(f"link failed:\n{out.stdout.decode()}")
