@@ -101,8 +101,9 @@ def _visible_index(local_rank):
 # CPU path (oracle port of the reference) — used for cpu_baseline and --impl reference
 # ---------------------------------------------------------------------------------------------
 def cpu_reference_steps(g_cpu, seed_batches, n_warm, n_steps, budget_s, threads):
-    """Times the oracle's full training step (sample + gather + SAGE fwd/bwd + Adam + exp3) on the
-    host cores.  Returns (steps timed, seconds, sampled edges per step)."""
+    """Times the oracle's full training step (sample + gather + SAGE fwd/bwd + Adam + exp3) on the host cores,
+    step by step (``time.perf_counter`` around each step; BASELINE.md §2: 3 warm-up steps, >= 20 timed steps,
+    median and p10/p90).  ``budget_s`` bounds the timed part.  Returns a dict."""
     import torch.nn.functional as F
     from oracle import model as omodel
     from oracle import samplers as osamp
@@ -134,17 +135,21 @@ def cpu_reference_steps(g_cpu, seed_batches, n_warm, n_steps, budget_s, threads)
         state["step"] += 1
         return sum(b.num_edges() for b in blocks)
 
-    t_first = time.perf_counter()
     for i in range(n_warm):
         one(seed_batches[i % len(seed_batches)])
-    t_warm = (time.perf_counter() - t_first) / max(n_warm, 1)
-    k = n_steps if t_warm <= 0 else max(1, min(n_steps, int(budget_s / max(t_warm, 1e-3))))
-    edges = 0
-    t0 = time.perf_counter()
-    for i in range(k):
+    times, edges = [], 0
+    t_begin = time.perf_counter()
+    for i in range(n_steps):
+        t0 = time.perf_counter()
         edges += one(seed_batches[(n_warm + i) % len(seed_batches)])
-    dt = time.perf_counter() - t0
-    return k, dt, edges / k
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    times.sort()
+    k = len(times)
+    pick = lambda q: times[min(k - 1, int(q * k))]
+    return {"steps": k, "warmup": n_warm, "seconds": sum(times), "median_s": statistics.median(times),
+            "p10_s": pick(0.10), "p90_s": pick(0.90), "edges_per_step": edges / k}
 
 
 def build_graph(shape, scale, device):
@@ -198,16 +203,20 @@ def main():
             return 0
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         g = build_graph(args.shape, args.scale, dev).to("cpu")
-        batches = seed_batches_for(g, 0, 1, max(args.steps + args.warmup, 4))
-        k, dt, edges = cpu_reference_steps(g, batches, min(args.warmup, 1) or 1, args.steps, 150.0, threads)
-        v = k / dt
-        sample = f"{k} full training steps (batch {BATCH}) of the oracle port on {threads} threads, bounded to ~150 s"
+        n_warm = max(1, min(args.warmup, 3))
+        batches = seed_batches_for(g, 0, 1, args.steps + n_warm)
+        r = cpu_reference_steps(g, batches, n_warm, args.steps, 150.0, threads)
+        v = 1.0 / r["median_s"]
+        sample = (f"{r['steps']} full training steps (batch {BATCH}) of the oracle port on {threads} threads after "
+                  f"{n_warm} warm-up steps, timed step by step, bounded to ~150 s; value = 1 / median step time")
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": k,
-            "warmup": min(args.warmup, 1) or 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
+            "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": r["steps"],
+            "warmup": n_warm, "ms_per_step": 1e3 * r["median_s"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "sampled_edges_per_s": edges * v,
-            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "sampled_edges_per_s": r["edges_per_step"] * v,
+            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample,
+                             "ms_per_step_median": 1e3 * r["median_s"], "ms_per_step_p10": 1e3 * r["p10_s"],
+                             "ms_per_step_p90": 1e3 * r["p90_s"]},
             "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -223,7 +232,11 @@ def main():
     torch.cuda.set_device(device)
     pg = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL's init lines (rank / nranks / transport of every communicator) go to stderr, stdout stays the one
+        # JSON line: the driver can read the rank count off the run's own log
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=device)
         pg = torch.distributed.group.WORLD
     torch.set_float32_matmul_precision("medium")      # the reference's --precision default (train_lightning.py:550)
@@ -234,7 +247,9 @@ def main():
     torch.manual_seed(3)
     model = build_model("sage", dm.in_feats, HIDDEN, dm.n_classes, 3, DROPOUT).to(device)
     tr = Trainer(dm, model, LR, pg, static_graph=not args.eager, eager_warmup=8)   # 8 ordinary steps size the pools
-    n_need = args.warmup + 3 * args.steps + 24
+    REPEATS = 5                    # timed regions of exactly `steps` steps each; the median region is reported
+    n_prof = min(args.steps, 50)
+    n_need = max(args.warmup, 3) + tr.eager_warmup + 2 + 2 * REPEATS * args.steps + n_prof + 8
     host_batches = [b.pin_memory() for b in seed_batches_for(g, rank, world, n_need)]
     dev_batches = [b.to(device) for b in host_batches]
     it = iter(range(n_need))
@@ -244,10 +259,16 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=device)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(max(args.warmup, 3) + (0 if args.eager else tr.eager_warmup + 2)):   # + pool sizing and graph capture
         tr.training_step(dev_batches[next(it)])
 
-    # ---- (1) device-resident throughput: EXACTLY `steps` steps between two events ----
+    # ---- (1) device-resident throughput: EXACTLY `steps` steps between two events, REPEATS times ----
     clocks = ClockSampler(_visible_index(local))
     N.STATS.reset(timing=False)
     replays0 = tr.graph_replays
@@ -255,139 +276,219 @@ def main():
     resizes0 = tr.pool_resizes
     barrier()
     clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    edges0 = tr.total_sampled_edges
-    e0.record()
-    for _ in range(args.steps):
-        tr.training_step(dev_batches[next(it)])
-    tr.flush()               # the last step's counters (sizes, capacity flags) are consumed inside the timed region
-    e1.record()
-    barrier()
-    edges = tr.total_sampled_edges - edges0
+    region_ms, edges = [], 0
+    for _ in range(REPEATS):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        edges0 = tr.total_sampled_edges
+        e0.record()
+        for _ in range(args.steps):
+            tr.training_step(dev_batches[next(it)])
+        tr.flush()           # the last step's counters (sizes, capacity flags) are consumed inside the timed region
+        e1.record()
+        barrier()
+        region_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+        edges += tr.total_sampled_edges - edges0
     clock_info = clocks.stop()
     # kernels launched eagerly + the hand-written kernels inside every CUDA-graph replay
-    launches = N.STATS.launches + (tr.graph_replays - replays0) * tr.graph_kernels
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-    if world > 1:
-        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    launches = (N.STATS.launches + (tr.graph_replays - replays0) * tr.graph_kernels) // REPEATS
+    ms_total = statistics.median(region_ms)
     value = world * args.steps / (ms_total / 1e3)
 
     # ---- (2) end to end: seeds from pinned host memory every step, loss read back every step ----
     # The loss of every step is copied to pinned host memory stream-ordered and consumed one step later
     # (like the step's counters), so the host never stalls the device inside the loop.
-    barrier()
     loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event() for _ in range(2)]
-    losses = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        loss = tr.training_step(host_batches[next(it)])
-        loss_host[i & 1].copy_(loss.reshape(1), non_blocking=True)
-        loss_ev[i & 1].record()
-        if i:
-            loss_ev[(i - 1) & 1].synchronize()
-            losses.append(float(loss_host[(i - 1) & 1]))
-    loss_ev[(args.steps - 1) & 1].synchronize()
-    losses.append(float(loss_host[(args.steps - 1) & 1]))
-    tr.flush()
-    e1.record()
-    barrier()
-    assert len(losses) == args.steps and all(l == l for l in losses), "e2e: a loss did not come back"
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=device)
-    if world > 1:
-        torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = world * args.steps / (float(ms2.item()) / 1e3)
+    e2e_ms = []
+    for _ in range(REPEATS):
+        barrier()
+        losses = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            loss = tr.training_step(host_batches[next(it)])
+            loss_host[i & 1].copy_(loss.reshape(1), non_blocking=True)
+            loss_ev[i & 1].record()
+            if i:
+                loss_ev[(i - 1) & 1].synchronize()
+                losses.append(float(loss_host[(i - 1) & 1]))
+        loss_ev[(args.steps - 1) & 1].synchronize()
+        losses.append(float(loss_host[(args.steps - 1) & 1]))
+        tr.flush()
+        e1.record()
+        barrier()
+        assert len(losses) == args.steps and all(l == l for l in losses), "e2e: a loss did not come back"
+        e2e_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+    e2e_value = world * args.steps / (statistics.median(e2e_ms) / 1e3)
 
-    # ---- (3) per-entry-point CUDA-event timing over the same kind of steps (roofline) ----
-    n_prof = min(args.steps, 50)
+    # ---- (3) per-KERNEL CUDA-event timing (csrc/profile.cu) over the same kind of steps: roofline ----
+    # The steps run eagerly (every kernel its own launch, bracketed by an event pair on its launch stream), so the
+    # times are the kernels' own durations; inside the replayed graph they overlap each other.
     tr.flush()
-    dm.sampler.force_stage_path = True     # one FFI call per kernel, so each is bracketed by its own events
-    N.STATS.reset(timing=True)
+    dm.sampler.force_stage_path = True
+    N.STATS.reset(timing=False)
+    N.profile_enable(True)
     sizes = []
     for _ in range(n_prof):
         tr.training_step(dev_batches[next(it)])
         sizes.append([(c.n_seeds, c.e_in, c.n_cand, c.n_src, c.n_edges) for c in dm.sampler.last_counters])
     torch.cuda.synchronize()
-    per_fn = N.STATS.elapsed_ms()
-    N.STATS.reset(timing=False)
+    per_kernel = N.profile_read()
+    N.profile_enable(False)
     dm.sampler.force_stage_path = False
     peak, peak_src = _peaks()
     try:
-        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
     except Exception:
         traffic_tab = {}
-
-    layer_dims = [HIDDEN, HIDDEN, dm.n_classes]          # width the aggregation runs at in each layer (SAGE, lin_before_mp)
-
-    def alg_bytes(name):
-        """Algorithmic (compulsory) bytes of one entry point over the profiled steps: every distinct
-        input read once, every output written once."""
-        total = 0.0
-        for step_sizes in sizes:
-            for l, (n_s, e_in, n_c, n_src, e_b) in enumerate(step_sizes):
-                if name == "bliss_frontier_prob":    # (index, weight) per in-edge + chunk records/partials + |V| accumulator scan + candidates
-                    total += 8.0 * e_in + 64.0 * (e_in / 256.0 + n_s) + 8.0 * g.num_nodes() + 8.0 * n_c
-                elif name == "bliss_block_count":    # indices + chunk records + keep bits + per kept edge (info, weight, first key)
-                    total += 4.0 * e_in + 76.0 * (e_in / 256.0 + n_s) + 20.0 * e_b
-                elif name in ("bliss_block_fill", "bliss_sample_layer_back"):
-                    total += 80.0 * (e_in / 256.0 + n_s) + 16.0 * e_b + 36.0 * e_b + 36.0 * n_c
-                elif name == "bliss_spmm":           # forward + backward of the layer at its aggregation width
-                    total += 2 * (8.0 * e_b + 8.0 * (n_s + 1) + 4.0 * layer_dims[l] * (n_src + n_s))
-                else:
-                    total += 8.0 * e_in
-        return total
-
-    def roofline_of(name, note):
-        calls, t_ms = per_fn[name]
-        achieved = alg_bytes(name) / 1e9 / (t_ms / 1e3) if t_ms > 0 else 0.0
-        tr_ = traffic_tab.get(name, {}).get("dram_bytes_per_launch")
-        return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": tr_, "alg_bytes_per_launch": alg_bytes(name) / max(calls, 1),
-                "peak_source": peak_src, "launches_timed": calls, "avg_launch_us": 1e3 * t_ms / max(calls, 1),
-                "note": note}
-
-    name = max(per_fn.items(), key=lambda kv: kv[1][1])[0]
-    roofline = roofline_of(name, "entry point with the largest total CUDA-event time over the profiled steps. The SpMM "
-                                 "gathers source rows that are L2-resident (<= 8 K rows x 1 KB), so its DRAM traffic is "
-                                 "about its compulsory bytes and the HBM fraction is low by construction: the kernel is "
-                                 "bound by L2->SM gather bandwidth, reported as l2_gather (DESIGN.md section 3)")
-    roofline["per_entry_point_ms_per_step"] = {k: v[1] / n_prof for k, v in sorted(per_fn.items())}
-    if "bliss_spmm" in per_fn:      # the bound that actually applies: bytes gathered through L2 per second
-        gathered = sum(2 * 4.0 * layer_dims[l] * e_b for st in sizes for l, (_, _, _, _, e_b) in enumerate(st))
-        t_ms = per_fn["bliss_spmm"][1]
-        roofline["l2_gather"] = {"achieved_gbs": gathered / 1e9 / (t_ms / 1e3),
-                                 "peak_gbs": 12000.0, "peak_source": "chip-level L2->SM throughput ~6300 B/clk "
-                                 "(/opt/skills/guides/B300_MICROARCH.md, TMA/LDG chip-throughput) x 1.9 GHz",
-                                 "bytes_per_step": gathered / n_prof}
-    roofline_sampling = roofline_of("bliss_frontier_prob", "the HBM-streaming sampling passes the north-star names "
-                                    "(three chunk passes + candidate scan); the scatter pass is bound by L2 atomic "
-                                    "throughput (one 64-bit RED per in-edge), not by HBM") if "bliss_frontier_prob" in per_fn else None
+    rl = roofline_tables(per_kernel, sizes, n_prof, dm.in_feats, [HIDDEN, HIDDEN, dm.n_classes], peak, peak_src,
+                         traffic_tab)
+    rl["roofline"]["l2_gather"] = l2_gather_probe(N, device, per_kernel, sizes, [HIDDEN, HIDDEN, dm.n_classes])
 
     out = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-           "sampled_edges_per_s": world * edges / (ms_total / 1e3), "clocks": clock_info,
+           "repeats": REPEATS, "ms_per_step_all_regions": [m / args.steps for m in region_ms],
+           "sampled_edges_per_s": world * edges / (sum(region_ms) / 1e3), "clocks": clock_info,
            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": BATCH * 4 * world,
                    "d2h_bytes_per_step": (4 + dm.sampler._wsp.ctr_all.numel()) * world,
+                   "ms_per_step_all_regions": [m / args.steps for m in e2e_ms],
                    "note": "seeds H2D from pinned memory every step; loss + per-layer counters D2H every step, "
                            "copied stream-ordered and consumed one step later"},
            "gpu_launches": launches, "graph_replays": tr.graph_replays,
-           "pool_resizes_in_timed_regions": tr.pool_resizes - resizes0, "roofline": roofline,
-           "roofline_sampling": roofline_sampling}
+           "pool_resizes_in_timed_regions": tr.pool_resizes - resizes0}
+    out.update(rl)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         g_cpu = g.to("cpu")
-        k, dt, e_cpu = cpu_reference_steps(g_cpu, [b.clone() for b in host_batches[:8]], 1, 4, args.cpu_budget_s,
-                                           threads)
-        out["cpu_baseline"] = {"value": k / dt, "unit": "steps/s", "cores": threads, "kind": "port",
-                               "sample": f"{k} full training steps of the same workload (oracle port, batch {BATCH})"}
+        r = cpu_reference_steps(g_cpu, [b.clone() for b in host_batches[:23]], 3, 20, args.cpu_budget_s, threads)
+        out["cpu_baseline"] = {"value": 1.0 / r["median_s"], "unit": "steps/s", "cores": threads, "kind": "port",
+                               "ms_per_step_median": 1e3 * r["median_s"], "ms_per_step_p10": 1e3 * r["p10_s"],
+                               "ms_per_step_p90": 1e3 * r["p90_s"],
+                               "sample": f"{r['steps']} full training steps of the same workload after 3 warm-up steps "
+                                         f"(oracle port, batch {BATCH}, {threads} threads), timed step by step; "
+                                         "value = 1 / median step time"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# roofline: SURVEY.md section 8(d)'s algorithmic (compulsory) bytes, verbatim
+# ---------------------------------------------------------------------------------------------
+#: kernel -> stage of the path (SURVEY.md section 8d names the stages)
+STAGE_OF = {"k_plan_rows": "sampling", "k_plan_scan": "sampling", "k_plan_chunks": "sampling", "k_prob_pass1": "sampling",
+            "k_prob_pass2": "sampling", "k_prob_pass3": "sampling", "k_collect_candidates": "sampling",
+            "k_scale_search": "sampling", "k_poisson_scale": "sampling", "k_select_poisson": "sampling",
+            "k_layer_front": "sampling",
+            "k_block_count<true>": "block_build", "k_block_count<false>": "block_build", "k_block_index": "block_build",
+            "k_block_fill": "block_build", "k_block_finish": "block_build",
+            "k_spmm_seg": "spmm", "k_spmm_combine": "spmm", "k_spmm": "spmm", "k_spmm_tma": "spmm",
+            "k_gather_rows": "gather", "k_reward_update": "bandit"}
+
+
+def stage_bytes(stage, sizes, in_feats, layer_dims):
+    """Algorithmic bytes of one stage over the profiled steps — SURVEY.md section 8(d), each distinct input read
+    once and each output written once, s = 4 (fp32):
+      sampling, per layer   B_samp  = 8 (n_s+1) + E_in (4 idx + 4 weight) + 4 N_c + n_src (4 nid + 4 P)
+      block build           B_blk   = E_b (4 src + 4 eid + 4 W~ + 4 q) + 4 (n_s+1)
+      SpMM, per layer       B_spmm  = E_b (4 idx + 4 W~) + 4 (n_s+1) + 4 D (n_src + n_s), forward and again backward
+      gather                B_g     = 2 * 4 F n_src0 + 4 n_src0
+      bandit                B_bandit= sum_l E_b (4 eid + 4 alpha + 4 q + 8 weight RMW) + 8 n_src + 4 n_s   (lazy norm)"""
+    total = 0.0
+    for step_sizes in sizes:
+        for l, (n_s, e_in, n_c, n_src, e_b) in enumerate(step_sizes):
+            if stage == "sampling":
+                total += 8.0 * (n_s + 1) + 8.0 * e_in + 4.0 * n_c + 8.0 * n_src
+            elif stage == "block_build":
+                total += 16.0 * e_b + 4.0 * (n_s + 1)
+            elif stage == "spmm":
+                total += 2 * (8.0 * e_b + 4.0 * (n_s + 1) + 4.0 * layer_dims[l] * (n_src + n_s))
+            elif stage == "gather" and l == 0:
+                total += 2 * 4.0 * in_feats * n_src + 4.0 * n_src
+            elif stage == "bandit":
+                total += 20.0 * e_b + 8.0 * n_src + 4.0 * n_s
+    return total
+
+
+def roofline_tables(per_kernel, sizes, n_prof, in_feats, layer_dims, peak, peak_src, traffic_tab):
+    """`roofline` = the dominant kernel (largest total CUDA-event time); `roofline_kernels` = every timed kernel;
+    `roofline_stages` = the stages of SURVEY section 8(d) with the stage's algorithmic bytes over the summed time of
+    its kernels.  A kernel that does its stage's whole work (SpMM, gather, reward update, a fused sampling kernel)
+    carries the stage's bytes; kernels that share a stage (the three probability passes re-read the same weights)
+    only have a stage-level fraction — dividing one compulsory read among them would be arbitrary."""
+    whole_stage = {"k_spmm_seg": "spmm", "k_spmm_tma": "spmm", "k_spmm": "spmm", "k_gather_rows": "gather",
+                   "k_reward_update": "bandit", "k_layer_front": "sampling"}
+    stages, kernels = {}, []
+    for name, (calls, ms) in sorted(per_kernel.items(), key=lambda kv: -kv[1][1]):
+        st = STAGE_OF.get(name, "other")
+        stages.setdefault(st, {"ms": 0.0, "kernels": []})
+        stages[st]["ms"] += ms
+        stages[st]["kernels"].append(name)
+        row = {"kernel": name, "stage": st, "launches_timed": calls, "avg_launch_us": 1e3 * ms / max(calls, 1),
+               "ms_per_step": ms / n_prof}
+        if name in whole_stage and ms > 0:
+            bts = stage_bytes(whole_stage[name], sizes, in_feats, layer_dims)
+            row.update({"alg_bytes_per_launch": bts / max(calls, 1), "achieved": bts / 1e9 / (ms / 1e3),
+                        "frac": bts / 1e9 / (ms / 1e3) / peak})
+        t = traffic_tab.get(name, {}).get("dram_bytes_per_launch")
+        if t is not None:
+            row["traffic"] = t
+        kernels.append(row)
+    stage_rows = {}
+    for st, d in stages.items():
+        if st == "other" or d["ms"] <= 0:
+            continue
+        bts = stage_bytes(st, sizes, in_feats, layer_dims)
+        stage_rows[st] = {"alg_bytes_per_step": bts / n_prof, "ms_per_step": d["ms"] / n_prof,
+                          "achieved": bts / 1e9 / (d["ms"] / 1e3), "frac": bts / 1e9 / (d["ms"] / 1e3) / peak,
+                          "kernels": d["kernels"]}
+    top = next((k for k in kernels if "achieved" in k), kernels[0] if kernels else {})
+    dominant = kernels[0] if kernels else {}
+    if "achieved" not in dominant and dominant:       # the dominant kernel shares its stage: report the stage's fraction
+        st = stage_rows.get(dominant["stage"], {})
+        dominant = dict(dominant, achieved=st.get("achieved", 0.0), frac=st.get("frac", 0.0),
+                        alg_bytes_per_launch=None, note_bytes="stage-level bytes / stage-level time (kernels share inputs)")
+    roofline = {"bound": "hbm", "kernel": dominant.get("kernel"), "achieved": dominant.get("achieved", 0.0), "peak": peak,
+                "unit": "GB/s", "frac": dominant.get("frac", 0.0), "traffic": dominant.get("traffic"),
+                "alg_bytes_per_launch": dominant.get("alg_bytes_per_launch"), "peak_source": peak_src,
+                "launches_timed": dominant.get("launches_timed"), "avg_launch_us": dominant.get("avg_launch_us"),
+                "note": "dominant kernel by total CUDA-event time over the profiled (eager) steps; algorithmic bytes per "
+                        "SURVEY.md section 8(d).  The sampled blocks' source rows (<= 8 K x 1 KB) are L2-resident, so the "
+                        "SpMM's DRAM traffic is about its compulsory bytes and its HBM fraction is low by construction; "
+                        "l2_gather gives the bound that applies, measured in this run."}
+    return {"roofline": roofline, "roofline_kernels": kernels, "roofline_stages": stage_rows,
+            "roofline_top_whole_stage_kernel": top.get("kernel")}
+
+
+def l2_gather_probe(N, device, per_kernel, sizes, layer_dims):
+    """MEASURES the chip's L2 -> SM gather bandwidth (warp-per-row gathers of 1 KB rows from an 8 MB, L2-resident
+    table, every SM busy) and puts the SpMM's gathered bytes per second beside it."""
+    rows, dim, per_warp = 8192, 256, 512
+    table = torch.randn(rows, dim, device=device)
+    best = None
+    for n_warps in (148 * 8 * 4, 148 * 8 * 8):
+        outp = torch.empty(n_warps, dim, device=device)
+        for _ in range(2):
+            N.call("bliss_l2_gather_probe", N.ptr(table), rows, dim, per_warp, N.ptr(outp), n_warps, N.stream())
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            N.call("bliss_l2_gather_probe", N.ptr(table), rows, dim, per_warp, N.ptr(outp), n_warps, N.stream())
+            e1.record()
+            e1.synchronize()
+            gbs = n_warps * per_warp * dim * 4 / 1e9 / (e0.elapsed_time(e1) / 1e3)
+            best = gbs if best is None else max(best, gbs)
+    res = {"peak_gbs": best, "peak_source": "measured in this run: bliss_l2_gather_probe (csrc/aggregate.cu), best of 10"}
+    t = sum(per_kernel.get(k, (0, 0.0))[1] for k in ("k_spmm_seg", "k_spmm_tma"))
+    if t > 0:
+        gathered = sum(2 * 4.0 * layer_dims[l] * e_b for st in sizes for l, (_, _, _, _, e_b) in enumerate(st))
+        res.update({"achieved_gbs": gathered / 1e9 / (t / 1e3), "bytes_per_step": gathered / len(sizes),
+                    "frac": gathered / 1e9 / (t / 1e3) / best})
+    return res
 
 
 if __name__ == "__main__":

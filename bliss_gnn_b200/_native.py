@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libbliss_b200.so")
-SOURCES = ["sampler.cu", "aggregate.cu", "bandit.cu", "gat.cu", "optim.cu", "epilogue.cu"]
+SOURCES = ["sampler.cu", "aggregate.cu", "bandit.cu", "gat.cu", "optim.cu", "epilogue.cu", "profile.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -136,6 +136,9 @@ PROTOTYPES = {
     "bliss_xent_mean": [_P, _P, _I32, _I32, _P, _P, _P, _P],
     "bliss_sage_epilogue_fwd": [_P, _P, _P, _I32, _I32, _I32, _F, _U64, _P, _U32, _P, _P, _P],
     "bliss_sage_epilogue_bwd": [_P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P],
+    "bliss_profile_enable": [_I32],
+    "bliss_profile_read": [C.c_char_p, _I32, _P, _P, _I32],
+    "bliss_l2_gather_probe": [_P, _I32, _I32, _I32, _P, _I32, _P],
 }
 
 _lib = None
@@ -187,6 +190,24 @@ class _Stats:
 
 
 STATS = _Stats()
+
+
+def profile_enable(on: bool):
+    """Per-kernel CUDA-event timing inside the library (csrc/profile.cu); clears earlier records."""
+    lib().bliss_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{kernel name: (launches, total ms)} of everything recorded since :func:`profile_enable` (synchronises)."""
+    cap = 256
+    names = C.create_string_buffer(1 << 14)
+    ms = (C.c_float * cap)()
+    calls = (C.c_int32 * cap)()
+    n = lib().bliss_profile_read(names, len(names), C.cast(ms, C.c_void_p), C.cast(calls, C.c_void_p), cap)
+    if n < 0:
+        raise BlissNativeError(f"bliss_profile_read failed: {n}")
+    keys = names.value.decode().split("\n") if n else []
+    return {k: (int(calls[i]), float(ms[i])) for i, k in enumerate(keys)}
 
 
 def call(name: str, *args):

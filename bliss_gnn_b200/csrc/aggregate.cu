@@ -6,6 +6,7 @@
 // row segment), 128-bit loads along the feature dimension, edge metadata loaded coalesced and
 // broadcast by shuffle.
 #include "common.cuh"
+#include "profile.cuh"
 
 namespace bliss {
 
@@ -300,6 +301,37 @@ __global__ void __launch_bounds__(256) k_spmm_combine(const int32_t* __restrict_
   }
 }
 
+// L2 -> SM gather probe (bench.py): what a warp-per-row gather of 1 KB rows can pull out of L2 on this chip.
+__global__ void __launch_bounds__(256) k_l2_gather_probe(const float* __restrict__ table, int n_rows, int dim,
+                                                        int rows_per_warp, float* __restrict__ out, int n_warps) {
+  const int lane = lane_id();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= n_warps) return;
+  unsigned state = 0x9E3779B9u * (unsigned)(warp + 1);
+  for (int c0 = 0; c0 < dim; c0 += 256) {     // 2 x float4 per lane per row and 256-column slice
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    for (int r0 = 0; r0 < rows_per_warp; r0 += 4) {
+      float4 v[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        state = state * 1664525u + 1013904223u;
+        const int row = (int)((state >> 8) % (unsigned)n_rows);
+        const float4* __restrict__ p = reinterpret_cast<const float4*>(table + (int64_t)row * dim + c0);
+        v[u][0] = __ldg(p + lane);
+        v[u][1] = (c0 + 128 < dim) ? __ldg(p + 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a0.x += v[u][0].x; a0.y += v[u][0].y; a0.z += v[u][0].z; a0.w += v[u][0].w;
+        a1.x += v[u][1].x; a1.y += v[u][1].y; a1.z += v[u][1].z; a1.w += v[u][1].w;
+      }
+    }
+    float4* __restrict__ o = reinterpret_cast<float4*>(out + (int64_t)warp * dim + c0);
+    o[lane] = a0;
+    if (c0 + 128 < dim) o[32 + lane] = a1;
+  }
+}
+
 }  // namespace bliss
 
 using namespace bliss;
@@ -327,11 +359,16 @@ static int launch_spmm(const int32_t* indptr, const int32_t* col, const int32_t*
 #define BLISS_SPMM_CASE(N)                                                                                    \
   case N:                                                                                                     \
     if (seg_ptr) {                                                                                            \
-      k_spmm_seg<VEC, N><<<grid, 256, smem, st>>>(indptr, seg_ptr, col, perm, w, sscale, dscale, agg, x,     \
-                                                  n_rows, dim, partial, item_cap, y);                        \
+      {                                                                                                       \
+        BLISS_KSCOPE("k_spmm_seg", st);                                                                       \
+        k_spmm_seg<VEC, N><<<grid, 256, smem, st>>>(indptr, seg_ptr, col, perm, w, sscale, dscale, agg, x,   \
+                                                    n_rows, dim, partial, item_cap, y);                      \
+      }                                                                                                       \
+      BLISS_KSCOPE("k_spmm_combine", st);                                                                     \
       k_spmm_combine<VEC, N><<<grid_c, 256, 0, st>>>(indptr, seg_ptr, dscale, agg, n_rows, dim, partial,     \
                                                      item_cap, y);                                            \
     } else {                                                                                                  \
+      BLISS_KSCOPE("k_spmm", st);                                                                             \
       k_spmm<VEC, N><<<grid, 256, 0, st>>>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, y);    \
     }                                                                                                         \
     break;
@@ -355,6 +392,7 @@ int bliss_gather_rows(const float* table, const int32_t* nid, int64_t n_rows, in
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = blocks_for_rows(n_rows, BLISS_SM_COUNT * 16);
   const bool al16 = ((uintptr_t)table % 16 == 0) && (!out || (uintptr_t)out % 16 == 0);
+  BLISS_KSCOPE("k_gather_rows", st);
   if (dim % 4 == 0 && al16)
     k_gather_rows<4><<<blocks, 256, 0, st>>>(table, nid, n_rows, dim, out, row_norm);
   else if (dim % 2 == 0)
@@ -362,6 +400,15 @@ int bliss_gather_rows(const float* table, const int32_t* nid, int64_t n_rows, in
   else
     k_gather_rows<1><<<blocks, 256, 0, st>>>(table, nid, n_rows, dim, out, row_norm);
   BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_l2_gather_probe(const float* table, int32_t n_rows, int32_t dim, int32_t rows_per_warp, float* out,
+                          int32_t n_warps, void* stream) {
+  if (!table || !out || n_rows <= 0 || dim <= 0 || dim % 128 || rows_per_warp <= 0 || n_warps <= 0) return -1;
+  if (((uintptr_t)table | (uintptr_t)out) % 16) return -1;
+  BLISS_LAUNCH(k_l2_gather_probe, (n_warps + 7) / 8, 256, 0, (cudaStream_t)stream, table, n_rows, dim, rows_per_warp, out,
+               n_warps);
   return 0;
 }
 

@@ -5,6 +5,7 @@
 // operand once and read-modify-writes the CSC-ordered weight in place.
 #include <float.h>
 #include "common.cuh"
+#include "profile.cuh"
 
 namespace bliss {
 
@@ -270,6 +271,7 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
   p.rewards = rewards;
   p.x_out = x_out;
   p.l1_delta = l1_delta;
+  BLISS_KSCOPE("k_reward_update", stream);
   k_reward_update<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(p);
   BLISS_CHECK_LAUNCH();
   return 0;
@@ -291,6 +293,7 @@ int bliss_apply_updates_packed(const void* recv, int64_t rank_stride_bytes, int3
   if (!recv || !exp3_w_csc || world <= 0 || cap < 0 || rank_stride_bytes <= 0) return -1;
   if ((count_off & 7) || (pos_off & 3) || (x_off & 3)) return -1;
   if (cap == 0) return 0;
+  BLISS_KSCOPE("k_apply_updates_packed", stream);
   k_apply_updates_packed<<<grid_for((int64_t)world * cap, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(
       (const unsigned char*)recv, rank_stride_bytes, world, count_off, pos_off, x_off, cap, exp3_w_csc, l1_delta);
   BLISS_CHECK_LAUNCH();

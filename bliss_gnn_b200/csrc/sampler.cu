@@ -11,6 +11,7 @@
 // the host inside a layer (or a step: the whole training step replays as one CUDA graph).
 #include <cooperative_groups.h>
 #include "common.cuh"
+#include "profile.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -1174,10 +1175,11 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
-#define BLISS_LAUNCH_PDL(...)                       \
-  do {                                              \
-    cudaError_t e__ = launch_pdl(__VA_ARGS__);      \
-    if (e__ != cudaSuccess) return (int)e__;        \
+#define BLISS_LAUNCH_PDL(kernel, grid, block, smem, st, ...)                         \
+  do {                                                                               \
+    BLISS_KSCOPE(#kernel, st);                                                       \
+    cudaError_t e__ = launch_pdl(kernel, grid, block, smem, st, __VA_ARGS__);        \
+    if (e__ != cudaSuccess) return (int)e__;                                         \
   } while (0)
 
 static inline GraphView view_of(const bliss_graph* g) {
@@ -1211,7 +1213,6 @@ int bliss_version(void) { return BLISS_B200_VERSION; }
 int bliss_workspace_init(const bliss_workspace* ws, int64_t num_nodes, void* stream) {
   if (!ws || num_nodes <= 0) return -1;
   k_ws_init<<<grid_for(num_nodes, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(*ws, num_nodes);
-  BLISS_CHECK_LAUNCH();
   return 0;
 }
 
@@ -1255,8 +1256,7 @@ int bliss_poisson_scale(int32_t n_seeds, int32_t fanout, double eps, int32_t poi
                         const bliss_workspace* ws, void* stream) {
   if (!ws || fanout < 0) return -1;
   const double fx_inv = 1.0 / (double)(1ull << fx_bits_for(n_seeds));
-  k_poisson_scale<<<1, 1024, 0, (cudaStream_t)stream>>>(n_seeds, fanout, eps, poisson, *ws, fx_inv);
-  BLISS_CHECK_LAUNCH();
+  BLISS_LAUNCH(k_poisson_scale, 1, 1024, 0, (cudaStream_t)stream, n_seeds, fanout, eps, poisson, *ws, fx_inv);
   return 0;
 }
 
@@ -1309,8 +1309,11 @@ int bliss_poisson_select(int32_t n_seeds, int32_t fanout, double eps, uint64_t s
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_scale_search, (int)fanout, eps, *ws);
-  if (e != cudaSuccess) return (int)e;
+  {
+    BLISS_KSCOPE("k_scale_search", stream);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_scale_search, (int)fanout, eps, *ws);
+    if (e != cudaSuccess) return (int)e;
+  }
   return bliss_select_poisson(n_seeds, seed, step, layer, u_inject, ws, stream);
 }
 
@@ -1321,12 +1324,9 @@ int bliss_select_topk(int32_t n_seeds, int32_t fanout, uint64_t seed, uint64_t s
   // the threshold triple lives in the tail of the caller's key scratch ([V + 4] floats)
   unsigned* thr = reinterpret_cast<unsigned*>(key_scratch);
   float* keys = key_scratch + 4;
-  k_topk_keys<<<BLISS_SM_COUNT * 4, 256, 0, st>>>(n_seeds, seed, step, layer, u_inject, keys, *ws);
-  BLISS_CHECK_LAUNCH();
-  k_topk_threshold<<<1, 1024, 0, st>>>(fanout, keys, thr, *ws);
-  BLISS_CHECK_LAUNCH();
-  k_topk_mark<<<1, 1024, 0, st>>>(n_seeds, keys, thr, *ws);
-  BLISS_CHECK_LAUNCH();
+  BLISS_LAUNCH(k_topk_keys, BLISS_SM_COUNT * 4, 256, 0, st, n_seeds, seed, step, layer, u_inject, keys, *ws);
+  BLISS_LAUNCH(k_topk_threshold, 1, 1024, 0, st, fanout, keys, thr, *ws);
+  BLISS_LAUNCH(k_topk_mark, 1, 1024, 0, st, n_seeds, keys, thr, *ws);
   return 0;
 }
 
@@ -1334,8 +1334,7 @@ int bliss_philox_fill(uint64_t seed, uint64_t step, uint32_t layer, const int32_
                       float* out, void* stream) {
   if (n < 0 || (n > 0 && (!nids || !out))) return -1;
   if (n == 0) return 0;
-  k_philox_fill<<<grid_for(n, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(seed, step, layer, nids, n, out);
-  BLISS_CHECK_LAUNCH();
+  BLISS_LAUNCH(k_philox_fill, grid_for(n, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream, seed, step, layer, nids, n, out);
   return 0;
 }
 
@@ -1380,8 +1379,7 @@ int bliss_block_fill(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds
   c.eta = eta;
   c.one_minus_eta = (float)(1.0 - (double)eta);
   c.mode = mode & 1;
-  k_block_fill<<<chunk_grid(n_seeds), BLISS_CTA, 0, (cudaStream_t)stream>>>(c, *ws, *out);
-  BLISS_CHECK_LAUNCH();
+  BLISS_LAUNCH(k_block_fill, chunk_grid(n_seeds), BLISS_CTA, 0, (cudaStream_t)stream, c, *ws, *out);
   return 0;
 }
 
@@ -1389,8 +1387,7 @@ int bliss_block_finish(int32_t n_seeds, int32_t mode, const bliss_workspace* ws,
                        const bliss_block_out* out, void* stream) {
   if (!ws || !out) return -1;
   (void)n_seeds;
-  k_block_finish<<<BLISS_SM_COUNT * 4, 256, 0, (cudaStream_t)stream>>>(mode & 1, *ws, *out);
-  BLISS_CHECK_LAUNCH();
+  BLISS_LAUNCH(k_block_finish, BLISS_SM_COUNT * 4, 256, 0, (cudaStream_t)stream, mode & 1, *ws, *out);
   return 0;
 }
 
@@ -1411,22 +1408,17 @@ int bliss_block_transpose(const int32_t* edge_src, const int32_t* edge_dst, int6
     if (n_edges > 0) {
       e = cudaMemsetAsync(t_bits, 0, sizeof(uint32_t) * (size_t)n_src * (size_t)t_words, st);
       if (e != cudaSuccess) return (int)e;
-      k_t_count<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, n_edges, t_cursor);
-      BLISS_CHECK_LAUNCH();
-      k_t_mark<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, edge_dst, n_edges, t_bits, t_words);
-      BLISS_CHECK_LAUNCH();
+      BLISS_LAUNCH(k_t_count, grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st, edge_src, n_edges, t_cursor);
+      BLISS_LAUNCH(k_t_mark, grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st, edge_src, edge_dst, n_edges, t_bits, t_words);
     }
   }
-  k_t_scan<<<1, 1024, 0, st>>>(t_cursor, n_src, t_indptr, t_seg_ptr);
-  BLISS_CHECK_LAUNCH();
+  BLISS_LAUNCH(k_t_scan, 1, 1024, 0, st, t_cursor, n_src, t_indptr, t_seg_ptr);
   if (n_edges == 0) return 0;
   const int n_words = (n_dst + 31) / 32;
-  k_t_rows<<<grid_for((int64_t)n_src * 32, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(t_indptr, n_src, n_words, t_bits, t_words,
+  BLISS_LAUNCH(k_t_rows, grid_for((int64_t)n_src * 32, 256, BLISS_SM_COUNT * 8), 256, 0, st, t_indptr, n_src, n_words, t_bits, t_words,
                                                                               t_pre, t_dst);
-  BLISS_CHECK_LAUNCH();
-  k_t_place<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st>>>(edge_src, edge_dst, n_edges, n_edges_dev, t_indptr,
+  BLISS_LAUNCH(k_t_place, grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, st, edge_src, edge_dst, n_edges, n_edges_dev, t_indptr,
                                                                    t_bits, t_pre, t_words, t_perm, edge_w, t_w);
-  BLISS_CHECK_LAUNCH();
   return 0;
 }
 

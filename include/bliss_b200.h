@@ -304,6 +304,21 @@ int bliss_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_
                     const float* lr_dev, float beta1, float beta2, float eps, int64_t* step_dev,
                     int32_t zero_grad, void* stream);
 
+/* ---- measurement hooks (bench.py; not on the product path) -------------------------------------
+ * Per-KERNEL CUDA-event timing: while enabled, every launch of the hot-path kernels is bracketed by an event
+ * pair on its launch stream.  bliss_profile_enable(on) clears what was recorded; bliss_profile_read waits for
+ * the recorded events and returns one entry per kernel name (names '\n'-separated, ms = total milliseconds,
+ * calls = launches); returns the number of entries, <0 if a buffer is too small.  Do not enable during
+ * stream capture. */
+int bliss_profile_enable(int32_t on);
+int bliss_profile_read(char* names, int32_t names_cap, float* ms, int32_t* calls, int32_t cap);
+/* L2 -> SM gather probe: every warp adds `rows_per_warp` pseudo-random rows (dim floats, dim % 128 == 0) of an
+ * L2-resident table into registers with `mlp` rows in flight, and stores one row of sums.  bench.py times
+ * it to MEASURE the gather bandwidth of the chip the SpMM is bounded by (its source rows are L2-resident),
+ * instead of quoting a figure from another chip's guide. */
+int bliss_l2_gather_probe(const float* table, int32_t n_rows, int32_t dim, int32_t rows_per_warp,
+                          float* out /* [n_warps, dim] */, int32_t n_warps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,212 @@
+"""Device vs CPU oracle on every configuration BASELINE.json names, at the configuration's full graph size,
+batch and fan-out (the Reddit shape lives in tests/test_gpu_fullsize.py next to its graph fixture):
+
+* Pubmed shape, GCN, poisson-bandit vs ladies          (configs[1])
+* Flickr shape, GATv2 — the GAT alpha branch of the bandit (configs[2])
+* Yelp shape, SAGE, 100 multi-label classes, BCE loss    (configs[4])
+* Cora shape, SAGE: 12-step trajectory of the whole-step CUDA graph against the oracle loop (configs[0])
+
+One full step per configuration, in the reference's order (``train_lightning.py:100-168,463-471``): sampled blocks
+(structure bit-exact, values 1e-5) → model forward (logits, embed_norm, a_ij) → loss → backward (every parameter
+gradient) → ``exp3`` (EXP3 weights) → the NEXT step's blocks drawn from the updated weights.  Floating-point
+values are held to 1e-5 against the oracle evaluated in float64 — the exact-arithmetic reference, so the error
+measured is the device's own fp32 rounding (north-star: "within 1e-5 relative in fp32").  Measured errors are
+written to gpurun_out/parity_stats.json.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import model as omodel
+from oracle import samplers as osamp
+from tests.util import (OracleLoop, SafeDraws, assert_blocks_equal, blocks_as, close, copy_params, philox_uniform_fn,
+                        record, rel_to_max)
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5      # north-star tolerance
+
+
+def _dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+SAMPLERS = {"poisson-bandit": "PoissonBanditLadiesSampler", "bandit": "BanditLadiesSampler",
+            "ladies": "LadiesSampler", "poisson-ladies": "PoissonLadiesSampler"}
+
+
+def _graph(shape):
+    """The synthetic graph of a dataset shape: generated on the GPU (seconds), mirrored to the CPU for the oracle."""
+    from bliss_gnn_b200.graph import normalized_edata, synthetic_graph
+    gd = synthetic_graph(shape, seed=0, device=_dev())
+    gd.edata["w"] = normalized_edata(gd)
+    return gd.to("cpu"), gd
+
+
+def _models(kind, in_f, hidden, n_classes, dev):
+    from bliss_gnn_b200 import model as M
+    torch.manual_seed(3)
+    if kind == "gat":
+        args = (3, in_f, hidden, n_classes, [4, 4, 1], F.elu, 0.0, 0.0, 0.2, False)     # train_lightning.py:247,581-596
+        dm, om = M.GATv2(*args).to(dev), omodel.GATv2(*args)
+    else:
+        cls_d, cls_o = (M.SAGE, omodel.SAGE) if kind == "sage" else (M.GCN, omodel.GCN)
+        dm, om = cls_d(in_f, hidden, n_classes, 3, F.relu, 0.0).to(dev), cls_o(in_f, hidden, n_classes, 3, F.relu, 0.0)
+    copy_params(om, dm, torch.float64)
+    return dm, om.double()
+
+
+def _gat_condition(ob):
+    """κ_i = Σ|a| / |Σ a| per destination: the GAT alpha (bandit_sampler.py:148-154) divides by a sum of signed
+    pre-softmax logits, so fp32 rounding of a_ij is amplified by κ_i in alpha and 2κ_i in the reward."""
+    a = ob.edata["a_ij"].double()
+    n = ob.num_dst_nodes()
+    s = torch.zeros(n, dtype=torch.float64).index_add_(0, ob.dst, a)
+    sa = torch.zeros(n, dtype=torch.float64).index_add_(0, ob.dst, a.abs())
+    return (sa / s.abs().clamp(min=1e-300))[ob.dst]
+
+
+@pytest.mark.parametrize("shape,kind,sampler,batch,fan,hidden", [
+    ("pubmed", "gcn", "poisson-bandit", 32, [512, 256, 128], 256),
+    ("pubmed", "gcn", "ladies", 32, [512, 256, 128], 256),
+    ("pubmed", "gcn", "poisson-ladies", 32, [512, 256, 128], 256),
+    ("flickr", "gat", "poisson-bandit", 256, [4096, 2048, 1024], 256),
+    ("yelp", "sage", "poisson-bandit", 256, [4096, 2048, 1024], 256),
+    ("cora", "sage", "poisson-bandit", 32, [512, 256, 128], 256),
+])
+def test_config_full_step_matches_oracle(native_lib, shape, kind, sampler, batch, fan, hidden):
+    from bliss_gnn_b200 import sampler as S
+    tag = f"{shape}-{kind}-{sampler}"
+    g, gd = _graph(shape)
+    dev, V = gd.device, g.num_nodes()
+    cls = SAMPLERS[sampler]
+    bandit, poisson = "Bandit" in cls, "Poisson" in cls
+    train = torch.nonzero(g.ndata["train_mask"], as_tuple=True)[0]
+    perm = train[torch.randperm(train.numel(), generator=torch.Generator().manual_seed(1))]
+    seed = 11
+    okw = dict(eta=0.1, model=kind) if bandit else {}
+    # Poisson samplers: float64 torch-order oracle (exact-arithmetic reference) with the tie band |u - P| <= 1e-4 P
+    # excluded by the draw generator; top-k samplers: the device's numeric contract (keys must order identically)
+    ora = getattr(osamp, cls)(fan, accum="native" if poisson else "contract",
+                              dtype=torch.float64 if poisson else torch.float32, **okw)
+    if poisson:
+        g.edata["w"] = osamp.normalized_edata(g, torch.float64)
+    dsm = getattr(S, cls)(fan, rng_seed=seed, **okw)
+    dmodel, omod = _models(kind, g.ndata["features"].shape[1], hidden, g.n_classes, dev)
+    multilabel = bool(g.multilabel)
+
+    for step in range(2):
+        seeds = perm[step * batch:(step + 1) * batch]
+        draws = SafeDraws(V, seed, step) if poisson else philox_uniform_fn(seed, step)
+        ora.uniform_fn = draws
+        o_in, _, ob = ora.sample_blocks(g, seeds)
+        dsm.step = step
+        if poisson:
+            dsm.inject_uniforms = {l: u.to(dev) for l, u in draws.per_layer.items()}
+        d_in, _, db = dsm.sample_blocks(gd, seeds)
+        assert torch.equal(d_in.cpu().long(), o_in), f"{tag}: input nodes of step {step} differ"
+        for l, (a, b) in enumerate(zip(db, ob)):
+            st = assert_blocks_equal(a, b, rtol=RTOL)
+            for k, v in st.items():
+                record(f"{tag}/step{step}/block{l}/{k}", v)
+            record(f"{tag}/step{step}/block{l}/sizes", [a.num_dst_nodes(), a.num_src_nodes(), a.num_edges()])
+        if step == 1:
+            break
+        # ---- model forward / backward on the same blocks ----
+        blocks_as(ob, torch.float64)
+        xd = gd.ndata["features"][d_in.long()]
+        xo = g.ndata["features"][o_in].double()
+        yd, yo = dmodel(db, xd), omod(ob, xo)
+        close(yd, yo, RTOL, f"{tag}/logits")
+        for l, (a, b) in enumerate(zip(db, ob)):
+            close(a.srcdata["embed_norm"], b.srcdata["embed_norm"], RTOL, f"{tag}/embed_norm{l}")
+            if kind == "gat":
+                assert torch.equal(a.edge_src.cpu().long(), b.src)          # same native edge order
+                close(a.edata["a_ij"], b.edata["a_ij"], RTOL, f"{tag}/a_ij{l}")
+        labels = g.ndata["labels"][seeds.long()]
+        if multilabel:                                                       # train_lightning.py:77-79
+            ld = F.binary_cross_entropy_with_logits(yd, labels.to(dev))
+            lo = F.binary_cross_entropy_with_logits(yo, labels.double())
+        else:
+            ld, lo = F.cross_entropy(yd, labels.to(dev)), F.cross_entropy(yo, labels)
+        close(ld.reshape(1), lo.reshape(1), RTOL, f"{tag}/loss")
+        ld.backward()
+        lo.backward()
+        dgrads = dict(dmodel.named_parameters())
+        for n, q in omod.named_parameters():
+            close(dgrads[n].grad, q.grad, RTOL, f"{tag}/grad/{n}")
+        if not bandit:
+            continue
+        # ---- bandit update from this step's forward pass (bandit_sampler.py:251-267) ----
+        for l, (a, b) in enumerate(zip(db, ob)):
+            b.srcdata["embed_norm"] = b.srcdata["embed_norm"].detach()
+            if kind == "gat":
+                b.edata["a_ij"] = b.edata["a_ij"].detach()
+            al = ora.calculate_alpha(b)
+            ora.calculate_rewards(l, b, g, al)
+            dsm.calculate_rewards(l, a, gd, dsm.calculate_alpha(a))
+            r_d, r_o = a.edata["rewards"].cpu().double(), b.edata["rewards"].double()
+            tol = RTOL * (2.0 * _gat_condition(b).clamp(min=1.0) if kind == "gat" else 1.0)
+            err = ((r_d - r_o).abs() / (tol * r_o.abs()).clamp(min=1e-300))
+            err = err[r_o.abs() > 1e-30]
+            record(f"{tag}/rewards{l}/max_err_over_tol", float(err.max()) if err.numel() else 0.0)
+            assert err.numel() == 0 or float(err.max()) <= 1.0, f"{tag}: rewards of layer {l}: {float(err.max())} x tolerance"
+        ora.exp3(ob, g)
+        dsm.exp3(db, gd)
+        w_dev, w_ora = dsm.exp3_weights.cpu().double(), ora.exp3_weights.double()
+        rel = ((w_dev - w_ora).abs() / w_ora).max().item()
+        record(f"{tag}/exp3_weights/max_rel", rel)
+        assert rel <= RTOL, f"{tag}: EXP3 weights max rel err {rel}"
+        torch.testing.assert_close(w_dev.sum(dim=1), torch.ones(len(fan), dtype=torch.float64), rtol=1e-6, atol=0)
+
+
+def _trajectory(shape, n_steps, hidden, batch, fan, eager_warmup, tag, loss_rtol=1e-4, param_rtol=1e-4):
+    """Trainer(static_graph=True) (eager sizing steps, then the whole step as one replayed CUDA graph) against
+    the oracle loop: same seed batches, same Philox stream, dropout 0, fp32 GEMMs (``--precision highest``)."""
+    from bliss_gnn_b200.train import DataModule, Trainer, build_model
+    torch.set_float32_matmul_precision("highest")
+    g, gd = _graph(shape)
+    dm = DataModule(shape, fan_out=fan, eta=0.1, device=gd.device, batch_size=batch, sampler="poisson-bandit",
+                    model="sage", seed=0, graph=gd)
+    torch.manual_seed(3)
+    model = build_model("sage", dm.in_feats, hidden, dm.n_classes, 3, dropout=0.0).to(gd.device)
+    omod = omodel.SAGE(g.ndata["features"].shape[1], hidden, g.n_classes, 3, F.relu, 0.0)
+    copy_params(omod, model)
+    tr = Trainer(dm, model, 0.002, static_graph=True, eager_warmup=eager_warmup, pipeline=False)
+    loop = OracleLoop(g, omod, "PoissonBanditLadiesSampler", fan, rng_seed=dm.sampler.rng_seed, eta=0.1, lr=0.002)
+    batches = []
+    while len(batches) < n_steps:
+        batches.extend(dm.train_batches())
+    d_loss, o_loss = [], []
+    for seeds in batches[:n_steps]:
+        d_loss.append(float(tr.training_step(seeds).item()))
+        o_loss.append(loop.training_step(seeds))
+        sizes_d = [(int(c.n_src), int(c.n_edges)) for c in dm.sampler.last_counters]
+        sizes_o = [(b.num_src_nodes(), b.num_edges()) for b in loop.last_blocks]
+        assert sizes_d == sizes_o, f"{tag}: step {len(d_loss) - 1}: sampled sizes {sizes_d} vs oracle {sizes_o}"
+    tr.flush()
+    assert tr.graph_replays >= n_steps - eager_warmup - 1
+    worst = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(d_loss, o_loss))
+    record(f"{tag}/loss_max_rel", worst)
+    record(f"{tag}/losses", [d_loss, o_loss])
+    assert worst <= loss_rtol, (d_loss, o_loss)
+    dparams = dict(model.named_parameters())
+    for n, q in omod.named_parameters():
+        close(dparams[n], q, param_rtol, f"{tag}/param/{n}")
+    w_dev, w_ora = dm.sampler.exp3_weights.cpu().double(), loop.smp.exp3_weights.double()
+    rel = ((w_dev - w_ora).abs() / w_ora).max().item()
+    record(f"{tag}/exp3_weights/max_rel", rel)
+    assert rel <= RTOL, f"{tag}: EXP3 weights after {n_steps} steps: max rel err {rel}"
+
+
+def test_cora_shape_trajectory_matches_oracle_loop(native_lib):
+    """configs[0]: 12 steps (3 eager + 9 graph replays) of sample → fwd → bwd → Adam → exp3 against the oracle."""
+    _trajectory("cora", 12, 256, 32, [512, 256, 128], 3, "trajectory-cora")
+
+
+def test_reddit_shape_trajectory_matches_oracle_loop(native_lib):
+    """configs[3], the bench workload (232,965 nodes, ~115 M edges, batch 256, fan-out 4096/2048/1024, hidden 256):
+    6 steps (2 eager + 4 replays of the whole-step CUDA graph) against the oracle loop — the sampled sizes of every
+    layer must be identical at every step (the sets are drawn from bandit weights both sides updated), losses within
+    1e-4, parameters within 1e-4 after 6 Adam steps, EXP3 weights within 1e-5."""
+    _trajectory("reddit", 6, 256, 256, [4096, 2048, 1024], 2, "trajectory-reddit")

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from oracle import samplers as osamp
-from tests.util import assert_blocks_equal, philox_uniform_fn, random_graph
+from tests.util import SafeDraws, assert_blocks_equal, philox_uniform_fn, random_graph, record
 
 pytestmark = pytest.mark.gpu
 
@@ -131,3 +131,53 @@ def test_reddit_shape_graph_replay_samples_like_eager(native_lib, reddit):
             assert tr.graph_replays >= 3
     # the first steps differ only through the bandit weights, which both paths update identically
     assert counts[True] == counts[False], (counts[True], counts[False])
+
+
+def test_reddit_shape_blocks_match_oracle_two_chained_steps(native_lib, reddit):
+    """BASELINE.json's headline configuration against the CPU oracle itself (``accum='contract'``: the device's
+    numeric contract), not only through invariants: batch 256, fan-out 4096/2048/1024 on the 115 M-edge graph.
+    Two consecutive steps with the bandit update between them (``bandit_sampler.py:341-367,251-267``), so the
+    second step's blocks are drawn from updated EXP3 weights.  Source order, block CSR and edge ids bit-exact;
+    q_ij, W~, P within 1e-5; EXP3 weights within 1e-5.  The draws are the device's Philox stream with the tie
+    band |u - P| <= 1e-4 P excluded (tests/util.SafeDraws)."""
+    from bliss_gnn_b200.graph import normalized_edata
+    from bliss_gnn_b200.sampler import PoissonBanditLadiesSampler
+    gd = reddit
+    if "w" not in gd.edata:
+        gd.edata["w"] = normalized_edata(gd)
+    g = gd.to("cpu")
+    V, fan, seed = g.num_nodes(), [4096, 2048, 1024], 11
+    train = torch.nonzero(g.ndata["train_mask"], as_tuple=True)[0]
+    perm = train[torch.randperm(train.numel(), generator=torch.Generator().manual_seed(7))]
+    ora = osamp.PoissonBanditLadiesSampler(fan, eta=0.1, accum="contract")
+    dev = PoissonBanditLadiesSampler(fan, eta=0.1, rng_seed=seed)
+    for step in range(2):
+        seeds = perm[step * 256:(step + 1) * 256]
+        draws = SafeDraws(V, seed, step)
+        ora.uniform_fn = draws
+        o_in, _, ob = ora.sample_blocks(g, seeds)
+        dev.step = step
+        dev.inject_uniforms = {l: u.to(gd.device) for l, u in draws.per_layer.items()}
+        d_in, _, db = dev.sample_blocks(gd, seeds)
+        assert torch.equal(d_in.cpu().long(), o_in), f"step {step}: input nodes differ"
+        for l, (a, b) in enumerate(zip(db, ob)):
+            st = assert_blocks_equal(a, b, rtol=1e-5)
+            record(f"reddit-blocks/step{step}/block{l}", dict(st, n_dst=a.num_dst_nodes(), n_src=a.num_src_nodes(),
+                                                           n_edges=a.num_edges()))
+            ctr = dev.last_counters[l]
+            assert ctr.n_cand == ora.trace["prob"][l][0].numel()
+            if l in ora.trace.get("c", {}):
+                c, it = ora.trace["c"][l]
+                assert ctr.iters == it and abs(ctr.c - c) <= 1e-6 * c
+            # a stand-in for the forward pass: ||h_j|| as a fixed function of the global node id
+            nid = b.srcdata["_ID"].long()
+            emb = 0.5 + ((nid * 2654435761) % 1000).float() / 1000.0
+            b.srcdata["embed_norm"] = emb
+            a.srcdata["embed_norm"] = emb.to(gd.device)
+        ora.exp3(ob, g)
+        dev.exp3(db, gd)
+        for l in range(3):
+            w_dev, w_ora = dev.exp3_weights[l].cpu().double(), ora.exp3_weights[l].double()
+            rel = ((w_dev - w_ora).abs() / w_ora).max().item()
+            record(f"reddit-blocks/step{step}/exp3_weights{l}", rel)
+            assert rel <= 1e-5, f"step {step} layer {l}: EXP3 weights max rel err {rel}"

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 from oracle import model as omodel
 from oracle import samplers as osamp
-from tests.util import philox_uniform_fn, random_graph
+from tests.util import blocks_as, copy_params, philox_uniform_fn, random_graph
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
@@ -102,10 +102,13 @@ def test_sage_gcn_models_forward_backward(native_lib, kind):
     torch.manual_seed(0)
     feats = torch.randn(g.num_nodes(), in_f)
     dmodel = (M.SAGE if kind == "sage" else M.GCN)(in_f, hid, ncls, 3, F.relu, 0.0).to(gd.device)
+    # the oracle runs in float64 (exact-arithmetic reference): the error measured is the device's own fp32 rounding
     omod = (omodel.SAGE if kind == "sage" else omodel.GCN)(in_f, hid, ncls, 3, F.relu, 0.0)
-    _copy_params(omod, dmodel)
+    copy_params(omod, dmodel, torch.float64)
+    omod = omod.double()
+    blocks_as(ob, torch.float64)
     xd = feats.to(gd.device)[db[0].srcdata["_ID"].long()]
-    xo = feats[ob[0].srcdata["_ID"].long()]
+    xo = feats[ob[0].srcdata["_ID"].long()].double()
     yd = dmodel(db, xd)
     yo = omod(ob, xo)
     _close(yd, yo, what=f"{kind} logits")
@@ -115,7 +118,7 @@ def test_sage_gcn_models_forward_backward(native_lib, kind):
     F.cross_entropy(yd, labels.to(gd.device)).backward()
     F.cross_entropy(yo, labels).backward()
     for (n, p), (_, q) in zip(dmodel.named_parameters(), omod.named_parameters()):
-        _close(p.grad, q.grad, rtol=5e-5, what=f"{kind} grad {n}")
+        _close(p.grad, q.grad, rtol=RTOL, what=f"{kind} grad {n}")
 
 
 @pytest.mark.parametrize("residual", [False, True])
@@ -128,9 +131,11 @@ def test_gatv2_model_forward_backward(native_lib, residual):
     args = (3, in_f, hid, ncls, heads, F.elu, 0.0, 0.0, 0.2, residual)
     dmodel = M.GATv2(*args).to(gd.device)
     omod = omodel.GATv2(*args)
-    _copy_params(omod, dmodel)
+    copy_params(omod, dmodel, torch.float64)
+    omod = omod.double()                       # float64 oracle: the exact-arithmetic reference
+    blocks_as(ob, torch.float64)
     yd = dmodel(db, feats.to(gd.device)[db[0].srcdata["_ID"].long()])
-    yo = omod(ob, feats[ob[0].srcdata["_ID"].long()])
+    yo = omod(ob, feats[ob[0].srcdata["_ID"].long()].double())
     _close(yd, yo, what="gat logits")
     for a, b in zip(db, ob):
         assert torch.equal(a.edge_src.cpu().long(), b.src)          # same native edge order
@@ -140,7 +145,7 @@ def test_gatv2_model_forward_backward(native_lib, residual):
     F.cross_entropy(yo, labels).backward()
     dgrads = dict(dmodel.named_parameters())
     for n, q in omod.named_parameters():
-        _close(dgrads[n].grad, q.grad, rtol=5e-5, what=f"gat grad {n}")
+        _close(dgrads[n].grad, q.grad, rtol=RTOL, what=f"gat grad {n}")
 
 
 def test_gatv2_attention_dropout_mask(native_lib):
@@ -157,18 +162,18 @@ def test_gatv2_attention_dropout_mask(native_lib):
     fd = feat.to(gd.device).requires_grad_(True)
     ad = attn.to(gd.device).requires_grad_(True)
     out, logits = ops.gatv2_attention(blk, fd, ad, 0.2, mask.to(gd.device))
-    fo, ao = feat.clone().requires_grad_(True), attn.clone().requires_grad_(True)
+    fo, ao = feat.double().requires_grad_(True), attn.double().requires_grad_(True)     # float64 reference
     e = F.leaky_relu(fo[oblk.src] + fo[: oblk.num_dst_nodes()][oblk.dst], 0.2)
     e = (e * ao).sum(-1)
-    a = dglops.edge_softmax(oblk, e) * mask
-    ref = torch.zeros(oblk.num_dst_nodes(), H, D).index_add(0, oblk.dst, fo[oblk.src] * a.unsqueeze(-1))
+    a = dglops.edge_softmax(oblk, e) * mask.double()
+    ref = torch.zeros(oblk.num_dst_nodes(), H, D, dtype=torch.float64).index_add(0, oblk.dst, fo[oblk.src] * a.unsqueeze(-1))
     _close(out, ref, what="gat out with dropout mask")
     _close(logits, e, what="gat logits")
-    go = torch.randn_like(ref)
+    go = torch.randn(ref.shape)
     out.backward(go.to(gd.device))
-    ref.backward(go)
-    _close(fd.grad, fo.grad, rtol=5e-5, what="gat grad feat")
-    _close(ad.grad, ao.grad, rtol=5e-5, what="gat grad attn")
+    ref.backward(go.double())
+    _close(fd.grad, fo.grad, rtol=RTOL, what="gat grad feat")
+    _close(ad.grad, ao.grad, rtol=RTOL, what="gat grad attn")
 
 
 def test_full_graph_inference(native_lib):

@@ -129,12 +129,12 @@ def test_poisson_bandit_contract_parity(native_lib, gname):
 
 
 @pytest.mark.parametrize("gname,dtype,rtol", [("light", torch.float32, RTOL), ("heavy", torch.float64, RTOL),
-                                              ("heavy", torch.float32, 1e-4)])
+                                              ("huge_row", torch.float64, RTOL)])
 def test_poisson_bandit_native_parity_safe_draws(native_lib, gname, dtype, rtol):
     """Device vs the torch-order oracle: sets bit-exact once ties are excluded by the draw generator.
-    Values: within 1e-5 of the float64 oracle (the exact-arithmetic reference).  The float32
-    torch-order oracle itself is only good to ~2e-5 on 1,500-edge rows (sequential fp32 index_add_),
-    so against it the heavy graph is held to 1e-4; the device is the more accurate of the two."""
+    Values: within 1e-5 of the float64 oracle (the exact-arithmetic reference) on the graphs with 1,500- and
+    9,500-edge rows; the float32 torch-order oracle is used on the light graph only (its own sequential fp32
+    ``index_add_`` is good to ~2e-5 on long rows, i.e. less accurate than the device)."""
     *_, (o_in, _, o_blocks), (d_in, _, d_blocks) = _oracle_and_device(
         gname, "PoissonBanditLadiesSampler", "native", draws="safe", ora_kw=dict(dtype=dtype))
     assert torch.equal(d_in.cpu().long(), o_in)
@@ -296,12 +296,19 @@ def test_gat_alpha_rewards(native_lib):
         ora.calculate_rewards(l, b, g, al)
         dev.calculate_rewards(l, a, gd, dev.calculate_alpha(a))
         r_d, r_o = a.edata["rewards"].cpu().double(), b.edata["rewards"].double()
-        # sums of signed attention logits cancel: compare with an absolute floor
-        assert ((r_d - r_o).abs() <= 1e-4 * r_o.abs() + 1e-9).all()
+        # alpha divides by a sum of SIGNED logits (bandit_sampler.py:148-154): fp32 rounding of the sum is amplified by
+        # the row's condition number kappa = sum|a| / |sum a| in alpha and 2 kappa in the reward (alpha^2), so the
+        # 1e-5 bar is scaled by it; rows whose sum does not cancel (kappa ~ 1) are held to 1e-5 itself
+        a64 = b.edata["a_ij"].double()
+        s = torch.zeros(b.num_dst_nodes(), dtype=torch.float64).index_add_(0, b.dst, a64)
+        sa = torch.zeros(b.num_dst_nodes(), dtype=torch.float64).index_add_(0, b.dst, a64.abs())
+        kappa = (sa / s.abs().clamp(min=1e-300))[b.dst].clamp(min=1.0)
+        assert ((r_d - r_o).abs() <= RTOL * 2.0 * kappa * r_o.abs() + 1e-30).all()
     ora.exp3(ob, g)
     dev.exp3(db, gd)
     w_dev, w_ora = dev.exp3_weights.cpu().double(), ora.exp3_weights.double()
-    assert ((w_dev - w_ora).abs() / w_ora).max().item() <= 1e-4
+    # the weight moves by exp(x), x = min(1, reward-term) (:240-246): the reward error enters damped by x <= 1
+    assert ((w_dev - w_ora).abs() / w_ora).max().item() <= RTOL
 
 
 def test_packed_exchange_apply_matches_sequential_updates(native_lib):

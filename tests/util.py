@@ -82,3 +82,113 @@ def assert_blocks_equal(dev_block, ora_block, rtol=1e-5, exact_values=False, che
             assert torch.equal(dev_block.srcdata["node_prob"].cpu(), ora_block.srcdata["node_prob"].float())
         stats["node_prob"] = rel
     return stats
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers of the configuration / trajectory parity tests
+# ---------------------------------------------------------------------------------------------
+import json
+import os
+
+_STATS = {}
+_STATS_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_stats.json")
+
+
+def record(name, value):
+    """Measured parity errors, dumped to gpurun_out/parity_stats.json (copied into profiles/ by hand)."""
+    _STATS[name] = value
+    try:
+        os.makedirs(os.path.dirname(_STATS_PATH), exist_ok=True)
+        old = {}
+        if os.path.exists(_STATS_PATH):
+            try:
+                old = json.load(open(_STATS_PATH))
+            except Exception:
+                old = {}
+        old.update(_STATS)
+        json.dump(old, open(_STATS_PATH, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def rel_to_max(a, b):
+    """max |a - b| / max |b| (cancelling sums do not produce false alarms)."""
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if b.numel() == 0:
+        return 0.0
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()
+
+
+def close(a, b, rtol, what):
+    err = rel_to_max(a, b)
+    record(what, err)
+    assert err <= rtol, f"{what}: max err / max|ref| = {err:.3e} > {rtol}"
+    return err
+
+
+def blocks_as(blocks, dtype):
+    """The oracle's blocks with their float payloads cast to ``dtype`` (so an fp64 oracle model sees exactly
+    the numbers the device model sees)."""
+    for b in blocks:
+        for frame in (b.edata, b.srcdata, b.dstdata):
+            for k, v in list(frame.items()):
+                if torch.is_tensor(v) and v.is_floating_point():
+                    frame[k] = v.to(dtype)
+    return blocks
+
+
+def copy_params(dst_model, src_model, dtype=None):
+    sd = {k: v.detach().cpu().clone() for k, v in src_model.state_dict().items()}
+    if dtype is not None:
+        sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+    missing = dst_model.load_state_dict(sd, strict=False)
+    assert not [k for k in missing.missing_keys if "fc_dst" not in k], missing
+
+
+class OracleLoop:
+    """The reference's training loop restated on the CPU oracle: ``train_lightning.py:100-168`` (sample → lazy
+    feature / label fetch → forward → loss → backward → Adam) followed by ``BatchSizeCallback.on_train_batch_end``
+    (``:463-471``: ``sampler.exp3``).  Draws are the device's Philox stream (seed, step = number of
+    ``sample_blocks`` calls so far)."""
+
+    def __init__(self, g_cpu, model, sampler_cls, fan, rng_seed, eta=0.1, lr=0.002, multilabel=False,
+                 model_kind="sage", accum="contract", dtype=torch.float32):
+        from oracle import samplers as osamp
+        self.g, self.model, self.step, self.seed = g_cpu, model, 0, rng_seed
+        kw = dict(eta=eta, model=model_kind) if "Bandit" in sampler_cls else {}
+        self.smp = getattr(osamp, sampler_cls)(list(fan), accum=accum, dtype=dtype, uniform_fn=self._draw, **kw)
+        self.opt = torch.optim.Adam(model.parameters(), lr=lr)
+        self.multilabel = multilabel
+        self.bandit = "Bandit" in sampler_cls
+        self.mdtype = next(model.parameters()).dtype
+
+    def _draw(self, layer, nids, prob=None):
+        return torch.from_numpy(philox.uniform_for_nodes(self.seed, self.step, layer, nids.numpy()))
+
+    def training_step(self, seeds):
+        import torch.nn.functional as F
+        g = self.g
+        inp, _, blocks = self.smp.sample_blocks(g, seeds.cpu())
+        self.step += 1
+        if self.mdtype != torch.float32:
+            blocks_as(blocks, self.mdtype)
+        x = g.ndata["features"][inp].to(self.mdtype)
+        y = g.ndata["labels"][seeds.cpu().long()]
+        pred = self.model(blocks, x)
+        loss = F.binary_cross_entropy_with_logits(pred, y.to(self.mdtype)) if self.multilabel else F.cross_entropy(pred, y)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        if self.bandit:
+            if self.mdtype != torch.float32:          # the sampler state stays in its own dtype
+                for b in blocks:
+                    for k in ("embed_norm",):
+                        b.srcdata[k] = b.srcdata[k].detach().to(self.smp.dtype)
+                    for k in ("q_ij", "a_ij", "w"):
+                        if k in b.edata:
+                            b.edata[k] = b.edata[k].detach().to(self.smp.dtype)
+                    b.srcdata["node_prob"] = b.srcdata["node_prob"].to(self.smp.dtype)
+            self.smp.exp3(blocks, g)
+        self.last_blocks = blocks
+        return float(loss.item())
