@@ -113,11 +113,12 @@ class _Workspace:
         self._ctr_slots[slot].copy_(self.ctr_all, non_blocking=True)
         self._ctr_events[slot].record()
 
-    def finish_counter_read(self, slot: int, n_layers: int):
-        """Wait for :meth:`enqueue_counter_read` of ``slot`` and parse the counters."""
+    def finish_counter_read(self, slot: int, n_layers: int, base: int = 0):
+        """Wait for :meth:`enqueue_counter_read` of ``slot`` and parse the counters of the blocks
+        ``base .. base + n_layers`` (the whole-step graph keeps one group of counter blocks per pool set)."""
         self._ctr_events[slot].synchronize()
         raw = self._ctr_slots[slot].numpy()
-        return [N.Counters.from_buffer_copy(raw[l].tobytes()) for l in range(n_layers)]
+        return [N.Counters.from_buffer_copy(raw[base + l].tobytes()) for l in range(n_layers)]
 
     def read_counters(self) -> N.Counters:
         self.ctr_host.copy_(self.ctr, non_blocking=True)
@@ -461,7 +462,8 @@ class BanditLadiesSampler:
         return self._finish_block(fr, out, bufs, pool)
 
     # ---- sync-free path (CUDA-graph capture of the whole step) -----------------------------------
-    def enqueue_static(self, g, seeds_static, pools, step_dev, transpose_stream=None, defer_last_transpose=False):
+    def enqueue_static(self, g, seeds_static, pools, step_dev, transpose_stream=None, defer_last_transpose=False,
+                       ctr_base: int = 0):
         """Enqueue the sampling of every layer into the capacity pools with NO host synchronisation:
         each layer reads its true seed count from the previous layer's device counters, the Philox
         step from ``step_dev``, and the transpose its edge count from the counters.  Capturable in a
@@ -470,7 +472,9 @@ class BanditLadiesSampler:
         ``transpose_stream``: side stream for every layer's back half (fill, workspace restore, transpose); the
         padded blocks get ``_ready`` / ``_t_ready`` events their readers wait for, and the caller must join the
         stream before the step ends.  ``defer_last_transpose``: do not launch the input layer's transpose here but
-        return it (a list of callables) for the caller to launch after the forward pass."""
+        return it (a list of callables) for the caller to launch after the forward pass.  ``ctr_base``: first
+        counters block to use (layer l writes block ``ctr_base + l``): the pipelined step samples the NEXT step's
+        blocks into a second pool set while this step's backward pass still reads the first set's counts."""
         wsp = self._bind(g)
         L = len(self.nodes_per_layer)
         bandit = self._mode == N.MODE_BANDIT
@@ -488,7 +492,8 @@ class BanditLadiesSampler:
             w = wsp if (side is None or (L - 1 - block_id) % 2 == 0) else self._wsp2
             seeds = seeds_static if top else pools[block_id + 1].src_nid
             n_cap = pool.cap_dst
-            ws = w.ws_layer(block_id, None if top else wsp.counter_ptr(block_id + 1, "n_src"), N.ptr(step_dev), counters=wsp)
+            ws = w.ws_layer(ctr_base + block_id, None if top else wsp.counter_ptr(ctr_base + block_id + 1, "n_src"),
+                            N.ptr(step_dev), counters=wsp)
             weights = self._w_csc[block_id] if bandit else weights_static
             mode = self._mode | (0 if self.importance_sampling else N.MODE_UNIFORM)
             if self.collect == "bitmap" or (self.collect == "auto" and g.num_nodes() > self.DENSE_COLLECT_MAX):
@@ -522,13 +527,13 @@ class BanditLadiesSampler:
                         pool.padded._ready = pool.ready
                 N.call("bliss_block_finish", n_cap, self._mode, C.byref(ws), C.byref(out), N.stream())
 
-            def transpose(pool=pool, e32=e32, block_id=block_id):
+            def transpose(pool=pool, e32=e32, block_id=block_id, back=back):
                 # read by the backward pass only (the caller joins ``transpose_stream`` before it)
                 with torch.cuda.stream(back):
                     N.call("bliss_block_transpose", N.ptr(e32[0]), N.ptr(e32[1]), pool.cap_edges, pool.cap_src,
                            pool.cap_dst, N.ptr(pool.t_indptr), N.ptr(pool.t_cursor), N.ptr(pool.t_bits), N.ptr(pool.t_pre),
                            pool.t_words, N.ptr(pool.t_dst), N.ptr(pool.t_perm), N.ptr(pool.t_seg_ptr), 1,
-                           wsp.counter_ptr(block_id, "n_edges"), N.ptr(e32[3]), N.ptr(pool.t_w), N.stream())
+                           wsp.counter_ptr(ctr_base + block_id, "n_edges"), N.ptr(e32[3]), N.ptr(pool.t_w), N.stream())
                     if pool.padded is not None:     # (weights tensor it was built from, transposed copy)
                         pool.padded._t_w = (e32[3].data_ptr(), pool.t_w)
                     if side is not None:            # readers of the transpose (backward pass, GCN out-degrees) wait for this
@@ -647,7 +652,10 @@ class BanditLadiesSampler:
         grows by at most e per update, ``bandit_sampler.py:244-246``)."""
         if self.normalize != "lazy":
             return
-        self._updates_since_renorm += 1
+        # every rank's update lands on this copy of the weights: an edge sampled by all W ranks can grow by e^W per
+        # step, so the range guard counts APPLIED updates, not steps
+        pg = self.process_group
+        self._updates_since_renorm += torch.distributed.get_world_size(pg) if pg is not None else 1
         if self._updates_since_renorm >= self.renorm_every:
             for idx in range(n_layers):
                 self._renormalize(idx)

@@ -143,9 +143,12 @@ class Trainer:
         # the data-parallel code path (two graphs with the collectives in between) can be forced on a
         # single rank, so it is testable on one GPU
         self._force_dp = bool(os.environ.get("BLISS_FORCE_DP_PATH")) and process_group is not None
-        self._graph, self._pools, self._padded, self._exchange, self._graph_b = None, None, None, None, None
+        self._graph, self._pools, self._padded, self._exchange = None, None, None, None
+        self._sets, self._graphs, self._graph_kernel_counts = None, {}, {}
+        self._cur, self._next_ready, self._prefetched_seeds = 0, False, None
         self._max_src, self._max_edges = None, None
         self.graph_replays, self.graph_kernels = 0, 0
+        self.graph_kernel_launches = 0      # hand-written kernels launched by graph replays so far (bench.py)
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.loss_fn = nn.BCEWithLogitsLoss() if datamodule.multilabel else nn.CrossEntropyLoss()   # :77-79
         if not datamodule.multilabel and next(model.parameters()).is_cuda:
@@ -184,10 +187,13 @@ class Trainer:
     def num_sampled_nodes(self, i):
         return self.cum_sampled_nodes[i] * (1 - self.w) / (1 - self.w ** self.num_steps)
 
-    def training_step(self, seeds: torch.Tensor) -> torch.Tensor:
+    def training_step(self, seeds: torch.Tensor, next_seeds: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One training step on ``seeds``.  ``next_seeds`` (optional): the batch the NEXT call will train on — the
+        look-ahead of a data loader; the static-graph path then samples its blocks in the shadow of this step's
+        backward pass (after this step's ``exp3``, so the trajectory is the reference's)."""
         if self.static_graph:
             if self._full_graph_ok():
-                return self._training_step_full_graph(seeds)
+                return self._training_step_full_graph(seeds, next_seeds)
             return self._training_step_static_partial(seeds)
         dm, g = self.dm, self.dm.g
         input_nodes, output_nodes, mfgs = dm.sampler.sample_blocks(g, seeds)
@@ -227,15 +233,19 @@ class Trainer:
         self.optimizer.step()
         self._grads_clean = isinstance(self.optimizer, FlatAdam)
 
-    # ---- static-shape path: padded blocks + one CUDA graph for forward/backward/Adam ---------------
+    # ---- static-shape path: capacity-padded blocks in persistent pools + CUDA graphs ------------------------
     def _alloc_pools(self):
+        """Two pool sets (double buffering): while the backward pass of step t still reads set p, the blocks of
+        step t+1 are sampled into set 1-p (``_training_step_full_graph``).  The eager-sampling variant
+        (``_training_step_static_partial``) uses set 0 only."""
         from .sampler import LayerPool
         from .graph import Block
         dm, g = self.dm, self.dm.g
         fan, L = dm.sampler.nodes_per_layer, len(dm.sampler.nodes_per_layer)
         dev = g.device
-        self._seeds_static = torch.zeros(dm.batch_size, dtype=torch.int32, device=dev)
         bandit = "bandit" in dm.sampler_name
+        if getattr(self, "_next_ready", False):             # an outstanding prefetch is dropped with its pool set
+            dm.sampler.step -= 1
         # edges of a block vary by +-17 % around their median from batch to batch at the Reddit shape (measured over
         # 400 steps): 1.45x the largest count seen so far; the high-water mark in _consume_counters re-sizes at 92 %
         cap_e = [int(1.45 * self._max_edges[l]) + 4096 for l in range(L)]
@@ -246,37 +256,37 @@ class Trainer:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.pg)
             cap_e = [int(v) for v in t.tolist()]
             self._exchange = BanditExchange(cap_e, self.world, dev, self.pg)
-        pools, cd = [None] * L, dm.batch_size
-        for l in reversed(range(L)):                       # output layer first: cap_dst[l] = cap_src[l+1]
-            # sources = destinations + Poisson-selected nodes (mean <= fan-out, sigma <= sqrt(fan-out)); the high-water
-            # mark in _consume_counters re-sizes long before a capacity can be hit
-            cap_src = max(cd + fan[l] + int(6 * math.sqrt(fan[l])) + 64, int(1.12 * self._max_src[l]) + 64)
-            cap_src = (cap_src + 63) // 64 * 64            # row counts the split-K weight gradients divide evenly
-            pools[l] = LayerPool(dev, cd, cap_src, cap_e[l], bandit=bandit)
-            cd = cap_src
-        padded = []
-        for l in range(L):
-            pool = pools[l]
-            dst_nid = pools[l + 1].src_nid if l < L - 1 else self._seeds_static
-            pb = Block(pool.indptr, pool.e32[0], pool.e32[1], pool.src_nid, dst_nid, graph=g, csc_pos=pool.csc_pos)
-            pb.seg_ptr, pb._mean_scale, pb._static_padded = pool.seg_ptr, pool.inv_deg, True
-            pb.edata["edge_weights"] = pool.e32[3].view(torch.float32)
-            pb._transpose = (pool.t_indptr, pool.t_dst, pool.t_perm, pool.t_seg_ptr)
-            pool.padded = pb
-            padded.append(pb)
-        self._pools, self._padded, self._graph = pools, padded, None
+        sets = []
+        for p in range(2):
+            seeds_static = torch.zeros(dm.batch_size, dtype=torch.int32, device=dev)
+            pools, cd = [None] * L, dm.batch_size
+            for l in reversed(range(L)):                       # output layer first: cap_dst[l] = cap_src[l+1]
+                # sources = destinations + Poisson-selected nodes (mean <= fan-out, sigma <= sqrt(fan-out)); the
+                # high-water mark in _consume_counters re-sizes long before a capacity can be hit
+                cap_src = max(cd + fan[l] + int(6 * math.sqrt(fan[l])) + 64, int(1.12 * self._max_src[l]) + 64)
+                cap_src = (cap_src + 63) // 64 * 64            # row counts the split-K weight gradients divide evenly
+                pools[l] = LayerPool(dev, cd, cap_src, cap_e[l], bandit=bandit)
+                cd = cap_src
+            padded = []
+            for l in range(L):
+                pool = pools[l]
+                dst_nid = pools[l + 1].src_nid if l < L - 1 else seeds_static
+                pb = Block(pool.indptr, pool.e32[0], pool.e32[1], pool.src_nid, dst_nid, graph=g, csc_pos=pool.csc_pos)
+                pb.seg_ptr, pb._mean_scale, pb._static_padded = pool.seg_ptr, pool.inv_deg, True
+                pb.edata["edge_weights"] = pool.e32[3].view(torch.float32)
+                pb._transpose = (pool.t_indptr, pool.t_dst, pool.t_perm, pool.t_seg_ptr)
+                pool.padded = pb
+                padded.append(pb)
+            sets.append(_PoolSet(pools, padded, seeds_static, ctr_base=8 * p))
+        self._sets = sets
+        self._pools, self._padded, self._seeds_static = sets[0].pools, sets[0].padded, sets[0].seeds
+        self._graph, self._graphs = None, {}
+        self._cur, self._next_ready, self._prefetched_seeds = 0, False, None
 
-    def _padded_fwd_bwd(self, step_optimizer: bool, after_forward=None, before_backward=None):
+    def _padded_fwd_bwd(self, step_optimizer: bool, after_forward=None, before_backward=None, pset=None):
         """``after_forward`` / ``before_backward``: hooks of the whole-step graph — work that only needs the
         forward pass is forked onto side streams there, work the backward pass needs is joined."""
-        g = self.dm.g
-        x, norm = ops.gather_rows(g.ndata["features"], self._pools[0].src_nid, with_norm=True)
-        x._bliss_row_norm = norm                       # layer 0's embed_norm comes with the gather (model.SAGE/GCN/GATv2)
-        y = self._gather_labels(g.ndata["labels"], self._seeds_static)
-        pred = self.model(self._padded, x)
-        if pred.shape[0] != self.dm.batch_size:          # (the top layer's capacity is the batch size: usually a no-op)
-            pred = pred[: self.dm.batch_size]
-        loss = self.loss_fn(pred, y)
+        loss, pred, y = self._padded_fwd(pset)
         if after_forward is not None:
             after_forward()
         self._zero_grads()
@@ -285,7 +295,7 @@ class Trainer:
         loss.backward()
         if step_optimizer:
             self._optimizer_step()
-        return loss.detach(), pred.detach(), y
+        return loss.detach(), pred, y
 
     @staticmethod
     def _gather_labels(labels, nid32):
@@ -296,12 +306,13 @@ class Trainer:
             return out.view(torch.int64).view(-1)
         return labels[nid32.long()]
 
-    def _padded_fwd(self):
+    def _padded_fwd(self, pset=None):
         g = self.dm.g
-        x, norm = ops.gather_rows(g.ndata["features"], self._pools[0].src_nid, with_norm=True)
-        x._bliss_row_norm = norm
-        y = self._gather_labels(g.ndata["labels"], self._seeds_static)
-        pred = self.model(self._padded, x)
+        pset = pset or self._sets[0]
+        x, norm = ops.gather_rows(g.ndata["features"], pset.pools[0].src_nid, with_norm=True)
+        x._bliss_row_norm = norm                       # layer 0's embed_norm comes with the gather (model.SAGE/GCN/GATv2)
+        y = self._gather_labels(g.ndata["labels"], pset.seeds)
+        pred = self.model(pset.padded, x)
         if pred.shape[0] != self.dm.batch_size:          # (the top layer's capacity is the batch size: usually a no-op)
             pred = pred[: self.dm.batch_size]
         return self.loss_fn(pred, y), pred.detach(), y
@@ -328,24 +339,19 @@ class Trainer:
         _native.STATS.launches = before
 
     def _training_step_static_partial(self, seeds: torch.Tensor) -> torch.Tensor:
-        """Eager sampling into the pools + replayed forward/backward(/Adam): the data-parallel variant
-        (the collectives sit between the sampler and the optimizer)."""
+        """Eager sampling into the pools + replayed forward/backward(/Adam): the variant for samplers whose stage
+        methods are overridden or whose draws are injected (the collectives sit between the sampler and the
+        optimizer)."""
         dm, g, smp = self.dm, self.dm.g, self.dm.sampler
         L = len(smp.nodes_per_layer)
-        if self._pools is None:
+        if self._sets is None:
             if self._sizing_steps < self.eager_warmup or seeds.numel() != dm.batch_size:
-                _, _, mfgs = smp.sample_blocks(g, seeds)
-                self._sizing_steps += 1
-                if self._max_src is None:
-                    self._max_src, self._max_edges = [0] * L, [0] * L
-                for l, b in enumerate(mfgs):
-                    self._max_src[l] = max(self._max_src[l], b.num_src_nodes())
-                    self._max_edges[l] = max(self._max_edges[l], b.num_edges())
-                return self._eager_rest(mfgs)
+                return self._sizing_step(seeds)
             self._alloc_pools()
         if seeds.numel() != dm.batch_size:                  # ragged last batch: ordinary path
             _, _, mfgs = smp.sample_blocks(g, seeds)
             return self._eager_rest(mfgs)
+        self._drop_prefetch()
         self._seeds_static.copy_(seeds, non_blocking=True)
         _, _, mfgs = smp.sample_blocks(g, self._seeds_static, pools=self._pools)
         if not smp.pool_used:                               # per-stage sampler path (overridden stage / profiling)
@@ -365,6 +371,7 @@ class Trainer:
         self._sync_lr()
         self._graph.replay()
         self.graph_replays += 1
+        self.graph_kernel_launches += self.graph_kernels
         if self.world > 1:
             self.grads.all_reduce_mean_(self.pg)
             self._optimizer_step()
@@ -378,87 +385,145 @@ class Trainer:
         self.last_blocks, self.last_pred, self.last_labels = mfgs, self._static_pred, self._static_y
         return self._static_loss
 
-    # ---- whole step in one CUDA graph (single rank): sampling included, one host sync per step ------
+    def _sizing_step(self, seeds):
+        """An ordinary (eager) step whose block sizes feed the capacity of the pools."""
+        dm, g, smp = self.dm, self.dm.g, self.dm.sampler
+        L = len(smp.nodes_per_layer)
+        self._drop_prefetch()
+        _, _, mfgs = smp.sample_blocks(g, seeds)
+        self._sizing_steps += 1
+        if self._max_src is None:
+            self._max_src, self._max_edges = [0] * L, [0] * L
+        for l, b in enumerate(mfgs):
+            self._max_src[l] = max(self._max_src[l], b.num_src_nodes())
+            self._max_edges[l] = max(self._max_edges[l], b.num_edges())
+        return self._eager_rest(mfgs)
+
+    def _drop_prefetch(self):
+        """Forget the blocks sampled ahead for a batch that is not going to be trained on next (eager step in
+        between, re-sized pools, checkpoint): their Philox step is given back, so the next sampling draws exactly
+        what an un-pipelined run would have drawn."""
+        if getattr(self, "_next_ready", False):
+            self._next_ready, self._prefetched_seeds = False, None
+            self.dm.sampler.step -= 1
+
+    # ---- whole step in CUDA graphs, sampling of step t+1 in the shadow of step t's backward pass --------------
     def _full_graph_ok(self) -> bool:
         smp = self.dm.sampler
         return smp._stages_not_overridden() and smp.inject_uniforms is None
 
-    def _training_step_full_graph(self, seeds: torch.Tensor) -> torch.Tensor:
+    def _training_step_full_graph(self, seeds: torch.Tensor, next_seeds: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One step on pool set p = replay of the step graph of that set:
+
+            forward(t) ─┬─ backward(t) ─ Adam(t) ───────────────────────────────┬─ (end of step t)
+                        └─ exp3(t) ─ sample_blocks(t+1) into set 1-p (prefetch) ─┘
+
+        ``exp3(t)`` needs only the forward pass (``embed_norm``, ``a_ij``) and ``sample_blocks(t+1)`` only the weights
+        after ``exp3(t)`` — the reference's order (``bandit_sampler.py:251-267`` after ``training_step``,
+        ``train_lightning.py:463-471``) is kept, the sampling just no longer waits for the backward pass it does
+        not depend on.  ``next_seeds`` is the batch of the next call (the data loader's look-ahead); without it the
+        step samples its own blocks first (prologue graph) and nothing is sampled ahead."""
         dm, g, smp = self.dm, self.dm.g, self.dm.sampler
         L = len(smp.nodes_per_layer)
-        if self._pools is None or seeds.numel() != dm.batch_size:
+        if self._sets is None or seeds.numel() != dm.batch_size:
             if self._sizing_steps < self.eager_warmup or self._max_src is None or seeds.numel() != dm.batch_size:
-                _, _, mfgs = smp.sample_blocks(g, seeds)           # ordinary steps: size the pools
-                self._sizing_steps += 1
-                if self._max_src is None:
-                    self._max_src, self._max_edges = [0] * L, [0] * L
-                for l, b in enumerate(mfgs):
-                    self._max_src[l] = max(self._max_src[l], b.num_src_nodes())
-                    self._max_edges[l] = max(self._max_edges[l], b.num_edges())
-                return self._eager_rest(mfgs)
+                return self._sizing_step(seeds)                # ordinary steps: size the pools / ragged batch
             self._alloc_pools()
-        if self._graph is None:
+        if not self._graphs:
             self._capture_full()
-        self._seeds_static.copy_(seeds, non_blocking=True)
         self._sync_lr()
+        if self._next_ready and seeds is not self._prefetched_seeds:
+            self._drop_prefetch()                              # the caller trains on another batch than announced
         if smp.step != self._dev_step_mirror:     # eager sampling in between (validation, ragged batch) advanced the
             self._step_dev.fill_(smp.step)        # host's Philox step: the device counter follows, draws never repeat
-        self._graph.replay()
-        self._dev_step_mirror = smp.step + 1
-        if self._graph_b is not None:             # data parallel: see _capture_full for the four graphs
+            self._dev_step_mirror = smp.step
+        p = self._cur
+        cur, nxt = self._sets[p], self._sets[1 - p]
+        fresh = []                                             # pool sets whose counters this call produces
+        if not self._next_ready:
+            cur.seeds.copy_(seeds, non_blocking=True)
+            self._replay(("S", p))
+            smp.step += 1
+            fresh.append(p)
+        prefetch = next_seeds is not None and next_seeds.numel() == dm.batch_size
+        if prefetch:
+            nxt.seeds.copy_(next_seeds, non_blocking=True)
+        if self._exchange is None and not (self.world > 1 or self._force_dp):
+            self._replay(("G" if prefetch else "GN", p))
+        else:                                                  # data parallel: see _capture_full
             main = torch.cuda.current_stream()
+            self._replay(("A1", p))
+            a1_done = torch.cuda.Event()
+            a1_done.record(main)
             work = None
             if self._exchange is not None:        # the bandit all-gather runs on NCCL's stream beside the backward pass
                 work = torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send, group=self.pg,
                                                                 async_op=True)
-            self._graph_a2.replay()
-            if work is not None:                  # … and so does the apply pass over all ranks' updates
-                with torch.cuda.stream(self._side_apply):
-                    work.wait()                   # (the all-gather itself was ordered after A1 when it was issued)
-                    self._graph_b1.replay()
+            self._replay(("A2", p))
+            with torch.cuda.stream(self._side_apply):          # … and so do the apply pass over all ranks' updates
+                self._side_apply.wait_event(a1_done)           # and the sampling of the next batch
+                if work is not None:
+                    work.wait()
+                self._replay(("B1" if prefetch else "B1N", p))
             self.grads.all_reduce_mean_(self.pg)
-            if work is not None:
-                main.wait_stream(self._side_apply)
-            self._graph_b.replay()
+            self._replay(("B2", 0))
+            main.wait_stream(self._side_apply)
+        if prefetch:
+            smp.step += 1
+            fresh.append(1 - p)
+        self._dev_step_mirror = smp.step
+        self._next_ready, self._prefetched_seeds = prefetch, (next_seeds if prefetch else None)
+        self._cur = 1 - p
+        self._static_loss, self._static_pred, self._static_y = self._static_out[p if prefetch or ("N", p) not in self._static_out
+                                                                                else ("N", p)]
         slot = self.graph_replays & 1
         self.graph_replays += 1
         smp._wsp.enqueue_counter_read(slot)                    # stream-ordered D2H, no host wait
-        smp.step += 1
         smp.tick_renorm(L)
-        if self.pipeline:                                      # consume the PREVIOUS step's counters
-            prev, self._pending = self._pending, slot
+        if self.pipeline:                                      # consume the PREVIOUS call's counters
+            prev, self._pending = self._pending, (slot, fresh)
             if prev is None:
                 return self._static_loss
-            slot = prev
-        self._consume_counters(smp._wsp.finish_counter_read(slot, L))
+            slot, fresh = prev
+        self._consume_counters(slot, fresh)
         return self._static_loss
+
+    def _replay(self, key):
+        self._graphs[key].replay()
+        self.graph_kernel_launches += self._graph_kernel_counts.get(key, 0)
 
     def flush(self):
         """Consume the counters of the last enqueued step (pipelined mode)."""
         if self._pending is not None:
-            slot, self._pending = self._pending, None
-            self._consume_counters(self.dm.sampler._wsp.finish_counter_read(slot, len(self.dm.sampler.nodes_per_layer)))
+            (slot, fresh), self._pending = self._pending, None
+            self._consume_counters(slot, fresh)
 
-    def _consume_counters(self, ctrs):
+    def _consume_counters(self, slot, fresh):
+        """Sizes and capacity flags of the blocks sampled by one call (``fresh``: the pool sets it sampled into)."""
         dm, g, smp = self.dm, self.dm.g, self.dm.sampler
         L = len(smp.nodes_per_layer)
         grow = False
-        for l, c in enumerate(ctrs):
-            if c.error:
-                raise RuntimeError(f"static step: capacity of layer {l} exceeded (n_src {c.n_src}/{self._pools[l].cap_src}, "
-                                   f"edges {c.n_edges}/{self._pools[l].cap_edges}); the step is invalid — "
-                                   "raise the pool margins (Trainer.pool_margin) or use static_graph=False")
-            self._max_src[l] = max(self._max_src[l], c.n_src)
-            self._max_edges[l] = max(self._max_edges[l], c.n_edges)
-            grow |= c.n_src > 0.92 * self._pools[l].cap_src or c.n_edges > 0.92 * self._pools[l].cap_edges
-        smp.last_counters = ctrs
-        self.num_steps += 1
-        for i, c in enumerate(ctrs):
-            self.cum_sampled_nodes[i] = self.cum_sampled_nodes[i] * self.w + c.n_src
-            self.cum_sampled_edges[i] = self.cum_sampled_edges[i] * self.w + c.n_edges
-        self.cum_sampled_nodes[L] = self.cum_sampled_nodes[L] * self.w + dm.batch_size
-        self.total_sampled_edges += sum(int(c.n_edges) for c in ctrs)
-        self.last_blocks = _CounterBlocks(ctrs)
+        for p in fresh:
+            pset = self._sets[p] if self._sets is not None else None
+            ctrs = smp._wsp.finish_counter_read(slot, L, base=8 * p)
+            for l, c in enumerate(ctrs):
+                if c.error:
+                    cap = (pset.pools[l].cap_src, pset.pools[l].cap_edges) if pset is not None else ("?", "?")
+                    raise RuntimeError(f"static step: capacity of layer {l} exceeded (n_src {c.n_src}/{cap[0]}, "
+                                       f"edges {c.n_edges}/{cap[1]}); the step is invalid — "
+                                       "raise the pool margins or use static_graph=False")
+                self._max_src[l] = max(self._max_src[l], c.n_src)
+                self._max_edges[l] = max(self._max_edges[l], c.n_edges)
+                if pset is not None:
+                    grow |= c.n_src > 0.92 * pset.pools[l].cap_src or c.n_edges > 0.92 * pset.pools[l].cap_edges
+            smp.last_counters = ctrs
+            self.num_steps += 1
+            for i, c in enumerate(ctrs):
+                self.cum_sampled_nodes[i] = self.cum_sampled_nodes[i] * self.w + c.n_src
+                self.cum_sampled_edges[i] = self.cum_sampled_edges[i] * self.w + c.n_edges
+            self.cum_sampled_nodes[L] = self.cum_sampled_nodes[L] * self.w + dm.batch_size
+            self.total_sampled_edges += sum(int(c.n_edges) for c in ctrs)
+            self.last_blocks = _CounterBlocks(ctrs)
         self.last_pred, self.last_labels = self._static_pred, self._static_y
         if self.world > 1:        # re-sizing allocates collectively: agree on it, every 32 steps
             self._grow_pending = getattr(self, "_grow_pending", False) or grow
@@ -479,146 +544,157 @@ class Trainer:
             torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send, group=self.pg)
 
     def _capture_full(self):
+        """Captures, per pool set p: S[p] (sampling of one batch into set p: the prologue of an un-prefetched step),
+        G[p] / GN[p] (the step on set p with / without sampling the next batch into set 1-p) — or, data parallel,
+        A1[p] (forward + exponents of the bandit update written into the exchange's send buffer), A2[p] (backward),
+        B1[p] / B1N[p] (apply every rank's gathered updates [+ sample the next batch]) and B2 (Adam), with the two
+        collectives launched between them:
+
+            A1 ─ all_gather (NCCL stream) ─ B1: apply all ranks' updates ─ sample_blocks(t+1)   ┐ side stream
+            └─── A2: backward ─ all_reduce of the gradients ─ B2: Adam                          ┘ main stream
+        """
         from . import _native
         dm, g, smp = self.dm, self.dm.g, self.dm.sampler
         L = len(smp.nodes_per_layer)
         smp._bind(g)
         if getattr(self, "_step_dev", None) is None:
-            self._step_dev = torch.zeros(1, dtype=torch.int64, device=g.device)
+            self._step_dev = torch.zeros(1, dtype=torch.int64, device=g.device)      # Philox step of the NEXT sampling
+            self._drop_dev = torch.zeros(1, dtype=torch.int64, device=g.device)      # dropout's Philox step (one per step)
+            if getattr(self.model, "_drop_step_t", None) is not None:               # continue the eager steps' count
+                self._drop_dev.copy_(self.model._drop_step_t)
         self._step_dev.fill_(smp.step)
-        if hasattr(self.model, "_drop_step"):       # dropout's Philox step = the trainer's device step counter
-            self.model._drop_step_t, self.model._external_drop_step = self._step_dev, True
-        for l, pb in enumerate(self._padded):
-            pool = self._pools[l]
-            pb._n_edges_dev = smp._wsp.counter_ptr(l, "n_edges")
-            if smp._mode == _native.MODE_BANDIT:
-                pb.edata["q_ij"] = pool.e32[4].view(torch.float32)
-                pb.srcdata[smp.node_prob] = pool.node_prob
-            dict.pop(pb.srcdata, "embed_norm", None)
-            dict.pop(pb.edata, "a_ij", None)
+        if hasattr(self.model, "_drop_step"):
+            self.model._drop_step_t, self.model._external_drop_step = self._drop_dev, True
+        bandit_mode = smp._mode == _native.MODE_BANDIT
+        for pset in self._sets:
+            for l, pb in enumerate(pset.padded):
+                pool = pset.pools[l]
+                pb._n_edges_dev = smp._wsp.counter_ptr(pset.ctr_base + l, "n_edges")
+                if bandit_mode:
+                    pb.edata["q_ij"] = pool.e32[4].view(torch.float32)
+                    pb.srcdata[smp.node_prob] = pool.node_prob
+                dict.pop(pb.srcdata, "embed_norm", None)
+                dict.pop(pb.edata, "a_ij", None)
         self.last_pred = None
 
         dp = self.world > 1 or self._force_dp
         bandit = "bandit" in dm.sampler_name
-
-        # Two side branches of the step's graph keep short kernels off the critical path: the block transposes
-        # (only the backward pass reads them) run beside the next layer's sampling / the forward pass, and the
-        # bandit update (needs embed_norm of the forward pass only) runs beside the backward pass and Adam.
         if getattr(self, "_side_t", None) is None:
-            # the step's critical path is captured on a high-priority stream, the side branches on normal-priority
-            # ones: their kernels fill idle SMs instead of competing with the bandwidth-bound aggregation
-            self._side_t, self._side_b = torch.cuda.Stream(), torch.cuda.Stream()
+            # the step's main line (forward, backward, Adam) is captured on a high-priority stream; the side branch
+            # (bandit update, next batch's sampling, transposes) on normal-priority ones
+            self._side_t, self._side_b, self._side_s = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
             self._main_hp = torch.cuda.Stream(priority=-5)
+            self._side_apply = torch.cuda.Stream()
+        def clear_events(pset):
+            for pb in pset.padded:                # events recorded in one capture must not be waited for in another
+                pb._ready = pb._t_ready = None
 
-        def bandit_update():
-            main = torch.cuda.current_stream()
-            self._side_b.wait_stream(main)
-            with torch.cuda.stream(self._side_b):
-                if not dp:
-                    smp.exp3(self._padded, g, count_renorm=False)
-                else:        # data parallel: emit the exponents + counts into the exchange's send buffer
-                    smp.exp3_emit(self._padded, g, self._exchange)
+        def sample_into(pset):
+            """Sampling of one batch (``pset.seeds``) into ``pset``: every layer's front half on the current stream,
+            back halves and transposes on ``_side_t``; complete (joined) on return."""
+            cur = torch.cuda.current_stream()
+            smp.enqueue_static(g, pset.seeds, pset.pools, self._step_dev, transpose_stream=self._side_t,
+                               defer_last_transpose=False, ctr_base=pset.ctr_base)
+            cur.wait_stream(self._side_t)
+            self._step_dev.add_(1)
+            clear_events(pset)
 
-        def body():          # graph A (the whole step on a single rank)
+        def body_sample(p):
+            sample_into(self._sets[p])
+
+        def body_step(p, prefetch):               # single rank: the whole step in one graph
+            pset, other = self._sets[p], self._sets[1 - p]
+            clear_events(pset)
             main = torch.cuda.current_stream()
-            deferred = smp.enqueue_static(g, self._seeds_static, self._pools, self._step_dev,
-                                          transpose_stream=self._side_t,
-                                          defer_last_transpose=not isinstance(self.model, GCN))   # GCN reads out-degrees in forward
 
             def after_forward():
-                self._side_t.wait_stream(main)       # the input layer's transpose: beside the backward pass of the upper layers
-                for launch in deferred:
-                    launch()
-                if bandit:
-                    bandit_update()
+                if not (bandit or prefetch):
+                    return
+                self._side_s.wait_stream(main)
+                with torch.cuda.stream(self._side_s):
+                    if bandit:
+                        smp.exp3(pset.padded, g, count_renorm=False)
+                    if prefetch:
+                        sample_into(other)
 
-            # no global join before the backward pass: every reader of a transpose waits for that block's own
-            # event (ops.block_transpose), so the upper layers' backward does not wait for the input layer's transpose
-            loss, pred, y = self._padded_fwd_bwd(not dp, after_forward=after_forward)
-            main.wait_stream(self._side_t)
-            if bandit:
-                main.wait_stream(self._side_b)
-            if not dp:
-                self._step_dev.add_(1)
+            loss, pred, y = self._padded_fwd_bwd(True, after_forward=after_forward, pset=pset)
+            if bandit or prefetch:
+                main.wait_stream(self._side_s)
+            self._drop_dev.add_(1)
             return loss, pred, y
 
-        # Data parallel: four graphs, so that the bandit all-gather and its apply pass overlap the backward pass:
-        #   A1 sampling + forward (+ every layer's exponents emitted as soon as its embed_norm exists)
-        #   -> all_gather (NCCL stream)  ||  A2 backward (+ the input layer's transpose on the side branch)
-        #   -> B1 apply all ranks' updates (side stream, after the all-gather)  ||  all_reduce of the gradients
-        #   -> B2 Adam + step counter.
         early_emit = bandit and smp.model != "gat"      # GAT's alpha needs a_ij: emitted after the forward pass
 
-        def body_a1():
+        def body_a1(p):
+            pset = self._sets[p]
+            clear_events(pset)
             main = torch.cuda.current_stream()
-            self._dp_deferred = smp.enqueue_static(g, self._seeds_static, self._pools, self._step_dev,
-                                                   transpose_stream=self._side_t,
-                                                   defer_last_transpose=not isinstance(self.model, GCN))
-            if early_emit:
+            if early_emit:      # a layer's exponents are emitted as soon as the model has stored its embed_norm
                 def make(l, pb):
                     def hook():
                         self._side_b.wait_stream(torch.cuda.current_stream())
                         with torch.cuda.stream(self._side_b):
-                            ops._wait_ready(pb)                      # the block's fill (side branch of the sampler)
                             smp.exp3_emit_layer(l, pb, g, self._exchange)
                     return hook
-                for l, pb in enumerate(self._padded):
+                for l, pb in enumerate(pset.padded):
                     pb.srcdata.on_set["embed_norm"] = make(l, pb)
             try:
-                loss, pred, y = self._padded_fwd()
+                loss, pred, y = self._padded_fwd(pset)
             finally:
-                for pb in self._padded:
+                for pb in pset.padded:
                     pb.srcdata.on_set.pop("embed_norm", None)
             if bandit and not early_emit:
                 self._side_b.wait_stream(main)
                 with torch.cuda.stream(self._side_b):
-                    smp.exp3_emit(self._padded, g, self._exchange)
-            main.wait_stream(self._side_t)
+                    smp.exp3_emit(pset.padded, g, self._exchange)
             if bandit:
                 main.wait_stream(self._side_b)
             return loss, pred.detach(), y
 
         def body_a2(loss):
-            main = torch.cuda.current_stream()
-            for pb in self._padded:       # A1 is complete in stream order; its events belong to another capture
-                pb._ready = pb._t_ready = None
-            self._side_t.wait_stream(main)
-            for launch in self._dp_deferred:                        # the input layer's transpose, beside the upper layers' backward
-                launch()
             self._zero_grads()
             loss.backward()
-            main.wait_stream(self._side_t)
 
-        def body_b1():
+        def body_b1(p, prefetch):
             if bandit:
                 smp.exp3_apply(self._exchange, L)
+            if prefetch:
+                sample_into(self._sets[1 - p])
+            if not (bandit or prefetch):
+                self._drop_dev.add_(0)            # (a captured graph must hold at least one node)
 
         def body_b2():
             self._optimizer_step()
-            self._step_dev.add_(1)
+            self._drop_dev.add_(1)
+
+        def dp_step_eager(p, prefetch):
+            loss_w, _, _ = body_a1(p)
+            if self._exchange is not None:
+                torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send, group=self.pg)
+            body_a2(loss_w)
+            body_b1(p, prefetch)
+            self.grads.all_reduce_mean_(self.pg)
+            body_b2()
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         state = (smp.state_dict()["exp3_w_csc"].clone(), smp._l1.clone()) if smp._w_csc is not None else None
-        opt_state = None
-        with torch.cuda.stream(side):                       # warm-up replays off the default stream …
+        with torch.cuda.stream(side):                       # warm-up runs off the default stream …
             import copy
             opt_state = copy.deepcopy(self.optimizer.state_dict())
-            params = [p.detach().clone() for p in self.grads.params]
-            self._seeds_static.copy_(self.dm.train_nid[: dm.batch_size])
-            for _ in range(2):
+            params = [p_.detach().clone() for p_ in self.grads.params]
+            drop0 = self._drop_dev.clone()
+            for pset in self._sets:
+                pset.seeds.copy_(self.dm.train_nid[: dm.batch_size])
+            body_sample(0)
+            for p in (0, 1):
                 if dp:
-                    loss_w, _, _ = body_a1()
-                    body_a2(loss_w)
-                    self._dp_exchange()
-                    body_b1()
-                    body_b2()
-                    del loss_w
+                    dp_step_eager(p, True)
                 else:
-                    body()
-            # … must not change the training state: restore parameters, Adam moments, bandit weights
-            for p, q in zip(self.grads.params, params):
-                p.data.copy_(q)
+                    body_step(p, True)
+            # … and must not change the training state: restore parameters, Adam moments, bandit weights
+            for p_, q in zip(self.grads.params, params):
+                p_.data.copy_(q)
             self.optimizer.load_state_dict(opt_state)
             if state is not None:
                 for l, w in enumerate(state[0]):
@@ -626,50 +702,64 @@ class Trainer:
                 smp._l1.copy_(state[1])
             self._step_dev.fill_(smp.step)
             self._dev_step_mirror = smp.step
+            self._drop_dev.copy_(drop0)
         torch.cuda.current_stream().wait_stream(side)
-        before = _native.STATS.launches
-        # (Capturing NCCL's collectives into ONE graph with both halves was measured at N=2: no faster than
-        # two replays with the collectives launched in between, and the process hung in NCCL teardown.)
-        self._graph_b = self._graph_a2 = self._graph_b1 = None
-        self._graph = torch.cuda.CUDAGraph()
-        if not dp:
-            with torch.cuda.graph(self._graph, stream=self._main_hp):
-                self._static_loss, self._static_pred, self._static_y = body()
-        else:
-            with torch.cuda.graph(self._graph, stream=self._main_hp):
-                loss, self._static_pred, self._static_y = body_a1()
-            self._static_loss = loss.detach()
-            self._graph_a2 = torch.cuda.CUDAGraph()     # the backward pass of A1's autograd graph: same memory pool
-            with torch.cuda.graph(self._graph_a2, pool=self._graph.pool(), stream=self._main_hp):
-                body_a2(loss)
-            del loss
-            self._graph_b1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph_b1):
-                body_b1()
-            self._graph_b = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph_b):
-                body_b2()
-            if getattr(self, "_side_apply", None) is None:
-                self._side_apply = torch.cuda.Stream()
-        self.graph_kernels = _native.STATS.launches - before    # hand-written kernels inside one replay
-        _native.STATS.launches = before
+
+        graphs, counts, outs = {}, {}, {}
+
+        def capture(key, fn, pool=None, stream=None):
+            before = _native.STATS.launches
+            gr = torch.cuda.CUDAGraph()
+            kw = {}
+            if pool is not None:
+                kw["pool"] = pool
+            with torch.cuda.graph(gr, stream=stream or self._main_hp, **kw):
+                res = fn()
+            counts[key] = _native.STATS.launches - before
+            _native.STATS.launches = before
+            graphs[key] = gr
+            return res
+
+        # (Capturing NCCL's collectives into ONE graph with both halves was measured at N=2: no faster than replays
+        # with the collectives launched in between, and the process hung in NCCL teardown.)
+        for p in (0, 1):
+            capture(("S", p), lambda: body_sample(p))
+            if not dp:
+                outs[p] = capture(("G", p), lambda: body_step(p, True))
+                outs[("N", p)] = capture(("GN", p), lambda: body_step(p, False))
+            else:
+                loss, pred, y = capture(("A1", p), lambda: body_a1(p))
+                outs[p] = (loss.detach(), pred, y)
+                # the backward pass of A1's autograd graph: same memory pool
+                capture(("A2", p), lambda: body_a2(loss), pool=graphs[("A1", p)].pool())
+                del loss
+                capture(("B1", p), lambda: body_b1(p, True), stream=self._side_apply)
+                capture(("B1N", p), lambda: body_b1(p, False), stream=self._side_apply)
+        if dp:
+            capture(("B2", 0), body_b2)
+        self._graphs, self._graph_kernel_counts, self._static_out = graphs, counts, outs
+        self.graph_kernels = counts.get(("G", 0), 0) or sum(counts.get((k, 0), 0) for k in ("A1", "A2", "B1", "B2"))
 
     # ---- checkpoint / resume (the reference checkpoints the model only; the bandit state is part of training) ----
     def state_dict(self):
         """Everything a resumed run needs to continue the same trajectory: parameters, Adam moments and step,
         lr schedule, the sampler's EXP3 weights / L1 norms / Philox step, and the step counters."""
         self.flush()
+        self._drop_prefetch()       # blocks sampled ahead are re-drawn after a restore (same Philox step, same weights)
         smp = self.dm.sampler
         return {"model": {k: v.detach().clone() for k, v in self.model.state_dict().items()},
                 "optimizer": self.optimizer.state_dict(), "scheduler": self.scheduler.state_dict(),
                 "sampler": smp.state_dict() if getattr(smp, "_w_csc", None) is not None else {"step": smp.step},
                 "num_steps": self.num_steps, "cum_nodes": list(self.cum_sampled_nodes),
-                "cum_edges": list(self.cum_sampled_edges), "epoch": self.dm._epoch}
+                "cum_edges": list(self.cum_sampled_edges), "epoch": self.dm._epoch,
+                "drop_step": (int(self.model._drop_step_t.item())
+                              if getattr(self.model, "_drop_step_t", None) is not None else 0)}
 
     def load_state_dict(self, sd):
         """In place: parameters, moments and bandit weights keep their addresses, so a captured step graph
         stays valid; the device-side Philox step follows at the next step."""
         self.flush()
+        self._drop_prefetch()
         smp = self.dm.sampler
         self.model.load_state_dict(sd["model"])
         self.optimizer.load_state_dict(sd["optimizer"])
@@ -681,6 +771,10 @@ class Trainer:
         self.num_steps = int(sd["num_steps"])
         self.cum_sampled_nodes, self.cum_sampled_edges = list(sd["cum_nodes"]), list(sd["cum_edges"])
         self.dm._epoch = int(sd["epoch"])
+        if getattr(self.model, "_drop_step_t", None) is not None:      # dropout's Philox step (eager and captured path)
+            self.model._drop_step_t.fill_(int(sd.get("drop_step", 0)))
+        elif hasattr(self.model, "_drop_step") and next(self.model.parameters()).is_cuda:
+            self.model._drop_step(next(self.model.parameters()).device).fill_(int(sd.get("drop_step", 0)))
         self._grads_clean = False
         self._dev_step_mirror = None
 
@@ -697,6 +791,14 @@ class Trainer:
             total += y.shape[0]
         self.model.train()
         return correct / max(total, 1)
+
+
+class _PoolSet:
+    """One of the two buffer sets of the pipelined static step: per-layer capacity pools, the capacity-padded
+    blocks over them, the seed buffer and the first of its counter blocks in the sampler workspace."""
+
+    def __init__(self, pools, padded, seeds, ctr_base):
+        self.pools, self.padded, self.seeds, self.ctr_base = pools, padded, seeds, ctr_base
 
 
 class _CounterBlocks(list):

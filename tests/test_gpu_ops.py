@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 from oracle import model as omodel
 from oracle import samplers as osamp
-from tests.util import blocks_as, copy_params, philox_uniform_fn, random_graph
+from tests.util import blocks_as, blocks_clone, close_grad, copy_params, philox_uniform_fn, random_graph
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
@@ -105,7 +105,10 @@ def test_sage_gcn_models_forward_backward(native_lib, kind):
     # the oracle runs in float64 (exact-arithmetic reference): the error measured is the device's own fp32 rounding
     omod = (omodel.SAGE if kind == "sage" else omodel.GCN)(in_f, hid, ncls, 3, F.relu, 0.0)
     copy_params(omod, dmodel, torch.float64)
+    omod32 = (omodel.SAGE if kind == "sage" else omodel.GCN)(in_f, hid, ncls, 3, F.relu, 0.0)
+    copy_params(omod32, dmodel)
     omod = omod.double()
+    ob32 = blocks_clone(ob, torch.float32)
     blocks_as(ob, torch.float64)
     xd = feats.to(gd.device)[db[0].srcdata["_ID"].long()]
     xo = feats[ob[0].srcdata["_ID"].long()].double()
@@ -117,8 +120,10 @@ def test_sage_gcn_models_forward_backward(native_lib, kind):
     labels = torch.randint(0, ncls, (yo.shape[0],))
     F.cross_entropy(yd, labels.to(gd.device)).backward()
     F.cross_entropy(yo, labels).backward()
+    F.cross_entropy(omod32(ob32, feats[ob[0].srcdata["_ID"].long()]), labels).backward()
+    g32 = dict(omod32.named_parameters())
     for (n, p), (_, q) in zip(dmodel.named_parameters(), omod.named_parameters()):
-        _close(p.grad, q.grad, rtol=RTOL, what=f"{kind} grad {n}")
+        close_grad(p.grad, q.grad, g32[n].grad, RTOL, f"ops/{kind} grad {n}")
 
 
 @pytest.mark.parametrize("residual", [False, True])
@@ -132,7 +137,10 @@ def test_gatv2_model_forward_backward(native_lib, residual):
     dmodel = M.GATv2(*args).to(gd.device)
     omod = omodel.GATv2(*args)
     copy_params(omod, dmodel, torch.float64)
+    omod32 = omodel.GATv2(*args)
+    copy_params(omod32, dmodel)
     omod = omod.double()                       # float64 oracle: the exact-arithmetic reference
+    ob32 = blocks_clone(ob, torch.float32)
     blocks_as(ob, torch.float64)
     yd = dmodel(db, feats.to(gd.device)[db[0].srcdata["_ID"].long()])
     yo = omod(ob, feats[ob[0].srcdata["_ID"].long()].double())
@@ -143,9 +151,10 @@ def test_gatv2_model_forward_backward(native_lib, residual):
     labels = torch.randint(0, ncls, (yo.shape[0],))
     F.cross_entropy(yd, labels.to(gd.device)).backward()
     F.cross_entropy(yo, labels).backward()
-    dgrads = dict(dmodel.named_parameters())
+    F.cross_entropy(omod32(ob32, feats[ob[0].srcdata["_ID"].long()]), labels).backward()
+    dgrads, g32 = dict(dmodel.named_parameters()), dict(omod32.named_parameters())
     for n, q in omod.named_parameters():
-        _close(dgrads[n].grad, q.grad, rtol=RTOL, what=f"gat grad {n}")
+        close_grad(dgrads[n].grad, q.grad, g32[n].grad, RTOL, f"ops/gat(residual={residual}) grad {n}")
 
 
 def test_gatv2_attention_dropout_mask(native_lib):
@@ -241,6 +250,39 @@ def test_static_graph_step_matches_eager(native_lib, kind, sampler):
         torch.testing.assert_close(w_static, w_eager, rtol=2e-3 if kind == "gat" else 1e-4, atol=0)
 
 
+@pytest.mark.parametrize("kind,sampler", [("sage", "poisson-bandit"), ("gat", "poisson-bandit"), ("gcn", "ladies")])
+def test_lookahead_sampling_keeps_the_trajectory(native_lib, kind, sampler):
+    """``training_step(seeds, next_seeds)``: the next batch's blocks are sampled into the second pool set in the shadow
+    of this step's backward pass (after this step's exp3) — same losses and bandit weights as the step that samples
+    its own blocks first, including across an eager step in between (ragged batch) and an unannounced batch."""
+    from bliss_gnn_b200.graph import synthetic_graph
+    from bliss_gnn_b200.train import DataModule, Trainer, build_model
+    dev = _dev()
+    g = synthetic_graph("flickr", seed=0, scale=0.05).to(dev)
+    res = {}
+    for ahead in (False, True):
+        dm = DataModule("flickr", fan_out=[128, 64, 32], eta=0.1, device=dev, batch_size=32, sampler=sampler,
+                        model=kind, seed=0, graph=g)
+        torch.manual_seed(3)
+        model = build_model(kind, dm.in_feats, 64, dm.n_classes, 3, dropout=0.0, attn_dropout=0.0,
+                            faithful_gcn_quirk=False).to(dev)
+        tr = Trainer(dm, model, 0.002, static_graph=True, eager_warmup=3)
+        batches = [b for _, b in zip(range(16), dm.train_batches())]
+        batches[9] = batches[9][:20]                       # a ragged batch: runs eagerly, the prefetch must be dropped
+        losses = []
+        for i, b in enumerate(batches):
+            nxt = batches[i + 1] if (ahead and i + 1 < len(batches) and i != 12) else None    # 12 -> 13 unannounced
+            losses.append(float(tr.training_step(b, nxt).item()))
+        tr.flush()
+        assert tr.num_steps == len(batches), tr.num_steps
+        res[ahead] = (losses, dm.sampler.exp3_weights.clone() if "bandit" in sampler else None, dm.sampler.step)
+    assert res[True][2] == res[False][2] == 16, "every sampling must consume exactly one Philox step"
+    for a, b in zip(res[False][0], res[True][0]):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (res[False][0], res[True][0])
+    if res[True][1] is not None:
+        torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-6, atol=0)
+
+
 def test_data_parallel_graph_path_on_one_rank(native_lib, monkeypatch):
     """The data-parallel step (graph A: sample+fwd+bwd+reward emit -> NCCL all-reduce / all-gather ->
     graph B: Adam + packed apply) forced on a 1-rank NCCL group follows the single-graph trajectory."""
@@ -262,7 +304,9 @@ def test_data_parallel_graph_path_on_one_rank(native_lib, monkeypatch):
             model = build_model("sage", dm.in_feats, 64, dm.n_classes, 3, dropout=0.0).to(dev)
             tr = Trainer(dm, model, 0.002, process_group=dist.group.WORLD if dp else None, static_graph=True,
                          eager_warmup=3)
-            losses = [float(tr.training_step(s).item()) for _, s in zip(range(12), dm.train_batches())]
+            batches = [b for _, b in zip(range(12), dm.train_batches())]
+            losses = [float(tr.training_step(b, batches[i + 1] if dp and i + 1 < 12 else None).item())
+                      for i, b in enumerate(batches)]       # the data-parallel run also samples one batch ahead
             assert tr.graph_replays >= 7 and (tr._exchange is not None) == dp
             res[dp] = (losses, dm.sampler.exp3_weights.clone())
         for a, b in zip(res[False][0], res[True][0]):
