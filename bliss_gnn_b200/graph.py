@@ -302,13 +302,22 @@ def toy_graph() -> Graph:
 
 
 def synthetic_graph(name: str, seed: int = 0, device="cpu", scale: float = 1.0,
-                    feat_dtype=torch.float32, with_features: bool = True) -> Graph:
+                    feat_dtype=torch.float32, with_features: bool = True, planted: bool = False,
+                    homophily: float = 0.7, signal: float = 0.35, label_noise: float = 0.1) -> Graph:
     """Chung-Lu power-law graph of a named dataset shape.
 
     Expected degree ∝ ``(rank+10)^(-1/(γ-1))`` capped at the real maximum degree,
     symmetrised, de-duplicated, self-loops removed then one added per node, node ids
     randomly permuted so degree is not correlated with id.  ``scale`` < 1 shrinks |V| and
     |E| together (tests).  Everything is seeded; generation runs on ``device``.
+
+    ``planted=False``: N(0,1) features and uniform labels — throughput only, nothing to learn.
+    ``planted=True``: a planted partition with the same degree sequence, for accuracy runs (the reference measures
+    test micro-F1, ``train_lightning.py:686-705``): every node belongs to one of C communities (C = classes;
+    16 for multi-label shapes), a fraction ``homophily`` of the edges is re-pointed to an equal-degree-rank node of
+    the source's own community, features are ``signal * mu[community] + N(0,1)`` (a weak per-node signal that
+    neighbourhood aggregation denoises) and labels are the community (multi-label: the community's random 10 %
+    pattern) with ``label_noise`` of them re-drawn at random.
     """
     shape = DATASET_SHAPES[name]
     dev = torch.device(device)
@@ -331,6 +340,7 @@ def synthetic_graph(name: str, seed: int = 0, device="cpu", scale: float = 1.0,
     cdf = torch.cumsum(wts, 0)
     cdf = cdf / cdf[-1]
 
+    n_comm = (16 if shape["multilabel"] else shape["classes"])      # communities of the planted partition, by degree rank
     n_pairs_target = E_target // 2
     keys = torch.empty(0, dtype=torch.int64, device=dev)
     draw = int(n_pairs_target * 1.08) + 16
@@ -339,6 +349,9 @@ def synthetic_graph(name: str, seed: int = 0, device="cpu", scale: float = 1.0,
         v = torch.searchsorted(cdf, torch.rand(draw, generator=gen, device=dev, dtype=torch.float64))
         u.clamp_(max=V - 1)
         v.clamp_(max=V - 1)
+        if planted:     # re-point to the node of u's community with (nearly) the same degree rank
+            same = torch.rand(draw, generator=gen, device=dev) < homophily
+            v = torch.where(same, ((v // n_comm) * n_comm + (u % n_comm)).clamp_(max=V - 1), v)
         ok = u != v
         lo, hi = torch.minimum(u, v)[ok], torch.maximum(u, v)[ok]
         keys = torch.unique(torch.cat([keys, lo * V + hi]))
@@ -357,13 +370,26 @@ def synthetic_graph(name: str, seed: int = 0, device="cpu", scale: float = 1.0,
     g = add_self_loops_and_build(src, dst, V)
     del src, dst
 
+    C = shape["classes"]
+    comm = torch.empty(V, dtype=torch.int64, device=dev)
+    comm[perm] = torch.arange(V, device=dev) % n_comm                # community of every node id (rank -> id by perm)
     if with_features:
         F = shape["feats"]
-        g.ndata["features"] = torch.randn(V, F, generator=gen, device=dev,
-                                          dtype=torch.float32).to(feat_dtype)
-    C = shape["classes"]
+        feats = torch.randn(V, F, generator=gen, device=dev, dtype=torch.float32)
+        if planted:
+            mu = torch.randn(n_comm, F, generator=gen, device=dev, dtype=torch.float32)
+            feats += signal * mu[comm]
+        g.ndata["features"] = feats.to(feat_dtype)
     if shape["multilabel"]:
-        g.ndata["labels"] = (torch.rand(V, C, generator=gen, device=dev) < 0.1).to(torch.float32)
+        if planted:
+            pattern = (torch.rand(n_comm, C, generator=gen, device=dev) < 0.1)
+            flip = torch.rand(V, C, generator=gen, device=dev) < label_noise * 0.1
+            g.ndata["labels"] = (pattern[comm] ^ flip).to(torch.float32)
+        else:
+            g.ndata["labels"] = (torch.rand(V, C, generator=gen, device=dev) < 0.1).to(torch.float32)
+    elif planted:
+        noisy = torch.rand(V, generator=gen, device=dev) < label_noise
+        g.ndata["labels"] = torch.where(noisy, torch.randint(0, C, (V,), generator=gen, device=dev), comm)
     else:
         g.ndata["labels"] = torch.randint(0, C, (V,), generator=gen, device=dev)
     sp = shape["split"]
@@ -385,24 +411,33 @@ def synthetic_graph(name: str, seed: int = 0, device="cpu", scale: float = 1.0,
     return g
 
 
-def load_dataset(dataset_name: str, device="cpu", seed: int = 0):
-    """``load_graph.load_dataset`` signature (``load_graph.py:65-80``) over synthetic shapes.
+def load_dataset(dataset_name: str, device="cpu", seed: int = 0, root: Optional[str] = None):
+    """``load_graph.load_dataset`` (``load_graph.py:65-80``): ``(g, n_classes, multilabel)``.
 
-    ``toy`` is the reference's fixture; ``<name>`` or ``synthetic:<name>[:scale]`` builds the
-    Chung-Lu graph of that dataset's shape (no network for the real files).  The returned
-    graph has NOT had self-loops normalised yet only for ``toy`` — callers run
-    :func:`add_self_loops_and_build` semantics through the DataModule like the reference.
+    * ``toy`` — the reference's fixture (``load_graph.py:91-119``).
+    * ``cora | citeseer | pubmed | reddit | yelp | flickr | ogbn-*`` — the REAL dataset, read from local raw files
+      under ``root`` / ``$BLISS_DATA`` by :mod:`bliss_gnn_b200.datasets` (the reference downloads them through
+      DGL / OGB; there is no network here).  Missing files raise: a real name is never silently replaced by random data.
+    * ``synthetic:<name>[:scale][:planted]`` — a Chung-Lu graph of that dataset's shape, stated
+      explicitly; ``planted`` gives it learnable labels (see :func:`synthetic_graph`).
     """
     name = dataset_name
-    scale = 1.0
     if name.startswith("synthetic:"):
         parts = name.split(":")
-        name = parts[1]
-        if len(parts) > 2:
-            scale = float(parts[2])
+        name, scale, planted = parts[1], 1.0, False
+        for extra in parts[2:]:
+            if extra == "planted":
+                planted = True
+            else:
+                scale = float(extra)
+        if name not in DATASET_SHAPES:
+            raise ValueError(f"unknown dataset shape '{name}'")
+        g = synthetic_graph(name, seed=seed, device=device, scale=scale, planted=planted)
+        return g, g.n_classes, g.multilabel
     if name == "toy":
         return toy_graph().to(device), 2, False
-    if name not in DATASET_SHAPES:
-        raise ValueError("unknown dataset")
-    g = synthetic_graph(name, seed=seed, device=device, scale=scale)
-    return g, g.n_classes, g.multilabel
+    from .datasets import REAL_DATASETS, load_real_dataset
+    if name not in REAL_DATASETS:
+        raise ValueError("unknown dataset")                                      # load_graph.py:77-78
+    g, n_classes, multilabel = load_real_dataset(name, root)
+    return g.to(device), n_classes, multilabel

@@ -399,6 +399,16 @@ class Trainer:
             self._max_edges[l] = max(self._max_edges[l], b.num_edges())
         return self._eager_rest(mfgs)
 
+    def set_batch_size(self, batch_size: int):
+        """``--vertex-limit`` changes the batch size between epochs (``train_lightning.py:480-485``): the capacity pools
+        are sized by the batch, so they are re-sized from fresh eager steps and the step graphs re-captured."""
+        self.flush()
+        self._drop_prefetch()
+        self.dm.batch_size = int(batch_size)
+        self._sets, self._graphs, self._graph = None, {}, None
+        self._pools = self._padded = None
+        self._sizing_steps, self._max_src, self._max_edges = 0, None, None
+
     def _drop_prefetch(self):
         """Forget the blocks sampled ahead for a batch that is not going to be trained on next (eager step in
         between, re-sized pools, checkpoint): their Philox step is given back, so the next sampling draws exactly
@@ -781,16 +791,30 @@ class Trainer:
     @torch.no_grad()
     def validate(self) -> float:
         """Per-epoch validation with the same stochastic sampler (``train_lightning.py:179-203,410-422``)."""
+        self.flush()
+        self._drop_prefetch()
+        smp = self.dm.sampler
+        seed = smp.rng_seed
+        smp.rng_seed = seed & 0xFFFFFFFF          # every rank validates with rank 0's draws: one val_acc, one stop decision
         self.model.eval()
-        correct, total = 0.0, 0
-        for seeds in self.dm.val_batches():
-            _, _, mfgs = self.dm.sampler.sample_blocks(self.dm.g, seeds)
-            pred = self.model(mfgs, mfgs[0].srcdata["features"])
-            y = mfgs[-1].dstdata["labels"]
-            correct += micro_f1(pred, y, self.dm.multilabel) * y.shape[0]
-            total += y.shape[0]
-        self.model.train()
-        return correct / max(total, 1)
+        tp = fp_fn = 0.0
+        try:
+            for seeds in self.dm.val_batches():
+                _, _, mfgs = smp.sample_blocks(self.dm.g, seeds)
+                pred = self.model(mfgs, mfgs[0].srcdata["features"])
+                y = mfgs[-1].dstdata["labels"]
+                # micro-F1 accumulated over the epoch like torchmetrics (:68-72,179-203): counts, not a mean of batch scores
+                if self.dm.multilabel:
+                    p, t = torch.sigmoid(pred) > 0.5, y > 0.5
+                    tp += float((p & t).sum())
+                    fp_fn += float(p.sum() + t.sum())
+                else:
+                    tp += float((pred.argmax(1) == y).sum())
+                    fp_fn += 2.0 * y.shape[0]
+        finally:
+            smp.rng_seed = seed
+            self.model.train()
+        return 2.0 * tp / max(fp_fn, 1.0)
 
 
 class _PoolSet:
@@ -865,7 +889,70 @@ def build_argparser() -> argparse.ArgumentParser:
     return ap
 
 
+class BatchSizeController:
+    """``BatchSizeCallback`` (``train_lightning.py:425-486``) without Lightning: running mean / variance of the
+    number of input nodes per batch (Welford, ``:437-451``); at the end of an epoch, when ``--vertex-limit`` is set and
+    the mean is off the limit by more than ``factor`` standard errors, the batch size is rescaled by
+    ``limit / mean`` (``:473-486``)."""
+
+    def __init__(self, limit, factor=3):
+        self.limit, self.factor = limit, factor
+        self.clear()
+
+    def clear(self):
+        self.n, self.m, self.s = 0, 0.0, 0.0
+
+    def push(self, x):
+        self.n += 1
+        m = self.m
+        self.m += (x - m) / self.n
+        self.s += (x - m) * (x - self.m)
+
+    @property
+    def var(self):
+        return self.s / (self.n - 1)
+
+    @property
+    def std(self):
+        return math.sqrt(self.var)
+
+    def on_train_epoch_end(self, batch_size: int) -> int:
+        """The batch size of the next epoch (unchanged unless the limit test fires)."""
+        if self.limit > 0 and self.n >= 2 and abs(self.limit - self.m) * self.n >= self.std * self.factor:
+            batch_size = max(1, int(batch_size * self.limit / self.m))
+            self.clear()
+        return batch_size
+
+
+class EarlyStopping:
+    """Lightning ``EarlyStopping(monitor='val_acc', mode='max', stopping_threshold, patience)`` as the reference
+    configures it (``train_lightning.py:627-634``): stop once the metric EXCEEDS the threshold, or after ``patience``
+    validation checks without a new best."""
+
+    def __init__(self, stopping_threshold, patience):
+        self.threshold, self.patience = stopping_threshold, patience
+        self.best, self.wait = -float("inf"), 0
+
+    def check(self, value: float) -> bool:
+        if value > self.best:
+            self.best, self.wait = value, 0
+        else:
+            self.wait += 1
+        return (self.threshold is not None and value > self.threshold) or self.wait >= self.patience
+
+
+_NO_EFFECT_FLAGS = {   # accepted for command-line compatibility with the reference, inert here — said once, loudly
+    "data_cpu": "the graph and its features are resident in HBM (the hot path has no CPU path)",
+    "use_uva": "the graph and its features are resident in HBM: nothing to address through UVA",
+    "cache_size": "no host-side feature store, hence no GPU feature cache",
+    "num_workers": "sampling runs on the GPU inside the step graph: there are no sampler worker processes",
+    "allow_zero_in_degree": "parsed and unused by the reference as well (train_lightning.py:510-511)",
+}
+
+
 def main(argv=None):
+    import json
+    import sys
     args = build_argparser().parse_args(argv)
     if args.gpu < 0 or not torch.cuda.is_available():
         raise SystemExit("this build runs the BLISS hot path on a CUDA device only (--gpu >= 0); "
@@ -874,12 +961,19 @@ def main(argv=None):
         torch.set_float32_matmul_precision(args.precision)                       # :554-555
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", args.gpu))
+    defaults = build_argparser().parse_args([])
+    for flag, why in _NO_EFFECT_FLAGS.items():
+        if rank == 0 and getattr(args, flag) != getattr(defaults, flag):
+            print(f"warning: --{flag.replace('_', '-')} has no effect in this build: {why}", file=sys.stderr)
     pg = None
     if world > 1:
         torch.distributed.init_process_group("nccl")
         pg = torch.distributed.group.WORLD
     device = torch.device(f"cuda:{local}")
     torch.cuda.set_device(device)
+    subdir = "paper_{}_{}_{}_{}_steps_{}_bs_{}_layers_{}_lr_{}_eta_{}".format(       # :636-646
+        args.model, args.dataset.replace(":", "-"), args.sampler, args.importance_sampling, args.num_steps, args.batch_size,
+        args.num_layers, args.lr, args.eta)
     results = []
     for run in range(args.k_runs):                                               # :562
         if rank == 0:
@@ -892,34 +986,86 @@ def main(argv=None):
         model = build_model(args.model, dm.in_feats, args.num_hidden, dm.n_classes, args.num_layers, args.dropout,
                             args.num_in_heads, args.num_out_heads, args.attn_dropout, args.negative_slope,
                             args.residual).to(device)
-        tr = Trainer(dm, model, args.lr, pg, static_graph=True)     # whole-step CUDA graph (ragged batches run eagerly)
-        step, epoch, best_val, done = 0, 0, -1.0, False
+        tr = Trainer(dm, model, args.lr, pg, static_graph=True)     # whole-step CUDA graphs (ragged batches run eagerly)
+        logdir = None
+        if rank == 0:                                               # TensorBoardLogger(logdir, name=subdir) -> version_k
+            base = os.path.join(args.logdir, subdir)
+            os.makedirs(base, exist_ok=True)
+            vers = [int(d.split("_")[-1]) for d in os.listdir(base) if d.startswith("version_")]
+            logdir = os.path.join(base, f"version_{max(vers) + 1 if vers else 0}")
+            os.makedirs(os.path.join(logdir, "checkpoints"), exist_ok=True)
+            json.dump(vars(args), open(os.path.join(logdir, "hparams.json"), "w"), indent=1)
+        log = open(os.path.join(logdir, "metrics.jsonl"), "w") if logdir else None
+
+        def emit(**kw):
+            if log:
+                log.write(json.dumps(kw) + "\n")
+                log.flush()
+
+        stopper = EarlyStopping(args.val_acc_target, args.early_stopping_patience)
+        limiter = BatchSizeController(args.vertex_limit)
+        best_ckpt, best_val = None, -float("inf")
+        step, epoch, done = 0, 0, False
         t_prev = time.time()
         while not done:
-            for seeds in dm.train_batches():
-                loss = tr.training_step(seeds)
+            batches = list(dm.train_batches())
+            if not batches:
+                raise SystemExit(f"no full training batch: {dm.train_nid.numel()} training nodes, batch size {dm.batch_size}")
+            for i, seeds in enumerate(batches):
+                # the next batch of the epoch is announced: its blocks are sampled beside this step's backward pass
+                loss = tr.training_step(seeds, batches[i + 1] if i + 1 < len(batches) else None)
                 step += 1
+                if tr.last_blocks is not None:
+                    limiter.push(tr.last_blocks[0].num_src_nodes())              # :464 (one step late when pipelined)
                 if rank == 0 and (step % 50 == 0 or step == 1):
                     acc = micro_f1(tr.last_pred.detach(), tr.last_labels, dm.multilabel)
                     t = time.time()
-                    edges = sum(tr.num_sampled_edges(i) for i in range(len(tr.cum_sampled_edges)))
+                    edges = sum(tr.num_sampled_edges(i_) for i_ in range(len(tr.cum_sampled_edges)))
                     print(f"step {step} loss {loss.item():.4f} train_acc {acc:.4f} iter_time {(t - t_prev):.4f} "
                           f"num_edges {edges:.0f}")
+                    emit(step=step, train_loss=float(loss.item()), train_acc=acc, num_edges=edges)
                     t_prev = t
                 if 0 < args.num_steps <= step:
                     done = True
                     break
             epoch += 1
-            tr.scheduler.step()
+            tr.scheduler.step()                                                  # StepLR per epoch (:205-216)
+            new_bs = limiter.on_train_epoch_end(dm.batch_size)                   # --vertex-limit (:473-486)
+            if new_bs != dm.batch_size:
+                if rank == 0:
+                    print(f"epoch {epoch}: vertex limit {args.vertex_limit}: batch size {dm.batch_size} -> {new_bs}")
+                tr.set_batch_size(new_bs)
             if dm.val_nid.numel():
                 val = tr.validate()
-                best_val = max(best_val, val)
+                stop = stopper.check(val)
+                if world > 1:     # every rank validated the same batches with the same draws; agree on the decision anyway
+                    flag = torch.tensor([1.0 if stop else 0.0, val], device=device)
+                    torch.distributed.broadcast(flag, src=0, group=pg)
+                    stop, val = bool(flag[0].item() > 0), float(flag[1].item())
                 if rank == 0:
                     print(f"epoch {epoch} val_acc {val:.4f}")
-                if val >= args.val_acc_target and step >= args.min_steps:       # EarlyStopping threshold :627-634
+                    emit(epoch=epoch, step=step, val_acc=val)
+                if val > best_val:                       # ModelCheckpoint(monitor='val_acc', save_top_k=1, mode='max') :622-625
+                    best_val = val
+                    if not args.disable_checkpoint and rank == 0:
+                        best_ckpt = os.path.join(logdir, "checkpoints", f"epoch={epoch - 1}-step={step}.ckpt")
+                        for old in os.listdir(os.path.dirname(best_ckpt)):
+                            os.remove(os.path.join(os.path.dirname(best_ckpt), old))
+                        torch.save(tr.state_dict(), best_ckpt)
+                if stop and step >= args.min_steps:                              # EarlyStopping :627-634, min_steps :654
                     done = True
             if 0 < args.num_epochs <= epoch:
                 done = True
+        tr.flush()
+        if not args.disable_checkpoint and dm.val_nid.numel():                   # reload the best checkpoint :662-685
+            if world > 1:
+                box = [best_ckpt]
+                torch.distributed.broadcast_object_list(box, src=0, group=pg)
+                best_ckpt = box[0]
+            if best_ckpt is not None:
+                if rank == 0:
+                    print("Evaluating model in", os.path.dirname(os.path.dirname(best_ckpt)))
+                model.load_state_dict(torch.load(best_ckpt, map_location=device)["model"])
         with torch.no_grad():                                                    # :686-705
             pred = model.inference(dm.g, device, 128, args.use_uva, args.num_workers)
             out = {}
@@ -928,7 +1074,14 @@ def main(argv=None):
                     out[split] = micro_f1(pred[nid.long()], dm.g.ndata["labels"][nid.long()], dm.multilabel)
                     if rank == 0:
                         print(f"{split} accuracy: {out[split]}")
+        emit(final=out, steps=step, epochs=epoch)
+        if log:
+            log.close()
         results.append(out)
+    if args.k_runs > 1 and rank == 0:       # the reference reduces the k runs' TensorBoard logs to mean / std (:711-733)
+        for split in results[0]:
+            vals = torch.tensor([r[split] for r in results], dtype=torch.float64)
+            print(f"{split} accuracy over {args.k_runs} runs: mean {vals.mean():.4f} std {vals.std(unbiased=False):.4f}")
     if world > 1:
         torch.distributed.destroy_process_group()
     return results

