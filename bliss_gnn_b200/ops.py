@@ -22,18 +22,26 @@ def _req(t: torch.Tensor, dtype=torch.float32, name="tensor"):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def gather_rows(table: torch.Tensor, nid: torch.Tensor, with_norm: bool = False):
+def gather_rows(table: torch.Tensor, nid: torch.Tensor, with_norm: bool = False, out=None, norm_out=None):
     """``table[nid]`` (lazy DGL frame gather, ``train_lightning.py:138-139``); optionally also the
-    row L2 norms of the gathered rows (``embed_norm`` of layer 0, ``model.py:318``)."""
+    row L2 norms of the gathered rows (``embed_norm`` of layer 0, ``model.py:318``).  ``out`` / ``norm_out``: persistent
+    destination buffers (the pipelined step gathers the next batch's inputs ahead of time)."""
     if table.dtype != torch.float32 or table.dim() != 2:
         # labels / masks / non-fp32 frames: not the hot path, plain indexing
-        out = table[nid.long()]
+        if out is not None:
+            torch.index_select(table, 0, nid.long(), out=out)
+        else:
+            out = table[nid.long()]
         return (out, None) if with_norm else out
     table = _req(table, name="table")
     nid = _req(nid, torch.int32, "nid")
     n, d = nid.numel(), table.shape[1]
-    out = torch.empty((n, d), dtype=torch.float32, device=table.device)
-    norm = torch.empty(n, dtype=torch.float32, device=table.device) if with_norm else None
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=table.device)
+    elif out.shape != (n, d) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("gather_rows: out must be a contiguous float32 [len(nid), dim] tensor")
+    norm = norm_out if norm_out is not None else (
+        torch.empty(n, dtype=torch.float32, device=table.device) if with_norm else None)
     N.call("bliss_gather_rows", N.ptr(table), N.ptr(nid), n, d, N.ptr(out), N.ptr(norm), N.stream())
     return (out, norm) if with_norm else out
 

@@ -277,16 +277,22 @@ class Trainer:
                 pb._transpose = (pool.t_indptr, pool.t_dst, pool.t_perm, pool.t_seg_ptr)
                 pool.padded = pb
                 padded.append(pb)
-            sets.append(_PoolSet(pools, padded, seeds_static, ctr_base=8 * p))
+            pset = _PoolSet(pools, padded, seeds_static, ctr_base=8 * p)
+            feats, labels = g.ndata["features"], g.ndata["labels"]
+            if feats.dtype == torch.float32 and feats.dim() == 2:      # inputs gathered ahead with the blocks
+                pset.x = torch.zeros((pools[0].cap_src, feats.shape[1]), dtype=torch.float32, device=dev)
+                pset.x_norm = torch.zeros(pools[0].cap_src, dtype=torch.float32, device=dev)
+                pset.y = torch.zeros((dm.batch_size,) + tuple(labels.shape[1:]), dtype=labels.dtype, device=dev)
+            sets.append(pset)
         self._sets = sets
         self._pools, self._padded, self._seeds_static = sets[0].pools, sets[0].padded, sets[0].seeds
         self._graph, self._graphs = None, {}
         self._cur, self._next_ready, self._prefetched_seeds = 0, False, None
 
-    def _padded_fwd_bwd(self, step_optimizer: bool, after_forward=None, before_backward=None, pset=None):
+    def _padded_fwd_bwd(self, step_optimizer: bool, after_forward=None, before_backward=None, pset=None, inputs=None):
         """``after_forward`` / ``before_backward``: hooks of the whole-step graph — work that only needs the
         forward pass is forked onto side streams there, work the backward pass needs is joined."""
-        loss, pred, y = self._padded_fwd(pset)
+        loss, pred, y = self._padded_fwd(pset, inputs)
         if after_forward is not None:
             after_forward()
         self._zero_grads()
@@ -298,20 +304,32 @@ class Trainer:
         return loss.detach(), pred, y
 
     @staticmethod
-    def _gather_labels(labels, nid32):
+    def _gather_labels(labels, nid32, out=None):
         """``labels[nid]`` in one launch: int64 class ids ride through the row-gather kernel as 2-float rows
         (torch's index / index_select paths cost 2-3 launches or a slow generic gather here)."""
         if labels.dim() == 1 and labels.dtype == torch.int64 and labels.is_contiguous():
-            out = ops.gather_rows(labels.view(torch.float32).view(-1, 2), nid32)
-            return out.view(torch.int64).view(-1)
+            buf = None if out is None else out.view(torch.float32).view(-1, 2)
+            res = ops.gather_rows(labels.view(torch.float32).view(-1, 2), nid32, out=buf)
+            return res.view(torch.int64).view(-1)
+        if out is not None:
+            return torch.index_select(labels, 0, nid32.long(), out=out)
         return labels[nid32.long()]
 
-    def _padded_fwd(self, pset=None):
+    def _gather_inputs(self, pset, ahead: bool):
+        """Input features (with their row norms: layer 0's embed_norm) and labels of the batch sampled into ``pset``.
+        ``ahead``: into the set's persistent buffers, as the tail of the look-ahead sampling."""
         g = self.dm.g
-        pset = pset or self._sets[0]
+        if ahead and pset.x is not None:
+            ops.gather_rows(g.ndata["features"], pset.pools[0].src_nid, with_norm=True, out=pset.x, norm_out=pset.x_norm)
+            self._gather_labels(g.ndata["labels"], pset.seeds, out=pset.y)
+            return pset.x, pset.x_norm, pset.y
         x, norm = ops.gather_rows(g.ndata["features"], pset.pools[0].src_nid, with_norm=True)
+        return x, norm, self._gather_labels(g.ndata["labels"], pset.seeds)
+
+    def _padded_fwd(self, pset=None, inputs=None):
+        pset = pset or self._sets[0]
+        x, norm, y = inputs if inputs is not None else self._gather_inputs(pset, False)
         x._bliss_row_norm = norm                       # layer 0's embed_norm comes with the gather (model.SAGE/GCN/GATv2)
-        y = self._gather_labels(g.ndata["labels"], pset.seeds)
         pred = self.model(pset.padded, x)
         if pred.shape[0] != self.dm.batch_size:          # (the top layer's capacity is the batch size: usually a no-op)
             pred = pred[: self.dm.batch_size]
@@ -592,9 +610,12 @@ class Trainer:
         if getattr(self, "_side_t", None) is None:
             # the step's main line (forward, backward, Adam) is captured on a high-priority stream; the side branch
             # (bandit update, next batch's sampling, transposes) on normal-priority ones
-            self._side_t, self._side_b, self._side_s = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-            self._main_hp = torch.cuda.Stream(priority=-5)
-            self._side_apply = torch.cuda.Stream()
+            # (BLISS_SAMPLE_PRIO=1 gives the priority to the sampling branch instead)
+            sp = -5 if os.environ.get("BLISS_SAMPLE_PRIO") == "1" else 0
+            self._side_t, self._side_s = torch.cuda.Stream(priority=sp), torch.cuda.Stream(priority=sp)
+            self._side_b = torch.cuda.Stream()
+            self._main_hp = torch.cuda.Stream(priority=0 if sp else -5)
+            self._side_apply = torch.cuda.Stream(priority=sp)
         def clear_events(pset):
             for pb in pset.padded:                # events recorded in one capture must not be waited for in another
                 pb._ready = pb._t_ready = None
@@ -605,6 +626,7 @@ class Trainer:
             cur = torch.cuda.current_stream()
             smp.enqueue_static(g, pset.seeds, pset.pools, self._step_dev, transpose_stream=self._side_t,
                                defer_last_transpose=False, ctr_base=pset.ctr_base)
+            self._gather_inputs(pset, True)       # beside the input layer's fill / transposes (needs its source list only)
             cur.wait_stream(self._side_t)
             self._step_dev.add_(1)
             clear_events(pset)
@@ -613,22 +635,54 @@ class Trainer:
             sample_into(self._sets[p])
 
         def body_step(p, prefetch):               # single rank: the whole step in one graph
+            """forward ─ backward ─ Adam on the main stream.  A layer's bandit update is launched (side_b) as soon as the
+            model has stored what it reads from the forward pass (that layer's embed_norm; a_ij for GAT); the top
+            layer's update and, right behind it, the sampling of the NEXT batch (top layer first) go to side_s — so
+            sampling starts while the last layer's forward pass is still running."""
             pset, other = self._sets[p], self._sets[1 - p]
             clear_events(pset)
             main = torch.cuda.current_stream()
+            inputs = (pset.x, pset.x_norm, pset.y) if pset.x is not None else None
+            fired = []
+
+            def make(l, pb):
+                def hook():
+                    cur = torch.cuda.current_stream()
+                    fired.append(l)
+                    if l < L - 1:
+                        self._side_b.wait_stream(cur)
+                        with torch.cuda.stream(self._side_b):
+                            smp.update_exp3_weights(l, pb, g)
+                    else:                         # the top layer: its update, then the look-ahead sampling
+                        self._side_s.wait_stream(cur)
+                        self._side_s.wait_stream(self._side_b)
+                        with torch.cuda.stream(self._side_s):
+                            smp.update_exp3_weights(l, pb, g)
+                            if prefetch:
+                                sample_into(other)
+                return hook
+
+            key = "a_ij" if smp.model == "gat" else "embed_norm"
+            if bandit:
+                for l, pb in enumerate(pset.padded):
+                    (pb.edata if key == "a_ij" else pb.srcdata).on_set[key] = make(l, pb)
 
             def after_forward():
-                if not (bandit or prefetch):
-                    return
-                self._side_s.wait_stream(main)
-                with torch.cuda.stream(self._side_s):
-                    if bandit:
-                        smp.exp3(pset.padded, g, count_renorm=False)
-                    if prefetch:
+                if bandit:
+                    assert sorted(fired) == list(range(L)), f"bandit update hooks fired for layers {fired}"
+                elif prefetch:
+                    self._side_s.wait_stream(main)
+                    with torch.cuda.stream(self._side_s):
                         sample_into(other)
 
-            loss, pred, y = self._padded_fwd_bwd(True, after_forward=after_forward, pset=pset)
+            try:
+                loss, pred, y = self._padded_fwd_bwd(True, after_forward=after_forward, pset=pset, inputs=inputs)
+            finally:
+                for pb in pset.padded:
+                    pb.srcdata.on_set.pop("embed_norm", None)
+                    pb.edata.on_set.pop("a_ij", None)
             if bandit or prefetch:
+                main.wait_stream(self._side_b)
                 main.wait_stream(self._side_s)
             self._drop_dev.add_(1)
             return loss, pred, y
@@ -649,7 +703,7 @@ class Trainer:
                 for l, pb in enumerate(pset.padded):
                     pb.srcdata.on_set["embed_norm"] = make(l, pb)
             try:
-                loss, pred, y = self._padded_fwd(pset)
+                loss, pred, y = self._padded_fwd(pset, (pset.x, pset.x_norm, pset.y) if pset.x is not None else None)
             finally:
                 for pb in pset.padded:
                     pb.srcdata.on_set.pop("embed_norm", None)
@@ -823,6 +877,7 @@ class _PoolSet:
 
     def __init__(self, pools, padded, seeds, ctr_base):
         self.pools, self.padded, self.seeds, self.ctr_base = pools, padded, seeds, ctr_base
+        self.x = self.x_norm = self.y = None      # input features / their row norms / labels, gathered with the blocks
 
 
 class _CounterBlocks(list):

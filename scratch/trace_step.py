@@ -23,34 +23,37 @@ model = build_model("sage", dm.in_feats, bench.HIDDEN, dm.n_classes, 3, bench.DR
 tr = Trainer(dm, model, bench.LR, None, static_graph=True)
 batches = [b.to(dev) for b in bench.seed_batches_for(g, 0, 1, 64)]
 for i in range(20):
-    tr.training_step(batches[i])
+    tr.training_step(batches[i], batches[i + 1])
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for i in range(20, 26):
-        tr.training_step(batches[i])
+    for i in range(20, 27):
+        tr.training_step(batches[i], batches[i + 1])
     torch.cuda.synchronize()
-ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-ev.sort(key=lambda e: e.time_range.start)
-# split into steps at k_frontier_plan triples: a step starts at every third plan kernel
-starts = [i for i, e in enumerate(ev) if "k_plan_rows" in e.name]
+ev = [e for e in prof.profiler.kineto_results.events() if "CUDA" in str(e.device_type()) or "cuda" in str(e.device_type()).lower()]
+ev = [e for e in ev if e.duration_ns() > 0]
+ev.sort(key=lambda e: e.start_ns())
+streams = {}
+# one step = from one feature gather (first kernel of the forward pass) to the next
+marks = [i for i, e in enumerate(ev) if "k_gather_rows<4>" in e.name()]
 with open(out_path, "w") as f:
-    if len(starts) >= 6:
-        a, b = starts[-6], starts[-3]
+    if len(marks) >= 4:
+        a, b = marks[-3], marks[-2]
         seg = ev[a:b]
-        t0 = seg[0].time_range.start
+        t0 = seg[0].start_ns()
         prev_end = t0
         busy = 0.0
         for e in seg:
-            s, d = e.time_range.start - t0, e.time_range.end - e.time_range.start
-            gap = e.time_range.start - prev_end
+            sid = streams.setdefault(e.device_resource_id(), len(streams))
+            s_, d = (e.start_ns() - t0) / 1e3, e.duration_ns() / 1e3
+            gap = (e.start_ns() - prev_end) / 1e3
             busy += d
-            prev_end = max(prev_end, e.time_range.end)
-            f.write(f"{s:9.1f} {d:8.1f} gap {gap:6.1f}  {e.name[:100]}\n")
-        f.write(f"# step span {ev[b].time_range.start - t0:.1f} us, busy {busy:.1f} us, kernels {len(seg)}\n")
+            prev_end = max(prev_end, e.start_ns() + e.duration_ns())
+            f.write(f"{s_:9.1f} {d:8.1f} gap {gap:6.1f}  s{sid} {e.name()[:96]}\n")
+        f.write(f"# step span {(ev[b].start_ns() - t0) / 1e3:.1f} us, busy {busy:.1f} us, kernels {len(seg)}, streams {len(streams)}\n")
     else:
-        f.write(f"# could not split steps: {len(ev)} device events, {len(starts)} plan kernels\n")
+        f.write(f"# could not split steps: {len(ev)} device events, {len(marks)} marks\n")
         for e in ev[:400]:
-            f.write(f"{e.time_range.start:.1f} {e.time_range.end - e.time_range.start:.1f} {e.name[:100]}\n")
+            f.write(f"{e.start_ns() / 1e3:.1f} {e.duration_ns() / 1e3:.1f} {e.name()[:100]}\n")
 print(open(out_path).read()[-3000:])

@@ -110,8 +110,12 @@ def test_config_full_step_matches_oracle(native_lib, shape, kind, sampler, batch
             dsm.inject_uniforms = {l: u.to(dev) for l, u in draws.per_layer.items()}
         d_in, _, db = dsm.sample_blocks(gd, seeds)
         assert torch.equal(d_in.cpu().long(), o_in), f"{tag}: input nodes of step {step} differ"
+        # step 1 is drawn from the UPDATED bandit weights: structure stays bit-exact; for GAT the values inherit the
+        # conditioned error of the reference's alpha (a sum of signed logits in the denominator, see below): the few
+        # ill-conditioned weights are ~1e-4 apart, and so are the q_ij / W~ of the edges that use them
+        rtol_b = RTOL if (step == 0 or kind != "gat") else 1e-3
         for l, (a, b) in enumerate(zip(db, ob)):
-            st = assert_blocks_equal(a, b, rtol=RTOL)
+            st = assert_blocks_equal(a, b, rtol=rtol_b)
             for k, v in st.items():
                 record(f"{tag}/step{step}/block{l}/{k}", v)
             record(f"{tag}/step{step}/block{l}/sizes", [a.num_dst_nodes(), a.num_src_nodes(), a.num_edges()])
