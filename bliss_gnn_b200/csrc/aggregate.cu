@@ -237,6 +237,150 @@ __global__ void __launch_bounds__(256, 5) k_spmm_seg(const int32_t* __restrict__
   }
 }
 
+// ---- bulk-copy (TMA) variant of the balanced SpMM -------------------------------------------------------
+// Same decomposition as k_spmm_seg (32-edge segments, 8 consecutive segments per CTA round, runs of one row added in
+// shared memory, partials + k_spmm_combine for rows that span several rounds), but the source rows are not gathered
+// through registers: every warp owns a ring of R row slots in shared memory and fetches each source row with ONE
+// cp.async.bulk (1 KB at D = 256) that completes on the slot's mbarrier.  The bytes in flight per SM are then bounded
+// by shared memory (3 CTAs x 8 warps x 8 slots = 192 rows), not by the registers a warp can spend on loads, the load
+// path issues one instruction per row instead of 2 x 32 LDG.128, and the accumulators are all the registers the
+// kernel needs.  Rows must be 16-byte multiples and 16-byte aligned (dim % 4 == 0); dim <= 512.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// arm the slot's barrier with the row's byte count and start the bulk copy global -> shared that completes on it
+__device__ __forceinline__ void bulk_row_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  const uint32_t b = smem_u32(bar);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot's earlier generic-proxy reads precede the async write
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(b)
+               : "memory");
+}
+
+template <int NCH4>   // float4 column chunks per lane: dim <= 128 * NCH4
+__global__ void __launch_bounds__(256, 3) k_spmm_tma(const int32_t* __restrict__ indptr, const int32_t* __restrict__ seg_ptr,
+                                                   const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+                                                   const float* __restrict__ w, const float* __restrict__ sscale,
+                                                   const float* __restrict__ dscale, int agg, const float* __restrict__ x,
+                                                   int n_rows, int dim, float* __restrict__ partial, int64_t item_cap,
+                                                   float* __restrict__ y, int R) {
+  constexpr int TILE = 128 * NCH4;                      // row stride of the partials (== k_spmm_combine<4, NCH4>)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);     // [8 warps][R slots][dim]
+  float* s_part = ring + (size_t)8 * R * dim;           // [8 warps][TILE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 8 * TILE);   // [8 warps][R]
+  __shared__ int s_row[8];
+  const int lane = lane_id(), wid = warp_id();
+  float* my_ring = ring + (size_t)wid * R * dim;
+  uint64_t* my_bars = bars + wid * R;
+  const uint32_t rowbytes = (uint32_t)dim * 4u;
+  if (lane < R) mbar_init(&my_bars[lane], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  uint32_t phase_bits = 0;                              // parity of every slot's next completion
+  const int n_items = seg_ptr[n_rows];
+  const int n_groups = (n_items + 7) >> 3;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int item = grp * 8 + wid;
+    const bool valid = item < n_items;
+    int r = -1, a = 0, b = 0, s0 = 0, nseg = 1;
+    float4 acc[NCH4];
+#pragma unroll
+    for (int ch = 0; ch < NCH4; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      int lo = 0, hi = n_rows - 1;   // row of the item: last r with seg_ptr[r] <= item (warp-uniform search)
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(seg_ptr + mid) <= item) lo = mid; else hi = mid - 1;
+      }
+      r = lo;
+      a = indptr[r];
+      b = indptr[r + 1];
+      s0 = seg_ptr[r];
+      nseg = seg_ptr[r + 1] - s0;
+      const int e_lo = a + (item - s0) * BLISS_SPMM_SEG;
+      const int n = min(BLISS_SPMM_SEG, b - e_lo);      // edges of this segment (may be 0 for an empty row)
+      int my_c = 0;
+      float my_w = 0.0f;
+      if (lane < n) {
+        const int e = e_lo + lane;
+        my_c = __ldg(col + e);
+        my_w = w ? __ldg(w + (perm ? __ldg(perm + e) : e)) : 1.0f;
+        if (sscale) my_w *= __ldg(sscale + my_c);
+        if (lane < R) bulk_row_g2s(my_ring + (size_t)lane * dim, x + (int64_t)my_c * dim, rowbytes, &my_bars[lane]);
+      }
+      for (int j = 0; j < n; ++j) {
+        const int slot = j & (R - 1);
+        mbar_wait(&my_bars[slot], (phase_bits >> slot) & 1u);
+        phase_bits ^= 1u << slot;
+        const float wj = __shfl_sync(0xffffffffu, my_w, j);
+        const float* __restrict__ row = my_ring + (size_t)slot * dim;
+#pragma unroll
+        for (int ch = 0; ch < NCH4; ++ch) {
+          const int c = ch * 128 + lane * 4;
+          if (c < dim) {
+            const float4 v = *reinterpret_cast<const float4*>(row + c);
+            acc[ch].x = fmaf(wj, v.x, acc[ch].x);
+            acc[ch].y = fmaf(wj, v.y, acc[ch].y);
+            acc[ch].z = fmaf(wj, v.z, acc[ch].z);
+            acc[ch].w = fmaf(wj, v.w, acc[ch].w);
+          }
+        }
+        __syncwarp();                                   // every lane has read the slot: it may be refilled
+        if (lane == j + R && lane < n)
+          bulk_row_g2s(my_ring + (size_t)slot * dim, x + (int64_t)my_c * dim, rowbytes, &my_bars[slot]);
+      }
+    }
+    if (lane == 0) s_row[wid] = r;
+#pragma unroll
+    for (int ch = 0; ch < NCH4; ++ch) *reinterpret_cast<float4*>(s_part + wid * TILE + ch * 128 + lane * 4) = acc[ch];
+    __syncthreads();
+    if (valid && (wid == 0 || s_row[wid - 1] != r)) {   // first segment of this row's run in the group
+      int len = 1;
+      while (wid + len < 8 && s_row[wid + len] == r) ++len;
+      for (int k = 1; k < len; ++k) {                    // run total, segment order
+#pragma unroll
+        for (int ch = 0; ch < NCH4; ++ch) {
+          const float4 v = *reinterpret_cast<const float4*>(s_part + (wid + k) * TILE + ch * 128 + lane * 4);
+          acc[ch].x += v.x;
+          acc[ch].y += v.y;
+          acc[ch].z += v.z;
+          acc[ch].w += v.w;
+        }
+      }
+      if (item == s0 && len == nseg) {                   // the whole row lies in this group
+        float sc = dscale ? dscale[r] : 1.0f;
+        if (agg == BLISS_AGG_MEAN) sc = sc / (float)max(b - a, 1);
+        float* __restrict__ yr = y + (int64_t)r * dim;
+#pragma unroll
+        for (int ch = 0; ch < NCH4; ++ch) {
+          const int c = ch * 128 + lane * 4;
+          if (c < dim)
+            *reinterpret_cast<float4*>(yr + c) = make_float4(acc[ch].x * sc, acc[ch].y * sc, acc[ch].z * sc, acc[ch].w * sc);
+        }
+      } else {
+        float* __restrict__ pr = partial + (int64_t)item * TILE;
+#pragma unroll
+        for (int ch = 0; ch < NCH4; ++ch) *reinterpret_cast<float4*>(pr + ch * 128 + lane * 4) = acc[ch];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Rows that span several groups of k_spmm_seg: add the runs' partials in group order.  Runs start
 // at the row's first segment s0 and at every multiple of 8 after it.  One warp per row.
 template <int VEC, int NCH>
@@ -383,6 +527,44 @@ static int launch_spmm(const int32_t* indptr, const int32_t* col, const int32_t*
   return 0;
 }
 
+static bool spmm_tma_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("BLISS_SPMM_TMA");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// bulk-copy SpMM over 32-edge segments (dim % 4 == 0, dim <= 512, 16-byte aligned operands); combine pass as before
+template <int NCH4>
+static int launch_spmm_tma(const int32_t* indptr, const int32_t* col, const int32_t* perm, const float* w,
+                           const float* sscale, const float* dscale, int agg, const float* x, int n_rows, int dim,
+                           const int32_t* seg_ptr, float* partial, int64_t item_cap, float* y, cudaStream_t st) {
+  constexpr int TILE = 128 * NCH4;
+  const int R = (dim <= 256) ? 8 : 4;
+  const size_t smem = (size_t)8 * R * dim * 4 + (size_t)8 * TILE * 4 + (size_t)8 * R * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_spmm_tma<NCH4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int64_t groups = (item_cap + 7) / 8;
+  int blocks = (int)(groups < BLISS_SM_COUNT * 3 ? (groups > 0 ? groups : 1) : BLISS_SM_COUNT * 3);
+  {
+    BLISS_KSCOPE("k_spmm_tma", st);
+    k_spmm_tma<NCH4><<<blocks, 256, smem, st>>>(indptr, seg_ptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, partial,
+                                               item_cap, y, R);
+    BLISS_CHECK_LAUNCH();
+  }
+  dim3 grid_c(blocks_for_rows(n_rows, BLISS_SM_COUNT * 8), 1);
+  BLISS_KSCOPE("k_spmm_combine", st);
+  k_spmm_combine<4, NCH4><<<grid_c, 256, 0, st>>>(indptr, seg_ptr, dscale, agg, n_rows, dim, partial, item_cap, y);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" {
 
 int bliss_gather_rows(const float* table, const int32_t* nid, int64_t n_rows, int32_t dim, float* out,
@@ -426,6 +608,13 @@ int bliss_spmm(const int32_t* indptr, const int32_t* col, const int32_t* perm, c
   if (seg_ptr && (!partial || item_cap <= 0)) return -1;
   cudaStream_t st = (cudaStream_t)stream;
   const bool al16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!seg_ptr || (uintptr_t)partial % 16 == 0);
+  if (seg_ptr && dim % 4 == 0 && al16 && dim <= 512 && spmm_tma_enabled()) {
+    if (dim <= 128)
+      return launch_spmm_tma<1>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, seg_ptr, partial, item_cap, y, st);
+    if (dim <= 256)
+      return launch_spmm_tma<2>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, seg_ptr, partial, item_cap, y, st);
+    return launch_spmm_tma<4>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, seg_ptr, partial, item_cap, y, st);
+  }
   if (dim % 4 == 0 && al16)
     return launch_spmm<4>(indptr, col, perm, w, sscale, dscale, agg, x, n_rows, dim, seg_ptr, partial, item_cap, y, st);
   if (dim % 2 == 0)

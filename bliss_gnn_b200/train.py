@@ -49,10 +49,10 @@ class DataModule:
     def __init__(self, dataset_name, undirected=False, data_cpu=False, use_uva=False, fan_out=(128, 256), eta=0.4,
                  device=torch.device("cpu"), batch_size=64, num_workers=0, sampler="bandit",
                  importance_sampling=1, cache_size=0, num_steps=500, model="sage", seed=0, rank=0, world_size=1,
-                 graph: Optional[Graph] = None, normalize="lazy", pad_features: bool = True):
+                 graph: Optional[Graph] = None, normalize="lazy", pad_features: bool = True, graph_seed: int = 0):
         self.sampler_name, self.num_steps, self.eta = sampler, num_steps, eta
-        if graph is None:
-            g, n_classes, multilabel = load_dataset(dataset_name, device=device, seed=seed)
+        if graph is None:     # (a synthetic graph is the same for every run of --k-runs: runs differ by their RNG streams only)
+            g, n_classes, multilabel = load_dataset(dataset_name, device=device, seed=graph_seed)
         else:
             g, n_classes, multilabel = graph, graph.n_classes, graph.multilabel
         if undirected:                                                           # :337-339
@@ -655,7 +655,8 @@ class Trainer:
                             smp.update_exp3_weights(l, pb, g)
                     else:                         # the top layer: its update, then the look-ahead sampling
                         self._side_s.wait_stream(cur)
-                        self._side_s.wait_stream(self._side_b)
+                        if L > 1:
+                            self._side_s.wait_stream(self._side_b)
                         with torch.cuda.stream(self._side_s):
                             smp.update_exp3_weights(l, pb, g)
                             if prefetch:
@@ -681,8 +682,9 @@ class Trainer:
                 for pb in pset.padded:
                     pb.srcdata.on_set.pop("embed_norm", None)
                     pb.edata.on_set.pop("a_ij", None)
-            if bandit or prefetch:
+            if bandit and L > 1:                  # (a stream that was not forked inside this capture must not be joined)
                 main.wait_stream(self._side_b)
+            if bandit or prefetch:
                 main.wait_stream(self._side_s)
             self._drop_dev.add_(1)
             return loss, pred, y

@@ -219,3 +219,62 @@ class OracleLoop:
             self.smp.exp3(blocks, g)
         self.last_blocks = blocks
         return float(loss.item())
+
+
+def oracle_fit(g_cpu, fan, batch, hidden, n_steps, seed, lr=0.002, dropout=0.1, eta=0.1):
+    """The reference's whole run restated on the CPU oracle (``train_lightning.py:562-705``): training steps with the
+    bandit update after each, StepLR(gamma=0.01, step_size=5) per EPOCH (``:205-216``), validation after every epoch
+    with the same stochastic sampler (``:179-203,410-422``), best-val checkpoint (``:622-625``) reloaded before the
+    layer-wise full-neighbour inference (``model.py:335-383``) and the final micro-F1 (``:686-705``)."""
+    import copy
+    import torch.nn.functional as F
+    from bliss_gnn_b200.train import DataModule
+    from oracle import dglops, model as omodel
+    dm = DataModule("oracle", fan_out=fan, eta=eta, device=torch.device("cpu"), batch_size=batch, sampler="poisson-bandit",
+                    model="sage", seed=seed, graph=g_cpu)
+    torch.manual_seed(seed + 3)
+    feats = g_cpu.ndata["features"]
+    model = omodel.SAGE(feats.shape[1], hidden, g_cpu.n_classes, len(fan), F.relu, dropout)
+    loop = OracleLoop(g_cpu, model, "PoissonBanditLadiesSampler", fan, rng_seed=dm.sampler.rng_seed & 0xFFFFFFFF, eta=eta,
+                      lr=lr)
+    sched = torch.optim.lr_scheduler.StepLR(loop.opt, gamma=0.01, step_size=5)
+    labels = g_cpu.ndata["labels"]
+
+    def validate():
+        model.eval()
+        hit = tot = 0
+        with torch.no_grad():
+            for seeds in dm.val_batches():
+                inp, _, blocks = loop.smp.sample_blocks(g_cpu, seeds.cpu())
+                loop.step += 1
+                pred = model(blocks, feats[inp])
+                hit += int((pred.argmax(1) == labels[seeds.long()]).sum())
+                tot += seeds.numel()
+        model.train()
+        return hit / max(tot, 1)
+
+    best, state, step, done = -1.0, None, 0, False
+    while not done:
+        for seeds in dm.train_batches():
+            loop.training_step(seeds)
+            step += 1
+            if step >= n_steps:
+                done = True
+                break
+        sched.step()
+        val = validate()
+        if val > best:
+            best, state = val, copy.deepcopy(model.state_dict())
+    model.load_state_dict(state)
+    model.eval()
+    src, dst = g_cpu.coo()
+    order = torch.sort(dst, stable=True).indices
+    full = dglops.OBlock(src[order], dst[order], g_cpu.num_nodes(), g_cpu.num_nodes())
+    h = feats
+    with torch.no_grad():
+        for l, layer in enumerate(model.layers):
+            h = layer(full, h)
+            if l < len(model.layers) - 1:
+                h = F.relu(h)
+    test = torch.nonzero(g_cpu.ndata["test_mask"], as_tuple=True)[0]
+    return float((h[test].argmax(1) == labels[test]).float().mean())
