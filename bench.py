@@ -398,7 +398,7 @@ STAGE_OF = {"k_plan_rows": "sampling", "k_plan_scan": "sampling", "k_plan_chunks
             "k_layer_front": "sampling",
             "k_block_count<true>": "block_build", "k_block_count<false>": "block_build", "k_block_index": "block_build",
             "k_block_fill": "block_build", "k_block_finish": "block_build",
-            "k_spmm_seg": "spmm", "k_spmm_combine": "spmm", "k_spmm": "spmm", "k_spmm_tma": "spmm",
+            "k_spmm_seg": "spmm", "k_spmm_item": "spmm", "k_spmm_combine": "spmm", "k_spmm": "spmm", "k_spmm_tma": "spmm",
             "k_gather_rows": "gather", "k_reward_update": "bandit"}
 
 
@@ -432,7 +432,7 @@ def roofline_tables(per_kernel, sizes, n_prof, in_feats, layer_dims, peak, peak_
     its kernels.  A kernel that does its stage's whole work (SpMM, gather, reward update, a fused sampling kernel)
     carries the stage's bytes; kernels that share a stage (the three probability passes re-read the same weights)
     only have a stage-level fraction — dividing one compulsory read among them would be arbitrary."""
-    whole_stage = {"k_spmm_seg": "spmm", "k_spmm_tma": "spmm", "k_spmm": "spmm", "k_gather_rows": "gather",
+    whole_stage = {"k_spmm_seg": "spmm", "k_spmm_item": "spmm", "k_spmm_tma": "spmm", "k_spmm": "spmm", "k_gather_rows": "gather",
                    "k_reward_update": "bandit", "k_layer_front": "sampling"}
     stages, kernels = {}, []
     for name, (calls, ms) in sorted(per_kernel.items(), key=lambda kv: -kv[1][1]):
@@ -495,7 +495,7 @@ def l2_gather_probe(N, device, per_kernel, sizes, layer_dims):
             gbs = n_warps * per_warp * dim * 4 / 1e9 / (e0.elapsed_time(e1) / 1e3)
             best = gbs if best is None else max(best, gbs)
     res = {"peak_gbs": best, "peak_source": "measured in this run: bliss_l2_gather_probe (csrc/aggregate.cu), best of 10"}
-    t = sum(per_kernel.get(k, (0, 0.0))[1] for k in ("k_spmm_seg", "k_spmm_tma"))
+    t = sum(per_kernel.get(k, (0, 0.0))[1] for k in ("k_spmm_seg", "k_spmm_item", "k_spmm_tma"))
     if t > 0:
         gathered = sum(2 * 4.0 * layer_dims[l] * e_b for st in sizes for l, (_, _, _, _, e_b) in enumerate(st))
         res.update({"achieved_gbs": gathered / 1e9 / (t / 1e3), "bytes_per_step": gathered / len(sizes),

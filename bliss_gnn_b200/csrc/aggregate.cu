@@ -70,12 +70,12 @@ __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ t
 // Up to 32 edges [e0, min(b, e0+32)): metadata loaded coalesced, then the source rows are gathered
 // MLP edges at a time with every load issued before the first use (a warp's gathers are a chain of
 // L2 round trips otherwise: ~1 us per 4 edges).
-template <int VEC, int NCH>
+template <int VEC, int NCH, int MLP_OVERRIDE = 0>
 __device__ __forceinline__ void spmm_chunk(float (&acc)[NCH][VEC], int e0, int b, int lane, int c0, int dim,
                                            const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
                                            const float* __restrict__ w, const float* __restrict__ sscale,
                                            const float* __restrict__ x) {
-  constexpr int MLP = (NCH * VEC <= 8) ? 4 : (NCH * VEC <= 16 ? 2 : 1);
+  constexpr int MLP = MLP_OVERRIDE ? MLP_OVERRIDE : ((NCH * VEC <= 8) ? 4 : (NCH * VEC <= 16 ? 2 : 1));
   const int e = e0 + lane;
   int my_c = 0;
   float my_w = 0.0f;
@@ -234,6 +234,124 @@ __global__ void __launch_bounds__(256, 5) k_spmm_seg(const int32_t* __restrict__
       }
     }
     __syncthreads();
+  }
+}
+
+// ---- independent-warp variant of the balanced SpMM ---------------------------------------------------------
+// Every warp walks the 32-edge segments round-robin on its own: no shared memory, no CTA barrier (in k_spmm_seg the
+// eight warps of a group wait for the slowest segment of every round), fewer registers, so more warps are resident
+// and each of them keeps its gathers in flight independently.  A row with a single segment is finished by its warp;
+// every segment of a longer row stores its partial sum (slot = segment index) and k_spmm_combine_items adds a row's
+// partials in segment order — a fixed order, deterministic, no atomics.
+template <int VEC, int NCH, int LB>
+__global__ void __launch_bounds__(256, LB) k_spmm_item(const int32_t* __restrict__ indptr, const int32_t* __restrict__ seg_ptr,
+                                                  const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+                                                  const float* __restrict__ w, const float* __restrict__ sscale,
+                                                  const float* __restrict__ dscale, int agg, const float* __restrict__ x,
+                                                  int n_rows, int dim, float* __restrict__ partial, int64_t item_cap,
+                                                  float* __restrict__ y) {
+  constexpr int TILE = 32 * VEC * NCH;
+  const int lane = lane_id();
+  const int c0 = blockIdx.y * TILE;
+  const int n_items = seg_ptr[n_rows];
+  float* __restrict__ tile_partial = partial + (int64_t)blockIdx.y * item_cap * TILE;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int item = gwarp; item < n_items; item += nwarps) {
+    int lo = 0, hi = n_rows - 1;   // row of the item: last r with seg_ptr[r] <= item (warp-uniform search, L1 resident)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(seg_ptr + mid) <= item) lo = mid; else hi = mid - 1;
+    }
+    const int r = lo;
+    const int a = __ldg(indptr + r), b = __ldg(indptr + r + 1);
+    const int s0 = __ldg(seg_ptr + r), nseg = __ldg(seg_ptr + r + 1) - s0;
+    float acc[NCH][VEC];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.0f;
+    const int e_lo = a + (item - s0) * BLISS_SPMM_SEG;
+    spmm_chunk<VEC, NCH, (LB == 3 && NCH * VEC <= 8) ? 8 : 0>(acc, e_lo, min(b, e_lo + BLISS_SPMM_SEG), lane, c0, dim, col, perm,
+                                                               w, sscale, x);
+    if (nseg == 1) {
+      float sc = dscale ? __ldg(dscale + r) : 1.0f;
+      if (agg == BLISS_AGG_MEAN) sc = sc / (float)max(b - a, 1);
+      float* __restrict__ yr = y + (int64_t)r * dim + c0;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int cc = (ch * 32 + lane) * VEC;
+        if (c0 + cc < dim) {
+          float v[VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) v[i] = acc[ch][i] * sc;
+          vstore<VEC>(yr + cc, v);
+        }
+      }
+    } else {
+      float* __restrict__ pr = tile_partial + (int64_t)item * TILE;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) vstore<VEC>(pr + (ch * 32 + lane) * VEC, acc[ch]);
+    }
+  }
+}
+
+// rows with more than one segment: add the segments' partials in segment order.  One warp per row.
+template <int VEC, int NCH>
+__global__ void __launch_bounds__(256) k_spmm_combine_items(const int32_t* __restrict__ indptr,
+                                                           const int32_t* __restrict__ seg_ptr,
+                                                           const float* __restrict__ dscale, int agg, int n_rows, int dim,
+                                                           const float* __restrict__ partial, int64_t item_cap,
+                                                           float* __restrict__ y) {
+  constexpr int TILE = 32 * VEC * NCH;
+  using T = typename VecT<VEC>::T;
+  const int lane = lane_id();
+  const int c0 = blockIdx.y * TILE;
+  const float* __restrict__ tile_partial = partial + (int64_t)blockIdx.y * item_cap * TILE;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < n_rows; r += nwarps) {
+    const int s0 = seg_ptr[r], s1 = seg_ptr[r + 1];
+    if (s1 - s0 <= 1) continue;   // finished by k_spmm_item
+    float acc[NCH][VEC];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.0f;
+    constexpr int CU = (NCH * VEC <= 8) ? 8 : (NCH * VEC <= 16 ? 4 : 2);   // partials in flight
+    for (int k0 = s0; k0 < s1; k0 += CU) {
+      T pv[CU][NCH];
+#pragma unroll
+      for (int u = 0; u < CU; ++u)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+          if (k0 + u < s1)
+            pv[u][ch] = __ldg(reinterpret_cast<const T*>(tile_partial + (int64_t)(k0 + u) * TILE + (ch * 32 + lane) * VEC));
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        if (k0 + u < s1) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            const float* f = reinterpret_cast<const float*>(&pv[u][ch]);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[ch][i] += f[i];
+          }
+        }
+      }
+    }
+    const int a = indptr[r], b = indptr[r + 1];
+    float sc = dscale ? dscale[r] : 1.0f;
+    if (agg == BLISS_AGG_MEAN) sc = sc / (float)max(b - a, 1);
+    float* __restrict__ yr = y + (int64_t)r * dim + c0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int cc = (ch * 32 + lane) * VEC;
+      if (c0 + cc < dim) {
+        float v[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = acc[ch][i] * sc;
+        vstore<VEC>(yr + cc, v);
+      }
+    }
   }
 }
 
@@ -500,9 +618,36 @@ static int launch_spmm(const int32_t* indptr, const int32_t* col, const int32_t*
   dim3 grid(blocks_for_rows(units, BLISS_SM_COUNT * 8), (dim + tile - 1) / tile);
   dim3 grid_c(blocks_for_rows(n_rows, BLISS_SM_COUNT * 8), (dim + tile - 1) / tile);
   const size_t smem = seg_ptr ? (size_t)8 * tile * sizeof(float) : 0;
+  static int item_mode = -1, item_lb = 4;   // BLISS_SPMM_MODE=group: the 8-segment CTA groups of k_spmm_seg; default: independent warps
+  if (item_mode < 0) {
+    const char* e = getenv("BLISS_SPMM_MODE");
+    item_mode = (e && e[0] == 'g') ? 0 : 1;
+    const char* l = getenv("BLISS_SPMM_LB");      // resident CTAs per SM the register budget is set for (4: no spills)
+    if (l && l[0] == '5') item_lb = 5;
+    if (l && l[0] == '3') item_lb = 3;      // 85 registers: 8 rows in flight per warp
+  }
+  const int64_t cta_cap = (int64_t)BLISS_SM_COUNT * item_lb;
+  dim3 grid_i((unsigned)(cta_cap < (units + 7) / 8 ? cta_cap : ((units + 7) / 8 > 0 ? (units + 7) / 8 : 1)),
+              (dim + tile - 1) / tile);
 #define BLISS_SPMM_CASE(N)                                                                                    \
   case N:                                                                                                     \
-    if (seg_ptr) {                                                                                            \
+    if (seg_ptr && item_mode) {                                                                               \
+      {                                                                                                       \
+        BLISS_KSCOPE("k_spmm_item", st);                                                                      \
+        if (item_lb == 5)                                                                                     \
+          k_spmm_item<VEC, N, 5><<<grid_i, 256, 0, st>>>(indptr, seg_ptr, col, perm, w, sscale, dscale, agg,  \
+                                                         x, n_rows, dim, partial, item_cap, y);               \
+        else if (item_lb == 3)                                                                                \
+          k_spmm_item<VEC, N, 3><<<grid_i, 256, 0, st>>>(indptr, seg_ptr, col, perm, w, sscale, dscale, agg,  \
+                                                         x, n_rows, dim, partial, item_cap, y);               \
+        else                                                                                                  \
+          k_spmm_item<VEC, N, 4><<<grid_i, 256, 0, st>>>(indptr, seg_ptr, col, perm, w, sscale, dscale, agg,  \
+                                                         x, n_rows, dim, partial, item_cap, y);               \
+      }                                                                                                       \
+      BLISS_KSCOPE("k_spmm_combine", st);                                                                     \
+      k_spmm_combine_items<VEC, N><<<grid_c, 256, 0, st>>>(indptr, seg_ptr, dscale, agg, n_rows, dim,        \
+                                                           partial, item_cap, y);                             \
+    } else if (seg_ptr) {                                                                                     \
       {                                                                                                       \
         BLISS_KSCOPE("k_spmm_seg", st);                                                                       \
         k_spmm_seg<VEC, N><<<grid, 256, smem, st>>>(indptr, seg_ptr, col, perm, w, sscale, dscale, agg, x,   \
@@ -530,8 +675,8 @@ static int launch_spmm(const int32_t* indptr, const int32_t* col, const int32_t*
 static bool spmm_tma_enabled() {
   static int on = -1;
   if (on < 0) {
-    const char* e = getenv("BLISS_SPMM_TMA");
-    on = (e && e[0] == '0') ? 0 : 1;
+    const char* e = getenv("BLISS_SPMM_TMA");     // opt-in: measured 2.5x slower than the LDG gather (profiles/r2_spmm_variants.md)
+    on = (e && e[0] == '1') ? 1 : 0;
   }
   return on == 1;
 }

@@ -22,9 +22,9 @@ def timeit(fn, n=30):
         e0.record(); fn(); e1.record(); e1.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     return statistics.median(ts)
-print("BLISS_SPMM_TMA =", os.environ.get("BLISS_SPMM_TMA", "1"))
+print("TMA", os.environ.get("BLISS_SPMM_TMA", "0"), "MODE", os.environ.get("BLISS_SPMM_MODE", "item"), "LB", os.environ.get("BLISS_SPMM_LB", "4"))
 for l, blk in enumerate(blocks):
-    for dim in (256, 128, 64):
+    for dim in (256,):
         x = torch.randn(blk.num_src_nodes(), dim, device=dev)
         gy = torch.randn(blk.num_dst_nodes(), dim, device=dev)
         w = blk.edata["edge_weights"]
