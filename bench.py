@@ -232,12 +232,16 @@ def main():
     device = torch.device(f"cuda:{local}")
     torch.cuda.set_device(device)
     pg = None
+    json_fd = 1
     if world > 1:
-        # NCCL's init lines (rank / nranks / transport of every communicator) go to stderr, stdout stays the one
-        # JSON line: the driver can read the rank count off the run's own log
+        # NCCL's init lines (version, rank / nranks / transport of every communicator) are written to stdout by the
+        # library: file descriptor 1 is pointed at stderr for the run and the ONE JSON line goes to the saved stdout,
+        # so the driver can read the rank count off the run's own log and still parse stdout
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         torch.distributed.init_process_group("nccl", device_id=device)
         pg = torch.distributed.group.WORLD
     torch.set_float32_matmul_precision("medium")      # the reference's --precision default (train_lightning.py:550)
@@ -382,7 +386,8 @@ def main():
                                          f"(oracle port, batch {BATCH}, {threads} threads), timed step by step; "
                                          "value = 1 / median step time"}
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0

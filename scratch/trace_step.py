@@ -13,15 +13,21 @@ from bliss_gnn_b200.train import DataModule, Trainer, build_model  # noqa: E402
 
 out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "trace_step.txt")
 N.build()
-dev = torch.device("cuda:0")
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+dev = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}")
+torch.cuda.set_device(dev)
+pg = None
+if world > 1:       # data-parallel timeline: python -m torch.distributed.run --nproc-per-node N scratch/trace_step.py out.txt
+    torch.distributed.init_process_group("nccl", device_id=dev)
+    pg = torch.distributed.group.WORLD
 torch.set_float32_matmul_precision("medium")
 g = bench.build_graph("reddit", 1.0, dev)
 dm = DataModule("reddit", fan_out=bench.FANOUT, eta=bench.ETA, device=dev, batch_size=bench.BATCH,
-                sampler="poisson-bandit", model="sage", seed=0, graph=g)
+                sampler="poisson-bandit", model="sage", seed=0, rank=rank, world_size=world, graph=g)
 torch.manual_seed(3)
 model = build_model("sage", dm.in_feats, bench.HIDDEN, dm.n_classes, 3, bench.DROPOUT).to(dev)
-tr = Trainer(dm, model, bench.LR, None, static_graph=True)
-batches = [b.to(dev) for b in bench.seed_batches_for(g, 0, 1, 64)]
+tr = Trainer(dm, model, bench.LR, pg, static_graph=True)
+batches = [b.to(dev) for b in bench.seed_batches_for(g, rank, world, 64)]
 for i in range(20):
     tr.training_step(batches[i], batches[i + 1])
 torch.cuda.synchronize()
@@ -37,7 +43,7 @@ ev.sort(key=lambda e: e.start_ns())
 streams = {}
 # one step = from one feature gather (first kernel of the forward pass) to the next
 marks = [i for i, e in enumerate(ev) if "k_gather_rows<4>" in e.name()]
-with open(out_path, "w") as f:
+with open(out_path if rank == 0 else os.devnull, "w") as f:
     if len(marks) >= 4:
         a, b = marks[-3], marks[-2]
         seg = ev[a:b]
@@ -56,4 +62,7 @@ with open(out_path, "w") as f:
         f.write(f"# could not split steps: {len(ev)} device events, {len(marks)} marks\n")
         for e in ev[:400]:
             f.write(f"{e.start_ns() / 1e3:.1f} {e.duration_ns() / 1e3:.1f} {e.name()[:100]}\n")
-print(open(out_path).read()[-3000:])
+if rank == 0:
+    print(open(out_path).read()[-3000:])
+if world > 1:
+    torch.distributed.destroy_process_group()
