@@ -96,6 +96,13 @@ class BlockOut(C.Structure):
                 ("seg_ptr", C.c_void_p), ("inv_deg", C.c_void_p), ("cap_edges", C.c_int64), ("cap_src", C.c_int64), ("pad_src", C.c_int64), ("pad_rows", C.c_int64)]
 
 
+class P2P(C.Structure):
+    _fields_ = [("peer_base", C.c_void_p), ("world", C.c_int32), ("rank", C.c_int32), ("parity_stride", C.c_int64),
+                ("rank_stride", C.c_int64), ("count_off", C.c_int64), ("pos_off", C.c_int64), ("x_off", C.c_int64),
+                ("flags_off", C.c_int64), ("layer", C.c_int32), ("n_layers", C.c_int32), ("step_dev", C.c_void_p),
+                ("done_ctr", C.c_void_p)]
+
+
 _P, _I32, _I64, _U32, _U64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_double
 _GP, _WP, _BP = C.POINTER(Graph), C.POINTER(Workspace), C.POINTER(BlockOut)
 
@@ -125,7 +132,8 @@ PROTOTYPES = {
     "bliss_gatv2_bwd_src": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _P],
     "bliss_gat_alpha_sums": [_P, _P, _P, _I32, _P, _P, _P],
     "bliss_reward_update": [_GP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _I32, _I64,
-                            _P, _P, _P, _P, _P, _P, _P, _P],
+                            _P, _P, _P, _P, _P, _P, _P, C.POINTER(P2P), _P],
+    "bliss_apply_updates_p2p": [C.POINTER(P2P), _I64, _P, _P, _P, _P],
     "bliss_apply_updates": [_P, _P, _I64, _P, _P, _P],
     "bliss_apply_updates_packed": [_P, _I64, _I32, _I64, _I64, _I64, _I64, _P, _P, _P],
     "bliss_l1_norm": [_P, _I64, _P, _P, _P],
@@ -167,7 +175,7 @@ class BlissNativeError(RuntimeError):
 #: kernels each entry point launches (for the ``gpu_launches`` count of bench.py)
 LAUNCHES = {"bliss_frontier_prob": 4, "bliss_sample_layer_front": 11, "bliss_poisson_select": 2, "bliss_frontier_plan": 3, "bliss_sample_layer_back": 2,
             "bliss_select_topk": 3, "bliss_block_transpose": 3, "bliss_l1_norm": 2, "bliss_version": 0,
-            "bliss_adam_step": 2, "bliss_spmm": 2, "bliss_sage_epilogue_bwd": 2,
+            "bliss_adam_step": 2, "bliss_spmm": 2, "bliss_apply_updates_p2p": 2, "bliss_sage_epilogue_bwd": 2,
             "bliss_sage_epilogue_parts": 0, "bliss_xent_mean": 2}
 
 

@@ -4,6 +4,7 @@
 // layer per step in the reference become one pass over the block's edges that reads every
 // operand once and read-modify-writes the CSC-ordered weight in place.
 #include <float.h>
+#include <string.h>
 #include "common.cuh"
 #include "profile.cuh"
 
@@ -67,7 +68,26 @@ struct RewardArgs {
   float* rewards;
   float* x_out;
   double* l1_delta;
+  bliss_p2p p2p;                // peer-memory exchange (world == 0: off)
 };
+
+// ---- peer-memory exchange of the sparse bandit updates (data parallel) -------------------------------------
+// Every rank owns a window in symmetric memory that all ranks can address:
+//   window = [parity 0 | parity 1] x [slot of rank 0 | ... | slot of rank W-1] ++ flags[2][L][W] (uint64)
+// and a slot has the layout of the packed exchange buffer (int64 counts, then per layer int32 pos[cap], fp32 x[cap]).
+// The reward kernel stores every edge's (position, exponent) straight into ITS slot of EVERY rank's window over
+// NVLink (fire-and-forget stores: the "all-gather" is fused into the kernel that produces the data); the last CTA to
+// finish publishes flag = step + 1 in every window.  A consumer polls its own flags (one CTA), then applies the W
+// slots of its own window.  Parity = step & 1: ranks are never two steps apart (the gradient all-reduce of every
+// step is a barrier), so a slot is not overwritten while a slower rank still reads it.
+__device__ __forceinline__ unsigned char* p2p_slot(const bliss_p2p& q, int peer, int parity, int src_rank) {
+  return reinterpret_cast<unsigned char*>(q.peer_base[peer]) + (int64_t)parity * q.parity_stride +
+         (int64_t)src_rank * q.rank_stride;
+}
+__device__ __forceinline__ unsigned long long* p2p_flag(const bliss_p2p& q, int peer, int parity, int layer, int src_rank) {
+  return reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(q.peer_base[peer]) + q.flags_off) +
+         ((int64_t)parity * q.n_layers + layer) * q.world + src_rank;
+}
 
 __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
   __shared__ double s_red[32];
@@ -75,6 +95,11 @@ __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
   double dsum = 0.0;
   const int64_t n_edges = p.n_edges_dev ? min(p.n_edges, *p.n_edges_dev) : p.n_edges;
   if (p.count_out && blockIdx.x == 0 && threadIdx.x == 0) *p.count_out = n_edges;
+  const int W = p.p2p.world;
+  const long long xstep = W ? *p.p2p.step_dev : 0;
+  const int parity = (int)(xstep & 1);
+  if (W && blockIdx.x == 0 && threadIdx.x < W)      // this layer's edge count into my slot of every window
+    *reinterpret_cast<int64_t*>(p2p_slot(p.p2p, threadIdx.x, parity, p.p2p.rank) + p.p2p.count_off) = n_edges;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += stride) {
     const int i = p.edge_dst[e];
     const int u = p.edge_src[e];
@@ -100,6 +125,11 @@ __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
     if (x > 1.0f) x = 1.0f;                                                      // :244
     if (p.x_out) p.x_out[e] = x;
     if (p.pos_out) p.pos_out[e] = (int32_t)pos;
+    for (int r = 0; r < W; ++r) {                   // my slot in rank r's window (r == rank: the local copy)
+      unsigned char* slot = p2p_slot(p.p2p, r, parity, p.p2p.rank);
+      reinterpret_cast<int32_t*>(slot + p.p2p.pos_off)[e] = (int32_t)pos;
+      reinterpret_cast<float*>(slot + p.p2p.x_off)[e] = x;
+    }
     if (p.exp3_w) {
       const float w_old = p.exp3_w[pos];
       const float w_new = __fmul_rn(w_old, expf(x));                             // :246-248
@@ -110,6 +140,72 @@ __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
   if (p.l1_delta) {
     dsum = block_sum(dsum, s_red);
     if (threadIdx.x == 0 && dsum != 0.0) atomicAdd(p.l1_delta, dsum);
+  }
+  if (W) {   // publish: every CTA's stores are ordered before its ticket; the last CTA raises the flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned t = atomicAdd(p.p2p.done_ctr, 1u);
+      if (t == gridDim.x - 1) {
+        *p.p2p.done_ctr = 0u;
+        __threadfence_system();
+        for (int r = 0; r < W; ++r)
+          *reinterpret_cast<volatile unsigned long long*>(p2p_flag(p.p2p, r, parity, p.p2p.layer, p.p2p.rank)) =
+              (unsigned long long)(xstep + 1);
+        __threadfence_system();
+      }
+    }
+  }
+}
+
+// One CTA polls this rank's flags of one layer until every rank has published this step (bounded: a peer that
+// never arrives raises *error instead of hanging the device), so that the apply kernel behind it never spins with
+// a full grid.
+__global__ void __launch_bounds__(32) k_p2p_wait(bliss_p2p q, int32_t* error) {
+  const long long want = *q.step_dev + 1;
+  const int parity = (int)((want - 1) & 1);
+  if ((int)threadIdx.x < q.world) {
+    volatile unsigned long long* f = p2p_flag(q, q.rank, parity, q.layer, threadIdx.x);
+    const long long t0 = clock64();
+    while ((long long)*f != want) {
+      if (clock64() - t0 > 8000000000ll) {      // ~4 s at 2 GHz
+        if (error) atomicOr(error, 1 << q.layer);
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __threadfence_system();
+}
+
+// apply all ranks' updates of one layer from this rank's own window (after k_p2p_wait)
+__global__ void __launch_bounds__(256) k_apply_updates_p2p(bliss_p2p q, int64_t cap, float* exp3_w, double* l1_delta) {
+  __shared__ double s_red[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t total = (int64_t)q.world * cap;
+  const int parity = (int)(*q.step_dev & 1);
+  double dsum = 0.0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int r = (int)(t / cap);
+    const int64_t k = t - (int64_t)r * cap;
+    const unsigned char* base = p2p_slot(q, q.rank, parity, r);
+    const int64_t n = __ldcg(reinterpret_cast<const long long*>(base + q.count_off));   // (L1 may hold the slot's old lines)
+    if (k >= n) continue;
+    const int64_t pos = __ldcg(reinterpret_cast<const int32_t*>(base + q.pos_off) + k);
+    const float f = expf(__ldcg(reinterpret_cast<const float*>(base + q.x_off) + k));
+    float* addr = exp3_w + pos;
+    unsigned old = __float_as_uint(*addr), assumed;
+    do {  // two ranks may have sampled the same edge: multiplicative update through a CAS loop
+      assumed = old;
+      old = atomicCAS(reinterpret_cast<unsigned*>(addr), assumed,
+                      __float_as_uint(__fmul_rn(__uint_as_float(assumed), f)));
+    } while (old != assumed);
+    const float w_old = __uint_as_float(old);
+    dsum += (double)__fmul_rn(w_old, f) - (double)w_old;
+  }
+  if (l1_delta) {
+    dsum = block_sum(dsum, s_red);
+    if (threadIdx.x == 0 && dsum != 0.0) atomicAdd(l1_delta, dsum);
   }
 }
 
@@ -241,8 +337,11 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
                         const float* w_static_csc, const float* a_ij, const float* asum, const float* qsum,
                         int32_t alpha_mode, float delta, int32_t n_dst, int64_t n_edges, float* exp3_w_csc,
                         float* rewards, float* x_out, double* l1_delta, const int64_t* n_edges_dev,
-                        int64_t* count_out, int32_t* pos_out, void* stream) {
+                        int64_t* count_out, int32_t* pos_out, const bliss_p2p* p2p, void* stream) {
   if (!g || n_edges < 0 || n_dst < 0) return -1;
+  if (p2p && (p2p->world <= 0 || p2p->world > 32 || !p2p->peer_base || !p2p->step_dev || !p2p->done_ctr ||
+              p2p->rank < 0 || p2p->rank >= p2p->world || p2p->layer < 0 || p2p->layer >= p2p->n_layers))
+    return -1;
   if (n_edges == 0) return 0;
   if (!blk_indptr || !edge_src || !edge_dst || !csc_pos || !dst_nid || !q_ij || !node_prob || !embed_norm) return -1;
   if (alpha_mode == 0 && !w_static_csc) return -1;
@@ -271,6 +370,11 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
   p.rewards = rewards;
   p.x_out = x_out;
   p.l1_delta = l1_delta;
+  if (p2p) {
+    p.p2p = *p2p;
+  } else {
+    memset(&p.p2p, 0, sizeof(p.p2p));
+  }
   BLISS_KSCOPE("k_reward_update", stream);
   k_reward_update<<<grid_for(n_edges, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(p);
   BLISS_CHECK_LAUNCH();
@@ -296,6 +400,23 @@ int bliss_apply_updates_packed(const void* recv, int64_t rank_stride_bytes, int3
   BLISS_KSCOPE("k_apply_updates_packed", stream);
   k_apply_updates_packed<<<grid_for((int64_t)world * cap, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(
       (const unsigned char*)recv, rank_stride_bytes, world, count_off, pos_off, x_off, cap, exp3_w_csc, l1_delta);
+  BLISS_CHECK_LAUNCH();
+  return 0;
+}
+
+int bliss_apply_updates_p2p(const bliss_p2p* p2p, int64_t cap, float* exp3_w_csc, double* l1_delta, int32_t* error,
+                            void* stream) {
+  if (!p2p || !exp3_w_csc || cap < 0 || p2p->world <= 0 || p2p->world > 32 || !p2p->peer_base || !p2p->step_dev) return -1;
+  if (cap == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    BLISS_KSCOPE("k_p2p_wait", st);
+    k_p2p_wait<<<1, 32, 0, st>>>(*p2p, error);
+    BLISS_CHECK_LAUNCH();
+  }
+  BLISS_KSCOPE("k_apply_updates_p2p", st);
+  k_apply_updates_p2p<<<grid_for((int64_t)p2p->world * cap, 256, BLISS_SM_COUNT * 4), 256, 0, st>>>(*p2p, cap, exp3_w_csc,
+                                                                                                 l1_delta);
   BLISS_CHECK_LAUNCH();
   return 0;
 }

@@ -7,6 +7,8 @@ north-star: every rank samples and aggregates its own seed batches, and only (1)
 """
 from __future__ import annotations
 
+import os
+import warnings
 from typing import List, Tuple
 
 import torch
@@ -75,6 +77,7 @@ class BanditExchange:
 
     def __init__(self, caps, world, device, group):
         self.caps, self.world, self.group = [int(c) for c in caps], int(world), group
+        self.device, self.p2p = device, False
         assert len(caps) * 8 <= self.HEADER
         off, self.pos_off, self.x_off = self.HEADER, [], []
         for c in self.caps:
@@ -92,6 +95,46 @@ class BanditExchange:
         self._hdr_host = torch.zeros(self.HEADER // 8, dtype=torch.int64)
         if device.type == "cuda":
             self._hdr_host = self._hdr_host.pin_memory()
+        if group is not None and device.type == "cuda" and os.environ.get("BLISS_P2P", "1") != "0":
+            try:
+                self._init_p2p(group)
+            except Exception as e:      # no symmetric memory on this system: the NCCL all-gather path stays
+                warnings.warn(f"peer-memory bandit exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gather")
+                self.p2p = False
+
+    def _init_p2p(self, group):
+        """Symmetric-memory window per rank (``torch.distributed._symmetric_memory``: CUDA VMM allocations mapped into
+        every rank of the node): [2 parities][world slots of ``stride`` bytes] ++ flags[2][L][world] uint64.  The reward
+        kernel of every rank stores its updates into its slot of EVERY window over NVLink and raises a flag per layer;
+        the apply kernel polls the local flags (``csrc/bandit.cu``) — the all-gather is fused into the producer."""
+        import torch.distributed._symmetric_memory as symm
+        from . import _native as N
+        L, W = len(self.caps), self.world
+        self.flags_off = 2 * W * self.stride
+        nbytes = self.flags_off + 2 * L * W * 8
+        window = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+        try:
+            hdl = symm.rendezvous(window, group)
+        except Exception:
+            symm.enable_symm_mem_for_group(group.group_name)
+            hdl = symm.rendezvous(window, group)
+        window.zero_()
+        self.window, self._hdl, self.rank = window, hdl, int(hdl.rank)
+        self.peer_base = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=self.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)     # exchange step: parity + flag value
+        self.done_ctr = torch.zeros(L, dtype=torch.int32, device=self.device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._structs = [N.P2P(peer_base=self.peer_base.data_ptr(), world=W, rank=self.rank,
+                               parity_stride=W * self.stride, rank_stride=self.stride, count_off=8 * l,
+                               pos_off=self.pos_off[l], x_off=self.x_off[l], flags_off=self.flags_off, layer=l,
+                               n_layers=L, step_dev=self.step_dev.data_ptr(),
+                               done_ctr=self.done_ctr[l:].data_ptr()) for l in range(L)]
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)               # every window is zeroed before anybody stores into it
+        self.p2p = True
+
+    def p2p_struct(self, layer: int):
+        return self._structs[layer]
 
     def exchange(self, counts):
         for l, c in enumerate(counts):

@@ -463,7 +463,7 @@ class BanditLadiesSampler:
 
     # ---- sync-free path (CUDA-graph capture of the whole step) -----------------------------------
     def enqueue_static(self, g, seeds_static, pools, step_dev, transpose_stream=None, defer_last_transpose=False,
-                       ctr_base: int = 0):
+                       ctr_base: int = 0, layer_pre=None):
         """Enqueue the sampling of every layer into the capacity pools with NO host synchronisation:
         each layer reads its true seed count from the previous layer's device counters, the Philox
         step from ``step_dev``, and the transpose its edge count from the counters.  Capturable in a
@@ -474,7 +474,9 @@ class BanditLadiesSampler:
         stream before the step ends.  ``defer_last_transpose``: do not launch the input layer's transpose here but
         return it (a list of callables) for the caller to launch after the forward pass.  ``ctr_base``: first
         counters block to use (layer l writes block ``ctr_base + l``): the pipelined step samples the NEXT step's
-        blocks into a second pool set while this step's backward pass still reads the first set's counts."""
+        blocks into a second pool set while this step's backward pass still reads the first set's counts.
+        ``layer_pre``: ``{layer: callable}`` run on the current stream right before that layer is sampled (the
+        data-parallel step applies all ranks' bandit updates of a layer just before the layer's weights are read)."""
         wsp = self._bind(g)
         L = len(self.nodes_per_layer)
         bandit = self._mode == N.MODE_BANDIT
@@ -509,6 +511,8 @@ class BanditLadiesSampler:
                              cap_edges=pool.cap_edges, cap_src=pool.cap_src, pad_src=pool.cap_src,
                              pad_rows=pool.cap_dst)
             main = torch.cuda.current_stream()
+            if layer_pre and block_id in layer_pre:
+                layer_pre[block_id]()
             if block_id + 2 in done:                # this workspace was last used two layers ago: its restore must be done
                 main.wait_event(done[block_id + 2])
             N.call("bliss_sample_layer_front", C.byref(w.gview), N.ptr(seeds), n_cap, N.ptr(weights), float(self.eta),
@@ -568,7 +572,7 @@ class BanditLadiesSampler:
         return ("static", None, None, None)
 
     def _reward_call(self, idx, mfg, g, alpha, weights, rewards=None, x_out=None, l1=None, n_edges_dev=None,
-                     count_out=None, pos_out=None):
+                     count_out=None, pos_out=None, p2p=None):
         kind, a, asum, qsum = alpha
         wsp = self._bind(g)
         w_static = g.csc_edata(self.edge_weight) if kind == "static" else None
@@ -583,7 +587,8 @@ class BanditLadiesSampler:
             N.ptr(mfg.dstdata[NID]), N.ptr(mfg.edata["q_ij"]), N.ptr(mfg.srcdata[self.node_prob]),
             N.ptr(emb.contiguous()), N.ptr(w_static), N.ptr(a), N.ptr(asum), N.ptr(qsum),
             1 if kind == "gat" else 0, 0.01, mfg.num_dst_nodes(), mfg.num_edges(), N.ptr(weights),
-            N.ptr(rewards), N.ptr(x_out), N.ptr(l1), n_edges_dev, count_out, N.ptr(pos_out), N.stream())
+            N.ptr(rewards), N.ptr(x_out), N.ptr(l1), n_edges_dev, count_out, N.ptr(pos_out),
+            C.byref(p2p) if p2p is not None else None, N.stream())
 
     def calculate_rewards(self, idx, mfg, g, alpha):
         """``bandit_sampler.py:160-193``: stores ``mfg.edata['rewards']`` (emit-only kernel call)."""
@@ -634,18 +639,28 @@ class BanditLadiesSampler:
     def exp3_emit_layer(self, idx, mfg, g, exchange):
         """One layer of :meth:`exp3_emit` (needs the layer's ``embed_norm`` — and ``a_ij`` for GAT — only)."""
         assert mfg.num_edges() <= exchange.caps[idx]
+        if exchange.p2p:      # straight into every rank's window over NVLink (flags raised by the kernel's last CTA)
+            self._reward_call(idx, mfg, g, self.calculate_alpha(mfg), None, p2p=exchange.p2p_struct(idx))
+            return
         self._reward_call(idx, mfg, g, self.calculate_alpha(mfg), None, x_out=exchange.x[idx],
                           count_out=exchange.header.data_ptr() + 8 * idx, pos_out=exchange.pos[idx])
 
     def exp3_apply(self, exchange, n_layers: int):
         """Apply all ranks' gathered updates (one kernel per layer, counts read from the headers)."""
         for idx in range(n_layers):
+            self.exp3_apply_layer(exchange, idx)
+
+    def exp3_apply_layer(self, exchange, idx: int):
+        if exchange.p2p:      # wait for every rank's flag of this layer, then apply the slots of the own window
+            N.call("bliss_apply_updates_p2p", C.byref(exchange.p2p_struct(idx)), exchange.caps[idx],
+                   N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]), N.ptr(exchange.err), N.stream())
+        else:
             N.call("bliss_apply_updates_packed", N.ptr(exchange.recv), exchange.stride, exchange.world,
                    8 * idx, exchange.pos_off[idx], exchange.x_off[idx], exchange.caps[idx],
                    N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]), N.stream())
-            self._updated[idx] = True
-            if self.normalize == "literal":
-                self._renormalize(idx)
+        self._updated[idx] = True
+        if self.normalize == "literal":
+            self._renormalize(idx)
 
     def tick_renorm(self, n_layers: int):
         """Lazy mode's range safety: physically re-normalise every ``renorm_every`` updates (a weight
@@ -669,7 +684,7 @@ class BanditLadiesSampler:
         self._bind(g)
         if (exchange is not None and g.num_edges() < 2 ** 31
                 and all(m.num_edges() <= exchange.caps[i] for i, m in enumerate(mfgs))):
-            for idx, mfg in enumerate(mfgs):
+            for idx, mfg in enumerate(mfgs):      # (eager steps always go through the NCCL all-gather)
                 self._reward_call(idx, mfg, g, self.calculate_alpha(mfg), None, x_out=exchange.x[idx],
                                   pos_out=exchange.pos[idx])
             exchange.exchange([m.num_edges() for m in mfgs])

@@ -480,19 +480,30 @@ class Trainer:
             self._replay(("G" if prefetch else "GN", p))
         else:                                                  # data parallel: see _capture_full
             main = torch.cuda.current_stream()
-            self._replay(("A1", p))
-            a1_done = torch.cuda.Event()
-            a1_done.record(main)
-            work = None
-            if self._exchange is not None:        # the bandit all-gather runs on NCCL's stream beside the backward pass
-                work = torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send, group=self.pg,
-                                                                async_op=True)
-            self._replay(("A2", p))
-            with torch.cuda.stream(self._side_apply):          # … and so do the apply pass over all ranks' updates
-                self._side_apply.wait_event(a1_done)           # and the sampling of the next batch
-                if work is not None:
-                    work.wait()
-                self._replay(("B1" if prefetch else "B1N", p))
+            if self._exchange is not None and self._exchange.p2p:
+                # peer-memory exchange: no collective call.  The apply + look-ahead sampling branch is launched at the
+                # START of the step: its first kernel polls the flags the ranks' reward kernels raise during A1
+                start = torch.cuda.Event()
+                start.record(main)
+                with torch.cuda.stream(self._side_apply):
+                    self._side_apply.wait_event(start)
+                    self._replay(("B1" if prefetch else "B1N", p))
+                self._replay(("A1", p))
+                self._replay(("A2", p))
+            else:
+                self._replay(("A1", p))
+                a1_done = torch.cuda.Event()
+                a1_done.record(main)
+                work = None
+                if self._exchange is not None:    # the bandit all-gather runs on NCCL's stream beside the backward pass
+                    work = torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send,
+                                                                    group=self.pg, async_op=True)
+                self._replay(("A2", p))
+                with torch.cuda.stream(self._side_apply):      # … and so do the apply pass over all ranks' updates
+                    self._side_apply.wait_event(a1_done)       # and the sampling of the next batch
+                    if work is not None:
+                        work.wait()
+                    self._replay(("B1" if prefetch else "B1N", p))
             self.grads.all_reduce_mean_(self.pg)
             self._replay(("B2", 0))
             main.wait_stream(self._side_apply)
@@ -557,6 +568,9 @@ class Trainer:
             self._grow_pending = getattr(self, "_grow_pending", False) or grow
             grow = False
             if self.num_steps % 32 == 0:
+                if self._exchange is not None and self._exchange.p2p and int(self._exchange.err.item()):
+                    raise RuntimeError("peer-memory bandit exchange: a rank's update did not arrive within the timeout "
+                                       f"(layer mask {int(self._exchange.err.item())})")
                 flag = torch.tensor([1.0 if self._grow_pending else 0.0], device=g.device)
                 torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX, group=self.pg)
                 grow, self._grow_pending = bool(flag.item() > 0), False
@@ -620,12 +634,12 @@ class Trainer:
             for pb in pset.padded:                # events recorded in one capture must not be waited for in another
                 pb._ready = pb._t_ready = None
 
-        def sample_into(pset):
+        def sample_into(pset, layer_pre=None):
             """Sampling of one batch (``pset.seeds``) into ``pset``: every layer's front half on the current stream,
             back halves and transposes on ``_side_t``; complete (joined) on return."""
             cur = torch.cuda.current_stream()
             smp.enqueue_static(g, pset.seeds, pset.pools, self._step_dev, transpose_stream=self._side_t,
-                               defer_last_transpose=False, ctr_base=pset.ctr_base)
+                               defer_last_transpose=False, ctr_base=pset.ctr_base, layer_pre=layer_pre)
             self._gather_inputs(pset, True)       # beside the input layer's fill / transposes (needs its source list only)
             cur.wait_stream(self._side_t)
             self._step_dev.add_(1)
@@ -721,7 +735,13 @@ class Trainer:
             self._zero_grads()
             loss.backward()
 
+        p2p = bandit and self._exchange is not None and self._exchange.p2p
+
         def body_b1(p, prefetch):
+            """All ranks' updates applied, then the next batch sampled.  Peer-memory exchange: every layer's apply kernel
+            first waits for all ranks' flags of that layer; the layers are applied in the order the forward pass emits
+            them (input layer first), so the big input-layer passes run beside the forward pass and only the small top
+            layer's is left when the top layer's flags arrive and sampling (top layer first) can start."""
             if bandit:
                 smp.exp3_apply(self._exchange, L)
             if prefetch:
@@ -732,10 +752,12 @@ class Trainer:
         def body_b2():
             self._optimizer_step()
             self._drop_dev.add_(1)
+            if p2p:
+                self._exchange.step_dev.add_(1)   # next step: other parity half of the windows, next flag value
 
         def dp_step_eager(p, prefetch):
             loss_w, _, _ = body_a1(p)
-            if self._exchange is not None:
+            if self._exchange is not None and not p2p:
                 torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send, group=self.pg)
             body_a2(loss_w)
             body_b1(p, prefetch)

@@ -127,6 +127,24 @@ typedef struct bliss_block_out {
                            (capacity-padded blocks for CUDA-graph replay); 0 = no padding          */
 } bliss_block_out;
 
+/* Peer-memory exchange of the sparse bandit updates (data parallel, one node): every rank owns a window in symmetric
+ * memory, mapped by all ranks:  [2 parities][world slots, one per source rank] ++ flags[2][n_layers][world] (uint64);
+ * a slot is laid out like the packed exchange buffer (int64 edge counts, then per layer int32 pos[cap] | fp32 x[cap]).
+ * bliss_reward_update with a bliss_p2p writes the layer's (position, exponent) pairs into ITS slot of EVERY window
+ * (NVLink stores) and raises flag = *step_dev + 1 in every window when its last CTA is done; bliss_apply_updates_p2p
+ * waits for all ranks' flags of the layer and applies the slots of the rank's own window.  parity = *step_dev & 1. */
+typedef struct bliss_p2p {
+  const int64_t* peer_base;   /* device array [world]: address of every rank's window in this rank's address space */
+  int32_t  world, rank;
+  int64_t  parity_stride;     /* bytes between the two parity halves of a window (= world * rank_stride) */
+  int64_t  rank_stride;       /* bytes of one slot */
+  int64_t  count_off, pos_off, x_off;   /* this layer's offsets inside a slot (bytes) */
+  int64_t  flags_off;         /* byte offset of the flags inside a window */
+  int32_t  layer, n_layers;
+  const int64_t* step_dev;    /* exchange step counter on the device */
+  uint32_t* done_ctr;         /* [1] zero between launches: last-CTA detection of the producing kernel */
+} bliss_p2p;
+
 int bliss_version(void);
 
 /* Fill the workspace invariant (once, after allocation). */
@@ -250,7 +268,12 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
                         const int64_t* n_edges_dev /* true edge count on the device (n_edges = capacity), or NULL */,
                         int64_t* count_out /* where to store the edge count (exchange header), or NULL */,
                         int32_t* pos_out /* [E_b] CSC positions as int32 (exchange send buffer; |E| < 2^31), or NULL */,
+                        const bliss_p2p* p2p /* also store (pos, x) into every rank's window + raise flags, or NULL */,
                         void* stream);
+/* wait for every rank's flag of p2p->layer (one polling CTA; a peer that never arrives sets bit `layer` of *error
+ * after ~4 s instead of hanging), then w[pos] *= exp(x) for all ranks' slots of this rank's window */
+int bliss_apply_updates_p2p(const bliss_p2p* p2p, int64_t cap, float* exp3_w_csc, double* l1_delta,
+                            int32_t* error /* device int, or NULL */, void* stream);
 /* apply gathered updates from other ranks: w[pos[k]] *= exp(x[k]) */
 int bliss_apply_updates(const int64_t* pos, const float* x, int64_t n, float* exp3_w_csc,
                         double* l1_delta, void* stream);
