@@ -103,6 +103,11 @@ class P2P(C.Structure):
                 ("done_ctr", C.c_void_p)]
 
 
+class GradP2P(C.Structure):
+    _fields_ = [("peer_base", C.c_void_p), ("world", C.c_int32), ("rank", C.c_int32), ("parity_stride", C.c_int64),
+                ("slot_bytes", C.c_int64), ("flags_off", C.c_int64), ("step_dev", C.c_void_p), ("done_ctr", C.c_void_p)]
+
+
 _P, _I32, _I64, _U32, _U64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_double
 _GP, _WP, _BP = C.POINTER(Graph), C.POINTER(Workspace), C.POINTER(BlockOut)
 
@@ -140,6 +145,8 @@ PROTOTYPES = {
     "bliss_scale_by_inv": [_P, _I64, _P, _D, _P],
     "bliss_adam_step": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _P, _I32, _P],
     "bliss_splitk_accumulate": [_P, _I32, _I32, _I32, _I32, _P, _P],
+    "bliss_grad_push": [_P, _I64, C.POINTER(GradP2P), _P],
+    "bliss_adam_step_p2p": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _P, C.POINTER(GradP2P), _P, _P],
     "bliss_sage_epilogue_parts": [],
     "bliss_xent_mean": [_P, _P, _I32, _I32, _P, _P, _P, _P],
     "bliss_sage_epilogue_fwd": [_P, _P, _P, _I32, _I32, _I32, _F, _U64, _P, _U32, _P, _P, _P],
@@ -175,7 +182,7 @@ class BlissNativeError(RuntimeError):
 #: kernels each entry point launches (for the ``gpu_launches`` count of bench.py)
 LAUNCHES = {"bliss_frontier_prob": 4, "bliss_sample_layer_front": 11, "bliss_poisson_select": 2, "bliss_frontier_plan": 3, "bliss_sample_layer_back": 2,
             "bliss_select_topk": 3, "bliss_block_transpose": 3, "bliss_l1_norm": 2, "bliss_version": 0,
-            "bliss_adam_step": 2, "bliss_spmm": 2, "bliss_apply_updates_p2p": 2, "bliss_sage_epilogue_bwd": 2,
+            "bliss_adam_step": 2, "bliss_adam_step_p2p": 3, "bliss_spmm": 2, "bliss_apply_updates_p2p": 2, "bliss_sage_epilogue_bwd": 2,
             "bliss_sage_epilogue_parts": 0, "bliss_xent_mean": 2}
 
 

@@ -143,6 +143,41 @@ class BanditExchange:
         dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
 
 
+class GradExchange:
+    """Symmetric-memory windows for the gradient all-reduce fused into the Adam launch (``csrc/optim.cu``): every rank
+    pushes its flat gradient into its slot of every rank's window, Adam adds the slots in rank order."""
+
+    def __init__(self, n_params: int, world: int, device, group):
+        import torch.distributed._symmetric_memory as symm
+        from . import _native as N
+        self.world, self.n = int(world), int(n_params)
+        self.slot_bytes = (4 * self.n + 15) // 16 * 16
+        self.flags_off = 2 * self.world * self.slot_bytes
+        window = symm.empty(self.flags_off + 2 * self.world * 8, dtype=torch.uint8, device=device)
+        try:
+            hdl = symm.rendezvous(window, group)
+        except Exception:
+            symm.enable_symm_mem_for_group(group.group_name)
+            hdl = symm.rendezvous(window, group)
+        window.zero_()
+        self.window, self._hdl, self.rank = window, hdl, int(hdl.rank)
+        self.peer_base = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        self.done_ctr = torch.zeros(1, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.struct = N.GradP2P(peer_base=self.peer_base.data_ptr(), world=self.world, rank=self.rank,
+                                parity_stride=self.world * self.slot_bytes, slot_bytes=self.slot_bytes,
+                                flags_off=self.flags_off, step_dev=self.step_dev.data_ptr(),
+                                done_ctr=self.done_ctr.data_ptr())
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+
+    def push(self, flat_grad: torch.Tensor):
+        import ctypes as C
+        from . import _native as N
+        N.call("bliss_grad_push", N.ptr(flat_grad), flat_grad.numel(), C.byref(self.struct), N.stream())
+
+
 class FlatAdam(torch.optim.Optimizer):
     """``torch.optim.Adam(params, lr)`` (``train_lightning.py:206``) over flat buffers: the parameters are
     re-homed as views of one flat fp32 tensor (like the gradients of :class:`FlatGrads`), the moments are
@@ -186,6 +221,18 @@ class FlatAdam(torch.optim.Optimizer):
         N.call("bliss_adam_step", N.ptr(self.flat_p), N.ptr(self.flat_g), N.ptr(self.exp_avg), N.ptr(self.exp_avg_sq),
                self.flat_p.numel(), N.ptr(self.lr_dev), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
                N.ptr(self.step_dev), 1, N.stream())
+
+    @torch.no_grad()
+    def step_p2p(self, gx: "GradExchange"):
+        """Adam over the MEAN of all ranks' gradients read from the peer-memory window (after ``gx.push``): replaces
+        ``all_reduce`` + ``div_`` + ``step``; advances the exchange's step counter."""
+        import ctypes as C
+        from . import _native as N
+        g = self.param_groups[0]
+        N.call("bliss_adam_step_p2p", N.ptr(self.flat_p), N.ptr(self.flat_g), N.ptr(self.exp_avg), N.ptr(self.exp_avg_sq),
+               self.flat_p.numel(), N.ptr(self.lr_dev), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+               N.ptr(self.step_dev), C.byref(gx.struct), N.ptr(gx.err), N.stream())
+        gx.step_dev.add_(1)
 
     def state_dict(self):
         return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_dev.clone(),

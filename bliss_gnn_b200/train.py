@@ -143,7 +143,7 @@ class Trainer:
         # the data-parallel code path (two graphs with the collectives in between) can be forced on a
         # single rank, so it is testable on one GPU
         self._force_dp = bool(os.environ.get("BLISS_FORCE_DP_PATH")) and process_group is not None
-        self._graph, self._pools, self._padded, self._exchange = None, None, None, None
+        self._graph, self._pools, self._padded, self._exchange, self._gradx = None, None, None, None, None
         self._sets, self._graphs, self._graph_kernel_counts = None, {}, {}
         self._cur, self._next_ready, self._prefetched_seeds = 0, False, None
         self._max_src, self._max_edges = None, None
@@ -256,6 +256,15 @@ class Trainer:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.pg)
             cap_e = [int(v) for v in t.tolist()]
             self._exchange = BanditExchange(cap_e, self.world, dev, self.pg)
+        if (self.world > 1 or self._force_dp) and self._gradx is None and isinstance(self.optimizer, FlatAdam) \
+                and os.environ.get("BLISS_P2P", "1") != "0":
+            from .parallel import GradExchange
+            try:       # gradient all-reduce through peer memory, fused into the Adam launch (csrc/optim.cu)
+                self._gradx = GradExchange(self._flat_grad.numel(), self.world, dev, self.pg)
+            except Exception as e:
+                import warnings
+                warnings.warn(f"peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+                self._gradx = False
         sets = []
         for p in range(2):
             seeds_static = torch.zeros(dm.batch_size, dtype=torch.int32, device=dev)
@@ -504,7 +513,8 @@ class Trainer:
                     if work is not None:
                         work.wait()
                     self._replay(("B1" if prefetch else "B1N", p))
-            self.grads.all_reduce_mean_(self.pg)
+            if not self._gradx:
+                self.grads.all_reduce_mean_(self.pg)
             self._replay(("B2", 0))
             main.wait_stream(self._side_apply)
         if prefetch:
@@ -571,6 +581,8 @@ class Trainer:
                 if self._exchange is not None and self._exchange.p2p and int(self._exchange.err.item()):
                     raise RuntimeError("peer-memory bandit exchange: a rank's update did not arrive within the timeout "
                                        f"(layer mask {int(self._exchange.err.item())})")
+                if self._gradx and int(self._gradx.err.item()):
+                    raise RuntimeError("peer-memory gradient exchange: a rank's gradient did not arrive within the timeout")
                 flag = torch.tensor([1.0 if self._grow_pending else 0.0], device=g.device)
                 torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX, group=self.pg)
                 grow, self._grow_pending = bool(flag.item() > 0), False
@@ -749,8 +761,15 @@ class Trainer:
             if not (bandit or prefetch):
                 self._drop_dev.add_(0)            # (a captured graph must hold at least one node)
 
+        gradx = self._gradx if self._gradx else None
+
         def body_b2():
-            self._optimizer_step()
+            if gradx is not None:                 # push the flat gradient into every rank's window; Adam adds the slots
+                gradx.push(self._flat_grad)
+                self.optimizer.step_p2p(gradx)
+                self._grads_clean = True
+            else:
+                self._optimizer_step()
             self._drop_dev.add_(1)
             if p2p:
                 self._exchange.step_dev.add_(1)   # next step: other parity half of the windows, next flag value
@@ -761,7 +780,8 @@ class Trainer:
                 torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send, group=self.pg)
             body_a2(loss_w)
             body_b1(p, prefetch)
-            self.grads.all_reduce_mean_(self.pg)
+            if gradx is None:
+                self.grads.all_reduce_mean_(self.pg)
             body_b2()
 
         side = torch.cuda.Stream()

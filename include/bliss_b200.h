@@ -145,6 +145,20 @@ typedef struct bliss_p2p {
   uint32_t* done_ctr;         /* [1] zero between launches: last-CTA detection of the producing kernel */
 } bliss_p2p;
 
+/* Gradient all-reduce through peer memory, fused into the optimizer step: window = [2 parities][world slots of
+ * slot_bytes] ++ flags[2][world] (uint64).  bliss_grad_push stores the flat gradient into the rank's slot of every
+ * window and raises flag = *step_dev + 1; bliss_adam_step_p2p waits for all flags, adds the world slots of the own
+ * window in rank order (bit-identical on every rank), divides by world and applies Adam (+ clears the gradients). */
+typedef struct bliss_grad_p2p {
+  const int64_t* peer_base;   /* device array [world] of window addresses */
+  int32_t  world, rank;
+  int64_t  parity_stride;     /* = world * slot_bytes */
+  int64_t  slot_bytes;        /* >= 4 * n, multiple of 16 */
+  int64_t  flags_off;
+  const int64_t* step_dev;    /* exchange step counter (parity, flag value) */
+  uint32_t* done_ctr;         /* [1], zero between launches */
+} bliss_grad_p2p;
+
 int bliss_version(void);
 
 /* Fill the workspace invariant (once, after allocation). */
@@ -326,6 +340,11 @@ int bliss_splitk_accumulate(const float* part, int32_t n_parts, int32_t rows, in
 int bliss_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                     const float* lr_dev, float beta1, float beta2, float eps, int64_t* step_dev,
                     int32_t zero_grad, void* stream);
+/* data parallel without an all-reduce call (see bliss_grad_p2p) */
+int bliss_grad_push(const float* grads, int64_t n, const bliss_grad_p2p* q, void* stream);
+int bliss_adam_step_p2p(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const float* lr_dev, float beta1, float beta2, float eps, int64_t* step_dev,
+                        const bliss_grad_p2p* q, int32_t* error /* device int or NULL */, void* stream);
 
 /* ---- measurement hooks (bench.py; not on the product path) -------------------------------------
  * Per-KERNEL CUDA-event timing: while enabled, every launch of the hot-path kernels is bracketed by an event
