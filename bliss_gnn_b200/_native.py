@@ -20,7 +20,7 @@ SOURCES = ["sampler.cu", "aggregate.cu", "bandit.cu", "gat.cu", "optim.cu", "epi
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
-MODE_BANDIT, MODE_LADIES, MODE_UNIFORM, COLLECT_BITMAP = 0, 1, 2, 16
+MODE_BANDIT, MODE_LADIES, MODE_UNIFORM, MODE_NEIGHBOR, COLLECT_BITMAP = 0, 1, 2, 4, 16
 AGG_SUM, AGG_MEAN = 0, 1
 
 
@@ -122,6 +122,7 @@ PROTOTYPES = {
     "bliss_poisson_select": [_I32, _I32, _D, _U64, _U64, _U32, _P, _WP, _P],
     "bliss_select_topk": [_I32, _I32, _U64, _U64, _U32, _P, _P, _WP, _P],
     "bliss_philox_fill": [_U64, _U64, _U32, _P, _I64, _P, _P],
+    "bliss_neighbor_select": [_GP, _I32, _I32, _U64, _U64, _U32, _WP, _P],
     "bliss_block_count": [_GP, _P, _I32, _P, _F, _I32, _WP, _P],
     "bliss_block_index": [_P, _I32, _WP, _BP, _P],
     "bliss_block_fill": [_GP, _P, _I32, _P, _F, _I32, _WP, _BP, _P],

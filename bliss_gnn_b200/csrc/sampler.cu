@@ -697,6 +697,147 @@ __global__ void k_philox_fill(unsigned long long seed, unsigned long long step, 
 }
 
 // ------------------------------------------------------------------------------------------
+// (2d) uniform neighbour sampling (`--sampler neighbor | full`, train_lightning.py:349-357: DGL NeighborSampler /
+//      MultiLayerFullNeighborSampler): every seed keeps min(fanout, degree) of its in-edges, chosen uniformly
+//      without replacement; fanout <= 0 keeps all.  One warp per row.  The draw: every in-edge gets the key
+//      Philox4x32-10(seed; CSC position, layer | 0x8000, step) (32 bits); the row keeps its `fanout` smallest keys,
+//      ties in CSC order — the k smallest of d i.i.d. keys are a uniform k-subset.  The threshold is found by a
+//      4-pass radix select over the row's keys (recomputed per pass: nothing edge-sized is stored), then one pass
+//      writes the row's keep bits (the layout k_block_count produces) and registers every kept edge's source as a
+//      block node (selected bit, list of selected nodes, candidate list for the workspace restore).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned edge_key(unsigned long long seed, unsigned long long step, unsigned layer, int64_t pos) {
+  const uint4 r = philox4x32_10(make_uint4((unsigned)pos, layer | 0x8000u | ((unsigned)(pos >> 32) << 16), (unsigned)step,
+                                           (unsigned)(step >> 32)),
+                                make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  return r.x;
+}
+__global__ void __launch_bounds__(256) k_neighbor_select(GraphView g, int fanout, unsigned long long seed,
+                                                        unsigned long long step, unsigned layer, bliss_workspace ws) {
+  pdl_wait();
+  pdl_trigger();
+  if (ws.step_dev) step = *ws.step_dev;
+  bliss_counters* ctr = ws.ctr;
+  const int n_seeds = ctr->n_seeds;
+  const int lane = lane_id();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < n_seeds; i += nwarps) {
+    const int64_t a = ws.row_a[i];
+    const int d = ws.row_d[i];
+    const int c_first = ws.chunk_first[i];
+    unsigned T = 0xffffffffu;     // keep keys < T, and `need` of the keys == T (first in CSC order)
+    int need = 0x7fffffff;
+    if (fanout > 0 && d > fanout) {
+      unsigned prefix = 0;
+      int k = fanout;             // rank of the threshold among the keys that match the prefix so far
+      for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const unsigned mask_hi = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        // 256-bin histogram of the next byte over the keys matching the prefix: 8 bins per lane
+        int hist[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) hist[b] = 0;
+        for (int j0 = 0; j0 < d; j0 += 32) {
+          const int j = j0 + lane;
+          unsigned key = 0;
+          bool in = false;
+          if (j < d) {
+            key = edge_key(seed, step, layer, a + j);
+            in = (key & mask_hi) == prefix;
+          }
+          const unsigned byte = (key >> shift) & 255u;
+          // every lane owns bins [8 lane, 8 lane + 8): count the matching keys of this round by ballots over the byte's owner
+          for (unsigned m = __ballot_sync(0xffffffffu, in); m;) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned bsrc = __shfl_sync(0xffffffffu, byte, src);
+            if ((int)(bsrc >> 3) == lane) ++hist[bsrc & 7];
+          }
+        }
+        // smallest byte value whose cumulative count reaches k
+        int mine = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) mine += hist[b];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const unsigned reach = __ballot_sync(0xffffffffu, incl >= k);
+        const int owner = __ffs(reach) - 1;            // lane whose bins contain the k-th key
+        int below = __shfl_sync(0xffffffffu, incl - mine, owner), bin = 0;
+        if (lane == owner) {
+          int run = below;
+          for (int b = 0; b < 8; ++b) {
+            if (run + hist[b] >= k) { bin = b; below = run; break; }
+            run += hist[b];
+          }
+        }
+        bin = __shfl_sync(0xffffffffu, bin, owner);
+        below = __shfl_sync(0xffffffffu, below, owner);
+        prefix |= (unsigned)(owner * 8 + bin) << shift;
+        k -= below;
+      }
+      T = prefix;
+      need = k;                    // keys equal to T still to take
+    }
+    int ties = 0;
+    for (int j0 = 0; j0 < d; j0 += 32) {
+      const int j = j0 + lane;
+      bool keep = false, tie = false;
+      int src = 0;
+      if (j < d) {
+        src = __ldg(g.indices + a + j);
+        if (fanout <= 0 || d <= fanout) {
+          keep = true;
+        } else {
+          const unsigned key = edge_key(seed, step, layer, a + j);
+          keep = key < T;
+          tie = key == T;
+        }
+      }
+      const unsigned tm = __ballot_sync(0xffffffffu, tie);
+      if (tie && ties + __popc(tm & ((1u << lane) - 1u)) < need) keep = true;
+      ties += __popc(tm);
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      // keep bits: chunk c_first + j0 / 256, word (j0 % 256) / 32
+      if (lane == 0) ws.keep_bits[(int64_t)(c_first + (j0 >> 8)) * (BLISS_CHUNK / 32) + ((j0 & 255) >> 5)] = km;
+      bool fresh = false;
+      if (keep) {
+        const unsigned bit = 1u << (src & 31);
+        const unsigned old = atomicOr(&ws.sel_bits[src >> 5], bit);
+        fresh = !(old & bit);      // seeds were marked by the plan, so a fresh node is a non-seed source
+      }
+      const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+      if (fm) {
+        int base = 0;
+        if (lane == __ffs(fm) - 1) {
+          base = atomicAdd(&ctr->n_sel, __popc(fm));
+          atomicAdd(&ctr->n_cand, __popc(fm));
+        }
+        base = __shfl_sync(0xffffffffu, base, __ffs(fm) - 1);
+        if (fresh) {
+          const int slot = base + __popc(fm & ((1u << lane) - 1u));
+          if (slot < ws.cap_sel) {
+            ws.sel[slot] = src;
+            ws.cand[n_seeds + slot] = src;
+            *reinterpret_cast<int2*>(&ws.node_info[2 * src]) = make_int2(-2, __float_as_int(1.0f));
+          } else {
+            ctr->error = BLISS_ERR_SEL_CAPACITY;
+          }
+        }
+      }
+    }
+    // the tail words of the row's last chunk stay zero from the previous use?  No: clear them explicitly
+    const int last_word = (d + 31) >> 5;
+    const int n_words_row = (ws.chunk_first[i + 1] - c_first) * (BLISS_CHUNK / 32);
+    for (int wd = last_word + lane; wd < n_words_row; wd += 32)
+      ws.keep_bits[(int64_t)c_first * (BLISS_CHUNK / 32) + wd] = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // (3a) kept in-edges (source selected) of every 256-edge chunk of the frontier: keep bits, kept
 //      count and — bandit mode — the chunk's partial of ΣW~ (W~ = q_ij / P_src); first occurrence
 //      of every selected non-seed source: key = (row+1, position in row).  bandit_sampler.py:289-314
@@ -715,7 +856,7 @@ struct FillCtx {
 // SMEM_BITS: the selected-node bitmap (|V| / 8 bytes) is copied into shared memory once per CTA — the
 // per-edge bit test is a 32-way gather, which an SM's L1 serves at one sector per cycle (it alone
 // would cost more than streaming the indices) but shared memory serves at bank speed.
-template <bool SMEM_BITS>
+template <bool SMEM_BITS, bool EDGE_BITS = false>   // EDGE_BITS: the keep bits were chosen per edge (k_neighbor_select)
 __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_count(FillCtx c, bliss_workspace ws, int bit_words) {
   pdl_wait();
   pdl_trigger();
@@ -745,10 +886,16 @@ __global__ void __launch_bounds__(BLISS_CTA, 6) k_block_count(FillCtx c, bliss_w
     }
     int cnt = 0;
     unsigned myword = 0;
+    const unsigned pre = (EDGE_BITS && lane < BLISS_CHUNK / 32)
+                             ? ws.keep_bits[(int64_t)ch * (BLISS_CHUNK / 32) + lane] : 0u;
 #pragma unroll
     for (int j = 0; j < BLISS_CHUNK / 32; ++j) {
       bool keep = false;
-      if (src[j] >= 0) keep = SMEM_BITS ? ((s_bits[src[j] >> 5] >> (src[j] & 31)) & 1u) : test_bit(ws.sel_bits, src[j]);
+      const unsigned pre_j = EDGE_BITS ? __shfl_sync(0xffffffffu, pre, j) : 0u;   // (every lane takes part in the shuffle)
+      if (EDGE_BITS)
+        keep = src[j] >= 0 && ((pre_j >> lane) & 1u);
+      else if (src[j] >= 0)
+        keep = SMEM_BITS ? ((s_bits[src[j] >> 5] >> (src[j] & 31)) & 1u) : test_bit(ws.sel_bits, src[j]);
       const unsigned bits = __ballot_sync(0xffffffffu, keep);
       if (keep) lk[cnt + __popc(bits & ((1u << lane) - 1u))] = (unsigned char)(lane + 32 * j);
       if (lane == j) myword = bits;
@@ -1338,6 +1485,15 @@ int bliss_philox_fill(uint64_t seed, uint64_t step, uint32_t layer, const int32_
   return 0;
 }
 
+int bliss_neighbor_select(const bliss_graph* g, int32_t n_seeds, int32_t fanout, uint64_t seed, uint64_t step,
+                          uint32_t layer, const bliss_workspace* ws, void* stream) {
+  if (!g || !ws || n_seeds < 0) return -1;
+  BLISS_LAUNCH_PDL(k_neighbor_select, dim3(grid_for((int64_t)n_seeds * 32, 256, BLISS_SM_COUNT * 8)), dim3(256), 0,
+                   (cudaStream_t)stream, view_of(g), (int)fanout, (unsigned long long)seed, (unsigned long long)step,
+                   (unsigned)layer, *ws);
+  return 0;
+}
+
 int bliss_block_count(const bliss_graph* g, const int32_t* seeds, int32_t n_seeds,
                       const float* edge_weight_csc, float eta, int32_t mode,
                       const bliss_workspace* ws, void* stream) {
@@ -1348,6 +1504,11 @@ int bliss_block_count(const bliss_graph* g, const int32_t* seeds, int32_t n_seed
   c.eta = eta;
   c.one_minus_eta = (float)(1.0 - (double)eta);
   c.mode = mode & 1;
+  if (mode & BLISS_MODE_NEIGHBOR) {   // the keep bits were chosen per edge by bliss_neighbor_select
+    BLISS_LAUNCH_PDL((k_block_count<false, true>), dim3(chunk_grid(n_seeds)), dim3(BLISS_CTA), 0, (cudaStream_t)stream, c,
+                     *ws, 0);
+    return 0;
+  }
   // selected-node bitmap in shared memory when six CTAs of it fit an SM (|V| <= ~280 K), else tested in L1/L2
   const int bit_words = (int)((g->num_nodes + 31) / 32);
   const size_t smem = (size_t)bit_words * sizeof(uint32_t);
@@ -1431,6 +1592,13 @@ int bliss_sample_layer_front(const bliss_graph* g, const int32_t* seeds, int32_t
                              void* stream) {
   int rc = bliss_frontier_plan(g, seeds, n_seeds, ws, stream);
   if (rc) return rc;
+  if (mode & BLISS_MODE_NEIGHBOR) {   // uniform fan-out per seed / full neighbourhood: no probabilities, no node selection
+    rc = bliss_neighbor_select(g, n_seeds, fanout, seed, step, layer, ws, stream);
+    if (rc) return rc;
+    rc = bliss_block_count(g, seeds, n_seeds, edge_weight_csc, eta, mode, ws, stream);
+    if (rc) return rc;
+    return bliss_block_index(seeds, n_seeds, ws, out, stream);
+  }
   rc = bliss_frontier_prob(g, seeds, n_seeds, edge_weight_csc, eta, mode, ws, stream);
   if (rc) return rc;
   if (poisson) {

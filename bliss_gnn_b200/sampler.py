@@ -175,6 +175,7 @@ class BanditLadiesSampler:
 
     _poisson = False
     _mode = N.MODE_BANDIT
+    attach_weights = True     # blocks carry ``edge_weights`` (importance weights); False for the uniform samplers
     DENSE_COLLECT_MAX = 1 << 22   # up to 4 M nodes the 8 B/node accumulator scan is cheaper than marking bits
 
     def __init__(self, nodes_per_layer, importance_sampling=True, weight="w", out_weight="edge_weights",
@@ -788,3 +789,59 @@ class PoissonLadiesSampler(LadiesSampler):
                          allow_zero_in_degree=allow_zero_in_degree, rng_seed=rng_seed)
 
     select_neighbors = PoissonBanditLadiesSampler.select_neighbors
+
+
+class NeighborSampler(LadiesSampler):
+    """``dgl.dataloading.NeighborSampler(fanouts)`` as the reference builds it for ``--sampler neighbor``
+    (``train_lightning.py:351-357``): layer by layer from the output side, every seed keeps ``min(fanout, in-degree)``
+    of its in-edges chosen uniformly without replacement (fanout ``-1``: all), the block's sources are the seeds
+    followed by the new sources in first-occurrence order (``dgl.to_block``).  No importance weights: the blocks carry
+    no ``edge_weights``, so the models aggregate with the plain mean (``model.py:321-329``).
+
+    Same workspace, plan, block-build and transpose kernels as the LADIES path; the per-edge choice is
+    ``bliss_neighbor_select`` (``csrc/sampler.cu``): key = Philox(seed; CSC position, layer, step), the row keeps its
+    ``fanout`` smallest keys.  DGL draws from its own generator, so the reference's sets are not reproducible bit for
+    bit by construction; the contract (uniform k-subsets, block layout) is checked against ``oracle.samplers``."""
+
+    _mode = N.MODE_LADIES | N.MODE_NEIGHBOR
+    _poisson = True          # (no top-k scratch; the flag is not consulted on the neighbour path)
+    attach_weights = False   # capacity-padded blocks of the step graph carry no edge_weights either
+
+    def __init__(self, fanouts, edge_dir="in", prob=None, mask=None, replace=False, prefetch_node_feats=None,
+                 prefetch_labels=None, prefetch_edge_feats=None, output_device=None, rng_seed: int = 0):
+        if edge_dir != "in" or prob is not None or mask is not None or replace:
+            raise NotImplementedError("NeighborSampler: only edge_dir='in', uniform, without replacement "
+                                      "(what train_lightning.py:351-357 constructs)")
+        super().__init__([int(f) for f in fanouts], rng_seed=rng_seed)
+        self.fanouts = self.nodes_per_layer
+
+    def _finish_block(self, fr, out, bufs, pool=None):
+        block = super()._finish_block(fr, out, bufs, pool)
+        dict.pop(block.edata, self.output_weight, None)      # uniform sampling: unweighted aggregation
+        return block
+
+    def sample_blocks(self, g, seed_nodes, exclude_eids=None, pools=None):
+        self._bind(g)
+        seed_nodes = self._prep_seeds(g, seed_nodes)
+        output_nodes = seed_nodes
+        blocks = []
+        W = g.csc_edata(self.edge_weight)
+        self.pool_overflow, self.pool_used = False, bool(pools)
+        for block_id in reversed(range(len(self.nodes_per_layer))):
+            block = self._sample_layer_fused(g, seed_nodes, block_id, self.nodes_per_layer[block_id], W,
+                                             pools[block_id] if pools else None)
+            seed_nodes = block.srcdata[NID]
+            blocks.insert(0, block)
+        self.step += 1
+        return seed_nodes, output_nodes, blocks
+
+    def _stages_not_overridden(self) -> bool:
+        return not getattr(self, "force_stage_path", False)
+
+
+class MultiLayerFullNeighborSampler(NeighborSampler):
+    """``dgl.dataloading.MultiLayerFullNeighborSampler(n_layers)`` (``--sampler full``, ``train_lightning.py:349-350``):
+    every layer takes the whole in-neighbourhood of its seeds."""
+
+    def __init__(self, num_layers, **kw):
+        super().__init__([-1] * int(num_layers), **kw)

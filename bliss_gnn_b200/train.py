@@ -26,14 +26,17 @@ from . import ops
 from .graph import NID, Graph, add_self_loops_and_build, load_dataset, normalized_edata
 from .model import GCN, SAGE, GATv2
 from .parallel import FlatAdam, FlatGrads, shard_batches
-from .sampler import BanditLadiesSampler, LadiesSampler, PoissonBanditLadiesSampler, PoissonLadiesSampler
+from .sampler import (BanditLadiesSampler, LadiesSampler, MultiLayerFullNeighborSampler, NeighborSampler,
+                      PoissonBanditLadiesSampler, PoissonLadiesSampler)
 
 
 def make_sampler(name: str, fanouts, importance_sampling=1, eta=0.1, num_steps=-1, model="sage", rng_seed=0,
                  normalize="lazy"):
     """Sampler factory with the reference's flag semantics (``train_lightning.py:349-370``)."""
-    if name in ("full", "neighbor"):
-        raise NotImplementedError(f"--sampler {name} is outside the BLISS hot path (SURVEY.md §8f row 4)")
+    if name == "full":                                                           # :349-350
+        return MultiLayerFullNeighborSampler(len(fanouts), rng_seed=rng_seed)
+    if name == "neighbor":                                                       # :351-357
+        return NeighborSampler(fanouts, rng_seed=rng_seed)
     if "ladies" in name:
         return (PoissonLadiesSampler if "poisson" in name else LadiesSampler)(fanouts, rng_seed=rng_seed)
     if "bandit" in name:
@@ -272,8 +275,12 @@ class Trainer:
             for l in reversed(range(L)):                       # output layer first: cap_dst[l] = cap_src[l+1]
                 # sources = destinations + Poisson-selected nodes (mean <= fan-out, sigma <= sqrt(fan-out)); the
                 # high-water mark in _consume_counters re-sizes long before a capacity can be hit
-                cap_src = max(cd + fan[l] + int(6 * math.sqrt(fan[l])) + 64, int(1.12 * self._max_src[l]) + 64)
+                if isinstance(dm.sampler, NeighborSampler):    # per-seed fan-outs: sized from the eager steps, bounded by |V|
+                    cap_src = min(g.num_nodes(), int(1.5 * self._max_src[l]) + 256)
+                else:
+                    cap_src = max(cd + fan[l] + int(6 * math.sqrt(fan[l])) + 64, int(1.12 * self._max_src[l]) + 64)
                 cap_src = (cap_src + 63) // 64 * 64            # row counts the split-K weight gradients divide evenly
+                cap_src = min(cap_src, g.num_nodes())          # (a frontier never holds more than |V| nodes)
                 pools[l] = LayerPool(dev, cd, cap_src, cap_e[l], bandit=bandit)
                 cd = cap_src
             padded = []
@@ -282,7 +289,8 @@ class Trainer:
                 dst_nid = pools[l + 1].src_nid if l < L - 1 else seeds_static
                 pb = Block(pool.indptr, pool.e32[0], pool.e32[1], pool.src_nid, dst_nid, graph=g, csc_pos=pool.csc_pos)
                 pb.seg_ptr, pb._mean_scale, pb._static_padded = pool.seg_ptr, pool.inv_deg, True
-                pb.edata["edge_weights"] = pool.e32[3].view(torch.float32)
+                if getattr(dm.sampler, "attach_weights", True):
+                    pb.edata["edge_weights"] = pool.e32[3].view(torch.float32)
                 pb._transpose = (pool.t_indptr, pool.t_dst, pool.t_perm, pool.t_seg_ptr)
                 pool.padded = pb
                 padded.append(pb)

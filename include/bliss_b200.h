@@ -29,6 +29,10 @@ extern "C" {
 #define BLISS_MODE_LADIES 1   /* p_j = sqrt(sum_i w_ij^2) with static w                         ladies_sampler.py:34-52 */
 #define BLISS_MODE_UNIFORM 2  /* flag OR-ed onto the above: importance_sampling=0, p_j = 1 for nodes with an out-edge  bandit_sampler.py:77-81 */
 
+#define BLISS_MODE_NEIGHBOR 4 /* flag OR-ed onto BLISS_MODE_LADIES: uniform neighbour sampling — every seed keeps min(fanout,
+                                degree) in-edges chosen uniformly without replacement (fanout <= 0: all): DGL NeighborSampler /
+                                MultiLayerFullNeighborSampler, train_lightning.py:349-357.  No probabilities, no node selection. */
+
 #define BLISS_COLLECT_BITMAP 16 /* flag OR-ed onto the mode: collect candidates from a bitmap the scatter marks
                                   (sparse frontiers in huge graphs) instead of a dense scan of the |V| accumulators */
 
@@ -190,6 +194,12 @@ int bliss_select_topk(int32_t n_seeds, int32_t fanout, uint64_t seed, uint64_t s
                       void* stream);
 int bliss_philox_fill(uint64_t seed, uint64_t step, uint32_t layer, const int32_t* nids,
                       int64_t n, float* out, void* stream);   /* test hook */
+/* uniform neighbour sampling of a planned frontier (after bliss_frontier_plan): per in-edge key =
+ * word 0 of Philox4x32-10(key = seed, ctr = (CSC position, layer | 0x8000, step)); a seed with more than `fanout`
+ * in-edges keeps its `fanout` smallest keys (ties in CSC order), else all (fanout <= 0: all).  Writes the keep bits and
+ * registers the kept edges' sources; follow with bliss_block_count(mode | BLISS_MODE_NEIGHBOR), index, fill. */
+int bliss_neighbor_select(const bliss_graph* g, int32_t n_seeds, int32_t fanout, uint64_t seed, uint64_t step,
+                          uint32_t layer, const bliss_workspace* ws, void* stream);
 
 /* ---- (3) block construction ---------------------------------------------------------------
  * replaces insg.subgraph + edge_subgraph + to_block + e_div_u/copy_e_sum/e_mul_v

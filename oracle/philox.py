@@ -47,3 +47,13 @@ def uniform_for_nodes(seed: int, step: int, layer: int, nids) -> np.ndarray:
         (nids, np.uint32(layer), np.uint32(step & 0xFFFFFFFF), np.uint32((step >> 32) & 0xFFFFFFFF)),
         (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
     return ((out[0] >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+
+
+def edge_keys(seed: int, step: int, layer: int, csc_pos) -> np.ndarray:
+    """The 32-bit key the device gives an in-edge for uniform neighbour sampling (csrc/sampler.cu ``edge_key``):
+    word 0 of ``philox(ctr=(pos_lo, layer | 0x8000 | pos_hi << 16, step_lo, step_hi), key=seed)``."""
+    pos = np.asarray(csc_pos, dtype=np.uint64)
+    c1 = (np.uint64(layer) | np.uint64(0x8000) | ((pos >> np.uint64(32)) << np.uint64(16))).astype(np.uint32)
+    out = philox4x32_10(((pos & MASK).astype(np.uint32), c1, np.uint32(step & 0xFFFFFFFF),
+                         np.uint32((step >> 32) & 0xFFFFFFFF)), (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    return out[0]

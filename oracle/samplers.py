@@ -358,3 +358,45 @@ class PoissonLadiesSampler(LadiesSampler):
     def select_neighbors(self, prob, num, insg=None):
         u = self._uniform(insg, prob)
         return torch.arange(prob.shape[0])[u < prob.to(torch.float32)]
+
+
+class NeighborSampler:
+    """``dgl.dataloading.NeighborSampler(fanouts)`` / ``MultiLayerFullNeighborSampler`` (``train_lightning.py:349-357``)
+    restated (DGL, recalled): ``for fanout in reversed(fanouts): frontier = g.sample_neighbors(seeds, fanout);
+    block = to_block(frontier, seeds); seeds = block.srcdata[NID]``.  ``sample_neighbors`` keeps, per seed,
+    ``min(fanout, in-degree)`` in-edges uniformly without replacement (``-1``: all).  DGL draws from its own generator;
+    here the draw is injectable: ``key_fn(block_id, csc_positions) -> uint32 keys`` and a seed keeps its ``fanout``
+    smallest keys (ties in CSC order) — a uniform subset for i.i.d. keys."""
+
+    def __init__(self, fanouts, key_fn=None):
+        self.fanouts, self.key_fn = [int(f) for f in fanouts], key_fn
+
+    def sample_blocks(self, g, seed_nodes, exclude_eids=None):
+        seed_nodes = seed_nodes.long()
+        output_nodes = seed_nodes
+        blocks = []
+        for block_id in reversed(range(len(self.fanouts))):
+            fanout = self.fanouts[block_id]
+            insg = ops.in_subgraph(g, seed_nodes)                  # all in-edges, seed order, CSC order within a seed
+            pos = insg.edata["_csc_pos"]
+            keep = torch.ones(insg.num_edges(), dtype=torch.bool)
+            if fanout > 0:
+                keys = torch.as_tensor(self.key_fn(block_id, pos)).long()
+                start = g.indptr[seed_nodes]
+                deg = g.indptr[seed_nodes + 1] - start
+                off = 0
+                for d in deg.tolist():
+                    if d > fanout:
+                        k = keys[off:off + d]
+                        order = torch.sort(k, stable=True).indices       # ties: CSC order
+                        m = torch.zeros(d, dtype=torch.bool)
+                        m[order[:fanout]] = True
+                        keep[off:off + d] = m
+                    off += d
+            frontier = ops.edge_subgraph(insg, keep)
+            frontier.edata[EID] = insg.edata[EID][frontier.edata[EID].long()]
+            block = ops.to_block(frontier, seed_nodes)
+            block.edata[EID] = frontier.edata[EID][block.edata[EID].long()]
+            seed_nodes = block.srcdata[NID]
+            blocks.insert(0, block)
+        return seed_nodes, output_nodes, blocks

@@ -185,33 +185,50 @@ def test_gatv2_attention_dropout_mask(native_lib):
     _close(ad.grad, ao.grad, rtol=RTOL, what="gat grad attn")
 
 
-def test_full_graph_inference(native_lib):
-    """model.inference: layer-wise full-neighbour pass (model.py:335-383) == oracle on the whole graph."""
+@pytest.mark.parametrize("kind", ["sage", "gcn", "gat"])
+def test_full_graph_inference(native_lib, kind):
+    """``model.inference``: layer-wise full-neighbour pass without edge weights (SAGE model.py:335-383, GCN :441-488,
+    GATv2 :236-289) == the oracle layers applied to the whole graph as one block.  The reference walks the nodes in
+    batches of ``batch_size`` through ``MultiLayerFullNeighborSampler(1)``; a node's output depends only on its own
+    in-edges and on the previous layer's full matrix, so one whole-graph block per layer is the same function (the
+    batch size only bounds the reference's memory) — checked here for two batch sizes as well."""
     from bliss_gnn_b200 import model as M
     from oracle import dglops
-    g = random_graph(700, 4000, seed=4)
+    g = random_graph(700, 4000, seed=4, hubs=2, hub_degree=400)
     feats = torch.randn(700, 24, generator=torch.Generator().manual_seed(5))
     g.ndata["features"] = feats
     gd = g.to(_dev())
-    dmodel = M.SAGE(24, 32, 4, 3, F.relu, 0.0).to(gd.device)
-    omod = omodel.SAGE(24, 32, 4, 3, F.relu, 0.0)
-    _copy_params(omod, dmodel)
+    torch.manual_seed(2)
+    if kind == "gat":
+        args = (3, 24, 16, 4, [2, 2, 1], F.elu, 0.0, 0.0, 0.2, True)
+        dmodel, omod = M.GATv2(*args).to(gd.device), omodel.GATv2(*args)
+    else:
+        cls_d, cls_o = (M.SAGE, omodel.SAGE) if kind == "sage" else (M.GCN, omodel.GCN)
+        dmodel, omod = cls_d(24, 32, 4, 3, F.relu, 0.0).to(gd.device), cls_o(24, 32, 4, 3, F.relu, 0.0)
+    copy_params(omod, dmodel, torch.float64)
+    omod = omod.double()
     pred = dmodel.inference(gd, gd.device, 128)
+    assert torch.equal(pred, dmodel.inference(gd, gd.device, 7))       # the batch size does not change the function
     src, dst = g.coo()
     order = torch.sort(dst, stable=True).indices
     full = dglops.OBlock(src[order], dst[order], 700, 700)
-    h = feats
+    h = feats.double()
     with torch.no_grad():
-        for l, layer in enumerate(omod.layers):
-            h = layer(full, h)
-            if l < 2:
-                h = F.relu(h)
-    _close(pred, h, what="full-graph inference")
+        if kind == "gat":
+            for l, layer in enumerate(omod.gatv2_layers):
+                h = layer(full, h)
+                h = h.flatten(1) if l < 2 else h.mean(1)
+        else:
+            for l, layer in enumerate(omod.layers):
+                h = layer(full, h)
+                if l < 2 and kind == "sage":
+                    h = F.relu(h)                                     # (GraphConv applies its activation itself)
+    _close(pred, h, what=f"{kind} full-graph inference")
 
 
 @pytest.mark.parametrize("kind,sampler", [("sage", "poisson-bandit"), ("gcn", "poisson-bandit"), ("gat", "poisson-bandit"),
                                           ("sage", "bandit"), ("sage", "ladies"), ("sage", "poisson-ladies"),
-                                          ("sage", "poisson-bandit/literal")])
+                                          ("sage", "poisson-bandit/literal"), ("sage", "neighbor"), ("gcn", "full")])
 def test_static_graph_step_matches_eager(native_lib, kind, sampler):
     """Trainer(static_graph=True) — the whole step (sampling with every sampler of the CLI, forward, backward,
     Adam, bandit update) as one replayed CUDA graph over capacity-padded blocks — follows the same loss

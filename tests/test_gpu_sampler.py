@@ -345,3 +345,59 @@ def test_packed_exchange_apply_matches_sequential_updates(native_lib):
         torch.testing.assert_close(w_dev[l].cpu().double(), expect[l], rtol=1e-6, atol=0)
         delta = float(l1[l].item())
         assert abs(delta - float((expect[l] - w[l].double()).sum())) <= 1e-5 * abs(delta)
+
+
+@pytest.mark.parametrize("fanouts", [[10, 5, 3], [300, 40, -1], [-1, -1]])
+def test_neighbor_and_full_samplers_match_oracle(native_lib, fanouts):
+    """``--sampler neighbor | full`` (train_lightning.py:349-357): per-seed uniform k-subsets of the in-edges (all of them
+    for -1) and ``to_block`` relabelling — block structure bit-exact against the oracle restatement under the same
+    per-edge Philox keys; rows of 1,500 in-edges exercise the radix select, fan-outs above the degree the take-all
+    branch; the blocks carry no edge weights."""
+    from bliss_gnn_b200.sampler import MultiLayerFullNeighborSampler, NeighborSampler
+    V, E, hubs, hdeg, batch, _ = GRAPHS["heavy"]
+    g = random_graph(V, E, seed=5, hubs=hubs, hub_degree=hdeg)
+    seeds = torch.randperm(V, generator=torch.Generator().manual_seed(1))[:batch]
+    seeds[:hubs] = torch.arange(hubs)
+    gd = g.to(_dev())
+    seed = 13
+    full = all(f < 0 for f in fanouts)
+    dev = MultiLayerFullNeighborSampler(len(fanouts), rng_seed=seed) if full else NeighborSampler(fanouts, rng_seed=seed)
+    for step in range(2):
+        ora = osamp.NeighborSampler(fanouts, key_fn=lambda l, pos, st=step: torch.from_numpy(
+            philox.edge_keys(seed, st, l, pos.numpy()).astype(np.int64)))
+        o_in, _, ob = ora.sample_blocks(g, seeds)
+        d_in, d_out, db = dev.sample_blocks(gd, seeds)
+        assert torch.equal(d_in.cpu().long(), o_in) and torch.equal(d_out.cpu().long(), seeds)
+        for l, (a, b) in enumerate(zip(db, ob)):
+            assert_blocks_equal(a, b, check=())
+            assert "edge_weights" not in dict.keys(a.edata)
+            deg = g.in_degrees(b.dstdata["_ID"])
+            want = deg if fanouts[l] < 0 else deg.clamp(max=fanouts[l])
+            assert torch.equal(a.in_degrees().cpu().long(), want), "every seed keeps min(fanout, in-degree) in-edges"
+    w = dev._wsp      # workspace invariant restored (nothing |V|-sized is cleared per step)
+    assert int(w.acc.count_nonzero()) == 0 and int((w.node_info[0::2] != -1).sum()) == 0
+    assert int(w.sel_bits.count_nonzero()) == 0
+
+
+def test_neighbor_sampler_is_uniform(native_lib):
+    """Every in-edge of a 1,500-edge row is kept with probability fanout / degree: 600 steps x fan-out 50, per-edge
+    counts against the binomial expectation (5 sigma) and a chi-square of the whole row."""
+    from bliss_gnn_b200.sampler import NeighborSampler
+    V, E, hubs, hdeg, _, _ = GRAPHS["heavy"]
+    g = random_graph(V, E, seed=5, hubs=hubs, hub_degree=hdeg).to(_dev())
+    dev = NeighborSampler([50], rng_seed=3)
+    seeds = torch.tensor([0])
+    d = int(g.in_degrees(seeds.to(g.device))[0])
+    counts = torch.zeros(g.num_edges(), device=g.device)
+    steps = 600
+    for _ in range(steps):
+        _, _, (b,) = dev.sample_blocks(g, seeds)
+        assert b.num_edges() == 50
+        counts[b.csc_pos.long()] += 1
+    a = int(g.indptr[0])
+    c = counts[a:a + d].cpu().double()
+    p = 50.0 / d
+    mean, sd = steps * p, (steps * p * (1 - p)) ** 0.5
+    assert float((c - mean).abs().max()) < 5.5 * sd, (float(c.min()), float(c.max()), mean, sd)
+    chi2 = float(((c - mean) ** 2 / (steps * p * (1 - p))).sum())
+    assert abs(chi2 - d) < 6 * (2 * d) ** 0.5, (chi2, d)
