@@ -451,7 +451,7 @@ def roofline_tables(per_kernel, sizes, n_prof, in_feats, layer_dims, peak, peak_
             bts = stage_bytes(whole_stage[name], sizes, in_feats, layer_dims)
             row.update({"alg_bytes_per_launch": bts / max(calls, 1), "achieved": bts / 1e9 / (ms / 1e3),
                         "frac": bts / 1e9 / (ms / 1e3) / peak})
-        t = traffic_tab.get(name, {}).get("dram_bytes_per_launch")
+        t = traffic_tab.get("kernels", {}).get(name, {}).get("dram_bytes_per_launch")
         if t is not None:
             row["traffic"] = t
         kernels.append(row)

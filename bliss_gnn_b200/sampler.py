@@ -666,7 +666,7 @@ class BanditLadiesSampler:
     def tick_renorm(self, n_layers: int):
         """Lazy mode's range safety: physically re-normalise every ``renorm_every`` updates (a weight
         grows by at most e per update, ``bandit_sampler.py:244-246``)."""
-        if self.normalize != "lazy":
+        if self.normalize != "lazy" or self._w_csc is None:     # (the LADIES / uniform samplers have no bandit state)
             return
         # every rank's update lands on this copy of the weights: an edge sampled by all W ranks can grow by e^W per
         # step, so the range guard counts APPLIED updates, not steps

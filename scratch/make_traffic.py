@@ -22,7 +22,7 @@ for r in rows[2:]:
     d["time_us"] += t
 ENTRY = {"bliss_frontier_prob": ["k_prob_pass1", "k_prob_pass2", "k_prob_pass3", "k_collect_candidates"],
          "bliss_block_count": ["k_block_count"], "bliss_block_index": ["k_block_index"],
-         "bliss_block_fill": ["k_block_fill"], "bliss_spmm": ["k_spmm_seg", "k_spmm_combine"]}
+         "bliss_block_fill": ["k_block_fill"], "bliss_spmm": ["k_spmm_item", "k_spmm_seg", "k_spmm_combine_items", "k_spmm_combine"]}
 res = {"_source": f"ncu --set full --clock-control none, {rep} (scratch/exp_layer.py: Reddit-shape step, stage path; "
                   "cold-cache replays, so kernels that hit L2 in a real step show their inputs as DRAM reads here); "
                   "dram__bytes_read.sum + dram__bytes_write.sum per launch", "kernels": {}}

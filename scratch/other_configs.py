@@ -14,21 +14,22 @@ for shape, kind, sampler in [("flickr", "gat", "poisson-bandit"), ("yelp", "sage
     torch.manual_seed(3)
     model = build_model(kind, dm.in_feats, 256, dm.n_classes, 3, 0.1, faithful_gcn_quirk=False).to(dev)
     tr = Trainer(dm, model, 0.002, static_graph=True, eager_warmup=6)
-    it = dm.train_batches()
+    batches = []
+    while len(batches) < 16 + 200 + 1:
+        batches.extend(dm.train_batches())
     losses = []
     for i in range(16):
-        losses.append(tr.training_step(next(it)))
+        losses.append(tr.training_step(batches[i], batches[i + 1]))
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    n = 60
-    for i in range(n):
-        try:
-            seeds = next(it)
-        except StopIteration:
-            it = dm.train_batches(); seeds = next(it)
-        loss = tr.training_step(seeds)
-    tr.flush(); torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    n = 200
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(16, 16 + n):
+        loss = tr.training_step(batches[i], batches[i + 1])      # the next batch is announced (look-ahead sampling)
+    tr.flush()
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) / 1e3
     print(f"{shape:7s} {kind:5s} {sampler:15s} V={g.num_nodes()} E={g.num_edges()} replays={tr.graph_replays} resizes={tr.pool_resizes} "
           f"steps/s={n/dt:8.1f} loss {float(losses[0]):.4f} -> {float(loss):.4f} blocks {[ (b.num_src_nodes(), b.num_edges()) for b in tr.last_blocks]}", flush=True)
     del tr, dm, model, g

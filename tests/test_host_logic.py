@@ -67,3 +67,37 @@ def test_cli_flags_match_the_reference_defaults():
         ("sage", "poisson-bandit", "16384,8192,4096", 1024, 256, 3)
     assert (a.eta, a.lr, a.dropout, a.importance_sampling, a.precision) == (0.1, 0.002, 0.1, 1, "medium")
     assert toy_graph().num_nodes() == 5
+
+
+def test_early_stopping_and_vertex_limit_controllers():
+    """``EarlyStopping(monitor='val_acc', mode='max', stopping_threshold, patience)`` (train_lightning.py:627-634) and
+    ``BatchSizeCallback`` (:425-486) restated without Lightning."""
+    from bliss_gnn_b200.train import BatchSizeController, EarlyStopping
+    es = EarlyStopping(stopping_threshold=0.9, patience=2)
+    assert [es.check(v) for v in (0.5, 0.6, 0.6, 0.55)] == [False, False, False, True]      # two checks without a new best
+    assert EarlyStopping(0.9, 100).check(0.95) and not EarlyStopping(1, 100).check(1.0)      # strictly above the threshold
+    c = BatchSizeController(limit=1000)
+    for x in (2000, 2100, 1900, 2050):
+        c.push(x)
+    assert abs(c.m - 2012.5) < 1e-9 and c.n == 4
+    assert c.on_train_epoch_end(64) == int(64 * 1000 / 2012.5) and c.n == 0                  # rescaled, statistics cleared
+    off = BatchSizeController(limit=-1)
+    off.push(5.0)
+    off.push(7.0)
+    assert off.on_train_epoch_end(64) == 64                                                  # --vertex-limit -1: never
+
+
+def test_sampler_factory_follows_the_flag():
+    """``--sampler`` choices of the reference CLI (train_lightning.py:349-370, :538-543)."""
+    from bliss_gnn_b200 import sampler as S
+    from bliss_gnn_b200.train import make_sampler
+    want = {"full": S.MultiLayerFullNeighborSampler, "neighbor": S.NeighborSampler, "bandit": S.BanditLadiesSampler,
+            "poisson-bandit": S.PoissonBanditLadiesSampler, "ladies": S.LadiesSampler, "poisson-ladies": S.PoissonLadiesSampler}
+    for name, cls in want.items():
+        s = make_sampler(name, [16, 8, 4], eta=0.1)
+        assert type(s) is cls, name
+        assert len(s.nodes_per_layer) == 3
+    assert make_sampler("full", [16, 8]).nodes_per_layer == [-1, -1]
+    assert not make_sampler("neighbor", [5, 5]).attach_weights and make_sampler("ladies", [5, 5]).attach_weights
+    args = build_argparser().parse_args(["--sampler", "neighbor", "--vertex-limit", "5000", "--early-stopping-patience", "3"])
+    assert args.sampler == "neighbor" and args.vertex_limit == 5000 and args.early_stopping_patience == 3

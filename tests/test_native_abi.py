@@ -44,9 +44,11 @@ def test_struct_layouts_match_header(tmp_path):
 #include <stddef.h>
 #include "bliss_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(bliss_graph), sizeof(bliss_counters), sizeof(bliss_workspace),
-         sizeof(bliss_block_out), offsetof(bliss_counters, c), offsetof(bliss_counters, error),
-         offsetof(bliss_workspace, ctr), offsetof(bliss_block_out, cap_edges));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(bliss_graph), sizeof(bliss_counters),
+         sizeof(bliss_workspace), sizeof(bliss_block_out), offsetof(bliss_counters, c), offsetof(bliss_counters, error),
+         offsetof(bliss_workspace, ctr), offsetof(bliss_block_out, cap_edges), sizeof(bliss_p2p),
+         offsetof(bliss_p2p, flags_off), offsetof(bliss_p2p, done_ctr), sizeof(bliss_grad_p2p),
+         offsetof(bliss_grad_p2p, step_dev));
   return 0;
 }
 """)
@@ -54,7 +56,9 @@ int main(void) {
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [ctypes.sizeof(N.Graph), ctypes.sizeof(N.Counters), ctypes.sizeof(N.Workspace), ctypes.sizeof(N.BlockOut),
-            N.Counters.c.offset, N.Counters.error.offset, N.Workspace.ctr.offset, N.BlockOut.cap_edges.offset]
+            N.Counters.c.offset, N.Counters.error.offset, N.Workspace.ctr.offset, N.BlockOut.cap_edges.offset,
+            ctypes.sizeof(N.P2P), N.P2P.flags_off.offset, N.P2P.done_ctr.offset, ctypes.sizeof(N.GradP2P),
+            N.GradP2P.step_dev.offset]
     assert got == want
 
 
