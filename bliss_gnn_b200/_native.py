@@ -100,7 +100,7 @@ class P2P(C.Structure):
     _fields_ = [("peer_base", C.c_void_p), ("world", C.c_int32), ("rank", C.c_int32), ("parity_stride", C.c_int64),
                 ("rank_stride", C.c_int64), ("count_off", C.c_int64), ("pos_off", C.c_int64), ("x_off", C.c_int64),
                 ("flags_off", C.c_int64), ("layer", C.c_int32), ("n_layers", C.c_int32), ("step_dev", C.c_void_p),
-                ("done_ctr", C.c_void_p)]
+                ("done_ctr", C.c_void_p), ("pull", C.c_int32), ("pad_", C.c_int32)]
 
 
 class GradP2P(C.Structure):

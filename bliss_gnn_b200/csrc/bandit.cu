@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
   const int W = p.p2p.world;
   const long long xstep = W ? *p.p2p.step_dev : 0;
   const int parity = (int)(xstep & 1);
-  if (W && blockIdx.x == 0 && threadIdx.x < W)      // this layer's edge count into my slot of every window
+  const int r_lo = (W && p.p2p.pull) ? p.p2p.rank : 0, r_hi = (W && p.p2p.pull) ? p.p2p.rank + 1 : W;   // windows written
+  if (W && blockIdx.x == 0 && (int)threadIdx.x >= r_lo && (int)threadIdx.x < r_hi)   // this layer's edge count
     *reinterpret_cast<int64_t*>(p2p_slot(p.p2p, threadIdx.x, parity, p.p2p.rank) + p.p2p.count_off) = n_edges;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += stride) {
     const int i = p.edge_dst[e];
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
     if (x > 1.0f) x = 1.0f;                                                      // :244
     if (p.x_out) p.x_out[e] = x;
     if (p.pos_out) p.pos_out[e] = (int32_t)pos;
-    for (int r = 0; r < W; ++r) {                   // my slot in rank r's window (r == rank: the local copy)
+    for (int r = r_lo; r < r_hi; ++r) {             // my slot in rank r's window (pull mode: only my own window)
       unsigned char* slot = p2p_slot(p.p2p, r, parity, p.p2p.rank);
       reinterpret_cast<int32_t*>(slot + p.p2p.pos_off)[e] = (int32_t)pos;
       reinterpret_cast<float*>(slot + p.p2p.x_off)[e] = x;
@@ -188,7 +189,8 @@ __global__ void __launch_bounds__(256) k_apply_updates_p2p(bliss_p2p q, int64_t 
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += stride) {
     const int r = (int)(t / cap);
     const int64_t k = t - (int64_t)r * cap;
-    const unsigned char* base = p2p_slot(q, q.rank, parity, r);
+    // push: every rank stored its slot into my window; pull: rank r's slot is read from rank r's window over NVLink
+    const unsigned char* base = p2p_slot(q, q.pull ? r : q.rank, parity, r);
     const int64_t n = __ldcg(reinterpret_cast<const long long*>(base + q.count_off));   // (L1 may hold the slot's old lines)
     if (k >= n) continue;
     const int64_t pos = __ldcg(reinterpret_cast<const int32_t*>(base + q.pos_off) + k);

@@ -106,7 +106,9 @@ class BanditExchange:
         """Symmetric-memory window per rank (``torch.distributed._symmetric_memory``: CUDA VMM allocations mapped into
         every rank of the node): [2 parities][world slots of ``stride`` bytes] ++ flags[2][L][world] uint64.  The reward
         kernel of every rank stores its updates into its slot of EVERY window over NVLink and raises a flag per layer;
-        the apply kernel polls the local flags (``csrc/bandit.cu``) — the all-gather is fused into the producer."""
+        the apply kernel polls the local flags (``csrc/bandit.cu``) — the all-gather is fused into the producer.
+        (``BLISS_P2P_PULL=1``: the producer stores locally only and the consumer reads the peers' windows — measured at
+        N = 8: 1.31 ms per step against 0.74 ms for push, the scattered CAS loop then waits on NVLink read latency.)"""
         import torch.distributed._symmetric_memory as symm
         from . import _native as N
         L, W = len(self.caps), self.world
@@ -128,7 +130,8 @@ class BanditExchange:
                                parity_stride=W * self.stride, rank_stride=self.stride, count_off=8 * l,
                                pos_off=self.pos_off[l], x_off=self.x_off[l], flags_off=self.flags_off, layer=l,
                                n_layers=L, step_dev=self.step_dev.data_ptr(),
-                               done_ctr=self.done_ctr[l:].data_ptr()) for l in range(L)]
+                               done_ctr=self.done_ctr[l:].data_ptr(),
+                               pull=1 if os.environ.get("BLISS_P2P_PULL", "0") == "1" else 0) for l in range(L)]
         torch.cuda.synchronize(self.device)
         dist.barrier(group)               # every window is zeroed before anybody stores into it
         self.p2p = True

@@ -147,6 +147,10 @@ typedef struct bliss_p2p {
   int32_t  layer, n_layers;
   const int64_t* step_dev;    /* exchange step counter on the device */
   uint32_t* done_ctr;         /* [1] zero between launches: last-CTA detection of the producing kernel */
+  int32_t  pull;              /* 0: the producer stores its slot into EVERY rank's window (push);
+                                 1: it stores only into its OWN window and raises the flags everywhere, the consumer
+                                    reads slot r from rank r's window over NVLink (pull: no duplicated stores) */
+  int32_t  pad_;
 } bliss_p2p;
 
 /* Gradient all-reduce through peer memory, fused into the optimizer step: window = [2 parities][world slots of
