@@ -73,6 +73,40 @@ def test_spmm_forward_backward(native_lib, dim):
         _close(x.grad, xr.grad, what=f"spmm bwd D={dim}")
 
 
+@pytest.mark.parametrize("env", [{"BLISS_SPMM_MODE": "group"}, {"BLISS_SPMM_TMA": "1"}, {"BLISS_SPMM_LB": "5"}])
+def test_spmm_variants_agree(native_lib, env):
+    """The SpMM variants kept for the ablation (profiles/r2_spmm_variants.md) — round-1 group kernel, cp.async.bulk
+    ring, other register budget — are selected by environment variables read once per process, so each runs in a
+    child process: forward and transposed SpMM over blocks with 600-edge rows against a float64 reference (1e-5)."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from tests.test_gpu_ops import _sample, _close
+from bliss_gnn_b200 import ops
+g, gd, ob, db = _sample(fan=(512, 256, 64), V=3000, E=20000, batch=48, hubs=4, hub_degree=1500)
+for blk in db:
+    for dim in (256, 128, 64, 300):
+        x = torch.randn(blk.num_src_nodes(), dim, device=gd.device, requires_grad=True)
+        w = blk.edata["edge_weights"]
+        y = ops.spmm(blk, x, w, dst_scale=ops.mean_scale(blk))
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        src, dst = blk.edge_src.long(), blk.edge_dst.long()
+        xr = x.detach().double().requires_grad_(True)
+        yr = torch.zeros(blk.num_dst_nodes(), dim, device=gd.device, dtype=torch.float64).index_add(
+            0, dst, xr[src] * w.double().unsqueeze(1)) * ops.mean_scale(blk).double().unsqueeze(1)
+        yr.backward(gy.double())
+        _close(y, yr, what="fwd")
+        _close(x.grad, xr.grad, what="bwd")
+print("ok")
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_block_transpose_is_sorted(native_lib):
     from bliss_gnn_b200 import ops
     _, gd, _, db = _sample()
