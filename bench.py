@@ -310,10 +310,9 @@ def main():
     value = world * args.steps / (ms_total / 1e3)
 
     # ---- (2) end to end: seeds from pinned host memory every step, loss read back every step ----
-    # The loss of every step is copied to pinned host memory stream-ordered and consumed one step later
-    # (like the step's counters), so the host never stalls the device inside the loop.
-    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    # The step graph copies its loss and its blocks' counters to pinned host memory itself (Trainer.host_loss,
+    # Trainer._ctr_pin); the host consumes them one step later, so it never stalls the device inside the loop.
+    # The seeds are host tensors: staged through pinned memory on a copy stream (Trainer._stage_seeds).
     e2e_ms = []
     for _ in range(REPEATS):
         barrier()
@@ -322,15 +321,11 @@ def main():
         e0.record()
 
         def read_back(i, loss):
-            loss_host[i & 1].copy_(loss.reshape(1), non_blocking=True)
-            loss_ev[i & 1].record()
-            if i:
-                loss_ev[(i - 1) & 1].synchronize()
-                losses.append(float(loss_host[(i - 1) & 1]))
+            if i:                                  # the previous step's loss: already in pinned memory, no stall
+                losses.append(tr.host_loss(back=1))
 
         run_steps(host_batches, args.steps, read_back)
-        loss_ev[(args.steps - 1) & 1].synchronize()
-        losses.append(float(loss_host[(args.steps - 1) & 1]))
+        losses.append(tr.host_loss())
         tr.flush()
         e1.record()
         barrier()
@@ -368,10 +363,10 @@ def main():
            "repeats": REPEATS, "ms_per_step_all_regions": [m / args.steps for m in region_ms],
            "sampled_edges_per_s": world * edges / (sum(region_ms) / 1e3), "clocks": clock_info,
            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": BATCH * 4 * world,
-                   "d2h_bytes_per_step": (4 + dm.sampler._wsp.ctr_all.numel()) * world,
+                   "d2h_bytes_per_step": (4 + 8 * dm.sampler._wsp.ctr_all.shape[1]) * world,
                    "ms_per_step_all_regions": [m / args.steps for m in e2e_ms],
-                   "note": "seeds H2D from pinned memory every step; loss + per-layer counters D2H every step, "
-                           "copied stream-ordered and consumed one step later"},
+                   "note": "seeds H2D from pinned memory every step (copy stream); loss + per-layer counters D2H every "
+                           "step (copy nodes of the step graph), consumed by the host one step later"},
            "gpu_launches": launches, "graph_replays": tr.graph_replays,
            "pool_resizes_in_timed_regions": tr.pool_resizes - resizes0}
     out.update(rl)

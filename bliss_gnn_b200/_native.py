@@ -85,7 +85,8 @@ class Workspace(C.Structure):
                 ("chunk_first", C.c_void_p), ("chunk_rec", C.c_void_p), ("part_w", C.c_void_p), ("part_q", C.c_void_p),
                 ("row_w", C.c_void_p), ("row_q", C.c_void_p),
                 ("row_cnt", C.c_void_p), ("part_cnt", C.c_void_p), ("part_t", C.c_void_p), ("chunk_pre", C.c_void_p), ("row_t", C.c_void_p), ("cap_seeds", C.c_int64),
-                ("cap_sel", C.c_int64), ("ctr", C.c_void_p), ("n_seeds_dev", C.c_void_p), ("step_dev", C.c_void_p)]
+                ("cap_sel", C.c_int64), ("ctr", C.c_void_p), ("n_seeds_dev", C.c_void_p), ("step_dev", C.c_void_p),
+                ("ctr_mirror", C.c_void_p)]
 
 
 class BlockOut(C.Structure):

@@ -1161,6 +1161,8 @@ __global__ void __launch_bounds__(256) k_block_finish(int mode, bliss_workspace 
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   (void)mode;  // the rows are normalised by k_block_fill itself; this kernel only restores the workspace
+  if (ws.ctr_mirror && t0 < (int64_t)(sizeof(bliss_counters) / sizeof(int32_t)))   // counters are final: host copy
+    reinterpret_cast<volatile int32_t*>(ws.ctr_mirror)[t0] = reinterpret_cast<const int32_t*>(ctr)[t0];
   for (int64_t j = t0; j < n_cand; j += stride) {
     int nid = ws.cand[j];
     ws.acc[nid] = 0ull;

@@ -71,9 +71,6 @@ class _Workspace:
         self.ctr = self.ctr_all[0]
         self.ctr_host = torch.zeros(csz, dtype=torch.uint8).pin_memory()
         self.ctr_all_host = torch.zeros(self.MAX_LAYERS, csz, dtype=torch.uint8).pin_memory()
-        # two more pinned copies + events: a step's counters can be read while the next step runs
-        self._ctr_slots = [torch.zeros(self.MAX_LAYERS, csz, dtype=torch.uint8).pin_memory() for _ in range(2)]
-        self._ctr_events = [torch.cuda.Event() for _ in range(2)]
         self.ws = N.Workspace(
             acc=N.ptr(self.acc), first_pos=N.ptr(self.first_pos), node_info=N.ptr(self.node_info),
             sel_bits=N.ptr(self.sel_bits), cand_bits=N.ptr(self.cand_bits), keep_bits=N.ptr(self.keep_bits), cand=N.ptr(self.cand), p_cand=N.ptr(self.p_cand), sel=N.ptr(self.sel),
@@ -87,7 +84,7 @@ class _Workspace:
         self._keep = (g.indptr, g.indices, g.eid)
         N.call("bliss_workspace_init", C.byref(self.ws), V, N.stream())
 
-    def ws_layer(self, layer: int, n_seeds_dev=None, step_dev=None, counters=None) -> "N.Workspace":
+    def ws_layer(self, layer: int, n_seeds_dev=None, step_dev=None, counters=None, ctr_mirror=None) -> "N.Workspace":
         """The workspace descriptor with layer ``layer``'s own counters block and, for sync-free
         chaining, the device addresses the kernels read the seed count / Philox step from.
         ``counters``: the workspace whose per-layer counters blocks to use (the step's second workspace
@@ -96,6 +93,7 @@ class _Workspace:
         ws.ctr = (counters or self).ctr_all[layer].data_ptr()
         ws.n_seeds_dev = n_seeds_dev
         ws.step_dev = step_dev
+        ws.ctr_mirror = ctr_mirror                # (pinned host address or None: see include/bliss_b200.h)
         return ws
 
     def counter_ptr(self, layer: int, field: str) -> int:
@@ -107,18 +105,6 @@ class _Workspace:
         torch.cuda.current_stream().synchronize()
         raw = self.ctr_all_host.numpy()
         return [N.Counters.from_buffer_copy(raw[l].tobytes()) for l in range(n_layers)]
-
-    def enqueue_counter_read(self, slot: int):
-        """Stream-ordered D2H copy of all layers' counters into pinned slot ``slot`` (no host wait)."""
-        self._ctr_slots[slot].copy_(self.ctr_all, non_blocking=True)
-        self._ctr_events[slot].record()
-
-    def finish_counter_read(self, slot: int, n_layers: int, base: int = 0):
-        """Wait for :meth:`enqueue_counter_read` of ``slot`` and parse the counters of the blocks
-        ``base .. base + n_layers`` (the whole-step graph keeps one group of counter blocks per pool set)."""
-        self._ctr_events[slot].synchronize()
-        raw = self._ctr_slots[slot].numpy()
-        return [N.Counters.from_buffer_copy(raw[base + l].tobytes()) for l in range(n_layers)]
 
     def read_counters(self) -> N.Counters:
         self.ctr_host.copy_(self.ctr, non_blocking=True)
@@ -464,7 +450,7 @@ class BanditLadiesSampler:
 
     # ---- sync-free path (CUDA-graph capture of the whole step) -----------------------------------
     def enqueue_static(self, g, seeds_static, pools, step_dev, transpose_stream=None, defer_last_transpose=False,
-                       ctr_base: int = 0, layer_pre=None):
+                       ctr_base: int = 0, layer_pre=None, ctr_mirror=None):
         """Enqueue the sampling of every layer into the capacity pools with NO host synchronisation:
         each layer reads its true seed count from the previous layer's device counters, the Philox
         step from ``step_dev``, and the transpose its edge count from the counters.  Capturable in a
@@ -477,7 +463,9 @@ class BanditLadiesSampler:
         counters block to use (layer l writes block ``ctr_base + l``): the pipelined step samples the NEXT step's
         blocks into a second pool set while this step's backward pass still reads the first set's counts.
         ``layer_pre``: ``{layer: callable}`` run on the current stream right before that layer is sampled (the
-        data-parallel step applies all ranks' bandit updates of a layer just before the layer's weights are read)."""
+        data-parallel step applies all ranks' bandit updates of a layer just before the layer's weights are read).
+        ``ctr_mirror``: pinned host tensor ``[>= L, sizeof(counters)]``; layer l's finish kernel writes its counters
+        to row l (device-mapped host memory), so the caller needs no device-to-host copy after the step."""
         wsp = self._bind(g)
         L = len(self.nodes_per_layer)
         bandit = self._mode == N.MODE_BANDIT
@@ -496,7 +484,8 @@ class BanditLadiesSampler:
             seeds = seeds_static if top else pools[block_id + 1].src_nid
             n_cap = pool.cap_dst
             ws = w.ws_layer(ctr_base + block_id, None if top else wsp.counter_ptr(ctr_base + block_id + 1, "n_src"),
-                            N.ptr(step_dev), counters=wsp)
+                            N.ptr(step_dev), counters=wsp,
+                            ctr_mirror=None if ctr_mirror is None else ctr_mirror[block_id].data_ptr())
             weights = self._w_csc[block_id] if bandit else weights_static
             mode = self._mode | (0 if self.importance_sampling else N.MODE_UNIFORM)
             if self.collect == "bitmap" or (self.collect == "auto" and g.num_nodes() > self.DENSE_COLLECT_MAX):

@@ -139,6 +139,9 @@ class Trainer:
         self.dm, self.model, self.pg = datamodule, model, process_group
         self.static_graph, self.eager_warmup = bool(static_graph), int(eager_warmup)
         self.pipeline, self._pending = bool(pipeline), None
+        self._ctr_pins, self._call_done, self._set_free = {}, None, [None, None]
+        self._loss_hist, self._loss_pins = [], None
+        self._seed_stage, self._seed_staged, self._copy_stream = [None, None], [None, None], None
         self.total_sampled_edges = 0        # Σ block edges over all consumed steps (bench.py's edges/s)
         self.pool_resizes = 0               # capacity re-sizings (each one re-captures the step graph)
         self._dev_step_mirror = None        # host's view of the device-side Philox step counter
@@ -194,13 +197,30 @@ class Trainer:
         """One training step on ``seeds``.  ``next_seeds`` (optional): the batch the NEXT call will train on — the
         look-ahead of a data loader; the static-graph path then samples its blocks in the shadow of this step's
         backward pass (after this step's ``exp3``, so the trajectory is the reference's)."""
+        self._graph_loss = None
         if self.static_graph:
             if self._full_graph_ok():
-                return self._training_step_full_graph(seeds, next_seeds)
-            return self._training_step_static_partial(seeds)
-        dm, g = self.dm, self.dm.g
-        input_nodes, output_nodes, mfgs = dm.sampler.sample_blocks(g, seeds)
-        return self._eager_rest(mfgs)
+                loss = self._training_step_full_graph(seeds, next_seeds)
+            else:
+                loss = self._training_step_static_partial(seeds)
+        else:
+            dm, g = self.dm, self.dm.g
+            input_nodes, output_nodes, mfgs = dm.sampler.sample_blocks(g, seeds)
+            loss = self._eager_rest(mfgs)
+        # (a step that was not a graph replay keeps the tensor itself)
+        self._loss_hist = (self._loss_hist + [self._graph_loss or ("eager", loss)])[-2:]
+        return loss
+
+    def host_loss(self, back: int = 0) -> float:
+        """The loss of the last ``training_step`` call (``back=0``: waits for that step) or of the call before it
+        (``back=1``: in a loop that runs one step ahead of the device this does not stall).  A replayed step graph
+        copies its loss to pinned host memory itself, so no copy has to be enqueued between two step graphs."""
+        kind, ref = self._loss_hist[-1 - back]
+        if kind == "eager":
+            return float(ref)
+        slot, p = ref
+        self._call_done[slot].synchronize()
+        return float(self._loss_pins[p])
 
     def _eager_rest(self, mfgs):
         dm, g = self.dm, self.dm.g
@@ -310,6 +330,7 @@ class Trainer:
         """``after_forward`` / ``before_backward``: hooks of the whole-step graph — work that only needs the
         forward pass is forked onto side streams there, work the backward pass needs is joined."""
         loss, pred, y = self._padded_fwd(pset, inputs)
+        self._fwd_loss = loss.detach()
         if after_forward is not None:
             after_forward()
         self._zero_grads()
@@ -338,7 +359,7 @@ class Trainer:
         g = self.dm.g
         if ahead and pset.x is not None:
             ops.gather_rows(g.ndata["features"], pset.pools[0].src_nid, with_norm=True, out=pset.x, norm_out=pset.x_norm)
-            self._gather_labels(g.ndata["labels"], pset.seeds, out=pset.y)
+            self._gather_labels(g.ndata["labels"], pset.seeds_in, out=pset.y)
             return pset.x, pset.x_norm, pset.y
         x, norm = ops.gather_rows(g.ndata["features"], pset.pools[0].src_nid, with_norm=True)
         return x, norm, self._gather_labels(g.ndata["labels"], pset.seeds)
@@ -476,6 +497,9 @@ class Trainer:
             self._alloc_pools()
         if not self._graphs:
             self._capture_full()
+        if self._call_done is None:
+            self._call_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._copy_stream = torch.cuda.Stream()
         self._sync_lr()
         if self._next_ready and seeds is not self._prefetched_seeds:
             self._drop_prefetch()                              # the caller trains on another batch than announced
@@ -484,15 +508,15 @@ class Trainer:
             self._dev_step_mirror = smp.step
         p = self._cur
         cur, nxt = self._sets[p], self._sets[1 - p]
-        fresh = []                                             # pool sets whose counters this call produces
+        fresh = []                      # (kind, set): pinned counter buffers this call's graphs write (see _ctr_pin)
         if not self._next_ready:
-            cur.seeds.copy_(seeds, non_blocking=True)
+            cur.seeds_in.copy_(seeds, non_blocking=True)
             self._replay(("S", p))
             smp.step += 1
-            fresh.append(p)
+            fresh.append(("S", p))
         prefetch = next_seeds is not None and next_seeds.numel() == dm.batch_size
         if prefetch:
-            nxt.seeds.copy_(next_seeds, non_blocking=True)
+            self._stage_seeds(nxt, next_seeds)
         if self._exchange is None and not (self.world > 1 or self._force_dp):
             self._replay(("G" if prefetch else "GN", p))
         else:                                                  # data parallel: see _capture_full
@@ -527,7 +551,7 @@ class Trainer:
             main.wait_stream(self._side_apply)
         if prefetch:
             smp.step += 1
-            fresh.append(1 - p)
+            fresh.append(("G", 1 - p))
         self._dev_step_mirror = smp.step
         self._next_ready, self._prefetched_seeds = prefetch, (next_seeds if prefetch else None)
         self._cur = 1 - p
@@ -535,7 +559,10 @@ class Trainer:
                                                                                 else ("N", p)]
         slot = self.graph_replays & 1
         self.graph_replays += 1
-        smp._wsp.enqueue_counter_read(slot)                    # stream-ordered D2H, no host wait
+        self._call_done[slot].record()            # (counters and loss were copied to pinned memory inside the graphs)
+        self._graph_loss = ("graph", (slot, p))
+        for _, q in fresh:                        # … and the seed buffers its sampling read may be overwritten after it
+            self._set_free[q] = self._call_done[slot]
         smp.tick_renorm(L)
         if self.pipeline:                                      # consume the PREVIOUS call's counters
             prev, self._pending = self._pending, (slot, fresh)
@@ -544,6 +571,43 @@ class Trainer:
             slot, fresh = prev
         self._consume_counters(slot, fresh)
         return self._static_loss
+
+    def _ctr_pin(self, kind, pset):
+        """Pinned host copy of a pool set's counter blocks, one per (graph kind that samples into the set, set):
+        S[p] and G[1-p] both sample into set p and may be in flight one call apart, so each has its own buffer; a
+        buffer is re-written two calls after the call that consumes it (``_consume_counters``, one call late)."""
+        smp = self.dm.sampler
+        key = (kind, pset.ctr_base // 8)
+        if key not in self._ctr_pins:
+            self._ctr_pins[key] = torch.zeros((8, smp._wsp.ctr_all.shape[1]), dtype=torch.uint8).pin_memory()
+        return self._ctr_pins[key]
+
+    def _stage_seeds(self, pset, seeds):
+        """The announced batch into the set's seed buffer.  Host seeds (the data loader's case) go through a pinned
+        staging buffer on a copy stream that only waits for the last step that read the buffer — two calls back — so
+        the copy runs beside the previous step instead of between two step graphs; a device tensor may have been
+        produced on the current stream just now and is copied in stream order."""
+        if seeds.is_cuda:
+            pset.seeds_in.copy_(seeds, non_blocking=True)
+            return
+        main = torch.cuda.current_stream()
+        i = pset.ctr_base // 8
+        if self._seed_stage[i] is None:
+            self._seed_stage[i] = torch.zeros(self.dm.batch_size, dtype=torch.int32).pin_memory()
+            self._seed_staged[i] = torch.cuda.Event()
+        elif self._seed_stage[i].numel() != seeds.numel():
+            self._seed_staged[i].synchronize()
+            self._seed_stage[i] = torch.zeros(seeds.numel(), dtype=torch.int32).pin_memory()
+        else:
+            self._seed_staged[i].synchronize()    # (the previous copy out of the staging buffer: two calls ago)
+        self._seed_stage[i].copy_(seeds)
+        cs = self._copy_stream
+        if self._set_free[i] is not None:
+            cs.wait_event(self._set_free[i])
+        with torch.cuda.stream(cs):
+            pset.seeds_in.copy_(self._seed_stage[i], non_blocking=True)
+            self._seed_staged[i].record(cs)
+        main.wait_event(self._seed_staged[i])
 
     def _replay(self, key):
         self._graphs[key].replay()
@@ -560,9 +624,12 @@ class Trainer:
         dm, g, smp = self.dm, self.dm.g, self.dm.sampler
         L = len(smp.nodes_per_layer)
         grow = False
-        for p in fresh:
+        from . import _native
+        self._call_done[slot].synchronize()
+        for kind, p in fresh:
             pset = self._sets[p] if self._sets is not None else None
-            ctrs = smp._wsp.finish_counter_read(slot, L, base=8 * p)
+            raw = self._ctr_pins[(kind, p)].numpy()
+            ctrs = [_native.Counters.from_buffer_copy(raw[l].tobytes()) for l in range(L)]
             for l, c in enumerate(ctrs):
                 if c.error:
                     cap = (pset.pools[l].cap_src, pset.pools[l].cap_edges) if pset is not None else ("?", "?")
@@ -654,19 +721,46 @@ class Trainer:
             for pb in pset.padded:                # events recorded in one capture must not be waited for in another
                 pb._ready = pb._t_ready = None
 
-        def sample_into(pset, layer_pre=None):
-            """Sampling of one batch (``pset.seeds``) into ``pset``: every layer's front half on the current stream,
-            back halves and transposes on ``_side_t``; complete (joined) on return."""
+        from .model import GCN
+        defer0 = not isinstance(getattr(self.model, "module", self.model), GCN)   # (GCN's forward pass reads the out-degrees off the transpose)
+
+        def sample_into(pset, kind, layer_pre=None):
+            """Sampling of one batch (``pset.seeds_in``) into ``pset``: every layer's front half on the current stream,
+            back halves and transposes on ``_side_t``; complete (joined) on return.  The input layer's transpose —
+            the last thing on the sampling chain, read by the backward pass only — is left to the step that trains
+            on the set (``launch_deferred``).  Every layer's finish kernel writes the layer's counters to the pinned buffer
+            ``(kind, set)`` (device-mapped host memory), so nothing has to be enqueued between two step graphs."""
             cur = torch.cuda.current_stream()
-            smp.enqueue_static(g, pset.seeds, pset.pools, self._step_dev, transpose_stream=self._side_t,
-                               defer_last_transpose=False, ctr_base=pset.ctr_base, layer_pre=layer_pre)
+            self._side_t.wait_stream(cur)
+            with torch.cuda.stream(self._side_t):
+                pset.seeds.copy_(pset.seeds_in, non_blocking=True)
+            pset.deferred = smp.enqueue_static(g, pset.seeds_in, pset.pools, self._step_dev, transpose_stream=self._side_t,
+                                               defer_last_transpose=defer0, ctr_base=pset.ctr_base, layer_pre=layer_pre,
+                                               ctr_mirror=self._ctr_pin(kind, pset))
+            self._step_dev.add_(1)                # (read by the layers' select kernels only: all launched by now)
             self._gather_inputs(pset, True)       # beside the input layer's fill / transposes (needs its source list only)
             cur.wait_stream(self._side_t)
-            self._step_dev.add_(1)
             clear_events(pset)
 
+        if self._loss_pins is None:
+            self._loss_pins = [torch.zeros(1).pin_memory() for _ in range(2)]
+            self._side_c = torch.cuda.Stream()
+
+        def emit_loss(loss, p):
+            """The step's loss to pinned host memory (``host_loss``): a 4-byte copy node beside the backward pass."""
+            self._side_c.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side_c):
+                self._loss_pins[p].copy_(loss.detach().reshape(1), non_blocking=True)
+
+        def launch_deferred(pset):
+            """The input layer's transpose of the set this step trains on, beside the forward pass."""
+            if pset.deferred:
+                self._side_t.wait_stream(torch.cuda.current_stream())
+                for fn in pset.deferred:
+                    fn()                          # (on _side_t; records the block's _t_ready for the backward pass)
+
         def body_sample(p):
-            sample_into(self._sets[p])
+            sample_into(self._sets[p], "S")
 
         def body_step(p, prefetch):               # single rank: the whole step in one graph
             """forward ─ backward ─ Adam on the main stream.  A layer's bandit update is launched (side_b) as soon as the
@@ -676,6 +770,7 @@ class Trainer:
             pset, other = self._sets[p], self._sets[1 - p]
             clear_events(pset)
             main = torch.cuda.current_stream()
+            launch_deferred(pset)
             inputs = (pset.x, pset.x_norm, pset.y) if pset.x is not None else None
             fired = []
 
@@ -683,9 +778,13 @@ class Trainer:
                 def hook():
                     cur = torch.cuda.current_stream()
                     fired.append(l)
+                    if l == 0 and late0:
+                        return                    # (launched with layer 1's, see below)
                     if l < L - 1:
                         self._side_b.wait_stream(cur)
                         with torch.cuda.stream(self._side_b):
+                            if l == 1 and late0:
+                                smp.update_exp3_weights(0, pset.padded[0], g)
                             smp.update_exp3_weights(l, pb, g)
                     else:                         # the top layer: its update, then the look-ahead sampling
                         self._side_s.wait_stream(cur)
@@ -694,21 +793,27 @@ class Trainer:
                         with torch.cuda.stream(self._side_s):
                             smp.update_exp3_weights(l, pb, g)
                             if prefetch:
-                                sample_into(other)
+                                sample_into(other, "G")
                 return hook
 
             key = "a_ij" if smp.model == "gat" else "embed_norm"
+            # The input layer's update (the largest: a random read-modify-write per edge of the 4096-fan-out block) could
+            # start with the step — its embed_norm comes with the gathered inputs — but it would share the memory system
+            # with the input layer's aggregation, the longest kernel of the forward pass, which the sampling chain is
+            # waiting behind.  It is launched with layer 1's update instead, beside the smaller layers' forward pass.
+            late0 = L > 2 and key == "embed_norm" and os.environ.get("BLISS_EXP3_L0_EARLY") != "1"
             if bandit:
                 for l, pb in enumerate(pset.padded):
                     (pb.edata if key == "a_ij" else pb.srcdata).on_set[key] = make(l, pb)
 
             def after_forward():
+                emit_loss(self._fwd_loss, p)
                 if bandit:
                     assert sorted(fired) == list(range(L)), f"bandit update hooks fired for layers {fired}"
                 elif prefetch:
                     self._side_s.wait_stream(main)
                     with torch.cuda.stream(self._side_s):
-                        sample_into(other)
+                        sample_into(other, "G")
 
             try:
                 loss, pred, y = self._padded_fwd_bwd(True, after_forward=after_forward, pset=pset, inputs=inputs)
@@ -716,11 +821,14 @@ class Trainer:
                 for pb in pset.padded:
                     pb.srcdata.on_set.pop("embed_norm", None)
                     pb.edata.on_set.pop("a_ij", None)
+            self._drop_dev.add_(1)                # (before the joins: nothing but the joins is left behind the sampling chain)
             if bandit and L > 1:                  # (a stream that was not forked inside this capture must not be joined)
                 main.wait_stream(self._side_b)
             if bandit or prefetch:
                 main.wait_stream(self._side_s)
-            self._drop_dev.add_(1)
+            if pset.deferred:
+                main.wait_stream(self._side_t)
+            main.wait_stream(self._side_c)
             return loss, pred, y
 
         early_emit = bandit and smp.model != "gat"      # GAT's alpha needs a_ij: emitted after the forward pass
@@ -729,6 +837,7 @@ class Trainer:
             pset = self._sets[p]
             clear_events(pset)
             main = torch.cuda.current_stream()
+            launch_deferred(pset)
             if early_emit:      # a layer's exponents are emitted as soon as the model has stored its embed_norm
                 def make(l, pb):
                     def hook():
@@ -749,6 +858,11 @@ class Trainer:
                     smp.exp3_emit(pset.padded, g, self._exchange)
             if bandit:
                 main.wait_stream(self._side_b)
+            if pset.deferred:                     # (the backward pass is its own graph: joined here, event dropped)
+                main.wait_stream(self._side_t)
+                clear_events(pset)
+            emit_loss(loss, p)
+            main.wait_stream(self._side_c)
             return loss, pred.detach(), y
 
         def body_a2(loss):
@@ -765,7 +879,7 @@ class Trainer:
             if bandit:
                 smp.exp3_apply(self._exchange, L)
             if prefetch:
-                sample_into(self._sets[1 - p])
+                sample_into(self._sets[1 - p], "G")
             if not (bandit or prefetch):
                 self._drop_dev.add_(0)            # (a captured graph must hold at least one node)
 
@@ -801,7 +915,7 @@ class Trainer:
             params = [p_.detach().clone() for p_ in self.grads.params]
             drop0 = self._drop_dev.clone()
             for pset in self._sets:
-                pset.seeds.copy_(self.dm.train_nid[: dm.batch_size])
+                pset.seeds_in.copy_(self.dm.train_nid[: dm.batch_size])
             body_sample(0)
             for p in (0, 1):
                 if dp:
@@ -929,6 +1043,11 @@ class _PoolSet:
 
     def __init__(self, pools, padded, seeds, ctr_base):
         self.pools, self.padded, self.seeds, self.ctr_base = pools, padded, seeds, ctr_base
+        # ``seeds_in`` is where a batch arrives and what the sampling graph reads; that graph also copies it to
+        # ``seeds`` (the top block's destination ids, read by the step that trains on the set), so the next batch but
+        # one can be staged into ``seeds_in`` while that step is still running
+        self.seeds_in = torch.zeros_like(seeds)
+        self.deferred = []                        # the input layer's transpose, launched by the step that trains on the set
         self.x = self.x_norm = self.y = None      # input features / their row norms / labels, gathered with the blocks
 
 

@@ -104,6 +104,9 @@ typedef struct bliss_workspace {
    * taking them from the host arguments, which then only give capacities.  NULL = use the host value. */
   const int32_t*  n_seeds_dev;  /* true seed count of this layer (e.g. the previous layer's n_src) */
   const uint64_t* step_dev;     /* Philox step counter                                            */
+  /* Optional host-visible copy of the layer's counters (pinned, device-mapped host memory): written by
+   * bliss_block_finish, the layer's last kernel, so a replayed step needs no separate device->host copy. */
+  bliss_counters* ctr_mirror;
 } bliss_workspace;
 
 /* Outputs of one sampled layer (device pointers, capacities checked against the counters). */

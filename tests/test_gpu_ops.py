@@ -311,7 +311,7 @@ def test_lookahead_sampling_keeps_the_trajectory(native_lib, kind, sampler):
     dev = _dev()
     g = synthetic_graph("flickr", seed=0, scale=0.05).to(dev)
     res = {}
-    for ahead in (False, True):
+    for ahead in (False, True, "host"):
         dm = DataModule("flickr", fan_out=[128, 64, 32], eta=0.1, device=dev, batch_size=32, sampler=sampler,
                         model=kind, seed=0, graph=g)
         torch.manual_seed(3)
@@ -320,16 +320,26 @@ def test_lookahead_sampling_keeps_the_trajectory(native_lib, kind, sampler):
         tr = Trainer(dm, model, 0.002, static_graph=True, eager_warmup=3)
         batches = [b for _, b in zip(range(16), dm.train_batches())]
         batches[9] = batches[9][:20]                       # a ragged batch: runs eagerly, the prefetch must be dropped
-        losses = []
+        if ahead == "host":        # the data loader's case: seeds arrive as host tensors (pinned staging, copy stream)
+            batches = [b.cpu() for b in batches]
+        losses, late = [], []
         for i, b in enumerate(batches):
             nxt = batches[i + 1] if (ahead and i + 1 < len(batches) and i != 12) else None    # 12 -> 13 unannounced
-            losses.append(float(tr.training_step(b, nxt).item()))
+            loss = tr.training_step(b, nxt)
+            if ahead == "host":    # losses through the step graph's own copy to pinned memory, one step late
+                if i:
+                    late.append(tr.host_loss(back=1))
+                if i == len(batches) - 1:
+                    late.append(tr.host_loss())
+            losses.append(float(loss.item()))
         tr.flush()
         assert tr.num_steps == len(batches), tr.num_steps
+        assert not late or late == losses, (late, losses)
         res[ahead] = (losses, dm.sampler.exp3_weights.clone() if "bandit" in sampler else None, dm.sampler.step)
-    assert res[True][2] == res[False][2] == 16, "every sampling must consume exactly one Philox step"
-    for a, b in zip(res[False][0], res[True][0]):
+    assert res[True][2] == res[False][2] == res["host"][2] == 16, "every sampling must consume exactly one Philox step"
+    for a, b, c in zip(res[False][0], res[True][0], res["host"][0]):
         assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (res[False][0], res[True][0])
+        assert abs(a - c) <= 1e-6 * max(1.0, abs(a)), (res[False][0], res["host"][0])
     if res[True][1] is not None:
         # GAT: the attn gradient is accumulated with atomics (run-to-run last-bit differences) and alpha divides by
         # sums of signed logits, which amplifies them (see test_static_graph_step_matches_eager)
