@@ -357,6 +357,11 @@ def main():
                          traffic_tab)
     rl["roofline"]["l2_gather"] = l2_gather_probe(N, device, per_kernel, sizes, [HIDDEN, HIDDEN, dm.n_classes])
 
+    if world > 1:
+        ex, gx = tr._exchange, tr._gradx
+        how = lambda o: ("peer-memory push" + (" through the NVSwitch multicast address" if getattr(o, "mc_base", 0) else "")) \
+            if o is not None and o is not False and getattr(o, "p2p", True) else "NCCL"
+        config["exchange"] = {"bandit_updates": how(ex), "gradients": how(gx)}
     out = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,

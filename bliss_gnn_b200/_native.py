@@ -101,12 +101,13 @@ class P2P(C.Structure):
     _fields_ = [("peer_base", C.c_void_p), ("world", C.c_int32), ("rank", C.c_int32), ("parity_stride", C.c_int64),
                 ("rank_stride", C.c_int64), ("count_off", C.c_int64), ("pos_off", C.c_int64), ("x_off", C.c_int64),
                 ("flags_off", C.c_int64), ("layer", C.c_int32), ("n_layers", C.c_int32), ("step_dev", C.c_void_p),
-                ("done_ctr", C.c_void_p), ("pull", C.c_int32), ("pad_", C.c_int32)]
+                ("done_ctr", C.c_void_p), ("pull", C.c_int32), ("pad_", C.c_int32), ("mc_base", C.c_uint64)]
 
 
 class GradP2P(C.Structure):
     _fields_ = [("peer_base", C.c_void_p), ("world", C.c_int32), ("rank", C.c_int32), ("parity_stride", C.c_int64),
-                ("slot_bytes", C.c_int64), ("flags_off", C.c_int64), ("step_dev", C.c_void_p), ("done_ctr", C.c_void_p)]
+                ("slot_bytes", C.c_int64), ("flags_off", C.c_int64), ("step_dev", C.c_void_p), ("done_ctr", C.c_void_p),
+                ("mc_base", C.c_uint64)]
 
 
 _P, _I32, _I64, _U32, _U64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_double

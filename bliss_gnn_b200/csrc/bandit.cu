@@ -101,6 +101,10 @@ __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
   const int r_lo = (W && p.p2p.pull) ? p.p2p.rank : 0, r_hi = (W && p.p2p.pull) ? p.p2p.rank + 1 : W;   // windows written
   if (W && blockIdx.x == 0 && (int)threadIdx.x >= r_lo && (int)threadIdx.x < r_hi)   // this layer's edge count
     *reinterpret_cast<int64_t*>(p2p_slot(p.p2p, threadIdx.x, parity, p.p2p.rank) + p.p2p.count_off) = n_edges;
+  unsigned char* mc_slot = (W && p.p2p.mc_base && !p.p2p.pull)     // my slot in the multicast view of the windows
+                               ? reinterpret_cast<unsigned char*>(p.p2p.mc_base) + (int64_t)parity * p.p2p.parity_stride +
+                                     (int64_t)p.p2p.rank * p.p2p.rank_stride
+                               : nullptr;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += stride) {
     const int i = p.edge_dst[e];
     const int u = p.edge_src[e];
@@ -126,10 +130,15 @@ __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
     if (x > 1.0f) x = 1.0f;                                                      // :244
     if (p.x_out) p.x_out[e] = x;
     if (p.pos_out) p.pos_out[e] = (int32_t)pos;
-    for (int r = r_lo; r < r_hi; ++r) {             // my slot in rank r's window (pull mode: only my own window)
-      unsigned char* slot = p2p_slot(p.p2p, r, parity, p.p2p.rank);
-      reinterpret_cast<int32_t*>(slot + p.p2p.pos_off)[e] = (int32_t)pos;
-      reinterpret_cast<float*>(slot + p.p2p.x_off)[e] = x;
+    if (mc_slot) {                                  // one store each, replicated into every window by the switch
+      multimem_st_b32(reinterpret_cast<int32_t*>(mc_slot + p.p2p.pos_off) + e, (uint32_t)(int32_t)pos);
+      multimem_st_f32(reinterpret_cast<float*>(mc_slot + p.p2p.x_off) + e, x);
+    } else {
+      for (int r = r_lo; r < r_hi; ++r) {           // my slot in rank r's window (pull mode: only my own window)
+        unsigned char* slot = p2p_slot(p.p2p, r, parity, p.p2p.rank);
+        reinterpret_cast<int32_t*>(slot + p.p2p.pos_off)[e] = (int32_t)pos;
+        reinterpret_cast<float*>(slot + p.p2p.x_off)[e] = x;
+      }
     }
     if (p.exp3_w) {
       const float w_old = p.exp3_w[pos];
@@ -186,24 +195,49 @@ __global__ void __launch_bounds__(256) k_apply_updates_p2p(bliss_p2p q, int64_t 
   const int64_t total = (int64_t)q.world * cap;
   const int parity = (int)(*q.step_dev & 1);
   double dsum = 0.0;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += stride) {
-    const int r = (int)(t / cap);
-    const int64_t k = t - (int64_t)r * cap;
-    // push: every rank stored its slot into my window; pull: rank r's slot is read from rank r's window over NVLink
-    const unsigned char* base = p2p_slot(q, q.pull ? r : q.rank, parity, r);
-    const int64_t n = __ldcg(reinterpret_cast<const long long*>(base + q.count_off));   // (L1 may hold the slot's old lines)
-    if (k >= n) continue;
-    const int64_t pos = __ldcg(reinterpret_cast<const int32_t*>(base + q.pos_off) + k);
-    const float f = expf(__ldcg(reinterpret_cast<const float*>(base + q.x_off) + k));
-    float* addr = exp3_w + pos;
-    unsigned old = __float_as_uint(*addr), assumed;
-    do {  // two ranks may have sampled the same edge: multiplicative update through a CAS loop
-      assumed = old;
-      old = atomicCAS(reinterpret_cast<unsigned*>(addr), assumed,
-                      __float_as_uint(__fmul_rn(__uint_as_float(assumed), f)));
-    } while (old != assumed);
-    const float w_old = __uint_as_float(old);
-    dsum += (double)__fmul_rn(w_old, f) - (double)w_old;
+  // Four updates per thread and round: their window reads, their reads of the old weights (random 4-byte reads of a
+  // |E|-sized array: DRAM latency) and their first compare-and-swap attempts are all in flight together.
+  constexpr int U = 4;
+  for (int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t0 < total; t0 += U * stride) {
+    float* addr[U];
+    float f[U];
+    unsigned old[U], got[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t t = t0 + u * stride;
+      addr[u] = nullptr;
+      if (t < total) {
+        const int r = (int)(t / cap);
+        const int64_t k = t - (int64_t)r * cap;
+        // push: every rank stored its slot into my window; pull: rank r's slot is read from rank r's window over NVLink
+        const unsigned char* base = p2p_slot(q, q.pull ? r : q.rank, parity, r);
+        const int64_t n = __ldcg(reinterpret_cast<const long long*>(base + q.count_off));   // (L1 may hold the slot's old lines)
+        if (k < n) {
+          addr[u] = exp3_w + __ldcg(reinterpret_cast<const int32_t*>(base + q.pos_off) + k);
+          f[u] = expf(__ldcg(reinterpret_cast<const float*>(base + q.x_off) + k));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (addr[u]) old[u] = __float_as_uint(*addr[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (addr[u])
+        got[u] = atomicCAS(reinterpret_cast<unsigned*>(addr[u]), old[u],
+                           __float_as_uint(__fmul_rn(__uint_as_float(old[u]), f[u])));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!addr[u]) continue;
+      unsigned seen = got[u], assumed = old[u];
+      while (seen != assumed) {   // two ranks sampled the same edge (or the same position twice in this round): retry
+        assumed = seen;
+        seen = atomicCAS(reinterpret_cast<unsigned*>(addr[u]), assumed,
+                         __float_as_uint(__fmul_rn(__uint_as_float(assumed), f[u])));
+      }
+      const float w_old = __uint_as_float(seen);
+      dsum += (double)__fmul_rn(w_old, f[u]) - (double)w_old;
+    }
   }
   if (l1_delta) {
     dsum = block_sum(dsum, s_red);

@@ -159,4 +159,18 @@ __device__ __forceinline__ bool test_bit(const uint32_t* __restrict__ bits, int 
   return (__ldg(bits + (v >> 5)) >> (v & 31)) & 1u;
 }
 
+// Stores to an NVSwitch multicast address (symmetric-memory windows, data-parallel exchanges): the switch replicates
+// one store into every rank's window.  Weak stores, ordered like any other store of the thread by the
+// __threadfence_system() in front of the flag that publishes them.
+__device__ __forceinline__ void multimem_st_b32(void* a, uint32_t v) {
+  asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st_f32(void* a, float v) {
+  asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st_f32x4(void* a, float4 v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 }  // namespace bliss

@@ -75,12 +75,21 @@ __global__ void __launch_bounds__(256) k_grad_push(const float* __restrict__ g, 
   const long long step = *q.step_dev;
   const int parity = (int)(step & 1);
   const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 v = reinterpret_cast<const float4*>(g)[i];
-    for (int r = 0; r < q.world; ++r) reinterpret_cast<float4*>(gslot(q, r, parity, q.rank))[i] = v;
+  if (q.mc_base) {   // one store per value into the multicast view of the windows: the switch replicates it
+    float* mc = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(q.mc_base) + (int64_t)parity * q.parity_stride +
+                                         (int64_t)q.rank * q.slot_bytes);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride)
+      multimem_st_f32x4(reinterpret_cast<float4*>(mc) + i, reinterpret_cast<const float4*>(g)[i]);
+    for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride)
+      multimem_st_f32(mc + i, g[i]);
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 v = reinterpret_cast<const float4*>(g)[i];
+      for (int r = 0; r < q.world; ++r) reinterpret_cast<float4*>(gslot(q, r, parity, q.rank))[i] = v;
+    }
+    for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride)
+      for (int r = 0; r < q.world; ++r) gslot(q, r, parity, q.rank)[i] = g[i];
   }
-  for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride)
-    for (int r = 0; r < q.world; ++r) gslot(q, r, parity, q.rank)[i] = g[i];
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {

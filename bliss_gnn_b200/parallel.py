@@ -126,7 +126,8 @@ class BanditExchange:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)     # exchange step: parity + flag value
         self.done_ctr = torch.zeros(L, dtype=torch.int32, device=self.device)
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._structs = [N.P2P(peer_base=self.peer_base.data_ptr(), world=W, rank=self.rank,
+        self.mc_base = _multicast_base(hdl)
+        self._structs = [N.P2P(peer_base=self.peer_base.data_ptr(), world=W, rank=self.rank, mc_base=self.mc_base,
                                parity_stride=W * self.stride, rank_stride=self.stride, count_off=8 * l,
                                pos_off=self.pos_off[l], x_off=self.x_off[l], flags_off=self.flags_off, layer=l,
                                n_layers=L, step_dev=self.step_dev.data_ptr(),
@@ -144,6 +145,19 @@ class BanditExchange:
             self._hdr_host[l] = int(c)
         self.header.copy_(self._hdr_host, non_blocking=True)
         dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+
+
+def _multicast_base(hdl) -> int:
+    """NVSwitch multicast address of a symmetric-memory window (0 when the fabric has none, or with BLISS_P2P_MC=0):
+    a store to it is replicated into every rank's window by the switch, so a producer issues one store per value
+    instead of one per rank."""
+    if os.environ.get("BLISS_P2P_MC", "1") == "0":
+        return 0
+    try:
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+    except Exception:
+        return 0
+    return mc
 
 
 class GradExchange:
@@ -168,7 +182,8 @@ class GradExchange:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=device)
         self.done_ctr = torch.zeros(1, dtype=torch.int32, device=device)
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
-        self.struct = N.GradP2P(peer_base=self.peer_base.data_ptr(), world=self.world, rank=self.rank,
+        self.mc_base = _multicast_base(hdl)
+        self.struct = N.GradP2P(peer_base=self.peer_base.data_ptr(), world=self.world, rank=self.rank, mc_base=self.mc_base,
                                 parity_stride=self.world * self.slot_bytes, slot_bytes=self.slot_bytes,
                                 flags_off=self.flags_off, step_dev=self.step_dev.data_ptr(),
                                 done_ctr=self.done_ctr.data_ptr())

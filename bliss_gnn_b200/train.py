@@ -517,7 +517,7 @@ class Trainer:
         prefetch = next_seeds is not None and next_seeds.numel() == dm.batch_size
         if prefetch:
             self._stage_seeds(nxt, next_seeds)
-        if self._exchange is None and not (self.world > 1 or self._force_dp):
+        if getattr(self, "_dp_one_graph", False) or (self._exchange is None and not (self.world > 1 or self._force_dp)):
             self._replay(("G" if prefetch else "GN", p))
         else:                                                  # data parallel: see _capture_full
             main = torch.cuda.current_stream()
@@ -722,7 +722,10 @@ class Trainer:
                 pb._ready = pb._t_ready = None
 
         from .model import GCN
-        defer0 = not isinstance(getattr(self.model, "module", self.model), GCN)   # (GCN's forward pass reads the out-degrees off the transpose)
+        # (GCN's forward pass reads the out-degrees off the transpose; data parallel, the main line's tail — gradient
+        # exchange, Adam over all ranks' slots — is longer than the sampling chain's, so the transpose stays there)
+        defer0 = not isinstance(getattr(self.model, "module", self.model), GCN) and not dp \
+            or os.environ.get("BLISS_DEFER_T0") == "1"
 
         def sample_into(pset, kind, layer_pre=None):
             """Sampling of one batch (``pset.seeds_in``) into ``pset``: every layer's front half on the current stream,
@@ -885,18 +888,89 @@ class Trainer:
 
         gradx = self._gradx if self._gradx else None
 
-        def body_b2():
+        def body_b2(adds=True):
             if gradx is not None:                 # push the flat gradient into every rank's window; Adam adds the slots
                 gradx.push(self._flat_grad)
                 self.optimizer.step_p2p(gradx)
                 self._grads_clean = True
             else:
                 self._optimizer_step()
+            if adds:
+                self._drop_dev.add_(1)
+                if p2p:
+                    self._exchange.step_dev.add_(1)   # next step: other parity half of the windows, next flag value
+
+        # Both exchanges through peer memory: no collective call is left between the parts of the step, so the whole
+        # data-parallel step is ONE graph like the single-rank one (three graph boundaries fewer on the main line).
+        one_graph = dp and gradx is not None and (p2p or not bandit)
+        self._dp_one_graph = one_graph
+
+        def body_step_p2p(p, prefetch):
+            """main: forward - backward - gradient push - Adam over all ranks' slots.  A layer's updates are emitted into
+            every rank's window (side_b) as soon as the model has stored its embed_norm; right behind the local emit
+            (side_apply) that layer's wait-for-all-ranks + apply, and behind the top layer's the sampling of the next
+            batch.  A wait kernel is therefore never scheduled ahead of the local kernel whose flag it waits for."""
+            pset, other = self._sets[p], self._sets[1 - p]
+            clear_events(pset)
+            main = torch.cuda.current_stream()
+            launch_deferred(pset)
+            forked = []
+
+            def apply_from(l0, l1, after):
+                """Layers l0..l1-1 applied behind ``after`` (the stream their local emit ran on); then, behind the top
+                layer, the look-ahead sampling."""
+                self._side_apply.wait_stream(after)
+                forked.append(True)
+                with torch.cuda.stream(self._side_apply):
+                    for l in range(l0, l1):
+                        smp.exp3_apply_layer(self._exchange, l)
+                    if l1 == L and prefetch:
+                        sample_into(other, "G")
+
+            if early_emit:
+                def make(l, pb):
+                    def hook():
+                        self._side_b.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(self._side_b):
+                            smp.exp3_emit_layer(l, pb, g, self._exchange)
+                        apply_from(l, l + 1, self._side_b)
+                    return hook
+                for l, pb in enumerate(pset.padded):
+                    pb.srcdata.on_set["embed_norm"] = make(l, pb)
+            try:
+                loss, pred, y = self._padded_fwd(pset, (pset.x, pset.x_norm, pset.y) if pset.x is not None else None)
+            finally:
+                for pb in pset.padded:
+                    pb.srcdata.on_set.pop("embed_norm", None)
+            emit_loss(loss, p)
+            if bandit and not early_emit:         # GAT: alpha needs a_ij, known after the forward pass
+                self._side_b.wait_stream(main)
+                with torch.cuda.stream(self._side_b):
+                    smp.exp3_emit(pset.padded, g, self._exchange)
+                apply_from(0, L, self._side_b)
+            elif not bandit and prefetch:
+                self._side_apply.wait_stream(main)
+                forked.append(True)
+                with torch.cuda.stream(self._side_apply):
+                    sample_into(other, "G")
+            self._zero_grads()
+            loss.backward()
+            body_b2(adds=False)
             self._drop_dev.add_(1)
+            if bandit:
+                main.wait_stream(self._side_b)
+            if forked:
+                main.wait_stream(self._side_apply)
+            if pset.deferred:
+                main.wait_stream(self._side_t)
+            main.wait_stream(self._side_c)
             if p2p:
-                self._exchange.step_dev.add_(1)   # next step: other parity half of the windows, next flag value
+                self._exchange.step_dev.add_(1)   # (after the apply kernels, which read the parity from it)
+            return loss.detach(), pred.detach(), y
 
         def dp_step_eager(p, prefetch):
+            if one_graph:
+                return body_step_p2p(p, prefetch)
             loss_w, _, _ = body_a1(p)
             if self._exchange is not None and not p2p:
                 torch.distributed.all_gather_into_tensor(self._exchange.recv, self._exchange.send, group=self.pg)
@@ -957,6 +1031,9 @@ class Trainer:
             if not dp:
                 outs[p] = capture(("G", p), lambda: body_step(p, True))
                 outs[("N", p)] = capture(("GN", p), lambda: body_step(p, False))
+            elif one_graph:
+                outs[p] = capture(("G", p), lambda: body_step_p2p(p, True))
+                outs[("N", p)] = capture(("GN", p), lambda: body_step_p2p(p, False))
             else:
                 loss, pred, y = capture(("A1", p), lambda: body_a1(p))
                 outs[p] = (loss.detach(), pred, y)
@@ -965,10 +1042,14 @@ class Trainer:
                 del loss
                 capture(("B1", p), lambda: body_b1(p, True), stream=self._side_apply)
                 capture(("B1N", p), lambda: body_b1(p, False), stream=self._side_apply)
-        if dp:
+        if dp and not one_graph:
             capture(("B2", 0), body_b2)
         self._graphs, self._graph_kernel_counts, self._static_out = graphs, counts, outs
         self.graph_kernels = counts.get(("G", 0), 0) or sum(counts.get((k, 0), 0) for k in ("A1", "A2", "B1", "B2"))
+        # (ranks enter the first replay together: a rank still capturing would leave its peers' wait kernels spinning)
+        if dp and torch.distributed.is_initialized():
+            torch.cuda.synchronize()
+            torch.distributed.barrier(group=self.pg)
 
     # ---- checkpoint / resume (the reference checkpoints the model only; the bandit state is part of training) ----
     def state_dict(self):

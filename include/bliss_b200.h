@@ -154,6 +154,8 @@ typedef struct bliss_p2p {
                                  1: it stores only into its OWN window and raises the flags everywhere, the consumer
                                     reads slot r from rank r's window over NVLink (pull: no duplicated stores) */
   int32_t  pad_;
+  uint64_t mc_base;           /* 0, or the NVSwitch multicast address of the windows (same layout): one multimem.st
+                                 per value reaches every rank's window, the switch replicates it (push mode only) */
 } bliss_p2p;
 
 /* Gradient all-reduce through peer memory, fused into the optimizer step: window = [2 parities][world slots of
@@ -168,6 +170,7 @@ typedef struct bliss_grad_p2p {
   int64_t  flags_off;
   const int64_t* step_dev;    /* exchange step counter (parity, flag value) */
   uint32_t* done_ctr;         /* [1], zero between launches */
+  uint64_t mc_base;           /* 0, or the multicast address of the windows (see bliss_p2p) */
 } bliss_grad_p2p;
 
 int bliss_version(void);

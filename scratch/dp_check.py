@@ -31,7 +31,9 @@ for mode in ("1", "0"):
     dist.broadcast(ref, src=0)
     same_across_ranks = bool(torch.equal(ref, flat))
     res[mode] = (losses, flat.clone(), dm.sampler.exp3_weights.clone(), same_across_ranks,
-                 bool(tr._exchange is not None and tr._exchange.p2p), bool(tr._gradx))
+                 bool(tr._exchange is not None and tr._exchange.p2p), bool(tr._gradx),
+                 bool(tr._exchange is not None and getattr(tr._exchange, "mc_base", 0)),
+                 bool(tr._gradx and getattr(tr._gradx, "mc_base", 0)))
 l1, l0 = res["1"][0], res["0"][0]
 worst = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(l1, l0))
 pdiff = ((res["1"][1] - res["0"][1]).abs().max() / res["0"][1].abs().max()).item()
