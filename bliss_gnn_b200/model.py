@@ -35,10 +35,13 @@ class _LinearSplitK(torch.autograd.Function):
         # on the main stream: beside the backward SpMM they would only fight it for SMs (measured: 79 us instead
         # of 50 for the aggregation, 82 instead of 14 for the GEMM).
         extra = x.shape[1] - weight.shape[1]
+        stored = getattr(weight, "_bliss_padded", None)      # the parameter's own storage, padded (parallel.flat_layout)
+        if extra and (stored is None or stored.shape[1] != x.shape[1]):
+            stored = None
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-            w = weight if extra == 0 else torch.nn.functional.pad(weight, (0, extra))
+            w = weight if extra == 0 else (stored if stored is not None else torch.nn.functional.pad(weight, (0, extra)))
             y = torch.nn.functional.linear(x, w, bias)
-        if side is not None and w is not weight:
+        if side is not None and w is not weight and w is not stored:
             w.record_stream(torch.cuda.current_stream())     # allocated on the side stream, read by backward on this one
         ctx.save_for_backward(x, w)
         ctx.weight, ctx.has_bias = weight, bias is not None
@@ -62,7 +65,12 @@ class _LinearSplitK(torch.autograd.Function):
             if rem:
                 torch.mm(gyc[k:].t(), xc[k:], out=part[S])
             g = weight.grad
-            if g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.is_cuda:
+            gp = getattr(weight, "_bliss_padded_grad", None)
+            if g is not None and gp is not None and gp.shape[1] == n_in_pad and g.data_ptr() == gp.data_ptr():
+                # the gradient lives in padded storage too: accumulate whole padded rows (the extra columns add zeros)
+                ops.N.call("bliss_splitk_accumulate", ops.N.ptr(part), part.shape[0], n_out, n_in_pad, n_in_pad,
+                           ops.N.ptr(gp), ops.N.stream())
+            elif g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.is_cuda:
                 ops.N.call("bliss_splitk_accumulate", ops.N.ptr(part), part.shape[0], n_out, n_in_pad, n_in,
                            ops.N.ptr(g), ops.N.stream())       # accumulated in place: nothing to return
             else:

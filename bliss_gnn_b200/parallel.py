@@ -22,17 +22,38 @@ def shard_batches(n_batches: int, rank: int, world: int) -> range:
     return range(rank, usable, world)
 
 
+def flat_layout(params):
+    """Offsets of the parameters in the flat buffers (gradients here, parameters and moments in :class:`FlatAdam`):
+    every tensor starts on a 16-byte boundary, and a 2-D parameter marked ``_bliss_pad_cols = k`` (the input layer's
+    weights when the feature rows are padded to a 16-byte multiple, ``train.Trainer``) gets ``k`` extra zero columns per
+    row IN its storage — the model then hands cuBLAS the padded matrix as it lies instead of building a padded copy
+    (a fill and a copy kernel per weight at the head of every step).  Returns ``[(offset, rows, cols, pad)]``, total."""
+    out, off = [], 0
+    for p in params:
+        k = int(getattr(p, "_bliss_pad_cols", 0)) if p.dim() == 2 else 0
+        n = p.shape[0] * (p.shape[1] + k) if k else p.numel()
+        out.append((off, k))
+        off += (n + 3) // 4 * 4
+    return out, off
+
+
+def flat_view(flat, off, p, k):
+    """(view shaped like ``p``, the padded ``[rows, cols + k]`` matrix it lives in or None)."""
+    if k:
+        full = flat[off:off + p.shape[0] * (p.shape[1] + k)].view(p.shape[0], p.shape[1] + k)
+        return full[:, :p.shape[1]], full
+    return flat[off:off + p.numel()].view_as(p), None
+
+
 class FlatGrads:
     """All parameter gradients as views of one flat buffer: a single all-reduce per step."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        self.layout, n = flat_layout(self.params)
         self.flat = torch.zeros(n, dtype=self.params[0].dtype, device=self.params[0].device)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        for p, (off, k) in zip(self.params, self.layout):
+            p.grad, p._bliss_padded_grad = flat_view(self.flat, off, p, k)
 
     def zero_(self):
         self.flat.zero_()
@@ -210,14 +231,13 @@ class FlatAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         dev = params[0].device
         self.flat_g = flat_grads.flat
-        self.flat_p = torch.empty_like(self.flat_g)
-        off = 0
-        with torch.no_grad():
-            for p in params:
-                n = p.numel()
-                self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
-                p.data = self.flat_p[off:off + n].view_as(p)
-                off += n
+        self.flat_p = torch.zeros_like(self.flat_g)         # (padding columns / alignment gaps stay zero: their
+        with torch.no_grad():                               # gradients and moments are zero, so Adam leaves them)
+            for p, (off, k) in zip(params, flat_grads.layout):
+                view, full = flat_view(self.flat_p, off, p, k)
+                view.copy_(p.detach())
+                p.data = view
+                p._bliss_padded = full
         self.exp_avg = torch.zeros_like(self.flat_g)
         self.exp_avg_sq = torch.zeros_like(self.flat_g)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)

@@ -24,7 +24,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .graph import NID, Graph, add_self_loops_and_build, load_dataset, normalized_edata
-from .model import GCN, SAGE, GATv2
+from .model import GCN, SAGE, GATv2, SAGEConv
 from .parallel import FlatAdam, FlatGrads, shard_batches
 from .sampler import (BanditLadiesSampler, LadiesSampler, MultiLayerFullNeighborSampler, NeighborSampler,
                       PoissonBanditLadiesSampler, PoissonLadiesSampler)
@@ -159,6 +159,15 @@ class Trainer:
         self.loss_fn = nn.BCEWithLogitsLoss() if datamodule.multilabel else nn.CrossEntropyLoss()   # :77-79
         if not datamodule.multilabel and next(model.parameters()).is_cuda:
             self.loss_fn = ops.cross_entropy_mean       # same loss, forward + gradient in one launch
+        # The feature rows are padded to a 16-byte multiple (DataModule): the input layer's weights get the matching zero
+        # columns inside their flat storage (parallel.flat_layout), so no padded copy is built per step.
+        feats = datamodule.g.ndata["features"] if hasattr(datamodule, "g") else None
+        extra = int(feats.shape[1] - datamodule.in_feats) if feats is not None and feats.dim() == 2 else 0
+        if extra > 0 and next(model.parameters()).is_cuda:
+            for name, p_ in model.named_parameters():
+                if name.startswith("layers.0.") and p_.dim() == 2 and p_.shape[1] == datamodule.in_feats \
+                        and "fc_" in name and isinstance(getattr(model, "layers", [None])[0], SAGEConv):
+                    p_._bliss_pad_cols = extra
         # one flat gradient buffer: a single all-reduce per step (~0.46 M parameters for SAGE/Reddit)
         self.grads = FlatGrads(model.parameters())
         params = self.grads.params
