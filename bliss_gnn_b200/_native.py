@@ -140,10 +140,10 @@ PROTOTYPES = {
     "bliss_gatv2_bwd_src": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _P],
     "bliss_gat_alpha_sums": [_P, _P, _P, _I32, _P, _P, _P],
     "bliss_reward_update": [_GP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _I32, _I64,
-                            _P, _P, _P, _P, _P, _P, _P, C.POINTER(P2P), _P],
-    "bliss_apply_updates_p2p": [C.POINTER(P2P), _I64, _P, _P, _P, _P],
-    "bliss_apply_updates": [_P, _P, _I64, _P, _P, _P],
-    "bliss_apply_updates_packed": [_P, _I64, _I32, _I64, _I64, _I64, _I64, _P, _P, _P],
+                            _P, _P, _P, _P, _P, _P, _P, C.POINTER(P2P), _P, _P],
+    "bliss_apply_updates_p2p": [C.POINTER(P2P), _I64, _P, _P, _P, _P, _P],
+    "bliss_apply_updates": [_P, _P, _I64, _P, _P, _P, _P],
+    "bliss_apply_updates_packed": [_P, _I64, _I32, _I64, _I64, _I64, _I64, _P, _P, _P, _P],
     "bliss_l1_norm": [_P, _I64, _P, _P, _P],
     "bliss_scale_by_inv": [_P, _I64, _P, _D, _P],
     "bliss_adam_step": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _P, _I32, _P],

@@ -68,6 +68,7 @@ struct RewardArgs {
   float* rewards;
   float* x_out;
   double* l1_delta;
+  float* wmax;                  // running max of the updated weights (or NULL)
   bliss_p2p p2p;                // peer-memory exchange (world == 0: off)
 };
 
@@ -80,6 +81,24 @@ struct RewardArgs {
 // finish publishes flag = step + 1 in every window.  A consumer polls its own flags (one CTA), then applies the W
 // slots of its own window.  Parity = step & 1: ranks are never two steps apart (the gradient all-reduce of every
 // step is a barrier), so a slot is not overwritten while a slower rank still reads it.
+// Running upper bound of a layer's EXP3 weights (range guard of the lazy normalisation: the weights are re-scaled
+// when it nears the top of the fp32 range, not on a schedule).  Weights are positive, so their bit patterns order
+// like integers.  One atomic per CTA.
+__device__ __forceinline__ void publish_wmax(float m, float* wmax, float* s_max /* [32] */) {
+  if (!wmax) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) s_max[warp] = m;
+  __syncthreads();
+  if (warp == 0) {
+    m = (lane < (int)((blockDim.x + 31) >> 5)) ? s_max[lane] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m > 0.0f) atomicMax(reinterpret_cast<int*>(wmax), __float_as_int(m));
+  }
+}
+
 __device__ __forceinline__ unsigned char* p2p_slot(const bliss_p2p& q, int peer, int parity, int src_rank) {
   return reinterpret_cast<unsigned char*>(q.peer_base[peer]) + (int64_t)parity * q.parity_stride +
          (int64_t)src_rank * q.rank_stride;
@@ -91,8 +110,10 @@ __device__ __forceinline__ unsigned long long* p2p_flag(const bliss_p2p& q, int 
 
 __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
   __shared__ double s_red[32];
+  __shared__ float s_max[32];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   double dsum = 0.0;
+  float wtop = 0.0f;
   const int64_t n_edges = p.n_edges_dev ? min(p.n_edges, *p.n_edges_dev) : p.n_edges;
   if (p.count_out && blockIdx.x == 0 && threadIdx.x == 0) *p.count_out = n_edges;
   const int W = p.p2p.world;
@@ -145,12 +166,14 @@ __global__ void __launch_bounds__(256) k_reward_update(RewardArgs p) {
       const float w_new = __fmul_rn(w_old, expf(x));                             // :246-248
       p.exp3_w[pos] = w_new;
       dsum += (double)w_new - (double)w_old;
+      wtop = fmaxf(wtop, w_new);
     }
   }
   if (p.l1_delta) {
     dsum = block_sum(dsum, s_red);
     if (threadIdx.x == 0 && dsum != 0.0) atomicAdd(p.l1_delta, dsum);
   }
+  if (p.exp3_w) publish_wmax(wtop, p.wmax, s_max);
   if (W) {   // publish: every CTA's stores are ordered before its ticket; the last CTA raises the flags
     __threadfence_system();
     __syncthreads();
@@ -189,8 +212,11 @@ __global__ void __launch_bounds__(32) k_p2p_wait(bliss_p2p q, int32_t* error) {
 }
 
 // apply all ranks' updates of one layer from this rank's own window (after k_p2p_wait)
-__global__ void __launch_bounds__(256) k_apply_updates_p2p(bliss_p2p q, int64_t cap, float* exp3_w, double* l1_delta) {
+__global__ void __launch_bounds__(256) k_apply_updates_p2p(bliss_p2p q, int64_t cap, float* exp3_w, double* l1_delta,
+                                                          float* wmax) {
   __shared__ double s_red[32];
+  __shared__ float s_max[32];
+  float wtop = 0.0f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t total = (int64_t)q.world * cap;
   const int parity = (int)(*q.step_dev & 1);
@@ -237,17 +263,21 @@ __global__ void __launch_bounds__(256) k_apply_updates_p2p(bliss_p2p q, int64_t 
       }
       const float w_old = __uint_as_float(seen);
       dsum += (double)__fmul_rn(w_old, f[u]) - (double)w_old;
+      wtop = fmaxf(wtop, __fmul_rn(w_old, f[u]));
     }
   }
   if (l1_delta) {
     dsum = block_sum(dsum, s_red);
     if (threadIdx.x == 0 && dsum != 0.0) atomicAdd(l1_delta, dsum);
   }
+  publish_wmax(wtop, wmax, s_max);
 }
 
 __global__ void __launch_bounds__(256) k_apply_updates(const int64_t* __restrict__ pos, const float* __restrict__ x,
-                                                      int64_t n, float* exp3_w, double* l1_delta) {
+                                                      int64_t n, float* exp3_w, double* l1_delta, float* wmax) {
   __shared__ double s_red[32];
+  __shared__ float s_max[32];
+  float wtop = 0.0f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   double dsum = 0.0;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += stride) {
@@ -262,11 +292,13 @@ __global__ void __launch_bounds__(256) k_apply_updates(const int64_t* __restrict
     } while (old != assumed);
     const float w_old = __uint_as_float(old);
     dsum += (double)__fmul_rn(w_old, f) - (double)w_old;
+    wtop = fmaxf(wtop, __fmul_rn(w_old, f));
   }
   if (l1_delta) {
     dsum = block_sum(dsum, s_red);
     if (threadIdx.x == 0 && dsum != 0.0) atomicAdd(l1_delta, dsum);
   }
+  publish_wmax(wtop, wmax, s_max);
 }
 
 // Apply every rank's update of one layer straight from the all-gathered exchange buffer:
@@ -275,8 +307,10 @@ __global__ void __launch_bounds__(256) k_apply_updates(const int64_t* __restrict
 __global__ void __launch_bounds__(256) k_apply_updates_packed(const unsigned char* __restrict__ recv,
                                                              int64_t rank_stride, int world, int64_t count_off,
                                                              int64_t pos_off, int64_t x_off, int64_t cap,
-                                                             float* exp3_w, double* l1_delta) {
+                                                             float* exp3_w, double* l1_delta, float* wmax) {
   __shared__ double s_red[32];
+  __shared__ float s_max[32];
+  float wtop = 0.0f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t total = (int64_t)world * cap;
   double dsum = 0.0;
@@ -297,11 +331,13 @@ __global__ void __launch_bounds__(256) k_apply_updates_packed(const unsigned cha
     } while (old != assumed);
     const float w_old = __uint_as_float(old);
     dsum += (double)__fmul_rn(w_old, f) - (double)w_old;
+    wtop = fmaxf(wtop, __fmul_rn(w_old, f));
   }
   if (l1_delta) {
     dsum = block_sum(dsum, s_red);
     if (threadIdx.x == 0 && dsum != 0.0) atomicAdd(l1_delta, dsum);
   }
+  publish_wmax(wtop, wmax, s_max);
 }
 
 // literal F.normalize(w, p=1): fixed two-level tree -> deterministic
@@ -373,7 +409,7 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
                         const float* w_static_csc, const float* a_ij, const float* asum, const float* qsum,
                         int32_t alpha_mode, float delta, int32_t n_dst, int64_t n_edges, float* exp3_w_csc,
                         float* rewards, float* x_out, double* l1_delta, const int64_t* n_edges_dev,
-                        int64_t* count_out, int32_t* pos_out, const bliss_p2p* p2p, void* stream) {
+                        int64_t* count_out, int32_t* pos_out, const bliss_p2p* p2p, float* wmax, void* stream) {
   if (!g || n_edges < 0 || n_dst < 0) return -1;
   if (p2p && (p2p->world <= 0 || p2p->world > 32 || !p2p->peer_base || !p2p->step_dev || !p2p->done_ctr ||
               p2p->rank < 0 || p2p->rank >= p2p->world || p2p->layer < 0 || p2p->layer >= p2p->n_layers))
@@ -406,6 +442,7 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
   p.rewards = rewards;
   p.x_out = x_out;
   p.l1_delta = l1_delta;
+  p.wmax = wmax;
   if (p2p) {
     p.p2p = *p2p;
   } else {
@@ -418,30 +455,30 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
 }
 
 int bliss_apply_updates(const int64_t* pos, const float* x, int64_t n, float* exp3_w_csc, double* l1_delta,
-                        void* stream) {
+                        float* wmax, void* stream) {
   if (n < 0 || !exp3_w_csc) return -1;
   if (n == 0) return 0;
   if (!pos || !x) return -1;
-  k_apply_updates<<<grid_for(n, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(pos, x, n, exp3_w_csc, l1_delta);
+  k_apply_updates<<<grid_for(n, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(pos, x, n, exp3_w_csc, l1_delta, wmax);
   BLISS_CHECK_LAUNCH();
   return 0;
 }
 
 int bliss_apply_updates_packed(const void* recv, int64_t rank_stride_bytes, int32_t world, int64_t count_off,
                                int64_t pos_off, int64_t x_off, int64_t cap, float* exp3_w_csc, double* l1_delta,
-                               void* stream) {
+                               float* wmax, void* stream) {
   if (!recv || !exp3_w_csc || world <= 0 || cap < 0 || rank_stride_bytes <= 0) return -1;
   if ((count_off & 7) || (pos_off & 3) || (x_off & 3)) return -1;
   if (cap == 0) return 0;
   BLISS_KSCOPE("k_apply_updates_packed", stream);
   k_apply_updates_packed<<<grid_for((int64_t)world * cap, 256, BLISS_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(
-      (const unsigned char*)recv, rank_stride_bytes, world, count_off, pos_off, x_off, cap, exp3_w_csc, l1_delta);
+      (const unsigned char*)recv, rank_stride_bytes, world, count_off, pos_off, x_off, cap, exp3_w_csc, l1_delta, wmax);
   BLISS_CHECK_LAUNCH();
   return 0;
 }
 
 int bliss_apply_updates_p2p(const bliss_p2p* p2p, int64_t cap, float* exp3_w_csc, double* l1_delta, int32_t* error,
-                            void* stream) {
+                            float* wmax, void* stream) {
   if (!p2p || !exp3_w_csc || cap < 0 || p2p->world <= 0 || p2p->world > 32 || !p2p->peer_base || !p2p->step_dev) return -1;
   if (cap == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -452,7 +489,7 @@ int bliss_apply_updates_p2p(const bliss_p2p* p2p, int64_t cap, float* exp3_w_csc
   }
   BLISS_KSCOPE("k_apply_updates_p2p", st);
   k_apply_updates_p2p<<<grid_for((int64_t)p2p->world * cap, 256, BLISS_SM_COUNT * 4), 256, 0, st>>>(*p2p, cap, exp3_w_csc,
-                                                                                                 l1_delta);
+                                                                                                 l1_delta, wmax);
   BLISS_CHECK_LAUNCH();
   return 0;
 }

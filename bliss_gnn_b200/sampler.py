@@ -22,6 +22,8 @@ import ctypes as C
 import os
 from typing import List, Optional
 
+import math
+
 import torch
 
 from . import _native as N
@@ -210,6 +212,11 @@ class BanditLadiesSampler:
             self._w_buf = torch.ones(L, e_pad, dtype=torch.float32, device=g.device)  # bandit_sampler.py:343
             self._w_csc = [self._w_buf[l, :E] for l in range(L)]
             self._l1 = torch.full((L,), float(E), dtype=torch.float64, device=g.device)
+            # running max of every layer's weights (kept by the update kernels) + a pinned copy a step graph refreshes:
+            # the lazy normalisation re-scales when a weight nears the top of the fp32 range (tick_renorm)
+            self._wmax = torch.ones(L, dtype=torch.float32, device=g.device)
+            self._wmax_host = torch.ones(L, dtype=torch.float32).pin_memory() if g.device.type == "cuda" \
+                else torch.ones(L, dtype=torch.float32)
             self._updated = [False] * L
             self._norm_partial = torch.empty(1024, dtype=torch.float64, device=g.device)
         return self._wsp
@@ -246,7 +253,12 @@ class BanditLadiesSampler:
         for l in range(v.shape[0]):
             self._w_csc[l].copy_(v[l, g.eid.long()])
         self._l1.copy_(torch.stack([w.double().abs().sum() for w in self._w_csc]))   # in place (captured graphs)
+        self._refresh_wmax()
         self._updated = [True] * v.shape[0]
+
+    def _refresh_wmax(self):
+        self._wmax.copy_(torch.stack([w.max() for w in self._w_csc]).clamp_min(0).float())
+        self._wmax_host.copy_(self._wmax)
 
     def state_dict(self):
         return {"exp3_w_csc": torch.stack(list(self._w_csc)), "l1": self._l1.clone(), "updated": list(self._updated),
@@ -257,6 +269,7 @@ class BanditLadiesSampler:
         for l, w in enumerate(sd["exp3_w_csc"]):
             self._w_csc[l].copy_(w)
         self._l1.copy_(sd["l1"])          # in place: a captured step graph holds this buffer's address
+        self._refresh_wmax()
         self._updates_since_renorm = int(sd.get("updates_since_renorm", 0))
         self._updated = list(sd["updated"])
         self.step = int(sd["step"])
@@ -578,7 +591,8 @@ class BanditLadiesSampler:
             N.ptr(emb.contiguous()), N.ptr(w_static), N.ptr(a), N.ptr(asum), N.ptr(qsum),
             1 if kind == "gat" else 0, 0.01, mfg.num_dst_nodes(), mfg.num_edges(), N.ptr(weights),
             N.ptr(rewards), N.ptr(x_out), N.ptr(l1), n_edges_dev, count_out, N.ptr(pos_out),
-            C.byref(p2p) if p2p is not None else None, N.stream())
+            C.byref(p2p) if p2p is not None else None,
+            N.ptr(self._wmax[idx:idx + 1]) if weights is not None else None, N.stream())
 
     def calculate_rewards(self, idx, mfg, g, alpha):
         """``bandit_sampler.py:160-193``: stores ``mfg.edata['rewards']`` (emit-only kernel call)."""
@@ -608,7 +622,7 @@ class BanditLadiesSampler:
         for pos_r, x_r in gather_updates(mfg.csc_pos, x, pg):
             if pos_r.numel():
                 N.call("bliss_apply_updates", N.ptr(pos_r), N.ptr(x_r), pos_r.numel(), N.ptr(self._w_csc[idx]),
-                       N.ptr(self._l1[idx:idx + 1]), N.stream())
+                       N.ptr(self._l1[idx:idx + 1]), N.ptr(self._wmax[idx:idx + 1]), N.stream())
 
     def _renormalize(self, idx):
         w = self._w_csc[idx]
@@ -617,6 +631,7 @@ class BanditLadiesSampler:
                                 N.stream())
         N.call("bliss_scale_by_inv", N.ptr(w), w.numel(), N.ptr(self._l1[idx:idx + 1]), 1e-12, N.stream())
         self._l1[idx:idx + 1].fill_(1.0)      # (a fill launch: capturable, unlike assigning a Python scalar)
+        self._wmax[idx:idx + 1].fill_(1.0)    # (an upper bound: the re-scaled weights sum to 1)
 
     def exp3_emit(self, mfgs, g, exchange):
         """Data-parallel, sync-free: compute every layer's clamped exponents into the exchange's send
@@ -643,28 +658,52 @@ class BanditLadiesSampler:
     def exp3_apply_layer(self, exchange, idx: int):
         if exchange.p2p:      # wait for every rank's flag of this layer, then apply the slots of the own window
             N.call("bliss_apply_updates_p2p", C.byref(exchange.p2p_struct(idx)), exchange.caps[idx],
-                   N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]), N.ptr(exchange.err), N.stream())
+                   N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]), N.ptr(exchange.err),
+                   N.ptr(self._wmax[idx:idx + 1]), N.stream())
         else:
             N.call("bliss_apply_updates_packed", N.ptr(exchange.recv), exchange.stride, exchange.world,
                    8 * idx, exchange.pos_off[idx], exchange.x_off[idx], exchange.caps[idx],
-                   N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]), N.stream())
+                   N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]), N.ptr(self._wmax[idx:idx + 1]), N.stream())
         self._updated[idx] = True
         if self.normalize == "literal":
             self._renormalize(idx)
 
-    def tick_renorm(self, n_layers: int):
-        """Lazy mode's range safety: physically re-normalise every ``renorm_every`` updates (a weight
-        grows by at most e per update, ``bandit_sampler.py:244-246``)."""
+    #: ln(FLT_MAX) with a little room
+    _LOG_RANGE = 88.0
+
+    def mirror_wmax_(self):
+        """Refresh the pinned copy of the running weight maxima (a copy node of the step graph; stream-ordered)."""
+        self._wmax_host.copy_(self._wmax, non_blocking=True)
+
+    def tick_renorm(self, n_layers: int, mirrored: bool = False):
+        """Lazy mode's range safety (a weight grows by at most e per update, ``bandit_sampler.py:244-246``; every
+        rank's update lands on this copy of the weights, so W ranks can grow an edge by e^W per step).  The update
+        kernels keep the running maximum of every layer's weights; the weights are physically re-normalised — a pass
+        over 3 x |E| floats — only when that maximum leaves room for fewer updates than can happen before the next
+        look, not on a fixed schedule.
+
+        ``mirrored``: a step graph refreshes the pinned copy of the maxima every step (``mirror_wmax_``): it is read
+        here without a sync, on every call, and may be up to 6 steps old.  Otherwise the device value is read (one
+        sync) every ``renorm_every`` updates."""
         if self.normalize != "lazy" or self._w_csc is None:     # (the LADIES / uniform samplers have no bandit state)
             return
-        # every rank's update lands on this copy of the weights: an edge sampled by all W ranks can grow by e^W per
-        # step, so the range guard counts APPLIED updates, not steps
         pg = self.process_group
-        self._updates_since_renorm += torch.distributed.get_world_size(pg) if pg is not None else 1
-        if self._updates_since_renorm >= self.renorm_every:
-            for idx in range(n_layers):
-                self._renormalize(idx)
+        W = torch.distributed.get_world_size(pg) if pg is not None else 1
+        if mirrored and self._LOG_RANGE - 7.0 * W >= 1.0:
+            if float(self._wmax_host[:n_layers].max()) <= math.exp(self._LOG_RANGE - 7.0 * W):
+                return
+        else:
+            self._updates_since_renorm += W
+            if self._updates_since_renorm < self.renorm_every:
+                return
             self._updates_since_renorm = 0
+            room = self._LOG_RANGE - self.renorm_every - W
+            if room >= 1.0 and float(self._wmax[:n_layers].max()) <= math.exp(room):
+                return
+        for idx in range(n_layers):
+            self._renormalize(idx)
+        self._wmax_host.fill_(1.0)
+        self._updates_since_renorm = 0
 
     def exp3(self, mfgs, g, exchange=None, count_renorm=True):
         """``bandit_sampler.py:251-267``: reward + weight update of every layer, one fused kernel each.
@@ -681,7 +720,7 @@ class BanditLadiesSampler:
             for idx in range(len(mfgs)):
                 N.call("bliss_apply_updates_packed", N.ptr(exchange.recv), exchange.stride, exchange.world,
                        8 * idx, exchange.pos_off[idx], exchange.x_off[idx], exchange.caps[idx],
-                       N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]), N.stream())
+                       N.ptr(self._w_csc[idx]), N.ptr(self._l1[idx:idx + 1]), N.ptr(self._wmax[idx:idx + 1]), N.stream())
                 self._updated[idx] = True
                 if self.normalize == "literal":
                     self._renormalize(idx)

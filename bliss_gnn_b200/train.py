@@ -566,13 +566,14 @@ class Trainer:
         self._cur = 1 - p
         self._static_loss, self._static_pred, self._static_y = self._static_out[p if prefetch or ("N", p) not in self._static_out
                                                                                 else ("N", p)]
+        bandit_mirror = getattr(smp, "_w_csc", None) is not None
         slot = self.graph_replays & 1
         self.graph_replays += 1
         self._call_done[slot].record()            # (counters and loss were copied to pinned memory inside the graphs)
         self._graph_loss = ("graph", (slot, p))
         for _, q in fresh:                        # … and the seed buffers its sampling read may be overwritten after it
             self._set_free[q] = self._call_done[slot]
-        smp.tick_renorm(L)
+        smp.tick_renorm(L, mirrored=bandit_mirror)
         if self.pipeline:                                      # consume the PREVIOUS call's counters
             prev, self._pending = self._pending, (slot, fresh)
             if prev is None:
@@ -764,6 +765,13 @@ class Trainer:
             with torch.cuda.stream(self._side_c):
                 self._loss_pins[p].copy_(loss.detach().reshape(1), non_blocking=True)
 
+        def mirror_wmax(after):
+            """The layers' running weight maxima to pinned memory, behind the step's last update (a copy node off the
+            sampling chain): the host's range guard reads them without a sync (sampler.tick_renorm)."""
+            self._side_c.wait_stream(after)
+            with torch.cuda.stream(self._side_c):
+                smp.mirror_wmax_()
+
         def launch_deferred(pset):
             """The input layer's transpose of the set this step trains on, beside the forward pass."""
             if pset.deferred:
@@ -804,6 +812,7 @@ class Trainer:
                             self._side_s.wait_stream(self._side_b)
                         with torch.cuda.stream(self._side_s):
                             smp.update_exp3_weights(l, pb, g)
+                            mirror_wmax(self._side_s)
                             if prefetch:
                                 sample_into(other, "G")
                 return hook
@@ -890,6 +899,7 @@ class Trainer:
             layer's is left when the top layer's flags arrive and sampling (top layer first) can start."""
             if bandit:
                 smp.exp3_apply(self._exchange, L)
+                smp.mirror_wmax_()
             if prefetch:
                 sample_into(self._sets[1 - p], "G")
             if not (bandit or prefetch):
@@ -933,6 +943,8 @@ class Trainer:
                 with torch.cuda.stream(self._side_apply):
                     for l in range(l0, l1):
                         smp.exp3_apply_layer(self._exchange, l)
+                    if l1 == L:
+                        mirror_wmax(self._side_apply)
                     if l1 == L and prefetch:
                         sample_into(other, "G")
 

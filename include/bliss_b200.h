@@ -303,21 +303,24 @@ int bliss_reward_update(const bliss_graph* g, const int32_t* blk_indptr, const i
                         int64_t* count_out /* where to store the edge count (exchange header), or NULL */,
                         int32_t* pos_out /* [E_b] CSC positions as int32 (exchange send buffer; |E| < 2^31), or NULL */,
                         const bliss_p2p* p2p /* also store (pos, x) into every rank's window + raise flags, or NULL */,
+                        float* wmax /* [1] running max of the updated weights (atomic max; weights are positive) — the
+                                       range guard of the lazy normalisation re-scales when it nears FLT_MAX —, or NULL */,
                         void* stream);
 /* wait for every rank's flag of p2p->layer (one polling CTA; a peer that never arrives sets bit `layer` of *error
  * after ~4 s instead of hanging), then w[pos] *= exp(x) for all ranks' slots of this rank's window */
 int bliss_apply_updates_p2p(const bliss_p2p* p2p, int64_t cap, float* exp3_w_csc, double* l1_delta,
-                            int32_t* error /* device int, or NULL */, void* stream);
+                            int32_t* error /* device int, or NULL */, float* wmax /* see bliss_reward_update */,
+                            void* stream);
 /* apply gathered updates from other ranks: w[pos[k]] *= exp(x[k]) */
 int bliss_apply_updates(const int64_t* pos, const float* x, int64_t n, float* exp3_w_csc,
-                        double* l1_delta, void* stream);
+                        double* l1_delta, float* wmax, void* stream);
 /* data-parallel fast path: apply all ranks' updates of one layer straight from the all-gathered
  * exchange buffer (per rank: int64 count at count_off, int32 pos[cap] at pos_off, fp32 x[cap] at
  * x_off; offsets in bytes).  The reward kernel wrote pos and x straight into the send buffer — no
  * packing pass, no host-side sizes; 8 bytes per sampled edge on the wire. */
 int bliss_apply_updates_packed(const void* recv, int64_t rank_stride_bytes, int32_t world,
                                int64_t count_off, int64_t pos_off, int64_t x_off, int64_t cap,
-                               float* exp3_w_csc, double* l1_delta, void* stream);
+                               float* exp3_w_csc, double* l1_delta, float* wmax, void* stream);
 /* literal F.normalize(p=1) of one layer's weights (bandit_sampler.py:249): two launches. */
 int bliss_l1_norm(const float* w, int64_t n, double* partial /* [1024] */, double* out /* [1] */,
                   void* stream);

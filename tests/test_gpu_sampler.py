@@ -272,6 +272,45 @@ def test_exp3_update_parity_three_steps(native_lib, normalize):
         torch.testing.assert_close(w_dev.sum(dim=1), torch.ones(3, dtype=torch.float64), rtol=1e-6, atol=0)
 
 
+def test_lazy_renorm_is_driven_by_the_weight_maximum(native_lib):
+    """Lazy normalisation: the update kernels keep the running maximum of a layer's weights; the physical
+    re-normalisation (a pass over L x |E| weights) happens when that maximum nears the top of the fp32 range, not on
+    a schedule — and leaves the normalised weights (``exp3_weights``) unchanged."""
+    V, E, hubs, hdeg, batch, fan = GRAPHS["heavy"]
+    gd = random_graph(V, E, seed=5, hubs=hubs, hub_degree=hdeg).to(_dev())
+    dev = _device_sampler("PoissonBanditLadiesSampler", fan, eta=0.1, rng_seed=3, normalize="lazy")
+    gen = torch.Generator().manual_seed(0)
+
+    def step():
+        _, _, db = dev.sample_blocks(gd, torch.randperm(V, generator=gen)[:batch])
+        for a in db:
+            a.srcdata["embed_norm"] = (torch.rand(a.num_src_nodes(), generator=gen) * 3 + 0.1).to(gd.device)
+        dev.exp3(db, gd)
+
+    step()
+    L = len(fan)
+    true_max = torch.stack([w.max() for w in dev._w_csc])
+    assert torch.all(dev._wmax >= true_max) and torch.all(dev._wmax <= true_max * 1.000001), (dev._wmax, true_max)
+    # the schedule's horizon passes with small weights: no re-normalisation (L1 stays ~|E|)
+    dev._updates_since_renorm = dev.renorm_every
+    dev.tick_renorm(L)
+    assert float(dev._l1.min()) > 0.5 * gd.num_edges() and dev._updates_since_renorm == 0
+    before = dev.exp3_weights.clone()
+    # a weight near the top of the range: re-normalised at the next look (device value, then the pinned copy)
+    for mirrored in (False, True):
+        dev._wmax.fill_(1e37)
+        dev._wmax_host.fill_(1e37 if mirrored else 1.0)
+        dev._updates_since_renorm = dev.renorm_every
+        dev.tick_renorm(L, mirrored=mirrored)
+        torch.testing.assert_close(dev._l1, torch.ones(L, dtype=torch.float64, device=gd.device))
+        assert float(dev._wmax.max()) == 1.0 and float(dev._wmax_host.max()) == 1.0
+        torch.testing.assert_close(dev.exp3_weights, before, rtol=1e-6, atol=0)
+        step()                                    # updates after the re-scale keep the bound
+        true_max = torch.stack([w.max() for w in dev._w_csc])
+        assert torch.all(dev._wmax >= true_max)
+        before = dev.exp3_weights.clone()
+
+
 def test_gat_alpha_rewards(native_lib):
     """GAT alpha path of the bandit (bandit_sampler.py:146-154) with random a_ij."""
     g = random_graph(800, 5000, seed=9)
@@ -339,10 +378,13 @@ def test_packed_exchange_apply_matches_sequential_updates(native_lib):
             base[ex.pos_off[l]:ex.pos_off[l] + 4 * n].view(torch.int32).copy_(pos.to(torch.int32))
             base[ex.x_off[l]:ex.x_off[l] + 4 * n].view(torch.float32).copy_(xs)
             expect[l][pos] = expect[l][pos] * torch.exp(xs.double())
+    wmax = torch.zeros(len(caps), dtype=torch.float32, device=w_dev[0].device)
     for l in range(len(caps)):
         N.call("bliss_apply_updates_packed", N.ptr(ex.recv), ex.stride, world, 8 * l, ex.pos_off[l], ex.x_off[l],
-               caps[l], N.ptr(w_dev[l]), N.ptr(l1[l:l + 1]), N.stream())
+               caps[l], N.ptr(w_dev[l]), N.ptr(l1[l:l + 1]), N.ptr(wmax[l:l + 1]), N.stream())
         torch.testing.assert_close(w_dev[l].cpu().double(), expect[l], rtol=1e-6, atol=0)
+        # the running maximum of the UPDATED weights (the range guard of the lazy normalisation)
+        assert 0.5 < float(wmax[l]) <= float(w_dev[l].max())
         delta = float(l1[l].item())
         assert abs(delta - float((expect[l] - w[l].double()).sum())) <= 1e-5 * abs(delta)
 

@@ -101,3 +101,27 @@ def test_sampler_factory_follows_the_flag():
     assert not make_sampler("neighbor", [5, 5]).attach_weights and make_sampler("ladies", [5, 5]).attach_weights
     args = build_argparser().parse_args(["--sampler", "neighbor", "--vertex-limit", "5000", "--early-stopping-patience", "3"])
     assert args.sampler == "neighbor" and args.vertex_limit == 5000 and args.early_stopping_patience == 3
+
+
+def test_flat_layout_pads_marked_weights_in_place():
+    """parallel.flat_layout: a 2-D parameter marked ``_bliss_pad_cols`` gets its zero columns inside the flat
+    storage (the gradient view and the padded matrix alias the same memory), every tensor starts 16-byte aligned."""
+    import torch
+    from bliss_gnn_b200.parallel import FlatGrads, flat_layout, flat_view
+    w0 = torch.nn.Parameter(torch.arange(6 * 5, dtype=torch.float32).view(6, 5))
+    b0 = torch.nn.Parameter(torch.ones(6))
+    w1 = torch.nn.Parameter(torch.ones(3, 6))
+    w0._bliss_pad_cols = 3
+    layout, total = flat_layout([w0, b0, w1])
+    assert [off % 4 for off, _ in layout] == [0, 0, 0] and layout[0][1] == 3 and layout[1][1] == 0
+    assert total >= 6 * 8 + 6 + 18
+    fg = FlatGrads([w0, b0, w1])
+    assert w0.grad.shape == (6, 5) and w0.grad.stride() == (8, 1) and w0._bliss_padded_grad.shape == (6, 8)
+    w0.grad.fill_(2.0)
+    assert float(w0._bliss_padded_grad[:, :5].min()) == 2.0 and float(w0._bliss_padded_grad[:, 5:].abs().max()) == 0.0
+    assert float(fg.flat.sum()) == 2.0 * 30
+    assert b0._bliss_padded_grad is None and b0.grad.is_contiguous()
+    flat = torch.zeros(total)
+    view, full = flat_view(flat, layout[0][0], w0, 3)
+    view.copy_(w0.detach())
+    assert torch.equal(full[:, :5], w0.detach()) and float(full[:, 5:].abs().max()) == 0.0
