@@ -237,8 +237,9 @@ def main():
         # NCCL's init lines (version, rank / nranks / transport of every communicator) are written to stdout by the
         # library: file descriptor 1 is pointed at stderr for the run and the ONE JSON line goes to the saved stdout,
         # so the driver can read the rank count off the run's own log and still parse stdout
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
         sys.stdout.flush()
         json_fd = os.dup(1)
         os.dup2(2, 1)
