@@ -643,9 +643,13 @@ class Trainer:
             for l, c in enumerate(ctrs):
                 if c.error:
                     cap = (pset.pools[l].cap_src, pset.pools[l].cap_edges) if pset is not None else ("?", "?")
-                    raise RuntimeError(f"static step: capacity of layer {l} exceeded (n_src {c.n_src}/{cap[0]}, "
-                                       f"edges {c.n_edges}/{cap[1]}); the step is invalid — "
-                                       "raise the pool margins or use static_graph=False")
+                    msg = (f"static step: capacity of layer {l} exceeded (n_src {c.n_src}/{cap[0]}, "
+                           f"edges {c.n_edges}/{cap[1]}); the step is invalid — "
+                           "raise the pool margins or use static_graph=False")
+                    if self.world > 1:            # abort on every rank together (at the next vote), not on this one alone
+                        self._cap_error = getattr(self, "_cap_error", None) or msg
+                        continue
+                    raise RuntimeError(msg)
                 self._max_src[l] = max(self._max_src[l], c.n_src)
                 self._max_edges[l] = max(self._max_edges[l], c.n_edges)
                 if pset is not None:
@@ -663,17 +667,50 @@ class Trainer:
             self._grow_pending = getattr(self, "_grow_pending", False) or grow
             grow = False
             if self.num_steps % 32 == 0:
-                if self._exchange is not None and self._exchange.p2p and int(self._exchange.err.item()):
-                    raise RuntimeError("peer-memory bandit exchange: a rank's update did not arrive within the timeout "
-                                       f"(layer mask {int(self._exchange.err.item())})")
-                if self._gradx and int(self._gradx.err.item()):
-                    raise RuntimeError("peer-memory gradient exchange: a rank's gradient did not arrive within the timeout")
-                flag = torch.tensor([1.0 if self._grow_pending else 0.0], device=g.device)
-                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX, group=self.pg)
-                grow, self._grow_pending = bool(flag.item() > 0), False
+                grow = self._dp_vote()
         if grow:                                               # high-water mark: re-size before it can overflow
             self.pool_resizes += 1
             self._alloc_pools()
+
+    def _dp_vote(self) -> bool:
+        """Data parallel, every 32 steps: do the pools have to grow (any rank over its high-water mark), did a capacity
+        overflow or an exchange time-out happen anywhere?  One 4-float MAX all-reduce whose result is read at the NEXT
+        vote (pinned copy behind an event), so the host never waits for the device here; every rank acts on the same
+        result at the same step (re-sizing and aborting are collective)."""
+        dev = self.dm.g.device
+        res = None
+        if getattr(self, "_vote", None) is not None:
+            self._vote.synchronize()
+            res = self._vote_pin.clone()
+        else:
+            self._vote_dev = torch.zeros(4, dtype=torch.float32, device=dev)
+            self._vote_stage = torch.zeros(4, dtype=torch.float32).pin_memory()
+            self._vote_pin = torch.zeros(4, dtype=torch.float32).pin_memory()
+            self._vote = torch.cuda.Event()
+        self._vote_stage[0] = 1.0 if self._grow_pending else 0.0
+        self._vote_stage[1] = 1.0 if getattr(self, "_cap_error", None) else 0.0
+        self._vote_stage[2:] = 0.0
+        self._grow_pending = False
+        v = self._vote_dev
+        v.copy_(self._vote_stage, non_blocking=True)
+        if self._exchange is not None and self._exchange.p2p:
+            v[2:3].copy_((self._exchange.err != 0).float())
+        if self._gradx:
+            v[3:4].copy_((self._gradx.err != 0).float())
+        torch.distributed.all_reduce(v, op=torch.distributed.ReduceOp.MAX, group=self.pg)     # (stream-ordered)
+        self._vote_pin.copy_(v, non_blocking=True)
+        self._vote.record()
+        if res is None:
+            return False
+        if res[1] > 0:
+            raise RuntimeError(getattr(self, "_cap_error", None) or
+                               "static step: a pool capacity was exceeded on another rank; the step is invalid — "
+                               "raise the pool margins or use static_graph=False")
+        if res[2] > 0:
+            raise RuntimeError("peer-memory bandit exchange: a rank's update did not arrive within the timeout")
+        if res[3] > 0:
+            raise RuntimeError("peer-memory gradient exchange: a rank's gradient did not arrive within the timeout")
+        return bool(res[0] > 0)
 
     def _dp_exchange(self):
         """The only exchanges of a data-parallel step: one all-reduce of the flat gradient buffer and one
