@@ -951,46 +951,53 @@ __global__ void __launch_bounds__(1024) k_block_index(const int32_t* __restrict_
   const int n_sel = min(ctr->n_sel, (int)ws.cap_sel);
   const int lane = lane_id();
   if (blockIdx.x == 0) {
+    // An overflowing block (more kept edges than the pool holds) must stay memory-safe for the kernels of a replayed
+    // step that run before the host sees the error flag: row extents are clamped to the capacity (the fill kernel
+    // skips the block, so the rows then point at older, in-range edges) and the counters report clamped sizes.
+    const int ecap = (out.cap_edges > 0) ? (int)min((int64_t)0x7fffffff, out.cap_edges) : 0x7fffffff;
     int base = 0, sbase = 0;
     for (int b = 0; b < n_seeds; b += blockDim.x * 4) {
       const int i0 = b + threadIdx.x * 4;
-      int v[4], sg[4], pre[4], spre[4];
+      int v[4], len[4], sg[4], pre[4], spre[4];
       load4(ws.row_cnt, i0, n_seeds, v);
       int vsum = 0, ssum = 0;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        sg[u] = (i0 + u < n_seeds) ? max(1, (v[u] + BLISS_SPMM_SEG - 1) / BLISS_SPMM_SEG) : 0;
-        vsum += v[u];
-        ssum += sg[u];
-      }
+      for (int u = 0; u < 4; ++u) vsum += v[u];
       int tot, st = 0;
       int p = base + block_excl_scan(vsum, s_scan, &tot);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        pre[u] = min(p, ecap);
+        len[u] = min(p + v[u], ecap) - pre[u];   // == v[u] unless the block overflows
+        sg[u] = (i0 + u < n_seeds) ? max(1, (len[u] + BLISS_SPMM_SEG - 1) / BLISS_SPMM_SEG) : 0;
+        ssum += sg[u];
+        p += v[u];
+      }
       int sp = sbase + (out.seg_ptr ? block_excl_scan(ssum, s_scan, &st) : 0);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        pre[u] = p;
         spre[u] = sp;
-        p += v[u];
         sp += sg[u];
       }
       store4(out.indptr, i0, n_seeds, pre);
       if (out.seg_ptr) store4(out.seg_ptr, i0, n_seeds, spre);
       if (out.inv_deg) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) pre[u] = __float_as_int(1.0f / (float)max(v[u], 1));   // fn.mean divisor
+        for (int u = 0; u < 4; ++u) pre[u] = __float_as_int(1.0f / (float)max(len[u], 1));   // fn.mean divisor
         store4(reinterpret_cast<int32_t*>(out.inv_deg), i0, n_seeds, pre);
       }
       base += tot;
       sbase += st;
     }
+    const int base_c = min(base, ecap);
     // capacity padding (static-shape replay): rows beyond n_seeds are empty (one empty segment each)
     for (int64_t i = n_seeds + threadIdx.x; i <= max((int64_t)n_seeds, out.pad_rows); i += blockDim.x) {
-      out.indptr[i] = base;
+      out.indptr[i] = base_c;
       if (out.seg_ptr) out.seg_ptr[i] = sbase + (int)(i - n_seeds);
     }
     if (threadIdx.x == 0) {
-      ctr->n_edges = base;
-      ctr->n_src = n_seeds + n_sel;
+      ctr->n_edges = base_c;
+      ctr->n_src = (int)min((int64_t)n_seeds + n_sel, out.cap_src > 0 ? out.cap_src : (int64_t)0x7fffffff);
       if (n_seeds + n_sel > out.cap_src) ctr->error |= BLISS_ERR_SEL_CAPACITY;
       if (base > out.cap_edges && out.cap_edges > 0) ctr->error |= BLISS_ERR_EDGE_CAPACITY;
     }

@@ -266,6 +266,9 @@ class Trainer:
         self._grads_clean = isinstance(self.optimizer, FlatAdam)
 
     # ---- static-shape path: capacity-padded blocks in persistent pools + CUDA graphs ------------------------
+    #: edge capacity of a pool = FACTOR x the largest block seen in the sizing steps + SLACK
+    POOL_EDGE_FACTOR, POOL_EDGE_SLACK = 1.45, 4096
+
     def _alloc_pools(self):
         """Two pool sets (double buffering): while the backward pass of step t still reads set p, the blocks of
         step t+1 are sampled into set 1-p (``_training_step_full_graph``).  The eager-sampling variant
@@ -280,7 +283,7 @@ class Trainer:
             dm.sampler.step -= 1
         # edges of a block vary by +-17 % around their median from batch to batch at the Reddit shape (measured over
         # 400 steps): 1.45x the largest count seen so far; the high-water mark in _consume_counters re-sizes at 92 %
-        cap_e = [int(1.45 * self._max_edges[l]) + 4096 for l in range(L)]
+        cap_e = [int(self.POOL_EDGE_FACTOR * self._max_edges[l]) + self.POOL_EDGE_SLACK for l in range(L)]
         self._exchange = None
         if (self.world > 1 or self._force_dp) and bandit:   # ranks must agree on the exchange layout
             from .parallel import BanditExchange

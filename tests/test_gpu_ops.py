@@ -346,6 +346,34 @@ def test_lookahead_sampling_keeps_the_trajectory(native_lib, kind, sampler):
         torch.testing.assert_close(res[True][1], res[False][1], rtol=2e-3 if kind == "gat" else 1e-6, atol=0)
 
 
+def test_pool_overflow_is_contained_and_reported(native_lib):
+    """A block that outgrows its capacity pool inside a replayed step: the index kernel clamps the row extents and the
+    counters to the capacity (the aggregation kernels of the same replay stay in bounds), the fill is skipped, and the
+    host raises when it reads the step's counters — the device stays usable."""
+    from bliss_gnn_b200.graph import synthetic_graph
+    from bliss_gnn_b200.train import DataModule, Trainer, build_model
+    dev = _dev()
+    g = synthetic_graph("flickr", seed=0, scale=0.3).to(dev)
+    dm = DataModule("flickr", fan_out=[512, 256, 128], eta=0.1, device=dev, batch_size=64, sampler="poisson-bandit",
+                    model="sage", seed=0, graph=g)
+    torch.manual_seed(3)
+    model = build_model("sage", dm.in_feats, 64, dm.n_classes, 3, dropout=0.0).to(dev)
+    tr = Trainer(dm, model, 0.002, static_graph=True, eager_warmup=3)
+    batches = [b for _, b in zip(range(12), dm.train_batches())]
+    for b in batches[:3]:
+        tr.training_step(b)                      # eager steps that size the pools
+    tr.POOL_EDGE_FACTOR, tr.POOL_EDGE_SLACK = 0.5, 0            # pools far too small for the blocks
+    with pytest.raises(RuntimeError, match="capacity of layer"):
+        for i, b in enumerate(batches[3:]):
+            tr.training_step(b, batches[4 + i] if 4 + i < len(batches) else None)
+        tr.flush()
+    torch.cuda.synchronize()                     # no illegal access happened on the way
+    for pset in tr._sets:
+        for pool in pset.pools:
+            assert int(pool.indptr.max()) <= pool.cap_edges and int(pool.src_nid.max()) < g.num_nodes()
+    assert float((torch.ones(8, device=dev) * 2).sum()) == 16.0
+
+
 def test_data_parallel_graph_path_on_one_rank(native_lib, monkeypatch):
     """The data-parallel step (graph A: sample+fwd+bwd+reward emit -> NCCL all-reduce / all-gather ->
     graph B: Adam + packed apply) forced on a 1-rank NCCL group follows the single-graph trajectory."""
