@@ -20,7 +20,7 @@ SOURCES = ["sampler.cu", "aggregate.cu", "bandit.cu", "gat.cu", "optim.cu", "epi
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
-MODE_BANDIT, MODE_LADIES, MODE_UNIFORM, MODE_NEIGHBOR, COLLECT_BITMAP = 0, 1, 2, 4, 16
+MODE_BANDIT, MODE_LADIES, MODE_UNIFORM, MODE_NEIGHBOR, MODE_PLANNED, COLLECT_BITMAP = 0, 1, 2, 4, 8, 16
 AGG_SUM, AGG_MEAN = 0, 1
 
 

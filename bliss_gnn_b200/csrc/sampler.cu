@@ -1599,8 +1599,9 @@ int bliss_sample_layer_front(const bliss_graph* g, const int32_t* seeds, int32_t
                              int32_t poisson, uint64_t seed, uint64_t step, uint32_t layer, const float* u_inject,
                              float* key_scratch, const bliss_workspace* ws, const bliss_block_out* out,
                              void* stream) {
-  int rc = bliss_frontier_plan(g, seeds, n_seeds, ws, stream);
+  int rc = (mode & BLISS_MODE_PLANNED) ? 0 : bliss_frontier_plan(g, seeds, n_seeds, ws, stream);
   if (rc) return rc;
+  mode &= ~BLISS_MODE_PLANNED;
   if (mode & BLISS_MODE_NEIGHBOR) {   // uniform fan-out per seed / full neighbourhood: no probabilities, no node selection
     rc = bliss_neighbor_select(g, n_seeds, fanout, seed, step, layer, ws, stream);
     if (rc) return rc;

@@ -11,6 +11,7 @@ GEMMs; message passing, edge softmax and ``embed_norm`` are the custom kernels (
 from __future__ import annotations
 
 import contextlib
+import os
 
 import torch
 import torch.nn as nn
@@ -26,7 +27,9 @@ class _LinearSplitK(torch.autograd.Function):
     ``weight.grad`` when that buffer exists (the flat gradient buffer of ``parallel.FlatGrads``), else summed
     and returned.  ``weight`` is the un-padded parameter; ``x`` may carry zero-padded extra columns."""
 
-    SPLIT, MIN_ROWS = 16, 2048
+    SPLIT, MIN_ROWS = int(os.environ.get("BLISS_SPLITK", "4")), 2048
+    #: the self projection's weight gradient on its side stream, beside the neighbour projection's (ablation switch)
+    WGRAD_OVERLAP = os.environ.get("BLISS_WGRAD_OVERLAP", "1") == "1"
 
     @staticmethod
     def forward(ctx, x, weight, bias, side=None):
@@ -44,7 +47,7 @@ class _LinearSplitK(torch.autograd.Function):
         if side is not None and w is not weight and w is not stored:
             w.record_stream(torch.cuda.current_stream())     # allocated on the side stream, read by backward on this one
         ctx.save_for_backward(x, w)
-        ctx.weight, ctx.has_bias = weight, bias is not None
+        ctx.weight, ctx.has_bias, ctx.side = weight, bias is not None, side
         return y
 
     @staticmethod
@@ -54,6 +57,30 @@ class _LinearSplitK(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = gy @ w
+        side = ctx.side if (_LinearSplitK.WGRAD_OVERLAP and ctx.needs_input_grad[1]) else None
+        ev = getattr(ops, "LAST_SPMM_BWD", None) if side is not None else None
+        if side is not None and ev is not None:
+            # this node runs last in its layer's backward pass (its forward was issued first): its weight gradient only
+            # needs the epilogue's gradient, so it goes to the side stream behind the layer's backward aggregation and
+            # runs beside the neighbour projection's weight gradient; the backward pass joins the stream when it ends
+            side.wait_event(ev)
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: torch.cuda.current_stream().wait_stream(side))
+        else:
+            side = None
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            gw = _LinearSplitK._wgrad(ctx, x, gy, weight)
+        if side is not None:
+            gy.record_stream(side)
+            x.record_stream(side)
+            if gw is not None:
+                torch.cuda.current_stream().wait_stream(side)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gw, gb, None
+
+    @staticmethod
+    def _wgrad(ctx, x, gy, weight):
+        gw = None
         if ctx.needs_input_grad[1]:
             S = _LinearSplitK.SPLIT
             k = (x.shape[0] // S) * S
@@ -75,9 +102,7 @@ class _LinearSplitK(torch.autograd.Function):
                            ops.N.ptr(g), ops.N.stream())       # accumulated in place: nothing to return
             else:
                 gw = part.sum(0)[:, :n_in]
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy.sum(0)
-        return gx, gw, gb, None
+        return gw
 
 
 def _linear(x, lin: nn.Linear, use_bias: bool = True, side=None):

@@ -9,6 +9,8 @@ Reference call sites replaced: ``train_lightning.py:138`` (feature fetch), ``mod
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _native as N
@@ -133,6 +135,14 @@ def _wait_ready(block, what="_ready"):
         torch.cuda.current_stream().wait_event(ev)
 
 
+#: recorded behind the latest backward aggregation (model._LinearSplitK's overlapped weight gradient waits for it)
+LAST_SPMM_BWD = None
+
+
+def _wgrad_overlap_on(t):
+    return t.is_cuda and os.environ.get("BLISS_WGRAD_OVERLAP", "1") == "1"
+
+
 class _SpMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, block, w, sscale, dscale):
@@ -154,6 +164,10 @@ class _SpMM(torch.autograd.Function):
         # dx_c = sscale_c * Σ_{e: src_e = c} w_e * dscale_{dst_e} * dy_{dst_e}
         gx = _spmm_raw(t_indptr, t_dst, perm, w, ctx.dscale, ctx.sscale, N.AGG_SUM, gy,
                        block.num_src_nodes(), t_seg)
+        global LAST_SPMM_BWD
+        if _wgrad_overlap_on(gy):
+            LAST_SPMM_BWD = torch.cuda.Event()
+            LAST_SPMM_BWD.record()
         return gx, None, None, None, None
 
 

@@ -462,8 +462,18 @@ class BanditLadiesSampler:
         return self._finish_block(fr, out, bufs, pool)
 
     # ---- sync-free path (CUDA-graph capture of the whole step) -----------------------------------
+    def plan_top_static(self, g, seeds_static, pools, step_dev, ctr_base: int = 0, ctr_mirror=None):
+        """The top layer's frontier plan (row extents, chunk lists, counters) of :meth:`enqueue_static`, enqueued on
+        its own: it depends on the batch only, so the whole-step graph runs it at the head of the step and the
+        sampling chain behind the bandit update starts with the probability passes."""
+        wsp = self._bind(g)
+        L = len(self.nodes_per_layer)
+        ws = wsp.ws_layer(ctr_base + L - 1, None, N.ptr(step_dev), counters=wsp,
+                          ctr_mirror=None if ctr_mirror is None else ctr_mirror[L - 1].data_ptr())
+        N.call("bliss_frontier_plan", C.byref(wsp.gview), N.ptr(seeds_static), pools[L - 1].cap_dst, C.byref(ws), N.stream())
+
     def enqueue_static(self, g, seeds_static, pools, step_dev, transpose_stream=None, defer_last_transpose=False,
-                       ctr_base: int = 0, layer_pre=None, ctr_mirror=None):
+                       ctr_base: int = 0, layer_pre=None, ctr_mirror=None, top_planned: bool = False):
         """Enqueue the sampling of every layer into the capacity pools with NO host synchronisation:
         each layer reads its true seed count from the previous layer's device counters, the Philox
         step from ``step_dev``, and the transpose its edge count from the counters.  Capturable in a
@@ -477,6 +487,7 @@ class BanditLadiesSampler:
         blocks into a second pool set while this step's backward pass still reads the first set's counts.
         ``layer_pre``: ``{layer: callable}`` run on the current stream right before that layer is sampled (the
         data-parallel step applies all ranks' bandit updates of a layer just before the layer's weights are read).
+        ``top_planned``: the top layer's plan was already enqueued (:meth:`plan_top_static`).
         ``ctr_mirror``: pinned host tensor ``[>= L, sizeof(counters)]``; layer l's finish kernel writes its counters
         to row l (device-mapped host memory), so the caller needs no device-to-host copy after the step."""
         wsp = self._bind(g)
@@ -503,6 +514,8 @@ class BanditLadiesSampler:
             mode = self._mode | (0 if self.importance_sampling else N.MODE_UNIFORM)
             if self.collect == "bitmap" or (self.collect == "auto" and g.num_nodes() > self.DENSE_COLLECT_MAX):
                 mode |= N.COLLECT_BITMAP
+            if top and top_planned:
+                mode |= N.MODE_PLANNED
             if not self._poisson and w.key_scratch is None:
                 w.key_scratch = torch.empty(g.num_nodes() + 4, dtype=torch.float32, device=g.device)
             e32 = pool.e32

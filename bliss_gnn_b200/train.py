@@ -777,7 +777,15 @@ class Trainer:
         defer0 = not isinstance(getattr(self.model, "module", self.model), GCN) and not dp \
             or os.environ.get("BLISS_DEFER_T0") == "1"
 
-        def sample_into(pset, kind, layer_pre=None):
+        plan_ahead = os.environ.get("BLISS_PLAN_AHEAD", "1") != "0"
+
+        def plan_top(pset):
+            """The top layer's plan of the next sampling into ``pset`` (depends on the batch only): at the head of the
+            step, on the stream the sampling will follow on."""
+            smp.plan_top_static(g, pset.seeds_in, pset.pools, self._step_dev, ctr_base=pset.ctr_base,
+                                ctr_mirror=self._ctr_pin("G", pset))
+
+        def sample_into(pset, kind, layer_pre=None, planned=False):
             """Sampling of one batch (``pset.seeds_in``) into ``pset``: every layer's front half on the current stream,
             back halves and transposes on ``_side_t``; complete (joined) on return.  The input layer's transpose —
             the last thing on the sampling chain, read by the backward pass only — is left to the step that trains
@@ -789,7 +797,7 @@ class Trainer:
                 pset.seeds.copy_(pset.seeds_in, non_blocking=True)
             pset.deferred = smp.enqueue_static(g, pset.seeds_in, pset.pools, self._step_dev, transpose_stream=self._side_t,
                                                defer_last_transpose=defer0, ctr_base=pset.ctr_base, layer_pre=layer_pre,
-                                               ctr_mirror=self._ctr_pin(kind, pset))
+                                               ctr_mirror=self._ctr_pin(kind, pset), top_planned=planned)
             self._step_dev.add_(1)                # (read by the layers' select kernels only: all launched by now)
             self._gather_inputs(pset, True)       # beside the input layer's fill / transposes (needs its source list only)
             cur.wait_stream(self._side_t)
@@ -831,6 +839,11 @@ class Trainer:
             clear_events(pset)
             main = torch.cuda.current_stream()
             launch_deferred(pset)
+            planned = bool(prefetch and plan_ahead)
+            if planned:
+                self._side_s.wait_stream(main)
+                with torch.cuda.stream(self._side_s):
+                    plan_top(other)
             inputs = (pset.x, pset.x_norm, pset.y) if pset.x is not None else None
             fired = []
 
@@ -854,7 +867,7 @@ class Trainer:
                             smp.update_exp3_weights(l, pb, g)
                             mirror_wmax(self._side_s)
                             if prefetch:
-                                sample_into(other, "G")
+                                sample_into(other, "G", planned=planned)
                 return hook
 
             key = "a_ij" if smp.model == "gat" else "embed_norm"
@@ -874,7 +887,7 @@ class Trainer:
                 elif prefetch:
                     self._side_s.wait_stream(main)
                     with torch.cuda.stream(self._side_s):
-                        sample_into(other, "G")
+                        sample_into(other, "G", planned=planned)
 
             try:
                 loss, pred, y = self._padded_fwd_bwd(True, after_forward=after_forward, pset=pset, inputs=inputs)

@@ -32,6 +32,9 @@ extern "C" {
 #define BLISS_MODE_NEIGHBOR 4 /* flag OR-ed onto BLISS_MODE_LADIES: uniform neighbour sampling — every seed keeps min(fanout,
                                 degree) in-edges chosen uniformly without replacement (fanout <= 0: all): DGL NeighborSampler /
                                 MultiLayerFullNeighborSampler, train_lightning.py:349-357.  No probabilities, no node selection. */
+#define BLISS_MODE_PLANNED 8  /* flag for bliss_sample_layer_front: bliss_frontier_plan for this layer (same seeds, same
+                                workspace) was already enqueued — the plan depends on the seeds only, so a caller that knows
+                                them early (the top layer's: the batch) can run it before the weights it samples with are final */
 
 #define BLISS_COLLECT_BITMAP 16 /* flag OR-ed onto the mode: collect candidates from a bitmap the scatter marks
                                   (sparse frontiers in huge graphs) instead of a dense scan of the |V| accumulators */
