@@ -987,6 +987,12 @@ class Trainer:
             main = torch.cuda.current_stream()
             launch_deferred(pset)
             forked = []
+            planned = bool(prefetch and plan_ahead)
+            if planned:                           # the next batch's top-layer plan: needs the batch only
+                self._side_apply.wait_stream(main)
+                forked.append(True)
+                with torch.cuda.stream(self._side_apply):
+                    plan_top(other)
 
             def apply_from(l0, l1, after):
                 """Layers l0..l1-1 applied behind ``after`` (the stream their local emit ran on); then, behind the top
@@ -999,7 +1005,7 @@ class Trainer:
                     if l1 == L:
                         mirror_wmax(self._side_apply)
                     if l1 == L and prefetch:
-                        sample_into(other, "G")
+                        sample_into(other, "G", planned=planned)
 
             if early_emit:
                 def make(l, pb):
@@ -1026,7 +1032,7 @@ class Trainer:
                 self._side_apply.wait_stream(main)
                 forked.append(True)
                 with torch.cuda.stream(self._side_apply):
-                    sample_into(other, "G")
+                    sample_into(other, "G", planned=planned)
             self._zero_grads()
             loss.backward()
             body_b2(adds=False)
