@@ -125,3 +125,38 @@ def test_flat_layout_pads_marked_weights_in_place():
     view, full = flat_view(flat, layout[0][0], w0, 3)
     view.copy_(w0.detach())
     assert torch.equal(full[:, :5], w0.detach()) and float(full[:, 5:].abs().max()) == 0.0
+
+
+def test_lazy_renorm_guard_decides_from_the_weight_maximum():
+    """sampler.tick_renorm (host logic, no device): with the pinned copy of the running maxima (step graphs) the
+    re-scale fires only above e^(88 - 7W); on the schedule path it looks at the device value every ``renorm_every``
+    updates and re-scales only when the room left is smaller than the next horizon."""
+    import math
+    import torch
+    from bliss_gnn_b200.sampler import PoissonBanditLadiesSampler
+    smp = PoissonBanditLadiesSampler([8, 4, 2], eta=0.1)
+    L = 3
+    smp._w_csc = [torch.ones(4) for _ in range(L)]
+    smp._wmax, smp._wmax_host = torch.ones(L), torch.ones(L)
+    calls = []
+    smp._renormalize = lambda idx: calls.append(idx)
+    for _ in range(500):                       # step graphs, small weights: never re-scaled, nothing counted
+        smp.tick_renorm(L, mirrored=True)
+    assert calls == [] and smp._updates_since_renorm == 0
+    smp._wmax_host[1] = math.exp(82.0)         # above e^(88 - 7): re-scale every layer, the copy is reset
+    smp.tick_renorm(L, mirrored=True)
+    assert calls == [0, 1, 2] and float(smp._wmax_host.max()) == 1.0
+    calls.clear()
+    for _ in range(smp.renorm_every - 1):      # schedule path (eager steps): counts updates …
+        smp.tick_renorm(L)
+    assert calls == [] and smp._updates_since_renorm == smp.renorm_every - 1
+    smp.tick_renorm(L)                         # … and at the horizon finds room for another one: counter reset only
+    assert calls == [] and smp._updates_since_renorm == 0
+    smp._wmax[0] = math.exp(30.0)              # room for fewer than renorm_every more updates: re-scale at the horizon
+    for _ in range(smp.renorm_every):
+        smp.tick_renorm(L)
+    assert calls == [0, 1, 2]
+    smp.normalize = "literal"                  # (the literal mode re-normalises after every update itself)
+    calls.clear()
+    smp.tick_renorm(L)
+    assert calls == []
