@@ -239,6 +239,7 @@ class Trainer:
         batch_pred = self.model(mfgs, batch_inputs)                              # :141
         loss = self.loss_fn(batch_pred, batch_labels)                            # :142
         self._zero_grads()
+        ops.LAST_SPMM_BWD = None          # (an event of an earlier pass / capture must not be waited for)
         loss.backward()
         self.grads.all_reduce_mean_(self.pg)
         self._optimizer_step()
@@ -348,6 +349,7 @@ class Trainer:
         self._zero_grads()
         if before_backward is not None:
             before_backward()
+        ops.LAST_SPMM_BWD = None          # (an event of an earlier pass / capture must not be waited for)
         loss.backward()
         if step_optimizer:
             self._optimizer_step()
@@ -941,6 +943,7 @@ class Trainer:
 
         def body_a2(loss):
             self._zero_grads()
+            ops.LAST_SPMM_BWD = None          # (an event of an earlier pass / capture must not be waited for)
             loss.backward()
 
         p2p = bandit and self._exchange is not None and self._exchange.p2p
@@ -1034,6 +1037,7 @@ class Trainer:
                 with torch.cuda.stream(self._side_apply):
                     sample_into(other, "G", planned=planned)
             self._zero_grads()
+            ops.LAST_SPMM_BWD = None          # (an event of an earlier pass / capture must not be waited for)
             loss.backward()
             body_b2(adds=False)
             self._drop_dev.add_(1)
