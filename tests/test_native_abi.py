@@ -44,11 +44,12 @@ def test_struct_layouts_match_header(tmp_path):
 #include <stddef.h>
 #include "bliss_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(bliss_graph), sizeof(bliss_counters),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(bliss_graph), sizeof(bliss_counters),
          sizeof(bliss_workspace), sizeof(bliss_block_out), offsetof(bliss_counters, c), offsetof(bliss_counters, error),
          offsetof(bliss_workspace, ctr), offsetof(bliss_block_out, cap_edges), sizeof(bliss_p2p),
          offsetof(bliss_p2p, flags_off), offsetof(bliss_p2p, done_ctr), sizeof(bliss_grad_p2p),
-         offsetof(bliss_grad_p2p, step_dev));
+         offsetof(bliss_grad_p2p, step_dev), offsetof(bliss_workspace, ctr_mirror), offsetof(bliss_p2p, mc_base),
+         offsetof(bliss_grad_p2p, mc_base));
   return 0;
 }
 """)
@@ -58,7 +59,7 @@ int main(void) {
     want = [ctypes.sizeof(N.Graph), ctypes.sizeof(N.Counters), ctypes.sizeof(N.Workspace), ctypes.sizeof(N.BlockOut),
             N.Counters.c.offset, N.Counters.error.offset, N.Workspace.ctr.offset, N.BlockOut.cap_edges.offset,
             ctypes.sizeof(N.P2P), N.P2P.flags_off.offset, N.P2P.done_ctr.offset, ctypes.sizeof(N.GradP2P),
-            N.GradP2P.step_dev.offset]
+            N.GradP2P.step_dev.offset, N.Workspace.ctr_mirror.offset, N.P2P.mc_base.offset, N.GradP2P.mc_base.offset]
     assert got == want
 
 
